@@ -1,0 +1,11 @@
+"""efficient_slowfast_b200 -- B200-native (sm_100a) batched clip forward path of weidafeng/Efficient-SlowFast.
+
+Public surface mirrors SlowFast/slowfast/models/__init__.py of the reference:
+    from efficient_slowfast_b200 import MODEL_REGISTRY, build_model, get_cfg
+"""
+from .build import MODEL_REGISTRY, build_model  # noqa: F401
+from .config import CfgNode, get_cfg, slowfast_4x16_r50_cfg, slowfast_dual_8x8_r50_cfg  # noqa: F401
+from . import nets_resnet  # noqa: F401  (registers SlowFast, SlowFastDualAttention)
+
+__all__ = ["MODEL_REGISTRY", "build_model", "get_cfg", "CfgNode", "slowfast_4x16_r50_cfg",
+           "slowfast_dual_8x8_r50_cfg"]

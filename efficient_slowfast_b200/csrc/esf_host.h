@@ -1,0 +1,43 @@
+// Host-side helpers shared by the .cu translation units of libesf_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/esf.h"
+
+namespace esf {
+
+int set_error(int code, const char* fmt, ...);  // stores a thread-local message, returns `code`
+void count_launch(int n = 1);
+
+#define ESF_CHECK_ARG(cond, ...)                                \
+  do {                                                          \
+    if (!(cond)) return ::esf::set_error(ESF_ERR_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define ESF_CUDA(call)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return ::esf::set_error(ESF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                              __LINE__);                                                                 \
+  } while (0)
+
+// checks the launch itself (configuration errors and sticky errors such as a device-side trap)
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(ESF_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  count_launch();
+  return ESF_OK;
+}
+
+inline bool view_ok(const esf_view* v) {
+  return v && v->ptr && v->B > 0 && v->T > 0 && v->H > 0 && v->W > 0 && v->C > 0 && v->sW >= v->C;
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace esf

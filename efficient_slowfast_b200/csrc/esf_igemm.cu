@@ -1,0 +1,570 @@
+// Dense Conv3d (+ folded BatchNorm, + residual, + ReLU) as a persistent, warp-specialised implicit GEMM on the
+// 5th-generation tensor cores:  D[m, n] = sum_{tap, c} X[pos(m) + tap, c] * Wp[n, tap, c]
+//
+//   M  = a box of (bw x bh x bt x bb) <= 128 output positions of the channels-last (B,T,H,W,C) activation,
+//   N  = n_tile output channels (16..256),  K = taps x input-channel chunks of kc in {16,32,64} elements.
+//
+//   warp 8      TMA producer: one 5-D box load per (tap, chunk) of the activation -- the filter tap is a coordinate
+//               offset, zero padding is TMA out-of-bounds fill, a strided conv reads one tensor map per stride phase
+//               -- plus a 2-D load of the packed weights; `stages`-deep mbarrier ring.
+//   warp 9      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=n_tile, K=16) into one of two TMEM
+//               accumulators; tcgen05.commit releases smem stages / publishes the accumulator.
+//   warps 0-7   epilogue: tcgen05.ld -> + bias (+ residual tile fetched by TMA) -> ReLU -> BF16/FP32 -> swizzled smem
+//               -> TMA store straight into the (possibly channel-sliced) destination, i.e. concat is free.
+//
+// Reference ops replaced: see include/esf.h (esf_conv_igemm_create).
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "esf_common.cuh"
+#include "esf_host.h"
+
+namespace esf {
+
+constexpr int kEpiThreads = 256;
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kThreads = 320;
+constexpr int kMaxStages = 8;
+constexpr int kMaxAMaps = 8;
+constexpr int kMaxTaps = 32;
+constexpr int kAStageBytes = 16384;   // 128 rows x 128 B
+constexpr int kOutStageBytes = 16384; // 128 rows x 128 B
+constexpr int kTmemCols = 512;
+constexpr int kSmemLimit = 232448;    // 227 KB
+
+struct __align__(64) IgemmParams {
+  CUtensorMap a_maps[kMaxAMaps];
+  CUtensorMap b_map;
+  CUtensorMap out_map;
+  CUtensorMap res_map;
+  int4 taps[kMaxTaps];  // x: a_map index, y/z/w: coordinate offsets along W/H/T in that map
+  int num_taps, kchunks, kc;
+  int n_tile, n_tiles;
+  int bw, bh, bt, bb;  // output box of one M tile
+  int tw, th, tt, tb;  // boxes per dimension
+  int rows;            // bw*bh*bt*bb
+  int stages;
+  uint32_t a_bytes, b_bytes, b_stride;  // TMA bytes per stage / smem stride of a B stage
+  uint32_t sbo, layout_type;            // UMMA descriptor fields for the A/B swizzle mode
+  uint32_t res_bytes;
+  const float* bias;
+  int act, has_res, out_f32;
+  int slab_cols;      // output columns per TMA store slab
+  uint32_t out_swz;   // swizzle mask of the staging rows (7 / 3 / 1)
+  int num_tiles;
+};
+
+struct TileCoord {
+  int n_idx, w0, h0, t0, b0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const IgemmParams& p, int tile) {
+  TileCoord c;
+  c.n_idx = tile % p.n_tiles;
+  int m = tile / p.n_tiles;
+  c.w0 = (m % p.tw) * p.bw;
+  m /= p.tw;
+  c.h0 = (m % p.th) * p.bh;
+  m /= p.th;
+  c.t0 = (m % p.tt) * p.bt;
+  c.b0 = (m / p.tt) * p.bb;
+  return c;
+}
+
+__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kEpiThreads) : "memory"); }
+
+// One epilogue thread: NC accumulator columns of its row for one output slab.
+template <int NC>
+__device__ __forceinline__ void epi_process(const IgemmParams& p, uint32_t taddr, const float* __restrict__ bias,
+                                            uint8_t* stage_buf, int r, int half, bool row_valid) {
+  float v[NC];
+  tmem_ld<NC>(taddr, v);
+#pragma unroll
+  for (int j = 0; j < NC; ++j) v[j] += __ldg(bias + j);
+  if (p.out_f32) {
+    const uint32_t base = r * (p.slab_cols * 4) + half * (NC * 4);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = apply_act(v[j], p.act);
+    if (row_valid) {
+#pragma unroll
+      for (int c = 0; c < NC / 4; ++c) {
+        float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        *reinterpret_cast<float4*>(stage_buf + swz(base + c * 16, p.out_swz)) = o;
+      }
+    }
+  } else {
+    const uint32_t base = r * (p.slab_cols * 2) + half * (NC * 2);
+    if (p.has_res) {
+#pragma unroll
+      for (int c = 0; c < NC / 8; ++c) {
+        const uint4 rr = *reinterpret_cast<const uint4*>(stage_buf + swz(base + c * 16, p.out_swz));
+        const uint32_t u[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16x2(u[e]);
+          v[8 * c + 2 * e] += f.x;
+          v[8 * c + 2 * e + 1] += f.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = apply_act(v[j], p.act);
+    if (row_valid) {
+#pragma unroll
+      for (int c = 0; c < NC / 8; ++c) {
+        uint4 o;
+        o.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]);
+        o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+        o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+        o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+        *reinterpret_cast<uint4*>(stage_buf + swz(base + c * 16, p.out_swz)) = o;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + p.stages * kAStageBytes;
+  uint8_t* smem_out = smem_b + p.stages * p.b_stride;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_out + 2 * kOutStageBytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* res_full = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);  // one arrival per epilogue warp
+      mbar_init(&res_full[a], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kProducerWarp && lane == 0) {
+    prefetch_tmap(&p.a_maps[0]);
+    prefetch_tmap(&p.b_map);
+    prefetch_tmap(&p.out_map);
+    if (p.has_res) prefetch_tmap(&p.res_map);
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_kb = p.num_taps * p.kchunks;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(p, tile);
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const int4 tp = p.taps[tap];
+          for (int ch = 0; ch < p.kchunks; ++ch) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+            mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+            tma_load_5d(smem_a + stage * kAStageBytes, &p.a_maps[tp.x], &full_bar[stage], ch * p.kc, tc.w0 + tp.y,
+                        tc.h0 + tp.z, tc.t0 + tp.w, tc.b0);
+            tma_load_2d(smem_b + stage * p.b_stride, &p.b_map, &full_bar[stage], (tap * p.kchunks + ch) * p.kc,
+                        tc.n_idx * p.n_tile);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.n_tile);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * p.n_tile;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * kAStageBytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * p.b_stride);
+          const int ksteps = p.kc >> 4;
+          for (int k = 0; k < ksteps; ++k) {
+            umma_bf16(d_tmem, make_kmajor_desc(a_addr + k * 32, p.sbo, p.layout_type),
+                      make_kmajor_desc(b_addr + k * 32, p.sbo, p.layout_type), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 0..7
+    const int q = warp & 3;      // TMEM lane quarter this warp may access
+    const int half = warp >> 2;  // which half of the slab's columns
+    const int r = q * 32 + lane;
+    const bool row_valid = r < p.rows;
+    const bool leader = threadIdx.x == 0;
+    const int slabs = p.n_tile / p.slab_cols;
+    const int cpt = p.slab_cols >> 1;  // columns per thread per slab
+    int g = 0;                         // running slab counter (staging buffer = g & 1)
+    if (p.has_res && leader && blockIdx.x < p.num_tiles) {
+      const TileCoord tc = tile_coord(p, blockIdx.x);
+      mbar_arrive_expect_tx(&res_full[0], p.res_bytes);
+      tma_load_5d(smem_out, &p.res_map, &res_full[0], tc.n_idx * p.n_tile, tc.w0, tc.h0, tc.t0, tc.b0);
+    }
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+      const TileCoord tc = tile_coord(p, tile);
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase, 4);
+      tc_fence_after();
+      for (int s = 0; s < slabs; ++s, ++g) {
+        const int buf = g & 1;
+        uint8_t* stage_buf = smem_out + buf * kOutStageBytes;
+        if (p.has_res) mbar_wait(&res_full[buf], (g >> 1) & 1, 5);
+        const int col = s * p.slab_cols + half * cpt;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_tile + col;
+        const float* bias = p.bias + tc.n_idx * p.n_tile + col;
+        if (cpt == 32) epi_process<32>(p, taddr, bias, stage_buf, r, half, row_valid);
+        else if (cpt == 16) epi_process<16>(p, taddr, bias, stage_buf, r, half, row_valid);
+        else epi_process<8>(p, taddr, bias, stage_buf, r, half, row_valid);
+        if (s == slabs - 1) {  // accumulator fully drained: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        fence_proxy_async_smem();
+        epi_bar_sync(1);
+        if (leader) {
+          tma_store_5d(&p.out_map, stage_buf, tc.n_idx * p.n_tile + s * p.slab_cols, tc.w0, tc.h0, tc.t0, tc.b0);
+          tma_store_commit();
+          tma_store_wait_read<1>();  // the previous slab's store no longer reads the other staging buffer
+          if (p.has_res) {
+            int ntile = tile, ns = s + 1;
+            if (ns == slabs) {
+              ns = 0;
+              ntile = tile + gridDim.x;
+            }
+            if (ntile < p.num_tiles) {
+              const TileCoord nc = tile_coord(p, ntile);
+              mbar_arrive_expect_tx(&res_full[buf ^ 1], p.res_bytes);
+              tma_load_5d(smem_out + (buf ^ 1) * kOutStageBytes, &p.res_map, &res_full[buf ^ 1],
+                          nc.n_idx * p.n_tile + ns * p.slab_cols, nc.w0, nc.h0, nc.t0, nc.b0);
+            }
+          }
+        }
+        epi_bar_sync(2);
+      }
+    }
+    if (leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
+  if (row_bytes == 128) return CU_TENSOR_MAP_SWIZZLE_128B;
+  if (row_bytes == 64) return CU_TENSOR_MAP_SWIZZLE_64B;
+  return CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+// 5-D map over a channels-last view: dims (C, W, H, T, B).
+static int encode_act_map(CUtensorMap* m, CUtensorMapDataType dt, int esize, void* base, int64_t C, int64_t W,
+                          int64_t H, int64_t T, int64_t B, int64_t sW, int64_t sH, int64_t sT, int64_t sB, int boxC,
+                          int bw, int bh, int bt, int bb, CUtensorMapSwizzle swz_mode, const char* what) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)(sW * esize), (cuuint64_t)(sH * esize), (cuuint64_t)(sT * esize),
+                           (cuuint64_t)(sB * esize)};
+  cuuint32_t box[5] = {(cuuint32_t)boxC, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bt, (cuuint32_t)bb};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return set_error(ESF_ERR_ARG, "%s: base address %p not 16-byte aligned", what, base);
+  for (int i = 0; i < 4; ++i)
+    if (strides[i] % 16 != 0)
+      return set_error(ESF_ERR_ARG, "%s: stride %d = %llu bytes is not a multiple of 16", what, i,
+                       (unsigned long long)strides[i]);
+  CUresult r = enc(m, dt, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz_mode,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(ESF_ERR_CUDA,
+                     "cuTensorMapEncodeTiled(%s) failed with %d: dims (%lld,%lld,%lld,%lld,%lld) box (%d,%d,%d,%d,%d)",
+                     what, (int)r, (long long)C, (long long)W, (long long)H, (long long)T, (long long)B, boxC, bw, bh,
+                     bt, bb);
+  return ESF_OK;
+}
+
+}  // namespace esf
+
+struct esf_op {
+  esf::IgemmParams params;
+  int grid;
+  int smem_bytes;
+};
+
+using namespace esf;
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms > 0) return g_num_sms;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  g_num_sms = n;
+  return n;
+}
+
+extern "C" int esf_igemm_geometry(int32_t cin, int32_t cout, int32_t* kc, int32_t* kchunks, int32_t* n_tile,
+                                  int32_t* n_pad) {
+  ESF_CHECK_ARG(cin > 0 && cout > 0, "esf_igemm_geometry: cin/cout must be positive");
+  const int k = cin <= 16 ? 16 : (cin <= 32 ? 32 : 64);
+  int nt = 16;
+  while (nt < cout && nt < 256) nt *= 2;
+  if (kc) *kc = k;
+  if (kchunks) *kchunks = cdiv(cin, k);
+  if (n_tile) *n_tile = nt;
+  if (n_pad) *n_pad = cdiv(cout, nt) * nt;
+  return ESF_OK;
+}
+
+// pick the output box (bw,bh,bt,bb), product <= 128, maximising the fraction of useful MMA rows
+static void choose_box(int W, int H, int T, int B, int* obw, int* obh, int* obt, int* obb) {
+  double best = -1.0;
+  int best_sp = 0;
+  int rb[4] = {1, 1, 1, 1};
+  for (int bw = 1; bw <= std::min(W, 128); ++bw)
+    for (int bh = 1; bh <= std::min(H, 128 / bw); ++bh)
+      for (int bt = 1; bt <= std::min(T, 128 / (bw * bh)); ++bt) {
+        const int bb = std::min(B, 128 / (bw * bh * bt));
+        const double tiles = (double)cdiv(W, bw) * cdiv(H, bh) * cdiv(T, bt) * cdiv(B, bb);
+        const double eff = ((double)W * H * T * B) / (tiles * 128.0);
+        const int sp = bw * bh;
+        if (eff > best + 1e-9 || (eff > best - 1e-9 && sp > best_sp)) {
+          best = std::max(best, eff);
+          best_sp = sp;
+          rb[0] = bw, rb[1] = bh, rb[2] = bt, rb[3] = bb;
+        }
+      }
+  *obw = rb[0], *obh = rb[1], *obt = rb[2], *obb = rb[3];
+}
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
+  ESF_CHECK_ARG(d && out, "esf_conv_igemm_create: null argument");
+  ESF_CHECK_ARG(view_ok(&d->x) && view_ok(&d->y), "esf_conv_igemm_create: bad x/y view");
+  ESF_CHECK_ARG(d->groups == 1, "esf_conv_igemm_create: groups must be 1 (use esf_conv_direct)");
+  ESF_CHECK_ARG(d->w && d->bias, "esf_conv_igemm_create: null weights/bias");
+  ESF_CHECK_ARG(d->kT >= 1 && d->kH >= 1 && d->kW >= 1 && d->sT >= 1 && d->sH >= 1 && d->sW >= 1 && d->dT >= 1 &&
+                    d->dH >= 1 && d->dW >= 1 && d->pT >= 0 && d->pH >= 0 && d->pW >= 0,
+                "esf_conv_igemm_create: bad kernel/stride/pad/dilation");
+  const esf_view& x = d->x;
+  const esf_view& y = d->y;
+  const int To = (x.T + 2 * d->pT - d->dT * (d->kT - 1) - 1) / d->sT + 1;
+  const int Ho = (x.H + 2 * d->pH - d->dH * (d->kH - 1) - 1) / d->sH + 1;
+  const int Wo = (x.W + 2 * d->pW - d->dW * (d->kW - 1) - 1) / d->sW + 1;
+  ESF_CHECK_ARG(y.B == x.B && y.T == To && y.H == Ho && y.W == Wo,
+                "esf_conv_igemm_create: output view (%d,%d,%d,%d) does not match conv output (%d,%d,%d,%d)", y.B, y.T,
+                y.H, y.W, x.B, To, Ho, Wo);
+  const int num_taps = d->kT * d->kH * d->kW;
+  ESF_CHECK_ARG(num_taps <= kMaxTaps, "esf_conv_igemm_create: %d taps > %d", num_taps, kMaxTaps);
+  ESF_CHECK_ARG(d->out_dtype == ESF_BF16 || d->out_dtype == ESF_F32, "esf_conv_igemm_create: bad out_dtype");
+  ESF_CHECK_ARG(!(d->out_dtype == ESF_F32 && d->res.ptr), "esf_conv_igemm_create: residual needs a BF16 output");
+  if (d->res.ptr)
+    ESF_CHECK_ARG(d->res.B == y.B && d->res.T == y.T && d->res.H == y.H && d->res.W == y.W && d->res.C == y.C,
+                  "esf_conv_igemm_create: residual view must match the output view");
+
+  esf_op* op = new (std::nothrow) esf_op();
+  if (!op) return set_error(ESF_ERR_ARG, "out of host memory");
+  IgemmParams& p = op->params;
+  memset(&p, 0, sizeof(p));
+  int kc, kchunks, n_tile, n_pad;
+  esf_igemm_geometry(x.C, y.C, &kc, &kchunks, &n_tile, &n_pad);
+  p.kc = kc;
+  p.kchunks = kchunks;
+  p.n_tile = n_tile;
+  p.n_tiles = n_pad / n_tile;
+  p.num_taps = num_taps;
+  choose_box(Wo, Ho, To, y.B, &p.bw, &p.bh, &p.bt, &p.bb);
+  p.tw = cdiv(Wo, p.bw);
+  p.th = cdiv(Ho, p.bh);
+  p.tt = cdiv(To, p.bt);
+  p.tb = cdiv(y.B, p.bb);
+  p.rows = p.bw * p.bh * p.bt * p.bb;
+  const long long ntiles = (long long)p.tw * p.th * p.tt * p.tb * p.n_tiles;
+  if (ntiles > 0x7fffffffLL) {
+    delete op;
+    return set_error(ESF_ERR_ARG, "too many tiles");
+  }
+  p.num_tiles = (int)ntiles;
+  const int row_bytes = kc * 2;
+  p.a_bytes = p.rows * row_bytes;
+  p.b_bytes = n_tile * row_bytes;
+  p.b_stride = (p.b_bytes + 1023) & ~1023u;
+  p.sbo = 8 * row_bytes;
+  p.layout_type = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  p.bias = d->bias;
+  p.act = d->act;
+  p.has_res = d->res.ptr != nullptr;
+  p.out_f32 = d->out_dtype == ESF_F32;
+  const int oes = p.out_f32 ? 4 : 2;
+  p.slab_cols = std::min(n_tile, 128 / oes);
+  const int out_row_bytes = p.slab_cols * oes;
+  p.out_swz = out_row_bytes == 128 ? 7 : (out_row_bytes == 64 ? 3 : 1);
+  p.res_bytes = p.rows * p.slab_cols * 2;
+
+  // stages: as deep as shared memory allows
+  const int fixed = 1024 + 2 * kOutStageBytes + 512;
+  int stages = (kSmemLimit - fixed) / (kAStageBytes + (int)p.b_stride);
+  stages = std::max(2, std::min(stages, kMaxStages));
+  p.stages = stages;
+  op->smem_bytes = fixed + stages * (kAStageBytes + (int)p.b_stride);
+
+  // ---- activation maps: one per distinct stride phase; taps carry the per-map coordinate offsets
+  struct Phase {
+    int pt, ph, pw;
+  };
+  std::vector<Phase> phases;
+  int rc = ESF_OK;
+  int tap_i = 0;
+  for (int it = 0; it < d->kT && rc == ESF_OK; ++it)
+    for (int ih = 0; ih < d->kH && rc == ESF_OK; ++ih)
+      for (int iw = 0; iw < d->kW && rc == ESF_OK; ++iw, ++tap_i) {
+        const int ot = it * d->dT - d->pT, oh = ih * d->dH - d->pH, ow = iw * d->dW - d->pW;
+        const int qt = floordiv(ot, d->sT), qh = floordiv(oh, d->sH), qw = floordiv(ow, d->sW);
+        const Phase ph = {ot - qt * d->sT, oh - qh * d->sH, ow - qw * d->sW};
+        int idx = -1;
+        for (size_t i = 0; i < phases.size(); ++i)
+          if (phases[i].pt == ph.pt && phases[i].ph == ph.ph && phases[i].pw == ph.pw) idx = (int)i;
+        if (idx < 0) {
+          if ((int)phases.size() == kMaxAMaps) {
+            rc = set_error(ESF_ERR_UNSUPPORTED, "conv needs more than %d stride phases", kMaxAMaps);
+            break;
+          }
+          idx = (int)phases.size();
+          phases.push_back(ph);
+          // phase view: element (c, w', h', t', b) = x[b, sT*t'+pt, sH*h'+ph, sW*w'+pw, c]
+          const int Tp = ph.pt < x.T ? cdiv(x.T - ph.pt, d->sT) : 0;
+          const int Hp = ph.ph < x.H ? cdiv(x.H - ph.ph, d->sH) : 0;
+          const int Wp = ph.pw < x.W ? cdiv(x.W - ph.pw, d->sW) : 0;
+          if (Tp <= 0 || Hp <= 0 || Wp <= 0) {
+            rc = set_error(ESF_ERR_UNSUPPORTED, "empty stride phase (input smaller than the stride)");
+            break;
+          }
+          char* base = static_cast<char*>(x.ptr) + 2 * (ph.pt * x.sT + ph.ph * x.sH + ph.pw * x.sW);
+          rc = encode_act_map(&p.a_maps[idx], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, x.C, Wp, Hp, Tp, x.B,
+                              x.sW * d->sW, x.sH * d->sH, x.sT * d->sT, x.sB, kc, p.bw, p.bh, p.bt, p.bb,
+                              swizzle_for_row_bytes(row_bytes), "activation");
+        }
+        p.taps[tap_i] = make_int4(idx, qw, qh, qt);
+      }
+  // unused map slots alias map 0 so that the kernel parameter block is fully initialised
+  if (rc == ESF_OK)
+    for (int i = (int)phases.size(); i < kMaxAMaps; ++i) p.a_maps[i] = p.a_maps[0];
+
+  // ---- packed weights: 2-D (K, n_pad), box (kc, n_tile)
+  if (rc == ESF_OK) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) rc = set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    else {
+      const cuuint64_t K = (cuuint64_t)num_taps * kchunks * kc;
+      cuuint64_t dims[2] = {K, (cuuint64_t)n_pad};
+      cuuint64_t strides[1] = {K * 2};
+      cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)n_tile};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = enc(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(row_bytes),
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) rc = set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+    }
+  }
+  // ---- output (+ residual) maps: box (slab_cols, bw, bh, bt, bb)
+  if (rc == ESF_OK)
+    rc = encode_act_map(&p.out_map, p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, oes,
+                        y.ptr, y.C, y.W, y.H, y.T, y.B, y.sW, y.sH, y.sT, y.sB, p.slab_cols, p.bw, p.bh, p.bt, p.bb,
+                        swizzle_for_row_bytes(out_row_bytes), "output");
+  if (rc == ESF_OK) {
+    if (p.has_res)
+      rc = encode_act_map(&p.res_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->res.ptr, d->res.C, d->res.W, d->res.H,
+                          d->res.T, d->res.B, d->res.sW, d->res.sH, d->res.sT, d->res.sB, p.slab_cols, p.bw, p.bh, p.bt,
+                          p.bb, swizzle_for_row_bytes(out_row_bytes), "residual");
+    else
+      p.res_map = p.out_map;
+  }
+  if (rc == ESF_OK) {
+    const int sms = num_sms();
+    if (sms <= 0) rc = set_error(ESF_ERR_CUDA, "no CUDA device");
+    else op->grid = std::min(p.num_tiles, sms);
+  }
+  if (rc == ESF_OK) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+      if (e != cudaSuccess) rc = set_error(ESF_ERR_CUDA, "cudaFuncSetAttribute(igemm) failed: %s", cudaGetErrorString(e));
+      else attr_set = true;
+    }
+  }
+  if (rc != ESF_OK) {
+    delete op;
+    return rc;
+  }
+  *out = op;
+  return ESF_OK;
+}
+
+extern "C" int esf_op_launch(esf_op* op, void* stream) {
+  ESF_CHECK_ARG(op, "esf_op_launch: null op");
+  igemm_kernel<<<op->grid, kThreads, op->smem_bytes, static_cast<cudaStream_t>(stream)>>>(op->params);
+  return check_launch("igemm_kernel");
+}
+
+extern "C" void esf_op_destroy(esf_op* op) { delete op; }

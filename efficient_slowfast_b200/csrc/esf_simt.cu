@@ -1,0 +1,507 @@
+// Memory-bound CUDA-core kernels of the clip forward path: stem convolution on the raw FP32 clip, thin
+// (grouped / depthwise / tiny-channel) convolutions, pooling, the ECA channel-attention fuse, and the head.
+// All activations are channels-last BF16 views (include/esf.h); accumulation is FP32.
+#include <math_constants.h>
+
+#include <algorithm>
+
+#include "esf_common.cuh"
+#include "esf_host.h"
+
+namespace esf {
+
+struct View {
+  char* ptr;
+  int B, T, H, W, C;
+  long long sB, sT, sH, sW;
+};
+static View to_view(const esf_view* v) {
+  View r;
+  r.ptr = static_cast<char*>(v->ptr);
+  r.B = v->B, r.T = v->T, r.H = v->H, r.W = v->W, r.C = v->C;
+  r.sB = v->sB, r.sT = v->sT, r.sH = v->sH, r.sW = v->sW;
+  return r;
+}
+__device__ __forceinline__ long long voff(const View& v, int b, int t, int h, int w) {
+  return b * v.sB + t * v.sT + h * v.sH + w * v.sW;
+}
+__device__ __forceinline__ float ldbf(const char* base, long long idx) {
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+}
+
+// ------------------------------------------------------------------------------------------- stem conv
+// One thread = one output position x CO_T consecutive output channels; the clip is FP32 NCDHW.
+struct StemParams {
+  const float* x;
+  int B, Cin, T, H, W;
+  const float* w;  // [kT][kH][kW][Cin][Cout]
+  const float* bias;
+  int Cout, kT, kH, kW, sT, sH, sW, pT, pH, pW, act;
+  int To, Ho, Wo;
+  View y;
+};
+
+template <int CO_T>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
+  const int cgroups = p.Cout / CO_T;
+  const long long total = (long long)p.B * p.To * p.Ho * p.Wo * cgroups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = idx % cgroups;
+    long long pos = idx / cgroups;
+    const int wo = pos % p.Wo;
+    pos /= p.Wo;
+    const int ho = pos % p.Ho;
+    pos /= p.Ho;
+    const int to = pos % p.To;
+    const int b = pos / p.To;
+    float acc[CO_T];
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) acc[j] = __ldg(p.bias + cg * CO_T + j);
+    for (int kt = 0; kt < p.kT; ++kt) {
+      const int ti = to * p.sT + kt - p.pT;
+      if (ti < 0 || ti >= p.T) continue;
+      for (int kh = 0; kh < p.kH; ++kh) {
+        const int hi = ho * p.sH + kh - p.pH;
+        if (hi < 0 || hi >= p.H) continue;
+        for (int kw = 0; kw < p.kW; ++kw) {
+          const int wi = wo * p.sW + kw - p.pW;
+          if (wi < 0 || wi >= p.W) continue;
+          for (int ci = 0; ci < p.Cin; ++ci) {
+            const float xv = __ldg(p.x + ((((long long)b * p.Cin + ci) * p.T + ti) * p.H + hi) * p.W + wi);
+            const float* wp = p.w + ((((long long)kt * p.kH + kh) * p.kW + kw) * p.Cin + ci) * p.Cout + cg * CO_T;
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j) acc[j] = fmaf(xv, __ldg(wp + j), acc[j]);
+          }
+        }
+      }
+    }
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + voff(p.y, b, to, ho, wo) + cg * CO_T;
+    if constexpr (CO_T == 8) {
+      uint4 o;
+      o.x = pack_bf16x2(apply_act(acc[0], p.act), apply_act(acc[1], p.act));
+      o.y = pack_bf16x2(apply_act(acc[2], p.act), apply_act(acc[3], p.act));
+      o.z = pack_bf16x2(apply_act(acc[4], p.act), apply_act(acc[5], p.act));
+      o.w = pack_bf16x2(apply_act(acc[6], p.act), apply_act(acc[7], p.act));
+      *reinterpret_cast<uint4*>(yp) = o;
+    } else {
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j) yp[j] = __float2bfloat16(apply_act(acc[j], p.act));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- direct conv
+struct DirectParams {
+  View x, y, res;
+  const float* w;  // [Cout][kT][kH][kW][Cin/groups]
+  const float* bias;
+  int kT, kH, kW, sT, sH, sW, pT, pH, pW, dT, dH, dW, groups, act, has_res, out_f32;
+};
+
+__global__ void __launch_bounds__(256) conv_direct_kernel(const DirectParams p) {
+  const int Cout = p.y.C;
+  const int cin_g = p.x.C / p.groups;
+  const int cout_g = Cout / p.groups;
+  const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W * Cout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int co = idx % Cout;
+    long long pos = idx / Cout;
+    const int wo = pos % p.y.W;
+    pos /= p.y.W;
+    const int ho = pos % p.y.H;
+    pos /= p.y.H;
+    const int to = pos % p.y.T;
+    const int b = pos / p.y.T;
+    const int g = co / cout_g;
+    float acc = __ldg(p.bias + co);
+    const float* wbase = p.w + (long long)co * p.kT * p.kH * p.kW * cin_g;
+    for (int kt = 0; kt < p.kT; ++kt) {
+      const int ti = to * p.sT + kt * p.dT - p.pT;
+      if (ti < 0 || ti >= p.x.T) continue;
+      for (int kh = 0; kh < p.kH; ++kh) {
+        const int hi = ho * p.sH + kh * p.dH - p.pH;
+        if (hi < 0 || hi >= p.x.H) continue;
+        for (int kw = 0; kw < p.kW; ++kw) {
+          const int wi = wo * p.sW + kw * p.dW - p.pW;
+          if (wi < 0 || wi >= p.x.W) continue;
+          const long long xo = voff(p.x, b, ti, hi, wi) + g * cin_g;
+          const float* wp = wbase + ((kt * p.kH + kh) * p.kW + kw) * cin_g;
+          for (int ci = 0; ci < cin_g; ++ci) acc = fmaf(ldbf(p.x.ptr, xo + ci), __ldg(wp + ci), acc);
+        }
+      }
+    }
+    const long long yo = voff(p.y, b, to, ho, wo) + co;
+    if (p.has_res) acc += ldbf(p.res.ptr, voff(p.res, b, to, ho, wo) + co);
+    acc = apply_act(acc, p.act);
+    if (p.out_f32) reinterpret_cast<float*>(p.y.ptr)[yo] = acc;
+    else reinterpret_cast<__nv_bfloat16*>(p.y.ptr)[yo] = __float2bfloat16(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- pooling
+struct PoolParams {
+  View x, y;
+  int kT, kH, kW, sT, sH, sW, pT, pH, pW, is_avg;
+};
+// VEC = 8: one thread handles 8 channels (16 B); VEC = 1: scalar tail path for C % 8 != 0.
+template <int VEC>
+__global__ void __launch_bounds__(256) pool3d_kernel(const PoolParams p) {
+  const int cv = p.y.C / VEC;
+  const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W * cv;
+  const float inv = 1.f / (p.kT * p.kH * p.kW);  // AvgPool3d default count_include_pad=True
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (idx % cv) * VEC;
+    long long pos = idx / cv;
+    const int wo = pos % p.y.W;
+    pos /= p.y.W;
+    const int ho = pos % p.y.H;
+    pos /= p.y.H;
+    const int to = pos % p.y.T;
+    const int b = pos / p.y.T;
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = p.is_avg ? 0.f : -CUDART_INF_F;
+    for (int kt = 0; kt < p.kT; ++kt) {
+      const int ti = to * p.sT + kt - p.pT;
+      if (ti < 0 || ti >= p.x.T) continue;
+      for (int kh = 0; kh < p.kH; ++kh) {
+        const int hi = ho * p.sH + kh - p.pH;
+        if (hi < 0 || hi >= p.x.H) continue;
+        for (int kw = 0; kw < p.kW; ++kw) {
+          const int wi = wo * p.sW + kw - p.pW;
+          if (wi < 0 || wi >= p.x.W) continue;
+          const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + voff(p.x, b, ti, hi, wi) + c;
+          if constexpr (VEC == 8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(xp);
+            const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16x2(uu[e]);
+              if (p.is_avg) {
+                acc[2 * e] += f.x;
+                acc[2 * e + 1] += f.y;
+              } else {
+                acc[2 * e] = fmaxf(acc[2 * e], f.x);
+                acc[2 * e + 1] = fmaxf(acc[2 * e + 1], f.y);
+              }
+            }
+          } else {
+            const float f = __bfloat162float(xp[0]);
+            acc[0] = p.is_avg ? acc[0] + f : fmaxf(acc[0], f);
+          }
+        }
+      }
+    }
+    if (p.is_avg) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[j] *= inv;
+    }
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + voff(p.y, b, to, ho, wo) + c;
+    if constexpr (VEC == 8) {
+      uint4 o;
+      o.x = pack_bf16x2(acc[0], acc[1]);
+      o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]);
+      o.w = pack_bf16x2(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(yp) = o;
+    } else {
+      yp[0] = __float2bfloat16(acc[0]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- ECA fuse
+constexpr int kEcaBlocksPerClip = 64;
+constexpr int kEcaThreads = 256;
+
+struct EcaParams {
+  View x;  // fast pathway (B, T, H, W, C)
+  View y;  // slow concat slice (B, T/alpha, H, W, C)
+  int alpha;
+  const float* eca_w;
+  int eca_k;
+  const float* bn_scale;
+  const float* bn_shift;
+  float* partial;  // [B][kEcaBlocksPerClip][C]
+};
+
+__device__ __forceinline__ float eca_tmax(const EcaParams& p, int b, long long pos, int c) {
+  // pos indexes (t', h, w) of the temporally max-pooled tensor
+  const int w = pos % p.x.W;
+  const long long r = pos / p.x.W;
+  const int h = r % p.x.H;
+  const int tp = r / p.x.H;
+  float m = -CUDART_INF_F;
+  for (int a = 0; a < p.alpha; ++a) m = fmaxf(m, ldbf(p.x.ptr, voff(p.x, b, tp * p.alpha + a, h, w) + c));
+  return m;
+}
+
+// pass 1: deterministic per-block partial sums of max_t(x) over a position chunk, per channel
+__global__ void __launch_bounds__(kEcaThreads) eca_partial_kernel(const EcaParams p) {
+  extern __shared__ float red[];  // [lanes][C]
+  const int C = p.x.C;
+  const int b = blockIdx.y;
+  const long long npos = (long long)(p.x.T / p.alpha) * p.x.H * p.x.W;
+  const long long chunk = (npos + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * chunk, p1 = min(npos, p0 + chunk);
+  for (int c0 = 0; c0 < C; c0 += kEcaThreads) {  // C <= 256 in every model: a single pass
+    const int cw = min(C - c0, kEcaThreads);
+    const int lanes = kEcaThreads / cw;
+    const int c = c0 + threadIdx.x % cw;
+    const int l = threadIdx.x / cw;
+    float s = 0.f;
+    if (l < lanes)
+      for (long long pos = p0 + l; pos < p1; pos += lanes) s += eca_tmax(p, b, pos, c);
+    if (l < lanes) red[l * cw + (c - c0)] = s;
+    __syncthreads();
+    if (threadIdx.x < cw) {
+      float t = 0.f;
+      for (int i = 0; i < lanes; ++i) t += red[i * cw + threadIdx.x];
+      p.partial[((long long)b * gridDim.x + blockIdx.x) * C + c0 + threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// pass 2: mean -> conv1d over the channel axis (zero padded) -> sigmoid -> x * s -> BN affine -> ReLU -> store
+__global__ void __launch_bounds__(kEcaThreads) eca_apply_kernel(const EcaParams p, int nblk) {
+  extern __shared__ float sm[];  // mean[C], mul[C]
+  const int C = p.x.C;
+  float* mean = sm;
+  float* mul = sm + C;
+  const int b = blockIdx.y;
+  const long long npos = (long long)(p.x.T / p.alpha) * p.x.H * p.x.W;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int i = 0; i < nblk; ++i) t += p.partial[((long long)b * nblk + i) * C + c];
+    mean[c] = t / (float)npos;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    const int half = (p.eca_k - 1) / 2;
+    for (int j = 0; j < p.eca_k; ++j) {
+      const int cc = c + j - half;
+      if (cc >= 0 && cc < C) a = fmaf(__ldg(p.eca_w + j), mean[cc], a);
+    }
+    const float sgm = 1.f / (1.f + __expf(-a));
+    mul[c] = sgm * __ldg(p.bn_scale + c);
+  }
+  __syncthreads();
+  const long long chunk = (npos + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * chunk, p1 = min(npos, p0 + chunk);
+  const long long items = (p1 - p0) * C;
+  for (long long i = threadIdx.x; i < items; i += blockDim.x) {
+    const int c = i % C;
+    const long long pos = p0 + i / C;
+    const float v = fmaxf(fmaf(eca_tmax(p, b, pos, c), mul[c], __ldg(p.bn_shift + c)), 0.f);
+    const int w = pos % p.x.W;
+    const long long r = pos / p.x.W;
+    const int h = r % p.x.H;
+    const int tp = r / p.x.H;
+    reinterpret_cast<__nv_bfloat16*>(p.y.ptr)[voff(p.y, b, tp, h, w) + c] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- head
+// feat[b][c] = mean over (T,H,W) of x[b,:,:,:,c]; one block per (clip, 64-channel group)
+__global__ void __launch_bounds__(256) head_pool_kernel(const View x, float* feat, int feat_stride, int feat_off) {
+  __shared__ float red[4][64];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int l = threadIdx.x >> 6;
+  const long long npos = (long long)x.T * x.H * x.W;
+  float s = 0.f;
+  if (c < x.C)
+    for (long long pos = l; pos < npos; pos += 4) {
+      const int w = pos % x.W;
+      const long long r = pos / x.W;
+      const int h = r % x.H;
+      const int t = r / x.H;
+      s += ldbf(x.ptr, voff(x, b, t, h, w) + c);
+    }
+  red[l][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (threadIdx.x < 64 && c < x.C)
+    feat[(long long)b * feat_stride + feat_off + c] =
+        (red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]) / (float)npos;
+}
+
+// out[b][k] = act(sum_c feat[b][c] * w[k][c] + bias[k]); one block per clip, one warp per class (strided)
+__global__ void __launch_bounds__(256) head_fc_kernel(const float* feat, int Cin, const float* w, const float* bias,
+                                                      int K, int act, float* out) {
+  extern __shared__ float sm[];  // feat[Cin], logits[K]
+  float* f = sm;
+  float* logit = sm + Cin;
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < Cin; c += blockDim.x) f[c] = feat[(long long)b * Cin + c];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int k = warp; k < K; k += nw) {
+    float s = 0.f;
+    for (int c = lane; c < Cin; c += 32) s = fmaf(f[c], __ldg(w + (long long)k * Cin + c), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) logit[k] = s + __ldg(bias + k);
+  }
+  __syncthreads();
+  if (act == 1) {  // softmax over classes
+    float m = -CUDART_INF_F;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) m = fmaxf(m, logit[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+    for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+    __syncthreads();
+    float s = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const float e = expf(logit[k] - m);
+      logit[k] = e;
+      s += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    s = 0.f;
+    for (int i = 0; i < nw; ++i) s += red[i];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) out[(long long)b * K + k] = logit[k] / s;
+  } else {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      float v = logit[k];
+      if (act == 2) v = fmaxf(v, 0.f);
+      else if (act == 3) v = 1.f / (1.f + expf(-v));
+      out[(long long)b * K + k] = v;
+    }
+  }
+}
+
+static int grid_for(long long total, int threads) {
+  long long g = (total + threads - 1) / threads;
+  const long long cap = 148LL * 32;
+  return (int)std::max(1LL, std::min(g, cap));
+}
+
+}  // namespace esf
+
+using namespace esf;
+
+extern "C" int esf_stem_conv(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, const float* w,
+                             const float* bias, int32_t Cout, int32_t kT, int32_t kH, int32_t kW, int32_t sT,
+                             int32_t sH, int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t act,
+                             const esf_view* y, void* stream) {
+  ESF_CHECK_ARG(x && w && bias && view_ok(y), "esf_stem_conv: null/bad argument");
+  StemParams p;
+  p.x = x, p.B = B, p.Cin = Cin, p.T = T, p.H = H, p.W = W, p.w = w, p.bias = bias, p.Cout = Cout;
+  p.kT = kT, p.kH = kH, p.kW = kW, p.sT = sT, p.sH = sH, p.sW = sW, p.pT = pT, p.pH = pH, p.pW = pW, p.act = act;
+  p.To = (T + 2 * pT - kT) / sT + 1;
+  p.Ho = (H + 2 * pH - kH) / sH + 1;
+  p.Wo = (W + 2 * pW - kW) / sW + 1;
+  p.y = to_view(y);
+  ESF_CHECK_ARG(y->B == B && y->T == p.To && y->H == p.Ho && y->W == p.Wo && y->C == Cout,
+                "esf_stem_conv: output view (%d,%d,%d,%d,%d) != expected (%d,%d,%d,%d,%d)", y->B, y->T, y->H, y->W,
+                y->C, B, p.To, p.Ho, p.Wo, Cout);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long pos = (long long)B * p.To * p.Ho * p.Wo;
+  const bool vec8 = Cout % 8 == 0 && (reinterpret_cast<uintptr_t>(y->ptr) % 16 == 0) && y->sW % 8 == 0 &&
+                    y->sH % 8 == 0 && y->sT % 8 == 0 && y->sB % 8 == 0;
+  if (vec8) stem_conv_kernel<8><<<grid_for(pos * (Cout / 8), 256), 256, 0, s>>>(p);
+  else stem_conv_kernel<1><<<grid_for(pos * Cout, 256), 256, 0, s>>>(p);
+  return check_launch("stem_conv_kernel");
+}
+
+extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {
+  ESF_CHECK_ARG(d && view_ok(&d->x) && view_ok(&d->y) && d->w && d->bias, "esf_conv_direct: null/bad argument");
+  ESF_CHECK_ARG(d->groups >= 1 && d->x.C % d->groups == 0 && d->y.C % d->groups == 0,
+                "esf_conv_direct: channels not divisible by groups");
+  const int To = (d->x.T + 2 * d->pT - d->dT * (d->kT - 1) - 1) / d->sT + 1;
+  const int Ho = (d->x.H + 2 * d->pH - d->dH * (d->kH - 1) - 1) / d->sH + 1;
+  const int Wo = (d->x.W + 2 * d->pW - d->dW * (d->kW - 1) - 1) / d->sW + 1;
+  ESF_CHECK_ARG(d->y.B == d->x.B && d->y.T == To && d->y.H == Ho && d->y.W == Wo,
+                "esf_conv_direct: output view does not match the conv output shape");
+  DirectParams p;
+  p.x = to_view(&d->x), p.y = to_view(&d->y);
+  p.has_res = d->res.ptr != nullptr;
+  p.res = p.has_res ? to_view(&d->res) : p.y;
+  p.w = static_cast<const float*>(d->w), p.bias = d->bias;
+  p.kT = d->kT, p.kH = d->kH, p.kW = d->kW, p.sT = d->sT, p.sH = d->sH, p.sW = d->sW;
+  p.pT = d->pT, p.pH = d->pH, p.pW = d->pW, p.dT = d->dT, p.dH = d->dH, p.dW = d->dW;
+  p.groups = d->groups, p.act = d->act, p.out_f32 = d->out_dtype == ESF_F32;
+  const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W * p.y.C;
+  conv_direct_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("conv_direct_kernel");
+}
+
+extern "C" int esf_pool3d(const esf_view* x, const esf_view* y, int32_t kT, int32_t kH, int32_t kW, int32_t sT,
+                          int32_t sH, int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t is_avg, void* stream) {
+  ESF_CHECK_ARG(view_ok(x) && view_ok(y) && x->C == y->C && x->B == y->B, "esf_pool3d: bad views");
+  const int To = (x->T + 2 * pT - kT) / sT + 1, Ho = (x->H + 2 * pH - kH) / sH + 1, Wo = (x->W + 2 * pW - kW) / sW + 1;
+  ESF_CHECK_ARG(y->T == To && y->H == Ho && y->W == Wo, "esf_pool3d: output view does not match the pooled shape");
+  PoolParams p;
+  p.x = to_view(x), p.y = to_view(y);
+  p.kT = kT, p.kH = kH, p.kW = kW, p.sT = sT, p.sH = sH, p.sW = sW, p.pT = pT, p.pH = pH, p.pW = pW, p.is_avg = is_avg;
+  auto al8 = [](const esf_view* v) {
+    return reinterpret_cast<uintptr_t>(v->ptr) % 16 == 0 && v->sW % 8 == 0 && v->sH % 8 == 0 && v->sT % 8 == 0 &&
+           v->sB % 8 == 0;
+  };
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long pos = (long long)y->B * To * Ho * Wo;
+  if (x->C % 8 == 0 && al8(x) && al8(y)) pool3d_kernel<8><<<grid_for(pos * (x->C / 8), 256), 256, 0, s>>>(p);
+  else pool3d_kernel<1><<<grid_for(pos * x->C, 256), 256, 0, s>>>(p);
+  return check_launch("pool3d_kernel");
+}
+
+extern "C" int64_t esf_eca_scratch_floats(int32_t B, int32_t C) { return (int64_t)B * kEcaBlocksPerClip * C; }
+
+extern "C" int esf_eca_fuse(const esf_view* x_fast, int32_t alpha, const float* eca_w, int32_t eca_k,
+                            const float* bn_scale, const float* bn_shift, float* partial,
+                            const esf_view* y_slow_slice, void* stream) {
+  ESF_CHECK_ARG(view_ok(x_fast) && view_ok(y_slow_slice) && eca_w && bn_scale && bn_shift && partial,
+                "esf_eca_fuse: null/bad argument");
+  ESF_CHECK_ARG(alpha >= 1 && x_fast->T % alpha == 0, "esf_eca_fuse: T=%d not divisible by alpha=%d", x_fast->T, alpha);
+  ESF_CHECK_ARG(y_slow_slice->B == x_fast->B && y_slow_slice->T == x_fast->T / alpha && y_slow_slice->H == x_fast->H &&
+                    y_slow_slice->W == x_fast->W && y_slow_slice->C == x_fast->C,
+                "esf_eca_fuse: output slice shape mismatch");
+  ESF_CHECK_ARG(eca_k % 2 == 1, "esf_eca_fuse: even ECA kernel");
+  EcaParams p;
+  p.x = to_view(x_fast), p.y = to_view(y_slow_slice);
+  p.alpha = alpha, p.eca_w = eca_w, p.eca_k = eca_k, p.bn_scale = bn_scale, p.bn_shift = bn_shift, p.partial = partial;
+  const long long npos = (long long)(x_fast->T / alpha) * x_fast->H * x_fast->W;
+  const int nblk = (int)std::max(1LL, std::min<long long>(kEcaBlocksPerClip, npos / 32));
+  dim3 grid(nblk, x_fast->B);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int cw = std::min(x_fast->C, kEcaThreads);
+  eca_partial_kernel<<<grid, kEcaThreads, (kEcaThreads / cw) * cw * sizeof(float), s>>>(p);
+  int rc = check_launch("eca_partial_kernel");
+  if (rc != ESF_OK) return rc;
+  eca_apply_kernel<<<grid, kEcaThreads, 2 * x_fast->C * sizeof(float), s>>>(p, nblk);
+  return check_launch("eca_apply_kernel");
+}
+
+extern "C" int esf_head_pool(const esf_view* x0, const esf_view* x1, float* feat, void* stream) {
+  ESF_CHECK_ARG(view_ok(x0) && feat, "esf_head_pool: null/bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int c1 = (x1 && x1->ptr) ? x1->C : 0;
+  const int stride = x0->C + c1;
+  head_pool_kernel<<<dim3(cdiv(x0->C, 64), x0->B), 256, 0, s>>>(to_view(x0), feat, stride, 0);
+  int rc = check_launch("head_pool_kernel");
+  if (rc != ESF_OK || c1 == 0) return rc;
+  ESF_CHECK_ARG(view_ok(x1) && x1->B == x0->B, "esf_head_pool: bad second pathway view");
+  head_pool_kernel<<<dim3(cdiv(x1->C, 64), x1->B), 256, 0, s>>>(to_view(x1), feat, stride, x0->C);
+  return check_launch("head_pool_kernel");
+}
+
+extern "C" int esf_head_fc(const float* feat, int32_t B, int32_t Cin, const float* w, const float* bias,
+                           int32_t num_classes, int32_t act, float* out, void* stream) {
+  ESF_CHECK_ARG(feat && w && bias && out && B > 0 && Cin > 0 && num_classes > 0, "esf_head_fc: null/bad argument");
+  const size_t smem = (size_t)(Cin + num_classes) * sizeof(float);
+  ESF_CHECK_ARG(smem <= 48 * 1024, "esf_head_fc: Cin + num_classes too large for one block");
+  head_fc_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(feat, Cin, w, bias, num_classes, act, out);
+  return check_launch("head_fc_kernel");
+}

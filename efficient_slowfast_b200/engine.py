@@ -1,0 +1,239 @@
+"""Launch-plan builder: turns a model's parameters into folded/packed device weights and an ordered list of
+libesf_b200 kernel launches over pre-allocated channels-last BF16 activation buffers.
+
+Design (B200-first, not a module-by-module translation of the reference):
+  * activations are (B,T,H,W,C) BF16; every torch.cat of the reference is a channel slice of one wider buffer that
+    the producers write into directly (concat is free), every eval BatchNorm3d is folded into the preceding conv,
+    ReLU / residual adds live in the conv epilogue;
+  * a plan is built once per input shape, captured into a CUDA graph and replayed;
+  * there is no PyTorch compute on the path -- torch only owns the memory and the stream.
+"""
+import ctypes
+
+import torch
+
+from . import runtime as rt
+
+BN_EPS_DEFAULT = 1e-5
+
+
+def bn_affine(bn):
+    """Eval-mode BatchNorm as y = x * scale + shift (FP64 math, FP32 result)."""
+    w = bn.weight.detach().double() if bn.weight is not None else torch.ones_like(bn.running_var).double()
+    b = bn.bias.detach().double() if bn.bias is not None else torch.zeros_like(bn.running_var).double()
+    scale = w / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    shift = b - bn.running_mean.detach().double() * scale
+    return scale, shift
+
+
+def fold_conv_bn(weight, conv_bias, bn):
+    """(Cout,Cin/g,kT,kH,kW) conv weight (+ optional bias) followed by eval BN -> folded FP64 weight and bias."""
+    w = weight.detach().double()
+    cout = w.shape[0]
+    b = conv_bias.detach().double() if conv_bias is not None else torch.zeros(cout, dtype=torch.float64, device=w.device)
+    if bn is not None:
+        scale, shift = bn_affine(bn)
+        w = w * scale.view(-1, 1, 1, 1, 1)
+        b = b * scale + shift
+    return w, b
+
+
+def pack_igemm_weight(w, bias, device):
+    """Folded (Cout,Cin,kT,kH,kW) FP64 weight -> BF16 [n_pad][taps*kchunks*kc] (tap-major, then input channel) and
+    FP32 bias [n_pad], the layout esf_conv_igemm_create expects."""
+    cout, cin, kt, kh, kw = w.shape
+    kc, kchunks, _, n_pad = rt.igemm_geometry(cin, cout)
+    cpad = kc * kchunks
+    wp = torch.zeros(n_pad, kt * kh * kw, cpad, dtype=torch.float64, device=w.device)
+    wp[:cout, :, :cin] = w.permute(0, 2, 3, 4, 1).reshape(cout, kt * kh * kw, cin)
+    bp = torch.zeros(n_pad, dtype=torch.float64, device=w.device)
+    bp[:cout] = bias
+    return (wp.reshape(n_pad, -1).to(device=device, dtype=torch.bfloat16).contiguous(),
+            bp.to(device=device, dtype=torch.float32).contiguous())
+
+
+class Plan:
+    """Ordered kernel launches + every tensor they touch.  `eager` ops read the caller's input tensors and are
+    launched on every forward; `graph` ops only touch plan-owned memory and are replayed from one CUDA graph."""
+
+    def __init__(self, device):
+        self.device = device
+        self.keep = []        # tensors / ctypes structs that must outlive the plan
+        self.ops = []         # callables taking a stream pointer
+        self.handles = []     # esf_op* to destroy
+        self.graph = None
+        self.out = None
+        self.launches_per_run = 0
+        self.buffers = {}     # name -> activation tensor (for tests / debugging)
+
+    # ---------------------------------------------------------------- memory
+    def act(self, B, T, H, W, C, name=None, dtype=torch.bfloat16):
+        t = torch.empty((B, T, H, W, C), dtype=dtype, device=self.device)
+        self.keep.append(t)
+        if name:
+            self.buffers[name] = t
+        return t
+
+    def tensor(self, t, dtype=torch.float32):
+        t = t.detach().to(device=self.device, dtype=dtype).contiguous()
+        self.keep.append(t)
+        return t
+
+    # ---------------------------------------------------------------- ops
+    def conv_igemm(self, x, y, w_folded, bias, stride=(1, 1, 1), padding=(0, 0, 0), dilation=(1, 1, 1), act=rt.ACT_NONE,
+                   res=None, out_dtype=rt.BF16):
+        wp, bp = pack_igemm_weight(w_folded, bias, self.device)
+        self.keep += [wp, bp]
+        kt, kh, kw = w_folded.shape[2:]
+        d = rt.EsfConvDesc(rt.view(x), rt.view(y), rt.view(res) if res is not None else rt.null_view(),
+                           wp.data_ptr(), bp.data_ptr(), kt, kh, kw, *stride, *padding, *dilation, 1, act, out_dtype)
+        h = ctypes.c_void_p()
+        rt.check(rt.lib().esf_conv_igemm_create(ctypes.byref(d), ctypes.byref(h)), "esf_conv_igemm_create")
+        self.handles.append(h)
+        L = rt.lib()
+        self.ops.append(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"))
+        self.launches_per_run += 1
+
+    def conv_direct(self, x, y, w_folded, bias, stride=(1, 1, 1), padding=(0, 0, 0), dilation=(1, 1, 1), groups=1,
+                    act=rt.ACT_NONE, res=None, out_dtype=rt.BF16):
+        wd = self.tensor(w_folded.permute(0, 2, 3, 4, 1))  # [Cout][kT][kH][kW][Cin/g]
+        bd = self.tensor(bias)
+        kt, kh, kw = w_folded.shape[2:]
+        d = rt.EsfConvDesc(rt.view(x), rt.view(y), rt.view(res) if res is not None else rt.null_view(),
+                           wd.data_ptr(), bd.data_ptr(), kt, kh, kw, *stride, *padding, *dilation, groups, act,
+                           out_dtype)
+        self.keep.append(d)
+        L = rt.lib()
+        self.ops.append(lambda s, d=d: rt.check(L.esf_conv_direct(ctypes.byref(d), s), "esf_conv_direct"))
+        self.launches_per_run += 1
+
+    def stem_conv(self, x_nc, y, w_folded, bias, stride, padding, act=rt.ACT_RELU):
+        """x_nc: FP32 (B,Cin,T,H,W) contiguous plan-owned input buffer."""
+        ws = self.tensor(w_folded.permute(2, 3, 4, 1, 0))  # [kT][kH][kW][Cin][Cout]
+        bs = self.tensor(bias)
+        B, Cin, T, H, W = x_nc.shape
+        cout = w_folded.shape[0]
+        kt, kh, kw = w_folded.shape[2:]
+        yv = rt.view(y)
+        self.keep.append(yv)
+        L = rt.lib()
+        self.ops.append(lambda s: rt.check(
+            L.esf_stem_conv(x_nc.data_ptr(), B, Cin, T, H, W, ws.data_ptr(), bs.data_ptr(), cout, kt, kh, kw, *stride,
+                            *padding, act, ctypes.byref(yv), s), "esf_stem_conv"))
+        self.launches_per_run += 1
+
+    def pool(self, x, y, kernel, stride, padding, is_avg=False):
+        xv, yv = rt.view(x), rt.view(y)
+        self.keep += [xv, yv]
+        L = rt.lib()
+        self.ops.append(lambda s: rt.check(
+            L.esf_pool3d(ctypes.byref(xv), ctypes.byref(yv), *kernel, *stride, *padding, int(is_avg), s), "esf_pool3d"))
+        self.launches_per_run += 1
+
+    def eca_fuse(self, x_fast, y_slice, alpha, eca_weight, bn):
+        """MaxPool(alpha,1,1) -> ECA -> BN -> ReLU -> concat slice (custom_video_model_builder.py:131-135)."""
+        scale, shift = bn_affine(bn)
+        w = self.tensor(eca_weight.reshape(-1))
+        sc, sh = self.tensor(scale), self.tensor(shift)
+        B, C = x_fast.shape[0], x_fast.shape[4]
+        L = rt.lib()
+        scratch = torch.empty(int(L.esf_eca_scratch_floats(B, C)), dtype=torch.float32, device=self.device)
+        self.keep.append(scratch)
+        xv, yv = rt.view(x_fast), rt.view(y_slice)
+        self.keep += [xv, yv]
+        k = int(w.numel())
+        self.ops.append(lambda s: rt.check(
+            L.esf_eca_fuse(ctypes.byref(xv), alpha, w.data_ptr(), k, sc.data_ptr(), sh.data_ptr(), scratch.data_ptr(),
+                           ctypes.byref(yv), s), "esf_eca_fuse"))
+        self.launches_per_run += 2
+
+    def position_attention(self, x_slow, y_slice, alpha, w_down, att, bn):
+        """1x1x1 C->d conv composed with the q/k/v 1x1x1 convs into one GEMM (FP32 out), hi/lo packing, fused
+        flash-style attention + gamma*O + x + BN + ReLU + x alpha upsample + concat
+        (custom_video_model_builder.py:141-146, wdf_attention_helper.py:33-54)."""
+        B, T, H, W, C = x_slow.shape
+        wd = w_down.detach().double().reshape(w_down.shape[0], C)            # (d, C)
+        d = wd.shape[0]
+        mats, biases = [wd], [torch.zeros(d, dtype=torch.float64, device=wd.device)]
+        for conv in (att.query_conv, att.key_conv, att.value_conv):
+            wc = conv.weight.detach().double().reshape(conv.weight.shape[0], d)
+            assert wc.shape[0] == d, "SpatialAttention reduction != 1 is not used by any registered model"
+            mats.append(wc @ wd)
+            biases.append(conv.bias.detach().double())
+        w_all = torch.cat(mats, 0).reshape(4 * d, C, 1, 1, 1)
+        b_all = torch.cat(biases, 0)
+        proj = self.act(B, T, H, W, 4 * d, dtype=torch.float32)
+        self.conv_igemm(x_slow, proj, w_all, b_all, out_dtype=rt.F32)
+        L = rt.lib()
+        N = T * H * W
+        nbytes = int(L.esf_attn_pack_bytes(B, N, d))
+        if nbytes < 0:
+            rt.check(nbytes, "esf_attn_pack_bytes")
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.keep.append(packed)
+        scale, shift = bn_affine(bn)
+        sc, sh = self.tensor(scale), self.tensor(shift)
+        gamma = float(att.gamma.detach().float().item())
+        yv = rt.view(y_slice)
+        self.keep.append(yv)
+        self.ops.append(lambda s: rt.check(L.esf_attn_pack(proj.data_ptr(), B, N, d, packed.data_ptr(), s),
+                                           "esf_attn_pack"))
+        self.ops.append(lambda s: rt.check(
+            L.esf_attn_fused(packed.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(), sh.data_ptr(), alpha,
+                             ctypes.byref(yv), s), "esf_attn_fused"))
+        self.launches_per_run += 2
+
+    def head(self, xs, weight, bias, act):
+        B = xs[0].shape[0]
+        cin = sum(x.shape[4] for x in xs)
+        K = weight.shape[0]
+        feat = torch.empty((B, cin), dtype=torch.float32, device=self.device)
+        out = torch.empty((B, K), dtype=torch.float32, device=self.device)
+        w, b = self.tensor(weight), self.tensor(bias)
+        v0 = rt.view(xs[0])
+        v1 = rt.view(xs[1]) if len(xs) > 1 else rt.null_view()
+        self.keep += [feat, out, v0, v1]
+        L = rt.lib()
+        self.ops.append(lambda s: rt.check(L.esf_head_pool(ctypes.byref(v0), ctypes.byref(v1), feat.data_ptr(), s),
+                                           "esf_head_pool"))
+        self.ops.append(lambda s: rt.check(
+            L.esf_head_fc(feat.data_ptr(), B, cin, w.data_ptr(), b.data_ptr(), K, act, out.data_ptr(), s),
+            "esf_head_fc"))
+        self.launches_per_run += len(xs) + 1
+        self.out = out
+        return out
+
+    # ---------------------------------------------------------------- execution
+    def launch_all(self):
+        s = rt.current_stream_ptr()
+        for op in self.ops:
+            op(s)
+
+    def capture(self):
+        """Record the launches into one CUDA graph (replayed by run())."""
+        torch.cuda.synchronize(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.launch_all()  # warm-up outside capture: sets kernel attributes, faults in the code
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.launch_all()
+        self.graph = g
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.launch_all()
+        return self.out
+
+    def __del__(self):
+        try:
+            L = rt.lib()
+            for h in self.handles:
+                L.esf_op_destroy(h)
+        except Exception:
+            pass

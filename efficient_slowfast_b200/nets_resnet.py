@@ -1,0 +1,521 @@
+"""The two ResNet-50 based two-stream models, behind the reference's registry / nn.Module surface:
+
+  SlowFastDualAttention   (reference: SlowFast/slowfast/models/custom_video_model_builder.py:171-445)
+  SlowFast                (reference: SlowFast/slowfast/models/video_model_builder.py:153-416)
+
+The module tree only *holds parameters* under the reference's state_dict keys, child names
+and child order, so checkpoints, BN scans and `load_state_dict` written against the reference keep working.  The
+arithmetic is not in these modules: `forward([slow, fast])` compiles (once per input shape) a launch plan of
+hand-written sm_100a kernels (engine.py, csrc/) and replays it.  Eval mode only -- the training path (batch-stat BN,
+autograd) is outside the hot path this package accelerates and raises.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import runtime as rt
+from .build import MODEL_REGISTRY
+from .engine import Plan, fold_conv_bn
+
+# video_model_builder.py:16-90 / custom_video_model_builder.py:151-168
+_MODEL_STAGE_DEPTH = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
+_TEMPORAL_KERNEL_BASIS = {
+    "slowfast": [[[1], [5]], [[1], [3]], [[1], [3]], [[3], [3]], [[3], [3]]],
+}
+_POOL1 = {"slowfast": [[1, 1, 1], [1, 1, 1]]}
+
+
+class _Holder(nn.Module):
+    """Parameter container; the computation happens in the model-level launch plan."""
+
+    def forward(self, *a, **k):
+        raise RuntimeError("%s only holds parameters; call the model's forward([slow, fast])" % type(self).__name__)
+
+
+def get_norm(cfg):
+    """batchnorm_helper.py:15-34.  Only plain BatchNorm3d exists on the eval forward path; the sub-/sync-BN variants
+    differ from it in training mode only and store the same parameters."""
+    if cfg.BN.NORM_TYPE in ("batchnorm", "sub_batchnorm", "sync_batchnorm"):
+        return nn.BatchNorm3d
+    raise NotImplementedError("Norm type {} is not supported".format(cfg.BN.NORM_TYPE))
+
+
+# --------------------------------------------------------------------------------------------- holders
+class ResNetBasicStem(_Holder):
+    """stem_helper.py:102-178: conv kxkxk s(1,2,2) -> BN -> ReLU -> MaxPool (1,3,3) s(1,2,2) p(0,1,1)."""
+
+    def __init__(self, dim_in, dim_out, kernel, stride, padding, norm_module, eps=1e-5, bn_mmt=0.1):
+        super().__init__()
+        self.kernel, self.stride, self.padding = kernel, stride, padding
+        self.conv = nn.Conv3d(dim_in, dim_out, kernel, stride=stride, padding=padding, bias=False)
+        self.bn = norm_module(num_features=dim_out, eps=eps, momentum=bn_mmt)
+        self.relu = nn.ReLU(True)
+        self.pool_layer = nn.MaxPool3d(kernel_size=[1, 3, 3], stride=[1, 2, 2], padding=[0, 1, 1])
+
+
+class VideoModelStem(_Holder):
+    """stem_helper.py:9-99."""
+
+    def __init__(self, dim_in, dim_out, kernel, stride, padding, norm_module):
+        super().__init__()
+        assert len({len(dim_in), len(dim_out), len(kernel), len(stride), len(padding)}) == 1, \
+            "Input pathway dimensions are not consistent."
+        self.num_pathways = len(dim_in)
+        for p in range(self.num_pathways):
+            self.add_module("pathway{}_stem".format(p),
+                            ResNetBasicStem(dim_in[p], dim_out[p], kernel[p], stride[p], padding[p], norm_module))
+
+
+class BottleneckTransform(_Holder):
+    """resnet_helper.py:110-240: Tx1x1 -> BN -> ReLU -> 1x3x3 (stride) -> BN -> ReLU -> 1x1x1 -> BN."""
+
+    def __init__(self, dim_in, dim_out, temp_kernel_size, stride, dim_inner, num_groups, stride_1x1, dilation,
+                 norm_module, eps=1e-5, bn_mmt=0.1):
+        super().__init__()
+        str1x1, str3x3 = (stride, 1) if stride_1x1 else (1, stride)
+        self.a = nn.Conv3d(dim_in, dim_inner, kernel_size=[temp_kernel_size, 1, 1], stride=[1, str1x1, str1x1],
+                           padding=[int(temp_kernel_size // 2), 0, 0], bias=False)
+        self.a_bn = norm_module(num_features=dim_inner, eps=eps, momentum=bn_mmt)
+        self.a_relu = nn.ReLU(inplace=True)
+        self.b = nn.Conv3d(dim_inner, dim_inner, [1, 3, 3], stride=[1, str3x3, str3x3],
+                           padding=[0, dilation, dilation], groups=num_groups, bias=False,
+                           dilation=[1, dilation, dilation])
+        self.b_bn = norm_module(num_features=dim_inner, eps=eps, momentum=bn_mmt)
+        self.b_relu = nn.ReLU(inplace=True)
+        self.c = nn.Conv3d(dim_inner, dim_out, kernel_size=[1, 1, 1], stride=[1, 1, 1], padding=[0, 0, 0], bias=False)
+        self.c_bn = norm_module(num_features=dim_out, eps=eps, momentum=bn_mmt)
+        self.c_bn.transform_final_bn = True
+
+
+class ResBlock(_Holder):
+    """resnet_helper.py:243-358."""
+
+    def __init__(self, dim_in, dim_out, temp_kernel_size, stride, dim_inner, num_groups, stride_1x1, dilation,
+                 norm_module, eps=1e-5, bn_mmt=0.1):
+        super().__init__()
+        if (dim_in != dim_out) or (stride != 1):
+            self.branch1 = nn.Conv3d(dim_in, dim_out, kernel_size=1, stride=[1, stride, stride], padding=0, bias=False,
+                                     dilation=1)
+            self.branch1_bn = norm_module(num_features=dim_out, eps=eps, momentum=bn_mmt)
+        self.branch2 = BottleneckTransform(dim_in, dim_out, temp_kernel_size, stride, dim_inner, num_groups,
+                                           stride_1x1, dilation, norm_module)
+        self.relu = nn.ReLU(True)
+
+
+class ResStage(_Holder):
+    """resnet_helper.py:361-561 (without Nonlocal blocks: every BASELINE config has NONLOCAL.LOCATION empty)."""
+
+    def __init__(self, dim_in, dim_out, stride, temp_kernel_sizes, num_blocks, dim_inner, num_groups,
+                 num_block_temp_kernel, nonlocal_inds, dilation, trans_func_name, stride_1x1, norm_module):
+        super().__init__()
+        assert all(num_block_temp_kernel[i] <= num_blocks[i] for i in range(len(temp_kernel_sizes)))
+        if trans_func_name != "bottleneck_transform":
+            raise NotImplementedError("RESNET.TRANS_FUNC '%s' (only bottleneck_transform is on the BASELINE path)"
+                                      % trans_func_name)
+        if any(len(x) for x in nonlocal_inds):
+            raise NotImplementedError("Nonlocal blocks are not built (NONLOCAL.LOCATION must be empty)")
+        self.num_blocks = num_blocks
+        self.temp_kernel_sizes = [
+            (temp_kernel_sizes[i] * num_blocks[i])[: num_block_temp_kernel[i]]
+            + [1] * (num_blocks[i] - num_block_temp_kernel[i])
+            for i in range(len(temp_kernel_sizes))
+        ]
+        self.num_pathways = len(num_blocks)
+        for p in range(self.num_pathways):
+            for i in range(num_blocks[p]):
+                blk = ResBlock(dim_in[p] if i == 0 else dim_out[p], dim_out[p], self.temp_kernel_sizes[p][i],
+                               stride[p] if i == 0 else 1, dim_inner[p], num_groups[p], stride_1x1, dilation[p],
+                               norm_module)
+                self.add_module("pathway{}_res{}".format(p, i), blk)
+
+
+class FuseFastToSlow(_Holder):
+    """video_model_builder.py:93-150: conv kx1x1 stride (alpha,1,1) C->ratio*C -> BN -> ReLU -> cat into slow."""
+
+    def __init__(self, dim_in, fusion_conv_channel_ratio, fusion_kernel, alpha, norm_module, eps=1e-5, bn_mmt=0.1):
+        super().__init__()
+        self.alpha = alpha
+        self.conv_f2s = nn.Conv3d(dim_in, dim_in * fusion_conv_channel_ratio, kernel_size=[fusion_kernel, 1, 1],
+                                  stride=[alpha, 1, 1], padding=[fusion_kernel // 2, 0, 0], bias=False)
+        self.bn = norm_module(num_features=dim_in * fusion_conv_channel_ratio, eps=eps, momentum=bn_mmt)
+        self.relu = nn.ReLU(True)
+
+
+class SpatialAttention(_Holder):
+    """wdf_attention_helper.py:13-54 (position attention; gamma starts at zero)."""
+
+    def __init__(self, channel, reduction=8):
+        super().__init__()
+        self.input_channel = channel
+        self.query_conv = nn.Conv3d(channel, channel // reduction, kernel_size=1)
+        self.key_conv = nn.Conv3d(channel, channel // reduction, kernel_size=1)
+        self.value_conv = nn.Conv3d(channel, channel, kernel_size=1)
+        self.gamma = nn.Parameter(torch.zeros(1))
+        self.softmax = nn.Softmax(dim=-1)
+
+
+class ECA(_Holder):
+    """wdf_attention_helper.py:57-91."""
+
+    def __init__(self, channel, k_size=3):
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool3d(1)
+        self.conv = nn.Conv1d(1, 1, kernel_size=k_size, padding=(k_size - 1) // 2, bias=False)
+        self.sigmoid = nn.Sigmoid()
+
+
+class FuseFastAndSlow(_Holder):
+    """CMDA, custom_video_model_builder.py:42-148."""
+
+    def __init__(self, dim_in, alpha, beta_inv, norm_module, eps=1e-5, bn_mmt=0.1, reduction=1):
+        super().__init__()
+        self.alpha = alpha
+        self.downsample_t_of_fast = nn.MaxPool3d(kernel_size=(alpha, 1, 1), stride=(alpha, 1, 1))
+        self.attention_channel_f2s = ECA(dim_in[1])
+        self.bn_f2s = norm_module(num_features=dim_in[1], eps=eps, momentum=bn_mmt)
+        self.relu_f2s = nn.ReLU(True)
+        self.downsample_c_of_slow = nn.Conv3d(dim_in[0], dim_in[0] // beta_inv, kernel_size=[1, 1, 1],
+                                              stride=[1, 1, 1], bias=False)
+        self.attention_spatial_s2f = SpatialAttention(int(dim_in[0] // beta_inv), reduction=reduction)
+        self.bn_s2f = norm_module(num_features=int(dim_in[0] // beta_inv), eps=eps, momentum=bn_mmt)
+        self.relu_s2f = nn.ReLU(True)
+        self.upsample_s2f = nn.Upsample(scale_factor=(alpha, 1, 1), mode="nearest")
+
+
+class ResNetBasicHead(_Holder):
+    """head_helper.py:133-223."""
+
+    def __init__(self, dim_in, num_classes, pool_size, dropout_rate=0.0, act_func="softmax"):
+        super().__init__()
+        assert len({len(pool_size), len(dim_in)}) == 1, "pathway dimensions are not consistent."
+        self.num_pathways = len(pool_size)
+        self.pool_size = pool_size
+        for p in range(self.num_pathways):
+            pool = nn.AdaptiveAvgPool3d((1, 1, 1)) if pool_size[p] is None else nn.AvgPool3d(pool_size[p], stride=1)
+            self.add_module("pathway{}_avgpool".format(p), pool)
+        if dropout_rate > 0.0:
+            self.dropout = nn.Dropout(dropout_rate)
+        self.projection = nn.Linear(sum(dim_in), num_classes, bias=True)
+        if act_func == "softmax":
+            self.act = nn.Softmax(dim=4)
+        elif act_func == "sigmoid":
+            self.act = nn.Sigmoid()
+        else:
+            raise NotImplementedError("{} is not supported as an activation function.".format(act_func))
+        self.act_func = act_func
+
+
+def init_weights(model, fc_init_std=0.01, zero_init_final_bn=True):
+    """utils/weight_init_helper.py:10-43: c2_msra_fill (kaiming normal, fan_out, relu; zero bias) on Conv3d, BN weight
+    1 (0 for the last BN of a bottleneck when zero_init_final_bn), BN bias 0, Linear N(0, fc_init_std) / zero bias.
+    Conv1d (ECA) keeps its constructor init, as in the reference."""
+    for m in model.modules():
+        if isinstance(m, nn.Conv3d):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.BatchNorm3d):
+            zero = getattr(m, "transform_final_bn", False) and zero_init_final_bn
+            if m.weight is not None:
+                m.weight.data.fill_(0.0 if zero else 1.0)
+            if m.bias is not None:
+                m.bias.data.zero_()
+        if isinstance(m, nn.Linear):
+            m.weight.data.normal_(mean=0.0, std=fc_init_std)
+            m.bias.data.zero_()
+
+
+# --------------------------------------------------------------------------------------------- model base
+class _PlannedModel(nn.Module):
+    """Shared forward machinery: shape-keyed launch plans, weight-version tracking, CUDA-graph replay."""
+
+    num_pathways = 2
+
+    def _init_runtime(self, cfg):
+        self._cfg = cfg
+        self._plans = {}
+        self._use_graph = bool(cfg.get("ESF", {}).get("CUDA_GRAPH", True)) if hasattr(cfg, "get") else True
+
+    def _weights_stamp(self):
+        s = 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            s += t._version + (t.data_ptr() & 0xFFFF)
+        return s
+
+    def invalidate_plans(self):
+        self._plans = {}
+
+    def _get_plan(self, shapes, device):
+        key = (tuple(tuple(s) for s in shapes), str(device))
+        stamp = self._weights_stamp()
+        ent = self._plans.get(key)
+        if ent is not None and ent[0] == stamp:
+            return ent[1]
+        plan = Plan(device)
+        plan.inputs = [torch.empty(s, dtype=torch.float32, device=device) for s in shapes]
+        with torch.no_grad():
+            self._compile(plan)
+        if self._use_graph:
+            plan.capture()
+        self._plans = {key: (stamp, plan)}  # one live plan: activation arenas are large
+        return plan
+
+    def input_buffers(self, shapes, device=None):
+        """Plan-owned static input tensors for `shapes`; filling these (e.g. as the target of the H2D copy) and then
+        calling forward() on them skips the device-to-device staging copy."""
+        device = device or next(self.parameters()).device
+        return self._get_plan(shapes, device).inputs
+
+    def forward(self, x, bboxes=None):
+        assert len(x) == self.num_pathways, "Input tensor does not contain {} pathway".format(self.num_pathways)
+        if self.training:
+            raise NotImplementedError("efficient_slowfast_b200 implements the eval-mode forward path only; call "
+                                      ".eval() (training / autograd is outside the accelerated hot path)")
+        if bboxes is not None:
+            raise NotImplementedError("detection (bboxes) is out of scope")
+        dev = x[0].device
+        if dev.type != "cuda":
+            raise rt.EsfError("the forward path is CUDA-only (sm_100a); got tensors on %s -- there is no CPU fallback"
+                              % dev)
+        plan = self._get_plan([tuple(t.shape) for t in x], dev)
+        for src, dst in zip(x, plan.inputs):
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        out = plan.run()
+        return out.clone()
+
+    def debug_buffers(self):
+        """name -> channels-last BF16 activation tensors of the live plan (tests only)."""
+        for _, plan in self._plans.values():
+            return plan.buffers
+        return {}
+
+
+def _stage_dims(cfg):
+    w = cfg.RESNET.WIDTH_PER_GROUP
+    return [w * 4, w * 8, w * 16, w * 32]
+
+
+class _TwoStreamResNet(_PlannedModel):
+    """Common structure of SlowFast and SlowFastDualAttention: stem, 4 residual stages, a fusion module after the
+    stem and after res2..res4, identity pathway pools, basic head."""
+
+    def _build(self, cfg, dual_attention):
+        assert cfg.MODEL.ARCH in _POOL1.keys()
+        pool_size = _POOL1[cfg.MODEL.ARCH]
+        assert len({len(pool_size), self.num_pathways}) == 1
+        assert cfg.RESNET.DEPTH in _MODEL_STAGE_DEPTH.keys()
+        if cfg.DETECTION.ENABLE:
+            raise NotImplementedError("DETECTION.ENABLE (ResNetRoIHead) is out of scope")
+        self.norm_module = get_norm(cfg)
+        self.enable_detection = False
+        self.dual_attention = dual_attention
+        depths = _MODEL_STAGE_DEPTH[cfg.RESNET.DEPTH]
+        num_groups = cfg.RESNET.NUM_GROUPS
+        wpg = cfg.RESNET.WIDTH_PER_GROUP
+        dim_inner = num_groups * wpg
+        beta = cfg.SLOWFAST.BETA_INV
+        alpha = cfg.SLOWFAST.ALPHA
+        if dual_attention:
+            out_dim_ratio = beta                                                # custom_video_model_builder.py:213
+        else:
+            out_dim_ratio = beta // cfg.SLOWFAST.FUSION_CONV_CHANNEL_RATIO      # video_model_builder.py:199-201
+        tk = _TEMPORAL_KERNEL_BASIS[cfg.MODEL.ARCH]
+
+        def fuse(c_slow):
+            if dual_attention:
+                return FuseFastAndSlow([c_slow, c_slow // beta], alpha, beta, self.norm_module, reduction=1)
+            return FuseFastToSlow(c_slow // beta, cfg.SLOWFAST.FUSION_CONV_CHANNEL_RATIO,
+                                  cfg.SLOWFAST.FUSION_KERNEL_SZ, alpha, self.norm_module)
+
+        self.s1 = VideoModelStem(
+            dim_in=cfg.DATA.INPUT_CHANNEL_NUM, dim_out=[wpg, wpg // beta],
+            kernel=[tk[0][0] + [7, 7], tk[0][1] + [7, 7]], stride=[[1, 2, 2]] * 2,
+            padding=[[tk[0][0][0] // 2, 3, 3], [tk[0][1][0] // 2, 3, 3]], norm_module=self.norm_module)
+        self.s1_fuse = fuse(wpg)
+        c_prev = wpg
+        for i, name in enumerate(("s2", "s3", "s4", "s5")):
+            c_out = wpg * 4 * (2 ** i)
+            fast_in = c_prev // beta + (c_prev // out_dim_ratio if dual_attention else 0)
+            stage = ResStage(
+                dim_in=[c_prev + c_prev // out_dim_ratio, fast_in], dim_out=[c_out, c_out // beta],
+                dim_inner=[dim_inner * (2 ** i), dim_inner * (2 ** i) // beta], temp_kernel_sizes=tk[i + 1],
+                stride=cfg.RESNET.SPATIAL_STRIDES[i], num_blocks=[depths[i]] * 2, num_groups=[num_groups] * 2,
+                num_block_temp_kernel=cfg.RESNET.NUM_BLOCK_TEMP_KERNEL[i], nonlocal_inds=cfg.NONLOCAL.LOCATION[i],
+                dilation=cfg.RESNET.SPATIAL_DILATIONS[i], trans_func_name=cfg.RESNET.TRANS_FUNC,
+                stride_1x1=cfg.RESNET.STRIDE_1X1, norm_module=self.norm_module)
+            setattr(self, name, stage)
+            if name != "s5":
+                setattr(self, name + "_fuse", fuse(c_out))
+            if name == "s2":
+                for p in range(self.num_pathways):
+                    self.add_module("pathway{}_pool".format(p),
+                                    nn.MaxPool3d(kernel_size=pool_size[p], stride=pool_size[p], padding=[0, 0, 0]))
+            c_prev = c_out
+        if cfg.MULTIGRID.SHORT_CYCLE:
+            head_pool = [None, None]
+        else:
+            c = cfg.DATA.CROP_SIZE // 32
+            head_pool = [
+                [cfg.DATA.NUM_FRAMES // alpha // pool_size[0][0], c // pool_size[0][1], c // pool_size[0][2]],
+                [cfg.DATA.NUM_FRAMES // pool_size[1][0], c // pool_size[1][1], c // pool_size[1][2]],
+            ]
+        self.head = ResNetBasicHead(dim_in=[wpg * 32, wpg * 32 // beta], num_classes=cfg.MODEL.NUM_CLASSES,
+                                    pool_size=head_pool, dropout_rate=cfg.MODEL.DROPOUT_RATE,
+                                    act_func=cfg.MODEL.HEAD_ACT)
+        init_weights(self, cfg.MODEL.FC_INIT_STD, cfg.RESNET.ZERO_INIT_FINAL_BN)
+        self._init_runtime(cfg)
+
+    # ------------------------------------------------------------------------------------------ plan
+    def _compile(self, plan):
+        cfg = self._cfg
+        alpha, beta = cfg.SLOWFAST.ALPHA, cfg.SLOWFAST.BETA_INV
+        xs_in = plan.inputs
+        B = xs_in[0].shape[0]
+        assert xs_in[1].shape[2] == xs_in[0].shape[2] * alpha, \
+            "fast pathway must have ALPHA x the frames of the slow pathway"
+        wpg = cfg.RESNET.WIDTH_PER_GROUP
+        c_fast = wpg // beta
+        dual = self.dual_attention
+        ratio = cfg.SLOWFAST.FUSION_CONV_CHANNEL_RATIO
+
+        def fused_channels(c_slow):
+            """channel widths of the [slow, fast] buffers that hold a stage output plus what the fusion appends."""
+            cf = c_slow // beta
+            if dual:
+                return c_slow + cf, cf + cf
+            return c_slow + ratio * cf, cf
+
+        def conv_out(n, k, s, p, d=1):
+            return (n + 2 * p - d * (k - 1) - 1) // s + 1
+
+        # ---- stem: conv+BN+ReLU (direct, FP32 clip in) then max-pool into the first concat buffers
+        cs_tot, cf_tot = fused_channels(wpg)
+        cur = []
+        for pw in range(2):
+            stem = getattr(self.s1, "pathway{}_stem".format(pw))
+            x = xs_in[pw]
+            _, _, T, H, W = x.shape
+            k, s, p = stem.kernel, stem.stride, stem.padding
+            To, Ho, Wo = conv_out(T, k[0], s[0], p[0]), conv_out(H, k[1], s[1], p[1]), conv_out(W, k[2], s[2], p[2])
+            cout = stem.conv.out_channels
+            y = plan.act(B, To, Ho, Wo, cout)
+            w, b = fold_conv_bn(stem.conv.weight, None, stem.bn)
+            plan.stem_conv(x, y, w, b, tuple(s), tuple(p), act=rt.ACT_RELU)
+            Hp, Wp = conv_out(Ho, 3, 2, 1), conv_out(Wo, 3, 2, 1)
+            buf = plan.act(B, To, Hp, Wp, cs_tot if pw == 0 else cf_tot, name="s1_cat%d" % pw)
+            # slow: [x_s | from_fast]; fast (dual attention): [from_slow | x_f]
+            off = 0 if (pw == 0 or not dual) else c_fast
+            plan.pool(y, buf[..., off:off + cout], (1, 3, 3), (1, 2, 2), (0, 1, 1))
+            cur.append((buf, off, cout))
+        self._emit_fuse(plan, self.s1_fuse, cur)
+
+        # ---- residual stages
+        c_prev = wpg
+        for i, name in enumerate(("s2", "s3", "s4", "s5")):
+            stage = getattr(self, name)
+            c_out = wpg * 4 * (2 ** i)
+            last = name == "s5"
+            nxt = []
+            for pw in range(2):
+                buf_in, _, _ = cur[pw]
+                x = buf_in                      # the stage consumes the whole concat buffer
+                co = c_out if pw == 0 else c_out // beta
+                stride = cfg.RESNET.SPATIAL_STRIDES[i][pw]
+                dil = cfg.RESNET.SPATIAL_DILATIONS[i][pw]
+                _, T, H, W, _ = x.shape
+                Ho, Wo = conv_out(H, 1, stride, 0), conv_out(W, 1, stride, 0)
+                if last:
+                    tot, off = co, 0
+                else:
+                    tots = fused_channels(c_out)
+                    tot = tots[pw]
+                    off = 0 if (pw == 0 or not dual) else c_out // beta
+                dst = plan.act(B, T, Ho, Wo, tot, name="%s_cat%d" % (name, pw))
+                nblocks = stage.num_blocks[pw]
+                ping = [plan.act(B, T, Ho, Wo, co) for _ in range(min(2, nblocks - 1))]
+                for bi in range(nblocks):
+                    blk = getattr(stage, "pathway{}_res{}".format(pw, bi))
+                    y = dst[..., off:off + co] if bi == nblocks - 1 else ping[bi % 2]
+                    self._emit_block(plan, blk, x, y, stride if bi == 0 else 1, dil)
+                    x = y
+                nxt.append((dst, off, co))
+            cur = nxt
+            if not last:
+                self._emit_fuse(plan, getattr(self, name + "_fuse"), cur)
+            c_prev = c_out
+
+        # ---- head
+        xs = [c[0] for c in cur]
+        for pw, ps in enumerate(self.head.pool_size):
+            if ps is not None:
+                _, T, H, W, _ = xs[pw].shape
+                if [T, H, W] != [int(v) for v in ps]:
+                    raise NotImplementedError(
+                        "head AvgPool3d kernel %s smaller than the feature map %s (fully-convolutional multi-position "
+                        "head) is not built yet; use MULTIGRID.SHORT_CYCLE or matching DATA.CROP_SIZE/NUM_FRAMES"
+                        % (ps, [T, H, W]))
+        act = {"softmax": rt.HEAD_SOFTMAX, "sigmoid": rt.HEAD_SIGMOID}[self.head.act_func]
+        plan.head(xs, self.head.projection.weight, self.head.projection.bias, act)
+
+    def _emit_block(self, plan, blk, x, y, stride, dil):
+        """ResBlock (resnet_helper.py:352-358): y = relu(shortcut(x) + bn(c(relu(bn(b(relu(bn(a(x))))))))).
+        4 (or 3) implicit-GEMM launches; BN folded, ReLU and the residual add in the epilogues."""
+        t = blk.branch2
+        B, T, H, W, _ = x.shape
+        _, _, Ho, Wo, co = y.shape
+        ci = t.a.out_channels
+        s1 = t.a.stride[1]
+        Ha, Wa = (H - 1) // s1 + 1, (W - 1) // s1 + 1   # Tx1x1 conv, stride (1,s1,s1), no spatial padding
+        ta = plan.act(B, T, Ha, Wa, ci)
+        tb = plan.act(B, T, Ho, Wo, ci)
+        if hasattr(blk, "branch1"):
+            sc = plan.act(B, T, Ho, Wo, co)
+            w, b = fold_conv_bn(blk.branch1.weight, None, blk.branch1_bn)
+            plan.conv_igemm(x, sc, w, b, stride=tuple(blk.branch1.stride))
+        else:
+            sc = x
+        w, b = fold_conv_bn(t.a.weight, None, t.a_bn)
+        plan.conv_igemm(x, ta, w, b, stride=tuple(t.a.stride), padding=tuple(t.a.padding), act=rt.ACT_RELU)
+        if t.b.groups != 1:
+            raise NotImplementedError("RESNET.NUM_GROUPS > 1 (ResNeXt) is not on the BASELINE path")
+        w, b = fold_conv_bn(t.b.weight, None, t.b_bn)
+        plan.conv_igemm(ta, tb, w, b, stride=tuple(t.b.stride), padding=tuple(t.b.padding),
+                        dilation=tuple(t.b.dilation), act=rt.ACT_RELU)
+        w, b = fold_conv_bn(t.c.weight, None, t.c_bn)
+        plan.conv_igemm(tb, y, w, b, act=rt.ACT_RELU, res=sc)
+
+    def _emit_fuse(self, plan, fuse, cur):
+        (sbuf, soff, cs), (fbuf, foff, cf) = cur
+        x_s = sbuf[..., soff:soff + cs]
+        x_f = fbuf[..., foff:foff + cf]
+        if isinstance(fuse, FuseFastAndSlow):
+            # fast -> slow: written behind x_s;  slow -> fast: written in front of x_f.  Both read only stage outputs.
+            plan.eca_fuse(x_f, sbuf[..., cs:cs + cf], fuse.alpha, fuse.attention_channel_f2s.conv.weight, fuse.bn_f2s)
+            d = fuse.downsample_c_of_slow.out_channels
+            plan.position_attention(x_s, fbuf[..., 0:d], fuse.alpha, fuse.downsample_c_of_slow.weight,
+                                    fuse.attention_spatial_s2f, fuse.bn_s2f)
+        else:
+            conv = fuse.conv_f2s
+            w, b = fold_conv_bn(conv.weight, None, fuse.bn)
+            plan.conv_igemm(x_f, sbuf[..., cs:cs + conv.out_channels], w, b, stride=tuple(conv.stride),
+                            padding=tuple(conv.padding), act=rt.ACT_RELU)
+
+
+@MODEL_REGISTRY.register()
+class SlowFastDualAttention(_TwoStreamResNet):
+    """custom_video_model_builder.py:171-445."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self._build(cfg, dual_attention=True)
+
+
+@MODEL_REGISTRY.register()
+class SlowFast(_TwoStreamResNet):
+    """video_model_builder.py:153-416."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self._build(cfg, dual_attention=False)

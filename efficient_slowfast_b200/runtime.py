@@ -1,0 +1,110 @@
+"""ctypes binding of libesf_b200.so (C ABI: include/esf.h).  There is no fallback: if the library is missing or a
+call fails this module raises."""
+import ctypes
+import os
+
+import torch
+
+_LIB = None
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libesf_b200.so")
+
+ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
+BF16, F32 = 0, 1
+HEAD_NONE, HEAD_SOFTMAX, HEAD_RELU, HEAD_SIGMOID = 0, 1, 2, 3
+
+
+class EsfView(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("H", ctypes.c_int32),
+                ("W", ctypes.c_int32), ("C", ctypes.c_int32), ("sB", ctypes.c_int64), ("sT", ctypes.c_int64),
+                ("sH", ctypes.c_int64), ("sW", ctypes.c_int64)]
+
+
+class EsfConvDesc(ctypes.Structure):
+    _fields_ = [("x", EsfView), ("y", EsfView), ("res", EsfView), ("w", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+                ("kT", ctypes.c_int32), ("kH", ctypes.c_int32), ("kW", ctypes.c_int32),
+                ("sT", ctypes.c_int32), ("sH", ctypes.c_int32), ("sW", ctypes.c_int32),
+                ("pT", ctypes.c_int32), ("pH", ctypes.c_int32), ("pW", ctypes.c_int32),
+                ("dT", ctypes.c_int32), ("dH", ctypes.c_int32), ("dW", ctypes.c_int32),
+                ("groups", ctypes.c_int32), ("act", ctypes.c_int32), ("out_dtype", ctypes.c_int32)]
+
+
+class EsfError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Load the shared library once; raises EsfError when it has not been built (python -m
+    efficient_slowfast_b200._build, or __graft_entry__.build())."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_LIB_PATH):
+        raise EsfError("libesf_b200.so not found at %s -- build it with `python -m efficient_slowfast_b200._build` "
+                       "(there is no CPU or PyTorch fallback for the forward path)" % _LIB_PATH)
+    L = ctypes.CDLL(_LIB_PATH)
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+    P = ctypes.POINTER
+    L.esf_last_error.restype = ctypes.c_char_p
+    L.esf_last_error.argtypes = []
+    L.esf_version.restype = ctypes.c_int
+    L.esf_launch_count.restype = i64
+    L.esf_igemm_geometry.argtypes = [i32, i32, P(i32), P(i32), P(i32), P(i32)]
+    L.esf_conv_igemm_create.argtypes = [P(EsfConvDesc), P(vp)]
+    L.esf_op_launch.argtypes = [vp, vp]
+    L.esf_op_destroy.argtypes = [vp]
+    L.esf_op_destroy.restype = None
+    L.esf_conv_direct.argtypes = [P(EsfConvDesc), vp]
+    L.esf_stem_conv.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32,
+                                i32, P(EsfView), vp]
+    L.esf_pool3d.argtypes = [P(EsfView), P(EsfView), i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.esf_eca_scratch_floats.argtypes = [i32, i32]
+    L.esf_eca_scratch_floats.restype = i64
+    L.esf_eca_fuse.argtypes = [P(EsfView), i32, vp, i32, vp, vp, vp, P(EsfView), vp]
+    L.esf_attn_pack_bytes.argtypes = [i32, i32, i32]
+    L.esf_attn_pack_bytes.restype = i64
+    L.esf_attn_pack.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.esf_attn_fused.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, i32, P(EsfView), vp]
+    L.esf_head_pool.argtypes = [P(EsfView), P(EsfView), vp, vp]
+    L.esf_head_fc.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp]
+    for name in ("esf_igemm_geometry", "esf_conv_igemm_create", "esf_op_launch", "esf_conv_direct", "esf_stem_conv",
+                 "esf_pool3d", "esf_eca_fuse", "esf_attn_pack", "esf_attn_fused", "esf_head_pool", "esf_head_fc"):
+        getattr(L, name).restype = ctypes.c_int
+    _LIB = L
+    return L
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().esf_last_error().decode("utf-8", "replace")
+        raise EsfError("%s failed (%d): %s" % (what or "libesf_b200 call", rc, msg))
+
+
+def launch_count():
+    return int(lib().esf_launch_count())
+
+
+def view(t):
+    """esf_view of a channels-last activation tensor (B,T,H,W,C), possibly a channel slice of a wider buffer."""
+    assert t.dim() == 5 and t.stride(4) == 1, "activation views are (B,T,H,W,C) with unit channel stride"
+    B, T, H, W, C = t.shape
+    sB, sT, sH, sW, _ = t.stride()
+    return EsfView(t.data_ptr(), B, T, H, W, C, sB, sT, sH, sW)
+
+
+def null_view():
+    return EsfView(None, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+
+
+def igemm_geometry(cin, cout):
+    kc, kch, nt, npad = (ctypes.c_int32() for _ in range(4))
+    check(lib().esf_igemm_geometry(cin, cout, ctypes.byref(kc), ctypes.byref(kch), ctypes.byref(nt),
+                                   ctypes.byref(npad)), "esf_igemm_geometry")
+    return kc.value, kch.value, nt.value, npad.value
+
+
+def current_stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,132 @@
+/*
+ * esf.h -- C ABI of libesf_b200.so: the sm_100a kernels behind the batched clip forward path of
+ * weidafeng/Efficient-SlowFast (`preds = model(inputs)`, SlowFast/tools/test_net.py:92).
+ *
+ * The reference has no FFI of its own (pure PyTorch: every op below is an ATen -> cuDNN/cuBLAS call in
+ * the reference), so each entry point cites the reference nn.Module code it replaces.  The binding a
+ * maintainer adds on the reference side is the ctypes stub in INTEGRATION.md; this repo's own binding is
+ * efficient_slowfast_b200/runtime.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless a name ends in _host;
+ *   - activations are channels-last 5-D views (B,T,H,W,C) with element strides (channel stride 1), BF16
+ *     unless stated; a view may be a channel slice of a wider concat buffer (C < sW);
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued, never synchronised;
+ *   - every function returns 0 on success or a negative code; esf_last_error() gives the message of the
+ *     last failure on the calling thread; nothing throws, nothing allocates device memory;
+ *   - no CPU fallback exists: on a machine without an sm_100 GPU every launch returns an error.
+ */
+#ifndef ESF_H_
+#define ESF_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESF_OK 0
+#define ESF_ERR_ARG (-1)
+#define ESF_ERR_CUDA (-2)
+#define ESF_ERR_UNSUPPORTED (-3)
+
+#define ESF_ACT_NONE 0
+#define ESF_ACT_RELU 1
+#define ESF_ACT_RELU6 2
+
+#define ESF_BF16 0
+#define ESF_F32 1
+
+typedef struct esf_view {
+  void* ptr;
+  int32_t B, T, H, W, C;
+  int64_t sB, sT, sH, sW; /* element strides; channel stride == 1 */
+} esf_view;
+
+typedef struct esf_conv_desc {
+  esf_view x;           /* BF16 input */
+  esf_view y;           /* output, BF16 or F32 (out_dtype) */
+  esf_view res;         /* optional BF16 residual added before the activation; ptr == NULL: none */
+  const void* w;        /* weights, layout depends on the entry point */
+  const float* bias;    /* folded BatchNorm shift (+ conv bias), FP32 */
+  int32_t kT, kH, kW;   /* kernel */
+  int32_t sT, sH, sW;   /* stride */
+  int32_t pT, pH, pW;   /* zero padding */
+  int32_t dT, dH, dW;   /* dilation */
+  int32_t groups;
+  int32_t act;          /* ESF_ACT_* */
+  int32_t out_dtype;    /* ESF_BF16 / ESF_F32 */
+} esf_conv_desc;
+
+typedef struct esf_op esf_op; /* opaque: one planned kernel launch (TMA descriptors + parameters) */
+
+const char* esf_last_error(void);
+int esf_version(void);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+int64_t esf_launch_count(void);
+
+/* ---- dense Conv3d (+ folded BN, + residual, + ReLU) as a tcgen05/TMEM implicit GEMM fed by TMA --------
+ * replaces nn.Conv3d + BatchNorm3d(eval) + ReLU (+ residual add) of
+ *   BottleneckTransform.forward   SlowFast/slowfast/models/resnet_helper.py:225-240
+ *   ResBlock.forward              SlowFast/slowfast/models/resnet_helper.py:352-358
+ *   FuseFastToSlow.forward        SlowFast/slowfast/models/video_model_builder.py:143-150
+ *   FuseFastAndSlow 1x1x1 convs   SlowFast/slowfast/models/custom_video_model_builder.py:141 and
+ *                                 wdf_attention_helper.py:42-48 (query/key/value convs)
+ * Weight packing: BF16 [n_pad][taps * kchunks * kc], tap-major then input channel, zero padded; the
+ * geometry (kc, kchunks, n_tile, n_pad) for a (cin, cout) pair comes from esf_igemm_geometry(). */
+int esf_igemm_geometry(int32_t cin, int32_t cout, int32_t* kc, int32_t* kchunks, int32_t* n_tile, int32_t* n_pad);
+int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out);
+int esf_op_launch(esf_op* op, void* stream);
+void esf_op_destroy(esf_op* op);
+
+/* ---- direct (CUDA-core) Conv3d for thin layers: grouped / depthwise / Cin < 16 -------------------------
+ * replaces the depthwise 3x3x3 / 1xkxk and small pointwise convs of shufflenetv2_helper.py:62-89,
+ * shufflenet_helper.py:50-62, mobilenetv2_helper.py:40-55, ghostnet_helper.py:88-143.
+ * Weights: FP32 [Cout][kT][kH][kW][Cin/groups]. */
+int esf_conv_direct(const esf_conv_desc* d, void* stream);
+
+/* ---- stem: Conv3d on the FP32 NCDHW clip + folded BN + ReLU -> BF16 channels-last ----------------------
+ * replaces ResNetBasicStem.conv/bn/relu (stem_helper.py:173-177) and the efficient stems
+ * (stem_helper.py:182-336).  x: FP32 (B,Cin,T,H,W) contiguous.  Weights FP32 [kT][kH][kW][Cin][Cout]. */
+int esf_stem_conv(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, const float* w,
+                  const float* bias, int32_t Cout, int32_t kT, int32_t kH, int32_t kW, int32_t sT, int32_t sH,
+                  int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t act, const esf_view* y, void* stream);
+
+/* ---- MaxPool3d / AvgPool3d on channels-last BF16 (padding: -inf for max, zeros counted for avg) ---------
+ * replaces ResNetBasicStem.pool_layer (stem_helper.py:169-171), the 3x3x3 stem pools
+ * (stem_helper.py:243,281) and the ShuffleNet shortcut AvgPool3d (shufflenet_helper.py:68-73). */
+int esf_pool3d(const esf_view* x, const esf_view* y, int32_t kT, int32_t kH, int32_t kW, int32_t sT, int32_t sH,
+               int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t is_avg, void* stream);
+
+/* ---- CMDA fast->slow: MaxPool(alpha,1,1) -> ECA -> BN -> ReLU -> write into the slow concat slice ------
+ * replaces FuseFastAndSlow.forward lines custom_video_model_builder.py:131-135 and ECA.forward
+ * (wdf_attention_helper.py:77-91).  Two launches: (1) per-(clip,channel) partial sums of the temporally
+ * max-pooled tensor, (2) channel conv1d + sigmoid + scale + BN affine + ReLU + store.
+ * partial: FP32 scratch of esf_eca_scratch_floats(B, C) elements. */
+int64_t esf_eca_scratch_floats(int32_t B, int32_t C);
+int esf_eca_fuse(const esf_view* x_fast, int32_t alpha, const float* eca_w, int32_t eca_k, const float* bn_scale,
+                 const float* bn_shift, float* partial, const esf_view* y_slow_slice, void* stream);
+
+/* ---- CMDA slow->fast position attention, fused (never materialises the N x N affinity) ------------------
+ * replaces SpatialAttention.forward (wdf_attention_helper.py:33-54) + bn_s2f + ReLU + nearest upsample +
+ * concat (custom_video_model_builder.py:142-146).
+ *   proj: FP32 (B*N, 4*d) rows [x_d | q | k | v] produced by the composed 1x1x1 GEMM (out_dtype F32);
+ *   esf_attn_pack splits q,k into BF16 hi/lo parts so QK^T keeps ~FP32 logits on BF16 tensor cores;
+ *   esf_attn_fused computes softmax_j(q_i.k_j) v_j with an online softmax, then
+ *   y[b, alpha*t + r, h, w, 0:d] = relu(bn_scale * (gamma * O + x_d) + bn_shift), r = 0..alpha-1. */
+int64_t esf_attn_pack_bytes(int32_t B, int32_t N, int32_t d);
+int esf_attn_pack(const float* proj, int32_t B, int32_t N, int32_t d, void* packed, void* stream);
+int esf_attn_fused(const void* packed, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d, float gamma,
+                   const float* bn_scale, const float* bn_shift, int32_t alpha, const esf_view* y_fast_slice,
+                   void* stream);
+
+/* ---- head: global average pool of each pathway -> concat -> Linear -> softmax/ReLU/none -----------------
+ * replaces ResNetBasicHead.forward eval branch (head_helper.py:198-223) and the efficient heads'
+ * pool+classifier tails.  feat: FP32 scratch (B, C0 + C1).  act: 0 none (logits), 1 softmax, 2 relu, 3 sigmoid. */
+int esf_head_pool(const esf_view* x0, const esf_view* x1, float* feat, void* stream);
+int esf_head_fc(const float* feat, int32_t B, int32_t Cin, const float* w, const float* bias, int32_t num_classes,
+                int32_t act, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESF_H_ */

@@ -1,0 +1,83 @@
+"""Deterministic weight / input recipe shared by the golden-vector generator (make_golden.py, runs the REFERENCE in
+the build container) and by the tests (run anywhere, no reference needed).
+
+Random-init parity is degenerate for this model family (SURVEY.md finding 5: ZERO_INIT_FINAL_BN and gamma = 0 zero
+out every bottleneck and every attention branch), so parity runs use perturbed weights:
+  * every tensor is drawn from a generator seeded by crc32(key) ^ seed  -> reproducible per key, on any machine;
+  * conv weights ~ N(0, 2/fan_out) (c2_msra_fill), BN weight ~ U(0.5,1.5), BN bias ~ U(-0.2,0.2), attention
+    gamma = 0.5, q/k/v biases ~ U(-0.1,0.1), ECA conv1d ~ U(-0.5,0.5), FC ~ N(0, 0.03), FC bias ~ U(-0.1,0.1);
+  * BN running statistics are calibrated by the generator with train-mode forwards of the reference model and are
+    STORED in the fixture (they cannot be regenerated without the reference).
+"""
+import zlib
+
+import torch
+
+
+def _gen(key, seed):
+    return torch.Generator().manual_seed((zlib.crc32(key.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+
+
+def seeded_state_dict(template, seed=0, bn_stats=None):
+    """template: {key: tensor} from model.state_dict() (shapes only are used).  Returns a new FP32 state_dict."""
+    out = {}
+    for key, ref in template.items():
+        shape = tuple(ref.shape)
+        g = _gen(key, seed)
+        is_bn = key.rsplit(".", 1)[0] + ".running_mean" in template
+        leaf = key.rsplit(".", 1)[-1]
+        if leaf == "num_batches_tracked":
+            t = torch.zeros(shape, dtype=torch.long)
+        elif leaf in ("running_mean", "running_var"):
+            if bn_stats is not None:
+                t = torch.as_tensor(bn_stats[key]).reshape(shape).float().clone()
+            else:
+                t = torch.zeros(shape) if leaf == "running_mean" else torch.ones(shape)
+        elif is_bn and leaf == "weight":
+            t = torch.rand(shape, generator=g) + 0.5
+        elif is_bn and leaf == "bias":
+            t = torch.rand(shape, generator=g) * 0.4 - 0.2
+        elif leaf == "gamma":
+            t = torch.full(shape, 0.5)
+        elif leaf == "weight" and len(shape) == 5:
+            fan_out = shape[0] * shape[2] * shape[3] * shape[4]
+            t = torch.randn(shape, generator=g) * (2.0 / fan_out) ** 0.5
+        elif leaf == "weight" and len(shape) == 3:
+            t = torch.rand(shape, generator=g) - 0.5
+        elif leaf == "weight" and len(shape) == 2:
+            t = torch.randn(shape, generator=g) * 0.03
+        elif leaf == "bias":
+            t = torch.rand(shape, generator=g) * 0.2 - 0.1
+        else:
+            raise KeyError("recipe does not know how to fill %s %s" % (key, shape))
+        out[key] = t
+    return out
+
+
+def seeded_clip(batch, frames, size, seed=1, channels=3):
+    """x ~ N(0,1) of shape (B, C, T, S, S): the full-rate (fast pathway) clip; slow = pack_pathway_output(x)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, channels, frames, size, size, generator=g)
+
+
+def pack_pathway_output(frames, alpha):
+    """datasets/utils.py:73-112 (arch 'slowfast'): slow = frames[:, :, linspace(0, T-1, T//alpha).long()]."""
+    T = frames.shape[2]
+    idx = torch.linspace(0, T - 1, T // alpha).long()
+    return [frames.index_select(2, idx).contiguous(), frames]
+
+
+def sample_indices(numel, n=64, seed=7):
+    g = torch.Generator().manual_seed(seed + numel % 1000003)
+    return torch.randint(0, numel, (min(n, numel),), generator=g)
+
+
+# name -> (model, yaml under SlowFast/, cfg overrides, list of (tag, batch, frames, crop))
+CASES = {
+    "dual_r50": dict(
+        model="SlowFastDualAttention", yaml="configs/Kinetics/SLOWFAST_DUAL_8x8_R50_stepwise_multigrid.yaml",
+        opts=[], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64), ("s224", 1, 32, 224)]),
+    "slowfast_r50": dict(
+        model="SlowFast", yaml="configs/Kinetics/SLOWFAST_4x16_R50.yaml",
+        opts=["MULTIGRID.SHORT_CYCLE", True], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64), ("s224", 1, 32, 224)]),
+}

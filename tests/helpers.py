@@ -1,0 +1,57 @@
+"""Shared test helpers (no reference needed)."""
+import os
+
+import numpy as np
+import torch
+
+import recipe  # tests/golden/recipe.py
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def case_cfg(name):
+    """Our own cfg for a golden case (mirrors the YAML + overrides listed in recipe.CASES)."""
+    import efficient_slowfast_b200 as esf
+
+    if name == "dual_r50":
+        cfg = esf.slowfast_dual_8x8_r50_cfg()
+    elif name == "slowfast_r50":
+        cfg = esf.slowfast_4x16_r50_cfg()
+        cfg.MULTIGRID.SHORT_CYCLE = True
+    else:
+        raise KeyError(name)
+    cfg.NUM_GPUS = 0
+    return cfg
+
+
+def case_model_and_weights(name):
+    """(cfg, model on CPU with the seeded + calibrated golden weights loaded)."""
+    import efficient_slowfast_b200 as esf
+
+    cfg = case_cfg(name)
+    torch.manual_seed(0)
+    model = esf.build_model(cfg)
+    gold = load_golden(name)
+    bn = {k[3:]: v for k, v in gold.items() if k.startswith("bn/")}
+    sd = recipe.seeded_state_dict(model.state_dict(), seed=0, bn_stats=bn)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    return cfg, model, gold
+
+
+def case_inputs(name, tag):
+    for t, b, frames, crop in recipe.CASES[name]["inputs"]:
+        if t == tag:
+            cfg = case_cfg(name)
+            return recipe.pack_pathway_output(recipe.seeded_clip(b, frames, crop, seed=1), cfg.SLOWFAST.ALPHA)
+    raise KeyError(tag)
+
+
+def rel_err(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()

@@ -1,0 +1,55 @@
+"""Oracle vs the real reference forward, stage by stage (build container only: needs /root/reference)."""
+import pytest
+import torch
+
+import helpers
+import recipe
+from oracle import ref_shim
+from oracle import slowfast_oracle as O
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not mounted")
+
+
+@pytest.mark.parametrize("name", ["dual_r50", "slowfast_r50"])
+def test_every_stage_bit_exact(name):
+    spec = recipe.CASES[name]
+    cfg = ref_shim.get_cfg(spec["yaml"], spec["opts"])
+    torch.manual_seed(0)
+    ref = ref_shim.build_reference_model(cfg)
+    gold = helpers.load_golden(name)
+    bn = {k[3:]: v for k, v in gold.items() if k.startswith("bn/")}
+    ref.load_state_dict(recipe.seeded_state_dict(ref.state_dict(), seed=0, bn_stats=bn), strict=True)
+    ref.eval()
+    xs = recipe.pack_pathway_output(recipe.seeded_clip(2, 32, 48, seed=5), cfg.SLOWFAST.ALPHA)
+    got = {}
+    hooks = [getattr(ref, n).register_forward_hook(lambda m, i, o, n=n: got.__setitem__(n, [t.clone() for t in o]))
+             for n in ("s1", "s1_fuse", "s2", "s2_fuse", "s3", "s3_fuse", "s4", "s4_fuse", "s5")]
+    with torch.no_grad():
+        y_ref = ref([t.clone() for t in xs])
+    for h in hooks:
+        h.remove()
+    taps = {}
+    y = O.forward(cfg, ref.state_dict(), xs, taps=taps)
+    for n, ts in got.items():
+        for pw in range(2):
+            assert torch.equal(ts[pw], taps[n][pw]), (n, pw)
+    assert torch.equal(y, y_ref)
+
+
+@pytest.mark.parametrize("name", ["dual_r50", "slowfast_r50"])
+def test_state_dict_schema_and_seeded_init_match_reference(name):
+    import efficient_slowfast_b200 as esf
+
+    spec = recipe.CASES[name]
+    rcfg = ref_shim.get_cfg(spec["yaml"], spec["opts"])
+    torch.manual_seed(11)
+    ref = ref_shim.build_reference_model(rcfg)
+    torch.manual_seed(11)
+    mine = esf.build_model(helpers.case_cfg(name))
+    a, b = mine.state_dict(), ref.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in b:
+        assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+    assert [n for n, _ in mine.named_children()] == [n for n, _ in ref.named_children()]
+    # a reference checkpoint loads into the drop-in (utils/checkpoint.py:279 uses strict=False)
+    mine.load_state_dict(ref.state_dict(), strict=True)
