@@ -1,0 +1,61 @@
+"""The C-ABI library builds here (nvcc cross-compiles without a GPU), loads, and exports every symbol that
+include/esf.h declares.  No compute calls: those are in the -m gpu tests."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "esf.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(esf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(esf_lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(esf_lib, s), "libesf_b200.so does not export %s" % s
+    assert esf_lib.esf_version() >= 100
+
+
+def test_geometry_rule(esf_lib):
+    from efficient_slowfast_b200 import runtime as rt
+
+    assert rt.igemm_geometry(64, 256) == (64, 1, 256, 256)
+    assert rt.igemm_geometry(72, 64) == (64, 2, 64, 64)
+    assert rt.igemm_geometry(8, 32) == (16, 1, 32, 32)
+    assert rt.igemm_geometry(32, 8) == (32, 1, 16, 16)
+    assert rt.igemm_geometry(1152, 2048) == (64, 18, 256, 2048)
+
+
+def test_bad_arguments_give_error_codes(esf_lib):
+    from efficient_slowfast_b200 import runtime as rt
+
+    assert esf_lib.esf_igemm_geometry(0, 4, None, None, None, None) < 0
+    assert b"positive" in esf_lib.esf_last_error()
+    assert esf_lib.esf_attn_pack_bytes(2, 100, 7) < 0      # head dim must be a multiple of 8 (R50 models)
+    assert esf_lib.esf_attn_pack_bytes(2, 100, 8) > 0
+    h = ctypes.c_void_p()
+    assert esf_lib.esf_conv_igemm_create(None, ctypes.byref(h)) < 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_forward_without_gpu_fails_loudly():
+    """No CPU fallback: the drop-in model refuses CPU tensors instead of silently computing elsewhere."""
+    import efficient_slowfast_b200 as esf
+    from efficient_slowfast_b200 import runtime as rt
+
+    cfg = esf.slowfast_dual_8x8_r50_cfg()
+    cfg.NUM_GPUS = 0
+    m = esf.build_model(cfg).eval()
+    with pytest.raises(rt.EsfError):
+        m([torch.zeros(1, 3, 8, 32, 32), torch.zeros(1, 3, 32, 32, 32)])
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m([torch.zeros(1, 3, 8, 32, 32), torch.zeros(1, 3, 32, 32, 32)])

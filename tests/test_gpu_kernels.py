@@ -1,0 +1,262 @@
+"""GPU parity of every kernel behind the C ABI against plain torch FP32/FP64 math on the same (BF16-rounded)
+operands.  Tolerances are stated per test; BF16 outputs carry 2^-9 relative rounding."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from efficient_slowfast_b200 import runtime as rt
+from efficient_slowfast_b200.engine import Plan
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand_act(g, B, T, H, W, C, scale=1.0):
+    return (torch.randn(B, T, H, W, C, generator=g) * scale).to(torch.bfloat16)
+
+
+def _to_ncdhw(t):
+    return t.float().permute(0, 4, 1, 2, 3).contiguous()
+
+
+def _to_ndhwc(t):
+    return t.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def _diagnose(name, got, ref, thr):
+    """Print where a conv result is wrong (which channels / positions), to debug without a local GPU."""
+    bad = (got - ref).abs() > thr
+    print("DIAG %s: %d / %d elements wrong; got finite %s; got==7 fraction %.3f; got==0 fraction %.3f" % (
+        name, int(bad.sum()), bad.numel(), bool(torch.isfinite(got).all()), float((got == 7).float().mean()),
+        float((got == 0).float().mean())))
+    B, C, T, H, W = got.shape
+    per_c = bad.float().mean((0, 2, 3, 4))
+    print("DIAG wrong fraction per channel (first 32):", [round(float(v), 2) for v in per_c[:32]])
+    print("DIAG wrong fraction per 8-channel chunk:", [round(float(v), 2) for v in per_c.reshape(-1, 8).mean(1)[:32]])
+    print("DIAG wrong fraction per t:", [round(float(v), 2) for v in bad.float().mean((0, 1, 3, 4))])
+    print("DIAG wrong fraction per h:", [round(float(v), 2) for v in bad.float().mean((0, 1, 2, 4))])
+    print("DIAG wrong fraction per w:", [round(float(v), 2) for v in bad.float().mean((0, 1, 2, 3))])
+    print("DIAG wrong fraction per b:", [round(float(v), 2) for v in bad.float().mean((1, 2, 3, 4))])
+    idx = bad.nonzero()[:6]
+    for i in idx:
+        i = tuple(int(v) for v in i)
+        print("DIAG  at (b,c,t,h,w)=%s got %.4f ref %.4f" % (i, float(got[i]), float(ref[i])))
+    print("DIAG got[0,:8,0,0,0] ", got[0, :8, 0, 0, 0].tolist())
+    print("DIAG ref[0,:8,0,0,0] ", ref[0, :8, 0, 0, 0].tolist())
+
+
+CONV_CASES = [
+    # name, (B,T,H,W), Cin, Cout, kernel, stride, pad, dil, act, res, out_f32
+    ("plain_1x1_one_tile", (1, 1, 8, 16), 64, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1), 0, False, False),
+    ("plain_1x1_k128", (1, 2, 8, 16), 128, 128, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1), 0, False, False),
+    ("c_1x1_res_relu", (2, 4, 14, 14), 64, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1), 1, True, False),
+    ("a_3x1x1_2chunks", (2, 8, 7, 7), 128, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), (1, 1, 1), 1, False, False),
+    ("b_1x3x3", (1, 2, 28, 28), 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), (1, 1, 1), 1, False, False),
+    ("b_1x3x3_s2_kc16", (2, 4, 28, 28), 16, 16, (1, 3, 3), (1, 2, 2), (0, 1, 1), (1, 1, 1), 1, False, False),
+    ("proj_1x1_s2_partial_chunk", (1, 2, 56, 56), 72, 128, (1, 1, 1), (1, 2, 2), (0, 0, 0), (1, 1, 1), 0, False, False),
+    ("b_1x3x3_kc32", (2, 4, 14, 14), 32, 32, (1, 3, 3), (1, 1, 1), (0, 1, 1), (1, 1, 1), 1, False, False),
+    ("lateral_5x1x1_s8", (2, 32, 14, 14), 8, 16, (5, 1, 1), (8, 1, 1), (2, 0, 0), (1, 1, 1), 1, False, False),
+    ("lateral_7x1x1_s4", (1, 32, 7, 7), 32, 64, (7, 1, 1), (4, 1, 1), (3, 0, 0), (1, 1, 1), 1, False, False),
+    ("proj_f32_out", (2, 2, 14, 14), 256, 128, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1), 0, False, True),
+    ("proj_f32_out_n32", (2, 2, 14, 14), 64, 32, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1), 0, False, True),
+    ("wide_2048", (4, 2, 7, 7), 512, 2048, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1), 1, True, False),
+    ("b_1x3x3_dil2", (1, 2, 14, 14), 64, 64, (1, 3, 3), (1, 1, 1), (0, 2, 2), (1, 2, 2), 1, False, False),
+    ("tiny_8to32", (2, 8, 14, 14), 8, 32, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1), 0, True, False),
+    ("b_1x3x3_s2_7x7", (3, 8, 14, 14), 512, 512, (1, 3, 3), (1, 2, 2), (0, 1, 1), (1, 1, 1), 1, False, False),
+    ("many_tiles", (8, 8, 28, 28), 128, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1), (1, 1, 1), 1, False, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_igemm(esf_lib, case):
+    name, (B, T, H, W), cin, cout, k, s, p, d, act, use_res, out_f32 = case
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    # input and output live inside wider concat buffers (channel slices) to exercise strided views
+    xbuf = _rand_act(g, B, T, H, W, cin + 8).to(DEV)
+    x = xbuf[..., 8:8 + cin]
+    w = torch.randn(cout, cin, *k, generator=g) * (2.0 / (cin * k[0] * k[1] * k[2])) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv3d(_to_ncdhw(x.cpu()), w.bfloat16().float(), bias, s, p, d)
+    _, _, To, Ho, Wo = ref.shape
+    res = None
+    if use_res:
+        res = _rand_act(g, B, To, Ho, Wo, cout).to(DEV)
+        ref = ref + _to_ncdhw(res.cpu())
+    if act == 1:
+        ref = ref.relu()
+    plan = Plan(DEV)
+    odt = torch.float32 if out_f32 else torch.bfloat16
+    ybuf = torch.full((B, To, Ho, Wo, cout + 16), 7.0, dtype=odt, device=DEV)
+    y = ybuf[..., 8:8 + cout] if not out_f32 else ybuf[..., 4:4 + cout]
+    plan.conv_igemm(x, y, w.double(), bias.double(), stride=s, padding=p, dilation=d, act=act, res=res,
+                    out_dtype=rt.F32 if out_f32 else rt.BF16)
+    plan.launch_all()
+    torch.cuda.synchronize()
+    got = _to_ncdhw(y.cpu())
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    tol = 2e-3 if out_f32 else 1e-2   # FP32 out: accumulation order only; BF16 out: + 2^-9 output rounding
+    if not err <= tol * scale:
+        _diagnose(name, got, ref, tol * scale)
+    assert err <= tol * scale, "%s: max err %.4g vs scale %.4g" % (name, err, scale)
+    # neighbours of the output slice are untouched
+    lo = ybuf[..., :4].float()
+    assert (lo == 7.0).all()
+    assert (ybuf[..., -4:].float() == 7.0).all()
+
+
+def test_conv_direct_depthwise_and_grouped(esf_lib):
+    g = torch.Generator().manual_seed(5)
+    for (cin, cout, groups, k, s, p) in [(24, 24, 24, (3, 3, 3), (1, 2, 2), (1, 1, 1)),
+                                         (12, 30, 3, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+                                         (6, 10, 1, (1, 3, 3), (1, 1, 1), (0, 1, 1))]:
+        x = _rand_act(g, 2, 4, 10, 10, cin).to(DEV)
+        w = torch.randn(cout, cin // groups, *k, generator=g) * 0.2
+        bias = torch.randn(cout, generator=g) * 0.1
+        ref = F.conv3d(_to_ncdhw(x.cpu()), w, bias, s, p, 1, groups).relu()
+        y = torch.empty(_to_ndhwc(ref).shape, dtype=torch.bfloat16, device=DEV)
+        plan = Plan(DEV)
+        plan.conv_direct(x, y, w.double(), bias.double(), stride=s, padding=p, groups=groups, act=rt.ACT_RELU)
+        plan.launch_all()
+        torch.cuda.synchronize()
+        err = (_to_ncdhw(y.cpu()) - ref).abs().max().item()
+        assert err <= 1e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("kt,cout", [(1, 64), (5, 8), (3, 6)])
+def test_stem_conv(esf_lib, kt, cout):
+    g = torch.Generator().manual_seed(kt)
+    x = torch.randn(2, 3, 8, 32, 32, generator=g)
+    k = (kt, 7, 7)
+    w = torch.randn(cout, 3, *k, generator=g) * 0.1
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv3d(x, w, bias, (1, 2, 2), (kt // 2, 3, 3)).relu()
+    y = torch.empty(_to_ndhwc(ref).shape, dtype=torch.bfloat16, device=DEV)
+    plan = Plan(DEV)
+    xd = x.to(DEV)
+    plan.stem_conv(xd, y, w.double(), bias.double(), (1, 2, 2), (kt // 2, 3, 3))
+    plan.launch_all()
+    torch.cuda.synchronize()
+    err = (_to_ncdhw(y.cpu()) - ref).abs().max().item()
+    assert err <= 6e-3 * ref.abs().max().item()   # FP32 math, BF16 output rounding (2^-8 relative worst case)
+
+
+@pytest.mark.parametrize("C", [64, 8, 6])
+def test_pool3d(esf_lib, C):
+    g = torch.Generator().manual_seed(C)
+    x = _rand_act(g, 2, 4, 17, 18, C).to(DEV)
+    for kernel, stride, pad, avg in [((1, 3, 3), (1, 2, 2), (0, 1, 1), False), ((3, 3, 3), (1, 2, 2), (1, 1, 1), False),
+                                     ((1, 3, 3), (1, 2, 2), (0, 1, 1), True)]:
+        xr = _to_ncdhw(x.cpu())
+        ref = F.avg_pool3d(xr, kernel, stride, pad) if avg else F.max_pool3d(xr, kernel, stride, pad)
+        y = torch.empty(_to_ndhwc(ref).shape, dtype=torch.bfloat16, device=DEV)
+        plan = Plan(DEV)
+        plan.pool(x, y, kernel, stride, pad, is_avg=avg)
+        plan.launch_all()
+        torch.cuda.synchronize()
+        got = _to_ncdhw(y.cpu())
+        if avg:
+            assert (got - ref).abs().max().item() <= 8e-3 * ref.abs().max().item()
+        else:
+            assert torch.equal(got, ref)   # max of BF16 values is exact
+
+
+@pytest.mark.parametrize("C,alpha", [(8, 4), (32, 4), (128, 4), (6, 4), (64, 8)])
+def test_eca_fuse(esf_lib, C, alpha):
+    g = torch.Generator().manual_seed(C)
+    B, T, H, W = 2, 8, 9, 7
+    xbuf = _rand_act(g, B, T, H, W, 2 * C).to(DEV)
+    x = xbuf[..., C:]
+    bn = torch.nn.BatchNorm3d(C)
+    bn.weight.data = torch.rand(C, generator=g) + 0.5
+    bn.bias.data = torch.rand(C, generator=g) - 0.5
+    bn.running_mean = torch.randn(C, generator=g) * 0.3
+    bn.running_var = torch.rand(C, generator=g) + 0.5
+    bn.eval()
+    wk = torch.rand(1, 1, 3, generator=g) - 0.5
+    xr = _to_ncdhw(x.cpu())
+    f = F.max_pool3d(xr, (alpha, 1, 1), (alpha, 1, 1))
+    s = torch.sigmoid(F.conv1d(f.mean((2, 3, 4)).unsqueeze(1), wk, padding=1).squeeze(1))
+    with torch.no_grad():
+        ref = bn(f * s[:, :, None, None, None]).relu()
+    ybuf = torch.zeros(B, T // alpha, H, W, 3 * C, dtype=torch.bfloat16, device=DEV)
+    plan = Plan(DEV)
+    plan.eca_fuse(x, ybuf[..., 2 * C:], alpha, wk, bn)
+    plan.launch_all()
+    torch.cuda.synchronize()
+    got = _to_ncdhw(ybuf[..., 2 * C:].cpu())
+    assert (got - ref).abs().max().item() <= 8e-3 * ref.abs().max().item()
+    assert (ybuf[..., :2 * C] == 0).all()
+
+
+def _attention_reference(proj, B, T, H, W, d, gamma, scale, shift, alpha):
+    N = T * H * W
+    p = proj.double().reshape(B, N, 4, d)
+    xd, q, k, v = p[:, :, 0], p[:, :, 1], p[:, :, 2], p[:, :, 3]
+    att = torch.softmax(q @ k.transpose(1, 2), dim=-1)
+    o = gamma * (att @ v) + xd
+    o = (o * scale.double() + shift.double()).relu().reshape(B, T, H, W, d)
+    return o.repeat_interleave(alpha, dim=1)
+
+
+@pytest.mark.parametrize("d,T,H,W,qk_scale", [(8, 2, 9, 8, 1.0), (8, 2, 9, 8, 4.0), (32, 2, 12, 11, 1.0),
+                                              (32, 4, 8, 8, 2.0), (64, 2, 7, 7, 1.0), (128, 2, 7, 7, 0.5),
+                                              (16, 1, 9, 9, 1.0)])
+def test_attention_fused(esf_lib, d, T, H, W, qk_scale):
+    g = torch.Generator().manual_seed(d + T)
+    B, alpha = 2, 4
+    N = T * H * W
+    proj = torch.randn(B * N, 4 * d, generator=g)
+    proj[:, d:3 * d] *= qk_scale / d ** 0.25      # logits ~ N(0, qk_scale^2 ...) up to |s| ~ 4*qk_scale^2
+    gamma = 0.7
+    scale = torch.rand(d, generator=g) + 0.5
+    shift = torch.rand(d, generator=g) - 0.5
+    ref = _attention_reference(proj, B, T, H, W, d, gamma, scale, shift, alpha)
+    L = esf_lib
+    nbytes = L.esf_attn_pack_bytes(B, N, d)
+    assert nbytes > 0
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    pj = proj.to(DEV)
+    ybuf = torch.zeros(B, T * alpha, H, W, 2 * d, dtype=torch.bfloat16, device=DEV)
+    yv = rt.view(ybuf[..., :d])
+    sc, sh = scale.to(DEV), shift.to(DEV)
+    s = rt.current_stream_ptr()
+    rt.check(L.esf_attn_pack(pj.data_ptr(), B, N, d, packed.data_ptr(), s))
+    rt.check(L.esf_attn_fused(packed.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(), sh.data_ptr(), alpha,
+                              ctypes.byref(yv), s))
+    torch.cuda.synchronize()
+    got = ybuf[..., :d].cpu().double()
+    err = (got - ref).abs().max().item()
+    # BF16 P and V (2^-9 each) + BF16 output rounding; logits themselves are ~FP32 thanks to the hi/lo split
+    assert err <= 1.5e-2 * ref.abs().max().item(), "d=%d err %.4g scale %.4g" % (d, err, ref.abs().max().item())
+    assert (ybuf[..., d:] == 0).all()
+
+
+def test_head(esf_lib):
+    g = torch.Generator().manual_seed(9)
+    B = 3
+    x0 = _rand_act(g, B, 2, 3, 3, 128).to(DEV)
+    x1 = _rand_act(g, B, 8, 3, 3, 24).to(DEV)
+    w = torch.randn(27, 152, generator=g) * 0.2
+    b = torch.randn(27, generator=g) * 0.1
+    feat = torch.cat([x0.cpu().float().mean((1, 2, 3)), x1.cpu().float().mean((1, 2, 3))], 1)
+    logits = feat @ w.t() + b
+    for act, ref in [(rt.HEAD_SOFTMAX, torch.softmax(logits, 1)), (rt.HEAD_NONE, logits), (rt.HEAD_RELU, logits.relu())]:
+        plan = Plan(DEV)
+        out = plan.head([x0, x1], w, b, act)
+        plan.launch_all()
+        torch.cuda.synchronize()
+        assert (out.cpu() - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_errors_are_reported_not_swallowed(esf_lib):
+    """bad arguments return an error code + message (no exception crosses the C boundary, no silent fallback)."""
+    L = esf_lib
+    x = torch.zeros(1, 2, 4, 4, 12, dtype=torch.bfloat16, device=DEV)   # stride 12 elements = 24 B: not 16 B aligned
+    y = torch.zeros(1, 2, 4, 4, 16, dtype=torch.bfloat16, device=DEV)
+    plan = Plan(DEV)
+    with pytest.raises(rt.EsfError):
+        plan.conv_igemm(x, y, torch.zeros(16, 12, 1, 1, 1).double(), torch.zeros(16).double())
+    assert "multiple of 16" in L.esf_last_error().decode()
