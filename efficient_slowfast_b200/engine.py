@@ -65,6 +65,7 @@ class Plan:
         self.out = None
         self.launches_per_run = 0
         self.buffers = {}     # name -> activation tensor (for tests / debugging)
+        self.meta = []        # one dict per op: kind, label, algorithmic flops / bytes / exps, launches
 
     # ---------------------------------------------------------------- memory
     def act(self, B, T, H, W, C, name=None, dtype=torch.bfloat16):
@@ -79,6 +80,16 @@ class Plan:
         self.keep.append(t)
         return t
 
+    def _add(self, fn, kind, label="", flops=0, nbytes=0, exps=0, launches=1):
+        self.ops.append(fn)
+        self.meta.append(dict(kind=kind, label=label, flops=float(flops), bytes=float(nbytes), exps=float(exps),
+                              launches=launches))
+        self.launches_per_run += launches
+
+    @staticmethod
+    def _nbytes(*tensors):
+        return sum(t.numel() * t.element_size() for t in tensors if t is not None)
+
     # ---------------------------------------------------------------- ops
     def conv_igemm(self, x, y, w_folded, bias, stride=(1, 1, 1), padding=(0, 0, 0), dilation=(1, 1, 1), act=rt.ACT_NONE,
                    res=None, out_dtype=rt.BF16):
@@ -91,8 +102,11 @@ class Plan:
         rt.check(rt.lib().esf_conv_igemm_create(ctypes.byref(d), ctypes.byref(h)), "esf_conv_igemm_create")
         self.handles.append(h)
         L = rt.lib()
-        self.ops.append(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"))
-        self.launches_per_run += 1
+        cout, cin = w_folded.shape[:2]
+        m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
+        self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "conv_igemm",
+                  "%dx%dx%d s%s %d->%d @%s" % (kt, kh, kw, "".join(map(str, stride)), cin, cout, tuple(y.shape[1:4])),
+                  flops=2.0 * m * cout * cin * kt * kh * kw, nbytes=self._nbytes(x, y, res) + wp.numel() * 2)
 
     def conv_direct(self, x, y, w_folded, bias, stride=(1, 1, 1), padding=(0, 0, 0), dilation=(1, 1, 1), groups=1,
                     act=rt.ACT_NONE, res=None, out_dtype=rt.BF16):
@@ -104,8 +118,11 @@ class Plan:
                            out_dtype)
         self.keep.append(d)
         L = rt.lib()
-        self.ops.append(lambda s, d=d: rt.check(L.esf_conv_direct(ctypes.byref(d), s), "esf_conv_direct"))
-        self.launches_per_run += 1
+        m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
+        self._add(lambda s, d=d: rt.check(L.esf_conv_direct(ctypes.byref(d), s), "esf_conv_direct"), "conv_direct",
+                  "%dx%dx%d g%d %d->%d" % (kt, kh, kw, groups, x.shape[4], y.shape[4]),
+                  flops=2.0 * m * y.shape[4] * (x.shape[4] // groups) * kt * kh * kw,
+                  nbytes=self._nbytes(x, y, res) + wd.numel() * 4)
 
     def stem_conv(self, x_nc, y, w_folded, bias, stride, padding, act=rt.ACT_RELU):
         """x_nc: FP32 (B,Cin,T,H,W) contiguous plan-owned input buffer."""
@@ -117,18 +134,20 @@ class Plan:
         yv = rt.view(y)
         self.keep.append(yv)
         L = rt.lib()
-        self.ops.append(lambda s: rt.check(
+        m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
+        self._add(lambda s: rt.check(
             L.esf_stem_conv(x_nc.data_ptr(), B, Cin, T, H, W, ws.data_ptr(), bs.data_ptr(), cout, kt, kh, kw, *stride,
-                            *padding, act, ctypes.byref(yv), s), "esf_stem_conv"))
-        self.launches_per_run += 1
+                            *padding, act, ctypes.byref(yv), s), "esf_stem_conv"), "stem_conv",
+            "%dx%dx%d %d->%d" % (kt, kh, kw, Cin, cout), flops=2.0 * m * cout * Cin * kt * kh * kw,
+            nbytes=self._nbytes(x_nc, y))
 
     def pool(self, x, y, kernel, stride, padding, is_avg=False):
         xv, yv = rt.view(x), rt.view(y)
         self.keep += [xv, yv]
         L = rt.lib()
-        self.ops.append(lambda s: rt.check(
-            L.esf_pool3d(ctypes.byref(xv), ctypes.byref(yv), *kernel, *stride, *padding, int(is_avg), s), "esf_pool3d"))
-        self.launches_per_run += 1
+        self._add(lambda s: rt.check(
+            L.esf_pool3d(ctypes.byref(xv), ctypes.byref(yv), *kernel, *stride, *padding, int(is_avg), s), "esf_pool3d"),
+            "pool", "%s" % (tuple(kernel),), nbytes=self._nbytes(x, y))
 
     def eca_fuse(self, x_fast, y_slice, alpha, eca_weight, bn):
         """MaxPool(alpha,1,1) -> ECA -> BN -> ReLU -> concat slice (custom_video_model_builder.py:131-135)."""
@@ -142,10 +161,10 @@ class Plan:
         xv, yv = rt.view(x_fast), rt.view(y_slice)
         self.keep += [xv, yv]
         k = int(w.numel())
-        self.ops.append(lambda s: rt.check(
+        self._add(lambda s: rt.check(
             L.esf_eca_fuse(ctypes.byref(xv), alpha, w.data_ptr(), k, sc.data_ptr(), sh.data_ptr(), scratch.data_ptr(),
-                           ctypes.byref(yv), s), "esf_eca_fuse"))
-        self.launches_per_run += 2
+                           ctypes.byref(yv), s), "esf_eca_fuse"), "eca_fuse", "C=%d" % C,
+            nbytes=2 * self._nbytes(x_fast) + self._nbytes(y_slice), launches=2)
 
     def position_attention(self, x_slow, y_slice, alpha, w_down, att, bn):
         """1x1x1 C->d conv composed with the q/k/v 1x1x1 convs into one GEMM (FP32 out), hi/lo packing, fused
@@ -176,12 +195,13 @@ class Plan:
         gamma = float(att.gamma.detach().float().item())
         yv = rt.view(y_slice)
         self.keep.append(yv)
-        self.ops.append(lambda s: rt.check(L.esf_attn_pack(proj.data_ptr(), B, N, d, packed.data_ptr(), s),
-                                           "esf_attn_pack"))
-        self.ops.append(lambda s: rt.check(
+        self._add(lambda s: rt.check(L.esf_attn_pack(proj.data_ptr(), B, N, d, packed.data_ptr(), s),
+                                     "esf_attn_pack"), "attn_pack", "N=%d d=%d" % (N, d),
+                  nbytes=self._nbytes(proj) + nbytes)
+        self._add(lambda s: rt.check(
             L.esf_attn_fused(packed.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(), sh.data_ptr(), alpha,
-                             ctypes.byref(yv), s), "esf_attn_fused"))
-        self.launches_per_run += 2
+                             ctypes.byref(yv), s), "esf_attn_fused"), "attention", "N=%d d=%d" % (N, d),
+            flops=4.0 * B * N * N * d, exps=float(B) * N * N, nbytes=nbytes + self._nbytes(y_slice))
 
     def head(self, xs, weight, bias, act):
         B = xs[0].shape[0]
@@ -194,12 +214,11 @@ class Plan:
         v1 = rt.view(xs[1]) if len(xs) > 1 else rt.null_view()
         self.keep += [feat, out, v0, v1]
         L = rt.lib()
-        self.ops.append(lambda s: rt.check(L.esf_head_pool(ctypes.byref(v0), ctypes.byref(v1), feat.data_ptr(), s),
-                                           "esf_head_pool"))
-        self.ops.append(lambda s: rt.check(
+        self._add(lambda s: rt.check(L.esf_head_pool(ctypes.byref(v0), ctypes.byref(v1), feat.data_ptr(), s),
+                                     "esf_head_pool"), "head_pool", "", nbytes=self._nbytes(*xs), launches=len(xs))
+        self._add(lambda s: rt.check(
             L.esf_head_fc(feat.data_ptr(), B, cin, w.data_ptr(), b.data_ptr(), K, act, out.data_ptr(), s),
-            "esf_head_fc"))
-        self.launches_per_run += len(xs) + 1
+            "esf_head_fc"), "head_fc", "", flops=2.0 * B * cin * K, nbytes=self._nbytes(feat, w, out))
         self.out = out
         return out
 
@@ -222,6 +241,21 @@ class Plan:
         with torch.cuda.graph(g):
             self.launch_all()
         self.graph = g
+
+    def profile_ops(self, repeats=3):
+        """Per-op device time (ms, best of `repeats`) with CUDA events on the launching stream, eager launches."""
+        s = rt.current_stream_ptr()
+        times = [float("inf")] * len(self.ops)
+        for _ in range(repeats):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.ops) + 1)]
+            evs[0].record()
+            for i, op in enumerate(self.ops):
+                op(s)
+                evs[i + 1].record()
+            torch.cuda.synchronize(self.device)
+            for i in range(len(self.ops)):
+                times[i] = min(times[i], evs[i].elapsed_time(evs[i + 1]))
+        return times
 
     def run(self):
         if self.graph is not None:

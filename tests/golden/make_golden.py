@@ -42,7 +42,7 @@ def make_case(name):
     alpha = cfg.SLOWFAST.ALPHA
     torch.manual_seed(0)
     model = ref_shim.build_reference_model(cfg)
-    sd = recipe.seeded_state_dict(model.state_dict(), seed=0)
+    sd = recipe.seeded_state_dict(model.state_dict(), seed=0, stress=spec.get("stress", False))
     model.load_state_dict(sd, strict=True)
     cb, cf, cs = spec["calib"]
     calibrate_bn(model, [recipe.seeded_clip(cb, cf, cs, seed=100 + i) for i in range(2)], alpha)
@@ -86,6 +86,8 @@ def make_default_init():
     """Corner case: the reference's own seeded default init (gamma = 0, zero final BN, fresh BN stats)."""
     out = {}
     for name, spec in recipe.CASES.items():
+        if spec.get("stress"):
+            continue
         cfg = ref_shim.get_cfg(spec["yaml"], spec["opts"])
         torch.manual_seed(1234)
         model = ref_shim.build_reference_model(cfg).eval()

@@ -6,6 +6,12 @@ out every bottleneck and every attention branch), so parity runs use perturbed w
   * every tensor is drawn from a generator seeded by crc32(key) ^ seed  -> reproducible per key, on any machine;
   * conv weights ~ N(0, 2/fan_out) (c2_msra_fill), BN weight ~ U(0.5,1.5), BN bias ~ U(-0.2,0.2), attention
     gamma = 0.5, q/k/v biases ~ U(-0.1,0.1), ECA conv1d ~ U(-0.5,0.5), FC ~ N(0, 0.03), FC bias ~ U(-0.1,0.1);
+  * the LAST BN of every bottleneck (`...branch2.c_bn`, the one the reference zero-initialises) gets
+    weight ~ U(0.15,0.45) in the default "trained" recipe: the residual branch then changes the trunk by ~30 % per
+    block (every conv matters) without the random network being chaotic.  With weight ~ U(0.5,1.5) there too (the
+    "stress" recipe) a perturbation grows ~3x per stage -- 16-bit rounding noise of 2^-9 reaches 30 % of the
+    activations at res5 in ANY implementation (measured on CPU by rounding the oracle's activations) --
+    so that recipe is kept only as a stress fixture with an argmax check and a loose bound;
   * BN running statistics are calibrated by the generator with train-mode forwards of the reference model and are
     STORED in the fixture (they cannot be regenerated without the reference).
 """
@@ -18,7 +24,7 @@ def _gen(key, seed):
     return torch.Generator().manual_seed((zlib.crc32(key.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
 
 
-def seeded_state_dict(template, seed=0, bn_stats=None):
+def seeded_state_dict(template, seed=0, bn_stats=None, stress=False):
     """template: {key: tensor} from model.state_dict() (shapes only are used).  Returns a new FP32 state_dict."""
     out = {}
     for key, ref in template.items():
@@ -35,6 +41,8 @@ def seeded_state_dict(template, seed=0, bn_stats=None):
                 t = torch.zeros(shape) if leaf == "running_mean" else torch.ones(shape)
         elif is_bn and leaf == "weight":
             t = torch.rand(shape, generator=g) + 0.5
+            if key.endswith("c_bn.weight") and not stress:
+                t = (t - 0.5) * 0.3 + 0.15
         elif is_bn and leaf == "bias":
             t = torch.rand(shape, generator=g) * 0.4 - 0.2
         elif leaf == "gamma":
@@ -80,4 +88,7 @@ CASES = {
     "slowfast_r50": dict(
         model="SlowFast", yaml="configs/Kinetics/SLOWFAST_4x16_R50.yaml",
         opts=["MULTIGRID.SHORT_CYCLE", True], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64), ("s224", 1, 32, 224)]),
+    "slowfast_r50_stress": dict(
+        model="SlowFast", yaml="configs/Kinetics/SLOWFAST_4x16_R50.yaml", stress=True,
+        opts=["MULTIGRID.SHORT_CYCLE", True], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),
 }

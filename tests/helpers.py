@@ -20,7 +20,7 @@ def case_cfg(name):
 
     if name == "dual_r50":
         cfg = esf.slowfast_dual_8x8_r50_cfg()
-    elif name == "slowfast_r50":
+    elif name in ("slowfast_r50", "slowfast_r50_stress"):
         cfg = esf.slowfast_4x16_r50_cfg()
         cfg.MULTIGRID.SHORT_CYCLE = True
     else:
@@ -38,7 +38,8 @@ def case_model_and_weights(name):
     model = esf.build_model(cfg)
     gold = load_golden(name)
     bn = {k[3:]: v for k, v in gold.items() if k.startswith("bn/")}
-    sd = recipe.seeded_state_dict(model.state_dict(), seed=0, bn_stats=bn)
+    sd = recipe.seeded_state_dict(model.state_dict(), seed=0, bn_stats=bn,
+                                  stress=recipe.CASES[name].get("stress", False))
     model.load_state_dict(sd, strict=True)
     model.eval()
     return cfg, model, gold

@@ -76,6 +76,18 @@ def test_stage_outputs_match_oracle(esf_lib, name):
     assert max(r[2] for r in report) <= 5e-2   # per-activation max-norm error (BF16 storage of every tensor)
 
 
+def test_stress_recipe_argmax_and_bound(esf_lib):
+    """Stress weights (final-BN gamma ~ U(0.5,1.5) everywhere): the random network amplifies any perturbation ~3x per
+    stage, so 16-bit storage noise reaches ~20 % of the probabilities in ANY implementation (CPU emulation of BF16
+    storage on the oracle gives 17 %, DESIGN.md 'Precision').  Checked: argmax identical and a loose bound."""
+    cfg, model, gold, y = _run("slowfast_r50_stress", "s64")
+    ref = torch.as_tensor(gold["s64/probs"])
+    err = helpers.rel_err(y, ref)
+    print("slowfast_r50_stress/s64: rel err of probs %.3e (bound 3e-1)" % err)
+    assert torch.equal(y.argmax(1), ref.argmax(1))
+    assert err <= 0.3
+
+
 def test_default_init_corner(esf_lib):
     """gamma = 0 / zero final BN: attention and bottleneck branches contribute exactly nothing."""
     import efficient_slowfast_b200 as esf

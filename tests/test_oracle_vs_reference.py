@@ -18,7 +18,8 @@ def test_every_stage_bit_exact(name):
     ref = ref_shim.build_reference_model(cfg)
     gold = helpers.load_golden(name)
     bn = {k[3:]: v for k, v in gold.items() if k.startswith("bn/")}
-    ref.load_state_dict(recipe.seeded_state_dict(ref.state_dict(), seed=0, bn_stats=bn), strict=True)
+    ref.load_state_dict(recipe.seeded_state_dict(ref.state_dict(), seed=0, bn_stats=bn,
+                                                  stress=spec.get("stress", False)), strict=True)
     ref.eval()
     xs = recipe.pack_pathway_output(recipe.seeded_clip(2, 32, 48, seed=5), cfg.SLOWFAST.ALPHA)
     got = {}
