@@ -267,10 +267,14 @@ def run_gpu(args):
         k["bytes"] += m["bytes"]
         k["exps"] += m["exps"]
         k["launches"] += m["launches"]
+    if args.dump_ops and rank == 0:
+        with open(args.dump_ops, "w") as fh:
+            for t, m in zip(times, plan.meta):
+                fh.write(json.dumps(dict(ms=round(t, 4), **m)) + "\n")
     top_i = max(range(len(times)), key=lambda i: times[i])
     top, top_ms = plan.meta[top_i], times[top_i]
     tensor_peak = pk.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"])       # burst figure: kernel timed alone
-    if top["kind"] in ("conv_igemm", "attention"):
+    if top["kind"] in ("conv_igemm", "attention", "stem_igemm"):
         ach = top["flops"] / (top_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak}
     else:
@@ -337,6 +341,7 @@ def main():
     ap.add_argument("--cpu-clips", type=int, default=1)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-ops", default="", help="write per-op device times (JSON lines) to this file")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for ncu: eager launches (no CUDA graph), 1 warm-up + --steps steps, nothing else")
     args = ap.parse_args()

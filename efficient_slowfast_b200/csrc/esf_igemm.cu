@@ -56,15 +56,20 @@ struct __align__(64) IgemmParams {
   int slab_cols;      // output columns per TMA store slab
   uint32_t out_swz;   // swizzle mask of the staging rows (7 / 3 / 1)
   int num_tiles;
+  // "column blocks" (banded stem GEMM): an extra tile index that shifts the innermost coordinate of the
+  // activation loads and of the output stores; ncb == 1 and zero strides for ordinary convolutions
+  int ncb, a_cb_stride, out_cb_stride;
 };
 
 struct TileCoord {
-  int n_idx, w0, h0, t0, b0;
+  int n_idx, cb, w0, h0, t0, b0;
 };
 __device__ __forceinline__ TileCoord tile_coord(const IgemmParams& p, int tile) {
   TileCoord c;
   c.n_idx = tile % p.n_tiles;
   int m = tile / p.n_tiles;
+  c.cb = m % p.ncb;
+  m /= p.ncb;
   c.w0 = (m % p.tw) * p.bw;
   m /= p.tw;
   c.h0 = (m % p.th) * p.bh;
@@ -181,8 +186,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           for (int ch = 0; ch < p.kchunks; ++ch) {
             mbar_wait(&empty_bar[stage], phase ^ 1, 1);
             mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-            tma_load_5d(smem_a + stage * kAStageBytes, &p.a_maps[tp.x], &full_bar[stage], ch * p.kc, tc.w0 + tp.y,
-                        tc.h0 + tp.z, tc.t0 + tp.w, tc.b0);
+            tma_load_5d(smem_a + stage * kAStageBytes, &p.a_maps[tp.x], &full_bar[stage],
+                        tc.cb * p.a_cb_stride + ch * p.kc, tc.w0 + tp.y, tc.h0 + tp.z, tc.t0 + tp.w, tc.b0);
             tma_load_2d(smem_b + stage * p.b_stride, &p.b_map, &full_bar[stage], (tap * p.kchunks + ch) * p.kc,
                         tc.n_idx * p.n_tile);
             if (++stage == p.stages) {
@@ -237,7 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     if (p.has_res && leader && blockIdx.x < p.num_tiles) {
       const TileCoord tc = tile_coord(p, blockIdx.x);
       mbar_arrive_expect_tx(&res_full[0], p.res_bytes);
-      tma_load_5d(smem_out, &p.res_map, &res_full[0], tc.n_idx * p.n_tile, tc.w0, tc.h0, tc.t0, tc.b0);
+      tma_load_5d(smem_out, &p.res_map, &res_full[0], tc.cb * p.out_cb_stride + tc.n_idx * p.n_tile, tc.w0, tc.h0,
+                  tc.t0, tc.b0);
     }
     int iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
@@ -264,7 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         fence_proxy_async_smem();
         epi_bar_sync(1);
         if (leader) {
-          tma_store_5d(&p.out_map, stage_buf, tc.n_idx * p.n_tile + s * p.slab_cols, tc.w0, tc.h0, tc.t0, tc.b0);
+          tma_store_5d(&p.out_map, stage_buf, tc.cb * p.out_cb_stride + tc.n_idx * p.n_tile + s * p.slab_cols, tc.w0,
+                       tc.h0, tc.t0, tc.b0);
           tma_store_commit();
           tma_store_wait_read<1>();  // the previous slab's store no longer reads the other staging buffer
           if (p.has_res) {
@@ -277,7 +284,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
               const TileCoord nc = tile_coord(p, ntile);
               mbar_arrive_expect_tx(&res_full[buf ^ 1], p.res_bytes);
               tma_load_5d(smem_out + (buf ^ 1) * kOutStageBytes, &p.res_map, &res_full[buf ^ 1],
-                          nc.n_idx * p.n_tile + ns * p.slab_cols, nc.w0, nc.h0, nc.t0, nc.b0);
+                          nc.cb * p.out_cb_stride + nc.n_idx * p.n_tile + ns * p.slab_cols, nc.w0, nc.h0, nc.t0,
+                          nc.b0);
             }
           }
         }
@@ -363,6 +371,19 @@ static int num_sms() {
   return n;
 }
 
+static int finish_op(esf_op* op) {
+  const int sms = num_sms();
+  if (sms <= 0) return set_error(ESF_ERR_CUDA, "no CUDA device");
+  op->grid = std::min(op->params.num_tiles, sms);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e != cudaSuccess) return set_error(ESF_ERR_CUDA, "cudaFuncSetAttribute(igemm) failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  return ESF_OK;
+}
+
 extern "C" int esf_igemm_geometry(int32_t cin, int32_t cout, int32_t* kc, int32_t* kchunks, int32_t* n_tile,
                                   int32_t* n_pad) {
   ESF_CHECK_ARG(cin > 0 && cout > 0, "esf_igemm_geometry: cin/cout must be positive");
@@ -446,6 +467,8 @@ extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
     return set_error(ESF_ERR_ARG, "too many tiles");
   }
   p.num_tiles = (int)ntiles;
+  p.ncb = 1;
+  p.a_cb_stride = p.out_cb_stride = 0;
   const int row_bytes = kc * 2;
   p.a_bytes = p.rows * row_bytes;
   p.b_bytes = n_tile * row_bytes;
@@ -540,18 +563,146 @@ extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
     else
       p.res_map = p.out_map;
   }
-  if (rc == ESF_OK) {
-    const int sms = num_sms();
-    if (sms <= 0) rc = set_error(ESF_ERR_CUDA, "no CUDA device");
-    else op->grid = std::min(p.num_tiles, sms);
+  if (rc == ESF_OK) rc = finish_op(op);
+  if (rc != ESF_OK) {
+    delete op;
+    return rc;
   }
-  if (rc == ESF_OK) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-      if (e != cudaSuccess) rc = set_error(ESF_ERR_CUDA, "cudaFuncSetAttribute(igemm) failed: %s", cudaGetErrorString(e));
-      else attr_set = true;
+  *out = op;
+  return ESF_OK;
+}
+
+// ---- stem as a banded GEMM -------------------------------------------------------------------------------------
+// A Cin = 3 stem conv has K = kT*kH*kW*3 with no 16-byte-aligned contiguous run to feed the tensor cores.  Instead,
+// for a block of WB = 8 consecutive output columns the (kW, Cin) taps are folded into a banded weight matrix:
+//   row   m = (b, t, ho)            one output row position, for a fixed block wb of 8 output columns
+//   col   n = (i, co)               i = 0..7 output column inside the block, co output channel   (N = 8 * Cout)
+//   k       = (kt, kh, j)           j = 0..63 indexes the contiguous run of ((8-1)*sW + kW) * Cin <= 64 input
+//                                   elements of input row (t+kt-pT, sH*ho+kh-pH) that the block reads
+//   Wb[n][k] = w[co][c][kt][kh][kw] with (w_in, c) = divmod(j, Cin), kw = w_in - sW*i   (zero outside the band)
+// so every (kt,kh) tap is one 128 B-row TMA box of the packed channels-last clip (esf_stem_pack: BF16, left zero
+// pad so that block starts are 16 B aligned) and the output tile (8*Cout contiguous BF16 per row) is one TMA store.
+// ~1/3 of the MACs hit structural zeros of the band; that is the price of running a 3-channel conv at tensor speed.
+constexpr int kStemWB = 8;
+
+extern "C" int esf_stem_geometry(int32_t W, int32_t Cin, int32_t kW, int32_t sW, int32_t pW, int32_t* pitch,
+                                 int32_t* lpad, int32_t* window) {
+  ESF_CHECK_ARG(W > 0 && Cin > 0 && kW > 0 && sW > 0 && pW >= 0, "esf_stem_geometry: bad argument");
+  const int win = ((kStemWB - 1) * sW + kW) * Cin;
+  if (win > 64) return set_error(ESF_ERR_UNSUPPORTED, "stem window of %d elements exceeds one 64-element K chunk", win);
+  if ((kStemWB * sW * Cin) % 8 != 0)
+    return set_error(ESF_ERR_UNSUPPORTED, "stem block stride %d elements is not 16-byte aligned", kStemWB * sW * Cin);
+  const int Wo = (W + 2 * pW - kW) / sW + 1;
+  const int ncb = cdiv(Wo, kStemWB);
+  const int lp = pW * Cin;
+  int pt = std::max(lp + W * Cin, kStemWB * sW * Cin * (ncb - 1) + 64);
+  pt = (pt + 7) & ~7;
+  if (pitch) *pitch = pt;
+  if (lpad) *lpad = lp;
+  if (window) *window = win;
+  return ESF_OK;
+}
+
+extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W,
+                                     int32_t pitch, const void* w_band, const float* bias_tiled, int32_t Cout,
+                                     int32_t kT, int32_t kH, int32_t kW, int32_t sH, int32_t sW, int32_t pT, int32_t pH,
+                                     int32_t pW, int32_t act, const esf_view* y, esf_op** out) {
+  ESF_CHECK_ARG(xp && w_band && bias_tiled && view_ok(y) && out, "esf_stem_igemm_create: null/bad argument");
+  int pt_expected = 0, lpad = 0, win = 0;
+  int rc = esf_stem_geometry(W, Cin, kW, sW, pW, &pt_expected, &lpad, &win);
+  if (rc != ESF_OK) return rc;
+  ESF_CHECK_ARG(pitch == pt_expected, "esf_stem_igemm_create: pitch %d != esf_stem_geometry pitch %d", pitch, pt_expected);
+  const int To = T + 2 * pT - kT + 1;
+  const int Ho = (H + 2 * pH - kH) / sH + 1;
+  const int Wo = (W + 2 * pW - kW) / sW + 1;
+  ESF_CHECK_ARG(y->B == B && y->T == To && y->H == Ho && y->W == Wo && y->C == Cout && y->sW == Cout,
+                "esf_stem_igemm_create: output must be a dense (B,%d,%d,%d,%d) channels-last tensor", To, Ho, Wo, Cout);
+  const int num_taps = kT * kH;
+  ESF_CHECK_ARG(num_taps <= kMaxTaps, "esf_stem_igemm_create: %d (kT*kH) taps > %d", num_taps, kMaxTaps);
+
+  esf_op* op = new (std::nothrow) esf_op();
+  if (!op) return set_error(ESF_ERR_ARG, "out of host memory");
+  IgemmParams& p = op->params;
+  memset(&p, 0, sizeof(p));
+  const int N = kStemWB * Cout;
+  int kc, kchunks, n_tile, n_pad;
+  esf_igemm_geometry(64, N, &kc, &kchunks, &n_tile, &n_pad);
+  p.kc = 64, p.kchunks = 1, p.n_tile = n_tile, p.n_tiles = n_pad / n_tile, p.num_taps = num_taps;
+  choose_box(1, Ho, To, B, &p.bw, &p.bh, &p.bt, &p.bb);
+  p.tw = 1, p.th = cdiv(Ho, p.bh), p.tt = cdiv(To, p.bt), p.tb = cdiv(B, p.bb);
+  p.rows = p.bw * p.bh * p.bt * p.bb;
+  p.ncb = cdiv(Wo, kStemWB);
+  p.a_cb_stride = kStemWB * sW * Cin;
+  p.out_cb_stride = kStemWB * Cout;
+  const long long ntiles = (long long)p.ncb * p.th * p.tt * p.tb * p.n_tiles;
+  if (ntiles > 0x7fffffffLL) {
+    delete op;
+    return set_error(ESF_ERR_ARG, "too many tiles");
+  }
+  p.num_tiles = (int)ntiles;
+  p.a_bytes = p.rows * 128, p.b_bytes = n_tile * 128, p.b_stride = (p.b_bytes + 1023) & ~1023u;
+  p.sbo = 1024, p.layout_type = 2;
+  p.bias = bias_tiled, p.act = act, p.has_res = 0, p.out_f32 = 0;
+  p.slab_cols = std::min(n_tile, 64);
+  const int out_row_bytes = p.slab_cols * 2;
+  p.out_swz = out_row_bytes == 128 ? 7 : (out_row_bytes == 64 ? 3 : 1);
+  p.res_bytes = 0;
+  const int fixed = 1024 + 2 * kOutStageBytes + 512;
+  int stages = (kSmemLimit - fixed) / (kAStageBytes + (int)p.b_stride);
+  p.stages = std::max(2, std::min(stages, kMaxStages));
+  op->smem_bytes = fixed + p.stages * (kAStageBytes + (int)p.b_stride);
+
+  // one activation map per row phase of the H stride
+  int phase_map[8];
+  for (int i = 0; i < 8; ++i) phase_map[i] = -1;
+  int nmaps = 0, tap_i = 0;
+  for (int it = 0; it < kT && rc == ESF_OK; ++it)
+    for (int ih = 0; ih < kH && rc == ESF_OK; ++ih, ++tap_i) {
+      const int oh = ih - pH;
+      const int qh = floordiv(oh, sH);
+      const int ph = oh - qh * sH;
+      if (ph >= 8 || sH > 8) {
+        rc = set_error(ESF_ERR_UNSUPPORTED, "stem H stride > 8");
+        break;
+      }
+      if (phase_map[ph] < 0) {
+        const int Hp = ph < H ? cdiv(H - ph, sH) : 0;
+        if (Hp <= 0) {
+          rc = set_error(ESF_ERR_UNSUPPORTED, "empty stride phase");
+          break;
+        }
+        char* base = static_cast<char*>(const_cast<void*>(xp)) + 2LL * ph * pitch;
+        rc = encode_act_map(&p.a_maps[nmaps], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, pitch, 1, Hp, T, B,
+                            (int64_t)sH * pitch, (int64_t)sH * pitch, (int64_t)H * pitch, (int64_t)T * H * pitch, 64,
+                            1, p.bh, p.bt, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, "stem activation");
+        phase_map[ph] = nmaps++;
+      }
+      p.taps[tap_i] = make_int4(phase_map[ph], 0, qh, it - pT);
     }
+  if (rc == ESF_OK)
+    for (int i = nmaps; i < kMaxAMaps; ++i) p.a_maps[i] = p.a_maps[0];
+  if (rc == ESF_OK) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) rc = set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    else {
+      const cuuint64_t K = (cuuint64_t)num_taps * 64;
+      cuuint64_t dims[2] = {K, (cuuint64_t)n_pad};
+      cuuint64_t strides[1] = {K * 2};
+      cuuint32_t box[2] = {64, (cuuint32_t)n_tile};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = enc(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_band), dims, strides, box,
+                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) rc = set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled(stem weights) failed with %d", (int)r);
+    }
+  }
+  if (rc == ESF_OK)
+    rc = encode_act_map(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y->ptr, (int64_t)Wo * Cout, 1, Ho, To, B,
+                        y->sH, y->sH, y->sT, y->sB, p.slab_cols, 1, p.bh, p.bt, p.bb,
+                        swizzle_for_row_bytes(out_row_bytes), "stem output");
+  if (rc == ESF_OK) {
+    p.res_map = p.out_map;
+    rc = finish_op(op);
   }
   if (rc != ESF_OK) {
     delete op;

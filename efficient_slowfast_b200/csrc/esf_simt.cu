@@ -91,6 +91,38 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------- stem pack
+// FP32 (B,Cin,T,H,W) clip -> BF16 channels-last rows [B][T][H][pitch] with xp[.., lpad + w*Cin + c] = x[b,c,t,h,w] and
+// zeros in the left/right padding (the zero padding of the stem conv along W, made explicit so that every banded
+// GEMM block starts 16-byte aligned).  One thread per 8 consecutive output elements (one 16 B store).
+__global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x, int B, int Cin, int T, int H, int W,
+                                                        int pitch, int lpad, __nv_bfloat16* __restrict__ xp) {
+  const int chunks = pitch / 8;
+  const long long total = (long long)B * T * H * chunks;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ck = idx % chunks;
+    long long r = idx / chunks;
+    const int h = r % H;
+    r /= H;
+    const int t = r % T;
+    const int b = r / T;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = ck * 8 + e - lpad;
+      const int w = j / Cin, c = j - w * Cin;
+      v[e] = (j >= 0 && w < W) ? __ldg(x + ((((long long)b * Cin + c) * T + t) * H + h) * W + w) : 0.f;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(xp + (((long long)b * T + t) * H + h) * pitch + ck * 8) = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------- direct conv
 struct DirectParams {
   View x, y, res;
@@ -414,6 +446,16 @@ extern "C" int esf_stem_conv(const float* x, int32_t B, int32_t Cin, int32_t T, 
   if (vec8) stem_conv_kernel<8><<<grid_for(pos * (Cout / 8), 256), 256, 0, s>>>(p);
   else stem_conv_kernel<1><<<grid_for(pos * Cout, 256), 256, 0, s>>>(p);
   return check_launch("stem_conv_kernel");
+}
+
+extern "C" int esf_stem_pack(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
+                             int32_t lpad, void* xp, void* stream) {
+  ESF_CHECK_ARG(x && xp && B > 0 && Cin > 0 && T > 0 && H > 0 && W > 0, "esf_stem_pack: null/bad argument");
+  ESF_CHECK_ARG(pitch % 8 == 0 && pitch >= lpad + W * Cin, "esf_stem_pack: bad pitch %d", pitch);
+  const long long total = (long long)B * T * H * (pitch / 8);
+  stem_pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, B, Cin, T, H, W, pitch, lpad, static_cast<__nv_bfloat16*>(xp));
+  return check_launch("stem_pack_kernel");
 }
 
 extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {

@@ -52,6 +52,29 @@ def pack_igemm_weight(w, bias, device):
             bp.to(device=device, dtype=torch.float32).contiguous())
 
 
+STEM_WB = 8  # output columns per banded-GEMM block (csrc/esf_igemm.cu kStemWB)
+
+
+def pack_stem_band(w, bias, stride_w, device):
+    """Folded (Cout,Cin,kT,kH,kW) stem weight -> band matrix BF16 [n_pad][kT*kH*64] and tiled bias FP32 [n_pad].
+    Row n = i*Cout + co (i = output column inside the 8-wide block); column k = (kt*kH + kh)*64 + j where
+    (w_in, c) = divmod(j, Cin) is the j-th element of the contiguous input run the block reads and kw = w_in - sW*i."""
+    cout, cin, kt, kh, kw = w.shape
+    N = STEM_WB * cout
+    _, _, _, n_pad = rt.igemm_geometry(64, N)
+    band = torch.zeros(n_pad, kt * kh, 64, dtype=torch.float64, device=w.device)
+    win = ((STEM_WB - 1) * stride_w + kw) * cin
+    assert win <= 64
+    wt = w.permute(0, 2, 3, 4, 1).reshape(cout, kt * kh, kw, cin)          # [co][tap][kw][c]
+    for i in range(STEM_WB):
+        j0 = stride_w * i * cin
+        band[i * cout:(i + 1) * cout, :, j0:j0 + kw * cin] = wt.reshape(cout, kt * kh, kw * cin)
+    bt = torch.zeros(n_pad, dtype=torch.float64, device=w.device)
+    bt[:N] = bias.repeat(STEM_WB)
+    return (band.reshape(n_pad, -1).to(device=device, dtype=torch.bfloat16).contiguous(),
+            bt.to(device=device, dtype=torch.float32).contiguous())
+
+
 class Plan:
     """Ordered kernel launches + every tensor they touch.  `eager` ops read the caller's input tensors and are
     launched on every forward; `graph` ops only touch plan-owned memory and are replayed from one CUDA graph."""
@@ -140,6 +163,33 @@ class Plan:
                             *padding, act, ctypes.byref(yv), s), "esf_stem_conv"), "stem_conv",
             "%dx%dx%d %d->%d" % (kt, kh, kw, Cin, cout), flops=2.0 * m * cout * Cin * kt * kh * kw,
             nbytes=self._nbytes(x_nc, y))
+
+    def stem(self, x_nc, y, w_folded, bias, stride, padding, act=rt.ACT_RELU):
+        """Stem conv + folded BN + ReLU.  Tensor-core banded GEMM when the geometry allows (temporal stride 1,
+        window <= 64 elements, dense output), else the generic CUDA-core stem kernel."""
+        B, Cin, T, H, W = x_nc.shape
+        cout = w_folded.shape[0]
+        kt, kh, kw = w_folded.shape[2:]
+        geo = rt.stem_geometry(W, Cin, kw, stride[2], padding[2]) if stride[0] == 1 else None
+        if geo is None or not y.is_contiguous():
+            return self.stem_conv(x_nc, y, w_folded, bias, stride, padding, act)
+        pitch, lpad, _ = geo
+        L = rt.lib()
+        xp = torch.empty((B, T, H, pitch), dtype=torch.bfloat16, device=self.device)
+        wb, bt = pack_stem_band(w_folded, bias, stride[2], self.device)
+        self.keep += [xp, wb, bt]
+        yv = rt.view(y)
+        h = ctypes.c_void_p()
+        rt.check(L.esf_stem_igemm_create(xp.data_ptr(), B, Cin, T, H, W, pitch, wb.data_ptr(), bt.data_ptr(), cout,
+                                         kt, kh, kw, stride[1], stride[2], padding[0], padding[1], padding[2], act,
+                                         ctypes.byref(yv), ctypes.byref(h)), "esf_stem_igemm_create")
+        self.handles.append(h)
+        m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
+        self._add(lambda s: rt.check(L.esf_stem_pack(x_nc.data_ptr(), B, Cin, T, H, W, pitch, lpad, xp.data_ptr(), s),
+                                     "esf_stem_pack"), "stem_pack", "", nbytes=self._nbytes(x_nc, xp))
+        self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "stem_igemm",
+                  "%dx%dx%d %d->%d banded" % (kt, kh, kw, Cin, cout), flops=2.0 * m * cout * Cin * kt * kh * kw,
+                  nbytes=self._nbytes(xp, y) + wb.numel() * 2)
 
     def pool(self, x, y, kernel, stride, padding, is_avg=False):
         xv, yv = rt.view(x), rt.view(y)

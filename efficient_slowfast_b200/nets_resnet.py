@@ -402,7 +402,7 @@ class _TwoStreamResNet(_PlannedModel):
             cout = stem.conv.out_channels
             y = plan.act(B, To, Ho, Wo, cout)
             w, b = fold_conv_bn(stem.conv.weight, None, stem.bn)
-            plan.stem_conv(x, y, w, b, tuple(s), tuple(p), act=rt.ACT_RELU)
+            plan.stem(x, y, w, b, tuple(s), tuple(p), act=rt.ACT_RELU)
             Hp, Wp = conv_out(Ho, 3, 2, 1), conv_out(Wo, 3, 2, 1)
             buf = plan.act(B, To, Hp, Wp, cs_tot if pw == 0 else cf_tot, name="s1_cat%d" % pw)
             # slow: [x_s | from_fast]; fast (dual attention): [from_slow | x_f]

@@ -60,6 +60,10 @@ def lib():
     L.esf_conv_direct.argtypes = [P(EsfConvDesc), vp]
     L.esf_stem_conv.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32,
                                 i32, P(EsfView), vp]
+    L.esf_stem_geometry.argtypes = [i32, i32, i32, i32, i32, P(i32), P(i32), P(i32)]
+    L.esf_stem_pack.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+    L.esf_stem_igemm_create.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32,
+                                        i32, i32, i32, P(EsfView), P(vp)]
     L.esf_pool3d.argtypes = [P(EsfView), P(EsfView), i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     L.esf_eca_scratch_floats.argtypes = [i32, i32]
     L.esf_eca_scratch_floats.restype = i64
@@ -70,7 +74,8 @@ def lib():
     L.esf_attn_fused.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, i32, P(EsfView), vp]
     L.esf_head_pool.argtypes = [P(EsfView), P(EsfView), vp, vp]
     L.esf_head_fc.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp]
-    for name in ("esf_igemm_geometry", "esf_conv_igemm_create", "esf_op_launch", "esf_conv_direct", "esf_stem_conv",
+    for name in ("esf_stem_geometry", "esf_stem_pack", "esf_stem_igemm_create", "esf_igemm_geometry",
+                 "esf_conv_igemm_create", "esf_op_launch", "esf_conv_direct", "esf_stem_conv",
                  "esf_pool3d", "esf_eca_fuse", "esf_attn_pack", "esf_attn_fused", "esf_head_pool", "esf_head_fc"):
         getattr(L, name).restype = ctypes.c_int
     _LIB = L
@@ -104,6 +109,15 @@ def igemm_geometry(cin, cout):
     check(lib().esf_igemm_geometry(cin, cout, ctypes.byref(kc), ctypes.byref(kch), ctypes.byref(nt),
                                    ctypes.byref(npad)), "esf_igemm_geometry")
     return kc.value, kch.value, nt.value, npad.value
+
+
+def stem_geometry(W, cin, kW, sW, pW):
+    """(pitch, lpad, window) of the packed stem rows, or None when the banded-GEMM stem does not apply."""
+    pitch, lpad, win = (ctypes.c_int32() for _ in range(3))
+    rc = lib().esf_stem_geometry(W, cin, kW, sW, pW, ctypes.byref(pitch), ctypes.byref(lpad), ctypes.byref(win))
+    if rc != 0:
+        return None
+    return pitch.value, lpad.value, win.value
 
 
 def current_stream_ptr():

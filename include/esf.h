@@ -91,6 +91,21 @@ int esf_stem_conv(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, 
                   const float* bias, int32_t Cout, int32_t kT, int32_t kH, int32_t kW, int32_t sT, int32_t sH,
                   int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t act, const esf_view* y, void* stream);
 
+/* ---- stem on the tensor cores: the Cin = 3 conv as a banded implicit GEMM ---------------------------------
+ * Same reference ops as esf_stem_conv (which stays as the generic CUDA-core path for stems whose window does not
+ * fit, e.g. very wide kernels).  esf_stem_pack converts the FP32 NCDHW clip to BF16 channels-last rows of `pitch`
+ * elements with explicit left/right zero padding; esf_stem_igemm_create plans the GEMM (launch with
+ * esf_op_launch).  w_band: BF16 [n_pad][kT*kH*64] band matrix, bias_tiled: FP32 [n_pad] (layout documented in
+ * csrc/esf_igemm.cu and built by engine.pack_stem_band). Temporal stride must be 1. */
+int esf_stem_geometry(int32_t W, int32_t Cin, int32_t kW, int32_t sW, int32_t pW, int32_t* pitch, int32_t* lpad,
+                      int32_t* window);
+int esf_stem_pack(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
+                  int32_t lpad, void* xp, void* stream);
+int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
+                          const void* w_band, const float* bias_tiled, int32_t Cout, int32_t kT, int32_t kH,
+                          int32_t kW, int32_t sH, int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t act,
+                          const esf_view* y, esf_op** out);
+
 /* ---- MaxPool3d / AvgPool3d on channels-last BF16 (padding: -inf for max, zeros counted for avg) ---------
  * replaces ResNetBasicStem.pool_layer (stem_helper.py:169-171), the 3x3x3 stem pools
  * (stem_helper.py:243,281) and the ShuffleNet shortcut AvgPool3d (shufflenet_helper.py:68-73). */

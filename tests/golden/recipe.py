@@ -71,7 +71,7 @@ def seeded_clip(batch, frames, size, seed=1, channels=3):
 def pack_pathway_output(frames, alpha):
     """datasets/utils.py:73-112 (arch 'slowfast'): slow = frames[:, :, linspace(0, T-1, T//alpha).long()]."""
     T = frames.shape[2]
-    idx = torch.linspace(0, T - 1, T // alpha).long()
+    idx = torch.linspace(0, T - 1, T // alpha).long().to(frames.device)
     return [frames.index_select(2, idx).contiguous(), frames]
 
 

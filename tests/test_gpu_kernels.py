@@ -143,6 +143,31 @@ def test_stem_conv(esf_lib, kt, cout):
     assert err <= 6e-3 * ref.abs().max().item()   # FP32 math, BF16 output rounding (2^-8 relative worst case)
 
 
+@pytest.mark.parametrize("kt,cout,k,size", [(1, 64, 7, 64), (5, 8, 7, 64), (3, 24, 3, 48), (1, 64, 7, 224)])
+def test_stem_banded_gemm(esf_lib, kt, cout, k, size):
+    """Tensor-core stem (banded implicit GEMM) vs F.conv3d on the BF16-rounded clip and weights."""
+    g = torch.Generator().manual_seed(kt + cout)
+    B, T = (2, 8) if size < 200 else (1, 2)
+    x = torch.randn(B, 3, T, size, size, generator=g)
+    kk = (kt, k, k)
+    w = torch.randn(cout, 3, *kk, generator=g) * 0.1
+    bias = torch.randn(cout, generator=g) * 0.1
+    pad = (kt // 2, k // 2, k // 2)
+    ref = F.conv3d(x.bfloat16().float(), w.bfloat16().float(), bias, (1, 2, 2), pad).relu()
+    y = torch.full(_to_ndhwc(ref).shape, 7.0, dtype=torch.bfloat16, device=DEV)
+    plan = Plan(DEV)
+    xd = x.to(DEV)
+    plan.stem(xd, y, w.double(), bias.double(), (1, 2, 2), pad)
+    assert plan.meta[-1]["kind"] == "stem_igemm"
+    plan.launch_all()
+    torch.cuda.synchronize()
+    got = _to_ncdhw(y.cpu())
+    err = (got - ref).abs().max().item()
+    if not err <= 1e-2 * ref.abs().max().item():
+        _diagnose("stem_banded", got, ref, 1e-2 * ref.abs().max().item())
+    assert err <= 1e-2 * ref.abs().max().item()
+
+
 @pytest.mark.parametrize("C", [64, 8, 6])
 def test_pool3d(esf_lib, C):
     g = torch.Generator().manual_seed(C)
