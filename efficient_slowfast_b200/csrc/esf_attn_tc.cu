@@ -1,0 +1,583 @@
+// CMDA slow->fast position attention on the 5th-generation tensor cores (tcgen05 + TMEM), two-pass softmax.
+//
+//   out[i] = relu(bn(gamma * sum_j softmax_j(q_i . k_j) v_j + x_i)),  N = T*H*W keys per clip, no N x N matrix.
+//
+// Work split: one CTA = 256 query rows of one clip (two 128-row tiles A/B that share every K/V tile), 10 warps:
+//   warp 8   TMA producer (Q once, then a `stages`-deep ring of K~ / V^T tiles, 64 keys each)
+//   warp 9   MMA issuer: S = Q~ K~^T (M=128, N=64) into double-buffered TMEM tiles, O += P V (M=128, N=DVp)
+//   warps 0-3 / 4-7  softmax warpgroups of tile A / B, one query row per thread
+// Pass 1 computes an (approximate, hi-parts only) row maximum, pass 2 re-computes S with the hi/lo split
+//   s = q_hi.k_hi + q_lo.k_hi + q_hi.k_lo   (~FP32 logits out of BF16 MMAs; the logits are unscaled and reach 1e2)
+// and streams p = exp2((s - m) log2e) as a BF16 A-operand through shared memory into the second MMA; O accumulates in
+// TMEM and is never rescaled.  The tensor pipe is mostly idle by construction: the kernel is bound by the MUFU (exp)
+// pipe -- 16 exp/clk/SM -- which is why the second QK^T pass is affordable (exp roofline).
+//
+// Reference ops replaced: SpatialAttention.forward (wdf_attention_helper.py:33-54) + bn_s2f + ReLU + nearest x alpha
+// upsample + concat (custom_video_model_builder.py:142-146).
+#include <math_constants.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "esf_common.cuh"
+#include "esf_host.h"
+
+namespace esf {
+
+constexpr int kTcThreads = 320;
+constexpr int kTcBN = 64;          // keys per tile
+constexpr int kTcMaxStages = 6;
+constexpr int kTcMaxSteps = 16;
+constexpr int kTcSmemLimit = 232448;
+constexpr float kTcLog2e = 1.4426950408889634f;
+
+struct __align__(64) AttnTcParams {
+  CUtensorMap q_map, k_map, v_map;
+  const float* x;  // [B][N][d]
+  int B, N, T, H, W, d, alpha;
+  float gamma;
+  const float* bn_scale;
+  const float* bn_shift;
+  __nv_bfloat16* y;
+  long long ysB, ysT, ysH, ysW;
+  int DVp;       // padded value dim (MMA N of the second GEMM): 16 / 32 / 64 / 128
+  int nchunks;   // 64-element (or KQ-element when KQ < 64) chunks per Q~/K~ row
+  int chunk_el;  // elements per chunk: 32 or 64
+  uint32_t sbo, layout_type;
+  int nsteps1, nsteps2;
+  uint32_t steps1[kTcMaxSteps], steps2[kTcMaxSteps];  // a_chunk | a_k << 4 | b_chunk << 8 | b_k << 12
+  int stages;
+  uint32_t q_tile_bytes, k_tile_bytes, v_tile_bytes;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;                                   // 2 tiles x q_tile_bytes
+  uint8_t* Ks = Qs + 2 * p.q_tile_bytes;                // stages x k_tile_bytes
+  uint8_t* Vs = Ks + p.stages * p.k_tile_bytes;         // stages x v_tile_bytes
+  uint8_t* Ps = Vs + p.stages * p.v_tile_bytes;         // 2 x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + 2 * 16384);
+  uint64_t* q_full = bars;                   // 1
+  uint64_t* kv_full = q_full + 1;            // stages
+  uint64_t* kv_empty = kv_full + kTcMaxStages;
+  uint64_t* s_full = kv_empty + kTcMaxStages;  // [q][buf]
+  uint64_t* s_free = s_full + 4;
+  uint64_t* p_full = s_free + 4;             // [q]
+  uint64_t* p_free = p_full + 2;
+  uint64_t* o_full = p_free + 2;             // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int row0 = blockIdx.x * 256;
+  const int N = p.N;
+  const int nt = (N + kTcBN - 1) / kTcBN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_free[i], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&p.q_map);
+    prefetch_tmap(&p.k_map);
+    prefetch_tmap(&p.v_map);
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t chunk_bytes_q = 128 * p.chunk_el * 2;  // one chunk of a 128-row Q tile
+  const uint32_t chunk_bytes_k = kTcBN * p.chunk_el * 2;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * p.q_tile_bytes);
+      for (int q = 0; q < 2; ++q)
+        for (int ch = 0; ch < p.nchunks; ++ch)
+          tma_load_3d(Qs + q * p.q_tile_bytes + ch * chunk_bytes_q, &p.q_map, q_full, ch * p.chunk_el, row0 + q * 128, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int j = 0; j < nt; ++j) {
+          mbar_wait(&kv_empty[stage], phase ^ 1, 11);
+          mbar_arrive_expect_tx(&kv_full[stage], p.k_tile_bytes + (pass ? p.v_tile_bytes : 0));
+          for (int ch = 0; ch < p.nchunks; ++ch)
+            tma_load_3d(Ks + stage * p.k_tile_bytes + ch * chunk_bytes_k, &p.k_map, &kv_full[stage], ch * p.chunk_el,
+                        j * kTcBN, b);
+          if (pass) tma_load_3d(Vs + stage * p.v_tile_bytes, &p.v_map, &kv_full[stage], j * kTcBN, 0, b);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, kTcBN);
+      const uint32_t idesc_o = make_idesc_bf16(128, p.DVp);
+      const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs), p_addr = smem_u32(Ps);
+      auto issue_s = [&](int q, int c, int stage, const uint32_t* steps, int nsteps) {
+        // S tile number c of query tile q: TMEM buffer c & 1
+        const int buf = c & 1;
+        mbar_wait(&s_free[q * 2 + buf], ((c >> 1) & 1) ^ 1, 12);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (q * 2 + buf) * kTcBN;
+        for (int i = 0; i < nsteps; ++i) {
+          const uint32_t st = steps[i];
+          const uint32_t a = q_addr + q * p.q_tile_bytes + (st & 15) * chunk_bytes_q + ((st >> 4) & 15) * 32;
+          const uint32_t bb = k_addr + stage * p.k_tile_bytes + ((st >> 8) & 15) * chunk_bytes_k + ((st >> 12) & 15) * 32;
+          umma_bf16(d_tmem, make_kmajor_desc(a, p.sbo, p.layout_type), make_kmajor_desc(bb, p.sbo, p.layout_type),
+                    idesc_s, i != 0);
+        }
+        umma_commit(&s_full[q * 2 + buf]);
+      };
+      mbar_wait(q_full, 0, 13);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      // pass 1: row maxima from the hi parts only
+      for (int j = 0; j < nt; ++j) {
+        mbar_wait(&kv_full[stage], phase, 14);
+        tc_fence_after();
+        issue_s(0, j, stage, p.steps1, p.nsteps1);
+        issue_s(1, j, stage, p.steps1, p.nsteps1);
+        umma_commit(&kv_empty[stage]);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      // pass 2: S one tile ahead of P.V
+      int s_stage = stage;          // stage of S tile j+1
+      uint32_t s_phase = phase;
+      mbar_wait(&kv_full[s_stage], s_phase, 15);
+      tc_fence_after();
+      issue_s(0, nt + 0, s_stage, p.steps2, p.nsteps2);
+      issue_s(1, nt + 0, s_stage, p.steps2, p.nsteps2);
+      for (int j = 0; j < nt; ++j) {
+        const int pv_stage = s_stage;
+        if (++s_stage == p.stages) {
+          s_stage = 0;
+          s_phase ^= 1;
+        }
+        if (j + 1 < nt) {
+          mbar_wait(&kv_full[s_stage], s_phase, 16);
+          tc_fence_after();
+          issue_s(0, nt + j + 1, s_stage, p.steps2, p.nsteps2);
+          issue_s(1, nt + j + 1, s_stage, p.steps2, p.nsteps2);
+        }
+        for (int q = 0; q < 2; ++q) {
+          mbar_wait(&p_full[q], j & 1, 17);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + 4 * kTcBN + q * p.DVp;
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, make_kmajor_desc(p_addr + q * 16384 + k * 32, 1024, 2),
+                      make_kmajor_desc(v_addr + pv_stage * p.v_tile_bytes + k * 32, 1024, 2), idesc_o, (j | k) != 0);
+          umma_commit(&p_free[q]);
+        }
+        umma_commit(&kv_empty[pv_stage]);
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int q = warp >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // row inside the 128-row tile
+    const int n = row0 + q * 128 + r;   // query position
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const bool tail = (N % kTcBN) != 0;
+    float m = -CUDART_INF_F;
+    // pass 1
+    for (int j = 0; j < nt; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&s_full[q * 2 + buf], (j >> 1) & 1, 18);
+      tc_fence_after();
+      float v[64];
+      tmem_ld32(lane_addr + (q * 2 + buf) * kTcBN, v);
+      tmem_ld32(lane_addr + (q * 2 + buf) * kTcBN + 32, v + 32);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[q * 2 + buf]);
+      if (tail && j == nt - 1) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (j * kTcBN + i >= N) v[i] = -CUDART_INF_F;
+      }
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) m = fmaxf(m, fmaxf(v[i], v[i + 1]));
+    }
+    const float ms = m * kTcLog2e;
+    float l = 0.f;
+    uint8_t* prow = Ps + q * 16384;
+    // pass 2
+    for (int j = 0; j < nt; ++j) {
+      const int c = nt + j;
+      const int buf = c & 1;
+      mbar_wait(&s_full[q * 2 + buf], (c >> 1) & 1, 19);
+      tc_fence_after();
+      float v[64];
+      tmem_ld32(lane_addr + (q * 2 + buf) * kTcBN, v);
+      tmem_ld32(lane_addr + (q * 2 + buf) * kTcBN + 32, v + 32);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[q * 2 + buf]);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = fast_exp2(fmaf(v[i], kTcLog2e, -ms));
+      if (tail && j == nt - 1) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (j * kTcBN + i >= N) v[i] = 0.f;
+      }
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        s0 += v[i];
+        s1 += v[i + 1];
+      }
+      l += s0 + s1;
+      mbar_wait(&p_free[q], (j & 1) ^ 1, 20);  // P.V of the previous key tile no longer reads the P buffer
+#pragma unroll
+      for (int ck = 0; ck < 8; ++ck) {
+        uint4 o;
+        o.x = pack_bf16x2(v[8 * ck + 0], v[8 * ck + 1]);
+        o.y = pack_bf16x2(v[8 * ck + 2], v[8 * ck + 3]);
+        o.z = pack_bf16x2(v[8 * ck + 4], v[8 * ck + 5]);
+        o.w = pack_bf16x2(v[8 * ck + 6], v[8 * ck + 7]);
+        *reinterpret_cast<uint4*>(prow + swz(r * 128 + ck * 16, 7)) = o;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[q]);
+    }
+    // epilogue: O / l, gamma * O + x, BN, ReLU, x alpha temporal replication
+    mbar_wait(o_full, 0, 21);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int HW = p.H * p.W;
+    const bool valid = n < N;
+    const int t = valid ? n / HW : 0, hw = valid ? n % HW : 0, hh = hw / p.W, ww = hw % p.W;
+    __nv_bfloat16* yb = p.y + b * p.ysB + hh * p.ysH + ww * p.ysW;
+    const float* xr = p.x + ((long long)b * N + (valid ? n : 0)) * p.d;
+    const bool vec_ok = (p.d % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) && (p.ysW % 8 == 0) &&
+                        (p.ysH % 8 == 0) && (p.ysT % 8 == 0) && (p.ysB % 8 == 0);
+    for (int c0 = 0; c0 < p.DVp; c0 += 16) {
+      float o[16];
+      tmem_ld16(lane_addr + 4 * kTcBN + q * p.DVp + c0, o);
+      if (!valid) continue;
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const int ch = c0 + jj;
+        if (ch < p.d) {
+          const float a = fmaf(p.gamma, o[jj] * inv, xr[ch]);
+          o[jj] = fmaxf(fmaf(a, __ldg(p.bn_scale + ch), __ldg(p.bn_shift + ch)), 0.f);
+        }
+      }
+      for (int rep = 0; rep < p.alpha; ++rep) {
+        __nv_bfloat16* yp = yb + (long long)(t * p.alpha + rep) * p.ysT + c0;
+        if (vec_ok) {
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            if (c0 + h8 * 8 < p.d) {
+              uint4 pk;
+              pk.x = pack_bf16x2(o[h8 * 8 + 0], o[h8 * 8 + 1]);
+              pk.y = pack_bf16x2(o[h8 * 8 + 2], o[h8 * 8 + 3]);
+              pk.z = pack_bf16x2(o[h8 * 8 + 4], o[h8 * 8 + 5]);
+              pk.w = pack_bf16x2(o[h8 * 8 + 6], o[h8 * 8 + 7]);
+              *reinterpret_cast<uint4*>(yp + h8 * 8) = pk;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj)
+            if (c0 + jj < p.d) yp[jj] = __float2bfloat16(o[jj]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+struct TcGeom {
+  int DVp, KQ, chunk_el, nchunks, mode;  // mode 0: d <= 8 (4 x 8 segments), 1: hi|lo halves, 2: unsplit
+};
+static bool tc_geom(int d, TcGeom* g) {
+  if (d <= 0 || d > 128) return false;
+  if (d <= 8) *g = {16, 32, 32, 1, 0};
+  else if (d <= 16) *g = {16, 32, 32, 1, 1};
+  else if (d <= 32) *g = {32, 64, 64, 1, 1};
+  else if (d <= 64) *g = {64, 128, 64, 2, 1};
+  else *g = {128, 128, 64, 2, 2};
+  return true;
+}
+struct TcLayout {
+  long long q_off, k_off, v_off, x_off, total;
+  int Npad;
+};
+static TcLayout tc_layout(int B, int N, int d, const TcGeom& g) {
+  auto al = [](long long v) { return (v + 1023) & ~1023LL; };
+  TcLayout L;
+  L.Npad = (N + 7) & ~7;
+  const long long rows = (long long)B * N;
+  L.q_off = 0;
+  L.k_off = al(L.q_off + rows * g.KQ * 2);
+  L.v_off = al(L.k_off + rows * g.KQ * 2);
+  L.x_off = al(L.v_off + (long long)B * g.DVp * L.Npad * 2);
+  L.total = al(L.x_off + rows * d * 4);
+  return L;
+}
+
+__device__ __forceinline__ __nv_bfloat16 bf_hi(float v) { return __float2bfloat16(v); }
+__device__ __forceinline__ __nv_bfloat16 bf_lo(float v) { return __float2bfloat16(v - __bfloat162float(__float2bfloat16(v))); }
+
+// proj rows are [x_d | q | k | v] (d each, FP32)
+__global__ void __launch_bounds__(256) attn_tc_pack_qk(const float* __restrict__ proj, long long rows, int d, int KQ,
+                                                       int mode, __nv_bfloat16* __restrict__ Q,
+                                                       __nv_bfloat16* __restrict__ K) {
+  const long long total = rows * KQ;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / KQ;
+    const int e = i % KQ;
+    const float* pr = proj + r * 4 * d;
+    __nv_bfloat16 qv = __float2bfloat16(0.f), kv = qv;
+    if (mode == 0) {
+      const int seg = e >> 3, jj = e & 7;
+      if (jj < d && seg < 3) {
+        const float q = pr[d + jj], k = pr[2 * d + jj];
+        qv = seg == 1 ? bf_lo(q) : bf_hi(q);
+        kv = seg == 2 ? bf_lo(k) : bf_hi(k);
+      }
+    } else if (mode == 1) {
+      const int half = KQ >> 1;
+      const int part = e / half, jj = e % half;
+      if (jj < d) {
+        const float q = pr[d + jj], k = pr[2 * d + jj];
+        qv = part ? bf_lo(q) : bf_hi(q);
+        kv = part ? bf_lo(k) : bf_hi(k);
+      }
+    } else {
+      if (e < d) {
+        qv = bf_hi(pr[d + e]);
+        kv = bf_hi(pr[2 * d + e]);
+      }
+    }
+    Q[i] = qv;
+    K[i] = kv;
+  }
+}
+// V^T[b][j][n] (j < DVp, zero rows beyond d) and X[b][n][j]
+__global__ void __launch_bounds__(256) attn_tc_pack_vx(const float* __restrict__ proj, int B, int N, int Npad, int d,
+                                                       int DVp, __nv_bfloat16* __restrict__ VT, float* __restrict__ X) {
+  const long long total = (long long)B * DVp * Npad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = i % Npad;
+    const long long t = i / Npad;
+    const int j = t % DVp;
+    const int b = t / DVp;
+    float v = 0.f;
+    if (n < N && j < d) {
+      const float* pr = proj + ((long long)b * N + n) * 4 * d;
+      v = pr[3 * d + j];
+      X[((long long)b * N + n) * d + j] = pr[j];
+    }
+    VT[i] = __float2bfloat16(v);
+  }
+}
+
+struct AttnTcOp : esf_op {
+  AttnTcParams params;
+  dim3 grid;
+  int smem_bytes = 0;
+  int launch(cudaStream_t stream) override {
+    attn_tc_kernel<<<grid, kTcThreads, smem_bytes, stream>>>(params);
+    return check_launch("attn_tc_kernel");
+  }
+};
+
+static int encode3(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
+                   uint64_t s2_bytes, uint32_t b0, uint32_t b1, CUtensorMapSwizzle sw, const char* what) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1_bytes, s2_bytes};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
+  return ESF_OK;
+}
+
+}  // namespace esf
+
+using namespace esf;
+
+extern "C" int64_t esf_attn_tc_pack_bytes(int32_t B, int32_t N, int32_t d) {
+  TcGeom g;
+  if (B <= 0 || N <= 0 || !tc_geom(d, &g)) return set_error(ESF_ERR_UNSUPPORTED, "esf_attn_tc: unsupported head dim %d", d);
+  return tc_layout(B, N, d, g).total;
+}
+
+extern "C" int esf_attn_tc_pack(const float* proj, int32_t B, int32_t N, int32_t d, void* packed, void* stream) {
+  ESF_CHECK_ARG(proj && packed && B > 0 && N > 0, "esf_attn_tc_pack: null/bad argument");
+  TcGeom g;
+  if (!tc_geom(d, &g)) return set_error(ESF_ERR_UNSUPPORTED, "esf_attn_tc_pack: unsupported head dim %d", d);
+  const TcLayout L = tc_layout(B, N, d, g);
+  char* base = static_cast<char*>(packed);
+  const long long rows = (long long)B * N;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto grid_of = [](long long total) { return (int)std::max(1LL, std::min<long long>((total + 255) / 256, 148LL * 32)); };
+  attn_tc_pack_qk<<<grid_of(rows * g.KQ), 256, 0, s>>>(proj, rows, d, g.KQ, g.mode,
+                                                        reinterpret_cast<__nv_bfloat16*>(base + L.q_off),
+                                                        reinterpret_cast<__nv_bfloat16*>(base + L.k_off));
+  int rc = check_launch("attn_tc_pack_qk");
+  if (rc != ESF_OK) return rc;
+  attn_tc_pack_vx<<<grid_of((long long)B * g.DVp * L.Npad), 256, 0, s>>>(
+      proj, B, N, L.Npad, d, g.DVp, reinterpret_cast<__nv_bfloat16*>(base + L.v_off),
+      reinterpret_cast<float*>(base + L.x_off));
+  return check_launch("attn_tc_pack_vx");
+}
+
+extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d,
+                                  float gamma, const float* bn_scale, const float* bn_shift, int32_t alpha,
+                                  const esf_view* y_fast_slice, esf_op** out) {
+  ESF_CHECK_ARG(packed && bn_scale && bn_shift && view_ok(y_fast_slice) && out, "esf_attn_tc_create: null/bad argument");
+  TcGeom g;
+  if (!tc_geom(d, &g)) return set_error(ESF_ERR_UNSUPPORTED, "esf_attn_tc_create: unsupported head dim %d", d);
+  const esf_view* y = y_fast_slice;
+  ESF_CHECK_ARG(y->B == B && y->T == T * alpha && y->H == H && y->W == W && y->C == d,
+                "esf_attn_tc_create: output slice (%d,%d,%d,%d,%d) != (%d,%d,%d,%d,%d)", y->B, y->T, y->H, y->W, y->C,
+                B, T * alpha, H, W, d);
+  const int N = T * H * W;
+  const TcLayout L = tc_layout(B, N, d, g);
+  char* base = static_cast<char*>(const_cast<void*>(packed));
+  AttnTcOp* op = new (std::nothrow) AttnTcOp();
+  if (!op) return set_error(ESF_ERR_ARG, "out of host memory");
+  AttnTcParams& p = op->params;
+  memset(&p, 0, sizeof(p));
+  p.x = reinterpret_cast<const float*>(base + L.x_off);
+  p.B = B, p.N = N, p.T = T, p.H = H, p.W = W, p.d = d, p.alpha = alpha, p.gamma = gamma;
+  p.bn_scale = bn_scale, p.bn_shift = bn_shift;
+  p.y = static_cast<__nv_bfloat16*>(y->ptr);
+  p.ysB = y->sB, p.ysT = y->sT, p.ysH = y->sH, p.ysW = y->sW;
+  p.DVp = g.DVp, p.nchunks = g.nchunks, p.chunk_el = g.chunk_el;
+  const int RB = g.chunk_el * 2;
+  p.sbo = 8 * RB;
+  p.layout_type = RB == 128 ? 2 : 4;
+  auto step = [](int ac, int ak, int bc, int bk) { return (uint32_t)(ac | (ak << 4) | (bc << 8) | (bk << 12)); };
+  int n1 = 0, n2 = 0;
+  if (g.mode == 0) {
+    // q~ = [q_hi q_lo | q_hi 0], k~ = [k_hi k_hi | k_lo 0]: step 0 = (q_hi+q_lo).k_hi, step 1 = q_hi.k_lo
+    p.steps1[n1++] = step(0, 0, 0, 0);
+    p.steps2[n2++] = step(0, 0, 0, 0);
+    p.steps2[n2++] = step(0, 1, 0, 1);
+  } else if (g.mode == 1) {
+    const int half = g.KQ / 2;            // elements of the hi (and of the lo) part
+    const int hs = half / 16;             // K steps per part
+    auto loc = [&](int part, int k, int* chunk, int* koff) {  // K step k of part -> (chunk, 32 B offset in chunk)
+      const int el = part * half + k * 16;
+      *chunk = el / g.chunk_el;
+      *koff = (el % g.chunk_el) / 16;
+    };
+    for (int k = 0; k < hs; ++k) {
+      int ac, ak, bc, bk;
+      loc(0, k, &ac, &ak), loc(0, k, &bc, &bk);
+      p.steps1[n1++] = step(ac, ak, bc, bk);
+      p.steps2[n2++] = step(ac, ak, bc, bk);  // hi.hi
+    }
+    for (int k = 0; k < hs; ++k) {
+      int ac, ak, bc, bk;
+      loc(1, k, &ac, &ak), loc(0, k, &bc, &bk);
+      p.steps2[n2++] = step(ac, ak, bc, bk);  // lo.hi
+    }
+    for (int k = 0; k < hs; ++k) {
+      int ac, ak, bc, bk;
+      loc(0, k, &ac, &ak), loc(1, k, &bc, &bk);
+      p.steps2[n2++] = step(ac, ak, bc, bk);  // hi.lo
+    }
+  } else {
+    for (int k = 0; k < g.KQ / 16; ++k) {
+      const int c = (k * 16) / g.chunk_el, ko = ((k * 16) % g.chunk_el) / 16;
+      p.steps1[n1++] = step(c, ko, c, ko);
+      p.steps2[n2++] = step(c, ko, c, ko);
+    }
+  }
+  p.nsteps1 = n1, p.nsteps2 = n2;
+  p.q_tile_bytes = 128 * g.KQ * 2;
+  p.k_tile_bytes = kTcBN * g.KQ * 2;
+  p.v_tile_bytes = g.DVp * 128;
+  const int fixed = 1024 + 2 * (int)p.q_tile_bytes + 2 * 16384 + 512;
+  int stages = (kTcSmemLimit - fixed) / (int)(p.k_tile_bytes + p.v_tile_bytes);
+  p.stages = std::max(2, std::min(stages, kTcMaxStages));
+  op->smem_bytes = fixed + p.stages * (int)(p.k_tile_bytes + p.v_tile_bytes);
+  op->grid = dim3(cdiv(N, 256), B);
+  const CUtensorMapSwizzle sw = RB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  int rc = encode3(&p.q_map, base + L.q_off, g.KQ, N, B, (uint64_t)g.KQ * 2, (uint64_t)N * g.KQ * 2, g.chunk_el, 128, sw,
+                   "attention Q");
+  if (rc == ESF_OK)
+    rc = encode3(&p.k_map, base + L.k_off, g.KQ, N, B, (uint64_t)g.KQ * 2, (uint64_t)N * g.KQ * 2, g.chunk_el, kTcBN, sw,
+                 "attention K");
+  if (rc == ESF_OK)
+    rc = encode3(&p.v_map, base + L.v_off, N, g.DVp, B, (uint64_t)L.Npad * 2, (uint64_t)g.DVp * L.Npad * 2, kTcBN, g.DVp,
+                 CU_TENSOR_MAP_SWIZZLE_128B, "attention V^T");
+  if (rc == ESF_OK) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+      if (e != cudaSuccess) rc = set_error(ESF_ERR_CUDA, "cudaFuncSetAttribute(attn_tc) failed: %s", cudaGetErrorString(e));
+      else attr_set = true;
+    }
+  }
+  if (rc != ESF_OK) {
+    delete op;
+    return rc;
+  }
+  *out = op;
+  return ESF_OK;
+}

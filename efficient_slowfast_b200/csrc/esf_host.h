@@ -40,4 +40,17 @@ inline bool view_ok(const esf_view* v) {
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+int num_sms();  // SM count of the current device (cached); 0 when there is no device
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();  // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda)
+
 }  // namespace esf
+
+// One planned kernel launch behind the opaque esf_op handle of the C ABI.
+struct esf_op {
+  virtual int launch(cudaStream_t stream) = 0;
+  virtual ~esf_op() {}
+};

@@ -30,7 +30,7 @@ constexpr int kMmaWarp = 9;
 constexpr int kThreads = 320;
 constexpr int kMaxStages = 8;
 constexpr int kMaxAMaps = 8;
-constexpr int kMaxTaps = 32;
+constexpr int kMaxTaps = 64;
 constexpr int kAStageBytes = 16384;   // 128 rows x 128 B
 constexpr int kOutStageBytes = 16384; // 128 rows x 128 B
 constexpr int kTmemCols = 512;
@@ -58,7 +58,7 @@ struct __align__(64) IgemmParams {
   int num_tiles;
   // "column blocks" (banded stem GEMM): an extra tile index that shifts the innermost coordinate of the
   // activation loads and of the output stores; ncb == 1 and zero strides for ordinary convolutions
-  int ncb, a_cb_stride, out_cb_stride;
+  int ncb, a_cb_stride, out_cb_w;  // out_cb_w: W-coordinate step of the output store per column block
 };
 
 struct TileCoord {
@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     if (p.has_res && leader && blockIdx.x < p.num_tiles) {
       const TileCoord tc = tile_coord(p, blockIdx.x);
       mbar_arrive_expect_tx(&res_full[0], p.res_bytes);
-      tma_load_5d(smem_out, &p.res_map, &res_full[0], tc.cb * p.out_cb_stride + tc.n_idx * p.n_tile, tc.w0, tc.h0,
-                  tc.t0, tc.b0);
+      tma_load_5d(smem_out, &p.res_map, &res_full[0], tc.n_idx * p.n_tile, tc.w0 + tc.cb * p.out_cb_w, tc.h0, tc.t0,
+                  tc.b0);
     }
     int iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         fence_proxy_async_smem();
         epi_bar_sync(1);
         if (leader) {
-          tma_store_5d(&p.out_map, stage_buf, tc.cb * p.out_cb_stride + tc.n_idx * p.n_tile + s * p.slab_cols, tc.w0,
+          tma_store_5d(&p.out_map, stage_buf, tc.n_idx * p.n_tile + s * p.slab_cols, tc.w0 + tc.cb * p.out_cb_w,
                        tc.h0, tc.t0, tc.b0);
           tma_store_commit();
           tma_store_wait_read<1>();  // the previous slab's store no longer reads the other staging buffer
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
               const TileCoord nc = tile_coord(p, ntile);
               mbar_arrive_expect_tx(&res_full[buf ^ 1], p.res_bytes);
               tma_load_5d(smem_out + (buf ^ 1) * kOutStageBytes, &p.res_map, &res_full[buf ^ 1],
-                          nc.cb * p.out_cb_stride + nc.n_idx * p.n_tile + ns * p.slab_cols, nc.w0, nc.h0, nc.t0,
+                          nc.n_idx * p.n_tile + ns * p.slab_cols, nc.w0 + nc.cb * p.out_cb_w, nc.h0, nc.t0,
                           nc.b0);
             }
           }
@@ -304,11 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
+EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (fn) return fn;
   void* p = nullptr;
@@ -351,18 +347,8 @@ static int encode_act_map(CUtensorMap* m, CUtensorMapDataType dt, int esize, voi
   return ESF_OK;
 }
 
-}  // namespace esf
-
-struct esf_op {
-  esf::IgemmParams params;
-  int grid;
-  int smem_bytes;
-};
-
-using namespace esf;
-
 static int g_num_sms = 0;
-static int num_sms() {
+int num_sms() {
   if (g_num_sms > 0) return g_num_sms;
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -371,7 +357,21 @@ static int num_sms() {
   return n;
 }
 
-static int finish_op(esf_op* op) {
+struct IgemmOp : esf_op {
+  IgemmParams params;
+  int grid = 0;
+  int smem_bytes = 0;
+  int launch(cudaStream_t stream) override {
+    igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(params);
+    return check_launch("igemm_kernel");
+  }
+};
+
+}  // namespace esf
+
+using namespace esf;
+
+static int finish_op(IgemmOp* op) {
   const int sms = num_sms();
   if (sms <= 0) return set_error(ESF_ERR_CUDA, "no CUDA device");
   op->grid = std::min(op->params.num_tiles, sms);
@@ -444,7 +444,7 @@ extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
     ESF_CHECK_ARG(d->res.B == y.B && d->res.T == y.T && d->res.H == y.H && d->res.W == y.W && d->res.C == y.C,
                   "esf_conv_igemm_create: residual view must match the output view");
 
-  esf_op* op = new (std::nothrow) esf_op();
+  IgemmOp* op = new (std::nothrow) IgemmOp();
   if (!op) return set_error(ESF_ERR_ARG, "out of host memory");
   IgemmParams& p = op->params;
   memset(&p, 0, sizeof(p));
@@ -468,7 +468,7 @@ extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
   }
   p.num_tiles = (int)ntiles;
   p.ncb = 1;
-  p.a_cb_stride = p.out_cb_stride = 0;
+  p.a_cb_stride = p.out_cb_w = 0;
   const int row_bytes = kc * 2;
   p.a_bytes = p.rows * row_bytes;
   p.b_bytes = n_tile * row_bytes;
@@ -617,10 +617,12 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
   const int Wo = (W + 2 * pW - kW) / sW + 1;
   ESF_CHECK_ARG(y->B == B && y->T == To && y->H == Ho && y->W == Wo && y->C == Cout && y->sW == Cout,
                 "esf_stem_igemm_create: output must be a dense (B,%d,%d,%d,%d) channels-last tensor", To, Ho, Wo, Cout);
+  if (Wo % kStemWB != 0)
+    return set_error(ESF_ERR_UNSUPPORTED, "banded stem needs an output width that is a multiple of %d (got %d)", kStemWB, Wo);
   const int num_taps = kT * kH;
   ESF_CHECK_ARG(num_taps <= kMaxTaps, "esf_stem_igemm_create: %d (kT*kH) taps > %d", num_taps, kMaxTaps);
 
-  esf_op* op = new (std::nothrow) esf_op();
+  IgemmOp* op = new (std::nothrow) IgemmOp();
   if (!op) return set_error(ESF_ERR_ARG, "out of host memory");
   IgemmParams& p = op->params;
   memset(&p, 0, sizeof(p));
@@ -633,7 +635,7 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
   p.rows = p.bw * p.bh * p.bt * p.bb;
   p.ncb = cdiv(Wo, kStemWB);
   p.a_cb_stride = kStemWB * sW * Cin;
-  p.out_cb_stride = kStemWB * Cout;
+  p.out_cb_w = 1;
   const long long ntiles = (long long)p.ncb * p.th * p.tt * p.tb * p.n_tiles;
   if (ntiles > 0x7fffffffLL) {
     delete op;
@@ -697,8 +699,9 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
     }
   }
   if (rc == ESF_OK)
-    rc = encode_act_map(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y->ptr, (int64_t)Wo * Cout, 1, Ho, To, B,
-                        y->sH, y->sH, y->sT, y->sB, p.slab_cols, 1, p.bh, p.bt, p.bb,
+    // dims (8*Cout, Wo/8, Ho, To, B): the column block is the W coordinate, so a tile wider than 8*Cout is clipped
+    rc = encode_act_map(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y->ptr, (int64_t)kStemWB * Cout, Wo / kStemWB,
+                        Ho, To, B, (int64_t)kStemWB * Cout, y->sH, y->sT, y->sB, p.slab_cols, 1, p.bh, p.bt, p.bb,
                         swizzle_for_row_bytes(out_row_bytes), "stem output");
   if (rc == ESF_OK) {
     p.res_map = p.out_map;
@@ -714,8 +717,7 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
 
 extern "C" int esf_op_launch(esf_op* op, void* stream) {
   ESF_CHECK_ARG(op, "esf_op_launch: null op");
-  igemm_kernel<<<op->grid, kThreads, op->smem_bytes, static_cast<cudaStream_t>(stream)>>>(op->params);
-  return check_launch("igemm_kernel");
+  return op->launch(static_cast<cudaStream_t>(stream));
 }
 
 extern "C" void esf_op_destroy(esf_op* op) { delete op; }

@@ -89,6 +89,7 @@ class Plan:
         self.launches_per_run = 0
         self.buffers = {}     # name -> activation tensor (for tests / debugging)
         self.meta = []        # one dict per op: kind, label, algorithmic flops / bytes / exps, launches
+        self.attn_impl = "tcgen05"   # "tcgen05" (TMEM, two-pass) or "mma_sync" (register-resident, online softmax)
 
     # ---------------------------------------------------------------- memory
     def act(self, B, T, H, W, C, name=None, dtype=torch.bfloat16):
@@ -235,6 +236,27 @@ class Plan:
         self.conv_igemm(x_slow, proj, w_all, b_all, out_dtype=rt.F32)
         L = rt.lib()
         N = T * H * W
+        if self.attn_impl == "tcgen05":
+            nbytes = int(L.esf_attn_tc_pack_bytes(B, N, d))
+            if nbytes < 0:
+                rt.check(nbytes, "esf_attn_tc_pack_bytes")
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.keep.append(packed)
+            scale, shift = bn_affine(bn)
+            sc, sh = self.tensor(scale), self.tensor(shift)
+            gamma = float(att.gamma.detach().float().item())
+            yv = rt.view(y_slice)
+            h = ctypes.c_void_p()
+            rt.check(L.esf_attn_tc_create(packed.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(), sh.data_ptr(), alpha,
+                                          ctypes.byref(yv), ctypes.byref(h)), "esf_attn_tc_create")
+            self.handles.append(h)
+            self._add(lambda s: rt.check(L.esf_attn_tc_pack(proj.data_ptr(), B, N, d, packed.data_ptr(), s),
+                                         "esf_attn_tc_pack"), "attn_pack", "N=%d d=%d" % (N, d),
+                      nbytes=self._nbytes(proj) + nbytes, launches=2)
+            self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "attention",
+                      "N=%d d=%d" % (N, d), flops=4.0 * B * N * N * d, exps=float(B) * N * N,
+                      nbytes=nbytes + self._nbytes(y_slice))
+            return
         nbytes = int(L.esf_attn_pack_bytes(B, N, d))
         if nbytes < 0:
             rt.check(nbytes, "esf_attn_pack_bytes")

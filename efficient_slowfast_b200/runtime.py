@@ -72,9 +72,13 @@ def lib():
     L.esf_attn_pack_bytes.restype = i64
     L.esf_attn_pack.argtypes = [vp, i32, i32, i32, vp, vp]
     L.esf_attn_fused.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, i32, P(EsfView), vp]
+    L.esf_attn_tc_pack_bytes.argtypes = [i32, i32, i32]
+    L.esf_attn_tc_pack_bytes.restype = i64
+    L.esf_attn_tc_pack.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.esf_attn_tc_create.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, i32, P(EsfView), P(vp)]
     L.esf_head_pool.argtypes = [P(EsfView), P(EsfView), vp, vp]
     L.esf_head_fc.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp]
-    for name in ("esf_stem_geometry", "esf_stem_pack", "esf_stem_igemm_create", "esf_igemm_geometry",
+    for name in ("esf_attn_tc_pack", "esf_attn_tc_create", "esf_stem_geometry", "esf_stem_pack", "esf_stem_igemm_create", "esf_igemm_geometry",
                  "esf_conv_igemm_create", "esf_op_launch", "esf_conv_direct", "esf_stem_conv",
                  "esf_pool3d", "esf_eca_fuse", "esf_attn_pack", "esf_attn_fused", "esf_head_pool", "esf_head_fc"):
         getattr(L, name).restype = ctypes.c_int
@@ -115,7 +119,7 @@ def stem_geometry(W, cin, kW, sW, pW):
     """(pitch, lpad, window) of the packed stem rows, or None when the banded-GEMM stem does not apply."""
     pitch, lpad, win = (ctypes.c_int32() for _ in range(3))
     rc = lib().esf_stem_geometry(W, cin, kW, sW, pW, ctypes.byref(pitch), ctypes.byref(lpad), ctypes.byref(win))
-    if rc != 0:
+    if rc != 0 or ((W + 2 * pW - kW) // sW + 1) % 8 != 0:
         return None
     return pitch.value, lpad.value, win.value
 

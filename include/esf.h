@@ -134,6 +134,15 @@ int esf_attn_fused(const void* packed, int32_t B, int32_t T, int32_t H, int32_t 
                    const float* bn_scale, const float* bn_shift, int32_t alpha, const esf_view* y_fast_slice,
                    void* stream);
 
+/* ---- the same attention on the tcgen05 tensor cores (TMEM accumulators, two-pass softmax) -------------------
+ * Preferred path; any head dim d <= 128.  esf_attn_tc_pack writes Q~/K~ (BF16 hi/lo split rows), V^T and x_d into
+ * `packed` (esf_attn_tc_pack_bytes bytes); esf_attn_tc_create plans the fused kernel (launch: esf_op_launch). */
+int64_t esf_attn_tc_pack_bytes(int32_t B, int32_t N, int32_t d);
+int esf_attn_tc_pack(const float* proj, int32_t B, int32_t N, int32_t d, void* packed, void* stream);
+int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d, float gamma,
+                       const float* bn_scale, const float* bn_shift, int32_t alpha, const esf_view* y_fast_slice,
+                       esf_op** out);
+
 /* ---- head: global average pool of each pathway -> concat -> Linear -> softmax/ReLU/none -----------------
  * replaces ResNetBasicHead.forward eval branch (head_helper.py:198-223) and the efficient heads'
  * pool+classifier tails.  feat: FP32 scratch (B, C0 + C1).  act: 0 none (logits), 1 softmax, 2 relu, 3 sigmoid. */

@@ -12,6 +12,10 @@ out every bottleneck and every attention branch), so parity runs use perturbed w
     "stress" recipe) a perturbation grows ~3x per stage -- 16-bit rounding noise of 2^-9 reaches 30 % of the
     activations at res5 in ANY implementation (measured on CPU by rounding the oracle's activations) --
     so that recipe is kept only as a stress fixture with an argmax check and a loose bound;
+  * the position-attention query/key convs are scaled by 0.25 in the "trained" recipe: with c2_msra_fill weights the
+    un-normalised logits q.k reach |s| ~ 200 on calibrated activations, the softmax is one-hot and the attention
+    output flips between keys under perturbations of 1e-3 (a property of that random draw, not of an
+    implementation); at |s| ~ 10 every key still matters and the branch is well conditioned;
   * BN running statistics are calibrated by the generator with train-mode forwards of the reference model and are
     STORED in the fixture (they cannot be regenerated without the reference).
 """
@@ -50,6 +54,8 @@ def seeded_state_dict(template, seed=0, bn_stats=None, stress=False):
         elif leaf == "weight" and len(shape) == 5:
             fan_out = shape[0] * shape[2] * shape[3] * shape[4]
             t = torch.randn(shape, generator=g) * (2.0 / fan_out) ** 0.5
+            if (".query_conv." in key or ".key_conv." in key) and not stress:
+                t = t * 0.25   # keeps the un-scaled q.k logits at |s| ~ 10 instead of ~ 200 (see module docstring)
         elif leaf == "weight" and len(shape) == 3:
             t = torch.rand(shape, generator=g) - 0.5
         elif leaf == "weight" and len(shape) == 2:
@@ -91,4 +97,7 @@ CASES = {
     "slowfast_r50_stress": dict(
         model="SlowFast", yaml="configs/Kinetics/SLOWFAST_4x16_R50.yaml", stress=True,
         opts=["MULTIGRID.SHORT_CYCLE", True], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),
+    "dual_r50_stress": dict(
+        model="SlowFastDualAttention", yaml="configs/Kinetics/SLOWFAST_DUAL_8x8_R50_stepwise_multigrid.yaml",
+        stress=True, opts=[], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),
 }

@@ -18,7 +18,7 @@ def case_cfg(name):
     """Our own cfg for a golden case (mirrors the YAML + overrides listed in recipe.CASES)."""
     import efficient_slowfast_b200 as esf
 
-    if name == "dual_r50":
+    if name in ("dual_r50", "dual_r50_stress"):
         cfg = esf.slowfast_dual_8x8_r50_cfg()
     elif name in ("slowfast_r50", "slowfast_r50_stress"):
         cfg = esf.slowfast_4x16_r50_cfg()

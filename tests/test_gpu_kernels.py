@@ -259,6 +259,45 @@ def test_attention_fused(esf_lib, d, T, H, W, qk_scale):
     assert (ybuf[..., d:] == 0).all()
 
 
+@pytest.mark.parametrize("d,T,H,W,qk_scale", [(8, 2, 9, 8, 1.0), (8, 2, 16, 16, 4.0), (32, 2, 12, 11, 1.0),
+                                              (32, 4, 16, 8, 2.0), (64, 2, 7, 7, 1.0), (128, 2, 7, 7, 0.5),
+                                              (16, 1, 9, 9, 1.0), (3, 2, 8, 8, 1.0), (12, 1, 20, 20, 1.0),
+                                              (24, 2, 14, 14, 1.0), (32, 8, 14, 14, 1.0)])
+def test_attention_tcgen05(esf_lib, d, T, H, W, qk_scale):
+    """tcgen05/TMEM two-pass attention vs FP64 softmax attention on the same FP32 projections."""
+    g = torch.Generator().manual_seed(d + T)
+    B, alpha = 2, 4
+    N = T * H * W
+    proj = torch.randn(B * N, 4 * d, generator=g)
+    proj[:, d:3 * d] *= qk_scale / d ** 0.25
+    gamma = 0.7
+    scale = torch.rand(d, generator=g) + 0.5
+    shift = torch.rand(d, generator=g) - 0.5
+    ref = _attention_reference(proj, B, T, H, W, d, gamma, scale, shift, alpha)
+    L = esf_lib
+    nbytes = L.esf_attn_tc_pack_bytes(B, N, d)
+    assert nbytes > 0
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    pj = proj.to(DEV)
+    cpad = (2 * d + 7) // 8 * 8
+    ybuf = torch.zeros(B, T * alpha, H, W, cpad, dtype=torch.bfloat16, device=DEV)
+    yv = rt.view(ybuf[..., :d])
+    sc, sh = scale.to(DEV), shift.to(DEV)
+    s = rt.current_stream_ptr()
+    h = ctypes.c_void_p()
+    rt.check(L.esf_attn_tc_pack(pj.data_ptr(), B, N, d, packed.data_ptr(), s))
+    rt.check(L.esf_attn_tc_create(packed.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(), sh.data_ptr(), alpha,
+                                  ctypes.byref(yv), ctypes.byref(h)))
+    rt.check(L.esf_op_launch(h, s))
+    torch.cuda.synchronize()
+    L.esf_op_destroy(h)
+    got = ybuf[..., :d].cpu().double()
+    err = (got - ref).abs().max().item()
+    print("attn_tc d=%d N=%d rel err %.3e" % (d, N, err / ref.abs().max().item()))
+    assert err <= 1.5e-2 * ref.abs().max().item(), "d=%d err %.4g scale %.4g" % (d, err, ref.abs().max().item())
+    assert (ybuf[..., d:] == 0).all()
+
+
 def test_head(esf_lib):
     g = torch.Generator().manual_seed(9)
     B = 3

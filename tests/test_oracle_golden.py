@@ -9,7 +9,8 @@ from oracle import slowfast_oracle as O
 
 
 @pytest.mark.parametrize("name,tag", [("dual_r50", "s64"), ("slowfast_r50", "s64"), ("dual_r50", "s224"),
-                                      ("slowfast_r50", "s224"), ("slowfast_r50_stress", "s64")])
+                                      ("slowfast_r50", "s224"), ("slowfast_r50_stress", "s64"),
+                                      ("dual_r50_stress", "s64")])
 def test_oracle_matches_reference_golden(name, tag):
     cfg, model, gold = helpers.case_model_and_weights(name)
     xs = helpers.case_inputs(name, tag)
