@@ -25,10 +25,10 @@
 
 namespace esf {
 
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 352;  // 8 softmax warps + TMA producer + 2 MMA issuers
 constexpr int kTcBN = 64;          // keys per tile
 constexpr int kTcMaxStages = 6;
-constexpr int kTcMaxSteps = 16;
+constexpr int kTcMaxSteps = 12;
 constexpr int kTcSmemLimit = 232448;
 constexpr float kTcLog2e = 1.4426950408889634f;
 
@@ -46,7 +46,7 @@ struct __align__(64) AttnTcParams {
   int chunk_el;  // elements per chunk: 32 or 64
   uint32_t sbo, layout_type;
   int nsteps1, nsteps2;
-  uint32_t steps1[kTcMaxSteps], steps2[kTcMaxSteps];  // a_chunk | a_k << 4 | b_chunk << 8 | b_k << 12
+  uint32_t steps1[kTcMaxSteps], steps2[kTcMaxSteps];  // A offset | B offset << 16 (16-byte units, see host code)
   int stages;
   uint32_t q_tile_bytes, k_tile_bytes, v_tile_bytes;
 };
@@ -80,10 +80,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
   uint64_t* s_free = s_full + 4;
   uint64_t* p_full = s_free + 4;             // [q]
   uint64_t* p_free = p_full + 2;
-  uint64_t* o_full = p_free + 2;             // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* o_full = p_free + 2;             // [q]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int row0 = blockIdx.x * 256;
   const int N = p.N;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
     mbar_init(q_full, 1);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&kv_empty[s], 2);  // one tcgen05.commit from each of the two MMA warps
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
@@ -102,8 +103,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
     for (int i = 0; i < 2; ++i) {
       mbar_init(&p_full[i], 4);
       mbar_init(&p_free[i], 1);
+      mbar_init(&o_full[i], 1);
     }
-    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 8 && lane == 0) {
@@ -123,97 +124,114 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
   const uint32_t chunk_bytes_k = kTcBN * p.chunk_el * 2;
 
   if (warp == 8) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (all lanes loop, one issues)
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * p.q_tile_bytes);
       for (int q = 0; q < 2; ++q)
         for (int ch = 0; ch < p.nchunks; ++ch)
           tma_load_3d(Qs + q * p.q_tile_bytes + ch * chunk_bytes_q, &p.q_map, q_full, ch * p.chunk_el, row0 + q * 128, b);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int j = 0; j < nt; ++j) {
-          mbar_wait(&kv_empty[stage], phase ^ 1, 11);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int j = 0; j < nt; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1, 11);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&kv_full[stage], p.k_tile_bytes + (pass ? p.v_tile_bytes : 0));
           for (int ch = 0; ch < p.nchunks; ++ch)
             tma_load_3d(Ks + stage * p.k_tile_bytes + ch * chunk_bytes_k, &p.k_map, &kv_full[stage], ch * p.chunk_el,
                         j * kTcBN, b);
           if (pass) tma_load_3d(Vs + stage * p.v_tile_bytes, &p.v_map, &kv_full[stage], j * kTcBN, 0, b);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-      }
-    }
-  } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(128, kTcBN);
-      const uint32_t idesc_o = make_idesc_bf16(128, p.DVp);
-      const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs), p_addr = smem_u32(Ps);
-      auto issue_s = [&](int q, int c, int stage, const uint32_t* steps, int nsteps) {
-        // S tile number c of query tile q: TMEM buffer c & 1
-        const int buf = c & 1;
-        mbar_wait(&s_free[q * 2 + buf], ((c >> 1) & 1) ^ 1, 12);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (q * 2 + buf) * kTcBN;
-        for (int i = 0; i < nsteps; ++i) {
-          const uint32_t st = steps[i];
-          const uint32_t a = q_addr + q * p.q_tile_bytes + (st & 15) * chunk_bytes_q + ((st >> 4) & 15) * 32;
-          const uint32_t bb = k_addr + stage * p.k_tile_bytes + ((st >> 8) & 15) * chunk_bytes_k + ((st >> 12) & 15) * 32;
-          umma_bf16(d_tmem, make_kmajor_desc(a, p.sbo, p.layout_type), make_kmajor_desc(bb, p.sbo, p.layout_type),
-                    idesc_s, i != 0);
-        }
-        umma_commit(&s_full[q * 2 + buf]);
-      };
-      mbar_wait(q_full, 0, 13);
-      tc_fence_after();
-      int stage = 0;
-      uint32_t phase = 0;
-      // pass 1: row maxima from the hi parts only
-      for (int j = 0; j < nt; ++j) {
-        mbar_wait(&kv_full[stage], phase, 14);
-        tc_fence_after();
-        issue_s(0, j, stage, p.steps1, p.nsteps1);
-        issue_s(1, j, stage, p.steps1, p.nsteps1);
-        umma_commit(&kv_empty[stage]);
+        __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      // pass 2: S one tile ahead of P.V
-      int s_stage = stage;          // stage of S tile j+1
-      uint32_t s_phase = phase;
-      mbar_wait(&kv_full[s_stage], s_phase, 15);
+    }
+  } else if (warp == 9 || warp == 10) {
+    // ------------------------------------------------------------------ MMA issuers: warp 9 -> tile A, warp 10 -> B
+    // One thread issues; the whole warp runs the (warp-uniform) control flow so that descriptors stay in uniform
+    // registers.  Two issuing warps because at N = 64 an MMA retires in 32 clk -- faster than one thread can issue.
+    const int q = warp - 9;
+    const uint32_t idesc_s = make_idesc_bf16(128, kTcBN);
+    const uint32_t idesc_o = make_idesc_bf16(128, p.DVp);
+    const uint32_t qk_hi = kmajor_desc_hi(p.sbo, p.layout_type);
+    const uint32_t pv_hi = kmajor_desc_hi(1024, 2);
+    const uint32_t q_lo = kmajor_desc_lo(smem_u32(Qs) + q * p.q_tile_bytes);
+    const uint32_t k_lo = kmajor_desc_lo(smem_u32(Ks));
+    const uint32_t v_lo = kmajor_desc_lo(smem_u32(Vs));
+    const uint32_t p_lo = kmajor_desc_lo(smem_u32(Ps) + q * 16384);
+    const uint32_t k_stage_step = p.k_tile_bytes >> 4, v_stage_step = p.v_tile_bytes >> 4;
+    const uint32_t o_tmem = tmem_base + 4 * kTcBN + q * p.DVp;
+    auto issue_s = [&](int c, int stage, bool second) {
+      const int buf = c & 1;  // S tile number c lives in TMEM buffer c & 1
+      mbar_wait(&s_free[q * 2 + buf], ((c >> 1) & 1) ^ 1, 12);
       tc_fence_after();
-      issue_s(0, nt + 0, s_stage, p.steps2, p.nsteps2);
-      issue_s(1, nt + 0, s_stage, p.steps2, p.nsteps2);
-      for (int j = 0; j < nt; ++j) {
-        const int pv_stage = s_stage;
-        if (++s_stage == p.stages) {
-          s_stage = 0;
-          s_phase ^= 1;
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + (q * 2 + buf) * kTcBN;
+        const uint32_t kb = k_lo + stage * k_stage_step;
+        if (second) {
+#pragma unroll
+          for (int i = 0; i < kTcMaxSteps; ++i)
+            if (i < p.nsteps2) umma_bf16_lohi(d_tmem, q_lo + (p.steps2[i] & 0xffff), qk_hi, kb + (p.steps2[i] >> 16), qk_hi, idesc_s, i != 0);
+        } else {
+#pragma unroll
+          for (int i = 0; i < kTcMaxSteps; ++i)
+            if (i < p.nsteps1) umma_bf16_lohi(d_tmem, q_lo + (p.steps1[i] & 0xffff), qk_hi, kb + (p.steps1[i] >> 16), qk_hi, idesc_s, i != 0);
         }
-        if (j + 1 < nt) {
-          mbar_wait(&kv_full[s_stage], s_phase, 16);
-          tc_fence_after();
-          issue_s(0, nt + j + 1, s_stage, p.steps2, p.nsteps2);
-          issue_s(1, nt + j + 1, s_stage, p.steps2, p.nsteps2);
-        }
-        for (int q = 0; q < 2; ++q) {
-          mbar_wait(&p_full[q], j & 1, 17);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + 4 * kTcBN + q * p.DVp;
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, make_kmajor_desc(p_addr + q * 16384 + k * 32, 1024, 2),
-                      make_kmajor_desc(v_addr + pv_stage * p.v_tile_bytes + k * 32, 1024, 2), idesc_o, (j | k) != 0);
-          umma_commit(&p_free[q]);
-        }
-        umma_commit(&kv_empty[pv_stage]);
+        umma_commit(&s_full[q * 2 + buf]);
       }
-      umma_commit(o_full);
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0, 13);
+    tc_fence_after();
+    int stage = 0;
+    uint32_t phase = 0;
+    // pass 1: row maxima from the hi parts only
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&kv_full[stage], phase, 14);
+      tc_fence_after();
+      issue_s(j, stage, false);
+      if (elect_one()) umma_commit(&kv_empty[stage]);
+      __syncwarp();
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    // pass 2: S runs one key tile ahead of P.V
+    int s_stage = stage;  // stage of S tile j + 1
+    uint32_t s_phase = phase;
+    mbar_wait(&kv_full[s_stage], s_phase, 15);
+    tc_fence_after();
+    issue_s(nt, s_stage, true);
+    for (int j = 0; j < nt; ++j) {
+      const int pv_stage = s_stage;
+      if (++s_stage == p.stages) {
+        s_stage = 0;
+        s_phase ^= 1;
+      }
+      if (j + 1 < nt) {
+        mbar_wait(&kv_full[s_stage], s_phase, 16);
+        tc_fence_after();
+        issue_s(nt + j + 1, s_stage, true);
+      }
+      mbar_wait(&p_full[q], j & 1, 17);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t vl = v_lo + pv_stage * v_stage_step;
+        umma_bf16_lohi(o_tmem, p_lo, pv_hi, vl, pv_hi, idesc_o, j != 0);
+        umma_bf16_lohi(o_tmem, p_lo + 2, pv_hi, vl + 2, pv_hi, idesc_o, 1);
+        umma_bf16_lohi(o_tmem, p_lo + 4, pv_hi, vl + 4, pv_hi, idesc_o, 1);
+        umma_bf16_lohi(o_tmem, p_lo + 6, pv_hi, vl + 6, pv_hi, idesc_o, 1);
+        umma_commit(&p_free[q]);
+        umma_commit(&kv_empty[pv_stage]);
+        if (j == nt - 1) umma_commit(&o_full[q]);
+      }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
@@ -287,7 +305,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
       if (lane == 0) mbar_arrive(&p_full[q]);
     }
     // epilogue: O / l, gamma * O + x, BN, ReLU, x alpha temporal replication
-    mbar_wait(o_full, 0, 21);
+    mbar_wait(&o_full[q], 0, 21);
     tc_fence_after();
     const float inv = 1.f / l;
     const int HW = p.H * p.W;
@@ -510,7 +528,10 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
   const int RB = g.chunk_el * 2;
   p.sbo = 8 * RB;
   p.layout_type = RB == 128 ? 2 : 4;
-  auto step = [](int ac, int ak, int bc, int bk) { return (uint32_t)(ac | (ak << 4) | (bc << 8) | (bk << 12)); };
+  // a step = (offset of the A operand inside a Q tile) | (offset of the B operand inside a K tile) << 16, both in
+  // 16-byte units (what gets added to the start-address field of the smem descriptors)
+  const uint32_t cq16 = (128u * g.chunk_el * 2) >> 4, ck16 = ((uint32_t)kTcBN * g.chunk_el * 2) >> 4;
+  auto step = [&](int ac, int ak, int bc, int bk) { return (uint32_t)((ac * cq16 + ak * 2) | ((bc * ck16 + bk * 2) << 16)); };
   int n1 = 0, n2 = 0;
   if (g.mode == 0) {
     // q~ = [q_hi q_lo | q_hi 0], k~ = [k_hi k_hi | k_lo 0]: step 0 = (q_hi+q_lo).k_hi, step 1 = q_hi.k_lo

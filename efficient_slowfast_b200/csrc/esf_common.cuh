@@ -49,16 +49,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a pipeline bug traps (sticky launch error surfaced by the C ABI) instead of hanging the box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (((++spins) & 0x3ff) == 0 && globaltimer_ns() - t0 > ESF_WAIT_TIMEOUT_NS) {
-      printf("[esf] mbarrier wait timeout: block %d thread %d tag %d parity %u\n", (int)blockIdx.x, (int)threadIdx.x, tag,
-             parity);
-      __trap();
+    if (((++spins) & 0xfff) == 0) {  // the slow global timer is only consulted on waits that are already very long
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > ESF_WAIT_TIMEOUT_NS) {
+        printf("[esf] mbarrier wait timeout: block %d thread %d tag %d parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+               tag, parity);
+        __trap();
+      }
     }
   }
 }
+
+// One leader lane of a fully converged warp (deterministic for a given mask).  Warp-specialised roles run their loops
+// with all 32 lanes (so the compiler keeps addresses / descriptors in uniform registers) and issue TMA / tcgen05
+// instructions from the elected lane only.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// warp index that the compiler can prove to be warp-uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); }
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
@@ -172,6 +187,26 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v) {
   if constexpr (N == 8) tmem_ld8(taddr, v);
   else if constexpr (N == 16) tmem_ld16(taddr, v);
   else tmem_ld32(taddr, v);
+}
+
+// Same MMA with the two 64-bit smem descriptors passed as (lo, hi) register pairs: the issuing thread keeps the
+// loop-invariant hi words and only adds to the 14-bit start-address field of the lo words.
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// lo / hi words of the K-major descriptor (see make_kmajor_desc): lo = start address >> 4 | LBO << 16,
+// hi = SBO >> 4 | version << 14 | layout_type << 29
+__device__ __forceinline__ uint32_t kmajor_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3fff) | (1u << 16); }
+__device__ __forceinline__ uint32_t kmajor_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3fff) | (1u << 14) | ((layout_type & 7) << 29);
 }
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows are 32/64/128 B wide and

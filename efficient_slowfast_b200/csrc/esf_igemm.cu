@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   uint64_t* res_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   const int num_kb = p.num_taps * p.kchunks;
 
   if (warp == kProducerWarp) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -185,11 +185,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           const int4 tp = p.taps[tap];
           for (int ch = 0; ch < p.kchunks; ++ch) {
             mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-            mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-            tma_load_5d(smem_a + stage * kAStageBytes, &p.a_maps[tp.x], &full_bar[stage],
-                        tc.cb * p.a_cb_stride + ch * p.kc, tc.w0 + tp.y, tc.h0 + tp.z, tc.t0 + tp.w, tc.b0);
-            tma_load_2d(smem_b + stage * p.b_stride, &p.b_map, &full_bar[stage], (tap * p.kchunks + ch) * p.kc,
-                        tc.n_idx * p.n_tile);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+              tma_load_5d(smem_a + stage * kAStageBytes, &p.a_maps[tp.x], &full_bar[stage],
+                          tc.cb * p.a_cb_stride + ch * p.kc, tc.w0 + tp.y, tc.h0 + tp.z, tc.t0 + tp.w, tc.b0);
+              tma_load_2d(smem_b + stage * p.b_stride, &p.b_map, &full_bar[stage], (tap * p.kchunks + ch) * p.kc,
+                          tc.n_idx * p.n_tile);
+            }
+            __syncwarp();
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -199,10 +202,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
+    {
+      // the issuing thread is a serial instruction stream: keep it to two adds per MMA (descriptor lo words)
       const uint32_t idesc = make_idesc_bf16(128, p.n_tile);
+      const uint32_t desc_hi = kmajor_desc_hi(p.sbo, p.layout_type);
+      const uint32_t a_lo0 = kmajor_desc_lo(smem_u32(smem_a)), b_lo0 = kmajor_desc_lo(smem_u32(smem_b));
+      const uint32_t a_step = kAStageBytes >> 4, b_step = p.b_stride >> 4;
+      const int ksteps = p.kc >> 4;
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t a_lo = a_lo0, b_lo = b_lo0;
       int iter = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
         const int acc = iter & 1;
@@ -210,23 +219,34 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * p.n_tile;
+        uint32_t accum = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * kAStageBytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * p.b_stride);
-          const int ksteps = p.kc >> 4;
-          for (int k = 0; k < ksteps; ++k) {
-            umma_bf16(d_tmem, make_kmajor_desc(a_addr + k * 32, p.sbo, p.layout_type),
-                      make_kmajor_desc(b_addr + k * 32, p.sbo, p.layout_type), idesc, (kb | k) != 0);
+          if (elect_one()) {
+            if (ksteps == 4) {
+              umma_bf16_lohi(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, accum);
+              umma_bf16_lohi(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1);
+              umma_bf16_lohi(d_tmem, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1);
+              umma_bf16_lohi(d_tmem, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1);
+            } else {
+              umma_bf16_lohi(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, accum);
+              if (ksteps == 2) umma_bf16_lohi(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
+          accum = 1;
+          a_lo += a_step;
+          b_lo += b_step;
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
+            a_lo = a_lo0;
+            b_lo = b_lo0;
           }
         }
-        umma_commit(&tmem_full[acc]);
       }
     }
   } else {
