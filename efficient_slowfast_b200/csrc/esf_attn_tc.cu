@@ -1,4 +1,4 @@
-// CMDA slow->fast position attention on the 5th-generation tensor cores (tcgen05 + TMEM), two-pass softmax.
+// CMDA slow->fast position attention on the 5th-generation tensor cores (tcgen05 + TMEM), single pass, lazy rescale.
 //
 //   out[i] = relu(bn(gamma * sum_j softmax_j(q_i . k_j) v_j + x_i)),  N = T*H*W keys per clip, no N x N matrix.
 //
@@ -6,11 +6,13 @@
 //   warp 8   TMA producer (Q once, then a `stages`-deep ring of K~ / V^T tiles, 64 keys each)
 //   warp 9   MMA issuer: S = Q~ K~^T (M=128, N=64) into double-buffered TMEM tiles, O += P V (M=128, N=DVp)
 //   warps 0-3 / 4-7  softmax warpgroups of tile A / B, one query row per thread
-// Pass 1 computes an (approximate, hi-parts only) row maximum, pass 2 re-computes S with the hi/lo split
+// S is computed with the hi/lo split
 //   s = q_hi.k_hi + q_lo.k_hi + q_hi.k_lo   (~FP32 logits out of BF16 MMAs; the logits are unscaled and reach 1e2)
-// and streams p = exp2((s - m) log2e) as a BF16 A-operand through shared memory into the second MMA; O accumulates in
-// TMEM and is never rescaled.  The tensor pipe is mostly idle by construction: the kernel is bound by the MUFU (exp)
-// pipe -- 16 exp/clk/SM -- which is why the second QK^T pass is affordable (exp roofline).
+// and p = exp2((s - m) log2e) is streamed as a BF16 A-operand through shared memory into the second MMA; O accumulates
+// in TMEM.  The running row maximum m is only raised when a key tile exceeds it by more than 8 in the log2 domain (p
+// stays <= 256, harmless in FP32 sums / BF16 P); on those rare tiles the owning warp rescales its 32 TMEM lanes of O
+// (tcgen05.ld / st) inside the window where no P.V MMA of its tile is in flight.  The tensor pipe is mostly idle by
+// construction: the kernel is bound by the MUFU (exp) pipe -- 16 exp/clk/SM (exp roofline).
 //
 // Reference ops replaced: SpatialAttention.forward (wdf_attention_helper.py:33-54) + bn_s2f + ReLU + nearest x alpha
 // upsample + concat (custom_video_model_builder.py:142-146).
@@ -134,21 +136,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
     __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int j = 0; j < nt; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1, 11);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&kv_full[stage], p.k_tile_bytes + (pass ? p.v_tile_bytes : 0));
-          for (int ch = 0; ch < p.nchunks; ++ch)
-            tma_load_3d(Ks + stage * p.k_tile_bytes + ch * chunk_bytes_k, &p.k_map, &kv_full[stage], ch * p.chunk_el,
-                        j * kTcBN, b);
-          if (pass) tma_load_3d(Vs + stage * p.v_tile_bytes, &p.v_map, &kv_full[stage], j * kTcBN, 0, b);
-        }
-        __syncwarp();
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
-        }
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&kv_empty[stage], phase ^ 1, 11);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[stage], p.k_tile_bytes + p.v_tile_bytes);
+        for (int ch = 0; ch < p.nchunks; ++ch)
+          tma_load_3d(Ks + stage * p.k_tile_bytes + ch * chunk_bytes_k, &p.k_map, &kv_full[stage], ch * p.chunk_el,
+                      j * kTcBN, b);
+        tma_load_3d(Vs + stage * p.v_tile_bytes, &p.v_map, &kv_full[stage], j * kTcBN, 0, b);
+      }
+      __syncwarp();
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
       }
     }
   } else if (warp == 9 || warp == 10) {
@@ -166,48 +166,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
     const uint32_t p_lo = kmajor_desc_lo(smem_u32(Ps) + q * 16384);
     const uint32_t k_stage_step = p.k_tile_bytes >> 4, v_stage_step = p.v_tile_bytes >> 4;
     const uint32_t o_tmem = tmem_base + 4 * kTcBN + q * p.DVp;
-    auto issue_s = [&](int c, int stage, bool second) {
+    auto issue_s = [&](int c, int stage) {
       const int buf = c & 1;  // S tile number c lives in TMEM buffer c & 1
       mbar_wait(&s_free[q * 2 + buf], ((c >> 1) & 1) ^ 1, 12);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + (q * 2 + buf) * kTcBN;
         const uint32_t kb = k_lo + stage * k_stage_step;
-        if (second) {
 #pragma unroll
-          for (int i = 0; i < kTcMaxSteps; ++i)
-            if (i < p.nsteps2) umma_bf16_lohi(d_tmem, q_lo + (p.steps2[i] & 0xffff), qk_hi, kb + (p.steps2[i] >> 16), qk_hi, idesc_s, i != 0);
-        } else {
-#pragma unroll
-          for (int i = 0; i < kTcMaxSteps; ++i)
-            if (i < p.nsteps1) umma_bf16_lohi(d_tmem, q_lo + (p.steps1[i] & 0xffff), qk_hi, kb + (p.steps1[i] >> 16), qk_hi, idesc_s, i != 0);
-        }
+        for (int i = 0; i < kTcMaxSteps; ++i)
+          if (i < p.nsteps2)
+            umma_bf16_lohi(d_tmem, q_lo + (p.steps2[i] & 0xffff), qk_hi, kb + (p.steps2[i] >> 16), qk_hi, idesc_s, i != 0);
         umma_commit(&s_full[q * 2 + buf]);
       }
       __syncwarp();
     };
     mbar_wait(q_full, 0, 13);
     tc_fence_after();
-    int stage = 0;
-    uint32_t phase = 0;
-    // pass 1: row maxima from the hi parts only
-    for (int j = 0; j < nt; ++j) {
-      mbar_wait(&kv_full[stage], phase, 14);
-      tc_fence_after();
-      issue_s(j, stage, false);
-      if (elect_one()) umma_commit(&kv_empty[stage]);
-      __syncwarp();
-      if (++stage == p.stages) {
-        stage = 0;
-        phase ^= 1;
-      }
-    }
-    // pass 2: S runs one key tile ahead of P.V
-    int s_stage = stage;  // stage of S tile j + 1
-    uint32_t s_phase = phase;
+    // S runs one key tile ahead of P.V
+    int s_stage = 0;  // stage of S tile j + 1
+    uint32_t s_phase = 0;
     mbar_wait(&kv_full[s_stage], s_phase, 15);
     tc_fence_after();
-    issue_s(nt, s_stage, true);
+    issue_s(0, s_stage);
     for (int j = 0; j < nt; ++j) {
       const int pv_stage = s_stage;
       if (++s_stage == p.stages) {
@@ -217,7 +198,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
       if (j + 1 < nt) {
         mbar_wait(&kv_full[s_stage], s_phase, 16);
         tc_fence_after();
-        issue_s(nt + j + 1, s_stage, true);
+        issue_s(j + 1, s_stage);
       }
       mbar_wait(&p_full[q], j & 1, 17);
       tc_fence_after();
@@ -241,11 +222,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
     const int n = row0 + q * 128 + r;   // query position
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const bool tail = (N % kTcBN) != 0;
-    float m = -CUDART_INF_F;
-    // pass 1
+    float m = -CUDART_INF_F;   // running row maximum (raised lazily), natural-log units
+    float l = 0.f;             // running sum of p
+    uint8_t* prow = Ps + q * 16384;
+    const uint32_t o_addr = lane_addr + 4 * kTcBN + q * p.DVp;
+    constexpr float kTau = 5.545177f;  // 8 * ln 2: p = exp(s - m) never exceeds 256
     for (int j = 0; j < nt; ++j) {
       const int buf = j & 1;
-      mbar_wait(&s_full[q * 2 + buf], (j >> 1) & 1, 18);
+      mbar_wait(&s_full[q * 2 + buf], (j >> 1) & 1, 19);
       tc_fence_after();
       float v[64];
       tmem_ld32(lane_addr + (q * 2 + buf) * kTcBN, v);
@@ -258,39 +242,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
         for (int i = 0; i < 64; ++i)
           if (j * kTcBN + i >= N) v[i] = -CUDART_INF_F;
       }
+      float mx0 = v[0], mx1 = v[1];
 #pragma unroll
-      for (int i = 0; i < 64; i += 2) m = fmaxf(m, fmaxf(v[i], v[i + 1]));
-    }
-    const float ms = m * kTcLog2e;
-    float l = 0.f;
-    uint8_t* prow = Ps + q * 16384;
-    // pass 2
-    for (int j = 0; j < nt; ++j) {
-      const int c = nt + j;
-      const int buf = c & 1;
-      mbar_wait(&s_full[q * 2 + buf], (c >> 1) & 1, 19);
-      tc_fence_after();
-      float v[64];
-      tmem_ld32(lane_addr + (q * 2 + buf) * kTcBN, v);
-      tmem_ld32(lane_addr + (q * 2 + buf) * kTcBN + 32, v + 32);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[q * 2 + buf]);
+      for (int i = 2; i < 64; i += 2) {
+        mx0 = fmaxf(mx0, v[i]);
+        mx1 = fmaxf(mx1, v[i + 1]);
+      }
+      const float mx = fmaxf(mx0, mx1);
+      const bool raise = mx > m + kTau;  // always true for the first tile (m = -inf)
+      const float m_new = raise ? mx : m;
+      const float f = raise ? fast_exp2((m - m_new) * kTcLog2e) : 1.f;  // first tile: exp2(-inf) = 0
+      m = m_new;
+      const float ms = m * kTcLog2e;
 #pragma unroll
       for (int i = 0; i < 64; ++i) v[i] = fast_exp2(fmaf(v[i], kTcLog2e, -ms));
-      if (tail && j == nt - 1) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (j * kTcBN + i >= N) v[i] = 0.f;
-      }
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 64; i += 2) {
         s0 += v[i];
         s1 += v[i + 1];
       }
-      l += s0 + s1;
-      mbar_wait(&p_free[q], (j & 1) ^ 1, 20);  // P.V of the previous key tile no longer reads the P buffer
+      l = fmaf(l, f, s0 + s1);
+      mbar_wait(&p_free[q], (j & 1) ^ 1, 20);  // P.V of the previous key tile is complete: P buffer and O are quiescent
+      if (j > 0 && __any_sync(0xffffffffu, raise)) {
+        // rare: some row of this warp raised its maximum -> rescale this warp's 32 TMEM lanes of O
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.DVp; c0 += 16) {
+          float o[16];
+          tmem_ld16(o_addr + c0, o);
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) o[jj] *= f;
+          tmem_st16(o_addr + c0, o);
+        }
+        tmem_wait_st();
+      }
 #pragma unroll
       for (int ck = 0; ck < 8; ++ck) {
         uint4 o;
@@ -301,6 +286,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
         *reinterpret_cast<uint4*>(prow + swz(r * 128 + ck * 16, 7)) = o;
       }
       fence_proxy_async_smem();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[q]);
     }
@@ -392,16 +378,27 @@ static TcLayout tc_layout(int B, int N, int d, const TcGeom& g) {
 __device__ __forceinline__ __nv_bfloat16 bf_hi(float v) { return __float2bfloat16(v); }
 __device__ __forceinline__ __nv_bfloat16 bf_lo(float v) { return __float2bfloat16(v - __bfloat162float(__float2bfloat16(v))); }
 
-// proj rows are [x_d | q | k | v] (d each, FP32)
-__global__ void __launch_bounds__(256) attn_tc_pack_qk(const float* __restrict__ proj, long long rows, int d, int KQ,
-                                                       int mode, __nv_bfloat16* __restrict__ Q,
-                                                       __nv_bfloat16* __restrict__ K) {
-  const long long total = rows * KQ;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / KQ;
-    const int e = i % KQ;
-    const float* pr = proj + r * 4 * d;
+// proj rows are [x_d | q | k | v] (d each, FP32).  One block stages R consecutive rows of one clip in shared memory
+// (coalesced loads) and writes Q~/K~ rows, x_d rows and the TRANSPOSED value tile V^T[j][n0..n0+R) from there, so every
+// global access is coalesced.
+__global__ void __launch_bounds__(256) attn_tc_pack_kernel(const float* __restrict__ proj, int N, int Npad, int d,
+                                                           int KQ, int DVp, int mode, int R,
+                                                           __nv_bfloat16* __restrict__ Q, __nv_bfloat16* __restrict__ K,
+                                                           __nv_bfloat16* __restrict__ VT, float* __restrict__ X) {
+  extern __shared__ float tile[];  // [R][4d + 1]
+  const int b = blockIdx.y;
+  const int n0 = blockIdx.x * R;
+  const int rows = min(R, N - n0);
+  const int W4 = 4 * d, pitch = W4 + 1;
+  const float* src = proj + ((long long)b * N + n0) * W4;
+  for (int i = threadIdx.x; i < rows * W4; i += blockDim.x) tile[(i / W4) * pitch + (i % W4)] = src[i];
+  __syncthreads();
+  // Q~ / K~
+  __nv_bfloat16* qd = Q + ((long long)b * N + n0) * KQ;
+  __nv_bfloat16* kd = K + ((long long)b * N + n0) * KQ;
+  for (int i = threadIdx.x; i < rows * KQ; i += blockDim.x) {
+    const int r = i / KQ, e = i % KQ;
+    const float* pr = tile + r * pitch;
     __nv_bfloat16 qv = __float2bfloat16(0.f), kv = qv;
     if (mode == 0) {
       const int seg = e >> 3, jj = e & 7;
@@ -418,33 +415,23 @@ __global__ void __launch_bounds__(256) attn_tc_pack_qk(const float* __restrict__
         qv = part ? bf_lo(q) : bf_hi(q);
         kv = part ? bf_lo(k) : bf_hi(k);
       }
-    } else {
-      if (e < d) {
-        qv = bf_hi(pr[d + e]);
-        kv = bf_hi(pr[2 * d + e]);
-      }
+    } else if (e < d) {
+      qv = bf_hi(pr[d + e]);
+      kv = bf_hi(pr[2 * d + e]);
     }
-    Q[i] = qv;
-    K[i] = kv;
+    qd[i] = qv;
+    kd[i] = kv;
   }
-}
-// V^T[b][j][n] (j < DVp, zero rows beyond d) and X[b][n][j]
-__global__ void __launch_bounds__(256) attn_tc_pack_vx(const float* __restrict__ proj, int B, int N, int Npad, int d,
-                                                       int DVp, __nv_bfloat16* __restrict__ VT, float* __restrict__ X) {
-  const long long total = (long long)B * DVp * Npad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int n = i % Npad;
-    const long long t = i / Npad;
-    const int j = t % DVp;
-    const int b = t / DVp;
-    float v = 0.f;
-    if (n < N && j < d) {
-      const float* pr = proj + ((long long)b * N + n) * 4 * d;
-      v = pr[3 * d + j];
-      X[((long long)b * N + n) * d + j] = pr[j];
+  // x_d
+  float* xd = X + ((long long)b * N + n0) * d;
+  for (int i = threadIdx.x; i < rows * d; i += blockDim.x) xd[i] = tile[(i / d) * pitch + (i % d)];
+  // V^T (rows j >= d and the columns n >= N of the padded row stay zero)
+  for (int i = threadIdx.x; i < DVp * R; i += blockDim.x) {
+    const int j = i / R, r = i % R;
+    if (n0 + r < Npad) {
+      const float v = (j < d && r < rows) ? tile[r * pitch + 3 * d + j] : 0.f;
+      VT[((long long)b * DVp + j) * Npad + n0 + r] = __float2bfloat16(v);
     }
-    VT[i] = __float2bfloat16(v);
   }
 }
 
@@ -488,18 +475,17 @@ extern "C" int esf_attn_tc_pack(const float* proj, int32_t B, int32_t N, int32_t
   if (!tc_geom(d, &g)) return set_error(ESF_ERR_UNSUPPORTED, "esf_attn_tc_pack: unsupported head dim %d", d);
   const TcLayout L = tc_layout(B, N, d, g);
   char* base = static_cast<char*>(packed);
-  const long long rows = (long long)B * N;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  auto grid_of = [](long long total) { return (int)std::max(1LL, std::min<long long>((total + 255) / 256, 148LL * 32)); };
-  attn_tc_pack_qk<<<grid_of(rows * g.KQ), 256, 0, s>>>(proj, rows, d, g.KQ, g.mode,
-                                                        reinterpret_cast<__nv_bfloat16*>(base + L.q_off),
-                                                        reinterpret_cast<__nv_bfloat16*>(base + L.k_off));
-  int rc = check_launch("attn_tc_pack_qk");
-  if (rc != ESF_OK) return rc;
-  attn_tc_pack_vx<<<grid_of((long long)B * g.DVp * L.Npad), 256, 0, s>>>(
-      proj, B, N, L.Npad, d, g.DVp, reinterpret_cast<__nv_bfloat16*>(base + L.v_off),
-      reinterpret_cast<float*>(base + L.x_off));
-  return check_launch("attn_tc_pack_vx");
+  int R = 64;
+  while (R > 8 && (size_t)R * (4 * d + 1) * sizeof(float) > 40 * 1024) R >>= 1;
+  const size_t smem = (size_t)R * (4 * d + 1) * sizeof(float);
+  dim3 grid(cdiv(L.Npad, R), B);
+  attn_tc_pack_kernel<<<grid, 256, smem, s>>>(proj, N, L.Npad, d, g.KQ, g.DVp, g.mode, R,
+                                              reinterpret_cast<__nv_bfloat16*>(base + L.q_off),
+                                              reinterpret_cast<__nv_bfloat16*>(base + L.k_off),
+                                              reinterpret_cast<__nv_bfloat16*>(base + L.v_off),
+                                              reinterpret_cast<float*>(base + L.x_off));
+  return check_launch("attn_tc_pack_kernel");
 }
 
 extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d,

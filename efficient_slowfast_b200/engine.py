@@ -252,7 +252,7 @@ class Plan:
             self.handles.append(h)
             self._add(lambda s: rt.check(L.esf_attn_tc_pack(proj.data_ptr(), B, N, d, packed.data_ptr(), s),
                                          "esf_attn_tc_pack"), "attn_pack", "N=%d d=%d" % (N, d),
-                      nbytes=self._nbytes(proj) + nbytes, launches=2)
+                      nbytes=self._nbytes(proj) + nbytes)
             self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "attention",
                       "N=%d d=%d" % (N, d), flops=4.0 * B * N * N * d, exps=float(B) * N * N,
                       nbytes=nbytes + self._nbytes(y_slice))
