@@ -109,3 +109,36 @@ def slowfast_dual_8x8_r50_cfg():
     c.MODEL._merge(dict(NUM_CLASSES=400, ARCH="slowfast", MODEL_NAME="SlowFastDualAttention", DROPOUT_RATE=0.5))
     c.MULTIGRID._merge(dict(SHORT_CYCLE=True, LONG_CYCLE=True))
     return c
+
+
+def _efficient_cfg(model_name, width_multi, groups=1, num_classes=400, num_frames=16, crop=112, dropout=0.5,
+                   short_cycle=True):
+    """Shared part of the four efficient YAMLs (configs/Kinetics/SLOWFAST_{SHUFFLENETV2,MOBILENETV2,GHOSTNET}_8x8_*.yaml,
+    configs/Jester/SLOWFAST_SHUFFLENET_8x8_*.yaml): NUM_FRAMES 16, ALPHA 4, BETA_INV 8, crop 112."""
+    c = get_cfg()
+    c.RESNET._merge(_R50_TWO_PATH)
+    c.NONLOCAL._merge(_NONLOCAL_OFF)
+    c.DATA._merge(dict(NUM_FRAMES=num_frames, INPUT_CHANNEL_NUM=[3, 3], CROP_SIZE=crop, TRAIN_CROP_SIZE=crop,
+                       TEST_CROP_SIZE=crop))
+    c.SLOWFAST._merge(dict(ALPHA=4, BETA_INV=8, FUSION_CONV_CHANNEL_RATIO=2, FUSION_KERNEL_SZ=7,
+                           WIDTH_MULTI=width_multi, GROUPS=groups))
+    c.MODEL._merge(dict(NUM_CLASSES=num_classes, ARCH="slowfast", MODEL_NAME=model_name, DROPOUT_RATE=dropout))
+    c.MULTIGRID._merge(dict(SHORT_CYCLE=short_cycle, LONG_CYCLE=short_cycle))
+    return c
+
+
+def slowfast_shufflenetv2_cfg(width_multi=2.0):
+    return _efficient_cfg("SlowFastShuffleNetV2", width_multi, short_cycle=False)
+
+
+def slowfast_shufflenet_cfg(width_multi=2.0, groups=3):
+    """Jester YAML: 27 classes, dropout 0.2."""
+    return _efficient_cfg("SlowFastShuffleNet", width_multi, groups=groups, num_classes=27, dropout=0.2)
+
+
+def slowfast_mobilenetv2_cfg(width_multi=0.5):
+    return _efficient_cfg("SlowFastMoibleNetV2", width_multi)
+
+
+def slowfast_ghostnet_cfg(width_multi=1.0):
+    return _efficient_cfg("SlowFastGhostNet", width_multi)

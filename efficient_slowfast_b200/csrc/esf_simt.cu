@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectParams p) 
 // ------------------------------------------------------------------------------------------- pooling
 struct PoolParams {
   View x, y;
-  int kT, kH, kW, sT, sH, sW, pT, pH, pW, is_avg;
+  int kT, kH, kW, sT, sH, sW, pT, pH, pW, is_avg, act;
 };
 // VEC = 8: one thread handles 8 channels (16 B); VEC = 1: scalar tail path for C % 8 != 0.
 template <int VEC>
@@ -231,6 +231,8 @@ __global__ void __launch_bounds__(256) pool3d_kernel(const PoolParams p) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) acc[j] *= inv;
     }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = apply_act(acc[j], p.act);
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + voff(p.y, b, to, ho, wo) + c;
     if constexpr (VEC == 8) {
       uint4 o;
@@ -409,8 +411,69 @@ __global__ void __launch_bounds__(256) head_fc_kernel(const float* feat, int Cin
       float v = logit[k];
       if (act == 2) v = fmaxf(v, 0.f);
       else if (act == 3) v = 1.f / (1.f + expf(-v));
+      else if (act == 4) v = fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);  // hard sigmoid: relu6(x + 3) / 6
       out[(long long)b * K + k] = v;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- channel plumbing
+// dst = channel_shuffle(cat(a, b), groups): input channel c = i * (C / groups) + j lands at j * groups + i
+// (shufflenetv2_helper.py:32-43 / shufflenet_helper.py:24-34); b may be empty (cb == 0).
+__global__ void __launch_bounds__(256) shuffle_concat_kernel(const View a, const View b, int cb, int groups, const View y) {
+  const int C = y.C;
+  const int cpg = C / groups;
+  const long long total = (long long)y.B * y.T * y.H * y.W * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int o = idx % C;
+    long long pos = idx / C;
+    const int w = pos % y.W;
+    pos /= y.W;
+    const int h = pos % y.H;
+    pos /= y.H;
+    const int t = pos % y.T;
+    const int bb = pos / y.T;
+    const int c = (o % groups) * cpg + o / groups;  // source channel in cat(a, b)
+    const __nv_bfloat16 v = c < a.C ? reinterpret_cast<const __nv_bfloat16*>(a.ptr)[voff(a, bb, t, h, w) + c]
+                                    : reinterpret_cast<const __nv_bfloat16*>(b.ptr)[voff(b, bb, t, h, w) + (c - a.C)];
+    reinterpret_cast<__nv_bfloat16*>(y.ptr)[voff(y, bb, t, h, w) + o] = v;
+  }
+}
+// y = act(a + b) elementwise
+__global__ void __launch_bounds__(256) eltwise_add_kernel(const View a, const View b, const View y, int act) {
+  const int C = y.C;
+  const long long total = (long long)y.B * y.T * y.H * y.W * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = idx % C;
+    long long pos = idx / C;
+    const int w = pos % y.W;
+    pos /= y.W;
+    const int h = pos % y.H;
+    pos /= y.H;
+    const int t = pos % y.T;
+    const int bb = pos / y.T;
+    const float v = ldbf(a.ptr, voff(a, bb, t, h, w) + c) + ldbf(b.ptr, voff(b, bb, t, h, w) + c);
+    reinterpret_cast<__nv_bfloat16*>(y.ptr)[voff(y, bb, t, h, w) + c] = __float2bfloat16(apply_act(v, act));
+  }
+}
+// y = x * scale[b][c]  (squeeze-excite gate, ghostnet_helper.py:46-52)
+__global__ void __launch_bounds__(256) channel_scale_kernel(const View x, const float* __restrict__ scale, const View y) {
+  const int C = y.C;
+  const long long total = (long long)y.B * y.T * y.H * y.W * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = idx % C;
+    long long pos = idx / C;
+    const int w = pos % y.W;
+    pos /= y.W;
+    const int h = pos % y.H;
+    pos /= y.H;
+    const int t = pos % y.T;
+    const int bb = pos / y.T;
+    const float v = ldbf(x.ptr, voff(x, bb, t, h, w) + c) * __ldg(scale + (long long)bb * C + c);
+    reinterpret_cast<__nv_bfloat16*>(y.ptr)[voff(y, bb, t, h, w) + c] = __float2bfloat16(v);
   }
 }
 
@@ -481,13 +544,15 @@ extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {
 }
 
 extern "C" int esf_pool3d(const esf_view* x, const esf_view* y, int32_t kT, int32_t kH, int32_t kW, int32_t sT,
-                          int32_t sH, int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t is_avg, void* stream) {
+                          int32_t sH, int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t is_avg, int32_t act,
+                          void* stream) {
   ESF_CHECK_ARG(view_ok(x) && view_ok(y) && x->C == y->C && x->B == y->B, "esf_pool3d: bad views");
   const int To = (x->T + 2 * pT - kT) / sT + 1, Ho = (x->H + 2 * pH - kH) / sH + 1, Wo = (x->W + 2 * pW - kW) / sW + 1;
   ESF_CHECK_ARG(y->T == To && y->H == Ho && y->W == Wo, "esf_pool3d: output view does not match the pooled shape");
   PoolParams p;
   p.x = to_view(x), p.y = to_view(y);
   p.kT = kT, p.kH = kH, p.kW = kW, p.sT = sT, p.sH = sH, p.sW = sW, p.pT = pT, p.pH = pH, p.pW = pW, p.is_avg = is_avg;
+  p.act = act;
   auto al8 = [](const esf_view* v) {
     return reinterpret_cast<uintptr_t>(v->ptr) % 16 == 0 && v->sW % 8 == 0 && v->sH % 8 == 0 && v->sT % 8 == 0 &&
            v->sB % 8 == 0;
@@ -546,4 +611,35 @@ extern "C" int esf_head_fc(const float* feat, int32_t B, int32_t Cin, const floa
   ESF_CHECK_ARG(smem <= 48 * 1024, "esf_head_fc: Cin + num_classes too large for one block");
   head_fc_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(feat, Cin, w, bias, num_classes, act, out);
   return check_launch("head_fc_kernel");
+}
+
+static bool same_pos(const esf_view* a, const esf_view* b) {
+  return a->B == b->B && a->T == b->T && a->H == b->H && a->W == b->W;
+}
+
+extern "C" int esf_shuffle_concat(const esf_view* a, const esf_view* b, int32_t groups, const esf_view* y, void* stream) {
+  ESF_CHECK_ARG(view_ok(a) && view_ok(y) && groups >= 1, "esf_shuffle_concat: null/bad argument");
+  const int cb = (b && b->ptr) ? b->C : 0;
+  ESF_CHECK_ARG(same_pos(a, y) && (cb == 0 || (view_ok(b) && same_pos(b, y))) && a->C + cb == y->C && y->C % groups == 0,
+                "esf_shuffle_concat: shape mismatch");
+  const long long total = (long long)y->B * y->T * y->H * y->W * y->C;
+  shuffle_concat_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      to_view(a), cb ? to_view(b) : to_view(a), cb, groups, to_view(y));
+  return check_launch("shuffle_concat_kernel");
+}
+
+extern "C" int esf_eltwise_add(const esf_view* a, const esf_view* b, const esf_view* y, int32_t act, void* stream) {
+  ESF_CHECK_ARG(view_ok(a) && view_ok(b) && view_ok(y) && same_pos(a, y) && same_pos(b, y) && a->C == y->C && b->C == y->C,
+                "esf_eltwise_add: null/bad argument");
+  const long long total = (long long)y->B * y->T * y->H * y->W * y->C;
+  eltwise_add_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(to_view(a), to_view(b),
+                                                                                          to_view(y), act);
+  return check_launch("eltwise_add_kernel");
+}
+
+extern "C" int esf_channel_scale(const esf_view* x, const float* scale, const esf_view* y, void* stream) {
+  ESF_CHECK_ARG(view_ok(x) && view_ok(y) && scale && same_pos(x, y) && x->C == y->C, "esf_channel_scale: null/bad argument");
+  const long long total = (long long)y->B * y->T * y->H * y->W * y->C;
+  channel_scale_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(to_view(x), scale, to_view(y));
+  return check_launch("channel_scale_kernel");
 }

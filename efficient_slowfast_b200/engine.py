@@ -132,6 +132,22 @@ class Plan:
                   "%dx%dx%d s%s %d->%d @%s" % (kt, kh, kw, "".join(map(str, stride)), cin, cout, tuple(y.shape[1:4])),
                   flops=2.0 * m * cout * cin * kt * kh * kw, nbytes=self._nbytes(x, y, res) + wp.numel() * 2)
 
+    @staticmethod
+    def _aligned(t):
+        """True when a view can be addressed by TMA / 16-byte vector accesses."""
+        if t is None:
+            return True
+        q = 16 // t.element_size()
+        return t.data_ptr() % 16 == 0 and all(st % q == 0 for st in t.stride()[:4])
+
+    def conv(self, x, y, w_folded, bias, stride=(1, 1, 1), padding=(0, 0, 0), dilation=(1, 1, 1), groups=1,
+             act=rt.ACT_NONE, res=None, out_dtype=rt.BF16):
+        """Conv3d + folded BN (+ residual) + activation: tensor-core implicit GEMM when the layer is dense and its
+        views are 16-byte addressable, CUDA-core direct conv otherwise (grouped / depthwise / odd channel counts)."""
+        if groups == 1 and x.shape[4] >= 8 and self._aligned(x) and self._aligned(y) and self._aligned(res):
+            return self.conv_igemm(x, y, w_folded, bias, stride, padding, dilation, act, res, out_dtype)
+        return self.conv_direct(x, y, w_folded, bias, stride, padding, dilation, groups, act, res, out_dtype)
+
     def conv_direct(self, x, y, w_folded, bias, stride=(1, 1, 1), padding=(0, 0, 0), dilation=(1, 1, 1), groups=1,
                     act=rt.ACT_NONE, res=None, out_dtype=rt.BF16):
         wd = self.tensor(w_folded.permute(0, 2, 3, 4, 1))  # [Cout][kT][kH][kW][Cin/g]
@@ -192,13 +208,50 @@ class Plan:
                   "%dx%dx%d %d->%d banded" % (kt, kh, kw, Cin, cout), flops=2.0 * m * cout * Cin * kt * kh * kw,
                   nbytes=self._nbytes(xp, y) + wb.numel() * 2)
 
-    def pool(self, x, y, kernel, stride, padding, is_avg=False):
+    def pool(self, x, y, kernel, stride, padding, is_avg=False, act=rt.ACT_NONE):
         xv, yv = rt.view(x), rt.view(y)
         self.keep += [xv, yv]
         L = rt.lib()
         self._add(lambda s: rt.check(
-            L.esf_pool3d(ctypes.byref(xv), ctypes.byref(yv), *kernel, *stride, *padding, int(is_avg), s), "esf_pool3d"),
-            "pool", "%s" % (tuple(kernel),), nbytes=self._nbytes(x, y))
+            L.esf_pool3d(ctypes.byref(xv), ctypes.byref(yv), *kernel, *stride, *padding, int(is_avg), act, s),
+            "esf_pool3d"), "pool", "%s" % (tuple(kernel),), nbytes=self._nbytes(x, y))
+
+    def shuffle_concat(self, a, b, groups, y):
+        av, yv = rt.view(a), rt.view(y)
+        bv = rt.view(b) if b is not None else rt.null_view()
+        self.keep += [av, bv, yv]
+        L = rt.lib()
+        self._add(lambda s: rt.check(L.esf_shuffle_concat(ctypes.byref(av), ctypes.byref(bv), groups, ctypes.byref(yv), s),
+                                     "esf_shuffle_concat"), "shuffle", "g%d" % groups, nbytes=2 * self._nbytes(y))
+
+    def eltwise_add(self, a, b, y, act=rt.ACT_NONE):
+        av, bv, yv = rt.view(a), rt.view(b), rt.view(y)
+        self.keep += [av, bv, yv]
+        L = rt.lib()
+        self._add(lambda s: rt.check(L.esf_eltwise_add(ctypes.byref(av), ctypes.byref(bv), ctypes.byref(yv), act, s),
+                                     "esf_eltwise_add"), "add", "", nbytes=3 * self._nbytes(y))
+
+    def squeeze_excite(self, x, y, se):
+        """SqueezeExcite (ghostnet_helper.py:34-52): global mean -> 1x1x1(+bias) -> ReLU -> 1x1x1(+bias) -> hard-sigmoid
+        -> channel scale.  Reuses the head kernels for the pooled MLP."""
+        B, C = x.shape[0], x.shape[4]
+        R = se.conv_reduce.out_channels
+        feat = torch.empty((B, C), dtype=torch.float32, device=self.device)
+        hid = torch.empty((B, R), dtype=torch.float32, device=self.device)
+        gate = torch.empty((B, C), dtype=torch.float32, device=self.device)
+        w1, b1 = self.tensor(se.conv_reduce.weight.reshape(R, C)), self.tensor(se.conv_reduce.bias)
+        w2, b2 = self.tensor(se.conv_expand.weight.reshape(C, R)), self.tensor(se.conv_expand.bias)
+        xv, yv, nv = rt.view(x), rt.view(y), rt.null_view()
+        self.keep += [feat, hid, gate, xv, yv, nv]
+        L = rt.lib()
+        self._add(lambda s: rt.check(L.esf_head_pool(ctypes.byref(xv), ctypes.byref(nv), feat.data_ptr(), s),
+                                     "esf_head_pool"), "se_pool", "", nbytes=self._nbytes(x))
+        self._add(lambda s: rt.check(L.esf_head_fc(feat.data_ptr(), B, C, w1.data_ptr(), b1.data_ptr(), R, rt.HEAD_RELU,
+                                                   hid.data_ptr(), s), "esf_head_fc"), "se_fc", "")
+        self._add(lambda s: rt.check(L.esf_head_fc(hid.data_ptr(), B, R, w2.data_ptr(), b2.data_ptr(), C,
+                                                   rt.HEAD_HARD_SIGMOID, gate.data_ptr(), s), "esf_head_fc"), "se_fc", "")
+        self._add(lambda s: rt.check(L.esf_channel_scale(ctypes.byref(xv), gate.data_ptr(), ctypes.byref(yv), s),
+                                     "esf_channel_scale"), "se_scale", "", nbytes=2 * self._nbytes(x))
 
     def eca_fuse(self, x_fast, y_slice, alpha, eca_weight, bn):
         """MaxPool(alpha,1,1) -> ECA -> BN -> ReLU -> concat slice (custom_video_model_builder.py:131-135)."""
@@ -233,7 +286,7 @@ class Plan:
         w_all = torch.cat(mats, 0).reshape(4 * d, C, 1, 1, 1)
         b_all = torch.cat(biases, 0)
         proj = self.act(B, T, H, W, 4 * d, dtype=torch.float32)
-        self.conv_igemm(x_slow, proj, w_all, b_all, out_dtype=rt.F32)
+        self.conv(x_slow, proj, w_all, b_all, out_dtype=rt.F32)
         L = rt.lib()
         N = T * H * W
         if self.attn_impl == "tcgen05":

@@ -285,6 +285,22 @@ class _PlannedModel(nn.Module):
         out = plan.run()
         return out.clone()
 
+    def _emit_fuse(self, plan, fuse, cur):
+        (sbuf, soff, cs), (fbuf, foff, cf) = cur
+        x_s = sbuf[..., soff:soff + cs]
+        x_f = fbuf[..., foff:foff + cf]
+        if isinstance(fuse, FuseFastAndSlow):
+            # fast -> slow: written behind x_s;  slow -> fast: written in front of x_f.  Both read only stage outputs.
+            plan.eca_fuse(x_f, sbuf[..., cs:cs + cf], fuse.alpha, fuse.attention_channel_f2s.conv.weight, fuse.bn_f2s)
+            d = fuse.downsample_c_of_slow.out_channels
+            plan.position_attention(x_s, fbuf[..., 0:d], fuse.alpha, fuse.downsample_c_of_slow.weight,
+                                    fuse.attention_spatial_s2f, fuse.bn_s2f)
+        else:
+            conv = fuse.conv_f2s
+            w, b = fold_conv_bn(conv.weight, None, fuse.bn)
+            plan.conv(x_f, sbuf[..., cs:cs + conv.out_channels], w, b, stride=tuple(conv.stride),
+                      padding=tuple(conv.padding), act=rt.ACT_RELU)
+
     def debug_buffers(self):
         """name -> channels-last BF16 activation tensors of the live plan (tests only)."""
         for _, plan in self._plans.values():
@@ -485,23 +501,6 @@ class _TwoStreamResNet(_PlannedModel):
                         dilation=tuple(t.b.dilation), act=rt.ACT_RELU)
         w, b = fold_conv_bn(t.c.weight, None, t.c_bn)
         plan.conv_igemm(tb, y, w, b, act=rt.ACT_RELU, res=sc)
-
-    def _emit_fuse(self, plan, fuse, cur):
-        (sbuf, soff, cs), (fbuf, foff, cf) = cur
-        x_s = sbuf[..., soff:soff + cs]
-        x_f = fbuf[..., foff:foff + cf]
-        if isinstance(fuse, FuseFastAndSlow):
-            # fast -> slow: written behind x_s;  slow -> fast: written in front of x_f.  Both read only stage outputs.
-            plan.eca_fuse(x_f, sbuf[..., cs:cs + cf], fuse.alpha, fuse.attention_channel_f2s.conv.weight, fuse.bn_f2s)
-            d = fuse.downsample_c_of_slow.out_channels
-            plan.position_attention(x_s, fbuf[..., 0:d], fuse.alpha, fuse.downsample_c_of_slow.weight,
-                                    fuse.attention_spatial_s2f, fuse.bn_s2f)
-        else:
-            conv = fuse.conv_f2s
-            w, b = fold_conv_bn(conv.weight, None, fuse.bn)
-            plan.conv_igemm(x_f, sbuf[..., cs:cs + conv.out_channels], w, b, stride=tuple(conv.stride),
-                            padding=tuple(conv.padding), act=rt.ACT_RELU)
-
 
 @MODEL_REGISTRY.register()
 class SlowFastDualAttention(_TwoStreamResNet):

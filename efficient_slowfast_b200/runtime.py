@@ -10,7 +10,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "li
 
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 BF16, F32 = 0, 1
-HEAD_NONE, HEAD_SOFTMAX, HEAD_RELU, HEAD_SIGMOID = 0, 1, 2, 3
+HEAD_NONE, HEAD_SOFTMAX, HEAD_RELU, HEAD_SIGMOID, HEAD_HARD_SIGMOID = 0, 1, 2, 3, 4
 
 
 class EsfView(ctypes.Structure):
@@ -64,7 +64,10 @@ def lib():
     L.esf_stem_pack.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     L.esf_stem_igemm_create.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32,
                                         i32, i32, i32, P(EsfView), P(vp)]
-    L.esf_pool3d.argtypes = [P(EsfView), P(EsfView), i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.esf_pool3d.argtypes = [P(EsfView), P(EsfView), i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.esf_shuffle_concat.argtypes = [P(EsfView), P(EsfView), i32, P(EsfView), vp]
+    L.esf_eltwise_add.argtypes = [P(EsfView), P(EsfView), P(EsfView), i32, vp]
+    L.esf_channel_scale.argtypes = [P(EsfView), vp, P(EsfView), vp]
     L.esf_eca_scratch_floats.argtypes = [i32, i32]
     L.esf_eca_scratch_floats.restype = i64
     L.esf_eca_fuse.argtypes = [P(EsfView), i32, vp, i32, vp, vp, vp, P(EsfView), vp]
@@ -78,7 +81,7 @@ def lib():
     L.esf_attn_tc_create.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, i32, P(EsfView), P(vp)]
     L.esf_head_pool.argtypes = [P(EsfView), P(EsfView), vp, vp]
     L.esf_head_fc.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp]
-    for name in ("esf_attn_tc_pack", "esf_attn_tc_create", "esf_stem_geometry", "esf_stem_pack", "esf_stem_igemm_create", "esf_igemm_geometry",
+    for name in ("esf_shuffle_concat", "esf_eltwise_add", "esf_channel_scale", "esf_attn_tc_pack", "esf_attn_tc_create", "esf_stem_geometry", "esf_stem_pack", "esf_stem_igemm_create", "esf_igemm_geometry",
                  "esf_conv_igemm_create", "esf_op_launch", "esf_conv_direct", "esf_stem_conv",
                  "esf_pool3d", "esf_eca_fuse", "esf_attn_pack", "esf_attn_fused", "esf_head_pool", "esf_head_fc"):
         getattr(L, name).restype = ctypes.c_int

@@ -110,7 +110,16 @@ int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int32_t T, int
  * replaces ResNetBasicStem.pool_layer (stem_helper.py:169-171), the 3x3x3 stem pools
  * (stem_helper.py:243,281) and the ShuffleNet shortcut AvgPool3d (shufflenet_helper.py:68-73). */
 int esf_pool3d(const esf_view* x, const esf_view* y, int32_t kT, int32_t kH, int32_t kW, int32_t sT, int32_t sH,
-               int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t is_avg, void* stream);
+               int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t is_avg, int32_t act, void* stream);
+
+/* ---- channel plumbing of the efficient backbones (BF16 views, any channel count) ---------------------------
+ * esf_shuffle_concat: y = channel_shuffle(cat(a, b), groups)   (shufflenetv2_helper.py:32-43,104-112,
+ *                     shufflenet_helper.py:24-34,77); b may be NULL.
+ * esf_eltwise_add:    y = act(a + b)                           (ghostnet_helper.py:161-162 residual add)
+ * esf_channel_scale:  y = x * scale[b][c]                      (SqueezeExcite gate, ghostnet_helper.py:46-52) */
+int esf_shuffle_concat(const esf_view* a, const esf_view* b, int32_t groups, const esf_view* y, void* stream);
+int esf_eltwise_add(const esf_view* a, const esf_view* b, const esf_view* y, int32_t act, void* stream);
+int esf_channel_scale(const esf_view* x, const float* scale, const esf_view* y, void* stream);
 
 /* ---- CMDA fast->slow: MaxPool(alpha,1,1) -> ECA -> BN -> ReLU -> write into the slow concat slice ------
  * replaces FuseFastAndSlow.forward lines custom_video_model_builder.py:131-135 and ECA.forward
@@ -145,7 +154,8 @@ int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int32_t H, int3
 
 /* ---- head: global average pool of each pathway -> concat -> Linear -> softmax/ReLU/none -----------------
  * replaces ResNetBasicHead.forward eval branch (head_helper.py:198-223) and the efficient heads'
- * pool+classifier tails.  feat: FP32 scratch (B, C0 + C1).  act: 0 none (logits), 1 softmax, 2 relu, 3 sigmoid. */
+ * pool+classifier tails.  feat: FP32 scratch (B, C0 + C1).  act: 0 none (logits), 1 softmax, 2 relu, 3 sigmoid,
+ * 4 hard-sigmoid (the same kernel serves the squeeze-excite MLP of ghostnet_helper.py:46-52). */
 int esf_head_pool(const esf_view* x0, const esf_view* x1, float* feat, void* stream);
 int esf_head_fc(const float* feat, int32_t B, int32_t Cin, const float* w, const float* bias, int32_t num_classes,
                 int32_t act, float* out, void* stream);

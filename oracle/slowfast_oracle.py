@@ -216,8 +216,14 @@ FORWARDS = {
 
 
 def forward(cfg, sd, inputs, dtype=torch.float32, taps=None):
+    """Dispatch on cfg.MODEL.MODEL_NAME over every model the oracle restates (R50 models here, efficient models in
+    efficient_oracle.py)."""
+    fwd = FORWARDS.get(cfg.MODEL.MODEL_NAME)
+    if fwd is None:
+        from . import efficient_oracle
+        fwd = efficient_oracle.FORWARDS[cfg.MODEL.MODEL_NAME]
     with torch.no_grad():
-        return FORWARDS[cfg.MODEL.MODEL_NAME](cfg, sd, inputs, dtype=dtype, taps=taps)
+        return fwd(cfg, sd, inputs, dtype=dtype, taps=taps)
 
 
 def pack_pathway_output(frames, alpha):

@@ -57,8 +57,8 @@ def make_case(name):
         for sname in stages:
             hooks.append(getattr(model, sname).register_forward_hook(
                 lambda m, i, o, sname=sname: taps.__setitem__(sname, [t.detach().clone() for t in o])))
-        hooks.append(model.head.projection.register_forward_hook(
-            lambda m, i, o: taps.__setitem__("logits", o.detach().clone())))
+        fc = [m for m in model.head.modules() if isinstance(m, torch.nn.Linear)][-1]
+        hooks.append(fc.register_forward_hook(lambda m, i, o: taps.__setitem__("logits", o.detach().clone())))
         x = recipe.seeded_clip(b, frames, crop, seed=1)
         with torch.no_grad():
             y = model([t.clone() for t in recipe.pack_pathway_output(x, alpha)])
@@ -86,7 +86,7 @@ def make_default_init():
     """Corner case: the reference's own seeded default init (gamma = 0, zero final BN, fresh BN stats)."""
     out = {}
     for name, spec in recipe.CASES.items():
-        if spec.get("stress"):
+        if spec.get("stress") or not name.endswith("_r50"):
             continue
         cfg = ref_shim.get_cfg(spec["yaml"], spec["opts"])
         torch.manual_seed(1234)

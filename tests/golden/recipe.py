@@ -45,8 +45,8 @@ def seeded_state_dict(template, seed=0, bn_stats=None, stress=False):
                 t = torch.zeros(shape) if leaf == "running_mean" else torch.ones(shape)
         elif is_bn and leaf == "weight":
             t = torch.rand(shape, generator=g) + 0.5
-            if key.endswith("c_bn.weight") and not stress:
-                t = (t - 0.5) * 0.3 + 0.15
+            if (key.endswith("c_bn.weight") or key.endswith(".bn3.weight")) and not stress:
+                t = (t - 0.5) * 0.3 + 0.15   # last BN of a residual branch (R50 bottleneck, ShuffleNet unit)
         elif is_bn and leaf == "bias":
             t = torch.rand(shape, generator=g) * 0.4 - 0.2
         elif leaf == "gamma":
@@ -97,6 +97,12 @@ CASES = {
     "slowfast_r50_stress": dict(
         model="SlowFast", yaml="configs/Kinetics/SLOWFAST_4x16_R50.yaml", stress=True,
         opts=["MULTIGRID.SHORT_CYCLE", True], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),
+    "shufflenetv2_w05": dict(   # BASELINE configs[0]: SlowFastShuffleNetV2 width 0.5
+        model="SlowFastShuffleNetV2", yaml="configs/Kinetics/SLOWFAST_SHUFFLENETV2_8x8_R50_stepwise_multigrid.yaml",
+        opts=["SLOWFAST.WIDTH_MULTI", 0.5], calib=(2, 16, 112), inputs=[("s112", 2, 16, 112), ("s224", 1, 32, 224)]),
+    "shufflenet_w2g3": dict(    # BASELINE configs[4]: SlowFastShuffleNet width 2.0 groups 3, Jester shape
+        model="SlowFastShuffleNet", yaml="configs/Jester/SLOWFAST_SHUFFLENET_8x8_R50_stepwise_multigrid.yaml",
+        opts=[], calib=(2, 16, 112), inputs=[("s112", 2, 16, 112), ("s64", 2, 16, 64)]),
     "dual_r50_stress": dict(
         model="SlowFastDualAttention", yaml="configs/Kinetics/SLOWFAST_DUAL_8x8_R50_stepwise_multigrid.yaml",
         stress=True, opts=[], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),

@@ -23,6 +23,10 @@ def case_cfg(name):
     elif name in ("slowfast_r50", "slowfast_r50_stress"):
         cfg = esf.slowfast_4x16_r50_cfg()
         cfg.MULTIGRID.SHORT_CYCLE = True
+    elif name == "shufflenetv2_w05":
+        cfg = esf.slowfast_shufflenetv2_cfg(0.5)
+    elif name == "shufflenet_w2g3":
+        cfg = esf.slowfast_shufflenet_cfg(2.0, 3)
     else:
         raise KeyError(name)
     cfg.NUM_GPUS = 0

@@ -298,6 +298,52 @@ def test_attention_tcgen05(esf_lib, d, T, H, W, qk_scale):
     assert (ybuf[..., d:] == 0).all()
 
 
+def test_channel_plumbing_kernels(esf_lib):
+    """shuffle-concat, elementwise add, SE channel scale, avg-pool + ReLU: bit-level semantics vs torch on BF16 data."""
+    g = torch.Generator().manual_seed(11)
+    B, T, H, W = 2, 3, 5, 7
+    a = _rand_act(g, B, T, H, W, 9).to(DEV)
+    b = _rand_act(g, B, T, H, W, 6).to(DEV)
+    plan = Plan(DEV)
+    ybuf = torch.zeros(B, T, H, W, 20, dtype=torch.bfloat16, device=DEV)
+    plan.shuffle_concat(a, b, 3, ybuf[..., 2:17])
+    y2 = torch.zeros(B, T, H, W, 9, dtype=torch.bfloat16, device=DEV)
+    plan.shuffle_concat(a, None, 3, y2)
+    a2 = _rand_act(g, B, T, H, W, 9).to(DEV)
+    y3 = torch.zeros(B, T, H, W, 9, dtype=torch.bfloat16, device=DEV)
+    plan.eltwise_add(a, a2, y3, act=rt.ACT_RELU)
+    plan.launch_all()
+    torch.cuda.synchronize()
+
+    def shuffle(x, groups):   # NCDHW reference semantics (shufflenetv2_helper.py:32-43)
+        bb, c, t, h, w = x.shape
+        return x.view(bb, groups, c // groups, t, h, w).permute(0, 2, 1, 3, 4, 5).reshape(bb, c, t, h, w)
+    ref = shuffle(torch.cat([_to_ncdhw(a.cpu()), _to_ncdhw(b.cpu())], 1), 3)
+    assert torch.equal(_to_ncdhw(ybuf[..., 2:17].cpu()), ref)
+    assert (ybuf[..., :2] == 0).all() and (ybuf[..., 17:] == 0).all()
+    assert torch.equal(_to_ncdhw(y2.cpu()), shuffle(_to_ncdhw(a.cpu()), 3))
+    assert torch.equal(y3.cpu().float(), (a.cpu().float() + a2.cpu().float()).relu().bfloat16().float())
+    # squeeze-excite
+    C, R = 12, 4
+    x = _rand_act(g, B, T, H, W, C).to(DEV)
+    se = torch.nn.Module()
+    se.conv_reduce = torch.nn.Conv3d(C, R, 1)
+    se.conv_expand = torch.nn.Conv3d(R, C, 1)
+    y = torch.zeros_like(x)
+    plan = Plan(DEV)
+    plan.squeeze_excite(x, y, se)
+    plan.pool(x, torch.zeros(B, T, 3, 4, C, dtype=torch.bfloat16, device=DEV), (1, 3, 3), (1, 2, 2), (0, 1, 1),
+              is_avg=True, act=rt.ACT_RELU)
+    plan.launch_all()
+    torch.cuda.synchronize()
+    xr = _to_ncdhw(x.cpu())
+    with torch.no_grad():
+        gate = F.relu6(se.conv_expand(F.relu(se.conv_reduce(xr.mean((2, 3, 4), keepdim=True)))) + 3.0) / 6.0
+    ref = xr * gate
+    assert (_to_ncdhw(y.cpu()) - ref).abs().max().item() <= 8e-3 * ref.abs().max().item()
+    pooled = plan.keep[-1]
+
+
 def test_head(esf_lib):
     g = torch.Generator().manual_seed(9)
     B = 3

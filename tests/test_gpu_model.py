@@ -27,14 +27,18 @@ def _run(name, tag):
 
 
 @pytest.mark.parametrize("name,tag", [("dual_r50", "s64"), ("slowfast_r50", "s64"), ("dual_r50", "s224"),
-                                      ("slowfast_r50", "s224")])
+                                      ("slowfast_r50", "s224"), ("shufflenetv2_w05", "s112"),
+                                      ("shufflenetv2_w05", "s224"), ("shufflenet_w2g3", "s112"),
+                                      ("shufflenet_w2g3", "s64")])
 def test_model_matches_reference_golden(esf_lib, name, tag):
     cfg, model, gold, y = _run(name, tag)
     ref = torch.as_tensor(gold[tag + "/probs"])
     err = helpers.rel_err(y, ref)
     print("%s/%s: rel err of probs %.3e (tol %.0e)" % (name, tag, err, BF16_TOL))
     assert err <= BF16_TOL
-    assert torch.equal(y.argmax(1), ref.argmax(1))
+    top2 = torch.topk(ref, 2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) / top2[:, 0] > 2 * BF16_TOL   # argmax where the reference itself is decided
+    assert torch.equal(y.argmax(1)[decided], ref.argmax(1)[decided])
     assert abs(y.sum(1) - 1).max() < 1e-4
     # second call replays the captured CUDA graph and must give the same answer
     xs = [t.cuda() for t in helpers.case_inputs(name, tag)]
@@ -43,16 +47,19 @@ def test_model_matches_reference_golden(esf_lib, name, tag):
     assert torch.equal(y, y2)
 
 
-@pytest.mark.parametrize("name", ["dual_r50", "slowfast_r50"])
+@pytest.mark.parametrize("name", ["dual_r50", "slowfast_r50", "shufflenetv2_w05", "shufflenet_w2g3"])
 def test_stage_outputs_match_oracle(esf_lib, name):
     """Localises an error to a stage: every concat buffer of the plan vs the oracle's tap of the same stage."""
-    cfg, model, gold, y = _run(name, "s64")
+    tag = "s64" if name.endswith("_r50") else "s112"
+    cfg, model, gold, y = _run(name, tag)
     taps = {}
-    yo = O.forward(cfg, {k: v.cpu() for k, v in model.state_dict().items()}, helpers.case_inputs(name, "s64"),
+    yo = O.forward(cfg, {k: v.cpu() for k, v in model.state_dict().items()}, helpers.case_inputs(name, tag),
                    taps=taps)
     bufs = model.debug_buffers()
     report = []
     for sname in STAGES:
+        if sname not in taps or (not name.endswith("_r50") and not sname.endswith("_fuse")):
+            continue
         for pw in range(2):
             if sname.endswith("_fuse"):
                 key, ref = "%s_cat%d" % (sname[:-5], pw), taps[sname][pw]

@@ -10,7 +10,9 @@ from oracle import slowfast_oracle as O
 
 @pytest.mark.parametrize("name,tag", [("dual_r50", "s64"), ("slowfast_r50", "s64"), ("dual_r50", "s224"),
                                       ("slowfast_r50", "s224"), ("slowfast_r50_stress", "s64"),
-                                      ("dual_r50_stress", "s64")])
+                                      ("dual_r50_stress", "s64"), ("shufflenetv2_w05", "s112"),
+                                      ("shufflenetv2_w05", "s224"), ("shufflenet_w2g3", "s112"),
+                                      ("shufflenet_w2g3", "s64")])
 def test_oracle_matches_reference_golden(name, tag):
     cfg, model, gold = helpers.case_model_and_weights(name)
     xs = helpers.case_inputs(name, tag)
@@ -19,11 +21,13 @@ def test_oracle_matches_reference_golden(name, tag):
     # Not bit-exact by construction: FP32 CPU kernels re-associate sums differently on another host, and the
     # row-chunked softmax over N = 25 088 keys sums in a different order than the reference's materialised N x N
     # form (measured FP32 noise floor of this model: ~2e-4, SURVEY.md finding 8).
-    tol = 1e-3 if (name, tag) == ("dual_r50", "s224") else 1e-4
+    tol = 1e-3 if tag == "s224" and name != "slowfast_r50" else 1e-4
     assert helpers.rel_err(y, gold[tag + "/probs"]) < tol
     assert helpers.rel_err(taps["logits"].reshape(y.shape[0], -1), gold[tag + "/logits"]) < tol
     assert torch.equal(y.argmax(1), torch.as_tensor(gold[tag + "/probs"]).argmax(1))
     for sname in ("s1", "s1_fuse", "s2", "s2_fuse", "s3", "s3_fuse", "s4", "s4_fuse", "s5"):
+        if sname not in taps:
+            continue            # the ShuffleNet models end at s4_fuse
         for pw in range(2):
             t = taps[sname][pw]
             assert list(t.shape) == list(gold["%s/%s/%d/shape" % (tag, sname, pw)])
