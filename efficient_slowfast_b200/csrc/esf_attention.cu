@@ -285,6 +285,47 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnParams p) 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- generic fallback
+// Any head dim, FP32 math straight from the projection rows [x_d | q | k | v]: one warp per query, logits staged in
+// shared memory.  Used only where the tensor-core kernels do not apply (d > 128, which in the reference's models
+// only occurs with N <= 392 keys: SlowFastShuffleNet s4_fuse, d = 240).
+__global__ void __launch_bounds__(128) attn_generic_kernel(const float* __restrict__ proj, int N, int T, int H, int W,
+                                                           int d, float gamma, const float* __restrict__ bn_scale,
+                                                           const float* __restrict__ bn_shift, int alpha,
+                                                           __nv_bfloat16* __restrict__ y, long long ysB, long long ysT,
+                                                           long long ysH, long long ysW) {
+  extern __shared__ float srow[];  // [4 warps][N]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 4 + warp;
+  if (i >= N) return;
+  float* s = srow + warp * N;
+  const float* base = proj + (long long)b * N * 4 * d;
+  const float* qi = base + (long long)i * 4 * d + d;
+  float m = -CUDART_INF_F;
+  for (int j = 0; j < N; ++j) {
+    const float* kj = base + (long long)j * 4 * d + 2 * d;
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) acc = fmaf(qi[c], kj[c], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s[j] = acc;
+    m = fmaxf(m, acc);
+  }
+  __syncwarp();
+  float l = 0.f;
+  for (int j = 0; j < N; ++j) l += expf(s[j] - m);
+  const int HW = H * W;
+  const int t = i / HW, hw = i % HW, hh = hw / W, ww = hw % W;
+  for (int c = lane; c < d; c += 32) {
+    float o = 0.f;
+    for (int j = 0; j < N; ++j) o = fmaf(expf(s[j] - m), base[(long long)j * 4 * d + 3 * d + c], o);
+    const float a = fmaf(gamma, o / l, base[(long long)i * 4 * d + c]);
+    const __nv_bfloat16 v = __float2bfloat16(fmaxf(fmaf(a, bn_scale[c], bn_shift[c]), 0.f));
+    for (int r = 0; r < alpha; ++r) y[b * ysB + (long long)(t * alpha + r) * ysT + hh * ysH + ww * ysW + c] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- packing
 struct PackGeom {
   int DV, DK, split;
@@ -419,4 +460,25 @@ extern "C" int esf_attn_fused(const void* packed, int32_t B, int32_t T, int32_t 
     case 128: return launch_attn<128, 128, 1>(p, s);
   }
   return set_error(ESF_ERR_UNSUPPORTED, "esf_attn_fused: no kernel for DV=%d", g.DV);
+}
+
+extern "C" int esf_attn_generic(const float* proj, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d, float gamma,
+                                const float* bn_scale, const float* bn_shift, int32_t alpha,
+                                const esf_view* y_fast_slice, void* stream) {
+  ESF_CHECK_ARG(proj && bn_scale && bn_shift && view_ok(y_fast_slice) && d > 0, "esf_attn_generic: null/bad argument");
+  const esf_view* y = y_fast_slice;
+  ESF_CHECK_ARG(y->B == B && y->T == T * alpha && y->H == H && y->W == W && y->C == d,
+                "esf_attn_generic: output slice shape mismatch");
+  const int N = T * H * W;
+  const size_t smem = (size_t)4 * N * sizeof(float);
+  ESF_CHECK_ARG(smem <= 160 * 1024, "esf_attn_generic: N = %d too large for the fallback kernel", N);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ESF_CUDA(cudaFuncSetAttribute(attn_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  attn_generic_kernel<<<dim3(cdiv(N, 4), B), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      proj, N, T, H, W, d, gamma, bn_scale, bn_shift, alpha, static_cast<__nv_bfloat16*>(y->ptr), y->sB, y->sT, y->sH,
+      y->sW);
+  return check_launch("attn_generic_kernel");
 }

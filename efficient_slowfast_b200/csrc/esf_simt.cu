@@ -365,14 +365,14 @@ __global__ void __launch_bounds__(256) head_pool_kernel(const View x, float* fea
 }
 
 // out[b][k] = act(sum_c feat[b][c] * w[k][c] + bias[k]); one block per clip, one warp per class (strided)
-__global__ void __launch_bounds__(256) head_fc_kernel(const float* feat, int Cin, const float* w, const float* bias,
-                                                      int K, int act, float* out) {
+__global__ void __launch_bounds__(256) head_fc_kernel(const float* feat, int Cin, int feat_stride, const float* w,
+                                                      const float* bias, int K, int act, float* out, int out_stride) {
   extern __shared__ float sm[];  // feat[Cin], logits[K]
   float* f = sm;
   float* logit = sm + Cin;
   __shared__ float red[32];
   const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < Cin; c += blockDim.x) f[c] = feat[(long long)b * Cin + c];
+  for (int c = threadIdx.x; c < Cin; c += blockDim.x) f[c] = feat[(long long)b * feat_stride + c];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int k = warp; k < K; k += nw) {
@@ -405,14 +405,14 @@ __global__ void __launch_bounds__(256) head_fc_kernel(const float* feat, int Cin
     __syncthreads();
     s = 0.f;
     for (int i = 0; i < nw; ++i) s += red[i];
-    for (int k = threadIdx.x; k < K; k += blockDim.x) out[(long long)b * K + k] = logit[k] / s;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) out[(long long)b * out_stride + k] = logit[k] / s;
   } else {
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
       float v = logit[k];
       if (act == 2) v = fmaxf(v, 0.f);
       else if (act == 3) v = 1.f / (1.f + expf(-v));
       else if (act == 4) v = fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);  // hard sigmoid: relu6(x + 3) / 6
-      out[(long long)b * K + k] = v;
+      out[(long long)b * out_stride + k] = v;
     }
   }
 }
@@ -604,12 +604,15 @@ extern "C" int esf_head_pool(const esf_view* x0, const esf_view* x1, float* feat
   return check_launch("head_pool_kernel");
 }
 
-extern "C" int esf_head_fc(const float* feat, int32_t B, int32_t Cin, const float* w, const float* bias,
-                           int32_t num_classes, int32_t act, float* out, void* stream) {
+extern "C" int esf_head_fc(const float* feat, int32_t B, int32_t Cin, int32_t feat_stride, const float* w,
+                           const float* bias, int32_t num_classes, int32_t act, float* out, int32_t out_stride,
+                           void* stream) {
   ESF_CHECK_ARG(feat && w && bias && out && B > 0 && Cin > 0 && num_classes > 0, "esf_head_fc: null/bad argument");
   const size_t smem = (size_t)(Cin + num_classes) * sizeof(float);
   ESF_CHECK_ARG(smem <= 48 * 1024, "esf_head_fc: Cin + num_classes too large for one block");
-  head_fc_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(feat, Cin, w, bias, num_classes, act, out);
+  ESF_CHECK_ARG(feat_stride >= Cin && out_stride >= num_classes, "esf_head_fc: strides smaller than the row lengths");
+  head_fc_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(feat, Cin, feat_stride, w, bias, num_classes, act,
+                                                                      out, out_stride);
   return check_launch("head_fc_kernel");
 }
 

@@ -246,10 +246,10 @@ class Plan:
         L = rt.lib()
         self._add(lambda s: rt.check(L.esf_head_pool(ctypes.byref(xv), ctypes.byref(nv), feat.data_ptr(), s),
                                      "esf_head_pool"), "se_pool", "", nbytes=self._nbytes(x))
-        self._add(lambda s: rt.check(L.esf_head_fc(feat.data_ptr(), B, C, w1.data_ptr(), b1.data_ptr(), R, rt.HEAD_RELU,
-                                                   hid.data_ptr(), s), "esf_head_fc"), "se_fc", "")
-        self._add(lambda s: rt.check(L.esf_head_fc(hid.data_ptr(), B, R, w2.data_ptr(), b2.data_ptr(), C,
-                                                   rt.HEAD_HARD_SIGMOID, gate.data_ptr(), s), "esf_head_fc"), "se_fc", "")
+        self._add(lambda s: rt.check(L.esf_head_fc(feat.data_ptr(), B, C, C, w1.data_ptr(), b1.data_ptr(), R, rt.HEAD_RELU,
+                                                   hid.data_ptr(), R, s), "esf_head_fc"), "se_fc", "")
+        self._add(lambda s: rt.check(L.esf_head_fc(hid.data_ptr(), B, R, R, w2.data_ptr(), b2.data_ptr(), C,
+                                                   rt.HEAD_HARD_SIGMOID, gate.data_ptr(), C, s), "esf_head_fc"), "se_fc", "")
         self._add(lambda s: rt.check(L.esf_channel_scale(ctypes.byref(xv), gate.data_ptr(), ctypes.byref(yv), s),
                                      "esf_channel_scale"), "se_scale", "", nbytes=2 * self._nbytes(x))
 
@@ -289,6 +289,17 @@ class Plan:
         self.conv(x_slow, proj, w_all, b_all, out_dtype=rt.F32)
         L = rt.lib()
         N = T * H * W
+        if d > 128:
+            scale, shift = bn_affine(bn)
+            sc, sh = self.tensor(scale), self.tensor(shift)
+            gamma = float(att.gamma.detach().float().item())
+            yv = rt.view(y_slice)
+            self.keep.append(yv)
+            self._add(lambda s: rt.check(
+                L.esf_attn_generic(proj.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(), sh.data_ptr(), alpha,
+                                   ctypes.byref(yv), s), "esf_attn_generic"), "attention", "N=%d d=%d generic" % (N, d),
+                flops=4.0 * B * N * N * d, exps=float(B) * N * N, nbytes=self._nbytes(proj, y_slice))
+            return
         if self.attn_impl == "tcgen05":
             nbytes = int(L.esf_attn_tc_pack_bytes(B, N, d))
             if nbytes < 0:
@@ -342,8 +353,36 @@ class Plan:
         self._add(lambda s: rt.check(L.esf_head_pool(ctypes.byref(v0), ctypes.byref(v1), feat.data_ptr(), s),
                                      "esf_head_pool"), "head_pool", "", nbytes=self._nbytes(*xs), launches=len(xs))
         self._add(lambda s: rt.check(
-            L.esf_head_fc(feat.data_ptr(), B, cin, w.data_ptr(), b.data_ptr(), K, act, out.data_ptr(), s),
+            L.esf_head_fc(feat.data_ptr(), B, cin, cin, w.data_ptr(), b.data_ptr(), K, act, out.data_ptr(), K, s),
             "esf_head_fc"), "head_fc", "", flops=2.0 * B * cin * K, nbytes=self._nbytes(feat, w, out))
+        self.out = out
+        return out
+
+    def pooled_fc(self, x, weight, bias, act, out, out_stride):
+        """global mean over (T,H,W) of one activation -> FC (+bias, act) -> `out` (FP32 rows of stride out_stride):
+        the `avg_pool3d -> conv_head_{slow,fast} -> ReLU` tail of GhostNetBasicHead (head_helper.py:676-688)."""
+        B, C = x.shape[0], x.shape[4]
+        K = weight.shape[0]
+        feat = torch.empty((B, C), dtype=torch.float32, device=self.device)
+        w, b = self.tensor(weight.reshape(K, C)), self.tensor(bias)
+        xv, nv = rt.view(x), rt.null_view()
+        self.keep += [feat, xv, nv, out]
+        L = rt.lib()
+        self._add(lambda s: rt.check(L.esf_head_pool(ctypes.byref(xv), ctypes.byref(nv), feat.data_ptr(), s),
+                                     "esf_head_pool"), "head_pool", "", nbytes=self._nbytes(x))
+        self._add(lambda s: rt.check(L.esf_head_fc(feat.data_ptr(), B, C, C, w.data_ptr(), b.data_ptr(), K, act,
+                                                   out.data_ptr(), out_stride, s), "esf_head_fc"), "head_fc", "")
+
+    def fc(self, feat, weight, bias, act):
+        """out = act(feat @ weight^T + bias) on FP32 rows (final classifier of the GhostNet head)."""
+        B, cin = feat.shape
+        K = weight.shape[0]
+        out = torch.empty((B, K), dtype=torch.float32, device=self.device)
+        w, b = self.tensor(weight), self.tensor(bias)
+        self.keep += [out, feat]
+        L = rt.lib()
+        self._add(lambda s: rt.check(L.esf_head_fc(feat.data_ptr(), B, cin, cin, w.data_ptr(), b.data_ptr(), K, act,
+                                                   out.data_ptr(), K, s), "esf_head_fc"), "head_fc", "")
         self.out = out
         return out
 

@@ -459,3 +459,528 @@ class SlowFastShuffleNet(_EfficientBase):
         act = {"softmax": rt.HEAD_SOFTMAX, "sigmoid": rt.HEAD_SIGMOID}[self.head.act_func]
         lin = self.head.classifier[1]
         plan.head([c[0] for c in cur], lin.weight, lin.bias, act)
+
+
+# ================================================================================================ MobileNetV2
+class MBInvertedResidual(_Holder):
+    """mobilenetv2_helper.py:30-68 (class name `InvertedResidual` in the reference's module)."""
+
+    def __init__(self, inp, oup, stride, expand_ratio):
+        super().__init__()
+        self.stride = stride
+        hidden_dim = round(inp * expand_ratio)
+        self.use_res_connect = self.stride == (1, 1, 1) and inp == oup
+        if expand_ratio == 1:
+            self.conv = nn.Sequential(
+                nn.Conv3d(hidden_dim, hidden_dim, 3, stride, 1, groups=hidden_dim, bias=False),
+                nn.BatchNorm3d(hidden_dim), nn.ReLU6(inplace=True),
+                nn.Conv3d(hidden_dim, oup, 1, 1, 0, bias=False), nn.BatchNorm3d(oup))
+        else:
+            self.conv = nn.Sequential(
+                nn.Conv3d(inp, hidden_dim, 1, 1, 0, bias=False), nn.BatchNorm3d(hidden_dim), nn.ReLU6(inplace=True),
+                nn.Conv3d(hidden_dim, hidden_dim, 3, stride, 1, groups=hidden_dim, bias=False),
+                nn.BatchNorm3d(hidden_dim), nn.ReLU6(inplace=True),
+                nn.Conv3d(hidden_dim, oup, 1, 1, 0, bias=False), nn.BatchNorm3d(oup))
+
+
+class MobileV2_Inverted_Residual_Block(_Holder):
+    """mobilenetv2_helper.py:71-105."""
+
+    def __init__(self, input_channel, setting, width_mult, beta_inv=None):
+        super().__init__()
+        feats = []
+        rows = setting if isinstance(setting[0], list) else [setting]
+        for t, c, n, s in rows:
+            output_channel = int(c * width_mult) if beta_inv is None else int(c * width_mult // beta_inv)
+            for i in range(n):
+                feats.append(MBInvertedResidual(input_channel, output_channel, s if i == 0 else (1, 1, 1), t))
+                input_channel = output_channel
+        self.features = nn.Sequential(*feats)
+
+
+class MobileNetV2_Stage(_Holder):
+    """mobilenetv2_helper.py:258-343."""
+
+    def __init__(self, input_channel, slow_residual_setting, fast_residual_setting, width_mult=1.0, beta_inv=4):
+        super().__init__()
+        self.names = []
+        for p, (setting, binv) in enumerate(((slow_residual_setting, None), (fast_residual_setting, beta_inv))):
+            blk = MobileV2_Inverted_Residual_Block(input_channel[p], setting, width_mult, beta_inv=binv)
+            name = "pathway{}_channel_{}".format(p, setting[0][1])
+            self.add_module(name, blk)
+            self.names.append(name)
+            _stage_init(self)
+
+    def pathway(self, p):
+        return getattr(self, self.names[p])
+
+
+class MobilenetV2_Basic_Stem(_Holder):
+    """stem_helper.py:191-201."""
+
+    def __init__(self, input_channel, width_mult, img_dim):
+        super().__init__()
+        c = int(input_channel * width_mult)
+        self.features = nn.Sequential(
+            nn.Conv3d(img_dim, c, kernel_size=3, stride=(1, 2, 2), padding=(1, 1, 1), bias=False), nn.BatchNorm3d(c),
+            nn.ReLU6(inplace=True))
+
+
+class MobilenetV2_Model_Stem(_Holder):
+    """stem_helper.py:204-232."""
+
+    def __init__(self, input_channels, width_mult, img_dim=3):
+        super().__init__()
+        self.num_pathways = len(input_channels)
+        for p in range(self.num_pathways):
+            self.add_module("pathway{}_stem".format(p), MobilenetV2_Basic_Stem(input_channels[p], width_mult[p], img_dim))
+
+
+class MobileNetV2BasicHead(_Holder):
+    """head_helper.py:436-486: per pathway 1x1x1 conv + BN + ReLU6 -> global avg -> cat -> Dropout -> Linear -> softmax."""
+
+    def __init__(self, input_channel, last_channel, num_classes, dropout_rate, act_func="softmax"):
+        super().__init__()
+        self.num_pathways = len(input_channel)
+        for p in range(self.num_pathways):
+            feats = nn.Sequential(nn.Conv3d(input_channel[p], last_channel[p], kernel_size=1, stride=1, padding=0,
+                                            bias=False), nn.BatchNorm3d(last_channel[p]), nn.ReLU6(inplace=True))
+            self.add_module("pathway{}_conv1x1x1".format(p), feats)
+        if act_func == "softmax":
+            self.act = nn.Softmax(dim=4)
+        elif act_func == "sigmoid":
+            self.act = nn.Sigmoid()
+        self.act_func = act_func
+        self.classifier = nn.Sequential(nn.Dropout(dropout_rate), nn.Linear(sum(last_channel), num_classes, bias=True))
+
+
+_MBV2_SETTING = [  # custom_video_model_builder.py:1029-1047 (t, c, n, s), identical for both pathways
+    [1, 16, 1, (1, 1, 1)], [6, 24, 2, (1, 2, 2)], [6, 32, 3, (1, 2, 2)], [6, 64, 4, (1, 2, 2)],
+    [6, 96, 3, (1, 1, 1)], [6, 160, 3, (1, 2, 2)], [6, 320, 1, (1, 1, 1)]]
+
+
+@MODEL_REGISTRY.register()
+class SlowFastMoibleNetV2(_EfficientBase):
+    """custom_video_model_builder.py:1057-1285 (the class name is spelled this way in the reference)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.norm_module = get_norm(cfg)
+        if cfg.DETECTION.ENABLE:
+            raise NotImplementedError("DETECTION.ENABLE is out of scope")
+        self.enable_detection = False
+        wm, beta, alpha = cfg.SLOWFAST.WIDTH_MULTI, cfg.SLOWFAST.BETA_INV, cfg.SLOWFAST.ALPHA
+        L = _MBV2_SETTING
+        wpg = 32
+        self.last_channel = int(1280 * wm) if wm > 1.0 else 1280
+        self.s1 = MobilenetV2_Model_Stem(input_channels=[wpg, wpg], width_mult=[wm, wm / beta],
+                                         img_dim=len(cfg.DATA.MEAN))
+
+        def stage(cin, rows):
+            return MobileNetV2_Stage(input_channel=cin, slow_residual_setting=rows, fast_residual_setting=rows,
+                                     width_mult=wm, beta_inv=beta)
+
+        def fuse(c):
+            return FuseFastAndSlow(dim_in=[int(c * wm), int(c * wm) // beta], alpha=alpha, beta_inv=beta,
+                                   norm_module=self.norm_module)
+
+        def fused_in(c):   # input channels of the stage that follows a fusion of width c (reference arithmetic kept)
+            return [int(c * wm + c * wm // beta), int(c * wm // beta + c * wm // beta)]
+
+        self.s2 = stage([int(wpg * wm), int(wpg * wm // beta)], L[0:2])
+        self.s3_fuse = fuse(L[1][1])
+        self.s4 = stage(fused_in(L[1][1]), L[2:3])
+        self.s4_fuse = fuse(L[2][1])
+        self.s5 = stage(fused_in(L[2][1]), L[3:4])
+        self.s5_fuse = fuse(L[3][1])
+        self.s6 = stage(fused_in(L[3][1]), L[4:5])
+        self.s7 = stage([int(L[4][1] * wm), int(L[4][1] * wm // beta)], L[5:6])
+        self.s7_fuse = fuse(L[5][1])
+        self.s8 = stage(fused_in(L[5][1]), L[6:])
+        self.head = MobileNetV2BasicHead(
+            input_channel=[int(L[6][1] * wm), int(L[6][1] * wm // beta)],
+            last_channel=[self.last_channel, self.last_channel // beta], num_classes=cfg.MODEL.NUM_CLASSES,
+            dropout_rate=cfg.MODEL.DROPOUT_RATE, act_func=cfg.MODEL.HEAD_ACT)
+        init_weights(self, cfg.MODEL.FC_INIT_STD, cfg.RESNET.ZERO_INIT_FINAL_BN)
+        self._init_runtime(cfg)
+
+    def _emit_unit(self, plan, unit, x, y):
+        """InvertedResidual.forward (mobilenetv2_helper.py:64-68)."""
+        seq = unit.conv
+        res = x if unit.use_res_connect else None
+        if len(seq) == 5:    # expand_ratio == 1: dw + BN + ReLU6 -> pw-linear + BN
+            t = self._emit_conv(plan, x, seq[0], seq[1], rt.ACT_RELU6)
+            self._emit_conv(plan, t, seq[3], seq[4], rt.ACT_NONE, y=y, res=res)
+        else:
+            t = self._emit_conv(plan, x, seq[0], seq[1], rt.ACT_RELU6)
+            t = self._emit_conv(plan, t, seq[3], seq[4], rt.ACT_RELU6)
+            self._emit_conv(plan, t, seq[6], seq[7], rt.ACT_NONE, y=y, res=res)
+
+    def _emit_stage(self, plan, stage, cur, fuse_after, name):
+        """Runs both pathways of a stage.  `cur` entries are plain tensors (whole buffers).  When a fusion follows,
+        the last unit writes into its slice of the fusion's concat buffer."""
+        beta = self._cfg.SLOWFAST.BETA_INV
+        B = cur[0].shape[0]
+        outs = []
+        for p in range(2):
+            x = cur[p]
+            units = stage.pathway(p).features
+            c_own = units[-1].conv[-2].out_channels
+            _, T, H, W, _ = x.shape
+            for u in units:
+                s = u.stride
+                H, W = _conv_out(H, 3, s[1], 1), _conv_out(W, 3, s[2], 1)
+            outs.append((c_own, T, H, W))
+        bufs = []
+        for p in range(2):
+            c_own, T, H, W = outs[p]
+            if fuse_after:
+                cs, cf = outs[0][0], outs[1][0]
+                tot = cs + cf if p == 0 else cs // beta + cf
+                off = 0 if p == 0 else cs // beta
+            else:
+                tot, off = c_own, 0
+            bufs.append((plan.act(B, T, H, W, tot, name="%s_cat%d" % (name, p)), off, c_own))
+        for p in range(2):
+            x = cur[p]
+            units = stage.pathway(p).features
+            dst, off, c_own = bufs[p]
+            _, T, H, W, _ = x.shape
+            for ui, u in enumerate(units):
+                s = u.stride
+                H, W = _conv_out(H, 3, s[1], 1), _conv_out(W, 3, s[2], 1)
+                last = ui == len(units) - 1
+                y = dst[..., off:off + c_own] if last else plan.act(B, T, H, W, u.conv[-2].out_channels)
+                self._emit_unit(plan, u, x, y)
+                x = y
+        return bufs
+
+    def _compile(self, plan):
+        cfg = self._cfg
+        alpha = cfg.SLOWFAST.ALPHA
+        xs_in = plan.inputs
+        B = xs_in[0].shape[0]
+        assert xs_in[1].shape[2] == xs_in[0].shape[2] * alpha, "fast pathway must have ALPHA x the frames of the slow one"
+        cur = []
+        for p in range(2):
+            seq = getattr(self.s1, "pathway{}_stem".format(p)).features
+            _, _, T, H, W = xs_in[p].shape
+            T, H, W = self._pooled_shape(T, H, W, seq)
+            buf = plan.act(B, T, H, W, seq[0].out_channels, name="s1_cat%d" % p)
+            w, b = fold_conv_bn(seq[0].weight, None, seq[1])
+            plan.stem(xs_in[p], buf, w, b, tuple(seq[0].stride), tuple(seq[0].padding), act=rt.ACT_RELU6)
+            cur.append(buf)
+        order = [("s2", True, "s3_fuse"), ("s4", True, "s4_fuse"), ("s5", True, "s5_fuse"), ("s6", False, None),
+                 ("s7", True, "s7_fuse"), ("s8", False, None)]
+        for sname, fuse_after, fname in order:
+            bufs = self._emit_stage(plan, getattr(self, sname), cur, fuse_after, sname)
+            if fuse_after:
+                self._emit_fuse(plan, getattr(self, fname), bufs)
+            cur = [b[0] for b in bufs]
+        feats = []
+        for p in range(2):
+            seq = getattr(self.head, "pathway{}_conv1x1x1".format(p))
+            feats.append(self._emit_conv(plan, cur[p], seq[0], seq[1], rt.ACT_RELU6))
+        act = {"softmax": rt.HEAD_SOFTMAX, "sigmoid": rt.HEAD_SIGMOID}[self.head.act_func]
+        lin = self.head.classifier[1]
+        plan.head(feats, lin.weight, lin.bias, act)
+
+
+MODEL_REGISTRY.register(SlowFastMoibleNetV2, name="SlowFastMobileNetV2")   # BASELINE.json spelling
+
+
+# ================================================================================================ GhostNet
+def _make_divisible(v, divisor, min_value=None):
+    """ghostnet_helper.py:11-24."""
+    if min_value is None:
+        min_value = divisor
+    new_v = max(min_value, int(v + divisor / 2) // divisor * divisor)
+    if new_v < 0.9 * v:
+        new_v += divisor
+    return new_v
+
+
+class SqueezeExcite(_Holder):
+    """ghostnet_helper.py:34-52 (gate: hard sigmoid)."""
+
+    def __init__(self, in_chs, se_ratio=0.25, divisor=4):
+        super().__init__()
+        reduced_chs = _make_divisible(in_chs * se_ratio, divisor)
+        self.avg_pool = nn.AdaptiveAvgPool3d(1)
+        self.conv_reduce = nn.Conv3d(in_chs, reduced_chs, 1, bias=True)
+        self.act1 = nn.ReLU(inplace=True)
+        self.conv_expand = nn.Conv3d(reduced_chs, in_chs, 1, bias=True)
+
+
+class ConvBnAct(_Holder):
+    """ghostnet_helper.py:55-68 / head_helper.py:612-627."""
+
+    def __init__(self, in_chs, out_chs, kernel_size, stride=1):
+        super().__init__()
+        self.conv = nn.Conv3d(in_chs, out_chs, kernel_size, stride, kernel_size // 2, bias=False)
+        self.bn1 = nn.BatchNorm3d(out_chs)
+        self.act1 = nn.ReLU(inplace=True)
+
+
+class GhostModule(_Holder):
+    """ghostnet_helper.py:71-99: 1xkxk primary conv + depthwise 3x3x3 'cheap operation', concat, slice to `oup`."""
+
+    def __init__(self, inp, oup, kernel_size=1, ratio=2, dw_size=3, stride=1, relu=True):
+        super().__init__()
+        self.oup = oup
+        self.relu = relu
+        init_channels = math.ceil(oup / ratio)
+        new_channels = init_channels * (ratio - 1)
+        self.primary_conv = nn.Sequential(
+            nn.Conv3d(inp, init_channels, kernel_size=(1, kernel_size, kernel_size), stride=(1, stride, stride),
+                      padding=(0, kernel_size // 2, kernel_size // 2), bias=False),
+            nn.BatchNorm3d(init_channels), nn.ReLU(inplace=True) if relu else nn.Sequential())
+        self.cheap_operation = nn.Sequential(
+            nn.Conv3d(init_channels, new_channels, kernel_size=dw_size, stride=1, padding=dw_size // 2,
+                      groups=init_channels, bias=False),
+            nn.BatchNorm3d(new_channels), nn.ReLU(inplace=True) if relu else nn.Sequential())
+
+
+class GhostBottleneck(_Holder):
+    """ghostnet_helper.py:102-163."""
+
+    def __init__(self, in_chs, mid_chs, out_chs, dw_kernel_size=3, stride=1, se_ratio=0.0):
+        super().__init__()
+        has_se = se_ratio is not None and se_ratio > 0.0
+        self.stride = stride
+        self.ghost1 = GhostModule(in_chs, mid_chs, relu=True)
+        if self.stride > 1:
+            self.conv_dw = nn.Conv3d(mid_chs, mid_chs, kernel_size=(1, dw_kernel_size, dw_kernel_size),
+                                     stride=(1, stride, stride),
+                                     padding=(0, (dw_kernel_size - 1) // 2, (dw_kernel_size - 1) // 2), groups=mid_chs,
+                                     bias=False)
+            self.bn_dw = nn.BatchNorm3d(mid_chs)
+        self.se = SqueezeExcite(mid_chs, se_ratio=se_ratio) if has_se else None
+        self.ghost2 = GhostModule(mid_chs, out_chs, relu=False)
+        if in_chs == out_chs and self.stride == 1:
+            self.shortcut = nn.Sequential()
+        else:
+            self.shortcut = nn.Sequential(
+                nn.Conv3d(in_chs, in_chs, kernel_size=(1, dw_kernel_size, dw_kernel_size), stride=(1, stride, stride),
+                          padding=(0, (dw_kernel_size - 1) // 2, (dw_kernel_size - 1) // 2), groups=in_chs, bias=False),
+                nn.BatchNorm3d(in_chs), nn.Conv3d(in_chs, out_chs, 1, stride=1, padding=0, bias=False),
+                nn.BatchNorm3d(out_chs))
+
+
+class GhostNet_Inverted_Residual_Block(_Holder):
+    """ghostnet_helper.py:266-312."""
+
+    def __init__(self, input_channel, cfg):
+        super().__init__()
+        layers = []
+        for k, exp_size, c, se_ratio, s in cfg:
+            output_channel = _make_divisible(c, 2)
+            hidden_channel = _make_divisible(exp_size, 2)
+            layers.append(GhostBottleneck(input_channel, hidden_channel, output_channel, dw_kernel_size=k, stride=s,
+                                          se_ratio=se_ratio))
+            input_channel = output_channel
+        self.features = nn.Sequential(*layers)
+        _stage_init(self)
+
+
+class GhostNet_Stage(_Holder):
+    """ghostnet_helper.py:315-380."""
+
+    def __init__(self, input_channel, slow_cfg, fast_cfg):
+        super().__init__()
+        self.names = []
+        for p, cfg in enumerate((slow_cfg, fast_cfg)):
+            name = "pathway{}_channel_{}".format(p, cfg[-1][2])
+            self.add_module(name, GhostNet_Inverted_Residual_Block(input_channel[p], cfg))
+            self.names.append(name)
+            _stage_init(self)
+
+    def pathway(self, p):
+        return getattr(self, self.names[p])
+
+
+class GhostNet_Model_Stem(_Holder):
+    """stem_helper.py:310-336: Conv3d 3x3x3 s(1,2,2) p1 -> BN -> ReLU (no pool)."""
+
+    def __init__(self, input_channels, img_dim=3):
+        super().__init__()
+        for p in range(len(input_channels)):
+            self.add_module("pathway{}_stem".format(p), nn.Sequential(
+                nn.Conv3d(img_dim, input_channels[p], kernel_size=3, stride=(1, 2, 2), padding=1, bias=False),
+                nn.BatchNorm3d(input_channels[p]), nn.ReLU(inplace=True)))
+
+
+class GhostNetBasicHead(_Holder):
+    """head_helper.py:630-700.  `self.act` is overwritten with ReLU in the reference (:653), so the eval output is
+    ReLU(logits), not a softmax -- reproduced."""
+
+    def __init__(self, input_channel, mid_channel, output_channel, num_classes, dropout_rate, act_func="softmax"):
+        super().__init__()
+        self.num_pathways = len(input_channel)
+        self.stage5_conv_slow = ConvBnAct(input_channel[0], mid_channel[0], 1)
+        self.stage5_conv_fast = ConvBnAct(input_channel[1], mid_channel[1], 1)
+        self.conv_head_slow = nn.Conv3d(mid_channel[0], output_channel[0], 1, 1, 0, bias=True)
+        self.conv_head_fast = nn.Conv3d(mid_channel[1], output_channel[1], 1, 1, 0, bias=True)
+        self.act = nn.ReLU(inplace=True)
+        self.classifier = nn.Sequential(nn.Dropout(dropout_rate), nn.Linear(sum(output_channel), num_classes, bias=True))
+
+
+_GHOST_STAGES = [   # k, t, c, SE, s   (custom_video_model_builder.py:813-845)
+    [[3, 16, 16, 0, 1]],
+    [[3, 48, 24, 0, 2], [3, 72, 24, 0, 1]],
+    [[5, 72, 40, 0.25, 2], [5, 120, 40, 0.25, 1]],
+    [[3, 240, 80, 0, 2], [3, 200, 80, 0, 1], [3, 184, 80, 0, 1], [3, 184, 80, 0, 1], [3, 480, 112, 0.25, 1],
+     [3, 672, 112, 0.25, 1]],
+    [[5, 672, 160, 0.25, 2], [5, 960, 160, 0, 1], [5, 960, 160, 0.25, 1], [5, 960, 160, 0, 1], [5, 960, 160, 0.25, 1]],
+]
+
+
+def ghost_cfgs(wm, beta):
+    slow, fast = [], []
+    for stage in _GHOST_STAGES:
+        fast.append([[c[0], _make_divisible(c[1] * wm // beta, 4), _make_divisible(c[2] * wm // beta, 4), c[3], c[4]]
+                     for c in stage])
+        slow.append([[c[0], _make_divisible(c[1] * wm, 4), _make_divisible(c[2] * wm, 4), c[3], c[4]] for c in stage])
+    return slow, fast
+
+
+@MODEL_REGISTRY.register()
+class SlowFastGhostNet(_EfficientBase):
+    """custom_video_model_builder.py:792-1026."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.norm_module = get_norm(cfg)
+        if cfg.DETECTION.ENABLE:
+            raise NotImplementedError("DETECTION.ENABLE is out of scope")
+        self.enable_detection = False
+        wm, beta, alpha = cfg.SLOWFAST.WIDTH_MULTI, cfg.SLOWFAST.BETA_INV, cfg.SLOWFAST.ALPHA
+        self.slow_cfgs, self.fast_cfgs = ghost_cfgs(wm, beta)
+        sc, fc = self.slow_cfgs, self.fast_cfgs
+        widths = [_make_divisible(16 * wm, 4), _make_divisible(16 * wm // beta, 4)]
+        outs = [int(1280 * wm), int(1280 * wm // beta)]
+        self.s0 = GhostNet_Model_Stem(input_channels=widths, img_dim=len(cfg.DATA.MEAN))
+        self.s1 = GhostNet_Stage(input_channel=widths, slow_cfg=sc[0], fast_cfg=fc[0])
+        for i in range(4):
+            fuse = FuseFastAndSlow(dim_in=[sc[i][-1][2], fc[i][-1][2]], alpha=alpha, beta_inv=beta,
+                                   norm_module=self.norm_module)
+            setattr(self, "s%d_fuse" % (i + 1), fuse)
+            own_s = sc[i][0][2] if i < 3 else sc[i][-1][2]      # the reference indexes [0][2] for s2..s4, [-1][2] for s5
+            own_f = fc[i][0][2] if i < 3 else fc[i][-1][2]
+            stage = GhostNet_Stage(input_channel=[own_s + fc[i][-1][2], own_f + sc[i][-1][2] // beta],
+                                   slow_cfg=sc[i + 1], fast_cfg=fc[i + 1])
+            setattr(self, "s%d" % (i + 2), stage)
+        self.head = GhostNetBasicHead(input_channel=[sc[4][-1][2], fc[4][-1][2]], mid_channel=[sc[4][-1][1], fc[4][-1][1]],
+                                      output_channel=outs, num_classes=cfg.MODEL.NUM_CLASSES,
+                                      dropout_rate=cfg.MODEL.DROPOUT_RATE, act_func=cfg.MODEL.HEAD_ACT)
+        init_weights(self, cfg.MODEL.FC_INIT_STD, cfg.RESNET.ZERO_INIT_FINAL_BN)
+        self._init_runtime(cfg)
+
+    def _emit_ghost(self, plan, gm, x, out, res=None):
+        """GhostModule.forward (ghostnet_helper.py:95-99) into `out` (oup channels).  With `res` (ghost2 of a
+        bottleneck) the residual is added after the concat; the cheap operation must read the un-added primary
+        output, so that goes through a temporary."""
+        act = rt.ACT_RELU if gm.relu else rt.ACT_NONE
+        pc, pbn = gm.primary_conv[0], gm.primary_conv[1]
+        cc, cbn = gm.cheap_operation[0], gm.cheap_operation[1]
+        init = pc.out_channels
+        keep = gm.oup - init                                  # channels of the cheap branch that survive the slice
+        B, T, H, W, _ = out.shape
+        x1 = out[..., :init] if res is None else plan.act(B, T, H, W, init)
+        self._emit_conv(plan, x, pc, pbn, act, y=x1)
+        if keep > 0:
+            w, b = fold_conv_bn(cc.weight, cc.bias, cbn)
+            # depthwise with channel multiplier 1: output channel j reads input channel j -> truncating is exact
+            plan.conv(x1[..., :keep], out[..., init:init + keep], w[:keep], b[:keep], stride=tuple(cc.stride),
+                      padding=tuple(cc.padding), groups=keep, act=act, res=None if res is None else res[..., init:init + keep])
+        if res is not None:
+            plan.eltwise_add(x1, res[..., :init], out[..., :init])
+
+    def _emit_unit(self, plan, blk, x, y):
+        """GhostBottleneck.forward (ghostnet_helper.py:149-163)."""
+        B, T, H, W, _ = x.shape
+        mid = blk.ghost1.oup
+        g1 = plan.act(B, T, H, W, mid)
+        self._emit_ghost(plan, blk.ghost1, x, g1)
+        t = g1
+        if blk.stride > 1:
+            t = self._emit_conv(plan, t, blk.conv_dw, blk.bn_dw, rt.ACT_NONE)
+        if blk.se is not None:
+            t2 = plan.act(*t.shape)
+            plan.squeeze_excite(t, t2, blk.se)
+            t = t2
+        if len(blk.shortcut) == 0:
+            sc = x
+        else:
+            sc = self._emit_conv(plan, x, blk.shortcut[0], blk.shortcut[1], rt.ACT_NONE)
+            sc = self._emit_conv(plan, sc, blk.shortcut[2], blk.shortcut[3], rt.ACT_NONE)
+        self._emit_ghost(plan, blk.ghost2, t, y, res=sc)
+
+    def _emit_stage(self, plan, stage, cur, fuse_after, name):
+        beta = self._cfg.SLOWFAST.BETA_INV
+        B = cur[0].shape[0]
+        outs = []
+        for p in range(2):
+            units = stage.pathway(p).features
+            _, T, H, W, _ = cur[p].shape
+            for u in units:
+                if u.stride > 1:
+                    k = u.conv_dw.kernel_size[1]
+                    H, W = _conv_out(H, k, u.stride, (k - 1) // 2), _conv_out(W, k, u.stride, (k - 1) // 2)
+            outs.append((units[-1].ghost2.oup, T, H, W))
+        bufs = []
+        for p in range(2):
+            c_own, T, H, W = outs[p]
+            if fuse_after:
+                cs, cf = outs[0][0], outs[1][0]
+                tot = cs + cf if p == 0 else cs // beta + cf
+                off = 0 if p == 0 else cs // beta
+            else:
+                tot, off = c_own, 0
+            bufs.append((plan.act(B, T, H, W, tot, name="%s_cat%d" % (name, p)), off, c_own))
+        for p in range(2):
+            x = cur[p]
+            units = stage.pathway(p).features
+            dst, off, c_own = bufs[p]
+            _, T, H, W, _ = x.shape
+            for ui, u in enumerate(units):
+                if u.stride > 1:
+                    k = u.conv_dw.kernel_size[1]
+                    H, W = _conv_out(H, k, u.stride, (k - 1) // 2), _conv_out(W, k, u.stride, (k - 1) // 2)
+                last = ui == len(units) - 1
+                y = dst[..., off:off + c_own] if last else plan.act(B, T, H, W, u.ghost2.oup)
+                self._emit_unit(plan, u, x, y)
+                x = y
+        return bufs
+
+    def _compile(self, plan):
+        cfg = self._cfg
+        alpha = cfg.SLOWFAST.ALPHA
+        xs_in = plan.inputs
+        B = xs_in[0].shape[0]
+        assert xs_in[1].shape[2] == xs_in[0].shape[2] * alpha, "fast pathway must have ALPHA x the frames of the slow one"
+        cur = []
+        for p in range(2):
+            seq = getattr(self.s0, "pathway{}_stem".format(p))
+            _, _, T, H, W = xs_in[p].shape
+            T, H, W = self._pooled_shape(T, H, W, seq)
+            buf = plan.act(B, T, H, W, seq[0].out_channels, name="s0_cat%d" % p)
+            w, b = fold_conv_bn(seq[0].weight, None, seq[1])
+            plan.stem(xs_in[p], buf, w, b, tuple(seq[0].stride), tuple(seq[0].padding), act=rt.ACT_RELU)
+            cur.append(buf)
+        for i in range(1, 6):
+            fuse_after = i < 5
+            bufs = self._emit_stage(plan, getattr(self, "s%d" % i), cur, fuse_after, "s%d" % i)
+            if fuse_after:
+                self._emit_fuse(plan, getattr(self, "s%d_fuse" % i), bufs)
+            cur = [b[0] for b in bufs]
+        h = self.head
+        outs = [h.conv_head_slow.out_channels, h.conv_head_fast.out_channels]
+        feat = torch.empty((B, sum(outs)), dtype=torch.float32, device=plan.device)
+        col = 0
+        for p, (cba, ch) in enumerate(((h.stage5_conv_slow, h.conv_head_slow), (h.stage5_conv_fast, h.conv_head_fast))):
+            t = self._emit_conv(plan, cur[p], cba.conv, cba.bn1, rt.ACT_RELU)
+            plan.pooled_fc(t, ch.weight, ch.bias, rt.HEAD_RELU, feat[:, col:], sum(outs))
+            col += outs[p]
+        lin = h.classifier[1]
+        plan.fc(feat, lin.weight, lin.bias, rt.HEAD_RELU)   # eval "act" of this head is ReLU (head_helper.py:653)

@@ -152,13 +152,19 @@ int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int32_t H, int3
                        const float* bn_scale, const float* bn_shift, int32_t alpha, const esf_view* y_fast_slice,
                        esf_op** out);
 
+/* ---- generic CUDA-core fallback of the same attention for head dims the tensor-core kernels do not cover (d > 128;
+ * in the reference's models that only happens with N <= 392 keys).  Reads the FP32 projection rows directly. */
+int esf_attn_generic(const float* proj, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d, float gamma,
+                     const float* bn_scale, const float* bn_shift, int32_t alpha, const esf_view* y_fast_slice,
+                     void* stream);
+
 /* ---- head: global average pool of each pathway -> concat -> Linear -> softmax/ReLU/none -----------------
  * replaces ResNetBasicHead.forward eval branch (head_helper.py:198-223) and the efficient heads'
  * pool+classifier tails.  feat: FP32 scratch (B, C0 + C1).  act: 0 none (logits), 1 softmax, 2 relu, 3 sigmoid,
  * 4 hard-sigmoid (the same kernel serves the squeeze-excite MLP of ghostnet_helper.py:46-52). */
 int esf_head_pool(const esf_view* x0, const esf_view* x1, float* feat, void* stream);
-int esf_head_fc(const float* feat, int32_t B, int32_t Cin, const float* w, const float* bias, int32_t num_classes,
-                int32_t act, float* out, void* stream);
+int esf_head_fc(const float* feat, int32_t B, int32_t Cin, int32_t feat_stride, const float* w, const float* bias,
+                int32_t num_classes, int32_t act, float* out, int32_t out_stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -153,7 +153,176 @@ def slowfast_shufflenet_forward(cfg, sd, inputs, dtype=torch.float32, taps=None)
     return y
 
 
+# ------------------------------------------------------------------------------------------------ MobileNetV2
+MBV2_SETTING = [[1, 16, 1, (1, 1, 1)], [6, 24, 2, (1, 2, 2)], [6, 32, 3, (1, 2, 2)], [6, 64, 4, (1, 2, 2)],
+                [6, 96, 3, (1, 1, 1)], [6, 160, 3, (1, 2, 2)], [6, 320, 1, (1, 1, 1)]]   # custom_video_model_builder.py:1029-1047
+
+
+def mbv2_unit(x, sd, p, stride, expand_ratio, oup):
+    """InvertedResidual.forward (mobilenetv2_helper.py:64-68)."""
+    inp = x.shape[1]
+    if expand_ratio == 1:
+        y = F.relu6(_bn(_conv(x, sd, p + ".conv.0", stride=stride, padding=1, groups=inp), sd, p + ".conv.1"))
+        y = _bn(_conv(y, sd, p + ".conv.3"), sd, p + ".conv.4")
+    else:
+        y = F.relu6(_bn(_conv(x, sd, p + ".conv.0"), sd, p + ".conv.1"))
+        y = F.relu6(_bn(_conv(y, sd, p + ".conv.3", stride=stride, padding=1, groups=y.shape[1]), sd, p + ".conv.4"))
+        y = _bn(_conv(y, sd, p + ".conv.6"), sd, p + ".conv.7")
+    return x + y if (tuple(stride) == (1, 1, 1) and inp == oup) else y
+
+
+def slowfast_mobilenetv2_forward(cfg, sd, inputs, dtype=torch.float32, taps=None):
+    """SlowFastMoibleNetV2.forward (custom_video_model_builder.py:1264-1285), eval mode."""
+    alpha, beta, wm = cfg.SLOWFAST.ALPHA, cfg.SLOWFAST.BETA_INV, cfg.SLOWFAST.WIDTH_MULTI
+    sd = {k: v.detach().to("cpu") for k, v in sd.items()}
+    xs = [t.detach().to("cpu", dtype) for t in inputs]
+
+    def tap(name, val):
+        if taps is not None:
+            taps[name] = [t.clone() for t in val] if isinstance(val, list) else val.clone()
+
+    def stage(xs, name, rows):
+        out = []
+        for p in range(2):
+            x = xs[p]
+            pre = "%s.pathway%d_channel_%d.features" % (name, p, rows[0][1])
+            u = 0
+            for t, c, n, s in rows:
+                oup = int(c * wm) if p == 0 else int(c * wm // beta)
+                for i in range(n):
+                    x = mbv2_unit(x, sd, "%s.%d" % (pre, u), s if i == 0 else (1, 1, 1), t, oup)
+                    u += 1
+            out.append(x)
+        tap(name, out)
+        return out
+
+    def fuse(xs, name):
+        xs = fuse_fast_and_slow(xs, sd, name, alpha)
+        tap(name, xs)
+        return xs
+
+    L = MBV2_SETTING
+    xs = [F.relu6(_bn(_conv(xs[p], sd, "s1.pathway%d_stem.features.0" % p, stride=(1, 2, 2), padding=(1, 1, 1)), sd,
+                      "s1.pathway%d_stem.features.1" % p)) for p in range(2)]
+    tap("s1", xs)
+    xs = fuse(stage(xs, "s2", L[0:2]), "s3_fuse")
+    xs = fuse(stage(xs, "s4", L[2:3]), "s4_fuse")
+    xs = fuse(stage(xs, "s5", L[3:4]), "s5_fuse")
+    xs = stage(xs, "s6", L[4:5])
+    xs = fuse(stage(xs, "s7", L[5:6]), "s7_fuse")
+    xs = stage(xs, "s8", L[6:])
+    feats = []
+    for p in range(2):
+        q = "head.pathway%d_conv1x1x1" % p
+        feats.append(F.relu6(_bn(_conv(xs[p], sd, q + ".0"), sd, q + ".1")))
+    y, logits = basic_head(feats, sd, "head", cfg.MODEL.HEAD_ACT, return_logits=True)
+    tap("logits", logits)
+    tap("head", y)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ GhostNet
+GHOST_STAGES = [   # k, t, c, SE, s   (custom_video_model_builder.py:813-845)
+    [[3, 16, 16, 0, 1]],
+    [[3, 48, 24, 0, 2], [3, 72, 24, 0, 1]],
+    [[5, 72, 40, 0.25, 2], [5, 120, 40, 0.25, 1]],
+    [[3, 240, 80, 0, 2], [3, 200, 80, 0, 1], [3, 184, 80, 0, 1], [3, 184, 80, 0, 1], [3, 480, 112, 0.25, 1],
+     [3, 672, 112, 0.25, 1]],
+    [[5, 672, 160, 0.25, 2], [5, 960, 160, 0, 1], [5, 960, 160, 0.25, 1], [5, 960, 160, 0, 1], [5, 960, 160, 0.25, 1]],
+]
+
+
+def make_divisible(v, divisor, min_value=None):
+    """ghostnet_helper.py:11-24."""
+    if min_value is None:
+        min_value = divisor
+    new_v = max(min_value, int(v + divisor / 2) // divisor * divisor)
+    if new_v < 0.9 * v:
+        new_v += divisor
+    return new_v
+
+
+def ghost_module(x, sd, p, oup, relu):
+    """GhostModule.forward (ghostnet_helper.py:95-99): the primary conv is 1x1x1 in every use (kernel_size=1), the cheap
+    operation a depthwise 3x3x3; concat then slice to `oup` channels."""
+    x1 = _bn(_conv(x, sd, p + ".primary_conv.0"), sd, p + ".primary_conv.1")
+    if relu:
+        x1 = F.relu(x1)
+    x2 = _bn(_conv(x1, sd, p + ".cheap_operation.0", padding=1, groups=x1.shape[1]), sd, p + ".cheap_operation.1")
+    if relu:
+        x2 = F.relu(x2)
+    return torch.cat([x1, x2], 1)[:, :oup]
+
+
+def ghost_bottleneck(x, sd, p, mid, out, k, stride, se_ratio):
+    """GhostBottleneck.forward (ghostnet_helper.py:149-163); SqueezeExcite :46-52 with the hard-sigmoid gate :27-31."""
+    residual = x
+    y = ghost_module(x, sd, p + ".ghost1", mid, True)
+    if stride > 1:
+        y = _bn(_conv(y, sd, p + ".conv_dw", stride=(1, stride, stride), padding=(0, (k - 1) // 2, (k - 1) // 2),
+                      groups=y.shape[1]), sd, p + ".bn_dw")
+    if se_ratio:
+        g = y.mean(dim=(2, 3, 4), keepdim=True)
+        g = F.relu(_conv(g, sd, p + ".se.conv_reduce"))
+        g = _conv(g, sd, p + ".se.conv_expand")
+        y = y * (F.relu6(g + 3.0) / 6.0)
+    y = ghost_module(y, sd, p + ".ghost2", out, False)
+    if (p + ".shortcut.0.weight") in sd:
+        r = _bn(_conv(residual, sd, p + ".shortcut.0", stride=(1, stride, stride),
+                      padding=(0, (k - 1) // 2, (k - 1) // 2), groups=residual.shape[1]), sd, p + ".shortcut.1")
+        residual = _bn(_conv(r, sd, p + ".shortcut.2"), sd, p + ".shortcut.3")
+    return y + residual
+
+
+def slowfast_ghostnet_forward(cfg, sd, inputs, dtype=torch.float32, taps=None):
+    """SlowFastGhostNet.forward (custom_video_model_builder.py:1009-1026), eval mode.  The head's `act` is ReLU
+    (head_helper.py:653), so the output is ReLU(logits)."""
+    alpha, beta, wm = cfg.SLOWFAST.ALPHA, cfg.SLOWFAST.BETA_INV, cfg.SLOWFAST.WIDTH_MULTI
+    sd = {k: v.detach().to("cpu") for k, v in sd.items()}
+    xs = [t.detach().to("cpu", dtype) for t in inputs]
+    slow = [[[c[0], make_divisible(c[1] * wm, 4), make_divisible(c[2] * wm, 4), c[3], c[4]] for c in st]
+            for st in GHOST_STAGES]
+    fast = [[[c[0], make_divisible(c[1] * wm // beta, 4), make_divisible(c[2] * wm // beta, 4), c[3], c[4]] for c in st]
+            for st in GHOST_STAGES]
+
+    def tap(name, val):
+        if taps is not None:
+            taps[name] = [t.clone() for t in val] if isinstance(val, list) else val.clone()
+
+    xs = [F.relu(_bn(_conv(xs[p], sd, "s0.pathway%d_stem.0" % p, stride=(1, 2, 2), padding=1), sd,
+                     "s0.pathway%d_stem.1" % p)) for p in range(2)]
+    tap("s0", xs)
+    for i in range(5):
+        name = "s%d" % (i + 1)
+        out = []
+        for p, rows in enumerate((slow[i], fast[i])):
+            x = xs[p]
+            pre = "%s.pathway%d_channel_%d.features" % (name, p, rows[-1][2])
+            for u, (k, t, c, se, s) in enumerate(rows):
+                x = ghost_bottleneck(x, sd, "%s.%d" % (pre, u), make_divisible(t, 2), make_divisible(c, 2), k, s, se)
+            out.append(x)
+        xs = out
+        tap(name, xs)
+        if i < 4:
+            xs = fuse_fast_and_slow(xs, sd, name + "_fuse", alpha)
+            tap(name + "_fuse", xs)
+    pooled = []
+    for p, tag in enumerate(("slow", "fast")):
+        x = F.relu(_bn(_conv(xs[p], sd, "head.stage5_conv_%s.conv" % tag), sd, "head.stage5_conv_%s.bn1" % tag))
+        x = F.avg_pool3d(x, x.shape[-3:])
+        pooled.append(F.relu(_conv(x, sd, "head.conv_head_%s" % tag)))
+    x = torch.cat(pooled, 1).permute(0, 2, 3, 4, 1)
+    logits = F.linear(x, sd["head.classifier.1.weight"].to(x.dtype), sd["head.classifier.1.bias"].to(x.dtype))
+    y = F.relu(logits).mean([1, 2, 3]).reshape(x.shape[0], -1)
+    tap("logits", logits)
+    tap("head", y)
+    return y
+
+
 FORWARDS = {
+    "SlowFastGhostNet": slowfast_ghostnet_forward,
     "SlowFastShuffleNetV2": slowfast_shufflenetv2_forward,
     "SlowFastShuffleNet": slowfast_shufflenet_forward,
+    "SlowFastMoibleNetV2": slowfast_mobilenetv2_forward,
+    "SlowFastMobileNetV2": slowfast_mobilenetv2_forward,
 }

@@ -103,6 +103,12 @@ CASES = {
     "shufflenet_w2g3": dict(    # BASELINE configs[4]: SlowFastShuffleNet width 2.0 groups 3, Jester shape
         model="SlowFastShuffleNet", yaml="configs/Jester/SLOWFAST_SHUFFLENET_8x8_R50_stepwise_multigrid.yaml",
         opts=[], calib=(2, 16, 112), inputs=[("s112", 2, 16, 112), ("s64", 2, 16, 64)]),
+    "mobilenetv2_w1": dict(     # BASELINE configs[3]: SlowFastMoibleNetV2 width 1.0
+        model="SlowFastMoibleNetV2", yaml="configs/Kinetics/SLOWFAST_MOBILENETV2_8x8_R50_stepwise_multigrid.yaml",
+        opts=["SLOWFAST.WIDTH_MULTI", 1.0], calib=(2, 16, 112), inputs=[("s112", 2, 16, 112), ("s224", 1, 32, 224)]),
+    "ghostnet_w1": dict(        # BASELINE configs[3]: SlowFastGhostNet width 1.0 (224^2 x 32 frames has N = 100 352)
+        model="SlowFastGhostNet", yaml="configs/Kinetics/SLOWFAST_GHOSTNET_8x8_R50_stepwise_multigrid.yaml",
+        opts=["SLOWFAST.WIDTH_MULTI", 1.0], calib=(2, 16, 112), inputs=[("s112", 2, 16, 112), ("s64", 2, 16, 64)]),
     "dual_r50_stress": dict(
         model="SlowFastDualAttention", yaml="configs/Kinetics/SLOWFAST_DUAL_8x8_R50_stepwise_multigrid.yaml",
         stress=True, opts=[], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),

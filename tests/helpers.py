@@ -25,6 +25,10 @@ def case_cfg(name):
         cfg.MULTIGRID.SHORT_CYCLE = True
     elif name == "shufflenetv2_w05":
         cfg = esf.slowfast_shufflenetv2_cfg(0.5)
+    elif name == "mobilenetv2_w1":
+        cfg = esf.slowfast_mobilenetv2_cfg(1.0)
+    elif name == "ghostnet_w1":
+        cfg = esf.slowfast_ghostnet_cfg(1.0)
     elif name == "shufflenet_w2g3":
         cfg = esf.slowfast_shufflenet_cfg(2.0, 3)
     else:

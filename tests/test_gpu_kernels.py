@@ -298,6 +298,26 @@ def test_attention_tcgen05(esf_lib, d, T, H, W, qk_scale):
     assert (ybuf[..., d:] == 0).all()
 
 
+def test_attention_generic_fallback(esf_lib):
+    d, T, H, W, B, alpha = 240, 2, 4, 5, 2, 4
+    g = torch.Generator().manual_seed(3)
+    N = T * H * W
+    proj = torch.randn(B * N, 4 * d, generator=g)
+    proj[:, d:3 * d] *= 1.0 / d ** 0.25
+    scale = torch.rand(d, generator=g) + 0.5
+    shift = torch.rand(d, generator=g) - 0.5
+    ref = _attention_reference(proj, B, T, H, W, d, 0.7, scale, shift, alpha)
+    ybuf = torch.zeros(B, T * alpha, H, W, 2 * d, dtype=torch.bfloat16, device=DEV)
+    yv = rt.view(ybuf[..., :d])
+    pj, sc, sh = proj.to(DEV), scale.to(DEV), shift.to(DEV)
+    rt.check(esf_lib.esf_attn_generic(pj.data_ptr(), B, T, H, W, d, 0.7, sc.data_ptr(), sh.data_ptr(), alpha,
+                                      ctypes.byref(yv), rt.current_stream_ptr()))
+    torch.cuda.synchronize()
+    got = ybuf[..., :d].cpu().double()
+    assert (got - ref).abs().max().item() <= 6e-3 * ref.abs().max().item()   # FP32 math, BF16 output rounding
+    assert (ybuf[..., d:] == 0).all()
+
+
 def test_channel_plumbing_kernels(esf_lib):
     """shuffle-concat, elementwise add, SE channel scale, avg-pool + ReLU: bit-level semantics vs torch on BF16 data."""
     g = torch.Generator().manual_seed(11)

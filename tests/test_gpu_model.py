@@ -29,7 +29,8 @@ def _run(name, tag):
 @pytest.mark.parametrize("name,tag", [("dual_r50", "s64"), ("slowfast_r50", "s64"), ("dual_r50", "s224"),
                                       ("slowfast_r50", "s224"), ("shufflenetv2_w05", "s112"),
                                       ("shufflenetv2_w05", "s224"), ("shufflenet_w2g3", "s112"),
-                                      ("shufflenet_w2g3", "s64")])
+                                      ("shufflenet_w2g3", "s64"), ("mobilenetv2_w1", "s112"),
+                                      ("mobilenetv2_w1", "s224"), ("ghostnet_w1", "s112"), ("ghostnet_w1", "s64")])
 def test_model_matches_reference_golden(esf_lib, name, tag):
     cfg, model, gold, y = _run(name, tag)
     ref = torch.as_tensor(gold[tag + "/probs"])
@@ -39,7 +40,8 @@ def test_model_matches_reference_golden(esf_lib, name, tag):
     top2 = torch.topk(ref, 2, dim=1).values
     decided = (top2[:, 0] - top2[:, 1]) / top2[:, 0] > 2 * BF16_TOL   # argmax where the reference itself is decided
     assert torch.equal(y.argmax(1)[decided], ref.argmax(1)[decided])
-    assert abs(y.sum(1) - 1).max() < 1e-4
+    if name != "ghostnet_w1":       # the GhostNet head returns ReLU(logits), not probabilities
+        assert abs(y.sum(1) - 1).max() < 1e-4
     # second call replays the captured CUDA graph and must give the same answer
     xs = [t.cuda() for t in helpers.case_inputs(name, tag)]
     with torch.no_grad():

@@ -10,7 +10,8 @@ from oracle import slowfast_oracle as O
 pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not mounted")
 
 
-@pytest.mark.parametrize("name", ["dual_r50", "slowfast_r50", "shufflenetv2_w05", "shufflenet_w2g3"])
+@pytest.mark.parametrize("name", ["dual_r50", "slowfast_r50", "shufflenetv2_w05", "shufflenet_w2g3", "mobilenetv2_w1",
+                                  "ghostnet_w1"])
 def test_every_stage_bit_exact(name):
     spec = recipe.CASES[name]
     cfg = ref_shim.get_cfg(spec["yaml"], spec["opts"])
@@ -24,7 +25,8 @@ def test_every_stage_bit_exact(name):
     xs = recipe.pack_pathway_output(recipe.seeded_clip(2, 32, 48, seed=5), cfg.SLOWFAST.ALPHA)
     got = {}
     hooks = [getattr(ref, n).register_forward_hook(lambda m, i, o, n=n: got.__setitem__(n, [t.clone() for t in o]))
-             for n in ("s1", "s1_fuse", "s2", "s2_fuse", "s3", "s3_fuse", "s4", "s4_fuse", "s5") if hasattr(ref, n)]
+             for n in ("s0", "s1", "s1_fuse", "s2", "s2_fuse", "s3", "s3_fuse", "s4", "s4_fuse", "s5", "s5_fuse", "s6",
+                       "s7", "s7_fuse", "s8") if hasattr(ref, n)]
     with torch.no_grad():
         y_ref = ref([t.clone() for t in xs])
     for h in hooks:
@@ -37,7 +39,8 @@ def test_every_stage_bit_exact(name):
     assert torch.equal(y, y_ref)
 
 
-@pytest.mark.parametrize("name", ["dual_r50", "slowfast_r50", "shufflenetv2_w05", "shufflenet_w2g3"])
+@pytest.mark.parametrize("name", ["dual_r50", "slowfast_r50", "shufflenetv2_w05", "shufflenet_w2g3", "mobilenetv2_w1",
+                                  "ghostnet_w1"])
 def test_state_dict_schema_and_seeded_init_match_reference(name):
     import efficient_slowfast_b200 as esf
 
