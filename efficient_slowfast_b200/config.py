@@ -75,7 +75,8 @@ def get_cfg():
     c.MULTIGRID = CfgNode(dict(SHORT_CYCLE=False, LONG_CYCLE=False))
     c.TEST = CfgNode(dict(BATCH_SIZE=8, NUM_ENSEMBLE_VIEWS=10, NUM_SPATIAL_CROPS=3))
     c.NUM_GPUS = 1
-    # extension (not in the reference): arithmetic of the CUDA path, "bf16" (tensor-core BF16, FP32 accumulate)
+    # extension (not in the reference): 16-bit storage / tensor-core operand format of the CUDA path, "bf16" or "fp16"
+    # (FP32 accumulation, softmax statistics and head in both; fp16 has 3 more mantissa bits and saturates at 65504)
     c.ESF = CfgNode(dict(PRECISION="bf16", CUDA_GRAPH=True))
     return c
 

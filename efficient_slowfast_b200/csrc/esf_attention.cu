@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnParams p) 
 // only occurs with N <= 392 keys: SlowFastShuffleNet s4_fuse, d = 240).
 __global__ void __launch_bounds__(128) attn_generic_kernel(const float* __restrict__ proj, int N, int T, int H, int W,
                                                            int d, float gamma, const float* __restrict__ bn_scale,
-                                                           const float* __restrict__ bn_shift, int alpha,
+                                                           const float* __restrict__ bn_shift, int alpha, int f16,
                                                            __nv_bfloat16* __restrict__ y, long long ysB, long long ysT,
                                                            long long ysH, long long ysW) {
   extern __shared__ float srow[];  // [4 warps][N]
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(128) attn_generic_kernel(const float* __restri
     float o = 0.f;
     for (int j = 0; j < N; ++j) o = fmaf(expf(s[j] - m), base[(long long)j * 4 * d + 3 * d + c], o);
     const float a = fmaf(gamma, o / l, base[(long long)i * 4 * d + c]);
-    const __nv_bfloat16 v = __float2bfloat16(fmaxf(fmaf(a, bn_scale[c], bn_shift[c]), 0.f));
+    const __nv_bfloat16 v = f2h16(fmaxf(fmaf(a, bn_scale[c], bn_shift[c]), 0.f), f16);
     for (int r = 0; r < alpha; ++r) y[b * ysB + (long long)(t * alpha + r) * ysT + hh * ysH + ww * ysW + c] = v;
   }
 }
@@ -430,6 +430,7 @@ extern "C" int esf_attn_fused(const void* packed, int32_t B, int32_t T, int32_t 
                               const float* bn_scale, const float* bn_shift, int32_t alpha,
                               const esf_view* y_fast_slice, void* stream) {
   ESF_CHECK_ARG(packed && bn_scale && bn_shift && view_ok(y_fast_slice), "esf_attn_fused: null/bad argument");
+  ESF_CHECK_ARG(y_fast_slice->dtype == ESF_BF16, "esf_attn_fused (mma.sync variant) is BF16-only; use esf_attn_tc_*");
   PackGeom g;
   if (!attn_geom(d, &g)) return set_error(ESF_ERR_UNSUPPORTED, "esf_attn_fused: unsupported head dim %d", d);
   const esf_view* y = y_fast_slice;
@@ -478,7 +479,7 @@ extern "C" int esf_attn_generic(const float* proj, int32_t B, int32_t T, int32_t
     attr_set = true;
   }
   attn_generic_kernel<<<dim3(cdiv(N, 4), B), 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      proj, N, T, H, W, d, gamma, bn_scale, bn_shift, alpha, static_cast<__nv_bfloat16*>(y->ptr), y->sB, y->sT, y->sH,
-      y->sW);
+      proj, N, T, H, W, d, gamma, bn_scale, bn_shift, alpha, y->dtype == ESF_F16, static_cast<__nv_bfloat16*>(y->ptr),
+      y->sB, y->sT, y->sH, y->sW);
   return check_launch("attn_generic_kernel");
 }

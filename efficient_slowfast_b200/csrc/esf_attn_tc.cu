@@ -51,6 +51,7 @@ struct __align__(64) AttnTcParams {
   uint32_t steps1[kTcMaxSteps], steps2[kTcMaxSteps];  // A offset | B offset << 16 (16-byte units, see host code)
   int stages;
   uint32_t q_tile_bytes, k_tile_bytes, v_tile_bytes;
+  int f16;  // 16-bit operands (Q~, K~, V^T, P) and the output are IEEE half instead of BF16
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -156,8 +157,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
     // One thread issues; the whole warp runs the (warp-uniform) control flow so that descriptors stay in uniform
     // registers.  Two issuing warps because at N = 64 an MMA retires in 32 clk -- faster than one thread can issue.
     const int q = warp - 9;
-    const uint32_t idesc_s = make_idesc_bf16(128, kTcBN);
-    const uint32_t idesc_o = make_idesc_bf16(128, p.DVp);
+    const uint32_t idesc_s = make_idesc_16(128, kTcBN, p.f16);
+    const uint32_t idesc_o = make_idesc_16(128, p.DVp, p.f16);
     const uint32_t qk_hi = kmajor_desc_hi(p.sbo, p.layout_type);
     const uint32_t pv_hi = kmajor_desc_hi(1024, 2);
     const uint32_t q_lo = kmajor_desc_lo(smem_u32(Qs) + q * p.q_tile_bytes);
@@ -279,10 +280,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
 #pragma unroll
       for (int ck = 0; ck < 8; ++ck) {
         uint4 o;
-        o.x = pack_bf16x2(v[8 * ck + 0], v[8 * ck + 1]);
-        o.y = pack_bf16x2(v[8 * ck + 2], v[8 * ck + 3]);
-        o.z = pack_bf16x2(v[8 * ck + 4], v[8 * ck + 5]);
-        o.w = pack_bf16x2(v[8 * ck + 6], v[8 * ck + 7]);
+        o.x = pack16x2(v[8 * ck + 0], v[8 * ck + 1], p.f16);
+        o.y = pack16x2(v[8 * ck + 2], v[8 * ck + 3], p.f16);
+        o.z = pack16x2(v[8 * ck + 4], v[8 * ck + 5], p.f16);
+        o.w = pack16x2(v[8 * ck + 6], v[8 * ck + 7], p.f16);
         *reinterpret_cast<uint4*>(prow + swz(r * 128 + ck * 16, 7)) = o;
       }
       fence_proxy_async_smem();
@@ -320,17 +321,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
           for (int h8 = 0; h8 < 2; ++h8) {
             if (c0 + h8 * 8 < p.d) {
               uint4 pk;
-              pk.x = pack_bf16x2(o[h8 * 8 + 0], o[h8 * 8 + 1]);
-              pk.y = pack_bf16x2(o[h8 * 8 + 2], o[h8 * 8 + 3]);
-              pk.z = pack_bf16x2(o[h8 * 8 + 4], o[h8 * 8 + 5]);
-              pk.w = pack_bf16x2(o[h8 * 8 + 6], o[h8 * 8 + 7]);
+              pk.x = pack16x2(o[h8 * 8 + 0], o[h8 * 8 + 1], p.f16);
+              pk.y = pack16x2(o[h8 * 8 + 2], o[h8 * 8 + 3], p.f16);
+              pk.z = pack16x2(o[h8 * 8 + 4], o[h8 * 8 + 5], p.f16);
+              pk.w = pack16x2(o[h8 * 8 + 6], o[h8 * 8 + 7], p.f16);
               *reinterpret_cast<uint4*>(yp + h8 * 8) = pk;
             }
           }
         } else {
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj)
-            if (c0 + jj < p.d) yp[jj] = __float2bfloat16(o[jj]);
+            if (c0 + jj < p.d) yp[jj] = f2h16(o[jj], p.f16);
         }
       }
     }
@@ -375,14 +376,15 @@ static TcLayout tc_layout(int B, int N, int d, const TcGeom& g) {
   return L;
 }
 
-__device__ __forceinline__ __nv_bfloat16 bf_hi(float v) { return __float2bfloat16(v); }
-__device__ __forceinline__ __nv_bfloat16 bf_lo(float v) { return __float2bfloat16(v - __bfloat162float(__float2bfloat16(v))); }
+// hi / lo split of an FP32 value into two 16-bit numbers of the plan's storage format: v ~= hi + lo
+__device__ __forceinline__ __nv_bfloat16 h_hi(float v, int f16) { return f2h16(v, f16); }
+__device__ __forceinline__ __nv_bfloat16 h_lo(float v, int f16) { return f2h16(v - h162f(f2h16(v, f16), f16), f16); }
 
 // proj rows are [x_d | q | k | v] (d each, FP32).  One block stages R consecutive rows of one clip in shared memory
 // (coalesced loads) and writes Q~/K~ rows, x_d rows and the TRANSPOSED value tile V^T[j][n0..n0+R) from there, so every
 // global access is coalesced.
 __global__ void __launch_bounds__(256) attn_tc_pack_kernel(const float* __restrict__ proj, int N, int Npad, int d,
-                                                           int KQ, int DVp, int mode, int R,
+                                                           int KQ, int DVp, int mode, int R, int f16,
                                                            __nv_bfloat16* __restrict__ Q, __nv_bfloat16* __restrict__ K,
                                                            __nv_bfloat16* __restrict__ VT, float* __restrict__ X) {
   extern __shared__ float tile[];  // [R][4d + 1]
@@ -399,25 +401,25 @@ __global__ void __launch_bounds__(256) attn_tc_pack_kernel(const float* __restri
   for (int i = threadIdx.x; i < rows * KQ; i += blockDim.x) {
     const int r = i / KQ, e = i % KQ;
     const float* pr = tile + r * pitch;
-    __nv_bfloat16 qv = __float2bfloat16(0.f), kv = qv;
+    __nv_bfloat16 qv = f2h16(0.f, f16), kv = qv;
     if (mode == 0) {
       const int seg = e >> 3, jj = e & 7;
       if (jj < d && seg < 3) {
         const float q = pr[d + jj], k = pr[2 * d + jj];
-        qv = seg == 1 ? bf_lo(q) : bf_hi(q);
-        kv = seg == 2 ? bf_lo(k) : bf_hi(k);
+        qv = seg == 1 ? h_lo(q, f16) : h_hi(q, f16);
+        kv = seg == 2 ? h_lo(k, f16) : h_hi(k, f16);
       }
     } else if (mode == 1) {
       const int half = KQ >> 1;
       const int part = e / half, jj = e % half;
       if (jj < d) {
         const float q = pr[d + jj], k = pr[2 * d + jj];
-        qv = part ? bf_lo(q) : bf_hi(q);
-        kv = part ? bf_lo(k) : bf_hi(k);
+        qv = part ? h_lo(q, f16) : h_hi(q, f16);
+        kv = part ? h_lo(k, f16) : h_hi(k, f16);
       }
     } else if (e < d) {
-      qv = bf_hi(pr[d + e]);
-      kv = bf_hi(pr[2 * d + e]);
+      qv = h_hi(pr[d + e], f16);
+      kv = h_hi(pr[2 * d + e], f16);
     }
     qd[i] = qv;
     kd[i] = kv;
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(256) attn_tc_pack_kernel(const float* __restri
     const int j = i / R, r = i % R;
     if (n0 + r < Npad) {
       const float v = (j < d && r < rows) ? tile[r * pitch + 3 * d + j] : 0.f;
-      VT[((long long)b * DVp + j) * Npad + n0 + r] = __float2bfloat16(v);
+      VT[((long long)b * DVp + j) * Npad + n0 + r] = f2h16(v, f16);
     }
   }
 }
@@ -445,7 +447,7 @@ struct AttnTcOp : esf_op {
   }
 };
 
-static int encode3(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
+static int encode3(CUtensorMap* m, int f16, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
                    uint64_t s2_bytes, uint32_t b0, uint32_t b1, CUtensorMapSwizzle sw, const char* what) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -453,7 +455,8 @@ static int encode3(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_
   cuuint64_t strides[2] = {s1_bytes, s2_bytes};
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
   return ESF_OK;
@@ -469,8 +472,9 @@ extern "C" int64_t esf_attn_tc_pack_bytes(int32_t B, int32_t N, int32_t d) {
   return tc_layout(B, N, d, g).total;
 }
 
-extern "C" int esf_attn_tc_pack(const float* proj, int32_t B, int32_t N, int32_t d, void* packed, void* stream) {
-  ESF_CHECK_ARG(proj && packed && B > 0 && N > 0, "esf_attn_tc_pack: null/bad argument");
+extern "C" int esf_attn_tc_pack(const float* proj, int32_t B, int32_t N, int32_t d, int32_t dtype, void* packed,
+                                void* stream) {
+  ESF_CHECK_ARG(proj && packed && B > 0 && N > 0 && is16(dtype), "esf_attn_tc_pack: null/bad argument");
   TcGeom g;
   if (!tc_geom(d, &g)) return set_error(ESF_ERR_UNSUPPORTED, "esf_attn_tc_pack: unsupported head dim %d", d);
   const TcLayout L = tc_layout(B, N, d, g);
@@ -480,7 +484,7 @@ extern "C" int esf_attn_tc_pack(const float* proj, int32_t B, int32_t N, int32_t
   while (R > 8 && (size_t)R * (4 * d + 1) * sizeof(float) > 40 * 1024) R >>= 1;
   const size_t smem = (size_t)R * (4 * d + 1) * sizeof(float);
   dim3 grid(cdiv(L.Npad, R), B);
-  attn_tc_pack_kernel<<<grid, 256, smem, s>>>(proj, N, L.Npad, d, g.KQ, g.DVp, g.mode, R,
+  attn_tc_pack_kernel<<<grid, 256, smem, s>>>(proj, N, L.Npad, d, g.KQ, g.DVp, g.mode, R, dtype == ESF_F16,
                                               reinterpret_cast<__nv_bfloat16*>(base + L.q_off),
                                               reinterpret_cast<__nv_bfloat16*>(base + L.k_off),
                                               reinterpret_cast<__nv_bfloat16*>(base + L.v_off),
@@ -492,6 +496,7 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
                                   float gamma, const float* bn_scale, const float* bn_shift, int32_t alpha,
                                   const esf_view* y_fast_slice, esf_op** out) {
   ESF_CHECK_ARG(packed && bn_scale && bn_shift && view_ok(y_fast_slice) && out, "esf_attn_tc_create: null/bad argument");
+  ESF_CHECK_ARG(is16(y_fast_slice->dtype), "esf_attn_tc_create: output must be BF16 or F16");
   TcGeom g;
   if (!tc_geom(d, &g)) return set_error(ESF_ERR_UNSUPPORTED, "esf_attn_tc_create: unsupported head dim %d", d);
   const esf_view* y = y_fast_slice;
@@ -511,6 +516,7 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
   p.y = static_cast<__nv_bfloat16*>(y->ptr);
   p.ysB = y->sB, p.ysT = y->sT, p.ysH = y->sH, p.ysW = y->sW;
   p.DVp = g.DVp, p.nchunks = g.nchunks, p.chunk_el = g.chunk_el;
+  p.f16 = y->dtype == ESF_F16;
   const int RB = g.chunk_el * 2;
   p.sbo = 8 * RB;
   p.layout_type = RB == 128 ? 2 : 4;
@@ -565,13 +571,13 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
   op->smem_bytes = fixed + p.stages * (int)(p.k_tile_bytes + p.v_tile_bytes);
   op->grid = dim3(cdiv(N, 256), B);
   const CUtensorMapSwizzle sw = RB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  int rc = encode3(&p.q_map, base + L.q_off, g.KQ, N, B, (uint64_t)g.KQ * 2, (uint64_t)N * g.KQ * 2, g.chunk_el, 128, sw,
+  int rc = encode3(&p.q_map, p.f16, base + L.q_off, g.KQ, N, B, (uint64_t)g.KQ * 2, (uint64_t)N * g.KQ * 2, g.chunk_el, 128, sw,
                    "attention Q");
   if (rc == ESF_OK)
-    rc = encode3(&p.k_map, base + L.k_off, g.KQ, N, B, (uint64_t)g.KQ * 2, (uint64_t)N * g.KQ * 2, g.chunk_el, kTcBN, sw,
+    rc = encode3(&p.k_map, p.f16, base + L.k_off, g.KQ, N, B, (uint64_t)g.KQ * 2, (uint64_t)N * g.KQ * 2, g.chunk_el, kTcBN, sw,
                  "attention K");
   if (rc == ESF_OK)
-    rc = encode3(&p.v_map, base + L.v_off, N, g.DVp, B, (uint64_t)L.Npad * 2, (uint64_t)g.DVp * L.Npad * 2, kTcBN, g.DVp,
+    rc = encode3(&p.v_map, p.f16, base + L.v_off, N, g.DVp, B, (uint64_t)L.Npad * 2, (uint64_t)g.DVp * L.Npad * 2, kTcBN, g.DVp,
                  CU_TENSOR_MAP_SWIZZLE_128B, "attention V^T");
   if (rc == ESF_OK) {
     static bool attr_set = false;

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -247,6 +248,37 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+// 16-bit activation storage: BF16 or FP16, selected per plan (f16 != 0 -> IEEE half, saturating at +-65504).
+// __nv_bfloat16 is used as the raw 16-bit container type in both cases.
+__device__ __forceinline__ float sat_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+__device__ __forceinline__ __nv_bfloat16 f2h16(float v, int f16) {
+  if (f16) {
+    __half h = __float2half_rn(sat_h(v));
+    return *reinterpret_cast<__nv_bfloat16*>(&h);
+  }
+  return __float2bfloat16(v);
+}
+__device__ __forceinline__ float h162f(__nv_bfloat16 b, int f16) {
+  if (f16) return __half2float(*reinterpret_cast<__half*>(&b));
+  return __bfloat162float(b);
+}
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int f16) {
+  if (f16) {
+    __half2 v = __floats2half2_rn(sat_h(lo), sat_h(hi));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack16x2(uint32_t u, int f16) {
+  if (f16) return __half22float2(*reinterpret_cast<__half2*>(&u));
+  return unpack_bf16x2(u);
+}
+// kind::f16 instruction descriptor for either 16-bit operand format (a/b format: 0 = F16, 1 = BF16)
+__host__ __device__ __forceinline__ uint32_t make_idesc_16(int M, int N, int f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == 1) return fmaxf(v, 0.f);
   if (act == 2) return fminf(fmaxf(v, 0.f), 6.f);

@@ -38,6 +38,8 @@ inline bool view_ok(const esf_view* v) {
   return v && v->ptr && v->B > 0 && v->T > 0 && v->H > 0 && v->W > 0 && v->C > 0 && v->sW >= v->C;
 }
 
+inline bool is16(int dtype) { return dtype == ESF_BF16 || dtype == ESF_F16; }
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 int num_sms();  // SM count of the current device (cached); 0 when there is no device

@@ -52,7 +52,7 @@ struct __align__(64) IgemmParams {
   uint32_t sbo, layout_type;            // UMMA descriptor fields for the A/B swizzle mode
   uint32_t res_bytes;
   const float* bias;
-  int act, has_res, out_f32;
+  int act, has_res, out_f32, f16;  // f16: 16-bit operands / outputs are IEEE half instead of BF16
   int slab_cols;      // output columns per TMA store slab
   uint32_t out_swz;   // swizzle mask of the staging rows (7 / 3 / 1)
   int num_tiles;
@@ -109,7 +109,7 @@ __device__ __forceinline__ void epi_process(const IgemmParams& p, uint32_t taddr
         const uint32_t u[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack_bf16x2(u[e]);
+          const float2 f = unpack16x2(u[e], p.f16);
           v[8 * c + 2 * e] += f.x;
           v[8 * c + 2 * e + 1] += f.y;
         }
@@ -121,10 +121,10 @@ __device__ __forceinline__ void epi_process(const IgemmParams& p, uint32_t taddr
 #pragma unroll
       for (int c = 0; c < NC / 8; ++c) {
         uint4 o;
-        o.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]);
-        o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
-        o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
-        o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+        o.x = pack16x2(v[8 * c + 0], v[8 * c + 1], p.f16);
+        o.y = pack16x2(v[8 * c + 2], v[8 * c + 3], p.f16);
+        o.z = pack16x2(v[8 * c + 4], v[8 * c + 5], p.f16);
+        o.w = pack16x2(v[8 * c + 6], v[8 * c + 7], p.f16);
         *reinterpret_cast<uint4*>(stage_buf + swz(base + c * 16, p.out_swz)) = o;
       }
     }
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   } else if (warp == kMmaWarp) {
     {
       // the issuing thread is a serial instruction stream: keep it to two adds per MMA (descriptor lo words)
-      const uint32_t idesc = make_idesc_bf16(128, p.n_tile);
+      const uint32_t idesc = make_idesc_16(128, p.n_tile, p.f16);
       const uint32_t desc_hi = kmajor_desc_hi(p.sbo, p.layout_type);
       const uint32_t a_lo0 = kmajor_desc_lo(smem_u32(smem_a)), b_lo0 = kmajor_desc_lo(smem_u32(smem_b));
       const uint32_t a_step = kAStageBytes >> 4, b_step = p.b_stride >> 4;
@@ -458,8 +458,12 @@ extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
                 y.H, y.W, x.B, To, Ho, Wo);
   const int num_taps = d->kT * d->kH * d->kW;
   ESF_CHECK_ARG(num_taps <= kMaxTaps, "esf_conv_igemm_create: %d taps > %d", num_taps, kMaxTaps);
-  ESF_CHECK_ARG(d->out_dtype == ESF_BF16 || d->out_dtype == ESF_F32, "esf_conv_igemm_create: bad out_dtype");
-  ESF_CHECK_ARG(!(d->out_dtype == ESF_F32 && d->res.ptr), "esf_conv_igemm_create: residual needs a BF16 output");
+  ESF_CHECK_ARG(is16(x.dtype), "esf_conv_igemm_create: input must be BF16 or F16");
+  ESF_CHECK_ARG(d->out_dtype == ESF_F32 || d->out_dtype == x.dtype,
+                "esf_conv_igemm_create: out_dtype must be F32 or the input's 16-bit format");
+  ESF_CHECK_ARG(y.dtype == d->out_dtype, "esf_conv_igemm_create: y.dtype != out_dtype");
+  ESF_CHECK_ARG(!(d->out_dtype == ESF_F32 && d->res.ptr), "esf_conv_igemm_create: residual needs a 16-bit output");
+  if (d->res.ptr) ESF_CHECK_ARG(d->res.dtype == x.dtype, "esf_conv_igemm_create: residual format != input format");
   if (d->res.ptr)
     ESF_CHECK_ARG(d->res.B == y.B && d->res.T == y.T && d->res.H == y.H && d->res.W == y.W && d->res.C == y.C,
                   "esf_conv_igemm_create: residual view must match the output view");
@@ -499,6 +503,8 @@ extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
   p.act = d->act;
   p.has_res = d->res.ptr != nullptr;
   p.out_f32 = d->out_dtype == ESF_F32;
+  p.f16 = x.dtype == ESF_F16;
+  const CUtensorMapDataType dt16 = p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const int oes = p.out_f32 ? 4 : 2;
   p.slab_cols = std::min(n_tile, 128 / oes);
   const int out_row_bytes = p.slab_cols * oes;
@@ -544,7 +550,7 @@ extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
             break;
           }
           char* base = static_cast<char*>(x.ptr) + 2 * (ph.pt * x.sT + ph.ph * x.sH + ph.pw * x.sW);
-          rc = encode_act_map(&p.a_maps[idx], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, x.C, Wp, Hp, Tp, x.B,
+          rc = encode_act_map(&p.a_maps[idx], dt16, 2, base, x.C, Wp, Hp, Tp, x.B,
                               x.sW * d->sW, x.sH * d->sH, x.sT * d->sT, x.sB, kc, p.bw, p.bh, p.bt, p.bb,
                               swizzle_for_row_bytes(row_bytes), "activation");
         }
@@ -564,7 +570,7 @@ extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
       cuuint64_t strides[1] = {K * 2};
       cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)n_tile};
       cuuint32_t estr[2] = {1, 1};
-      CUresult r = enc(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
+      CUresult r = enc(&p.b_map, dt16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(row_bytes),
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) rc = set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
@@ -572,12 +578,12 @@ extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
   }
   // ---- output (+ residual) maps: box (slab_cols, bw, bh, bt, bb)
   if (rc == ESF_OK)
-    rc = encode_act_map(&p.out_map, p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, oes,
+    rc = encode_act_map(&p.out_map, p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt16, oes,
                         y.ptr, y.C, y.W, y.H, y.T, y.B, y.sW, y.sH, y.sT, y.sB, p.slab_cols, p.bw, p.bh, p.bt, p.bb,
                         swizzle_for_row_bytes(out_row_bytes), "output");
   if (rc == ESF_OK) {
     if (p.has_res)
-      rc = encode_act_map(&p.res_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->res.ptr, d->res.C, d->res.W, d->res.H,
+      rc = encode_act_map(&p.res_map, dt16, 2, d->res.ptr, d->res.C, d->res.W, d->res.H,
                           d->res.T, d->res.B, d->res.sW, d->res.sH, d->res.sT, d->res.sB, p.slab_cols, p.bw, p.bh, p.bt,
                           p.bb, swizzle_for_row_bytes(out_row_bytes), "residual");
     else
@@ -628,6 +634,7 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
                                      int32_t kT, int32_t kH, int32_t kW, int32_t sH, int32_t sW, int32_t pT, int32_t pH,
                                      int32_t pW, int32_t act, const esf_view* y, esf_op** out) {
   ESF_CHECK_ARG(xp && w_band && bias_tiled && view_ok(y) && out, "esf_stem_igemm_create: null/bad argument");
+  ESF_CHECK_ARG(is16(y->dtype), "esf_stem_igemm_create: output must be BF16 or F16");
   int pt_expected = 0, lpad = 0, win = 0;
   int rc = esf_stem_geometry(W, Cin, kW, sW, pW, &pt_expected, &lpad, &win);
   if (rc != ESF_OK) return rc;
@@ -665,6 +672,8 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
   p.a_bytes = p.rows * 128, p.b_bytes = n_tile * 128, p.b_stride = (p.b_bytes + 1023) & ~1023u;
   p.sbo = 1024, p.layout_type = 2;
   p.bias = bias_tiled, p.act = act, p.has_res = 0, p.out_f32 = 0;
+  p.f16 = y->dtype == ESF_F16;
+  const CUtensorMapDataType dt16 = p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   p.slab_cols = std::min(n_tile, 64);
   const int out_row_bytes = p.slab_cols * 2;
   p.out_swz = out_row_bytes == 128 ? 7 : (out_row_bytes == 64 ? 3 : 1);
@@ -694,7 +703,7 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
           break;
         }
         char* base = static_cast<char*>(const_cast<void*>(xp)) + 2LL * ph * pitch;
-        rc = encode_act_map(&p.a_maps[nmaps], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, pitch, 1, Hp, T, B,
+        rc = encode_act_map(&p.a_maps[nmaps], dt16, 2, base, pitch, 1, Hp, T, B,
                             (int64_t)sH * pitch, (int64_t)sH * pitch, (int64_t)H * pitch, (int64_t)T * H * pitch, 64,
                             1, p.bh, p.bt, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, "stem activation");
         phase_map[ph] = nmaps++;
@@ -712,7 +721,7 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
       cuuint64_t strides[1] = {K * 2};
       cuuint32_t box[2] = {64, (cuuint32_t)n_tile};
       cuuint32_t estr[2] = {1, 1};
-      CUresult r = enc(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_band), dims, strides, box,
+      CUresult r = enc(&p.b_map, dt16, 2, const_cast<void*>(w_band), dims, strides, box,
                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) rc = set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled(stem weights) failed with %d", (int)r);
@@ -720,7 +729,7 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
   }
   if (rc == ESF_OK)
     // dims (8*Cout, Wo/8, Ho, To, B): the column block is the W coordinate, so a tile wider than 8*Cout is clipped
-    rc = encode_act_map(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y->ptr, (int64_t)kStemWB * Cout, Wo / kStemWB,
+    rc = encode_act_map(&p.out_map, dt16, 2, y->ptr, (int64_t)kStemWB * Cout, Wo / kStemWB,
                         Ho, To, B, (int64_t)kStemWB * Cout, y->sH, y->sT, y->sB, p.slab_cols, 1, p.bh, p.bt, p.bb,
                         swizzle_for_row_bytes(out_row_bytes), "stem output");
   if (rc == ESF_OK) {

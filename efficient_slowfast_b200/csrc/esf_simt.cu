@@ -14,19 +14,24 @@ struct View {
   char* ptr;
   int B, T, H, W, C;
   long long sB, sT, sH, sW;
+  int f16;  // 16-bit storage is IEEE half (else BF16)
 };
 static View to_view(const esf_view* v) {
   View r;
   r.ptr = static_cast<char*>(v->ptr);
   r.B = v->B, r.T = v->T, r.H = v->H, r.W = v->W, r.C = v->C;
   r.sB = v->sB, r.sT = v->sT, r.sH = v->sH, r.sW = v->sW;
+  r.f16 = v->dtype == ESF_F16;
   return r;
 }
 __device__ __forceinline__ long long voff(const View& v, int b, int t, int h, int w) {
   return b * v.sB + t * v.sT + h * v.sH + w * v.sW;
 }
-__device__ __forceinline__ float ldbf(const char* base, long long idx) {
-  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+__device__ __forceinline__ float ldbf(const View& v, long long idx) {
+  return h162f(reinterpret_cast<const __nv_bfloat16*>(v.ptr)[idx], v.f16);
+}
+__device__ __forceinline__ void sth(const View& v, long long idx, float x) {
+  reinterpret_cast<__nv_bfloat16*>(v.ptr)[idx] = f2h16(x, v.f16);
 }
 
 // ------------------------------------------------------------------------------------------- stem conv
@@ -79,14 +84,14 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + voff(p.y, b, to, ho, wo) + cg * CO_T;
     if constexpr (CO_T == 8) {
       uint4 o;
-      o.x = pack_bf16x2(apply_act(acc[0], p.act), apply_act(acc[1], p.act));
-      o.y = pack_bf16x2(apply_act(acc[2], p.act), apply_act(acc[3], p.act));
-      o.z = pack_bf16x2(apply_act(acc[4], p.act), apply_act(acc[5], p.act));
-      o.w = pack_bf16x2(apply_act(acc[6], p.act), apply_act(acc[7], p.act));
+      o.x = pack16x2(apply_act(acc[0], p.act), apply_act(acc[1], p.act), p.y.f16);
+      o.y = pack16x2(apply_act(acc[2], p.act), apply_act(acc[3], p.act), p.y.f16);
+      o.z = pack16x2(apply_act(acc[4], p.act), apply_act(acc[5], p.act), p.y.f16);
+      o.w = pack16x2(apply_act(acc[6], p.act), apply_act(acc[7], p.act), p.y.f16);
       *reinterpret_cast<uint4*>(yp) = o;
     } else {
 #pragma unroll
-      for (int j = 0; j < CO_T; ++j) yp[j] = __float2bfloat16(apply_act(acc[j], p.act));
+      for (int j = 0; j < CO_T; ++j) yp[j] = f2h16(apply_act(acc[j], p.act), p.y.f16);
     }
   }
 }
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
 // zeros in the left/right padding (the zero padding of the stem conv along W, made explicit so that every banded
 // GEMM block starts 16-byte aligned).  One thread per 8 consecutive output elements (one 16 B store).
 __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x, int B, int Cin, int T, int H, int W,
-                                                        int pitch, int lpad, __nv_bfloat16* __restrict__ xp) {
+                                                        int pitch, int lpad, int f16, __nv_bfloat16* __restrict__ xp) {
   const int chunks = pitch / 8;
   const long long total = (long long)B * T * H * chunks;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -115,10 +120,10 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict_
       v[e] = (j >= 0 && w < W) ? __ldg(x + ((((long long)b * Cin + c) * T + t) * H + h) * W + w) : 0.f;
     }
     uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]);
-    o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]);
-    o.w = pack_bf16x2(v[6], v[7]);
+    o.x = pack16x2(v[0], v[1], f16);
+    o.y = pack16x2(v[2], v[3], f16);
+    o.z = pack16x2(v[4], v[5], f16);
+    o.w = pack16x2(v[6], v[7], f16);
     *reinterpret_cast<uint4*>(xp + (((long long)b * T + t) * H + h) * pitch + ck * 8) = o;
   }
 }
@@ -160,15 +165,15 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectParams p) 
           if (wi < 0 || wi >= p.x.W) continue;
           const long long xo = voff(p.x, b, ti, hi, wi) + g * cin_g;
           const float* wp = wbase + ((kt * p.kH + kh) * p.kW + kw) * cin_g;
-          for (int ci = 0; ci < cin_g; ++ci) acc = fmaf(ldbf(p.x.ptr, xo + ci), __ldg(wp + ci), acc);
+          for (int ci = 0; ci < cin_g; ++ci) acc = fmaf(ldbf(p.x, xo + ci), __ldg(wp + ci), acc);
         }
       }
     }
     const long long yo = voff(p.y, b, to, ho, wo) + co;
-    if (p.has_res) acc += ldbf(p.res.ptr, voff(p.res, b, to, ho, wo) + co);
+    if (p.has_res) acc += ldbf(p.res, voff(p.res, b, to, ho, wo) + co);
     acc = apply_act(acc, p.act);
     if (p.out_f32) reinterpret_cast<float*>(p.y.ptr)[yo] = acc;
-    else reinterpret_cast<__nv_bfloat16*>(p.y.ptr)[yo] = __float2bfloat16(acc);
+    else sth(p.y, yo, acc);
   }
 }
 
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(256) pool3d_kernel(const PoolParams p) {
             const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16x2(uu[e]);
+              const float2 f = unpack16x2(uu[e], p.x.f16);
               if (p.is_avg) {
                 acc[2 * e] += f.x;
                 acc[2 * e + 1] += f.y;
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(256) pool3d_kernel(const PoolParams p) {
               }
             }
           } else {
-            const float f = __bfloat162float(xp[0]);
+            const float f = h162f(xp[0], p.x.f16);
             acc[0] = p.is_avg ? acc[0] + f : fmaxf(acc[0], f);
           }
         }
@@ -236,13 +241,13 @@ __global__ void __launch_bounds__(256) pool3d_kernel(const PoolParams p) {
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + voff(p.y, b, to, ho, wo) + c;
     if constexpr (VEC == 8) {
       uint4 o;
-      o.x = pack_bf16x2(acc[0], acc[1]);
-      o.y = pack_bf16x2(acc[2], acc[3]);
-      o.z = pack_bf16x2(acc[4], acc[5]);
-      o.w = pack_bf16x2(acc[6], acc[7]);
+      o.x = pack16x2(acc[0], acc[1], p.y.f16);
+      o.y = pack16x2(acc[2], acc[3], p.y.f16);
+      o.z = pack16x2(acc[4], acc[5], p.y.f16);
+      o.w = pack16x2(acc[6], acc[7], p.y.f16);
       *reinterpret_cast<uint4*>(yp) = o;
     } else {
-      yp[0] = __float2bfloat16(acc[0]);
+      yp[0] = f2h16(acc[0], p.y.f16);
     }
   }
 }
@@ -269,7 +274,7 @@ __device__ __forceinline__ float eca_tmax(const EcaParams& p, int b, long long p
   const int h = r % p.x.H;
   const int tp = r / p.x.H;
   float m = -CUDART_INF_F;
-  for (int a = 0; a < p.alpha; ++a) m = fmaxf(m, ldbf(p.x.ptr, voff(p.x, b, tp * p.alpha + a, h, w) + c));
+  for (int a = 0; a < p.alpha; ++a) m = fmaxf(m, ldbf(p.x, voff(p.x, b, tp * p.alpha + a, h, w) + c));
   return m;
 }
 
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(kEcaThreads) eca_apply_kernel(const EcaParams 
     const long long r = pos / p.x.W;
     const int h = r % p.x.H;
     const int tp = r / p.x.H;
-    reinterpret_cast<__nv_bfloat16*>(p.y.ptr)[voff(p.y, b, tp, h, w) + c] = __float2bfloat16(v);
+    sth(p.y, voff(p.y, b, tp, h, w) + c, v);
   }
 }
 
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(256) head_pool_kernel(const View x, float* fea
       const long long r = pos / x.W;
       const int h = r % x.H;
       const int t = r / x.H;
-      s += ldbf(x.ptr, voff(x, b, t, h, w) + c);
+      s += ldbf(x, voff(x, b, t, h, w) + c);
     }
   red[l][threadIdx.x & 63] = s;
   __syncthreads();
@@ -454,8 +459,8 @@ __global__ void __launch_bounds__(256) eltwise_add_kernel(const View a, const Vi
     pos /= y.H;
     const int t = pos % y.T;
     const int bb = pos / y.T;
-    const float v = ldbf(a.ptr, voff(a, bb, t, h, w) + c) + ldbf(b.ptr, voff(b, bb, t, h, w) + c);
-    reinterpret_cast<__nv_bfloat16*>(y.ptr)[voff(y, bb, t, h, w) + c] = __float2bfloat16(apply_act(v, act));
+    const float v = ldbf(a, voff(a, bb, t, h, w) + c) + ldbf(b, voff(b, bb, t, h, w) + c);
+    sth(y, voff(y, bb, t, h, w) + c, apply_act(v, act));
   }
 }
 // y = x * scale[b][c]  (squeeze-excite gate, ghostnet_helper.py:46-52)
@@ -472,8 +477,8 @@ __global__ void __launch_bounds__(256) channel_scale_kernel(const View x, const 
     pos /= y.H;
     const int t = pos % y.T;
     const int bb = pos / y.T;
-    const float v = ldbf(x.ptr, voff(x, bb, t, h, w) + c) * __ldg(scale + (long long)bb * C + c);
-    reinterpret_cast<__nv_bfloat16*>(y.ptr)[voff(y, bb, t, h, w) + c] = __float2bfloat16(v);
+    const float v = ldbf(x, voff(x, bb, t, h, w) + c) * __ldg(scale + (long long)bb * C + c);
+    sth(y, voff(y, bb, t, h, w) + c, v);
   }
 }
 
@@ -512,12 +517,13 @@ extern "C" int esf_stem_conv(const float* x, int32_t B, int32_t Cin, int32_t T, 
 }
 
 extern "C" int esf_stem_pack(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
-                             int32_t lpad, void* xp, void* stream) {
+                             int32_t lpad, int32_t dtype, void* xp, void* stream) {
+  ESF_CHECK_ARG(is16(dtype), "esf_stem_pack: dtype must be BF16 or F16");
   ESF_CHECK_ARG(x && xp && B > 0 && Cin > 0 && T > 0 && H > 0 && W > 0, "esf_stem_pack: null/bad argument");
   ESF_CHECK_ARG(pitch % 8 == 0 && pitch >= lpad + W * Cin, "esf_stem_pack: bad pitch %d", pitch);
   const long long total = (long long)B * T * H * (pitch / 8);
   stem_pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, B, Cin, T, H, W, pitch, lpad, static_cast<__nv_bfloat16*>(xp));
+      x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp));
   return check_launch("stem_pack_kernel");
 }
 

@@ -38,8 +38,8 @@ def fold_conv_bn(weight, conv_bias, bn):
     return w, b
 
 
-def pack_igemm_weight(w, bias, device):
-    """Folded (Cout,Cin,kT,kH,kW) FP64 weight -> BF16 [n_pad][taps*kchunks*kc] (tap-major, then input channel) and
+def pack_igemm_weight(w, bias, device, dtype=torch.bfloat16):
+    """Folded (Cout,Cin,kT,kH,kW) FP64 weight -> 16-bit [n_pad][taps*kchunks*kc] (tap-major, then input channel) and
     FP32 bias [n_pad], the layout esf_conv_igemm_create expects."""
     cout, cin, kt, kh, kw = w.shape
     kc, kchunks, _, n_pad = rt.igemm_geometry(cin, cout)
@@ -48,14 +48,14 @@ def pack_igemm_weight(w, bias, device):
     wp[:cout, :, :cin] = w.permute(0, 2, 3, 4, 1).reshape(cout, kt * kh * kw, cin)
     bp = torch.zeros(n_pad, dtype=torch.float64, device=w.device)
     bp[:cout] = bias
-    return (wp.reshape(n_pad, -1).to(device=device, dtype=torch.bfloat16).contiguous(),
+    return (wp.reshape(n_pad, -1).to(device=device, dtype=dtype).contiguous(),
             bp.to(device=device, dtype=torch.float32).contiguous())
 
 
 STEM_WB = 8  # output columns per banded-GEMM block (csrc/esf_igemm.cu kStemWB)
 
 
-def pack_stem_band(w, bias, stride_w, device):
+def pack_stem_band(w, bias, stride_w, device, dtype=torch.bfloat16):
     """Folded (Cout,Cin,kT,kH,kW) stem weight -> band matrix BF16 [n_pad][kT*kH*64] and tiled bias FP32 [n_pad].
     Row n = i*Cout + co (i = output column inside the 8-wide block); column k = (kt*kH + kh)*64 + j where
     (w_in, c) = divmod(j, Cin) is the j-th element of the contiguous input run the block reads and kw = w_in - sW*i."""
@@ -71,7 +71,7 @@ def pack_stem_band(w, bias, stride_w, device):
         band[i * cout:(i + 1) * cout, :, j0:j0 + kw * cin] = wt.reshape(cout, kt * kh, kw * cin)
     bt = torch.zeros(n_pad, dtype=torch.float64, device=w.device)
     bt[:N] = bias.repeat(STEM_WB)
-    return (band.reshape(n_pad, -1).to(device=device, dtype=torch.bfloat16).contiguous(),
+    return (band.reshape(n_pad, -1).to(device=device, dtype=dtype).contiguous(),
             bt.to(device=device, dtype=torch.float32).contiguous())
 
 
@@ -79,8 +79,11 @@ class Plan:
     """Ordered kernel launches + every tensor they touch.  `eager` ops read the caller's input tensors and are
     launched on every forward; `graph` ops only touch plan-owned memory and are replayed from one CUDA graph."""
 
-    def __init__(self, device):
+    def __init__(self, device, precision="bf16"):
         self.device = device
+        self.precision = precision
+        self.adt = rt.TORCH_DTYPE[precision]      # 16-bit storage format of activations / tensor-core operands
+        self.a16 = rt.dtype_code(self.adt)
         self.keep = []        # tensors / ctypes structs that must outlive the plan
         self.ops = []         # callables taking a stream pointer
         self.handles = []     # esf_op* to destroy
@@ -92,8 +95,8 @@ class Plan:
         self.attn_impl = "tcgen05"   # "tcgen05" (TMEM, two-pass) or "mma_sync" (register-resident, online softmax)
 
     # ---------------------------------------------------------------- memory
-    def act(self, B, T, H, W, C, name=None, dtype=torch.bfloat16):
-        t = torch.empty((B, T, H, W, C), dtype=dtype, device=self.device)
+    def act(self, B, T, H, W, C, name=None, dtype=None):
+        t = torch.empty((B, T, H, W, C), dtype=dtype or self.adt, device=self.device)
         self.keep.append(t)
         if name:
             self.buffers[name] = t
@@ -116,8 +119,9 @@ class Plan:
 
     # ---------------------------------------------------------------- ops
     def conv_igemm(self, x, y, w_folded, bias, stride=(1, 1, 1), padding=(0, 0, 0), dilation=(1, 1, 1), act=rt.ACT_NONE,
-                   res=None, out_dtype=rt.BF16):
-        wp, bp = pack_igemm_weight(w_folded, bias, self.device)
+                   res=None, out_dtype=None):
+        out_dtype = rt.dtype_code(y)
+        wp, bp = pack_igemm_weight(w_folded, bias, self.device, self.adt)
         self.keep += [wp, bp]
         kt, kh, kw = w_folded.shape[2:]
         d = rt.EsfConvDesc(rt.view(x), rt.view(y), rt.view(res) if res is not None else rt.null_view(),
@@ -141,7 +145,7 @@ class Plan:
         return t.data_ptr() % 16 == 0 and all(st % q == 0 for st in t.stride()[:4])
 
     def conv(self, x, y, w_folded, bias, stride=(1, 1, 1), padding=(0, 0, 0), dilation=(1, 1, 1), groups=1,
-             act=rt.ACT_NONE, res=None, out_dtype=rt.BF16):
+             act=rt.ACT_NONE, res=None, out_dtype=None):
         """Conv3d + folded BN (+ residual) + activation: tensor-core implicit GEMM when the layer is dense and its
         views are 16-byte addressable, CUDA-core direct conv otherwise (grouped / depthwise / odd channel counts)."""
         if groups == 1 and x.shape[4] >= 8 and self._aligned(x) and self._aligned(y) and self._aligned(res):
@@ -149,7 +153,8 @@ class Plan:
         return self.conv_direct(x, y, w_folded, bias, stride, padding, dilation, groups, act, res, out_dtype)
 
     def conv_direct(self, x, y, w_folded, bias, stride=(1, 1, 1), padding=(0, 0, 0), dilation=(1, 1, 1), groups=1,
-                    act=rt.ACT_NONE, res=None, out_dtype=rt.BF16):
+                    act=rt.ACT_NONE, res=None, out_dtype=None):
+        out_dtype = rt.dtype_code(y)
         wd = self.tensor(w_folded.permute(0, 2, 3, 4, 1))  # [Cout][kT][kH][kW][Cin/g]
         bd = self.tensor(bias)
         kt, kh, kw = w_folded.shape[2:]
@@ -192,8 +197,8 @@ class Plan:
             return self.stem_conv(x_nc, y, w_folded, bias, stride, padding, act)
         pitch, lpad, _ = geo
         L = rt.lib()
-        xp = torch.empty((B, T, H, pitch), dtype=torch.bfloat16, device=self.device)
-        wb, bt = pack_stem_band(w_folded, bias, stride[2], self.device)
+        xp = torch.empty((B, T, H, pitch), dtype=self.adt, device=self.device)
+        wb, bt = pack_stem_band(w_folded, bias, stride[2], self.device, self.adt)
         self.keep += [xp, wb, bt]
         yv = rt.view(y)
         h = ctypes.c_void_p()
@@ -202,7 +207,7 @@ class Plan:
                                          ctypes.byref(yv), ctypes.byref(h)), "esf_stem_igemm_create")
         self.handles.append(h)
         m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
-        self._add(lambda s: rt.check(L.esf_stem_pack(x_nc.data_ptr(), B, Cin, T, H, W, pitch, lpad, xp.data_ptr(), s),
+        self._add(lambda s: rt.check(L.esf_stem_pack(x_nc.data_ptr(), B, Cin, T, H, W, pitch, lpad, self.a16, xp.data_ptr(), s),
                                      "esf_stem_pack"), "stem_pack", "", nbytes=self._nbytes(x_nc, xp))
         self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "stem_igemm",
                   "%dx%dx%d %d->%d banded" % (kt, kh, kw, Cin, cout), flops=2.0 * m * cout * Cin * kt * kh * kw,
@@ -286,7 +291,7 @@ class Plan:
         w_all = torch.cat(mats, 0).reshape(4 * d, C, 1, 1, 1)
         b_all = torch.cat(biases, 0)
         proj = self.act(B, T, H, W, 4 * d, dtype=torch.float32)
-        self.conv(x_slow, proj, w_all, b_all, out_dtype=rt.F32)
+        self.conv(x_slow, proj, w_all, b_all)
         L = rt.lib()
         N = T * H * W
         if d > 128:
@@ -314,7 +319,7 @@ class Plan:
             rt.check(L.esf_attn_tc_create(packed.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(), sh.data_ptr(), alpha,
                                           ctypes.byref(yv), ctypes.byref(h)), "esf_attn_tc_create")
             self.handles.append(h)
-            self._add(lambda s: rt.check(L.esf_attn_tc_pack(proj.data_ptr(), B, N, d, packed.data_ptr(), s),
+            self._add(lambda s: rt.check(L.esf_attn_tc_pack(proj.data_ptr(), B, N, d, self.a16, packed.data_ptr(), s),
                                          "esf_attn_tc_pack"), "attn_pack", "N=%d d=%d" % (N, d),
                       nbytes=self._nbytes(proj) + nbytes)
             self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "attention",

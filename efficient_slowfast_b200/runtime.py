@@ -9,14 +9,16 @@ _LIB = None
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libesf_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
-BF16, F32 = 0, 1
+BF16, F32, F16 = 0, 1, 2
+_DTYPE_CODE = {torch.bfloat16: BF16, torch.float32: F32, torch.float16: F16}
+TORCH_DTYPE = {"bf16": torch.bfloat16, "fp16": torch.float16}
 HEAD_NONE, HEAD_SOFTMAX, HEAD_RELU, HEAD_SIGMOID, HEAD_HARD_SIGMOID = 0, 1, 2, 3, 4
 
 
 class EsfView(ctypes.Structure):
     _fields_ = [("ptr", ctypes.c_void_p), ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("H", ctypes.c_int32),
                 ("W", ctypes.c_int32), ("C", ctypes.c_int32), ("sB", ctypes.c_int64), ("sT", ctypes.c_int64),
-                ("sH", ctypes.c_int64), ("sW", ctypes.c_int64)]
+                ("sH", ctypes.c_int64), ("sW", ctypes.c_int64), ("dtype", ctypes.c_int32)]
 
 
 class EsfConvDesc(ctypes.Structure):
@@ -61,7 +63,7 @@ def lib():
     L.esf_stem_conv.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32,
                                 i32, P(EsfView), vp]
     L.esf_stem_geometry.argtypes = [i32, i32, i32, i32, i32, P(i32), P(i32), P(i32)]
-    L.esf_stem_pack.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+    L.esf_stem_pack.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     L.esf_stem_igemm_create.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32,
                                         i32, i32, i32, P(EsfView), P(vp)]
     L.esf_pool3d.argtypes = [P(EsfView), P(EsfView), i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
@@ -77,7 +79,7 @@ def lib():
     L.esf_attn_fused.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, i32, P(EsfView), vp]
     L.esf_attn_tc_pack_bytes.argtypes = [i32, i32, i32]
     L.esf_attn_tc_pack_bytes.restype = i64
-    L.esf_attn_tc_pack.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.esf_attn_tc_pack.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.esf_attn_tc_create.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, i32, P(EsfView), P(vp)]
     L.esf_attn_generic.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, i32, P(EsfView), vp]
     L.esf_head_pool.argtypes = [P(EsfView), P(EsfView), vp, vp]
@@ -105,11 +107,15 @@ def view(t):
     assert t.dim() == 5 and t.stride(4) == 1, "activation views are (B,T,H,W,C) with unit channel stride"
     B, T, H, W, C = t.shape
     sB, sT, sH, sW, _ = t.stride()
-    return EsfView(t.data_ptr(), B, T, H, W, C, sB, sT, sH, sW)
+    return EsfView(t.data_ptr(), B, T, H, W, C, sB, sT, sH, sW, _DTYPE_CODE[t.dtype])
 
 
 def null_view():
-    return EsfView(None, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+    return EsfView(None, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+
+
+def dtype_code(t):
+    return _DTYPE_CODE[t.dtype if isinstance(t, torch.Tensor) else t]
 
 
 def igemm_geometry(cin, cout):

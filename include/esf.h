@@ -9,8 +9,10 @@
  *
  * Conventions
  *   - plain pointers and sizes only; all pointers are DEVICE pointers unless a name ends in _host;
- *   - activations are channels-last 5-D views (B,T,H,W,C) with element strides (channel stride 1), BF16
- *     unless stated; a view may be a channel slice of a wider concat buffer (C < sW);
+ *   - activations are channels-last 5-D views (B,T,H,W,C) with element strides (channel stride 1) in one
+ *     16-bit storage format per plan -- BF16 or FP16 (view.dtype; all views of a call must agree; tensor-core
+ *     operands and packed weights use the same format, accumulation is always FP32); a view may be a channel
+ *     slice of a wider concat buffer (C < sW);
  *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued, never synchronised;
  *   - every function returns 0 on success or a negative code; esf_last_error() gives the message of the
  *     last failure on the calling thread; nothing throws, nothing allocates device memory;
@@ -35,11 +37,13 @@ extern "C" {
 
 #define ESF_BF16 0
 #define ESF_F32 1
+#define ESF_F16 2
 
 typedef struct esf_view {
   void* ptr;
   int32_t B, T, H, W, C;
   int64_t sB, sT, sH, sW; /* element strides; channel stride == 1 */
+  int32_t dtype;          /* ESF_BF16 / ESF_F16 (16-bit activation storage) or ESF_F32 */
 } esf_view;
 
 typedef struct esf_conv_desc {
@@ -100,7 +104,7 @@ int esf_stem_conv(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, 
 int esf_stem_geometry(int32_t W, int32_t Cin, int32_t kW, int32_t sW, int32_t pW, int32_t* pitch, int32_t* lpad,
                       int32_t* window);
 int esf_stem_pack(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
-                  int32_t lpad, void* xp, void* stream);
+                  int32_t lpad, int32_t dtype, void* xp, void* stream);
 int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
                           const void* w_band, const float* bias_tiled, int32_t Cout, int32_t kT, int32_t kH,
                           int32_t kW, int32_t sH, int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t act,
@@ -147,7 +151,7 @@ int esf_attn_fused(const void* packed, int32_t B, int32_t T, int32_t H, int32_t 
  * Preferred path; any head dim d <= 128.  esf_attn_tc_pack writes Q~/K~ (BF16 hi/lo split rows), V^T and x_d into
  * `packed` (esf_attn_tc_pack_bytes bytes); esf_attn_tc_create plans the fused kernel (launch: esf_op_launch). */
 int64_t esf_attn_tc_pack_bytes(int32_t B, int32_t N, int32_t d);
-int esf_attn_tc_pack(const float* proj, int32_t B, int32_t N, int32_t d, void* packed, void* stream);
+int esf_attn_tc_pack(const float* proj, int32_t B, int32_t N, int32_t d, int32_t dtype, void* packed, void* stream);
 int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d, float gamma,
                        const float* bn_scale, const float* bn_shift, int32_t alpha, const esf_view* y_fast_slice,
                        esf_op** out);

@@ -37,11 +37,12 @@ def case_cfg(name):
     return cfg
 
 
-def case_model_and_weights(name):
+def case_model_and_weights(name, precision="bf16"):
     """(cfg, model on CPU with the seeded + calibrated golden weights loaded)."""
     import efficient_slowfast_b200 as esf
 
     cfg = case_cfg(name)
+    cfg.ESF.PRECISION = precision
     torch.manual_seed(0)
     model = esf.build_model(cfg)
     gold = load_golden(name)

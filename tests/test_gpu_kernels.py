@@ -13,8 +13,8 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _rand_act(g, B, T, H, W, C, scale=1.0):
-    return (torch.randn(B, T, H, W, C, generator=g) * scale).to(torch.bfloat16)
+def _rand_act(g, B, T, H, W, C, scale=1.0, dtype=torch.bfloat16):
+    return (torch.randn(B, T, H, W, C, generator=g) * scale).to(dtype)
 
 
 def _to_ncdhw(t):
@@ -69,35 +69,37 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_conv_igemm(esf_lib, case):
+def test_conv_igemm(esf_lib, case, precision):
     name, (B, T, H, W), cin, cout, k, s, p, d, act, use_res, out_f32 = case
-    g = torch.Generator().manual_seed(hash(name) % 1000)
+    adt = rt.TORCH_DTYPE[precision]
+    g = torch.Generator().manual_seed(sum(map(ord, name)) % 1000)
     # input and output live inside wider concat buffers (channel slices) to exercise strided views
-    xbuf = _rand_act(g, B, T, H, W, cin + 8).to(DEV)
+    xbuf = _rand_act(g, B, T, H, W, cin + 8, dtype=adt).to(DEV)
     x = xbuf[..., 8:8 + cin]
     w = torch.randn(cout, cin, *k, generator=g) * (2.0 / (cin * k[0] * k[1] * k[2])) ** 0.5
     bias = torch.randn(cout, generator=g) * 0.1
-    ref = F.conv3d(_to_ncdhw(x.cpu()), w.bfloat16().float(), bias, s, p, d)
+    ref = F.conv3d(_to_ncdhw(x.cpu()), w.to(adt).float(), bias, s, p, d)
     _, _, To, Ho, Wo = ref.shape
     res = None
     if use_res:
-        res = _rand_act(g, B, To, Ho, Wo, cout).to(DEV)
+        res = _rand_act(g, B, To, Ho, Wo, cout, dtype=adt).to(DEV)
         ref = ref + _to_ncdhw(res.cpu())
     if act == 1:
         ref = ref.relu()
-    plan = Plan(DEV)
-    odt = torch.float32 if out_f32 else torch.bfloat16
+    plan = Plan(DEV, precision)
+    odt = torch.float32 if out_f32 else adt
     ybuf = torch.full((B, To, Ho, Wo, cout + 16), 7.0, dtype=odt, device=DEV)
     y = ybuf[..., 8:8 + cout] if not out_f32 else ybuf[..., 4:4 + cout]
-    plan.conv_igemm(x, y, w.double(), bias.double(), stride=s, padding=p, dilation=d, act=act, res=res,
-                    out_dtype=rt.F32 if out_f32 else rt.BF16)
+    plan.conv_igemm(x, y, w.double(), bias.double(), stride=s, padding=p, dilation=d, act=act, res=res)
     plan.launch_all()
     torch.cuda.synchronize()
     got = _to_ncdhw(y.cpu())
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
-    tol = 2e-3 if out_f32 else 1e-2   # FP32 out: accumulation order only; BF16 out: + 2^-9 output rounding
+    # FP32 out: accumulation order only; 16-bit out: + 2^-9 (BF16) / 2^-12 (FP16) output rounding
+    tol = 2e-3 if (out_f32 or precision == "fp16") else 1e-2
     if not err <= tol * scale:
         _diagnose(name, got, ref, tol * scale)
     assert err <= tol * scale, "%s: max err %.4g vs scale %.4g" % (name, err, scale)
@@ -143,9 +145,11 @@ def test_stem_conv(esf_lib, kt, cout):
     assert err <= 6e-3 * ref.abs().max().item()   # FP32 math, BF16 output rounding (2^-8 relative worst case)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
 @pytest.mark.parametrize("kt,cout,k,size", [(1, 64, 7, 64), (5, 8, 7, 64), (3, 24, 3, 48), (1, 64, 7, 224)])
-def test_stem_banded_gemm(esf_lib, kt, cout, k, size):
-    """Tensor-core stem (banded implicit GEMM) vs F.conv3d on the BF16-rounded clip and weights."""
+def test_stem_banded_gemm(esf_lib, kt, cout, k, size, precision):
+    """Tensor-core stem (banded implicit GEMM) vs F.conv3d on the 16-bit-rounded clip and weights."""
+    adt = rt.TORCH_DTYPE[precision]
     g = torch.Generator().manual_seed(kt + cout)
     B, T = (2, 8) if size < 200 else (1, 2)
     x = torch.randn(B, 3, T, size, size, generator=g)
@@ -153,9 +157,9 @@ def test_stem_banded_gemm(esf_lib, kt, cout, k, size):
     w = torch.randn(cout, 3, *kk, generator=g) * 0.1
     bias = torch.randn(cout, generator=g) * 0.1
     pad = (kt // 2, k // 2, k // 2)
-    ref = F.conv3d(x.bfloat16().float(), w.bfloat16().float(), bias, (1, 2, 2), pad).relu()
-    y = torch.full(_to_ndhwc(ref).shape, 7.0, dtype=torch.bfloat16, device=DEV)
-    plan = Plan(DEV)
+    ref = F.conv3d(x.to(adt).float(), w.to(adt).float(), bias, (1, 2, 2), pad).relu()
+    y = torch.full(_to_ndhwc(ref).shape, 7.0, dtype=adt, device=DEV)
+    plan = Plan(DEV, precision)
     xd = x.to(DEV)
     plan.stem(xd, y, w.double(), bias.double(), (1, 2, 2), pad)
     assert plan.meta[-1]["kind"] == "stem_igemm"
@@ -263,8 +267,10 @@ def test_attention_fused(esf_lib, d, T, H, W, qk_scale):
                                               (32, 4, 16, 8, 2.0), (64, 2, 7, 7, 1.0), (128, 2, 7, 7, 0.5),
                                               (16, 1, 9, 9, 1.0), (3, 2, 8, 8, 1.0), (12, 1, 20, 20, 1.0),
                                               (24, 2, 14, 14, 1.0), (32, 8, 14, 14, 1.0)])
-def test_attention_tcgen05(esf_lib, d, T, H, W, qk_scale):
-    """tcgen05/TMEM two-pass attention vs FP64 softmax attention on the same FP32 projections."""
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_attention_tcgen05(esf_lib, d, T, H, W, qk_scale, precision):
+    """tcgen05/TMEM fused attention vs FP64 softmax attention on the same FP32 projections."""
+    adt = rt.TORCH_DTYPE[precision]
     g = torch.Generator().manual_seed(d + T)
     B, alpha = 2, 4
     N = T * H * W
@@ -280,12 +286,12 @@ def test_attention_tcgen05(esf_lib, d, T, H, W, qk_scale):
     packed = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
     pj = proj.to(DEV)
     cpad = (2 * d + 7) // 8 * 8
-    ybuf = torch.zeros(B, T * alpha, H, W, cpad, dtype=torch.bfloat16, device=DEV)
+    ybuf = torch.zeros(B, T * alpha, H, W, cpad, dtype=adt, device=DEV)
     yv = rt.view(ybuf[..., :d])
     sc, sh = scale.to(DEV), shift.to(DEV)
     s = rt.current_stream_ptr()
     h = ctypes.c_void_p()
-    rt.check(L.esf_attn_tc_pack(pj.data_ptr(), B, N, d, packed.data_ptr(), s))
+    rt.check(L.esf_attn_tc_pack(pj.data_ptr(), B, N, d, rt.dtype_code(adt), packed.data_ptr(), s))
     rt.check(L.esf_attn_tc_create(packed.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(), sh.data_ptr(), alpha,
                                   ctypes.byref(yv), ctypes.byref(h)))
     rt.check(L.esf_op_launch(h, s))
@@ -293,8 +299,9 @@ def test_attention_tcgen05(esf_lib, d, T, H, W, qk_scale):
     L.esf_op_destroy(h)
     got = ybuf[..., :d].cpu().double()
     err = (got - ref).abs().max().item()
-    print("attn_tc d=%d N=%d rel err %.3e" % (d, N, err / ref.abs().max().item()))
-    assert err <= 1.5e-2 * ref.abs().max().item(), "d=%d err %.4g scale %.4g" % (d, err, ref.abs().max().item())
+    print("attn_tc %s d=%d N=%d rel err %.3e" % (precision, d, N, err / ref.abs().max().item()))
+    tol = 1.5e-2 if precision == "bf16" else 3e-3   # P, V and the output are rounded to the storage format
+    assert err <= tol * ref.abs().max().item(), "d=%d err %.4g scale %.4g" % (d, err, ref.abs().max().item())
     assert (ybuf[..., d:] == 0).all()
 
 

@@ -29,7 +29,7 @@ sh = torch.zeros(d, device=DEV)
 s = rt.current_stream_ptr()
 if impl == "tc":
     packed = torch.empty(L.esf_attn_tc_pack_bytes(B, N, d), dtype=torch.uint8, device=DEV)
-    rt.check(L.esf_attn_tc_pack(proj.data_ptr(), B, N, d, packed.data_ptr(), s))
+    rt.check(L.esf_attn_tc_pack(proj.data_ptr(), B, N, d, rt.BF16, packed.data_ptr(), s))
     h = ctypes.c_void_p()
     rt.check(L.esf_attn_tc_create(packed.data_ptr(), B, T, HW, HW, d, 0.5, sc.data_ptr(), sh.data_ptr(), alpha,
                                   ctypes.byref(yv), ctypes.byref(h)))
