@@ -92,6 +92,7 @@ def bench_cfg(args):
     cfg = esf.slowfast_dual_8x8_r50_cfg() if args.model == "SlowFastDualAttention" else esf.slowfast_4x16_r50_cfg()
     cfg.DATA.CROP_SIZE = args.crop
     cfg.DATA.NUM_FRAMES = args.frames
+    cfg.ESF.PRECISION = args.precision
     return cfg
 
 
@@ -342,6 +343,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-ops", default="", help="write per-op device times (JSON lines) to this file")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
+                    help="16-bit storage / tensor-core operand format (FP32 accumulation in both)")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for ncu: eager launches (no CUDA graph), 1 warm-up + --steps steps, nothing else")
     args = ap.parse_args()

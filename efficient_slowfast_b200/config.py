@@ -77,7 +77,7 @@ def get_cfg():
     c.NUM_GPUS = 1
     # extension (not in the reference): 16-bit storage / tensor-core operand format of the CUDA path, "bf16" or "fp16"
     # (FP32 accumulation, softmax statistics and head in both; fp16 has 3 more mantissa bits and saturates at 65504)
-    c.ESF = CfgNode(dict(PRECISION="bf16", CUDA_GRAPH=True))
+    c.ESF = CfgNode(dict(PRECISION="fp16", CUDA_GRAPH=True))
     return c
 
 

