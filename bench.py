@@ -190,12 +190,13 @@ def run_gpu(args):
     ins[1].normal_(generator=g)
     ins[0].copy_(recipe.pack_pathway_output(ins[1], alpha)[0])
     K = cfg.MODEL.NUM_CLASSES
-    gathered = torch.empty(world * B, K, dtype=torch.float32, device=dev) if world > 1 else None
+
+    from efficient_slowfast_b200 import distributed as esf_dist
 
     def step():
         out = model(ins)                            # graph replay; no staging copy (inputs are the static buffers)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)   # the only collective on the path (tools/test_net.py:95-98)
+            return esf_dist.all_gather([out])[0]    # the only collective on the path (tools/test_net.py:95-98)
         return out
 
     def barrier():
@@ -245,7 +246,7 @@ def run_gpu(args):
             d.copy_(h, non_blocking=True)
         out = model(ins)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+            esf_dist.all_gather([out])
         host_out.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 

@@ -263,9 +263,10 @@ __device__ __forceinline__ float h162f(__nv_bfloat16 b, int f16) {
   return __bfloat162float(b);
 }
 __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int f16) {
-  if (f16) {
-    __half2 v = __floats2half2_rn(sat_h(lo), sat_h(hi));
-    return *reinterpret_cast<uint32_t*>(&v);
+  if (f16) {  // one F2FP.SATFINITE: round to nearest, saturate at the largest finite half
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
   }
   return pack_bf16x2(lo, hi);
 }
