@@ -346,17 +346,305 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
   }
 }
 
+// ================================================================================================ v2 (d <= 32)
+// Same algorithm with 16 softmax warps (4 per scheduler instead of 2 -- the v1 profile is latency bound: XU pipe 53 %,
+// issue slots 39 %): every query row is handled by TWO threads, one per 32-key half of each 64-key tile.  The two
+// halves are independent split-K streams with their own running maximum and their own TMEM accumulator O[q][h]; the
+// row sums come out of the P.V MMA itself (V^T has a row of ones), so the hot loop is FFMA + MUFU.EX2 + 1/2 F2FP +
+// 1/2 FMNMX3 per element.  The epilogue merges the halves: O = (O0 f0 + O1 f1) / (l0 f0 + l1 f1), f_h = exp(m_h - M).
+constexpr int kV2Threads = 608;  // 16 softmax warps + TMA producer + 2 MMA issuers
+
+__global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_constant__ AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;
+  uint8_t* Ks = Qs + 2 * p.q_tile_bytes;
+  uint8_t* Vs = Ks + p.stages * p.k_tile_bytes;
+  uint8_t* Ps = Vs + p.stages * p.v_tile_bytes;          // 2 x 16 KB
+  float* mx_sh = reinterpret_cast<float*>(Ps + 2 * 16384);  // [q][h][128] running maxima for the final merge
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mx_sh + 2 * 2 * 128);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = q_full + 1;
+  uint64_t* kv_empty = kv_full + kTcMaxStages;
+  uint64_t* s_full = kv_empty + kTcMaxStages;  // [q][buf]
+  uint64_t* s_free = s_full + 4;
+  uint64_t* p_full = s_free + 4;               // [q][h]
+  uint64_t* p_free = p_full + 4;
+  uint64_t* o_full = p_free + 4;               // [q]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int row0 = blockIdx.x * 256;
+  const int N = p.N;
+  const int nt = (N + kTcBN - 1) / kTcBN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 2);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 8);   // 8 softmax warps read every S tile
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_free[i], 1);
+    }
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 16 && lane == 0) {
+    prefetch_tmap(&p.q_map);
+    prefetch_tmap(&p.k_map);
+    prefetch_tmap(&p.v_map);
+  }
+  if (warp == 17) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 16) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, 2 * p.q_tile_bytes);
+      for (int q = 0; q < 2; ++q) tma_load_3d(Qs + q * p.q_tile_bytes, &p.q_map, q_full, 0, row0 + q * 128, b);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&kv_empty[stage], phase ^ 1, 31);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[stage], p.k_tile_bytes + p.v_tile_bytes);
+        tma_load_3d(Ks + stage * p.k_tile_bytes, &p.k_map, &kv_full[stage], 0, j * kTcBN, b);
+        tma_load_3d(Vs + stage * p.v_tile_bytes, &p.v_map, &kv_full[stage], j * kTcBN, 0, b);
+      }
+      __syncwarp();
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 17 || warp == 18) {
+    // ------------------------------------------------------------------ MMA issuers (one per query tile)
+    const int q = warp - 17;
+    const uint32_t idesc_s = make_idesc_16(128, kTcBN, p.f16);
+    const uint32_t idesc_o = make_idesc_16(128, p.DVp, p.f16);
+    const uint32_t qk_hi = kmajor_desc_hi(p.sbo, p.layout_type);
+    const uint32_t pv_hi = kmajor_desc_hi(1024, 2);
+    const uint32_t q_lo = kmajor_desc_lo(smem_u32(Qs) + q * p.q_tile_bytes);
+    const uint32_t k_lo = kmajor_desc_lo(smem_u32(Ks));
+    const uint32_t v_lo = kmajor_desc_lo(smem_u32(Vs));
+    const uint32_t p_lo = kmajor_desc_lo(smem_u32(Ps) + q * 16384);
+    const uint32_t k_stage_step = p.k_tile_bytes >> 4, v_stage_step = p.v_tile_bytes >> 4;
+    auto issue_s = [&](int c, int stage) {
+      const int buf = c & 1;
+      mbar_wait(&s_free[q * 2 + buf], ((c >> 1) & 1) ^ 1, 32);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + (q * 2 + buf) * kTcBN;
+        const uint32_t kb = k_lo + stage * k_stage_step;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+          if (i < p.nsteps2)
+            umma_bf16_lohi(d_tmem, q_lo + (p.steps2[i] & 0xffff), qk_hi, kb + (p.steps2[i] >> 16), qk_hi, idesc_s, i != 0);
+        umma_commit(&s_full[q * 2 + buf]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0, 33);
+    tc_fence_after();
+    int s_stage = 0;
+    uint32_t s_phase = 0;
+    mbar_wait(&kv_full[s_stage], s_phase, 34);
+    tc_fence_after();
+    issue_s(0, s_stage);
+    for (int j = 0; j < nt; ++j) {
+      const int pv_stage = s_stage;
+      if (++s_stage == p.stages) {
+        s_stage = 0;
+        s_phase ^= 1;
+      }
+      if (j + 1 < nt) {
+        mbar_wait(&kv_full[s_stage], s_phase, 35);
+        tc_fence_after();
+        issue_s(j + 1, s_stage);
+      }
+      const uint32_t vl = v_lo + pv_stage * v_stage_step;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(&p_full[q * 2 + h], j & 1, 36);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t o_tmem = tmem_base + 4 * kTcBN + (q * 2 + h) * p.DVp;
+          umma_bf16_lohi(o_tmem, p_lo + 4 * h, pv_hi, vl + 4 * h, pv_hi, idesc_o, j != 0);      // keys 32h .. 32h+15
+          umma_bf16_lohi(o_tmem, p_lo + 4 * h + 2, pv_hi, vl + 4 * h + 2, pv_hi, idesc_o, 1);  // keys 32h+16 .. 32h+31
+          umma_commit(&p_free[q * 2 + h]);
+          if (h == 1) {
+            umma_commit(&kv_empty[pv_stage]);
+            if (j == nt - 1) umma_commit(&o_full[q]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax: warp = q * 8 + h * 4 + quarter
+    const int q = warp >> 3;
+    const int h = (warp >> 2) & 1;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int n = row0 + q * 128 + r;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t o_addr = lane_addr + 4 * kTcBN + (q * 2 + h) * p.DVp;
+    const bool tail = (N % kTcBN) != 0;
+    float m = -CUDART_INF_F;
+    uint8_t* prow = Ps + q * 16384;
+    constexpr float kTau = 5.545177f;
+    for (int j = 0; j < nt; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&s_full[q * 2 + buf], (j >> 1) & 1, 37);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(lane_addr + (q * 2 + buf) * kTcBN + 32 * h, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[q * 2 + buf]);
+      if (tail && j == nt - 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (j * kTcBN + 32 * h + i >= N) v[i] = -CUDART_INF_F;
+      }
+      float mx0 = v[0], mx1 = v[1];
+#pragma unroll
+      for (int i = 2; i < 32; i += 2) {
+        mx0 = fmaxf(mx0, v[i]);
+        mx1 = fmaxf(mx1, v[i + 1]);
+      }
+      const float mx = fmaxf(mx0, mx1);
+      // raise lazily; a half tile that is entirely masked (tail) must not raise from -inf to -inf
+      const bool raise = mx > m + kTau;
+      const float m_new = raise ? mx : m;
+      const float f = raise ? fast_exp2((m - m_new) * kTcLog2e) : 1.f;
+      m = m_new;
+      const float ms = (m == -CUDART_INF_F) ? 0.f : m * kTcLog2e;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fast_exp2(fmaf(v[i], kTcLog2e, -ms));
+      mbar_wait(&p_free[q * 2 + h], (j & 1) ^ 1, 38);
+      if (j > 0 && __any_sync(0xffffffffu, raise)) {
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.DVp; c0 += 16) {
+          float o[16];
+          tmem_ld16(o_addr + c0, o);
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) o[jj] *= f;
+          tmem_st16(o_addr + c0, o);
+        }
+        tmem_wait_st();
+      }
+#pragma unroll
+      for (int ck = 0; ck < 4; ++ck) {
+        uint4 o;
+        o.x = pack16x2(v[8 * ck + 0], v[8 * ck + 1], p.f16);
+        o.y = pack16x2(v[8 * ck + 2], v[8 * ck + 3], p.f16);
+        o.z = pack16x2(v[8 * ck + 4], v[8 * ck + 5], p.f16);
+        o.w = pack16x2(v[8 * ck + 6], v[8 * ck + 7], p.f16);
+        *reinterpret_cast<uint4*>(prow + swz(r * 128 + (4 * h + ck) * 16, 7)) = o;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[q * 2 + h]);
+    }
+    // ---- merge the two halves of every row and write the output
+    mx_sh[(q * 2 + h) * 128 + r] = m;
+    asm volatile("bar.sync %0, 256;" ::"r"(q + 1) : "memory");   // the 8 warps of this query tile
+    const float m0 = mx_sh[(q * 2 + 0) * 128 + r], m1 = mx_sh[(q * 2 + 1) * 128 + r];
+    const float M = fmaxf(m0, m1);
+    const float f0 = (m0 == -CUDART_INF_F) ? 0.f : fast_exp2((m0 - M) * kTcLog2e);
+    const float f1 = (m1 == -CUDART_INF_F) ? 0.f : fast_exp2((m1 - M) * kTcLog2e);
+    mbar_wait(&o_full[q], 0, 39);
+    tc_fence_after();
+    const uint32_t o0 = lane_addr + 4 * kTcBN + (q * 2 + 0) * p.DVp, o1 = o0 + p.DVp;
+    // row sum l = column d of both accumulators
+    float t0[8], t1[8];
+    const int lc = p.d & ~7;
+    tmem_ld8(o0 + lc, t0);
+    tmem_ld8(o1 + lc, t1);
+    float l = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+      if (lc + jj == p.d) l = t0[jj] * f0 + t1[jj] * f1;
+    const float inv = 1.f / l;
+    const int HW = p.H * p.W;
+    const bool valid = n < N;
+    const int t = valid ? n / HW : 0, hw = valid ? n % HW : 0, hh = hw / p.W, ww = hw % p.W;
+    __nv_bfloat16* yb = p.y + b * p.ysB + hh * p.ysH + ww * p.ysW;
+    const float* xr = p.x + ((long long)b * N + (valid ? n : 0)) * p.d;
+    const bool vec_ok = (p.d % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) && (p.ysW % 8 == 0) &&
+                        (p.ysH % 8 == 0) && (p.ysT % 8 == 0) && (p.ysB % 8 == 0);
+    // half h of the row's thread pair writes the channel chunks c0 = 8 * (2 * i + h)
+    for (int c0 = 8 * h; c0 < p.d; c0 += 16) {
+      tmem_ld8(o0 + c0, t0);
+      tmem_ld8(o1 + c0, t1);
+      if (!valid) continue;
+      float o[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int ch = c0 + jj;
+        o[jj] = 0.f;
+        if (ch < p.d) {
+          const float a = fmaf(p.gamma, (t0[jj] * f0 + t1[jj] * f1) * inv, xr[ch]);
+          o[jj] = fmaxf(fmaf(a, __ldg(p.bn_scale + ch), __ldg(p.bn_shift + ch)), 0.f);
+        }
+      }
+      for (int rep = 0; rep < p.alpha; ++rep) {
+        __nv_bfloat16* yp = yb + (long long)(t * p.alpha + rep) * p.ysT + c0;
+        if (vec_ok) {
+          uint4 pk;
+          pk.x = pack16x2(o[0], o[1], p.f16);
+          pk.y = pack16x2(o[2], o[3], p.f16);
+          pk.z = pack16x2(o[4], o[5], p.f16);
+          pk.w = pack16x2(o[6], o[7], p.f16);
+          *reinterpret_cast<uint4*>(yp) = pk;
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            if (c0 + jj < p.d) yp[jj] = f2h16(o[jj], p.f16);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ packing
 struct TcGeom {
   int DVp, KQ, chunk_el, nchunks, mode;  // mode 0: d <= 8 (4 x 8 segments), 1: hi|lo halves, 2: unsplit
+  int v2;                                // d <= 32: half-row kernel; V^T carries a row of ones at index d (row sums)
 };
 static bool tc_geom(int d, TcGeom* g) {
   if (d <= 0 || d > 128) return false;
-  if (d <= 8) *g = {16, 32, 32, 1, 0};
-  else if (d <= 16) *g = {16, 32, 32, 1, 1};
-  else if (d <= 32) *g = {32, 64, 64, 1, 1};
-  else if (d <= 64) *g = {64, 128, 64, 2, 1};
-  else *g = {128, 128, 64, 2, 2};
+  const int dv2 = d < 16 ? 16 : (d < 32 ? 32 : 48);   // room for the ones row
+  if (d <= 8) *g = {dv2, 32, 32, 1, 0, 1};
+  else if (d <= 16) *g = {dv2, 32, 32, 1, 1, 1};
+  else if (d <= 32) *g = {dv2, 64, 64, 1, 1, 1};
+  else if (d <= 64) *g = {64, 128, 64, 2, 1, 0};
+  else *g = {128, 128, 64, 2, 2, 0};
   return true;
 }
 struct TcLayout {
@@ -384,7 +672,7 @@ __device__ __forceinline__ __nv_bfloat16 h_lo(float v, int f16) { return f2h16(v
 // (coalesced loads) and writes Q~/K~ rows, x_d rows and the TRANSPOSED value tile V^T[j][n0..n0+R) from there, so every
 // global access is coalesced.
 __global__ void __launch_bounds__(256) attn_tc_pack_kernel(const float* __restrict__ proj, int N, int Npad, int d,
-                                                           int KQ, int DVp, int mode, int R, int f16,
+                                                           int KQ, int DVp, int mode, int R, int f16, int ones_row,
                                                            __nv_bfloat16* __restrict__ Q, __nv_bfloat16* __restrict__ K,
                                                            __nv_bfloat16* __restrict__ VT, float* __restrict__ X) {
   extern __shared__ float tile[];  // [R][4d + 1]
@@ -431,7 +719,8 @@ __global__ void __launch_bounds__(256) attn_tc_pack_kernel(const float* __restri
   for (int i = threadIdx.x; i < DVp * R; i += blockDim.x) {
     const int j = i / R, r = i % R;
     if (n0 + r < Npad) {
-      const float v = (j < d && r < rows) ? tile[r * pitch + 3 * d + j] : 0.f;
+      float v = (j < d && r < rows) ? tile[r * pitch + 3 * d + j] : 0.f;
+      if (ones_row && j == d && r < rows) v = 1.f;   // sum_j p_ij comes out of the P.V MMA as column d of O
       VT[((long long)b * DVp + j) * Npad + n0 + r] = f2h16(v, f16);
     }
   }
@@ -441,7 +730,12 @@ struct AttnTcOp : esf_op {
   AttnTcParams params;
   dim3 grid;
   int smem_bytes = 0;
+  int v2 = 0;
   int launch(cudaStream_t stream) override {
+    if (v2) {
+      attn_tc_v2_kernel<<<grid, kV2Threads, smem_bytes, stream>>>(params);
+      return check_launch("attn_tc_v2_kernel");
+    }
     attn_tc_kernel<<<grid, kTcThreads, smem_bytes, stream>>>(params);
     return check_launch("attn_tc_kernel");
   }
@@ -484,7 +778,7 @@ extern "C" int esf_attn_tc_pack(const float* proj, int32_t B, int32_t N, int32_t
   while (R > 8 && (size_t)R * (4 * d + 1) * sizeof(float) > 40 * 1024) R >>= 1;
   const size_t smem = (size_t)R * (4 * d + 1) * sizeof(float);
   dim3 grid(cdiv(L.Npad, R), B);
-  attn_tc_pack_kernel<<<grid, 256, smem, s>>>(proj, N, L.Npad, d, g.KQ, g.DVp, g.mode, R, dtype == ESF_F16,
+  attn_tc_pack_kernel<<<grid, 256, smem, s>>>(proj, N, L.Npad, d, g.KQ, g.DVp, g.mode, R, dtype == ESF_F16, g.v2,
                                               reinterpret_cast<__nv_bfloat16*>(base + L.q_off),
                                               reinterpret_cast<__nv_bfloat16*>(base + L.k_off),
                                               reinterpret_cast<__nv_bfloat16*>(base + L.v_off),
@@ -565,7 +859,8 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
   p.q_tile_bytes = 128 * g.KQ * 2;
   p.k_tile_bytes = kTcBN * g.KQ * 2;
   p.v_tile_bytes = g.DVp * 128;
-  const int fixed = 1024 + 2 * (int)p.q_tile_bytes + 2 * 16384 + 512;
+  op->v2 = g.v2;
+  const int fixed = 1024 + 2 * (int)p.q_tile_bytes + 2 * 16384 + 512 + (g.v2 ? 2048 : 0);
   int stages = (kTcSmemLimit - fixed) / (int)(p.k_tile_bytes + p.v_tile_bytes);
   p.stages = std::max(2, std::min(stages, kTcMaxStages));
   op->smem_bytes = fixed + p.stages * (int)(p.k_tile_bytes + p.v_tile_bytes);
@@ -583,6 +878,8 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
       if (e != cudaSuccess) rc = set_error(ESF_ERR_CUDA, "cudaFuncSetAttribute(attn_tc) failed: %s", cudaGetErrorString(e));
       else attr_set = true;
     }
