@@ -33,6 +33,7 @@ constexpr int kMaxAMaps = 8;
 constexpr int kMaxTaps = 64;
 constexpr int kAStageBytes = 16384;   // 128 rows x 128 B
 constexpr int kOutStageBytes = 16384; // 128 rows x 128 B
+constexpr int kMaxOutBufs = 8;
 constexpr int kTmemCols = 512;
 constexpr int kSmemLimit = 232448;    // 227 KB
 
@@ -59,6 +60,10 @@ struct __align__(64) IgemmParams {
   // "column blocks" (banded stem GEMM): an extra tile index that shifts the innermost coordinate of the
   // activation loads and of the output stores; ncb == 1 and zero strides for ordinary convolutions
   int ncb, a_cb_stride, out_cb_w;  // out_cb_w: W-coordinate step of the output store per column block
+  int obufs;                       // depth of the output/residual staging ring (2..kMaxOutBufs)
+  // W-folded GEMMs (thin-channel layers): innermost start coordinate of the activation loads, and -- when the output
+  // (residual) is a channel slice -- the (w, c) decomposition of an output column n = w_in_block * cout + c
+  int a_c_base, fold_wb, out_fold_cout, res_fold_cout;
 };
 
 struct TileCoord {
@@ -137,12 +142,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + p.stages * kAStageBytes;
   uint8_t* smem_out = smem_b + p.stages * p.b_stride;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_out + 2 * kOutStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_out + p.obufs * kOutStageBytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_full = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + kMaxOutBufs);
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -155,8 +160,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 8);  // one arrival per epilogue warp
-      mbar_init(&res_full[a], 1);
     }
+    for (int a = 0; a < p.obufs; ++a) mbar_init(&res_full[a], 1);
     fence_barrier_init();
   }
   if (warp == kProducerWarp && lane == 0) {
@@ -188,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             if (elect_one()) {
               mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
               tma_load_5d(smem_a + stage * kAStageBytes, &p.a_maps[tp.x], &full_bar[stage],
-                          tc.cb * p.a_cb_stride + ch * p.kc, tc.w0 + tp.y, tc.h0 + tp.z, tc.t0 + tp.w, tc.b0);
+                            p.a_c_base + tc.cb * p.a_cb_stride + ch * p.kc, tc.w0 + tp.y, tc.h0 + tp.z, tc.t0 + tp.w, tc.b0);
               tma_load_2d(smem_b + stage * p.b_stride, &p.b_map, &full_bar[stage], (tap * p.kchunks + ch) * p.kc,
                           tc.n_idx * p.n_tile);
             }
@@ -258,13 +263,25 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const bool leader = threadIdx.x == 0;
     const int slabs = p.n_tile / p.slab_cols;
     const int cpt = p.slab_cols >> 1;  // columns per thread per slab
-    int g = 0;                         // running slab counter (staging buffer = g & 1)
-    if (p.has_res && leader && blockIdx.x < p.num_tiles) {
-      const TileCoord tc = tile_coord(p, blockIdx.x);
-      mbar_arrive_expect_tx(&res_full[0], p.res_bytes);
-      tma_load_5d(smem_out, &p.res_map, &res_full[0], tc.n_idx * p.n_tile, tc.w0 + tc.cb * p.out_cb_w, tc.h0, tc.t0,
-                  tc.b0);
-    }
+    int g = 0;                         // running slab counter of this CTA (staging buffer = g % obufs)
+    const int R = p.obufs;
+    // residual tile of this CTA's k-th slab -> staging buffer k % R; issued R - 1 slabs ahead of its consumer so the
+    // DRAM latency of the (HBM-bound) residual stream is off the epilogue's critical path
+    auto prefetch_res = [&](int k) {
+      const int ktile = blockIdx.x + (k / slabs) * gridDim.x;
+      if (ktile >= p.num_tiles) return;
+      const TileCoord kc = tile_coord(p, ktile);
+      const int kb = k % R;
+      int c = kc.n_idx * p.n_tile + (k % slabs) * p.slab_cols, w = kc.w0 + kc.cb * p.out_cb_w;
+      if (p.res_fold_cout) {
+        w = kc.cb * p.fold_wb + c / p.res_fold_cout;
+        c = c % p.res_fold_cout;
+      }
+      mbar_arrive_expect_tx(&res_full[kb], p.res_bytes);
+      tma_load_5d(smem_out + kb * kOutStageBytes, &p.res_map, &res_full[kb], c, w, kc.h0, kc.t0, kc.b0);
+    };
+    if (p.has_res && leader)
+      for (int k = 0; k < R - 1; ++k) prefetch_res(k);
     int iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
       const TileCoord tc = tile_coord(p, tile);
@@ -273,9 +290,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       mbar_wait(&tmem_full[acc], acc_phase, 4);
       tc_fence_after();
       for (int s = 0; s < slabs; ++s, ++g) {
-        const int buf = g & 1;
+        const int buf = g % R;
         uint8_t* stage_buf = smem_out + buf * kOutStageBytes;
-        if (p.has_res) mbar_wait(&res_full[buf], (g >> 1) & 1, 5);
+        if (p.has_res) mbar_wait(&res_full[buf], (g / R) & 1, 5);
         const int col = s * p.slab_cols + half * cpt;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_tile + col;
         const float* bias = p.bias + tc.n_idx * p.n_tile + col;
@@ -290,24 +307,15 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         fence_proxy_async_smem();
         epi_bar_sync(1);
         if (leader) {
-          tma_store_5d(&p.out_map, stage_buf, tc.n_idx * p.n_tile + s * p.slab_cols, tc.w0 + tc.cb * p.out_cb_w,
-                       tc.h0, tc.t0, tc.b0);
-          tma_store_commit();
-          tma_store_wait_read<1>();  // the previous slab's store no longer reads the other staging buffer
-          if (p.has_res) {
-            int ntile = tile, ns = s + 1;
-            if (ns == slabs) {
-              ns = 0;
-              ntile = tile + gridDim.x;
-            }
-            if (ntile < p.num_tiles) {
-              const TileCoord nc = tile_coord(p, ntile);
-              mbar_arrive_expect_tx(&res_full[buf ^ 1], p.res_bytes);
-              tma_load_5d(smem_out + (buf ^ 1) * kOutStageBytes, &p.res_map, &res_full[buf ^ 1],
-                          nc.n_idx * p.n_tile + ns * p.slab_cols, nc.w0 + nc.cb * p.out_cb_w, nc.h0, nc.t0,
-                          nc.b0);
-            }
+          int c = tc.n_idx * p.n_tile + s * p.slab_cols, w = tc.w0 + tc.cb * p.out_cb_w;
+          if (p.out_fold_cout) {
+            w = tc.cb * p.fold_wb + c / p.out_fold_cout;
+            c = c % p.out_fold_cout;
           }
+          tma_store_5d(&p.out_map, stage_buf, c, w, tc.h0, tc.t0, tc.b0);
+          tma_store_commit();
+          tma_store_wait_read<1>();  // every store before this one has finished reading its staging buffer
+          if (p.has_res) prefetch_res(g + R - 1);  // into the buffer that slab g - 1 just released
         }
         epi_bar_sync(2);
       }
@@ -512,7 +520,8 @@ extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
   p.res_bytes = p.rows * p.slab_cols * 2;
 
   // stages: as deep as shared memory allows
-  const int fixed = 1024 + 2 * kOutStageBytes + 512;
+  p.obufs = p.has_res ? (n_tile >= 256 ? 4 : 6) : 2;
+  const int fixed = 1024 + p.obufs * kOutStageBytes + 512;
   int stages = (kSmemLimit - fixed) / (kAStageBytes + (int)p.b_stride);
   stages = std::max(2, std::min(stages, kMaxStages));
   p.stages = stages;
@@ -678,7 +687,8 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
   const int out_row_bytes = p.slab_cols * 2;
   p.out_swz = out_row_bytes == 128 ? 7 : (out_row_bytes == 64 ? 3 : 1);
   p.res_bytes = 0;
-  const int fixed = 1024 + 2 * kOutStageBytes + 512;
+  p.obufs = 2;
+  const int fixed = 1024 + p.obufs * kOutStageBytes + 512;
   int stages = (kSmemLimit - fixed) / (kAStageBytes + (int)p.b_stride);
   p.stages = std::max(2, std::min(stages, kMaxStages));
   op->smem_bytes = fixed + p.stages * (kAStageBytes + (int)p.b_stride);
@@ -736,6 +746,154 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
     p.res_map = p.out_map;
     rc = finish_op(op);
   }
+  if (rc != ESF_OK) {
+    delete op;
+    return rc;
+  }
+  *out = op;
+  return ESF_OK;
+}
+
+// ---- W-folded dense conv for thin layers (C_in <= 32) ------------------------------------------------------------
+// A (B,T,H,W,C) activation with C = 8..32 gives TMA rows of 16..64 bytes and MMA tiles of N = 8..32: both far below
+// what the hardware wants.  Folding a block of WB output columns into the GEMM's N and the ((WB-1)*sW + kW) input
+// columns it reads into the GEMM's K (the same banded / block-diagonal weight trick as the stem) turns every tap into
+// 128-byte rows and N into WB * Cout (up to 256).  The extra MACs hit structural zeros; these layers are HBM bound.
+extern "C" int esf_conv_wfold_create(const esf_conv_desc* d, int32_t WB, esf_op** out) {
+  ESF_CHECK_ARG(d && out && WB >= 1, "esf_conv_wfold_create: null/bad argument");
+  ESF_CHECK_ARG(view_ok(&d->x) && view_ok(&d->y) && d->w && d->bias, "esf_conv_wfold_create: bad views/weights");
+  const esf_view& x = d->x;
+  const esf_view& y = d->y;
+  ESF_CHECK_ARG(d->groups == 1 && d->sT == 1 && d->dT == 1 && d->dH == 1 && d->dW == 1,
+                "esf_conv_wfold_create: needs groups 1, temporal stride 1, no dilation");
+  ESF_CHECK_ARG(is16(x.dtype) && y.dtype == x.dtype && d->out_dtype == x.dtype,
+                "esf_conv_wfold_create: 16-bit input and output of the same format");
+  ESF_CHECK_ARG(x.sW == x.C && x.C % 8 == 0, "esf_conv_wfold_create: input must be dense in (W,C) with C %% 8 == 0");
+  const int To = x.T + 2 * d->pT - d->kT + 1;
+  const int Ho = (x.H + 2 * d->pH - d->kH) / d->sH + 1;
+  const int Wo = (x.W + 2 * d->pW - d->kW) / d->sW + 1;
+  ESF_CHECK_ARG(y.B == x.B && y.T == To && y.H == Ho && y.W == Wo, "esf_conv_wfold_create: output shape mismatch");
+  ESF_CHECK_ARG(Wo % WB == 0, "esf_conv_wfold_create: Wo %% WB != 0");
+  const int C = x.C, Cout = y.C;
+  const int win = ((WB - 1) * d->sW + d->kW) * C;
+  ESF_CHECK_ARG(win <= 128, "esf_conv_wfold_create: window of %d elements > 128", win);
+  const int kchunks = cdiv(win, 64);
+  const int N = WB * Cout;
+  ESF_CHECK_ARG(N <= 256, "esf_conv_wfold_create: WB * Cout = %d > 256", N);
+  const int num_taps = d->kT * d->kH;
+  ESF_CHECK_ARG(num_taps <= kMaxTaps, "esf_conv_wfold_create: too many taps");
+  const bool y_dense = y.sW == y.C;
+  const bool has_res = d->res.ptr != nullptr;
+  const bool r_dense = has_res && d->res.sW == d->res.C;
+  if (has_res)
+    ESF_CHECK_ARG(d->res.dtype == x.dtype && d->res.B == y.B && d->res.T == y.T && d->res.H == y.H && d->res.W == y.W &&
+                      d->res.C == y.C, "esf_conv_wfold_create: residual view must match the output view");
+
+  IgemmOp* op = new (std::nothrow) IgemmOp();
+  if (!op) return set_error(ESF_ERR_ARG, "out of host memory");
+  IgemmParams& p = op->params;
+  memset(&p, 0, sizeof(p));
+  int kc, kch, n_tile, n_pad;
+  esf_igemm_geometry(64, N, &kc, &kch, &n_tile, &n_pad);
+  const bool need_pow2 = !y_dense || (has_res && !r_dense);
+  if (need_pow2 && (n_pad != N || (Cout < 64 ? 64 % Cout : Cout % 64) != 0 || N % std::min(64, N) != 0)) {
+    delete op;
+    return set_error(ESF_ERR_UNSUPPORTED, "esf_conv_wfold_create: sliced output needs WB*Cout a power of two");
+  }
+  p.kc = 64, p.kchunks = kchunks, p.n_tile = n_tile, p.n_tiles = n_pad / n_tile, p.num_taps = num_taps;
+  choose_box(1, Ho, To, y.B, &p.bw, &p.bh, &p.bt, &p.bb);
+  p.tw = 1, p.th = cdiv(Ho, p.bh), p.tt = cdiv(To, p.bt), p.tb = cdiv(y.B, p.bb);
+  p.rows = p.bw * p.bh * p.bt * p.bb;
+  p.ncb = Wo / WB;
+  p.a_cb_stride = WB * d->sW * C;
+  p.a_c_base = -d->pW * C;
+  p.fold_wb = WB;
+  const long long ntiles = (long long)p.ncb * p.th * p.tt * p.tb * p.n_tiles;
+  if (ntiles > 0x7fffffffLL) {
+    delete op;
+    return set_error(ESF_ERR_ARG, "too many tiles");
+  }
+  p.num_tiles = (int)ntiles;
+  p.a_bytes = p.rows * 128, p.b_bytes = n_tile * 128, p.b_stride = (p.b_bytes + 1023) & ~1023u;
+  p.sbo = 1024, p.layout_type = 2;
+  p.bias = d->bias, p.act = d->act, p.has_res = has_res, p.out_f32 = 0;
+  p.f16 = x.dtype == ESF_F16;
+  const CUtensorMapDataType dt16 = p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  p.slab_cols = std::min(n_tile, 64);
+  const int out_row_bytes = p.slab_cols * 2;
+  // a sliced destination is written through a (c, w) box whose smem image is the plain row-major slab: no swizzle
+  const bool plain = need_pow2;
+  p.out_swz = plain ? 0 : (out_row_bytes == 128 ? 7 : (out_row_bytes == 64 ? 3 : 1));
+  const CUtensorMapSwizzle out_sw = plain ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_for_row_bytes(out_row_bytes);
+  p.res_bytes = p.rows * p.slab_cols * 2;
+  p.obufs = has_res ? (n_tile >= 256 ? 4 : 6) : 2;
+  const int fixed = 1024 + p.obufs * kOutStageBytes + 512;
+  int stages = (kSmemLimit - fixed) / (kAStageBytes + (int)p.b_stride);
+  p.stages = std::max(2, std::min(stages, kMaxStages));
+  op->smem_bytes = fixed + p.stages * (kAStageBytes + (int)p.b_stride);
+
+  int rc = ESF_OK;
+  int phase_map[8];
+  for (int i = 0; i < 8; ++i) phase_map[i] = -1;
+  int nmaps = 0, tap_i = 0;
+  for (int it = 0; it < d->kT && rc == ESF_OK; ++it)
+    for (int ih = 0; ih < d->kH && rc == ESF_OK; ++ih, ++tap_i) {
+      const int oh = ih - d->pH;
+      const int qh = floordiv(oh, d->sH);
+      const int ph = oh - qh * d->sH;
+      if (ph >= 8) {
+        rc = set_error(ESF_ERR_UNSUPPORTED, "H stride > 8");
+        break;
+      }
+      if (phase_map[ph] < 0) {
+        const int Hp = ph < x.H ? cdiv(x.H - ph, d->sH) : 0;
+        if (Hp <= 0) {
+          rc = set_error(ESF_ERR_UNSUPPORTED, "empty stride phase");
+          break;
+        }
+        char* base = static_cast<char*>(x.ptr) + 2LL * ph * x.sH;
+        rc = encode_act_map(&p.a_maps[nmaps], dt16, 2, base, (int64_t)x.W * C, 1, Hp, x.T, x.B, x.sH * d->sH,
+                            x.sH * d->sH, x.sT, x.sB, 64, 1, p.bh, p.bt, p.bb, CU_TENSOR_MAP_SWIZZLE_128B,
+                            "folded activation");
+        phase_map[ph] = nmaps++;
+      }
+      p.taps[tap_i] = make_int4(phase_map[ph], 0, qh, it - d->pT);
+    }
+  if (rc == ESF_OK)
+    for (int i = nmaps; i < kMaxAMaps; ++i) p.a_maps[i] = p.a_maps[0];
+  if (rc == ESF_OK) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) rc = set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    else {
+      const cuuint64_t K = (cuuint64_t)num_taps * kchunks * 64;
+      cuuint64_t dims[2] = {K, (cuuint64_t)n_pad};
+      cuuint64_t strides[1] = {K * 2};
+      cuuint32_t box[2] = {64, (cuuint32_t)n_tile};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = enc(&p.b_map, dt16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) rc = set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled(folded weights) failed with %d", (int)r);
+    }
+  }
+  auto encode_io = [&](CUtensorMap* m, const esf_view& v, bool dense, int* fold_cout, const char* what) {
+    if (dense && !plain) {   // rows of WB*Cout contiguous elements: (WB*Cout, Wo/WB, Ho, To, B)
+      *fold_cout = 0;
+      return encode_act_map(m, dt16, 2, v.ptr, (int64_t)N, Wo / WB, Ho, To, v.B, (int64_t)N, v.sH, v.sT, v.sB,
+                            p.slab_cols, 1, p.bh, p.bt, p.bb, out_sw, what);
+    }
+    *fold_cout = Cout;       // (Cout, Wo, Ho, To, B) with a (c, w) box per 64-column slab
+    const int cbox = std::min(Cout, p.slab_cols), wbox = std::max(1, p.slab_cols / Cout);
+    return encode_act_map(m, dt16, 2, v.ptr, Cout, Wo, Ho, To, v.B, v.sW, v.sH, v.sT, v.sB, cbox, wbox, p.bh, p.bt, p.bb,
+                          out_sw, what);
+  };
+  if (rc == ESF_OK) rc = encode_io(&p.out_map, y, y_dense, &p.out_fold_cout, "folded output");
+  if (rc == ESF_OK) {
+    if (has_res) rc = encode_io(&p.res_map, d->res, r_dense, &p.res_fold_cout, "folded residual");
+    else p.res_map = p.out_map;
+  }
+  p.out_cb_w = 1;
+  if (rc == ESF_OK) rc = finish_op(op);
   if (rc != ESF_OK) {
     delete op;
     return rc;

@@ -75,6 +75,51 @@ def pack_stem_band(w, bias, stride_w, device, dtype=torch.bfloat16):
             bt.to(device=device, dtype=torch.float32).contiguous())
 
 
+def pack_wfold_band(w, bias, WB, stride_w, device, dtype=torch.bfloat16):
+    """Folded (Cout,Cin,kT,kH,kW) weight of a thin layer -> band matrix [n_pad][kT*kH*kchunks*64] and tiled bias [n_pad]
+    for esf_conv_wfold_create.  Row n = i*Cout + co (i = output column inside the WB-wide block); column
+    k = (kt*kH + kh)*kchunks*64 + j where (w_in, c) = divmod(j, Cin) indexes the contiguous input run the block reads
+    (starting at input column WB*sW*block - pW) and kw = w_in - sW*i."""
+    cout, cin, kt, kh, kw = w.shape
+    N = WB * cout
+    _, _, _, n_pad = rt.igemm_geometry(64, N)
+    win = ((WB - 1) * stride_w + kw) * cin
+    kpad = -(-win // 64) * 64
+    band = torch.zeros(n_pad, kt * kh, kpad, dtype=torch.float64, device=w.device)
+    wt = w.permute(0, 2, 3, 4, 1).reshape(cout, kt * kh, kw * cin).to(torch.float64)   # [co][tap][(kw, c)]
+    for i in range(WB):
+        j0 = stride_w * i * cin
+        band[i * cout:(i + 1) * cout, :, j0:j0 + kw * cin] = wt
+    bt = torch.zeros(n_pad, dtype=torch.float64, device=w.device)
+    bt[:N] = bias.repeat(WB)
+    return (band.reshape(n_pad, -1).to(device=device, dtype=dtype).contiguous(),
+            bt.to(device=device, dtype=torch.float32).contiguous())
+
+
+def wfold_block(x, y, res, w_shape, stride, padding, dilation):
+    """Width of the output-column block to fold into the GEMM's N for a thin layer, or 0 when the regular implicit
+    GEMM should run.  Mirrors the argument checks of esf_conv_wfold_create."""
+    cout, cin, kt, kh, kw = w_shape
+    if cin > 32 or cin % 8 or stride[0] != 1 or tuple(dilation) != (1, 1, 1):
+        return 0
+    if x.stride(3) != cin or x.stride(4) != 1:
+        return 0
+    Wo = y.shape[3]
+    sliced = y.stride(3) != cout or (res is not None and res.stride(3) != cout)
+    best, best_key = 0, None
+    for wb in range(1, 33):
+        N = wb * cout
+        win = ((wb - 1) * stride[2] + kw) * cin
+        if Wo % wb or N > 256 or win > 128:
+            continue
+        if sliced and (N & (N - 1) or (64 % cout if cout < 64 else cout % 64)):
+            continue
+        key = (N, -((win + 63) // 64))      # widest MMA first, then fewest K chunks
+        if best_key is None or key > best_key:
+            best, best_key = wb, key
+    return best if best >= 2 else 0     # a block of one column is the plain implicit GEMM
+
+
 class Plan:
     """Ordered kernel launches + every tensor they touch.  `eager` ops read the caller's input tensors and are
     launched on every forward; `graph` ops only touch plan-owned memory and are replayed from one CUDA graph."""
@@ -92,6 +137,7 @@ class Plan:
         self.launches_per_run = 0
         self.buffers = {}     # name -> activation tensor (for tests / debugging)
         self.meta = []        # one dict per op: kind, label, algorithmic flops / bytes / exps, launches
+        self.wfold = True            # thin layers (C_in <= 32) as W-folded banded GEMMs
         self.attn_impl = "tcgen05"   # "tcgen05" (TMEM, two-pass) or "mma_sync" (register-resident, online softmax)
 
     # ---------------------------------------------------------------- memory
@@ -136,6 +182,25 @@ class Plan:
                   "%dx%dx%d s%s %d->%d @%s" % (kt, kh, kw, "".join(map(str, stride)), cin, cout, tuple(y.shape[1:4])),
                   flops=2.0 * m * cout * cin * kt * kh * kw, nbytes=self._nbytes(x, y, res) + wp.numel() * 2)
 
+    def conv_wfold(self, x, y, w_folded, bias, WB, stride=(1, 1, 1), padding=(0, 0, 0), act=rt.ACT_NONE, res=None):
+        """Thin-layer (C_in <= 32) conv as a W-folded banded GEMM: see esf_conv_wfold_create."""
+        wp, bp = pack_wfold_band(w_folded, bias, WB, stride[2], self.device, self.adt)
+        self.keep += [wp, bp]
+        kt, kh, kw = w_folded.shape[2:]
+        d = rt.EsfConvDesc(rt.view(x), rt.view(y), rt.view(res) if res is not None else rt.null_view(),
+                           wp.data_ptr(), bp.data_ptr(), kt, kh, kw, *stride, *padding, 1, 1, 1, 1, act,
+                           rt.dtype_code(y))
+        h = ctypes.c_void_p()
+        L = rt.lib()
+        rt.check(L.esf_conv_wfold_create(ctypes.byref(d), WB, ctypes.byref(h)), "esf_conv_wfold_create")
+        self.handles.append(h)
+        cout, cin = w_folded.shape[:2]
+        m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
+        self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "conv_wfold",
+                  "%dx%dx%d s%s %d->%d @%s wb%d" % (kt, kh, kw, "".join(map(str, stride)), cin, cout,
+                                                   tuple(y.shape[1:4]), WB),
+                  flops=2.0 * m * cout * cin * kt * kh * kw, nbytes=self._nbytes(x, y, res) + wp.numel() * 2)
+
     @staticmethod
     def _aligned(t):
         """True when a view can be addressed by TMA / 16-byte vector accesses."""
@@ -149,6 +214,9 @@ class Plan:
         """Conv3d + folded BN (+ residual) + activation: tensor-core implicit GEMM when the layer is dense and its
         views are 16-byte addressable, CUDA-core direct conv otherwise (grouped / depthwise / odd channel counts)."""
         if groups == 1 and x.shape[4] >= 8 and self._aligned(x) and self._aligned(y) and self._aligned(res):
+            wb = wfold_block(x, y, res, w_folded.shape, stride, padding, dilation) if self.wfold else 0
+            if wb:
+                return self.conv_wfold(x, y, w_folded, bias, wb, stride, padding, act, res)
             return self.conv_igemm(x, y, w_folded, bias, stride, padding, dilation, act, res, out_dtype)
         return self.conv_direct(x, y, w_folded, bias, stride, padding, dilation, groups, act, res, out_dtype)
 

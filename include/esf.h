@@ -79,6 +79,10 @@ int64_t esf_launch_count(void);
  * geometry (kc, kchunks, n_tile, n_pad) for a (cin, cout) pair comes from esf_igemm_geometry(). */
 int esf_igemm_geometry(int32_t cin, int32_t cout, int32_t* kc, int32_t* kchunks, int32_t* n_tile, int32_t* n_pad);
 int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out);
+/* Same convolution for thin layers (C_in <= 32): a block of WB output columns is folded into the GEMM's N and the
+ * input columns it reads into K (banded weights), so TMA rows are 128 B and N = WB * Cout.  Weights: 16-bit band
+ * matrix [n_pad][kT*kH*kchunks*64] and tiled bias (engine.pack_wfold_band).  x must be dense in (W, C). */
+int esf_conv_wfold_create(const esf_conv_desc* d, int32_t WB, esf_op** out);
 int esf_op_launch(esf_op* op, void* stream);
 void esf_op_destroy(esf_op* op);
 

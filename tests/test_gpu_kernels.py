@@ -109,6 +109,65 @@ def test_conv_igemm(esf_lib, case, precision):
     assert (ybuf[..., -4:].float() == 7.0).all()
 
 
+# name, (B,T,H,W), Cin, Cout, kernel, stride, padding, act, residual ("", "dense", "slice"), sliced output
+WFOLD_CASES = [
+    ("b_1x3x3_8", (2, 4, 56, 56), 8, 8, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, "", False),
+    ("c_1x1x1_8to32_res", (2, 4, 56, 56), 8, 32, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, "dense", False),
+    ("c_1x1x1_8to32_res_slice_out", (2, 4, 56, 56), 8, 32, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, "dense", True),
+    ("c_res_slice", (2, 4, 28, 28), 16, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, "slice", True),
+    ("a_3x1x1_32to8", (2, 6, 56, 56), 32, 8, (3, 1, 1), (1, 1, 1), (1, 0, 0), 1, "", False),
+    ("a_3x1x1_16to8", (1, 5, 56, 56), 16, 8, (3, 1, 1), (1, 1, 1), (1, 0, 0), 1, "", False),
+    ("b_1x3x3_s2_16", (2, 4, 56, 56), 16, 16, (1, 3, 3), (1, 2, 2), (0, 1, 1), 1, "", False),
+    ("branch1_s2_32to128", (2, 4, 28, 28), 32, 128, (1, 1, 1), (1, 2, 2), (0, 0, 0), 0, "", False),
+    ("b_1x3x3_32_14", (3, 4, 14, 14), 32, 32, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, "", False),
+    ("c_32to128_14_slice", (3, 4, 14, 14), 32, 128, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, "dense", True),
+    ("odd_w_30", (1, 3, 10, 30), 8, 24, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, "dense", False),
+    ("fuse_5x1x1_8to16_slice", (2, 8, 28, 28), 8, 16, (5, 1, 1), (1, 1, 1), (2, 0, 0), 1, "", True),
+]
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", WFOLD_CASES, ids=[c[0] for c in WFOLD_CASES])
+def test_conv_wfold(esf_lib, case, precision):
+    """Thin layers as W-folded banded GEMMs (esf_conv_wfold_create) against torch conv3d."""
+    from efficient_slowfast_b200.engine import wfold_block
+    name, (B, T, H, W), cin, cout, k, s, p, act, res_kind, slice_out = case
+    adt = rt.TORCH_DTYPE[precision]
+    g = torch.Generator().manual_seed(sum(map(ord, name)) % 1000)
+    x = _rand_act(g, B, T, H, W, cin, dtype=adt).to(DEV)
+    w = torch.randn(cout, cin, *k, generator=g) * (2.0 / (cin * k[0] * k[1] * k[2])) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv3d(_to_ncdhw(x.cpu()), w.to(adt).float(), bias, s, p)
+    _, _, To, Ho, Wo = ref.shape
+    res = None
+    if res_kind:
+        extra = 16 if res_kind == "slice" else 0
+        rbuf = _rand_act(g, B, To, Ho, Wo, cout + extra, dtype=adt).to(DEV)
+        res = rbuf[..., extra // 2:extra // 2 + cout]
+        ref = ref + _to_ncdhw(res.cpu())
+    if act == 1:
+        ref = ref.relu()
+    extra = 16 if slice_out else 0
+    ybuf = torch.full((B, To, Ho, Wo, cout + extra), 7.0, dtype=adt, device=DEV)
+    y = ybuf[..., extra // 2:extra // 2 + cout]
+    wb = wfold_block(x, y, res, w.shape, s, p, (1, 1, 1))
+    assert wb >= 2, "planner refused to fold %s" % name
+    plan = Plan(DEV, precision)
+    plan.conv(x, y, w.double(), bias.double(), stride=s, padding=p, act=act, res=res)
+    assert plan.meta[-1]["kind"] == "conv_wfold"
+    plan.launch_all()
+    torch.cuda.synchronize()
+    got = _to_ncdhw(y.cpu())
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    tol = 2e-3 if precision == "fp16" else 1e-2
+    if not err <= tol * scale:
+        _diagnose(name, got, ref, tol * scale)
+    assert err <= tol * scale, "%s (wb %d): max err %.4g vs scale %.4g" % (name, wb, err, scale)
+    if slice_out:
+        assert (ybuf[..., :8].float() == 7.0).all() and (ybuf[..., -8:].float() == 7.0).all()
+
+
 def test_conv_direct_depthwise_and_grouped(esf_lib):
     g = torch.Generator().manual_seed(5)
     for (cin, cout, groups, k, s, p) in [(24, 24, 24, (3, 3, 3), (1, 2, 2), (1, 1, 1)),
