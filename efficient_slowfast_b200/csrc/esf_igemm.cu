@@ -4,13 +4,17 @@
 //   M  = a box of (bw x bh x bt x bb) <= 128 output positions of the channels-last (B,T,H,W,C) activation,
 //   N  = n_tile output channels (16..256),  K = taps x input-channel chunks of kc in {16,32,64} elements.
 //
-//   warp 8      TMA producer: one 5-D box load per (tap, chunk) of the activation -- the filter tap is a coordinate
+//   warp 16     TMA producer: one 5-D box load per (tap, chunk) of the activation -- the filter tap is a coordinate
 //               offset, zero padding is TMA out-of-bounds fill, a strided conv reads one tensor map per stride phase
 //               -- plus a 2-D load of the packed weights; `stages`-deep mbarrier ring.
-//   warp 9      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=n_tile, K=16) into one of two TMEM
+//   warp 17     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=n_tile, K=16) into one of two TMEM
 //               accumulators; tcgen05.commit releases smem stages / publishes the accumulator.
-//   warps 0-7   epilogue: tcgen05.ld -> + bias (+ residual tile fetched by TMA) -> ReLU -> BF16/FP32 -> swizzled smem
-//               -> TMA store straight into the (possibly channel-sliced) destination, i.e. concat is free.
+//   warps 0-15  epilogue: tcgen05.ld -> + bias (+ residual tile fetched by TMA) -> ReLU -> 16-bit/FP32 -> swizzled smem
+//               -> TMA store straight into the (possibly channel-sliced) destination, i.e. concat is free.  Sixteen
+//               warps (four per TMEM lane quarter, a quarter of the slab's columns each) because 1x1x1 expansions are
+//               bound by this path, not by the MMAs.
+//   warp 18     residual producer: TMA-loads the residual tile of each output slab into the staging buffer the
+//               epilogue will overwrite in place, `obufs - 1` slabs ahead of its consumer.
 //
 // Reference ops replaced: see include/esf.h (esf_conv_igemm_create).
 #include <string.h>
@@ -24,10 +28,12 @@
 
 namespace esf {
 
-constexpr int kEpiThreads = 256;
-constexpr int kProducerWarp = 8;
-constexpr int kMmaWarp = 9;
-constexpr int kThreads = 320;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kProducerWarp = 16;
+constexpr int kMmaWarp = 17;
+constexpr int kResWarp = 18;
+constexpr int kThreads = 19 * 32;
 constexpr int kMaxStages = 8;
 constexpr int kMaxAMaps = 8;
 constexpr int kMaxTaps = 64;
@@ -60,7 +66,7 @@ struct __align__(64) IgemmParams {
   // "column blocks" (banded stem GEMM): an extra tile index that shifts the innermost coordinate of the
   // activation loads and of the output stores; ncb == 1 and zero strides for ordinary convolutions
   int ncb, a_cb_stride, out_cb_w;  // out_cb_w: W-coordinate step of the output store per column block
-  int obufs;                       // depth of the output/residual staging ring (2..kMaxOutBufs)
+  int obufs;                       // depth of the output/residual staging ring (3..kMaxOutBufs)
   // W-folded GEMMs (thin-channel layers): innermost start coordinate of the activation loads, and -- when the output
   // (residual) is a channel slice -- the (w, c) decomposition of an output column n = w_in_block * cout + c
   int a_c_base, fold_wb, out_fold_cout, res_fold_cout;
@@ -86,53 +92,67 @@ __device__ __forceinline__ TileCoord tile_coord(const IgemmParams& p, int tile) 
 
 __device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kEpiThreads) : "memory"); }
 
-// One epilogue thread: NC accumulator columns of its row for one output slab.
-template <int NC>
-__device__ __forceinline__ void epi_process(const IgemmParams& p, uint32_t taddr, const float* __restrict__ bias,
-                                            uint8_t* stage_buf, int r, int half, bool row_valid) {
-  float v[NC];
+// One epilogue thread: NC accumulator columns of its row for one output slab.  `row` points at the thread's staging row,
+// `inner` is the byte offset of its first column inside the row and `x` the row's swizzle XOR term.
+template <int NC, bool F16>
+__device__ __forceinline__ void epi_process16(uint32_t taddr, const float* __restrict__ bias, uint8_t* row, uint32_t inner,
+                                              uint32_t x, bool has_res, int act, bool row_valid) {
+  float v[NC], b[NC];
+  uint4 rr[NC / 8];
+#pragma unroll
+  for (int c = 0; c < NC / 4; ++c) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(bias) + c);
+    b[4 * c] = t.x, b[4 * c + 1] = t.y, b[4 * c + 2] = t.z, b[4 * c + 3] = t.w;
+  }
+  if (has_res) {
+#pragma unroll
+    for (int c = 0; c < NC / 8; ++c) rr[c] = *reinterpret_cast<const uint4*>(row + ((inner + c * 16) ^ x));
+  }
   tmem_ld<NC>(taddr, v);
 #pragma unroll
-  for (int j = 0; j < NC; ++j) v[j] += __ldg(bias + j);
-  if (p.out_f32) {
-    const uint32_t base = r * (p.slab_cols * 4) + half * (NC * 4);
+  for (int j = 0; j < NC; ++j) v[j] += b[j];
+  if (has_res) {
 #pragma unroll
-    for (int j = 0; j < NC; ++j) v[j] = apply_act(v[j], p.act);
-    if (row_valid) {
+    for (int c = 0; c < NC / 8; ++c) {
+      const uint32_t u[4] = {rr[c].x, rr[c].y, rr[c].z, rr[c].w};
 #pragma unroll
-      for (int c = 0; c < NC / 4; ++c) {
-        float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-        *reinterpret_cast<float4*>(stage_buf + swz(base + c * 16, p.out_swz)) = o;
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack16x2(u[e], F16);
+        v[8 * c + 2 * e] += f.x;
+        v[8 * c + 2 * e + 1] += f.y;
       }
     }
-  } else {
-    const uint32_t base = r * (p.slab_cols * 2) + half * (NC * 2);
-    if (p.has_res) {
+  }
+  const float lo = act ? 0.f : -INFINITY;
 #pragma unroll
-      for (int c = 0; c < NC / 8; ++c) {
-        const uint4 rr = *reinterpret_cast<const uint4*>(stage_buf + swz(base + c * 16, p.out_swz));
-        const uint32_t u[4] = {rr.x, rr.y, rr.z, rr.w};
+  for (int j = 0; j < NC; ++j) v[j] = fmaxf(v[j], lo);
+  if (act == 2) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack16x2(u[e], p.f16);
-          v[8 * c + 2 * e] += f.x;
-          v[8 * c + 2 * e + 1] += f.y;
-        }
-      }
+    for (int j = 0; j < NC; ++j) v[j] = fminf(v[j], 6.f);
+  }
+  if (row_valid) {
+#pragma unroll
+    for (int c = 0; c < NC / 8; ++c) {
+      uint4 o;
+      o.x = pack16x2(v[8 * c + 0], v[8 * c + 1], F16);
+      o.y = pack16x2(v[8 * c + 2], v[8 * c + 3], F16);
+      o.z = pack16x2(v[8 * c + 4], v[8 * c + 5], F16);
+      o.w = pack16x2(v[8 * c + 6], v[8 * c + 7], F16);
+      *reinterpret_cast<uint4*>(row + ((inner + c * 16) ^ x)) = o;
     }
+  }
+}
+
+// FP32 destination (attention projections): 8 columns per thread, no residual.
+__device__ __forceinline__ void epi_process32(uint32_t taddr, const float* __restrict__ bias, uint8_t* row, uint32_t inner,
+                                              uint32_t x, int act, bool row_valid) {
+  float v[8];
+  tmem_ld<8>(taddr, v);
 #pragma unroll
-    for (int j = 0; j < NC; ++j) v[j] = apply_act(v[j], p.act);
-    if (row_valid) {
-#pragma unroll
-      for (int c = 0; c < NC / 8; ++c) {
-        uint4 o;
-        o.x = pack16x2(v[8 * c + 0], v[8 * c + 1], p.f16);
-        o.y = pack16x2(v[8 * c + 2], v[8 * c + 3], p.f16);
-        o.z = pack16x2(v[8 * c + 4], v[8 * c + 5], p.f16);
-        o.w = pack16x2(v[8 * c + 6], v[8 * c + 7], p.f16);
-        *reinterpret_cast<uint4*>(stage_buf + swz(base + c * 16, p.out_swz)) = o;
-      }
-    }
+  for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j] + __ldg(bias + j), act);
+  if (row_valid) {
+    *reinterpret_cast<float4*>(row + (inner ^ x)) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(row + ((inner + 16) ^ x)) = make_float4(v[4], v[5], v[6], v[7]);
   }
 }
 
@@ -147,7 +167,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_full = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + kMaxOutBufs);
+  uint64_t* buf_free = res_full + kMaxOutBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_free + kMaxOutBufs);
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -159,9 +180,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 8);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[a], kEpiWarps);  // one arrival per epilogue warp
     }
-    for (int a = 0; a < p.obufs; ++a) mbar_init(&res_full[a], 1);
+    for (int a = 0; a < p.obufs; ++a) {
+      mbar_init(&res_full[a], 1);
+      mbar_init(&buf_free[a], 1);
+    }
     fence_barrier_init();
   }
   if (warp == kProducerWarp && lane == 0) {
@@ -254,34 +278,53 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         }
       }
     }
+  } else if (warp == kResWarp) {
+    // residual tile of this CTA's k-th slab -> staging buffer k % R, as soon as the store that last used the buffer
+    // has read it: the DRAM latency of the (HBM-bound) residual stream and the coordinate arithmetic stay off the
+    // epilogue's critical path
+    if (p.has_res) {
+      const int slabs = p.n_tile / p.slab_cols;
+      const int R = p.obufs;
+      int buf = 0, use = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(p, tile);
+        for (int s = 0; s < slabs; ++s) {
+          if (use > 0) mbar_wait(&buf_free[buf], (use - 1) & 1, 6);
+          if (elect_one()) {
+            int c = tc.n_idx * p.n_tile + s * p.slab_cols, w = tc.w0 + tc.cb * p.out_cb_w;
+            if (p.res_fold_cout) {
+              w = tc.cb * p.fold_wb + c / p.res_fold_cout;
+              c = c % p.res_fold_cout;
+            }
+            mbar_arrive_expect_tx(&res_full[buf], p.res_bytes);
+            tma_load_5d(smem_out + buf * kOutStageBytes, &p.res_map, &res_full[buf], c, w, tc.h0, tc.t0, tc.b0);
+          }
+          __syncwarp();
+          if (++buf == R) {
+            buf = 0;
+            ++use;
+          }
+        }
+      }
+    }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 0..7
-    const int q = warp & 3;      // TMEM lane quarter this warp may access
-    const int half = warp >> 2;  // which half of the slab's columns
+    // ------------------------------------------------------------------ epilogue warps 0..15
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int part = warp >> 2;   // which share of the slab's columns
     const int r = q * 32 + lane;
     const bool row_valid = r < p.rows;
     const bool leader = threadIdx.x == 0;
     const int slabs = p.n_tile / p.slab_cols;
-    const int cpt = p.slab_cols >> 1;  // columns per thread per slab
-    int g = 0;                         // running slab counter of this CTA (staging buffer = g % obufs)
+    const int cpt = max(8, p.slab_cols >> 2);  // columns per thread per slab
+    const bool active = part * cpt < p.slab_cols;
+    const int oes = p.out_f32 ? 4 : 2;
+    const uint32_t rowoff = r * p.slab_cols * oes;
+    const uint32_t inner = part * cpt * oes;
+    const uint32_t x = ((rowoff >> 7) & p.out_swz) << 4;
     const int R = p.obufs;
-    // residual tile of this CTA's k-th slab -> staging buffer k % R; issued R - 1 slabs ahead of its consumer so the
-    // DRAM latency of the (HBM-bound) residual stream is off the epilogue's critical path
-    auto prefetch_res = [&](int k) {
-      const int ktile = blockIdx.x + (k / slabs) * gridDim.x;
-      if (ktile >= p.num_tiles) return;
-      const TileCoord kc = tile_coord(p, ktile);
-      const int kb = k % R;
-      int c = kc.n_idx * p.n_tile + (k % slabs) * p.slab_cols, w = kc.w0 + kc.cb * p.out_cb_w;
-      if (p.res_fold_cout) {
-        w = kc.cb * p.fold_wb + c / p.res_fold_cout;
-        c = c % p.res_fold_cout;
-      }
-      mbar_arrive_expect_tx(&res_full[kb], p.res_bytes);
-      tma_load_5d(smem_out + kb * kOutStageBytes, &p.res_map, &res_full[kb], c, w, kc.h0, kc.t0, kc.b0);
-    };
-    if (p.has_res && leader)
-      for (int k = 0; k < R - 1; ++k) prefetch_res(k);
+    const bool has_res = p.has_res != 0;
+    int buf = 0, use = 0, prev_buf = 0;
+    bool first = true;
     int iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
       const TileCoord tc = tile_coord(p, tile);
@@ -289,22 +332,31 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const uint32_t acc_phase = (iter >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase, 4);
       tc_fence_after();
-      for (int s = 0; s < slabs; ++s, ++g) {
-        const int buf = g % R;
+      for (int s = 0; s < slabs; ++s) {
         uint8_t* stage_buf = smem_out + buf * kOutStageBytes;
-        if (p.has_res) mbar_wait(&res_full[buf], (g / R) & 1, 5);
-        const int col = s * p.slab_cols + half * cpt;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_tile + col;
-        const float* bias = p.bias + tc.n_idx * p.n_tile + col;
-        if (cpt == 32) epi_process<32>(p, taddr, bias, stage_buf, r, half, row_valid);
-        else if (cpt == 16) epi_process<16>(p, taddr, bias, stage_buf, r, half, row_valid);
-        else epi_process<8>(p, taddr, bias, stage_buf, r, half, row_valid);
+        if (has_res) mbar_wait(&res_full[buf], use & 1, 5);
+        if (active) {
+          const int col = s * p.slab_cols + part * cpt;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_tile + col;
+          const float* bias = p.bias + tc.n_idx * p.n_tile + col;
+          uint8_t* row = stage_buf + rowoff;
+          if (p.out_f32) epi_process32(taddr, bias, row, inner, x, p.act, row_valid);
+          else if (cpt == 16) {
+            if (p.f16) epi_process16<16, true>(taddr, bias, row, inner, x, has_res, p.act, row_valid);
+            else epi_process16<16, false>(taddr, bias, row, inner, x, has_res, p.act, row_valid);
+          } else {
+            if (p.f16) epi_process16<8, true>(taddr, bias, row, inner, x, has_res, p.act, row_valid);
+            else epi_process16<8, false>(taddr, bias, row, inner, x, has_res, p.act, row_valid);
+          }
+        }
         if (s == slabs - 1) {  // accumulator fully drained: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
         fence_proxy_async_smem();
+        // One barrier per slab is enough with a ring of >= 3 buffers: a thread that runs ahead writes buffer
+        // (g + 1) % R, whose previous store (g + 1 - R <= g - 2) the leader saw finish reading before it arrived here.
         epi_bar_sync(1);
         if (leader) {
           int c = tc.n_idx * p.n_tile + s * p.slab_cols, w = tc.w0 + tc.cb * p.out_cb_w;
@@ -315,9 +367,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           tma_store_5d(&p.out_map, stage_buf, c, w, tc.h0, tc.t0, tc.b0);
           tma_store_commit();
           tma_store_wait_read<1>();  // every store before this one has finished reading its staging buffer
-          if (p.has_res) prefetch_res(g + R - 1);  // into the buffer that slab g - 1 just released
+          if (has_res && !first) mbar_arrive(&buf_free[prev_buf]);
         }
-        epi_bar_sync(2);
+        first = false;
+        prev_buf = buf;
+        if (++buf == R) {
+          buf = 0;
+          ++use;
+        }
       }
     }
     if (leader) tma_store_wait_all<0>();
@@ -340,6 +397,22 @@ EncodeTiledFn get_encode_fn() {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
   fn = reinterpret_cast<EncodeTiledFn>(p);
   return fn;
+}
+
+// Split shared memory between the operand pipeline and the output/residual staging ring.  Layers with a short K loop
+// (1x1x1 expansions) are bound by the epilogue and the residual stream, so they get the deeper ring; layers with a
+// long K loop need the stages.
+static void plan_smem(IgemmParams& p, int* smem_bytes) {
+  const int stage_bytes = kAStageBytes + (int)p.b_stride;
+  const int avail = kSmemLimit - 1024 - 512;
+  const int ksteps = p.num_taps * p.kchunks;
+  const int want_stages = std::min(p.n_tile >= 256 ? 3 : 4, ksteps + 1);
+  int R = p.has_res ? 6 : 3;
+  while (R > 3 && (avail - R * kOutStageBytes) / stage_bytes < want_stages) --R;
+  p.obufs = R;
+  const int stages = (avail - R * kOutStageBytes) / stage_bytes;
+  p.stages = std::max(2, std::min(stages, kMaxStages));
+  *smem_bytes = 1024 + 512 + R * kOutStageBytes + p.stages * stage_bytes;
 }
 
 static CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
@@ -519,13 +592,7 @@ extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
   p.out_swz = out_row_bytes == 128 ? 7 : (out_row_bytes == 64 ? 3 : 1);
   p.res_bytes = p.rows * p.slab_cols * 2;
 
-  // stages: as deep as shared memory allows
-  p.obufs = p.has_res ? (n_tile >= 256 ? 4 : 6) : 2;
-  const int fixed = 1024 + p.obufs * kOutStageBytes + 512;
-  int stages = (kSmemLimit - fixed) / (kAStageBytes + (int)p.b_stride);
-  stages = std::max(2, std::min(stages, kMaxStages));
-  p.stages = stages;
-  op->smem_bytes = fixed + stages * (kAStageBytes + (int)p.b_stride);
+  plan_smem(p, &op->smem_bytes);
 
   // ---- activation maps: one per distinct stride phase; taps carry the per-map coordinate offsets
   struct Phase {
@@ -687,11 +754,7 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
   const int out_row_bytes = p.slab_cols * 2;
   p.out_swz = out_row_bytes == 128 ? 7 : (out_row_bytes == 64 ? 3 : 1);
   p.res_bytes = 0;
-  p.obufs = 2;
-  const int fixed = 1024 + p.obufs * kOutStageBytes + 512;
-  int stages = (kSmemLimit - fixed) / (kAStageBytes + (int)p.b_stride);
-  p.stages = std::max(2, std::min(stages, kMaxStages));
-  op->smem_bytes = fixed + p.stages * (kAStageBytes + (int)p.b_stride);
+  plan_smem(p, &op->smem_bytes);
 
   // one activation map per row phase of the H stride
   int phase_map[8];
@@ -826,11 +889,7 @@ extern "C" int esf_conv_wfold_create(const esf_conv_desc* d, int32_t WB, esf_op*
   p.out_swz = plain ? 0 : (out_row_bytes == 128 ? 7 : (out_row_bytes == 64 ? 3 : 1));
   const CUtensorMapSwizzle out_sw = plain ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_for_row_bytes(out_row_bytes);
   p.res_bytes = p.rows * p.slab_cols * 2;
-  p.obufs = has_res ? (n_tile >= 256 ? 4 : 6) : 2;
-  const int fixed = 1024 + p.obufs * kOutStageBytes + 512;
-  int stages = (kSmemLimit - fixed) / (kAStageBytes + (int)p.b_stride);
-  p.stages = std::max(2, std::min(stages, kMaxStages));
-  op->smem_bytes = fixed + p.stages * (kAStageBytes + (int)p.b_stride);
+  plan_smem(p, &op->smem_bytes);
 
   int rc = ESF_OK;
   int phase_map[8];

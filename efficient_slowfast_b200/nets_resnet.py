@@ -492,18 +492,18 @@ class _TwoStreamResNet(_PlannedModel):
         if hasattr(blk, "branch1"):
             sc = plan.act(B, T, Ho, Wo, co)
             w, b = fold_conv_bn(blk.branch1.weight, None, blk.branch1_bn)
-            plan.conv_igemm(x, sc, w, b, stride=tuple(blk.branch1.stride))
+            plan.conv(x, sc, w, b, stride=tuple(blk.branch1.stride))
         else:
             sc = x
         w, b = fold_conv_bn(t.a.weight, None, t.a_bn)
-        plan.conv_igemm(x, ta, w, b, stride=tuple(t.a.stride), padding=tuple(t.a.padding), act=rt.ACT_RELU)
+        plan.conv(x, ta, w, b, stride=tuple(t.a.stride), padding=tuple(t.a.padding), act=rt.ACT_RELU)
         if t.b.groups != 1:
             raise NotImplementedError("RESNET.NUM_GROUPS > 1 (ResNeXt) is not on the BASELINE path")
         w, b = fold_conv_bn(t.b.weight, None, t.b_bn)
-        plan.conv_igemm(ta, tb, w, b, stride=tuple(t.b.stride), padding=tuple(t.b.padding),
+        plan.conv(ta, tb, w, b, stride=tuple(t.b.stride), padding=tuple(t.b.padding),
                         dilation=tuple(t.b.dilation), act=rt.ACT_RELU)
         w, b = fold_conv_bn(t.c.weight, None, t.c_bn)
-        plan.conv_igemm(tb, y, w, b, act=rt.ACT_RELU, res=sc)
+        plan.conv(tb, y, w, b, act=rt.ACT_RELU, res=sc)
 
 @MODEL_REGISTRY.register()
 class SlowFastDualAttention(_TwoStreamResNet):
