@@ -352,16 +352,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
 // halves are independent split-K streams with their own running maximum and their own TMEM accumulator O[q][h]; the
 // row sums come out of the P.V MMA itself (V^T has a row of ones), so the hot loop is FFMA + MUFU.EX2 + 1/2 F2FP +
 // 1/2 FMNMX3 per element.  The epilogue merges the halves: O = (O0 f0 + O1 f1) / (l0 f0 + l1 f1), f_h = exp(m_h - M).
+//
+// The loop is shaped to keep the MUFU pipe fed (the only roofline this kernel has):
+//   * the exponentials of a tile are computed speculatively with the CURRENT running maximum, interleaved with the
+//     tile-maximum reduction instead of after it; only when some row of the warp exceeds its maximum by more than tau
+//     (rare after the first tiles) the scores are re-read from TMEM and the tile is replayed with the raised maximum;
+//   * P never touches shared memory: it is written to TMEM (tcgen05.st) and the P.V MMA takes its A operand from
+//     there, which removes the swizzled st.shared, the generic->async proxy fence and their address arithmetic;
+// Two things that were measured and did NOT help (so the kernel is issue/latency bound, not MUFU-throughput bound):
+// fetching the scores of tile j+1 before P of tile j is stored (-25 %), and evaluating 1/8 .. 3/8 of the exponentials
+// with a polynomial on the FMA pipe (-5 .. -25 %).
+// TMEM columns: S[q][buf] 4 x 64 | O[q][h] 4 x DVp (<= 48) | P[q][h] 4 x 16  = 512.
 constexpr int kV2Threads = 608;  // 16 softmax warps + TMA producer + 2 MMA issuers
+constexpr int kV2PCol = 448;     // first TMEM column of P
 
+template <bool F16>
 __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Qs = smem;
   uint8_t* Ks = Qs + 2 * p.q_tile_bytes;
   uint8_t* Vs = Ks + p.stages * p.k_tile_bytes;
-  uint8_t* Ps = Vs + p.stages * p.v_tile_bytes;          // 2 x 16 KB
-  float* mx_sh = reinterpret_cast<float*>(Ps + 2 * 16384);  // [q][h][128] running maxima for the final merge
+  float* mx_sh = reinterpret_cast<float*>(Vs + p.stages * p.v_tile_bytes);  // [q][h][128] running maxima for the final merge
   uint64_t* bars = reinterpret_cast<uint64_t*>(mx_sh + 2 * 2 * 128);
   uint64_t* q_full = bars;
   uint64_t* kv_full = q_full + 1;
@@ -435,14 +447,13 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
   } else if (warp == 17 || warp == 18) {
     // ------------------------------------------------------------------ MMA issuers (one per query tile)
     const int q = warp - 17;
-    const uint32_t idesc_s = make_idesc_16(128, kTcBN, p.f16);
-    const uint32_t idesc_o = make_idesc_16(128, p.DVp, p.f16);
+    const uint32_t idesc_s = make_idesc_16(128, kTcBN, F16);
+    const uint32_t idesc_o = make_idesc_16(128, p.DVp, F16);
     const uint32_t qk_hi = kmajor_desc_hi(p.sbo, p.layout_type);
     const uint32_t pv_hi = kmajor_desc_hi(1024, 2);
     const uint32_t q_lo = kmajor_desc_lo(smem_u32(Qs) + q * p.q_tile_bytes);
     const uint32_t k_lo = kmajor_desc_lo(smem_u32(Ks));
     const uint32_t v_lo = kmajor_desc_lo(smem_u32(Vs));
-    const uint32_t p_lo = kmajor_desc_lo(smem_u32(Ps) + q * 16384);
     const uint32_t k_stage_step = p.k_tile_bytes >> 4, v_stage_step = p.v_tile_bytes >> 4;
     auto issue_s = [&](int c, int stage) {
       const int buf = c & 1;
@@ -484,8 +495,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
         tc_fence_after();
         if (elect_one()) {
           const uint32_t o_tmem = tmem_base + 4 * kTcBN + (q * 2 + h) * p.DVp;
-          umma_bf16_lohi(o_tmem, p_lo + 4 * h, pv_hi, vl + 4 * h, pv_hi, idesc_o, j != 0);      // keys 32h .. 32h+15
-          umma_bf16_lohi(o_tmem, p_lo + 4 * h + 2, pv_hi, vl + 4 * h + 2, pv_hi, idesc_o, 1);  // keys 32h+16 .. 32h+31
+          const uint32_t p_tmem = tmem_base + kV2PCol + (q * 2 + h) * 16;
+          umma_f16_ts(o_tmem, p_tmem, vl + 4 * h, pv_hi, idesc_o, j != 0);      // keys 32h .. 32h+15
+          umma_f16_ts(o_tmem, p_tmem + 8, vl + 4 * h + 2, pv_hi, idesc_o, 1);  // keys 32h+16 .. 32h+31
           umma_commit(&p_free[q * 2 + h]);
           if (h == 1) {
             umma_commit(&kv_empty[pv_stage]);
@@ -504,42 +516,65 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
     const int n = row0 + q * 128 + r;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t o_addr = lane_addr + 4 * kTcBN + (q * 2 + h) * p.DVp;
+    const uint32_t p_addr = lane_addr + kV2PCol + (q * 2 + h) * 16;
     const bool tail = (N % kTcBN) != 0;
     float m = -CUDART_INF_F;
-    uint8_t* prow = Ps + q * 16384;
     constexpr float kTau = 5.545177f;
+    float v[32];
+    mbar_wait(&s_full[q * 2], 0, 37);
+    tc_fence_after();
+    tmem_ld32_nowait(lane_addr + (q * 2) * kTcBN + 32 * h, v);
+    tmem_wait_ld();
+    tmem_ld32_acquire(v);
     for (int j = 0; j < nt; ++j) {
       const int buf = j & 1;
-      mbar_wait(&s_full[q * 2 + buf], (j >> 1) & 1, 37);
-      tc_fence_after();
-      float v[32];
-      tmem_ld32(lane_addr + (q * 2 + buf) * kTcBN + 32 * h, v);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[q * 2 + buf]);
-      if (tail && j == nt - 1) {
+      const uint32_t s_addr = lane_addr + (q * 2 + buf) * kTcBN + 32 * h;
+      const bool last_tail = tail && j == nt - 1;
+      if (last_tail) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (j * kTcBN + 32 * h + i >= N) v[i] = -CUDART_INF_F;
       }
-      float mx0 = v[0], mx1 = v[1];
+      // speculative pass with the current maximum; the tile maximum rides along
+      float ms = (m == -CUDART_INF_F) ? 0.f : m * kTcLog2e;
+      float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
 #pragma unroll
-      for (int i = 2; i < 32; i += 2) {
-        mx0 = fmaxf(mx0, v[i]);
-        mx1 = fmaxf(mx1, v[i + 1]);
+      for (int i = 0; i < 32; i += 4) {
+        mx0 = fmaxf(fmaxf(mx0, v[i]), v[i + 1]);
+        mx1 = fmaxf(fmaxf(mx1, v[i + 2]), v[i + 3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[i + e] = fast_exp2(fmaf(v[i + e], kTcLog2e, -ms));
       }
       const float mx = fmaxf(mx0, mx1);
       // raise lazily; a half tile that is entirely masked (tail) must not raise from -inf to -inf
       const bool raise = mx > m + kTau;
-      const float m_new = raise ? mx : m;
-      const float f = raise ? fast_exp2((m - m_new) * kTcLog2e) : 1.f;
-      m = m_new;
-      const float ms = (m == -CUDART_INF_F) ? 0.f : m * kTcLog2e;
+      const bool any_raise = __any_sync(0xffffffffu, raise);
+      float f = 1.f;
+      if (any_raise) {  // replay the tile with the raised maxima (the scores are still in TMEM)
+        tmem_ld32_nowait(s_addr, v);
+        tmem_wait_ld();
+        tmem_ld32_acquire(v);
+        if (last_tail) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = fast_exp2(fmaf(v[i], kTcLog2e, -ms));
+          for (int i = 0; i < 32; ++i)
+            if (j * kTcBN + 32 * h + i >= N) v[i] = -CUDART_INF_F;
+        }
+        const float m_new = raise ? mx : m;
+        f = raise ? fast_exp2((m - m_new) * kTcLog2e) : 1.f;
+        m = m_new;
+        ms = (m == -CUDART_INF_F) ? 0.f : m * kTcLog2e;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fast_exp2(fmaf(v[i], kTcLog2e, -ms));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[q * 2 + buf]);
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = pack16x2(v[2 * i], v[2 * i + 1], F16);
       mbar_wait(&p_free[q * 2 + h], (j & 1) ^ 1, 38);
-      if (j > 0 && __any_sync(0xffffffffu, raise)) {
-        tc_fence_after();
+      tc_fence_after();
+      if (j > 0 && any_raise) {
         for (int c0 = 0; c0 < p.DVp; c0 += 16) {
           float o[16];
           tmem_ld16(o_addr + c0, o);
@@ -547,21 +582,19 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
           for (int jj = 0; jj < 16; ++jj) o[jj] *= f;
           tmem_st16(o_addr + c0, o);
         }
-        tmem_wait_st();
       }
-#pragma unroll
-      for (int ck = 0; ck < 4; ++ck) {
-        uint4 o;
-        o.x = pack16x2(v[8 * ck + 0], v[8 * ck + 1], p.f16);
-        o.y = pack16x2(v[8 * ck + 2], v[8 * ck + 3], p.f16);
-        o.z = pack16x2(v[8 * ck + 4], v[8 * ck + 5], p.f16);
-        o.w = pack16x2(v[8 * ck + 6], v[8 * ck + 7], p.f16);
-        *reinterpret_cast<uint4*>(prow + swz(r * 128 + (4 * h + ck) * 16, 7)) = o;
-      }
-      fence_proxy_async_smem();
+      tmem_st16_b32(p_addr, pk);
+      tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[q * 2 + h]);
+      if (j + 1 < nt) {
+        mbar_wait(&s_full[q * 2 + (buf ^ 1)], ((j + 1) >> 1) & 1, 37);
+        tc_fence_after();
+        tmem_ld32_nowait(lane_addr + (q * 2 + (buf ^ 1)) * kTcBN + 32 * h, v);
+        tmem_wait_ld();
+        tmem_ld32_acquire(v);
+      }
     }
     // ---- merge the two halves of every row and write the output
     mx_sh[(q * 2 + h) * 128 + r] = m;
@@ -609,15 +642,15 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
         __nv_bfloat16* yp = yb + (long long)(t * p.alpha + rep) * p.ysT + c0;
         if (vec_ok) {
           uint4 pk;
-          pk.x = pack16x2(o[0], o[1], p.f16);
-          pk.y = pack16x2(o[2], o[3], p.f16);
-          pk.z = pack16x2(o[4], o[5], p.f16);
-          pk.w = pack16x2(o[6], o[7], p.f16);
+          pk.x = pack16x2(o[0], o[1], F16);
+          pk.y = pack16x2(o[2], o[3], F16);
+          pk.z = pack16x2(o[4], o[5], F16);
+          pk.w = pack16x2(o[6], o[7], F16);
           *reinterpret_cast<uint4*>(yp) = pk;
         } else {
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj)
-            if (c0 + jj < p.d) yp[jj] = f2h16(o[jj], p.f16);
+            if (c0 + jj < p.d) yp[jj] = f2h16(o[jj], F16);
         }
       }
     }
@@ -733,7 +766,8 @@ struct AttnTcOp : esf_op {
   int v2 = 0;
   int launch(cudaStream_t stream) override {
     if (v2) {
-      attn_tc_v2_kernel<<<grid, kV2Threads, smem_bytes, stream>>>(params);
+      if (params.f16) attn_tc_v2_kernel<true><<<grid, kV2Threads, smem_bytes, stream>>>(params);
+      else attn_tc_v2_kernel<false><<<grid, kV2Threads, smem_bytes, stream>>>(params);
       return check_launch("attn_tc_v2_kernel");
     }
     attn_tc_kernel<<<grid, kTcThreads, smem_bytes, stream>>>(params);
@@ -860,7 +894,8 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
   p.k_tile_bytes = kTcBN * g.KQ * 2;
   p.v_tile_bytes = g.DVp * 128;
   op->v2 = g.v2;
-  const int fixed = 1024 + 2 * (int)p.q_tile_bytes + 2 * 16384 + 512 + (g.v2 ? 2048 : 0);
+  // v1 streams P through 2 x 16 KB of shared memory; v2 keeps P in TMEM and needs 2 KB for the split-K maxima
+  const int fixed = 1024 + 2 * (int)p.q_tile_bytes + 512 + (g.v2 ? 2048 : 2 * 16384);
   int stages = (kTcSmemLimit - fixed) / (int)(p.k_tile_bytes + p.v_tile_bytes);
   p.stages = std::max(2, std::min(stages, kTcMaxStages));
   op->smem_bytes = fixed + p.stages * (int)(p.k_tile_bytes + p.v_tile_bytes);
@@ -879,7 +914,9 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
       if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(attn_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+        e = cudaFuncSetAttribute(attn_tc_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_tc_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
       if (e != cudaSuccess) rc = set_error(ESF_ERR_CUDA, "cudaFuncSetAttribute(attn_tc) failed: %s", cudaGetErrorString(e));
       else attr_set = true;
     }
