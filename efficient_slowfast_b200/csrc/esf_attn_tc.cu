@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
 // The loop is shaped to keep the MUFU pipe fed (the only roofline this kernel has):
 //   * the exponentials of a tile are computed speculatively with the CURRENT running maximum, interleaved with the
 //     tile-maximum reduction instead of after it; only when some row of the warp exceeds its maximum by more than tau
-//     (rare after the first tiles) the scores are re-read from TMEM and the tile is replayed with the raised maximum;
+//     the values are rescaled by exp2(m_old - m_new) -- or, if they may have overflowed (first tile), the scores are
+//     re-read from TMEM and the tile is replayed with the raised maximum;
 //   * P never touches shared memory: it is written to TMEM (tcgen05.st) and the P.V MMA takes its A operand from
 //     there, which removes the swizzled st.shared, the generic->async proxy fence and their address arithmetic;
 // Two things that were measured and did NOT help (so the kernel is issue/latency bound, not MUFU-throughput bound):
@@ -519,7 +520,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
     const uint32_t p_addr = lane_addr + kV2PCol + (q * 2 + h) * 16;
     const bool tail = (N % kTcBN) != 0;
     float m = -CUDART_INF_F;
-    constexpr float kTau = 5.545177f;
+    // 12 * ln 2: p = exp(s - m) stays <= 4096, inside FP16 and harmless in the FP32 sums; a larger window means
+    // fewer raise events and keeps small probabilities further away from the FP16 subnormals
+    constexpr float kTau = 8.317766f;
     float v[32];
     mbar_wait(&s_full[q * 2], 0, 37);
     tc_fence_after();
@@ -550,21 +553,29 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
       const bool raise = mx > m + kTau;
       const bool any_raise = __any_sync(0xffffffffu, raise);
       float f = 1.f;
-      if (any_raise) {  // replay the tile with the raised maxima (the scores are still in TMEM)
-        tmem_ld32_nowait(s_addr, v);
-        tmem_wait_ld();
-        tmem_ld32_acquire(v);
-        if (last_tail) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (j * kTcBN + 32 * h + i >= N) v[i] = -CUDART_INF_F;
-        }
+      if (any_raise) {
         const float m_new = raise ? mx : m;
-        f = raise ? fast_exp2((m - m_new) * kTcLog2e) : 1.f;
+        f = raise ? fast_exp2((m - m_new) * kTcLog2e) : 1.f;  // first tile: exp2(-inf) = 0
+        // exp2(x - m_new) = exp2(x - m) * f: the speculative values only need scaling, unless they may have
+        // overflowed FP32 (always on the first tile, where m = -inf): then the tile is replayed from TMEM
+        const bool big = raise && !((mx - m) * kTcLog2e < 100.f);
         m = m_new;
-        ms = (m == -CUDART_INF_F) ? 0.f : m * kTcLog2e;
+        if (__any_sync(0xffffffffu, big)) {
+          tmem_ld32_nowait(s_addr, v);
+          tmem_wait_ld();
+          tmem_ld32_acquire(v);
+          if (last_tail) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fast_exp2(fmaf(v[i], kTcLog2e, -ms));
+            for (int i = 0; i < 32; ++i)
+              if (j * kTcBN + 32 * h + i >= N) v[i] = -CUDART_INF_F;
+          }
+          ms = (m == -CUDART_INF_F) ? 0.f : m * kTcLog2e;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fast_exp2(fmaf(v[i], kTcLog2e, -ms));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= f;
+        }
       }
       tc_fence_before();
       __syncwarp();

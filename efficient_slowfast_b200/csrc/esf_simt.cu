@@ -345,7 +345,145 @@ __global__ void __launch_bounds__(kEcaThreads) eca_apply_kernel(const EcaParams 
   }
 }
 
+// 16-byte variants (C % 8 == 0, C / 8 a power of two <= 256, 16-byte addressable views): one thread = 8 channels of one
+// position; consecutive threads walk the channel groups of consecutive positions, i.e. contiguous memory.
+__device__ __forceinline__ void unpack8(const uint4& u, int f16, float* v) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack16x2(w[e], f16);
+    v[2 * e] = f.x, v[2 * e + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void eca_tmax8(const EcaParams& p, int b, int pos, int cg, float* m) {
+  const int w = pos % p.x.W;
+  const int r = pos / p.x.W;
+  const int h = r % p.x.H;
+  const int tp = r / p.x.H;
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + voff(p.x, b, tp * p.alpha, h, w) + cg * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -CUDART_INF_F;
+  for (int a = 0; a < p.alpha; ++a) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + a * p.x.sT)), p.x.f16, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+  }
+}
+
+__global__ void __launch_bounds__(kEcaThreads) eca_partial_vec_kernel(const EcaParams p) {
+  __shared__ float red[kEcaThreads][9];
+  const int C = p.x.C, cgs = C >> 3;
+  const int b = blockIdx.y;
+  const int npos = (p.x.T / p.alpha) * p.x.H * p.x.W;
+  const int chunk = (npos + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * chunk, p1 = min(npos, p0 + chunk);
+  const int cg = threadIdx.x & (cgs - 1);          // kEcaThreads % cgs == 0: a thread keeps its channel group
+  const int lanes = kEcaThreads / cgs;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int pos = p0 + threadIdx.x / cgs; pos < p1; pos += lanes) {
+    float m[8];
+    eca_tmax8(p, b, pos, cg, m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += m[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < C) {
+    const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float t = 0.f;
+    for (int i = 0; i < lanes; ++i) t += red[i * cgs + g][j];
+    p.partial[((long long)b * gridDim.x + blockIdx.x) * C + threadIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kEcaThreads) eca_apply_vec_kernel(const EcaParams p, int nblk) {
+  extern __shared__ float sm[];  // mean[C], mul[C], shift[C]
+  const int C = p.x.C, cgs = C >> 3;
+  float* mean = sm;
+  float* mul = sm + C;
+  float* shift = sm + 2 * C;
+  const int b = blockIdx.y;
+  const int npos = (p.x.T / p.alpha) * p.x.H * p.x.W;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int i = 0; i < nblk; ++i) t += p.partial[((long long)b * nblk + i) * C + c];
+    mean[c] = t / (float)npos;
+    shift[c] = __ldg(p.bn_shift + c);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    const int half = (p.eca_k - 1) / 2;
+    for (int j = 0; j < p.eca_k; ++j) {
+      const int cc = c + j - half;
+      if (cc >= 0 && cc < C) a = fmaf(__ldg(p.eca_w + j), mean[cc], a);
+    }
+    const float sgm = 1.f / (1.f + __expf(-a));
+    mul[c] = sgm * __ldg(p.bn_scale + c);
+  }
+  __syncthreads();
+  const int chunk = (npos + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * chunk, p1 = min(npos, p0 + chunk);
+  const int cg = threadIdx.x & (cgs - 1);
+  const int lanes = kEcaThreads / cgs;
+  float ml[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ml[j] = mul[cg * 8 + j], sh[j] = shift[cg * 8 + j];
+  for (int pos = p0 + threadIdx.x / cgs; pos < p1; pos += lanes) {
+    float m[8];
+    eca_tmax8(p, b, pos, cg, m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(fmaf(m[j], ml[j], sh[j]), 0.f);
+    const int w = pos % p.x.W;
+    const int r = pos / p.x.W;
+    const int h = r % p.x.H;
+    const int tp = r / p.x.H;
+    uint4 o;
+    o.x = pack16x2(m[0], m[1], p.y.f16), o.y = pack16x2(m[2], m[3], p.y.f16);
+    o.z = pack16x2(m[4], m[5], p.y.f16), o.w = pack16x2(m[6], m[7], p.y.f16);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + voff(p.y, b, tp, h, w) + cg * 8) = o;
+  }
+}
+
+static bool vec8_ok(const View& v) {
+  return (reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && v.sB % 8 == 0 && v.sT % 8 == 0 && v.sH % 8 == 0 && v.sW % 8 == 0;
+}
+
 // ------------------------------------------------------------------------------------------- head
+// 16-byte variant of head_pool_kernel: block = (clip, up to 256 channels), thread = 8 channels x a strided set of positions
+__global__ void __launch_bounds__(256) head_pool_vec_kernel(const View x, float* feat, int feat_stride, int feat_off) {
+  __shared__ float red[256][9];
+  const int b = blockIdx.y;
+  const int cgs_total = x.C >> 3;
+  const int cgs = min(cgs_total - blockIdx.x * 32, 32);   // channel groups of this block (power of two by construction)
+  const int cg = threadIdx.x % cgs, l = threadIdx.x / cgs, lanes = 256 / cgs;
+  const int npos = x.T * x.H * x.W;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int pos = l; pos < npos; pos += lanes) {
+    const int w = pos % x.W;
+    const int r = pos / x.W;
+    const int h = r % x.H;
+    const int t = r / x.H;
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x.ptr) + voff(x, b, t, h, w) +
+                                                 (blockIdx.x * 32 + cg) * 8)),
+            x.f16, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < cgs * 8) {
+    const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float t = 0.f;
+    for (int i = 0; i < lanes; ++i) t += red[i * cgs + g][j];
+    feat[(long long)b * feat_stride + feat_off + blockIdx.x * 256 + threadIdx.x] = t / (float)npos;
+  }
+}
+
 // feat[b][c] = mean over (T,H,W) of x[b,:,:,:,c]; one block per (clip, 64-channel group)
 __global__ void __launch_bounds__(256) head_pool_kernel(const View x, float* feat, int feat_stride, int feat_off) {
   __shared__ float red[4][64];
@@ -420,6 +558,69 @@ __global__ void __launch_bounds__(256) head_fc_kernel(const float* feat, int Cin
       out[(long long)b * out_stride + k] = v;
     }
   }
+}
+
+// Tiled variant for batches: block = 8 classes (one per warp) x 8 clips; every weight element is loaded once per block
+// and reused for the 8 clips.  Writes act(logit) for the pointwise activations, raw logits for softmax (act 1), which
+// head_softmax_kernel then normalises in place.
+__global__ void __launch_bounds__(256) head_fc_tiled_kernel(const float* __restrict__ feat, int B, int Cin, int feat_stride,
+                                                            const float* __restrict__ w, const float* __restrict__ bias,
+                                                            int K, int act, float* out, int out_stride) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + warp;
+  const int b0 = blockIdx.y * 8;
+  if (k >= K) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float* wr = w + (long long)k * Cin;
+  for (int c = lane; c < Cin; c += 32) {
+    const float wv = __ldg(wr + c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (b0 + i < B) acc[i] = fmaf(__ldg(feat + (long long)(b0 + i) * feat_stride + c), wv, acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  }
+  if (lane == 0) {
+    const float bk = __ldg(bias + k);
+    for (int i = 0; i < 8 && b0 + i < B; ++i) {
+      float v = acc[i] + bk;
+      if (act == 2) v = fmaxf(v, 0.f);
+      else if (act == 3) v = 1.f / (1.f + expf(-v));
+      else if (act == 4) v = fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+      out[(long long)(b0 + i) * out_stride + k] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) head_softmax_kernel(float* out, int K, int out_stride) {
+  __shared__ float red[8];
+  float* row = out + (long long)blockIdx.x * out_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float m = -CUDART_INF_F;
+  for (int k = threadIdx.x; k < K; k += 256) m = fmaxf(m, row[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int k = threadIdx.x; k < K; k += 256) {
+    const float e = expf(row[k] - m);
+    row[k] = e;
+    s += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < 8; ++i) s += red[i];
+  for (int k = threadIdx.x; k < K; k += 256) row[k] = row[k] / s;
 }
 
 // ------------------------------------------------------------------------------------------- channel plumbing
@@ -590,6 +791,15 @@ extern "C" int esf_eca_fuse(const esf_view* x_fast, int32_t alpha, const float* 
   dim3 grid(nblk, x_fast->B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int cw = std::min(x_fast->C, kEcaThreads);
+  const int cgs = x_fast->C / 8;
+  if (x_fast->C % 8 == 0 && cgs <= 32 && (cgs & (cgs - 1)) == 0 && vec8_ok(p.x) && vec8_ok(p.y) &&
+      npos < (1LL << 31)) {
+    eca_partial_vec_kernel<<<grid, kEcaThreads, 0, s>>>(p);
+    int rc = check_launch("eca_partial_vec_kernel");
+    if (rc != ESF_OK) return rc;
+    eca_apply_vec_kernel<<<grid, kEcaThreads, 3 * x_fast->C * sizeof(float), s>>>(p, nblk);
+    return check_launch("eca_apply_vec_kernel");
+  }
   eca_partial_kernel<<<grid, kEcaThreads, (kEcaThreads / cw) * cw * sizeof(float), s>>>(p);
   int rc = check_launch("eca_partial_kernel");
   if (rc != ESF_OK) return rc;
@@ -602,12 +812,19 @@ extern "C" int esf_head_pool(const esf_view* x0, const esf_view* x1, float* feat
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int c1 = (x1 && x1->ptr) ? x1->C : 0;
   const int stride = x0->C + c1;
-  head_pool_kernel<<<dim3(cdiv(x0->C, 64), x0->B), 256, 0, s>>>(to_view(x0), feat, stride, 0);
-  int rc = check_launch("head_pool_kernel");
+  auto pool_one = [&](const esf_view* x, int off) {
+    const View v = to_view(x);
+    const int cgs = x->C / 8, last = cgs % 32;   // channel groups in the last block must divide 256 threads evenly
+    if (x->C % 8 == 0 && (last & (last - 1)) == 0 && vec8_ok(v) && (long long)x->T * x->H * x->W < (1LL << 31))
+      head_pool_vec_kernel<<<dim3(cdiv(cgs, 32), x->B), 256, 0, s>>>(v, feat, stride, off);
+    else
+      head_pool_kernel<<<dim3(cdiv(x->C, 64), x->B), 256, 0, s>>>(v, feat, stride, off);
+    return check_launch("head_pool_kernel");
+  };
+  int rc = pool_one(x0, 0);
   if (rc != ESF_OK || c1 == 0) return rc;
   ESF_CHECK_ARG(view_ok(x1) && x1->B == x0->B, "esf_head_pool: bad second pathway view");
-  head_pool_kernel<<<dim3(cdiv(x1->C, 64), x1->B), 256, 0, s>>>(to_view(x1), feat, stride, x0->C);
-  return check_launch("head_pool_kernel");
+  return pool_one(x1, x0->C);
 }
 
 extern "C" int esf_head_fc(const float* feat, int32_t B, int32_t Cin, int32_t feat_stride, const float* w,
@@ -615,8 +832,16 @@ extern "C" int esf_head_fc(const float* feat, int32_t B, int32_t Cin, int32_t fe
                            void* stream) {
   ESF_CHECK_ARG(feat && w && bias && out && B > 0 && Cin > 0 && num_classes > 0, "esf_head_fc: null/bad argument");
   const size_t smem = (size_t)(Cin + num_classes) * sizeof(float);
-  ESF_CHECK_ARG(smem <= 48 * 1024, "esf_head_fc: Cin + num_classes too large for one block");
   ESF_CHECK_ARG(feat_stride >= Cin && out_stride >= num_classes, "esf_head_fc: strides smaller than the row lengths");
+  if (B >= 8 || smem > 48 * 1024) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    head_fc_tiled_kernel<<<dim3(cdiv(num_classes, 8), cdiv(B, 8)), 256, 0, s>>>(feat, B, Cin, feat_stride, w, bias,
+                                                                                 num_classes, act, out, out_stride);
+    int rc = check_launch("head_fc_tiled_kernel");
+    if (rc != ESF_OK || act != 1) return rc;
+    head_softmax_kernel<<<B, 256, 0, s>>>(out, num_classes, out_stride);
+    return check_launch("head_softmax_kernel");
+  }
   head_fc_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(feat, Cin, feat_stride, w, bias, num_classes, act,
                                                                       out, out_stride);
   return check_launch("head_fc_kernel");

@@ -120,6 +120,13 @@ def wfold_block(x, y, res, w_shape, stride, padding, dilation):
     return best if best >= 2 else 0     # a block of one column is the plain implicit GEMM
 
 
+def head_fc_launches(B, cin, K, act):
+    """Kernel launches of one esf_head_fc call: the tiled kernel (B >= 8, or rows too long for one block) applies the
+    class softmax in a second, tiny kernel."""
+    tiled = B >= 8 or (cin + K) * 4 > 48 * 1024
+    return 2 if (tiled and act == rt.HEAD_SOFTMAX) else 1
+
+
 class Plan:
     """Ordered kernel launches + every tensor they touch.  `eager` ops read the caller's input tensors and are
     launched on every forward; `graph` ops only touch plan-owned memory and are replayed from one CUDA graph."""
@@ -427,7 +434,8 @@ class Plan:
                                      "esf_head_pool"), "head_pool", "", nbytes=self._nbytes(*xs), launches=len(xs))
         self._add(lambda s: rt.check(
             L.esf_head_fc(feat.data_ptr(), B, cin, cin, w.data_ptr(), b.data_ptr(), K, act, out.data_ptr(), K, s),
-            "esf_head_fc"), "head_fc", "", flops=2.0 * B * cin * K, nbytes=self._nbytes(feat, w, out))
+            "esf_head_fc"), "head_fc", "", flops=2.0 * B * cin * K, nbytes=self._nbytes(feat, w, out),
+            launches=head_fc_launches(B, cin, K, act))
         self.out = out
         return out
 
@@ -444,7 +452,8 @@ class Plan:
         self._add(lambda s: rt.check(L.esf_head_pool(ctypes.byref(xv), ctypes.byref(nv), feat.data_ptr(), s),
                                      "esf_head_pool"), "head_pool", "", nbytes=self._nbytes(x))
         self._add(lambda s: rt.check(L.esf_head_fc(feat.data_ptr(), B, C, C, w.data_ptr(), b.data_ptr(), K, act,
-                                                   out.data_ptr(), out_stride, s), "esf_head_fc"), "head_fc", "")
+                                                   out.data_ptr(), out_stride, s), "esf_head_fc"), "head_fc", "",
+                  launches=head_fc_launches(B, C, K, act))
 
     def fc(self, feat, weight, bias, act):
         """out = act(feat @ weight^T + bias) on FP32 rows (final classifier of the GhostNet head)."""
@@ -455,7 +464,8 @@ class Plan:
         self.keep += [out, feat]
         L = rt.lib()
         self._add(lambda s: rt.check(L.esf_head_fc(feat.data_ptr(), B, cin, cin, w.data_ptr(), b.data_ptr(), K, act,
-                                                   out.data_ptr(), K, s), "esf_head_fc"), "head_fc", "")
+                                                   out.data_ptr(), K, s), "esf_head_fc"), "head_fc", "",
+                  launches=head_fc_launches(B, cin, K, act))
         self.out = out
         return out
 
