@@ -7,8 +7,9 @@ from .build import MODEL_REGISTRY, build_model  # noqa: F401
 from .config import (CfgNode, get_cfg, slowfast_4x16_r50_cfg, slowfast_dual_8x8_r50_cfg,  # noqa: F401
                      slowfast_ghostnet_cfg, slowfast_mobilenetv2_cfg, slowfast_shufflenet_cfg,
                      slowfast_shufflenetv2_cfg)
+from .pipeline import ClipStream  # noqa: F401
 from . import nets_resnet  # noqa: F401  (registers SlowFast, SlowFastDualAttention)
 from . import nets_efficient  # noqa: F401  (registers SlowFastShuffleNetV2, SlowFastShuffleNet, ...)
 
-__all__ = ["MODEL_REGISTRY", "build_model", "get_cfg", "CfgNode", "slowfast_4x16_r50_cfg",
+__all__ = ["MODEL_REGISTRY", "build_model", "get_cfg", "CfgNode", "ClipStream", "slowfast_4x16_r50_cfg",
            "slowfast_dual_8x8_r50_cfg"]

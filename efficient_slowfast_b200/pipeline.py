@@ -1,0 +1,76 @@
+"""Host -> device -> host streaming of clip batches around the forward path.
+
+The reference's test loop (SlowFast/tools/test_net.py:58-110) is strictly serial per batch: `inputs[i].cuda()`,
+`model(inputs)`, `all_gather`, `.cpu()`.  A batch of 64 clips is 1.5 GB of FP32 pixels, i.e. ~30 ms of PCIe time next to
+a ~45 ms forward, so serialising the two wastes 40 % of the wall clock.  `ClipStream` keeps the same per-batch contract
+(every batch is copied from pinned host memory, run through `model.forward`, and its predictions copied back to the
+host) but double-buffers the device staging tensors and issues the H2D copy of batch i+1 on a copy stream while batch i
+computes.  Results are returned in submission order.
+
+    stream = ClipStream(model, shapes)            # shapes of [slow, fast]
+    for host_inputs in loader:                    # pinned FP32 tensors
+        done = stream.submit(host_inputs)         # -> (index, preds) of an EARLIER batch, or None while filling
+    for index, preds in stream.flush(): ...
+"""
+import torch
+
+from . import distributed as esf_dist
+from . import runtime as rt
+
+
+class ClipStream:
+    def __init__(self, model, shapes, device=None, depth=2, gather=False):
+        """`depth` staging slots (>= 2 overlaps copy and compute); `gather=True` all-gathers the predictions over the
+        process group before the D2H copy, like the reference's test loop."""
+        device = torch.device(device) if device is not None else next(model.parameters()).device
+        if device.type != "cuda":
+            raise rt.EsfError("ClipStream needs a CUDA device; there is no CPU fallback")
+        assert depth >= 1
+        self.model, self.device, self.depth, self.gather = model, device, depth, gather
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.stage = [[torch.empty(tuple(s), dtype=torch.float32, device=device) for s in shapes] for _ in range(depth)]
+        self.ready = [torch.cuda.Event() for _ in range(depth)]     # H2D of the slot finished
+        self.consumed = [torch.cuda.Event() for _ in range(depth)]  # forward no longer reads the slot
+        self.done = [torch.cuda.Event() for _ in range(depth)]      # predictions of the slot are on the host
+        self.host_out = [None] * depth
+        self.pending = []   # (index, slot) in flight, oldest first
+        self.n = 0
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.stage[0])
+
+    def submit(self, host_inputs):
+        """Queue one batch (list of pinned host tensors, reference order [slow, fast]).  Never blocks on the batch just
+        queued; when all staging slots are busy it first waits for the oldest batch and returns its (index, preds)."""
+        finished = None
+        if len(self.pending) == self.depth:
+            finished = self._pop()
+        slot = self.n % self.depth
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[slot])
+            for h, d in zip(host_inputs, self.stage[slot]):
+                d.copy_(h, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+        cur.wait_event(self.ready[slot])
+        out = self.model(self.stage[slot])
+        self.consumed[slot].record(cur)
+        if self.gather:
+            out = esf_dist.all_gather([out])[0]
+        if self.host_out[slot] is None or self.host_out[slot].shape != out.shape:
+            self.host_out[slot] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        self.host_out[slot].copy_(out, non_blocking=True)
+        self.done[slot].record(cur)
+        self.pending.append((self.n, slot))
+        self.n += 1
+        return finished
+
+    def _pop(self):
+        index, slot = self.pending.pop(0)
+        self.done[slot].synchronize()
+        return index, self.host_out[slot].clone()
+
+    def flush(self):
+        """Wait for every batch still in flight; returns their (index, preds) in submission order."""
+        out = []
+        while self.pending:
+            out.append(self._pop())
+        return out

@@ -142,3 +142,30 @@ def test_pathway_count_and_shape_checks(esf_lib):
         model([torch.zeros(1, 3, 4, 64, 64, device="cuda")])
     with pytest.raises(AssertionError):
         model([torch.zeros(1, 3, 8, 64, 64, device="cuda"), torch.zeros(1, 3, 32, 64, 64, device="cuda")])
+
+
+def test_clip_stream_matches_direct_forward(esf_lib):
+    """ClipStream (pinned host -> H2D on a copy stream -> forward -> D2H, double buffered) returns, in submission
+    order, exactly what a direct forward of each batch returns."""
+    import efficient_slowfast_b200 as esf
+
+    cfg, model, gold, _ = _run("slowfast_r50", "s64")
+    base = helpers.case_inputs("slowfast_r50", "s64")
+    batches = []
+    for i in range(5):
+        fast = torch.roll(base[1], shifts=i, dims=2) * (1.0 + 0.1 * i)
+        xs = recipe.pack_pathway_output(fast, cfg.SLOWFAST.ALPHA)
+        batches.append([t.contiguous().pin_memory() for t in xs])
+    with torch.no_grad():
+        want = [model([t.cuda() for t in xs]).cpu() for xs in batches]
+        stream = esf.ClipStream(model, [tuple(t.shape) for t in batches[0]], depth=2)
+        got = []
+        for xs in batches:
+            r = stream.submit(xs)
+            if r is not None:
+                got.append(r)
+        got += stream.flush()
+    assert [i for i, _ in got] == list(range(5))
+    for (_, y), w in zip(got, want):
+        assert torch.equal(y, w)
+    assert not torch.equal(want[0], want[3])
