@@ -286,7 +286,13 @@ def run_gpu(args):
     else:
         ach = top["bytes"] / (top_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"]}
-    roof.update({"traffic": None, "kernel": "%s %s" % (top["kind"], top["label"]), "ms": top_ms,
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    # `ncu --set full` capture of this command at the default workload (profiles/r1_ncu_bench_attention_d32_b64.md)
+    traffic = None
+    if top["kind"] == "attention" and top["label"] == "N=25088 d=32" and B == 64:
+        traffic = 772309504 + 389359104
+    roof.update({"traffic": traffic, "algorithmic_bytes": top["bytes"],
+                 "kernel": "%s %s" % (top["kind"], top["label"]), "ms": top_ms,
                  "share_of_step": top_ms / total_ms, "peak_source": pk["_source"]})
     if top["exps"]:
         sm_mhz = (clocks or {}).get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)
