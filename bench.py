@@ -86,10 +86,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def bench_cfg(args):
-    import efficient_slowfast_b200 as esf
+# --model -> golden case that carries its calibrated BN statistics (tests/golden/recipe.py CASES).  The default is the
+# headline workload; the others are BASELINE.json's remaining configs, benchmarked with explicit --batch/--frames/--crop.
+MODEL_CASES = {
+    "SlowFastDualAttention": "dual_r50", "SlowFast": "slowfast_r50", "SlowFastShuffleNetV2": "shufflenetv2_w05",
+    "SlowFastShuffleNet": "shufflenet_w2g3", "SlowFastMoibleNetV2": "mobilenetv2_w1", "SlowFastGhostNet": "ghostnet_w1",
+}
 
-    cfg = esf.slowfast_dual_8x8_r50_cfg() if args.model == "SlowFastDualAttention" else esf.slowfast_4x16_r50_cfg()
+
+def bench_cfg(args):
+    import helpers
+
+    cfg = helpers.case_cfg(MODEL_CASES[args.model])
+    cfg.NUM_GPUS = 1
     cfg.DATA.CROP_SIZE = args.crop
     cfg.DATA.NUM_FRAMES = args.frames
     cfg.ESF.PRECISION = args.precision
@@ -103,7 +112,7 @@ def build_weights(cfg):
     import recipe
     import efficient_slowfast_b200 as esf
 
-    name = "dual_r50" if cfg.MODEL.MODEL_NAME == "SlowFastDualAttention" else "slowfast_r50"
+    name = MODEL_CASES[cfg.MODEL.MODEL_NAME]
     c = cfg.clone()
     c.NUM_GPUS = 0
     torch.manual_seed(0)
@@ -114,9 +123,13 @@ def build_weights(cfg):
     return model.eval()
 
 
+def metric_name(args):
+    return METRIC if args.model == "SlowFastDualAttention" else "clips/sec %s fwd" % args.model
+
+
 def workload_name(args):
-    return "%s R50 %dx(%d|%d)x%dx%d fwd, batch %d per GPU, synthetic N(0,1) clips" % (
-        args.model, args.batch, args.frames // args.alpha, args.frames, args.crop, args.crop, args.batch)
+    return "%s %dx(%d|%d)x%dx%d fwd, batch %d per GPU, synthetic N(0,1) clips" % (
+        args.model + (" R50" if args.model in ("SlowFast", "SlowFastDualAttention") else ""), args.batch, args.frames // args.alpha, args.frames, args.crop, args.crop, args.batch)
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -150,7 +163,7 @@ def run_reference(args):
     cores = torch.get_num_threads()
     sample = "%d clip(s) of the workload per step (same shape, CPU FP32 oracle port of the reference forward)" % clips
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "cpu_sample_clips_per_step": clips},
@@ -320,7 +333,7 @@ def run_gpu(args):
                "sample": "%d clip(s) of the same workload, 1 warm-up + 1 timed oracle forward (%.1f s)" % (
                    args.cpu_clips, csec)}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": str(cfg.ESF.PRECISION), "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": world * B, "parallelism": "dp%d" % world,
@@ -346,7 +359,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="SlowFastDualAttention", choices=["SlowFastDualAttention", "SlowFast"])
+    ap.add_argument("--model", default="SlowFastDualAttention", choices=sorted(MODEL_CASES))
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--frames", type=int, default=32)
     ap.add_argument("--crop", type=int, default=224)
@@ -359,7 +372,7 @@ def main():
     ap.add_argument("--profile-mode", action="store_true",
                     help="for ncu: eager launches (no CUDA graph), 1 warm-up + --steps steps, nothing else")
     args = ap.parse_args()
-    args.alpha = 4 if args.model == "SlowFastDualAttention" else 8
+    args.alpha = 8 if args.model == "SlowFast" else 4
     if args.impl == "reference":
         run_reference(args)
     else:

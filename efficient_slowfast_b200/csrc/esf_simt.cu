@@ -177,6 +177,152 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectParams p) 
   }
 }
 
+// Depthwise k x k x 3 convolution (groups == C), the HBM-bound half of the efficient backbones.  One thread = VEC
+// channels x OW consecutive output columns of one (b, t, h) row: every input column it loads is reused by up to three
+// kw taps and OW outputs, loads are VEC * 2 bytes wide (16 B when C % 8 == 0), and consecutive threads walk the channel
+// groups, i.e. contiguous memory.  A block owns a fixed range of <= 32 channel groups whose weights and bias are staged
+// in shared memory transposed to [tap][channel].
+template <int VEC>
+__device__ __forceinline__ void load_vec(const __nv_bfloat16* ptr, int f16, float* v) {
+  if constexpr (VEC == 8) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(ptr));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack16x2(w[e], f16);
+      v[2 * e] = f.x, v[2 * e + 1] = f.y;
+    }
+  } else if constexpr (VEC == 4) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(ptr));
+    const float2 a = unpack16x2(u.x, f16), b = unpack16x2(u.y, f16);
+    v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+  } else if constexpr (VEC == 2) {
+    const float2 a = unpack16x2(__ldg(reinterpret_cast<const uint32_t*>(ptr)), f16);
+    v[0] = a.x, v[1] = a.y;
+  } else {
+    v[0] = h162f(*ptr, f16);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void store_vec(__nv_bfloat16* ptr, int f16, const float* v) {
+  if constexpr (VEC == 8) {
+    uint4 o;
+    o.x = pack16x2(v[0], v[1], f16), o.y = pack16x2(v[2], v[3], f16);
+    o.z = pack16x2(v[4], v[5], f16), o.w = pack16x2(v[6], v[7], f16);
+    *reinterpret_cast<uint4*>(ptr) = o;
+  } else if constexpr (VEC == 4) {
+    *reinterpret_cast<uint2*>(ptr) = make_uint2(pack16x2(v[0], v[1], f16), pack16x2(v[2], v[3], f16));
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<uint32_t*>(ptr) = pack16x2(v[0], v[1], f16);
+  } else {
+    *ptr = f2h16(v[0], f16);
+  }
+}
+
+constexpr int kDwCgPerBlock = 32;
+template <int VEC, int OW, int SW>
+__global__ void __launch_bounds__(256) dwconv_kernel(const DirectParams p) {
+  extern __shared__ float dw_sm[];  // w[taps][cb * VEC], bias[cb * VEC]
+  const int C = p.x.C, cgs = C / VEC;
+  const int cg0 = blockIdx.y * kDwCgPerBlock;
+  const int cb = min(cgs - cg0, kDwCgPerBlock);  // channel groups of this block
+  const int chb = cb * VEC;
+  const int taps = p.kT * p.kH * 3;
+  for (int i = threadIdx.x; i < taps * chb; i += blockDim.x) {
+    const int tap = i / chb, c = i - tap * chb;
+    dw_sm[i] = __ldg(p.w + (long long)(cg0 * VEC + c) * taps + tap);
+  }
+  float* bias_s = dw_sm + taps * chb;
+  for (int i = threadIdx.x; i < chb; i += blockDim.x) bias_s[i] = __ldg(p.bias + cg0 * VEC + i);
+  __syncthreads();
+  const int lanes = blockDim.x / cb;
+  const int cgl = threadIdx.x % cb, lane = threadIdx.x / cb;
+  if (lane >= lanes) return;
+  const int wblocks = (p.y.W + OW - 1) / OW;
+  const long long items = (long long)p.y.B * p.y.T * p.y.H * wblocks;
+  constexpr int NCOL = (OW - 1) * SW + 3;
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + (cg0 + cgl) * VEC;
+  __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + (cg0 + cgl) * VEC;
+  const float* ws = dw_sm + cgl * VEC;
+  for (long long it = (long long)blockIdx.x * lanes + lane; it < items; it += (long long)gridDim.x * lanes) {
+    const int wb = it % wblocks;
+    long long r = it / wblocks;
+    const int ho = r % p.y.H;
+    r /= p.y.H;
+    const int to = r % p.y.T;
+    const int b = r / p.y.T;
+    float acc[OW][VEC];
+#pragma unroll
+    for (int o = 0; o < OW; ++o)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[o][e] = bias_s[cgl * VEC + e];
+    const int wi0 = wb * OW * SW - p.pW;
+    for (int kt = 0; kt < p.kT; ++kt) {
+      const int ti = to * p.sT + kt - p.pT;
+      if (ti < 0 || ti >= p.x.T) continue;
+      for (int kh = 0; kh < p.kH; ++kh) {
+        const int hi = ho * p.sH + kh - p.pH;
+        if (hi < 0 || hi >= p.x.H) continue;
+        const float* wt = ws + ((kt * p.kH + kh) * 3) * chb;
+        float wv[3][VEC];
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) wv[kw][e] = wt[kw * chb + e];
+        const long long rowoff = voff(p.x, b, ti, hi, 0);
+#pragma unroll
+        for (int col = 0; col < NCOL; ++col) {
+          const int wi = wi0 + col;
+          if (wi < 0 || wi >= p.x.W) continue;
+          float xv[VEC];
+          load_vec<VEC>(xb + rowoff + wi * p.x.sW, p.x.f16, xv);
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            if ((col - kw) % SW == 0 && col - kw >= 0 && (col - kw) / SW < OW) {
+              const int o = (col - kw) / SW;
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) acc[o][e] = fmaf(xv[e], wv[kw][e], acc[o][e]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < OW; ++o) {
+      const int wo = wb * OW + o;
+      if (wo >= p.y.W) break;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[o][e] = apply_act(acc[o][e], p.act);
+      store_vec<VEC>(yb + voff(p.y, b, to, ho, wo), p.y.f16, acc[o]);
+    }
+  }
+}
+
+template <int VEC>
+static bool launch_dwconv(const DirectParams& p, cudaStream_t s) {
+  const int cgs = p.x.C / VEC;
+  const int cb = std::min(cgs, kDwCgPerBlock);
+  const int taps = p.kT * p.kH * 3;
+  const size_t smem = (size_t)(taps + 1) * kDwCgPerBlock * VEC * sizeof(float);
+  if (smem > 48 * 1024) return false;
+  const int lanes = 256 / cb;
+  if (p.sW == 1) {
+    const long long items = (long long)p.y.B * p.y.T * p.y.H * cdiv(p.y.W, 4);
+    dim3 grid((unsigned)std::min<long long>(cdiv(items, lanes), 148 * 64), cdiv(cgs, kDwCgPerBlock));
+    dwconv_kernel<VEC, 4, 1><<<grid, 256, smem, s>>>(p);
+  } else {
+    const long long items = (long long)p.y.B * p.y.T * p.y.H * cdiv(p.y.W, 2);
+    dim3 grid((unsigned)std::min<long long>(cdiv(items, lanes), 148 * 64), cdiv(cgs, kDwCgPerBlock));
+    dwconv_kernel<VEC, 2, 2><<<grid, 256, smem, s>>>(p);
+  }
+  return true;
+}
+
+static bool vec_ok(const View& v, int vec) {
+  return reinterpret_cast<uintptr_t>(v.ptr) % (2 * vec) == 0 && v.sB % vec == 0 && v.sT % vec == 0 && v.sH % vec == 0 &&
+         v.sW % vec == 0;
+}
+
 // ------------------------------------------------------------------------------------------- pooling
 struct PoolParams {
   View x, y;
@@ -745,8 +891,20 @@ extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {
   p.kT = d->kT, p.kH = d->kH, p.kW = d->kW, p.sT = d->sT, p.sH = d->sH, p.sW = d->sW;
   p.pT = d->pT, p.pH = d->pH, p.pW = d->pW, p.dT = d->dT, p.dH = d->dH, p.dW = d->dW;
   p.groups = d->groups, p.act = d->act, p.out_f32 = d->out_dtype == ESF_F32;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p.groups == p.x.C && p.y.C == p.x.C && d->kW == 3 && d->dT == 1 && d->dH == 1 && d->dW == 1 &&
+      (d->sW == 1 || d->sW == 2) && !p.has_res && !p.out_f32 && is16(d->x.dtype) && d->y.dtype == d->x.dtype &&
+      (long long)p.y.B * p.y.T * p.y.H * p.y.W < (1LL << 40)) {
+    bool done = false;
+    const int C = p.x.C;
+    if (C % 8 == 0 && vec_ok(p.x, 8) && vec_ok(p.y, 8)) done = launch_dwconv<8>(p, s);
+    else if (C % 4 == 0 && vec_ok(p.x, 4) && vec_ok(p.y, 4)) done = launch_dwconv<4>(p, s);
+    else if (C % 2 == 0 && vec_ok(p.x, 2) && vec_ok(p.y, 2)) done = launch_dwconv<2>(p, s);
+    else done = launch_dwconv<1>(p, s);
+    if (done) return check_launch("dwconv_kernel");
+  }
   const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W * p.y.C;
-  conv_direct_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  conv_direct_kernel<<<grid_for(total, 256), 256, 0, s>>>(p);
   return check_launch("conv_direct_kernel");
 }
 

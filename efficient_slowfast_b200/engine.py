@@ -149,8 +149,15 @@ class Plan:
 
     # ---------------------------------------------------------------- memory
     def act(self, B, T, H, W, C, name=None, dtype=None):
-        t = torch.empty((B, T, H, W, C), dtype=dtype or self.adt, device=self.device)
+        dtype = dtype or self.adt
+        # 16-bit activations with C >= 8 get a channel pitch that is a multiple of 8 elements (16 bytes), so that every
+        # buffer -- also with C = 27, 36, 180, 540 ... of the efficient backbones -- is addressable by TMA and by
+        # 16-byte vector accesses; the logical tensor is the [..., :C] view
+        Cp = C if (dtype != self.adt or C < 8) else (C + 7) // 8 * 8
+        t = torch.empty((B, T, H, W, Cp), dtype=dtype, device=self.device)
         self.keep.append(t)
+        if Cp != C:
+            t = t[..., :C]
         if name:
             self.buffers[name] = t
         return t
@@ -225,7 +232,23 @@ class Plan:
             if wb:
                 return self.conv_wfold(x, y, w_folded, bias, wb, stride, padding, act, res)
             return self.conv_igemm(x, y, w_folded, bias, stride, padding, dilation, act, res, out_dtype)
-        return self.conv_direct(x, y, w_folded, bias, stride, padding, dilation, groups, act, res, out_dtype)
+        cout, cin_g = w_folded.shape[:2]
+        if (groups > 1 and cin_g % 8 == 0 and (cout // groups) % 8 == 0 and cin_g >= 16 and self._aligned(x)
+                and self._aligned(y) and self._aligned(res)):
+            # grouped dense conv (ShuffleNet's grouped 1x1x1): one implicit GEMM per group on channel slices
+            cout_g = cout // groups
+            for g in range(groups):
+                self.conv_igemm(x[..., g * cin_g:(g + 1) * cin_g], y[..., g * cout_g:(g + 1) * cout_g],
+                                w_folded[g * cout_g:(g + 1) * cout_g], bias[g * cout_g:(g + 1) * cout_g], stride,
+                                padding, dilation, act, None if res is None else res[..., g * cout_g:(g + 1) * cout_g],
+                                out_dtype)
+            return
+        self.conv_direct(x, y, w_folded, bias, stride, padding, dilation, groups, act, res, out_dtype)
+        why = [n for n, t in (("x", x), ("y", y), ("res", res)) if not self._aligned(t)]
+        self.meta[-1]["why_direct"] = ("groups=%d " % groups if groups != 1 else "") + \
+            ("cin<8 " if x.shape[4] < 8 else "") + ("unaligned " + ",".join(
+                "%s(off %d, strides %s)" % (n, (t.data_ptr() % 16) // 2, tuple(t.stride()[:4]))
+                for n, t in (("x", x), ("y", y), ("res", res)) if n in why) if why else "")
 
     def conv_direct(self, x, y, w_folded, bias, stride=(1, 1, 1), padding=(0, 0, 0), dilation=(1, 1, 1), groups=1,
                     act=rt.ACT_NONE, res=None, out_dtype=None):
@@ -239,7 +262,9 @@ class Plan:
         self.keep.append(d)
         L = rt.lib()
         m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
-        self._add(lambda s, d=d: rt.check(L.esf_conv_direct(ctypes.byref(d), s), "esf_conv_direct"), "conv_direct",
+        depthwise = groups == x.shape[4] == y.shape[4] and kw == 3
+        self._add(lambda s, d=d: rt.check(L.esf_conv_direct(ctypes.byref(d), s), "esf_conv_direct"),
+                  "dwconv" if depthwise else "conv_direct",
                   "%dx%dx%d g%d %d->%d" % (kt, kh, kw, groups, x.shape[4], y.shape[4]),
                   flops=2.0 * m * y.shape[4] * (x.shape[4] // groups) * kt * kh * kw,
                   nbytes=self._nbytes(x, y, res) + wd.numel() * 4)

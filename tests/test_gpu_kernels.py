@@ -186,6 +186,59 @@ def test_conv_direct_depthwise_and_grouped(esf_lib):
         assert err <= 1e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("C,k,s,shape", [
+    (144, (3, 3, 3), (1, 1, 1), (2, 4, 14, 14)), (24, (3, 3, 3), (1, 2, 2), (2, 4, 14, 14)),
+    (12, (3, 3, 3), (1, 1, 1), (1, 3, 10, 9)), (18, (3, 3, 3), (1, 2, 2), (1, 3, 11, 13)),
+    (27, (3, 3, 3), (1, 1, 1), (1, 2, 7, 6)), (48, (1, 3, 3), (1, 1, 1), (2, 2, 8, 8)),
+    (4, (3, 3, 3), (1, 1, 1), (1, 4, 12, 12)), (320, (3, 3, 3), (1, 2, 2), (1, 2, 7, 7)),
+    (40, (3, 3, 3), (2, 2, 2), (1, 4, 9, 9))])
+def test_depthwise_vector_kernel(esf_lib, C, k, s, shape, precision):
+    """Depthwise convs through Plan.conv: vector kernel (VEC 8/4/2/1 by channel count), padded channel pitch, slices."""
+    adt = rt.TORCH_DTYPE[precision]
+    g = torch.Generator().manual_seed(C)
+    B, T, H, W = shape
+    plan = Plan(DEV, precision)
+    x = plan.act(B, T, H, W, C)
+    x.copy_(_rand_act(g, B, T, H, W, C, dtype=adt))
+    w = torch.randn(C, 1, *k, generator=g) * 0.3
+    bias = torch.randn(C, generator=g) * 0.1
+    p = (k[0] // 2, 1, 1)
+    ref = F.conv3d(_to_ncdhw(x.cpu()), w, bias, s, p, 1, C).relu()
+    y = plan.act(*_to_ndhwc(ref).shape)
+    plan.conv(x, y, w.double(), bias.double(), stride=s, padding=p, groups=C, act=rt.ACT_RELU)
+    assert plan.meta[-1]["kind"] == "dwconv"
+    plan.launch_all()
+    torch.cuda.synchronize()
+    err = (_to_ncdhw(y.cpu()) - ref).abs().max().item()
+    assert err <= (2e-3 if precision == "fp16" else 1e-2) * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("cin,cout,groups", [(27, 162, 1), (180, 1080, 1), (540, 480, 1), (240, 480, 3), (1080, 960, 3),
+                                             (36, 216, 1), (120, 72, 3)])
+def test_pointwise_odd_channels_on_tensor_cores(esf_lib, cin, cout, groups):
+    """1x1x1 convs whose channel counts are not multiples of 8 (or are grouped) run on the implicit GEMM thanks to the
+    padded channel pitch / per-group slicing; residual + ReLU fused."""
+    g = torch.Generator().manual_seed(cin + cout)
+    B, T, H, W = 2, 4, 7, 7
+    plan = Plan(DEV, "fp16")
+    x = plan.act(B, T, H, W, cin)
+    x.copy_(_rand_act(g, B, T, H, W, cin, dtype=torch.float16))
+    res = plan.act(B, T, H, W, cout)
+    res.copy_(_rand_act(g, B, T, H, W, cout, dtype=torch.float16))
+    w = torch.randn(cout, cin // groups, 1, 1, 1, generator=g) * (2.0 / (cin // groups)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = (F.conv3d(_to_ncdhw(x.cpu()), w.half().float(), bias, groups=groups) + _to_ncdhw(res.cpu())).relu()
+    y = plan.act(B, T, H, W, cout)
+    plan.conv(x, y, w.double(), bias.double(), groups=groups, act=rt.ACT_RELU, res=res)
+    assert all(m["kind"] in ("conv_igemm", "conv_wfold") for m in plan.meta), [m["kind"] for m in plan.meta]
+    assert len(plan.meta) == groups
+    plan.launch_all()
+    torch.cuda.synchronize()
+    err = (_to_ncdhw(y.cpu()) - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item(), err
+
+
 @pytest.mark.parametrize("kt,cout", [(1, 64), (5, 8), (3, 6)])
 def test_stem_conv(esf_lib, kt, cout):
     g = torch.Generator().manual_seed(kt)
