@@ -219,15 +219,72 @@ __device__ __forceinline__ void store_vec(__nv_bfloat16* ptr, int f16, const flo
   }
 }
 
+// Pointwise (1x1x1, stride 1, dense) convolution with a tiny channel count on one side (C_in < 8 or C_out < 8: the
+// first fast-pathway layers of the efficient backbones, which the tensor-core GEMM cannot address).  One thread = one
+// position x one group of up to 8 output channels; the weights sit in shared memory as [c_in][c_out]; inputs are read
+// with the widest aligned vector, outputs written as one 16-byte store when the group is full and aligned.
+template <int VIN>
+__global__ void __launch_bounds__(256) pw_small_kernel(const DirectParams p, int vec_out) {
+  extern __shared__ float pw_sm[];  // w[cin][coutp], bias[coutp]
+  const int cin = p.x.C, cout = p.y.C, cogs = (cout + 7) / 8, coutp = cogs * 8;
+  for (int i = threadIdx.x; i < cin * coutp; i += blockDim.x) {
+    const int ci = i / coutp, co = i - ci * coutp;
+    pw_sm[i] = co < cout ? __ldg(p.w + (long long)co * cin + ci) : 0.f;
+  }
+  float* bias_s = pw_sm + cin * coutp;
+  for (int i = threadIdx.x; i < coutp; i += blockDim.x) bias_s[i] = i < cout ? __ldg(p.bias + i) : 0.f;
+  __syncthreads();
+  const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W * cogs;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cog = idx % cogs;
+    long long pos = idx / cogs;
+    const int w = pos % p.y.W;
+    pos /= p.y.W;
+    const int h = pos % p.y.H;
+    pos /= p.y.H;
+    const int t = pos % p.y.T;
+    const int b = pos / p.y.T;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias_s[cog * 8 + j];
+    const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + voff(p.x, b, t, h, w);
+    for (int c0 = 0; c0 < cin; c0 += VIN) {
+      float xv[VIN];
+      load_vec<VIN>(xr + c0, p.x.f16, xv);
+#pragma unroll
+      for (int e = 0; e < VIN; ++e) {
+        const float* wr = pw_sm + (c0 + e) * coutp + cog * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[e], wr[j], acc[j]);
+      }
+    }
+    const long long yo = voff(p.y, b, t, h, w) + cog * 8;
+    const int valid = min(8, cout - cog * 8);
+    if (p.has_res) {
+      const long long ro = voff(p.res, b, t, h, w) + cog * 8;
+      for (int j = 0; j < valid; ++j) acc[j] += ldbf(p.res, ro + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], p.act);
+    if (valid == 8 && vec_out) {
+      store_vec<8>(reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + yo, p.y.f16, acc);
+    } else {
+      for (int j = 0; j < valid; ++j) sth(p.y, yo + j, acc[j]);
+    }
+  }
+}
+
 constexpr int kDwCgPerBlock = 32;
-template <int VEC, int OW, int SW>
-__global__ void __launch_bounds__(256) dwconv_kernel(const DirectParams p) {
+constexpr int kDwTileT = 4, kDwTileH = 8;   // a block walks a (4 x 8)-row tile so the (kt, kh) re-reads hit its L1
+template <int VEC, int OW, int SW, int KW>
+__global__ void __launch_bounds__(256) dwconv_kernel(const DirectParams p, int res_vec) {
   extern __shared__ float dw_sm[];  // w[taps][cb * VEC], bias[cb * VEC]
   const int C = p.x.C, cgs = C / VEC;
   const int cg0 = blockIdx.y * kDwCgPerBlock;
   const int cb = min(cgs - cg0, kDwCgPerBlock);  // channel groups of this block
   const int chb = cb * VEC;
-  const int taps = p.kT * p.kH * 3;
+  const int taps = p.kT * p.kH * KW;
   for (int i = threadIdx.x; i < taps * chb; i += blockDim.x) {
     const int tap = i / chb, c = i - tap * chb;
     dw_sm[i] = __ldg(p.w + (long long)(cg0 * VEC + c) * taps + tap);
@@ -239,83 +296,108 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DirectParams p) {
   const int cgl = threadIdx.x % cb, lane = threadIdx.x / cb;
   if (lane >= lanes) return;
   const int wblocks = (p.y.W + OW - 1) / OW;
-  const long long items = (long long)p.y.B * p.y.T * p.y.H * wblocks;
-  constexpr int NCOL = (OW - 1) * SW + 3;
+  const int nth = (p.y.H + kDwTileH - 1) / kDwTileH, ntt = (p.y.T + kDwTileT - 1) / kDwTileT;
+  const long long tiles = (long long)p.y.B * ntt * nth;
+  constexpr int NCOL = (OW - 1) * SW + KW;
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + (cg0 + cgl) * VEC;
   __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + (cg0 + cgl) * VEC;
+  const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(p.res.ptr) + (cg0 + cgl) * VEC;
   const float* ws = dw_sm + cgl * VEC;
-  for (long long it = (long long)blockIdx.x * lanes + lane; it < items; it += (long long)gridDim.x * lanes) {
-    const int wb = it % wblocks;
-    long long r = it / wblocks;
-    const int ho = r % p.y.H;
-    r /= p.y.H;
-    const int to = r % p.y.T;
-    const int b = r / p.y.T;
-    float acc[OW][VEC];
+  const int per_tile = kDwTileT * kDwTileH * wblocks;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int th = tile % nth;
+    long long r = tile / nth;
+    const int tt = r % ntt;
+    const int b = r / ntt;
+    for (int item = lane; item < per_tile; item += lanes) {
+      const int wb = item % wblocks, row = item / wblocks;
+      const int to = tt * kDwTileT + row / kDwTileH, ho = th * kDwTileH + row % kDwTileH;
+      if (to >= p.y.T || ho >= p.y.H) continue;
+      const int wi0 = wb * OW * SW - p.pW;
+      float acc[OW][VEC];
 #pragma unroll
-    for (int o = 0; o < OW; ++o)
+      for (int o = 0; o < OW; ++o)
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) acc[o][e] = bias_s[cgl * VEC + e];
-    const int wi0 = wb * OW * SW - p.pW;
-    for (int kt = 0; kt < p.kT; ++kt) {
-      const int ti = to * p.sT + kt - p.pT;
-      if (ti < 0 || ti >= p.x.T) continue;
-      for (int kh = 0; kh < p.kH; ++kh) {
-        const int hi = ho * p.sH + kh - p.pH;
-        if (hi < 0 || hi >= p.x.H) continue;
-        const float* wt = ws + ((kt * p.kH + kh) * 3) * chb;
-        float wv[3][VEC];
+        for (int e = 0; e < VEC; ++e) acc[o][e] = bias_s[cgl * VEC + e];
+      for (int kt = 0; kt < p.kT; ++kt) {
+        const int ti = to * p.sT + kt - p.pT;
+        if (ti < 0 || ti >= p.x.T) continue;
+        for (int kh = 0; kh < p.kH; ++kh) {
+          const int hi = ho * p.sH + kh - p.pH;
+          if (hi < 0 || hi >= p.x.H) continue;
+          const float* wt = ws + ((kt * p.kH + kh) * KW) * chb;
+          float wv[KW][VEC];
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
+          for (int kw = 0; kw < KW; ++kw)
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) wv[kw][e] = wt[kw * chb + e];
-        const long long rowoff = voff(p.x, b, ti, hi, 0);
+            for (int e = 0; e < VEC; ++e) wv[kw][e] = wt[kw * chb + e];
+          const long long rowoff = voff(p.x, b, ti, hi, 0);
 #pragma unroll
-        for (int col = 0; col < NCOL; ++col) {
-          const int wi = wi0 + col;
-          if (wi < 0 || wi >= p.x.W) continue;
-          float xv[VEC];
-          load_vec<VEC>(xb + rowoff + wi * p.x.sW, p.x.f16, xv);
+          for (int col = 0; col < NCOL; ++col) {
+            const int wi = wi0 + col;
+            if (wi < 0 || wi >= p.x.W) continue;
+            float xv[VEC];
+            load_vec<VEC>(xb + rowoff + wi * p.x.sW, p.x.f16, xv);
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            if ((col - kw) % SW == 0 && col - kw >= 0 && (col - kw) / SW < OW) {
-              const int o = (col - kw) / SW;
+            for (int kw = 0; kw < KW; ++kw) {
+              if ((col - kw) % SW == 0 && col - kw >= 0 && (col - kw) / SW < OW) {
+                const int o = (col - kw) / SW;
 #pragma unroll
-              for (int e = 0; e < VEC; ++e) acc[o][e] = fmaf(xv[e], wv[kw][e], acc[o][e]);
+                for (int e = 0; e < VEC; ++e) acc[o][e] = fmaf(xv[e], wv[kw][e], acc[o][e]);
+              }
             }
           }
         }
       }
-    }
 #pragma unroll
-    for (int o = 0; o < OW; ++o) {
-      const int wo = wb * OW + o;
-      if (wo >= p.y.W) break;
+      for (int o = 0; o < OW; ++o) {
+        const int wo = wb * OW + o;
+        if (wo >= p.y.W) break;
+        if (p.has_res) {
+          const long long ro = voff(p.res, b, to, ho, wo);
+          float rv[VEC];
+          if (res_vec) load_vec<VEC>(rb + ro, p.res.f16, rv);
+          else {
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) acc[o][e] = apply_act(acc[o][e], p.act);
-      store_vec<VEC>(yb + voff(p.y, b, to, ho, wo), p.y.f16, acc[o]);
+            for (int e = 0; e < VEC; ++e) rv[e] = h162f(rb[ro + e], p.res.f16);
+          }
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[o][e] += rv[e];
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[o][e] = apply_act(acc[o][e], p.act);
+        store_vec<VEC>(yb + voff(p.y, b, to, ho, wo), p.y.f16, acc[o]);
+      }
     }
   }
 }
 
-template <int VEC>
+static bool vec_ok(const View& v, int vec);
+template <int VEC, int KW>
 static bool launch_dwconv(const DirectParams& p, cudaStream_t s) {
   const int cgs = p.x.C / VEC;
   const int cb = std::min(cgs, kDwCgPerBlock);
-  const int taps = p.kT * p.kH * 3;
+  const int taps = p.kT * p.kH * KW;
   const size_t smem = (size_t)(taps + 1) * kDwCgPerBlock * VEC * sizeof(float);
   if (smem > 48 * 1024) return false;
   const int lanes = 256 / cb;
-  if (p.sW == 1) {
-    const long long items = (long long)p.y.B * p.y.T * p.y.H * cdiv(p.y.W, 4);
-    dim3 grid((unsigned)std::min<long long>(cdiv(items, lanes), 148 * 64), cdiv(cgs, kDwCgPerBlock));
-    dwconv_kernel<VEC, 4, 1><<<grid, 256, smem, s>>>(p);
-  } else {
-    const long long items = (long long)p.y.B * p.y.T * p.y.H * cdiv(p.y.W, 2);
-    dim3 grid((unsigned)std::min<long long>(cdiv(items, lanes), 148 * 64), cdiv(cgs, kDwCgPerBlock));
-    dwconv_kernel<VEC, 2, 2><<<grid, 256, smem, s>>>(p);
-  }
+  const int res_vec = p.has_res && vec_ok(p.res, VEC);
+  const int ow = p.sW == 1 ? 4 : 2;
+  (void)lanes;
+  (void)ow;
+  const long long tiles = (long long)p.y.B * cdiv(p.y.T, kDwTileT) * cdiv(p.y.H, kDwTileH);
+  dim3 grid((unsigned)std::min<long long>(tiles, 148 * 64), cdiv(cgs, kDwCgPerBlock));
+  if (p.sW == 1) dwconv_kernel<VEC, 4, 1, KW><<<grid, 256, smem, s>>>(p, res_vec);
+  else dwconv_kernel<VEC, 2, 2, KW><<<grid, 256, smem, s>>>(p, res_vec);
   return true;
+}
+template <int KW>
+static bool dispatch_dwconv(const DirectParams& p, cudaStream_t s) {
+  const int C = p.x.C;
+  if (C % 8 == 0 && vec_ok(p.x, 8) && vec_ok(p.y, 8)) return launch_dwconv<8, KW>(p, s);
+  if (C % 4 == 0 && vec_ok(p.x, 4) && vec_ok(p.y, 4)) return launch_dwconv<4, KW>(p, s);
+  if (C % 2 == 0 && vec_ok(p.x, 2) && vec_ok(p.y, 2)) return launch_dwconv<2, KW>(p, s);
+  return launch_dwconv<1, KW>(p, s);
 }
 
 static bool vec_ok(const View& v, int vec) {
@@ -892,16 +974,27 @@ extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {
   p.pT = d->pT, p.pH = d->pH, p.pW = d->pW, p.dT = d->dT, p.dH = d->dH, p.dW = d->dW;
   p.groups = d->groups, p.act = d->act, p.out_f32 = d->out_dtype == ESF_F32;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (p.groups == p.x.C && p.y.C == p.x.C && d->kW == 3 && d->dT == 1 && d->dH == 1 && d->dW == 1 &&
-      (d->sW == 1 || d->sW == 2) && !p.has_res && !p.out_f32 && is16(d->x.dtype) && d->y.dtype == d->x.dtype &&
-      (long long)p.y.B * p.y.T * p.y.H * p.y.W < (1LL << 40)) {
-    bool done = false;
-    const int C = p.x.C;
-    if (C % 8 == 0 && vec_ok(p.x, 8) && vec_ok(p.y, 8)) done = launch_dwconv<8>(p, s);
-    else if (C % 4 == 0 && vec_ok(p.x, 4) && vec_ok(p.y, 4)) done = launch_dwconv<4>(p, s);
-    else if (C % 2 == 0 && vec_ok(p.x, 2) && vec_ok(p.y, 2)) done = launch_dwconv<2>(p, s);
-    else done = launch_dwconv<1>(p, s);
+  if (p.groups == p.x.C && p.y.C == p.x.C && (d->kW == 3 || d->kW == 5) && d->dT == 1 && d->dH == 1 && d->dW == 1 &&
+      (d->sW == 1 || d->sW == 2) && !p.out_f32 && is16(d->x.dtype) && d->y.dtype == d->x.dtype &&
+      (!p.has_res || d->res.dtype == d->x.dtype) && (long long)p.y.T * p.y.H * p.y.W < (1LL << 31)) {
+    const bool done = d->kW == 3 ? dispatch_dwconv<3>(p, s) : dispatch_dwconv<5>(p, s);
     if (done) return check_launch("dwconv_kernel");
+  }
+  if (p.groups == 1 && d->kT == 1 && d->kH == 1 && d->kW == 1 && d->sT == 1 && d->sH == 1 && d->sW == 1 && d->pT == 0 &&
+      d->pH == 0 && d->pW == 0 && !p.out_f32 && is16(d->x.dtype) && d->y.dtype == d->x.dtype &&
+      (!p.has_res || d->res.dtype == d->x.dtype) && (p.x.C < 8 || p.y.C < 8 || p.x.C * p.y.C <= 1024)) {
+    const int cin = p.x.C, coutp = (p.y.C + 7) / 8 * 8;
+    const size_t smem = (size_t)(cin + 1) * coutp * sizeof(float);
+    if (smem <= 48 * 1024) {
+      const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W * (coutp / 8);
+      const int vec_out = vec_ok(p.y, 8);
+      const unsigned grid = grid_for(total, 256);
+      if (cin % 8 == 0 && vec_ok(p.x, 8)) pw_small_kernel<8><<<grid, 256, smem, s>>>(p, vec_out);
+      else if (cin % 4 == 0 && vec_ok(p.x, 4)) pw_small_kernel<4><<<grid, 256, smem, s>>>(p, vec_out);
+      else if (cin % 2 == 0 && vec_ok(p.x, 2)) pw_small_kernel<2><<<grid, 256, smem, s>>>(p, vec_out);
+      else pw_small_kernel<1><<<grid, 256, smem, s>>>(p, vec_out);
+      return check_launch("pw_small_kernel");
+    }
   }
   const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W * p.y.C;
   conv_direct_kernel<<<grid_for(total, 256), 256, 0, s>>>(p);

@@ -243,6 +243,17 @@ class Plan:
                                 padding, dilation, act, None if res is None else res[..., g * cout_g:(g + 1) * cout_g],
                                 out_dtype)
             return
+        if (1 < groups <= 8 and cin_g * groups >= 8 and x.shape[4] != groups and self._aligned(x) and self._aligned(y)
+                and self._aligned(res)):
+            # grouped conv whose group slices are not 16-byte addressable (ShuffleNet g3: 180 / 18 / 5 channels per
+            # group): one dense GEMM over all input channels with a block-diagonal weight.  The layer is HBM bound, the
+            # `groups`-fold MACs on structural zeros cost nothing next to the CUDA-core fallback.
+            cout_g = cout // groups
+            wd = torch.zeros((cout, cin_g * groups) + tuple(w_folded.shape[2:]), dtype=w_folded.dtype,
+                             device=w_folded.device)
+            for g in range(groups):
+                wd[g * cout_g:(g + 1) * cout_g, g * cin_g:(g + 1) * cin_g] = w_folded[g * cout_g:(g + 1) * cout_g]
+            return self.conv_igemm(x, y, wd, bias, stride, padding, dilation, act, res, out_dtype)
         self.conv_direct(x, y, w_folded, bias, stride, padding, dilation, groups, act, res, out_dtype)
         why = [n for n, t in (("x", x), ("y", y), ("res", res)) if not self._aligned(t)]
         self.meta[-1]["why_direct"] = ("groups=%d " % groups if groups != 1 else "") + \
@@ -262,7 +273,7 @@ class Plan:
         self.keep.append(d)
         L = rt.lib()
         m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
-        depthwise = groups == x.shape[4] == y.shape[4] and kw == 3
+        depthwise = groups == x.shape[4] == y.shape[4] and kw in (3, 5)
         self._add(lambda s, d=d: rt.check(L.esf_conv_direct(ctypes.byref(d), s), "esf_conv_direct"),
                   "dwconv" if depthwise else "conv_direct",
                   "%dx%dx%d g%d %d->%d" % (kt, kh, kw, groups, x.shape[4], y.shape[4]),

@@ -192,7 +192,9 @@ def test_conv_direct_depthwise_and_grouped(esf_lib):
     (12, (3, 3, 3), (1, 1, 1), (1, 3, 10, 9)), (18, (3, 3, 3), (1, 2, 2), (1, 3, 11, 13)),
     (27, (3, 3, 3), (1, 1, 1), (1, 2, 7, 6)), (48, (1, 3, 3), (1, 1, 1), (2, 2, 8, 8)),
     (4, (3, 3, 3), (1, 1, 1), (1, 4, 12, 12)), (320, (3, 3, 3), (1, 2, 2), (1, 2, 7, 7)),
-    (40, (3, 3, 3), (2, 2, 2), (1, 4, 9, 9))])
+    (40, (3, 3, 3), (2, 2, 2), (1, 4, 9, 9)), (72, (1, 5, 5), (1, 1, 1), (2, 3, 9, 9)),
+    (28, (1, 5, 5), (1, 2, 2), (1, 3, 14, 14)), (7, (1, 5, 5), (1, 2, 2), (1, 2, 9, 11)),
+    (12, (3, 3, 3), (1, 1, 1), (2, 10, 17, 19))])
 def test_depthwise_vector_kernel(esf_lib, C, k, s, shape, precision):
     """Depthwise convs through Plan.conv: vector kernel (VEC 8/4/2/1 by channel count), padded channel pitch, slices."""
     adt = rt.TORCH_DTYPE[precision]
@@ -203,10 +205,16 @@ def test_depthwise_vector_kernel(esf_lib, C, k, s, shape, precision):
     x.copy_(_rand_act(g, B, T, H, W, C, dtype=adt))
     w = torch.randn(C, 1, *k, generator=g) * 0.3
     bias = torch.randn(C, generator=g) * 0.1
-    p = (k[0] // 2, 1, 1)
-    ref = F.conv3d(_to_ncdhw(x.cpu()), w, bias, s, p, 1, C).relu()
+    p = (k[0] // 2, k[1] // 2, k[2] // 2)
+    ref = F.conv3d(_to_ncdhw(x.cpu()), w, bias, s, p, 1, C)
+    res = None
+    if C in (12, 28, 144):      # residual fused into the depthwise epilogue (GhostNet shortcut branches)
+        res = plan.act(*_to_ndhwc(ref).shape)
+        res.copy_(_rand_act(g, *res.shape, dtype=adt))
+        ref = ref + _to_ncdhw(res.cpu())
+    ref = ref.relu()
     y = plan.act(*_to_ndhwc(ref).shape)
-    plan.conv(x, y, w.double(), bias.double(), stride=s, padding=p, groups=C, act=rt.ACT_RELU)
+    plan.conv(x, y, w.double(), bias.double(), stride=s, padding=p, groups=C, act=rt.ACT_RELU, res=res)
     assert plan.meta[-1]["kind"] == "dwconv"
     plan.launch_all()
     torch.cuda.synchronize()
@@ -215,7 +223,8 @@ def test_depthwise_vector_kernel(esf_lib, C, k, s, shape, precision):
 
 
 @pytest.mark.parametrize("cin,cout,groups", [(27, 162, 1), (180, 1080, 1), (540, 480, 1), (240, 480, 3), (1080, 960, 3),
-                                             (36, 216, 1), (120, 72, 3)])
+                                             (36, 216, 1), (120, 72, 3), (540, 480, 3), (54, 240, 3), (15, 60, 3),
+                                             (120, 60, 3)])
 def test_pointwise_odd_channels_on_tensor_cores(esf_lib, cin, cout, groups):
     """1x1x1 convs whose channel counts are not multiples of 8 (or are grouped) run on the implicit GEMM thanks to the
     padded channel pitch / per-group slicing; residual + ReLU fused."""
@@ -232,11 +241,42 @@ def test_pointwise_odd_channels_on_tensor_cores(esf_lib, cin, cout, groups):
     y = plan.act(B, T, H, W, cout)
     plan.conv(x, y, w.double(), bias.double(), groups=groups, act=rt.ACT_RELU, res=res)
     assert all(m["kind"] in ("conv_igemm", "conv_wfold") for m in plan.meta), [m["kind"] for m in plan.meta]
-    assert len(plan.meta) == groups
+    assert len(plan.meta) in (1, groups)     # per-group GEMMs on aligned slices, else one block-diagonal GEMM
     plan.launch_all()
     torch.cuda.synchronize()
     err = (_to_ncdhw(y.cpu()) - ref).abs().max().item()
     assert err <= 2e-3 * ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("cin,cout,use_res,slice_out", [(2, 12, False, False), (6, 36, False, False), (3, 18, False, True),
+                                                        (4, 2, False, False), (18, 3, True, True), (12, 3, False, False),
+                                                        (4, 24, False, False), (6, 4, True, False), (7, 7, False, False)])
+def test_pointwise_tiny_channels(esf_lib, cin, cout, use_res, slice_out):
+    """1x1x1 convs with C_in < 8 or C_out < 8 (first fast-pathway layers of the efficient nets): pw_small kernel."""
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    B, T, H, W = 2, 3, 9, 10
+    plan = Plan(DEV, "fp16")
+    x = plan.act(B, T, H, W, cin)
+    x.copy_(_rand_act(g, B, T, H, W, cin, dtype=torch.float16))
+    w = torch.randn(cout, cin, 1, 1, 1, generator=g) * (2.0 / cin) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv3d(_to_ncdhw(x.cpu()), w, bias)
+    res = None
+    if use_res:
+        res = plan.act(B, T, H, W, cout)
+        res.copy_(_rand_act(g, B, T, H, W, cout, dtype=torch.float16))
+        ref = ref + _to_ncdhw(res.cpu())
+    ref = ref.relu()
+    ybuf = plan.act(B, T, H, W, cout + (cout if slice_out else 0))
+    ybuf.fill_(7.0)
+    y = ybuf[..., cout:] if slice_out else ybuf
+    plan.conv(x, y, w.double(), bias.double(), act=rt.ACT_RELU, res=res)
+    plan.launch_all()
+    torch.cuda.synchronize()
+    err = (_to_ncdhw(y.cpu()) - ref).abs().max().item()
+    assert err <= 2e-3 * max(ref.abs().max().item(), 1e-3), err
+    if slice_out:
+        assert (ybuf[..., :cout].float() == 7.0).all()
 
 
 @pytest.mark.parametrize("kt,cout", [(1, 64), (5, 8), (3, 6)])
