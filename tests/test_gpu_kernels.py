@@ -206,7 +206,7 @@ def test_depthwise_vector_kernel(esf_lib, C, k, s, shape, precision):
     w = torch.randn(C, 1, *k, generator=g) * 0.3
     bias = torch.randn(C, generator=g) * 0.1
     p = (k[0] // 2, k[1] // 2, k[2] // 2)
-    ref = F.conv3d(_to_ncdhw(x.cpu()), w, bias, s, p, 1, C)
+    ref = F.conv3d(_to_ncdhw(x.cpu()), w.to(adt).float(), bias, s, p, 1, C)   # weights are held in the 16-bit format
     res = None
     if C in (12, 28, 144):      # residual fused into the depthwise epilogue (GhostNet shortcut branches)
         res = plan.act(*_to_ndhwc(ref).shape)

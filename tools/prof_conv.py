@@ -15,18 +15,21 @@ B, T, H, W, cin, cout, kt, kh, kw, st, sh, sw, use_res = a
 reps = int(sys.argv[14]) if len(sys.argv) > 14 else 5
 precision = sys.argv[15] if len(sys.argv) > 15 else "fp16"
 wfold = int(sys.argv[16]) if len(sys.argv) > 16 else 1
+groups = int(os.environ.get("ESF_PROF_GROUPS", "1"))
 DEV = "cuda:0"
 adt = rt.TORCH_DTYPE[precision]
 pad = (kt // 2, kh // 2, kw // 2)
 To, Ho, Wo = (T + 2 * pad[0] - kt) // st + 1, (H + 2 * pad[1] - kh) // sh + 1, (W + 2 * pad[2] - kw) // sw + 1
 g = torch.Generator().manual_seed(0)
-x = torch.randn(B, T, H, W, cin, generator=g).to(DEV, adt)
-y = torch.empty(B, To, Ho, Wo, cout, dtype=adt, device=DEV)
-res = torch.randn(B, To, Ho, Wo, cout, generator=g).to(DEV, adt) if use_res else None
-w = torch.randn(cout, cin, kt, kh, kw, generator=g).double() * (2.0 / (cin * kt * kh * kw)) ** 0.5
 plan = Plan(DEV, precision)
+x = plan.act(B, T, H, W, cin)
+x.copy_(torch.randn(B, T, H, W, cin, generator=g).to(DEV, adt))
+y = plan.act(B, To, Ho, Wo, cout)
+res = torch.randn(B, To, Ho, Wo, cout, generator=g).to(DEV, adt) if use_res else None
+w = torch.randn(cout, cin // groups, kt, kh, kw, generator=g).double() * (2.0 * groups / (cin * kt * kh * kw)) ** 0.5
 plan.wfold = bool(wfold)
-plan.conv(x, y, w, torch.zeros(cout, dtype=torch.float64), stride=(st, sh, sw), padding=pad, act=rt.ACT_RELU, res=res)
+plan.conv(x, y, w, torch.zeros(cout, dtype=torch.float64), stride=(st, sh, sw), padding=pad, groups=groups, act=rt.ACT_RELU,
+          res=res)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
 plan.launch_all()
 torch.cuda.synchronize()
