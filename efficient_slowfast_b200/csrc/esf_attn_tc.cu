@@ -727,13 +727,11 @@ __global__ void __launch_bounds__(256) attn_tc_pack_kernel(const float* __restri
   const float* src = proj + ((long long)b * N + n0) * W4;
   for (int i = threadIdx.x; i < rows * W4; i += blockDim.x) tile[(i / W4) * pitch + (i % W4)] = src[i];
   __syncthreads();
-  // Q~ / K~
+  // Q~ / K~: one thread = 8 consecutive elements of a row (one 16-byte store each)
   __nv_bfloat16* qd = Q + ((long long)b * N + n0) * KQ;
   __nv_bfloat16* kd = K + ((long long)b * N + n0) * KQ;
-  for (int i = threadIdx.x; i < rows * KQ; i += blockDim.x) {
-    const int r = i / KQ, e = i % KQ;
-    const float* pr = tile + r * pitch;
-    __nv_bfloat16 qv = f2h16(0.f, f16), kv = qv;
+  auto qk_elem = [&](const float* pr, int e, __nv_bfloat16& qv, __nv_bfloat16& kv) {
+    qv = f2h16(0.f, f16), kv = qv;
     if (mode == 0) {
       const int seg = e >> 3, jj = e & 7;
       if (jj < d && seg < 3) {
@@ -753,20 +751,57 @@ __global__ void __launch_bounds__(256) attn_tc_pack_kernel(const float* __restri
       qv = h_hi(pr[d + e], f16);
       kv = h_hi(pr[2 * d + e], f16);
     }
-    qd[i] = qv;
-    kd[i] = kv;
+  };
+  auto bits = [](__nv_bfloat16 a, __nv_bfloat16 b2) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+  };
+  if (KQ % 8 == 0) {
+    const int g8 = KQ >> 3;
+    for (int i = threadIdx.x; i < rows * g8; i += blockDim.x) {
+      const int r = i / g8, e0 = (i % g8) * 8;
+      const float* pr = tile + r * pitch;
+      __nv_bfloat16 qv[8], kv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) qk_elem(pr, e0 + e, qv[e], kv[e]);
+      *reinterpret_cast<uint4*>(qd + (long long)r * KQ + e0) =
+          make_uint4(bits(qv[0], qv[1]), bits(qv[2], qv[3]), bits(qv[4], qv[5]), bits(qv[6], qv[7]));
+      *reinterpret_cast<uint4*>(kd + (long long)r * KQ + e0) =
+          make_uint4(bits(kv[0], kv[1]), bits(kv[2], kv[3]), bits(kv[4], kv[5]), bits(kv[6], kv[7]));
+    }
+  } else {
+    for (int i = threadIdx.x; i < rows * KQ; i += blockDim.x) {
+      __nv_bfloat16 qv, kv;
+      qk_elem(tile + (i / KQ) * pitch, i % KQ, qv, kv);
+      qd[i] = qv;
+      kd[i] = kv;
+    }
   }
   // x_d
   float* xd = X + ((long long)b * N + n0) * d;
-  for (int i = threadIdx.x; i < rows * d; i += blockDim.x) xd[i] = tile[(i / d) * pitch + (i % d)];
-  // V^T (rows j >= d and the columns n >= N of the padded row stay zero)
-  for (int i = threadIdx.x; i < DVp * R; i += blockDim.x) {
-    const int j = i / R, r = i % R;
-    if (n0 + r < Npad) {
-      float v = (j < d && r < rows) ? tile[r * pitch + 3 * d + j] : 0.f;
-      if (ones_row && j == d && r < rows) v = 1.f;   // sum_j p_ij comes out of the P.V MMA as column d of O
-      VT[((long long)b * DVp + j) * Npad + n0 + r] = f2h16(v, f16);
+  if (d % 4 == 0) {
+    const int g4 = d >> 2;
+    for (int i = threadIdx.x; i < rows * g4; i += blockDim.x) {
+      const float* pr = tile + (i / g4) * pitch + (i % g4) * 4;
+      *reinterpret_cast<float4*>(xd + (long long)i * 4) = make_float4(pr[0], pr[1], pr[2], pr[3]);
     }
+  } else {
+    for (int i = threadIdx.x; i < rows * d; i += blockDim.x) xd[i] = tile[(i / d) * pitch + (i % d)];
+  }
+  // V^T (rows j >= d and the columns n >= N of the padded row stay zero): one thread = 8 consecutive keys of one row
+  const int r8n = R >> 3;
+  for (int i = threadIdx.x; i < DVp * r8n; i += blockDim.x) {
+    const int j = i / r8n, r0 = (i % r8n) * 8;
+    if (n0 + r0 >= Npad) continue;
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int r = r0 + e;
+      float x = (j < d && r < rows) ? tile[r * pitch + 3 * d + j] : 0.f;
+      if (ones_row && j == d && r < rows) x = 1.f;   // sum_j p_ij comes out of the P.V MMA as column d of O
+      v[e] = f2h16(x, f16);
+    }
+    *reinterpret_cast<uint4*>(VT + ((long long)b * DVp + j) * Npad + n0 + r0) =
+        make_uint4(bits(v[0], v[1]), bits(v[2], v[3]), bits(v[4], v[5]), bits(v[6], v[7]));
   }
 }
 

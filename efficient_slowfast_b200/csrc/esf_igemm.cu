@@ -17,6 +17,7 @@
 //               epilogue will overwrite in place, `obufs - 1` slabs ahead of its consumer.
 //
 // Reference ops replaced: see include/esf.h (esf_conv_igemm_create).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -884,8 +885,12 @@ extern "C" int esf_conv_wfold_create(const esf_conv_desc* d, int32_t WB, esf_op*
   const CUtensorMapDataType dt16 = p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   p.slab_cols = std::min(n_tile, 64);
   const int out_row_bytes = p.slab_cols * 2;
-  // a sliced destination is written through a (c, w) box whose smem image is the plain row-major slab: no swizzle
-  const bool plain = need_pow2;
+  // A sliced destination is written through a (c, w) box whose smem image is the plain row-major slab: no swizzle.
+  // (Measured: declaring the 128 B swizzle on such a box does NOT reproduce the dense-row image -- the swizzle atom
+  // follows the box's inner extent, not just the shared-memory address -- so the staging writes of this mode keep
+  // their 8-way bank conflicts.)
+  const bool slice_mode = need_pow2;
+  const bool plain = slice_mode;
   p.out_swz = plain ? 0 : (out_row_bytes == 128 ? 7 : (out_row_bytes == 64 ? 3 : 1));
   const CUtensorMapSwizzle out_sw = plain ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_for_row_bytes(out_row_bytes);
   p.res_bytes = p.rows * p.slab_cols * 2;
@@ -936,7 +941,7 @@ extern "C" int esf_conv_wfold_create(const esf_conv_desc* d, int32_t WB, esf_op*
     }
   }
   auto encode_io = [&](CUtensorMap* m, const esf_view& v, bool dense, int* fold_cout, const char* what) {
-    if (dense && !plain) {   // rows of WB*Cout contiguous elements: (WB*Cout, Wo/WB, Ho, To, B)
+    if (dense && !slice_mode) {   // rows of WB*Cout contiguous elements: (WB*Cout, Wo/WB, Ho, To, B)
       *fold_cout = 0;
       return encode_act_map(m, dt16, 2, v.ptr, (int64_t)N, Wo / WB, Ho, To, v.B, (int64_t)N, v.sH, v.sT, v.sB,
                             p.slab_cols, 1, p.bh, p.bt, p.bb, out_sw, what);
