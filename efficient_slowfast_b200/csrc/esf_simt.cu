@@ -939,6 +939,45 @@ __global__ void __launch_bounds__(256) shuffle_concat_kernel(const View a, const
     reinterpret_cast<__nv_bfloat16*>(y.ptr)[voff(y, bb, t, h, w) + o] = v;
   }
 }
+// Same permutation, one thread = VEC consecutive OUTPUT channels: VEC gathered 2-byte loads (the row is L1 resident,
+// a warp covers it completely) and one VEC*2-byte store.
+template <int VEC>
+__global__ void __launch_bounds__(256) shuffle_concat_vec_kernel(const View a, const View b, int cb, int groups,
+                                                                 const View y) {
+  const int C = y.C, cv = C / VEC;
+  const int cpg = C / groups;
+  const long long total = (long long)y.B * y.T * y.H * y.W * cv;
+  const unsigned short* ap = reinterpret_cast<const unsigned short*>(a.ptr);
+  const unsigned short* bp = reinterpret_cast<const unsigned short*>(b.ptr);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int o0 = (idx % cv) * VEC;
+    long long pos = idx / cv;
+    const int w = pos % y.W;
+    pos /= y.W;
+    const int h = pos % y.H;
+    pos /= y.H;
+    const int t = pos % y.T;
+    const int bb = pos / y.T;
+    const long long ao = voff(a, bb, t, h, w), bo = cb ? voff(b, bb, t, h, w) : 0;
+    unsigned short v[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int o = o0 + e;
+      const int c = (o % groups) * cpg + o / groups;  // source channel in cat(a, b)
+      v[e] = c < a.C ? __ldg(ap + ao + c) : __ldg(bp + bo + (c - a.C));
+    }
+    unsigned short* yp = reinterpret_cast<unsigned short*>(y.ptr) + voff(y, bb, t, h, w) + o0;
+    if constexpr (VEC == 8) {
+      *reinterpret_cast<uint4*>(yp) = make_uint4(v[0] | ((uint32_t)v[1] << 16), v[2] | ((uint32_t)v[3] << 16),
+                                                  v[4] | ((uint32_t)v[5] << 16), v[6] | ((uint32_t)v[7] << 16));
+    } else if constexpr (VEC == 4) {
+      *reinterpret_cast<uint2*>(yp) = make_uint2(v[0] | ((uint32_t)v[1] << 16), v[2] | ((uint32_t)v[3] << 16));
+    } else {
+      *reinterpret_cast<uint32_t*>(yp) = v[0] | ((uint32_t)v[1] << 16);
+    }
+  }
+}
 // y = act(a + b) elementwise
 __global__ void __launch_bounds__(256) eltwise_add_kernel(const View a, const View b, const View y, int act) {
   const int C = y.C;
@@ -1173,8 +1212,16 @@ extern "C" int esf_shuffle_concat(const esf_view* a, const esf_view* b, int32_t 
   ESF_CHECK_ARG(same_pos(a, y) && (cb == 0 || (view_ok(b) && same_pos(b, y))) && a->C + cb == y->C && y->C % groups == 0,
                 "esf_shuffle_concat: shape mismatch");
   const long long total = (long long)y->B * y->T * y->H * y->W * y->C;
-  shuffle_concat_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      to_view(a), cb ? to_view(b) : to_view(a), cb, groups, to_view(y));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const View va = to_view(a), vb = cb ? to_view(b) : to_view(a), vy = to_view(y);
+  if (y->C % 8 == 0 && vec_ok(vy, 8))
+    shuffle_concat_vec_kernel<8><<<grid_for(total / 8, 256), 256, 0, s>>>(va, vb, cb, groups, vy);
+  else if (y->C % 4 == 0 && vec_ok(vy, 4))
+    shuffle_concat_vec_kernel<4><<<grid_for(total / 4, 256), 256, 0, s>>>(va, vb, cb, groups, vy);
+  else if (y->C % 2 == 0 && vec_ok(vy, 2))
+    shuffle_concat_vec_kernel<2><<<grid_for(total / 2, 256), 256, 0, s>>>(va, vb, cb, groups, vy);
+  else
+    shuffle_concat_kernel<<<grid_for(total, 256), 256, 0, s>>>(va, vb, cb, groups, vy);
   return check_launch("shuffle_concat_kernel");
 }
 

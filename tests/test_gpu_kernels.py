@@ -279,6 +279,31 @@ def test_pointwise_tiny_channels(esf_lib, cin, cout, use_res, slice_out):
         assert (ybuf[..., :cout].float() == 7.0).all()
 
 
+@pytest.mark.parametrize("ca,cb,groups", [(24, 24, 2), (240, 0, 3), (6, 6, 2), (3, 3, 2), (27, 27, 2), (12, 0, 3),
+                                          (116, 116, 2), (15, 0, 3)])
+def test_shuffle_concat(esf_lib, ca, cb, groups):
+    """channel_shuffle(cat(a, b), groups) (shufflenetv2_helper.py:32-43, shufflenet_helper.py:24-34), bit exact;
+    covers the 16/8/4-byte store variants and the scalar tail kernel."""
+    g = torch.Generator().manual_seed(ca * 7 + cb)
+    B, T, H, W = 2, 3, 5, 6
+    plan = Plan(DEV, "fp16")
+    a = plan.act(B, T, H, W, ca)
+    a.copy_(_rand_act(g, B, T, H, W, ca, dtype=torch.float16))
+    b = None
+    if cb:
+        bbuf = plan.act(B, T, H, W, cb + 8)       # second operand as a channel slice
+        b = bbuf[..., 8:]
+        b.copy_(_rand_act(g, B, T, H, W, cb, dtype=torch.float16))
+    C = ca + cb
+    y = plan.act(B, T, H, W, C)
+    plan.shuffle_concat(a, b, groups, y)
+    plan.launch_all()
+    torch.cuda.synchronize()
+    cat = torch.cat([a] + ([b] if cb else []), dim=4)
+    ref = cat.reshape(B, T, H, W, groups, C // groups).transpose(4, 5).reshape(B, T, H, W, C)
+    assert torch.equal(y.cpu(), ref.cpu())
+
+
 @pytest.mark.parametrize("kt,cout", [(1, 64), (5, 8), (3, 6)])
 def test_stem_conv(esf_lib, kt, cout):
     g = torch.Generator().manual_seed(kt)
