@@ -78,3 +78,77 @@ def test_zero_init_final_bn_and_gamma_zero():
     assert float(m.s2.pathway0_res0.branch2.a_bn.weight.min()) == 1.0
     assert float(m.s1_fuse.attention_spatial_s2f.gamma) == 0.0
     assert m.s1_fuse.attention_channel_f2s.conv.weight.shape == (1, 1, 3)
+
+
+def _banded_gemm_reference(x_ndhwc, band, bias_t, cout, k, stride_hw, pad, WB):
+    """CPU emulation of what esf_conv_wfold_create computes: for every block of WB output columns, the GEMM row is the
+    contiguous run of ((WB-1)*sW + kW) input columns x C, zero outside the tensor; K = taps(kt,kh) x padded window."""
+    B, T, H, W, C = x_ndhwc.shape
+    kt, kh, kw = k
+    sH, sW = stride_hw
+    pT, pH, pW = pad
+    To, Ho, Wo = T + 2 * pT - kt + 1, (H + 2 * pH - kh) // sH + 1, (W + 2 * pW - kw) // sW + 1
+    win = ((WB - 1) * sW + kw) * C
+    kpad = -(-win // 64) * 64
+    band = band.double().reshape(band.shape[0], kt * kh, kpad)
+    xp = F.pad(x_ndhwc.double(), (0, 0, pW, pW + kpad, pH, pH, pT, pT))   # generous right padding = TMA zero fill
+    out = torch.zeros(B, To, Ho, Wo, cout, dtype=torch.float64)
+    for cb in range(Wo // WB):
+        w0 = cb * WB * sW
+        for t in range(To):
+            for h in range(Ho):
+                acc = bias_t[:WB * cout].double().clone().repeat(B, 1)
+                for it in range(kt):
+                    for ih in range(kh):
+                        row = xp[:, t + it, h * sH + ih, w0:w0 + kpad // C + 1].reshape(B, -1)[:, :kpad]
+                        acc += row @ band[:WB * cout, it * kh + ih].T
+                out[:, t, h, cb * WB:(cb + 1) * WB] = acc.reshape(B, WB, cout)
+    return out
+
+
+@pytest.mark.parametrize("cin,cout,k,s,WB", [(8, 8, (1, 3, 3), (1, 1), 4), (16, 8, (3, 1, 1), (1, 1), 8),
+                                             (8, 32, (1, 1, 1), (1, 1), 8), (16, 16, (1, 3, 3), (2, 2), 2)])
+def test_pack_wfold_band_is_the_convolution(esf_lib, cin, cout, k, s, WB):
+    g = torch.Generator().manual_seed(cin + cout)
+    pad = (k[0] // 2, k[1] // 2, k[2] // 2)
+    x = torch.randn(2, 3, 6, 8 * s[1], cin, generator=g)
+    w = torch.randn(cout, cin, *k, generator=g).double()
+    b = torch.randn(cout, generator=g).double()
+    band, bt = engine.pack_wfold_band(w, b, WB, s[1], "cpu", torch.float32)
+    ref = F.conv3d(x.permute(0, 4, 1, 2, 3).double(), w, b, (1, s[0], s[1]), pad).permute(0, 2, 3, 4, 1)
+    got = _banded_gemm_reference(x, band, bt, cout, k, s, pad, WB)
+    assert got.shape == ref.shape
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4)
+
+
+def test_wfold_block_planner():
+    def views(B, T, H, W, cin, cout, slice_out=False):
+        x = torch.empty(B, T, H, W, cin)
+        yb = torch.empty(B, T, H, W, cout + (16 if slice_out else 0))
+        return x, (yb[..., 8:8 + cout] if slice_out else yb)
+    x, y = views(1, 4, 56, 56, 8, 8)
+    assert engine.wfold_block(x, y, None, (8, 8, 1, 3, 3), (1, 1, 1), (0, 1, 1), (1, 1, 1)) == 14
+    x, y = views(1, 4, 56, 56, 8, 32, slice_out=True)          # sliced destination: WB * Cout must be a power of two
+    assert engine.wfold_block(x, y, None, (32, 8, 1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1)) == 8
+    x, y = views(1, 4, 14, 14, 64, 64)                          # C_in > 32: plain implicit GEMM
+    assert engine.wfold_block(x, y, None, (64, 64, 1, 3, 3), (1, 1, 1), (0, 1, 1), (1, 1, 1)) == 0
+    x, y = views(1, 4, 56, 56, 8, 16)                           # temporal stride: not folded
+    assert engine.wfold_block(x, y, None, (16, 8, 5, 1, 1), (4, 1, 1), (2, 0, 0), (1, 1, 1)) == 0
+    xs = torch.empty(1, 4, 56, 56, 24)[..., :8]                 # input is a channel slice (not dense in W, C)
+    assert engine.wfold_block(xs, y, None, (16, 8, 1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1)) == 0
+
+
+def test_activation_pitch_rule():
+    plan = engine.Plan("cpu", "fp16")
+    for C, pitch in [(3, 3), (7, 7), (8, 8), (27, 32), (180, 184), (540, 544), (64, 64)]:
+        t = plan.act(1, 2, 3, 4, C)
+        assert t.shape[4] == C and t.stride(3) == pitch and t.dtype == torch.float16
+        assert engine.Plan._aligned(t) == (C >= 8)
+    assert plan.act(1, 2, 3, 4, 12, dtype=torch.float32).stride(3) == 12     # FP32 projections stay dense
+
+
+def test_head_fc_launch_accounting():
+    assert engine.head_fc_launches(64, 2304, 400, rt.HEAD_SOFTMAX) == 2
+    assert engine.head_fc_launches(64, 2304, 400, rt.HEAD_RELU) == 1
+    assert engine.head_fc_launches(2, 2304, 400, rt.HEAD_SOFTMAX) == 1
+    assert engine.head_fc_launches(2, 20000, 400, rt.HEAD_SOFTMAX) == 2
