@@ -8,6 +8,8 @@ from .config import (CfgNode, get_cfg, slowfast_4x16_r50_cfg, slowfast_dual_8x8_
                      slowfast_ghostnet_cfg, slowfast_mobilenetv2_cfg, slowfast_shufflenet_cfg,
                      slowfast_shufflenetv2_cfg)
 from .pipeline import ClipStream  # noqa: F401
+from .testing import TestMeter, perform_test, topks_correct  # noqa: F401
+from .checkpoint import load_checkpoint, save_checkpoint  # noqa: F401
 from . import nets_resnet  # noqa: F401  (registers SlowFast, SlowFastDualAttention)
 from . import nets_efficient  # noqa: F401  (registers SlowFastShuffleNetV2, SlowFastShuffleNet, ...)
 

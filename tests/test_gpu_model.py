@@ -172,3 +172,33 @@ def test_clip_stream_matches_direct_forward(esf_lib):
     for (_, y), w in zip(got, want):
         assert torch.equal(y, w)
     assert not torch.equal(want[0], want[3])
+
+
+def test_perform_test_multi_view_ensemble(esf_lib):
+    """perform_test (tools/test_net.py:21-123, classification) over a synthetic loader: 3 videos x 2 views in batches
+    of 2, streamed through ClipStream; the ensembled video predictions equal the sum of direct per-clip forwards."""
+    import efficient_slowfast_b200 as esf
+
+    cfg, model, gold, _ = _run("slowfast_r50", "s64")
+    base = helpers.case_inputs("slowfast_r50", "s64")[1][:1]
+    clips, labels = [], torch.tensor([5, 5, 17, 17, 3, 3])
+    for i in range(6):
+        fast = torch.roll(base, shifts=3 * i, dims=3) * (1.0 + 0.05 * i)
+        clips.append(recipe.pack_pathway_output(fast, cfg.SLOWFAST.ALPHA))
+    loader = []
+    for i in range(0, 6, 2):
+        inputs = [torch.cat([clips[i][p], clips[i + 1][p]]).contiguous().pin_memory() for p in range(2)]
+        loader.append((inputs, labels[i:i + 2], torch.tensor([i, i + 1]), {}))
+    with torch.no_grad():
+        direct = torch.cat([model([t.cuda() for t in c]).cpu() for c in clips])
+    meter = esf.TestMeter(3, 2, cfg.MODEL.NUM_CLASSES, len(loader))
+    snapshots = []
+    orig = meter.finalize_metrics
+    meter.finalize_metrics = lambda ks=(1, 5): (snapshots.append(meter.video_preds.clone()), orig(ks))[1]
+    cfg.NUM_GPUS = 1
+    stats = esf.perform_test(loader, model, meter, cfg)
+    want = direct.view(3, 2, -1).sum(1)
+    assert torch.allclose(snapshots[0], want, atol=1e-6)
+    top1 = (want.argmax(1) == torch.tensor([5, 17, 3])).float().mean().item() * 100
+    assert stats["top1_acc"] == "{:.2f}".format(top1) and stats["complete"]
+    assert meter.clip_count.sum() == 0      # reset after finalize, like the reference
