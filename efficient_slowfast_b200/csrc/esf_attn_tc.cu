@@ -361,8 +361,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
 //   * P never touches shared memory: it is written to TMEM (tcgen05.st) and the P.V MMA takes its A operand from
 //     there, which removes the swizzled st.shared, the generic->async proxy fence and their address arithmetic;
 // Two things that were measured and did NOT help (so the kernel is issue/latency bound, not MUFU-throughput bound):
-// fetching the scores of tile j+1 before P of tile j is stored (-25 %), and evaluating 1/8 .. 3/8 of the exponentials
-// with a polynomial on the FMA pipe (-5 .. -25 %).
+// fetching the scores of tile j+1 before P of tile j is stored (-25 %), evaluating 1/8 .. 3/8 of the exponentials
+// with a polynomial on the FMA pipe (-5 .. -25 %), and computing the tile maximum first so that the S buffer can be
+// handed back to the MMA warp before the exponentials (-2 .. -4 %; the ncu source page shows the softmax warps find
+// S_{j+1} not yet complete on 87 % of the tiles, but that wait overlaps other warps' MUFU work).
 // TMEM columns: S[q][buf] 4 x 64 | O[q][h] 4 x DVp (<= 48) | P[q][h] 4 x 16  = 512.
 constexpr int kV2Threads = 608;  // 16 softmax warps + TMA producer + 2 MMA issuers
 constexpr int kV2PCol = 448;     // first TMEM column of P
