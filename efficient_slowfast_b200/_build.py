@@ -14,8 +14,8 @@ SOURCES = ["esf_api.cu", "esf_igemm.cu", "esf_simt.cu", "esf_attention.cu", "esf
 HEADERS = ["esf_common.cuh", "esf_host.h", os.path.join("..", "..", "include", "esf.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DESF_NO_FAST_MATH",
-]
+    "-Xcompiler", "-fPIC", "-DESF_NO_FAST_MATH",
+] + os.environ.get("ESF_NVCC_EXTRA", "").split()      # e.g. ESF_NVCC_EXTRA=-DESF_ATTN_TIMING for kernel phase timing
 
 
 def _nvcc():

@@ -363,10 +363,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
 // Two things that were measured and did NOT help (so the kernel is issue/latency bound, not MUFU-throughput bound):
 // fetching the scores of tile j+1 before P of tile j is stored (-25 %), evaluating 1/8 .. 3/8 of the exponentials
 // with a polynomial on the FMA pipe (-5 .. -25 %), and computing the tile maximum first so that the S buffer can be
-// handed back to the MMA warp before the exponentials (-2 .. -4 %; the ncu source page shows the softmax warps find
-// S_{j+1} not yet complete on 87 % of the tiles, but that wait overlaps other warps' MUFU work).
+// handed back to the MMA warp before the exponentials (-2 .. -4 %), and a FlashAttention-3 style ping-pong of the two
+// key halves through named barriers (-2 .. -17 %: the non-MUFU phase of a tile is longer than its MUFU phase).
+// What DID help after instrumenting the loop with clock64 (-DESF_ATTN_TIMING): the softmax warps found S_{j+1} missing
+// on 87 % of the tiles (~200 of ~1500 cycles) because one warp issued both MMAs and could only issue S_{j+1} after it
+// had waited for both halves of P_{j-1}; a Q.K^T issuer warp of its own removed that wait (-4 .. -8 %).
 // TMEM columns: S[q][buf] 4 x 64 | O[q][h] 4 x DVp (<= 48) | P[q][h] 4 x 16  = 512.
-constexpr int kV2Threads = 608;  // 16 softmax warps + TMA producer + 2 MMA issuers
+// 16 softmax warps + TMA producer + Q.K^T issuer + 2 P.V issuers.  20 warps: ptxas sizes the register file for the
+// block rounded up to 128 threads, so 21 warps would cap the softmax threads at 80 registers (spills).
+constexpr int kV2Threads = 640;
 constexpr int kV2PCol = 448;     // first TMEM column of P
 
 template <bool F16>
@@ -447,51 +452,56 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
         phase ^= 1;
       }
     }
-  } else if (warp == 17 || warp == 18) {
-    // ------------------------------------------------------------------ MMA issuers (one per query tile)
-    const int q = warp - 17;
+  } else if (warp == 17) {
+    // ------------------------------------------------------------------ Q.K^T issuer (both query tiles)
+    // Separate from the P.V issuers: with one warp doing both, S_{j+1} could only be issued after that warp had waited
+    // for BOTH halves of P_{j-1}, and the softmax warps found it missing on 87 % of the tiles (~200 cycles each).
     const uint32_t idesc_s = make_idesc_16(128, kTcBN, F16);
-    const uint32_t idesc_o = make_idesc_16(128, p.DVp, F16);
     const uint32_t qk_hi = kmajor_desc_hi(p.sbo, p.layout_type);
-    const uint32_t pv_hi = kmajor_desc_hi(1024, 2);
-    const uint32_t q_lo = kmajor_desc_lo(smem_u32(Qs) + q * p.q_tile_bytes);
+    const uint32_t q_lo0 = kmajor_desc_lo(smem_u32(Qs));
+    const uint32_t q_step = p.q_tile_bytes >> 4;
     const uint32_t k_lo = kmajor_desc_lo(smem_u32(Ks));
-    const uint32_t v_lo = kmajor_desc_lo(smem_u32(Vs));
-    const uint32_t k_stage_step = p.k_tile_bytes >> 4, v_stage_step = p.v_tile_bytes >> 4;
-    auto issue_s = [&](int c, int stage) {
-      const int buf = c & 1;
-      mbar_wait(&s_free[q * 2 + buf], ((c >> 1) & 1) ^ 1, 32);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t d_tmem = tmem_base + (q * 2 + buf) * kTcBN;
-        const uint32_t kb = k_lo + stage * k_stage_step;
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-          if (i < p.nsteps2)
-            umma_bf16_lohi(d_tmem, q_lo + (p.steps2[i] & 0xffff), qk_hi, kb + (p.steps2[i] >> 16), qk_hi, idesc_s, i != 0);
-        umma_commit(&s_full[q * 2 + buf]);
-      }
-      __syncwarp();
-    };
+    const uint32_t k_stage_step = p.k_tile_bytes >> 4;
     mbar_wait(q_full, 0, 33);
     tc_fence_after();
-    int s_stage = 0;
-    uint32_t s_phase = 0;
-    mbar_wait(&kv_full[s_stage], s_phase, 34);
-    tc_fence_after();
-    issue_s(0, s_stage);
-    for (int j = 0; j < nt; ++j) {
-      const int pv_stage = s_stage;
-      if (++s_stage == p.stages) {
-        s_stage = 0;
-        s_phase ^= 1;
-      }
-      if (j + 1 < nt) {
-        mbar_wait(&kv_full[s_stage], s_phase, 35);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int c = 0; c < nt; ++c) {
+      const int buf = c & 1;
+      mbar_wait(&kv_full[stage], phase, 34);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        mbar_wait(&s_free[q * 2 + buf], ((c >> 1) & 1) ^ 1, 32);
         tc_fence_after();
-        issue_s(j + 1, s_stage);
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + (q * 2 + buf) * kTcBN;
+          const uint32_t kb = k_lo + stage * k_stage_step;
+          const uint32_t q_lo = q_lo0 + q * q_step;
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+            if (i < p.nsteps2)
+              umma_bf16_lohi(d_tmem, q_lo + (p.steps2[i] & 0xffff), qk_hi, kb + (p.steps2[i] >> 16), qk_hi, idesc_s, i != 0);
+          umma_commit(&s_full[q * 2 + buf]);
+        }
+        __syncwarp();
       }
-      const uint32_t vl = v_lo + pv_stage * v_stage_step;
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 18 || warp == 19) {
+    // ------------------------------------------------------------------ P.V issuers (one per query tile)
+    const int q = warp - 18;
+    const uint32_t idesc_o = make_idesc_16(128, p.DVp, F16);
+    const uint32_t pv_hi = kmajor_desc_hi(1024, 2);
+    const uint32_t v_lo = kmajor_desc_lo(smem_u32(Vs));
+    const uint32_t v_stage_step = p.v_tile_bytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&kv_full[stage], phase, 35);   // already complete (S_j was computed from this stage): visibility only
+      const uint32_t vl = v_lo + stage * v_stage_step;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         mbar_wait(&p_full[q * 2 + h], j & 1, 36);
@@ -503,11 +513,15 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
           umma_f16_ts(o_tmem, p_tmem + 8, vl + 4 * h + 2, pv_hi, idesc_o, 1);  // keys 32h+16 .. 32h+31
           umma_commit(&p_free[q * 2 + h]);
           if (h == 1) {
-            umma_commit(&kv_empty[pv_stage]);
+            umma_commit(&kv_empty[stage]);
             if (j == nt - 1) umma_commit(&o_full[q]);
           }
         }
         __syncwarp();
+      }
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
       }
     }
   } else {
@@ -531,6 +545,13 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
     tmem_ld32_nowait(lane_addr + (q * 2) * kTcBN + 32 * h, v);
     tmem_wait_ld();
     tmem_ld32_acquire(v);
+#ifdef ESF_ATTN_TIMING
+    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#define ESF_TICK(k) { const long long tn = clock64(); tph[k] += tn - tlast; tlast = tn; }
+#else
+#define ESF_TICK(k)
+#endif
     for (int j = 0; j < nt; ++j) {
       const int buf = j & 1;
       const uint32_t s_addr = lane_addr + (q * 2 + buf) * kTcBN + 32 * h;
@@ -543,6 +564,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
       // speculative pass with the current maximum; the tile maximum rides along
       float ms = (m == -CUDART_INF_F) ? 0.f : m * kTcLog2e;
       float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+      ESF_TICK(0)   // tail mask + ping-pong wait
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         mx0 = fmaxf(fmaxf(mx0, v[i]), v[i + 1]);
@@ -551,6 +573,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
         for (int e = 0; e < 4; ++e) v[i + e] = fast_exp2(fmaf(v[i + e], kTcLog2e, -ms));
       }
       const float mx = fmaxf(mx0, mx1);
+      asm volatile("" ::"f"(v[31]), "f"(mx));
+      ESF_TICK(1)   // exponentials + tile maximum
       // raise lazily; a half tile that is entirely masked (tail) must not raise from -inf to -inf
       const bool raise = mx > m + kTau;
       const bool any_raise = __any_sync(0xffffffffu, raise);
@@ -582,11 +606,15 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[q * 2 + buf]);
+      ESF_TICK(2)   // raise handling + s_free arrive
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) pk[i] = pack16x2(v[2 * i], v[2 * i + 1], F16);
+      asm volatile("" ::"r"(pk[15]));
+      ESF_TICK(3)   // pack
       mbar_wait(&p_free[q * 2 + h], (j & 1) ^ 1, 38);
       tc_fence_after();
+      ESF_TICK(4)   // wait p_free
       if (j > 0 && any_raise) {
         for (int c0 = 0; c0 < p.DVp; c0 += 16) {
           float o[16];
@@ -601,14 +629,22 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[q * 2 + h]);
+      ESF_TICK(5)   // O rescale + P store + p_full arrive
       if (j + 1 < nt) {
         mbar_wait(&s_full[q * 2 + (buf ^ 1)], ((j + 1) >> 1) & 1, 37);
         tc_fence_after();
+        ESF_TICK(6)   // wait s_full
         tmem_ld32_nowait(lane_addr + (q * 2 + (buf ^ 1)) * kTcBN + 32 * h, v);
         tmem_wait_ld();
         tmem_ld32_acquire(v);
+        ESF_TICK(7)   // tcgen05.ld of the next scores
       }
     }
+#ifdef ESF_ATTN_TIMING
+    if (blockIdx.x == 3 && blockIdx.y == 0 && lane == 0)
+      printf("warp %2d q%d h%d: pp-wait %lld  exp %lld  raise %lld  pack %lld  p_free %lld  Pstore %lld  s_full %lld  ld %lld  (cycles/tile, nt %d)\n",
+             warp, q, h, tph[0] / nt, tph[1] / nt, tph[2] / nt, tph[3] / nt, tph[4] / nt, tph[5] / nt, tph[6] / nt, tph[7] / nt, nt);
+#endif
     // ---- merge the two halves of every row and write the output
     mx_sh[(q * 2 + h) * 128 + r] = m;
     asm volatile("bar.sync %0, 256;" ::"r"(q + 1) : "memory");   // the 8 warps of this query tile
