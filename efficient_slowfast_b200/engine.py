@@ -138,6 +138,8 @@ class Plan:
         self.a16 = rt.dtype_code(self.adt)
         self.keep = []        # tensors / ctypes structs that must outlive the plan
         self.ops = []         # callables taking a stream pointer
+        self.eager = []       # per op: launched outside the CUDA graph (reads a caller-provided input tensor)
+        self.input_override = {}   # plan-owned input data_ptr -> data_ptr of the caller's tensor for this run
         self.handles = []     # esf_op* to destroy
         self.graph = None
         self.out = None
@@ -167,8 +169,11 @@ class Plan:
         self.keep.append(t)
         return t
 
-    def _add(self, fn, kind, label="", flops=0, nbytes=0, exps=0, launches=1):
+    def _add(self, fn, kind, label="", flops=0, nbytes=0, exps=0, launches=1, eager=False):
+        """`eager` ops read the caller's input tensors (their source pointer can change per call): they stay outside
+        the CUDA graph and are launched on every run, ahead of the graph replay."""
         self.ops.append(fn)
+        self.eager.append(bool(eager))
         self.meta.append(dict(kind=kind, label=label, flops=float(flops), bytes=float(nbytes), exps=float(exps),
                               launches=launches))
         self.launches_per_run += launches
@@ -292,10 +297,14 @@ class Plan:
         L = rt.lib()
         m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
         self._add(lambda s: rt.check(
-            L.esf_stem_conv(x_nc.data_ptr(), B, Cin, T, H, W, ws.data_ptr(), bs.data_ptr(), cout, kt, kh, kw, *stride,
+            L.esf_stem_conv(self._in_ptr(x_nc), B, Cin, T, H, W, ws.data_ptr(), bs.data_ptr(), cout, kt, kh, kw, *stride,
                             *padding, act, ctypes.byref(yv), s), "esf_stem_conv"), "stem_conv",
             "%dx%dx%d %d->%d" % (kt, kh, kw, Cin, cout), flops=2.0 * m * cout * Cin * kt * kh * kw,
-            nbytes=self._nbytes(x_nc, y))
+            nbytes=self._nbytes(x_nc, y), eager=True)
+
+    def _in_ptr(self, x_nc):
+        p = x_nc.data_ptr()
+        return self.input_override.get(p, p)
 
     def stem(self, x_nc, y, w_folded, bias, stride, padding, act=rt.ACT_RELU):
         """Stem conv + folded BN + ReLU.  Tensor-core banded GEMM when the geometry allows (temporal stride 1,
@@ -318,8 +327,9 @@ class Plan:
                                          ctypes.byref(yv), ctypes.byref(h)), "esf_stem_igemm_create")
         self.handles.append(h)
         m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
-        self._add(lambda s: rt.check(L.esf_stem_pack(x_nc.data_ptr(), B, Cin, T, H, W, pitch, lpad, self.a16, xp.data_ptr(), s),
-                                     "esf_stem_pack"), "stem_pack", "", nbytes=self._nbytes(x_nc, xp))
+        self._add(lambda s: rt.check(L.esf_stem_pack(self._in_ptr(x_nc), B, Cin, T, H, W, pitch, lpad, self.a16,
+                                                     xp.data_ptr(), s),
+                                     "esf_stem_pack"), "stem_pack", "", nbytes=self._nbytes(x_nc, xp), eager=True)
         self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "stem_igemm",
                   "%dx%dx%d %d->%d banded" % (kt, kh, kw, Cin, cout), flops=2.0 * m * cout * Cin * kt * kh * kw,
                   nbytes=self._nbytes(xp, y) + wb.numel() * 2)
@@ -511,8 +521,21 @@ class Plan:
         for op in self.ops:
             op(s)
 
+    def launch_graph_ops(self):
+        s = rt.current_stream_ptr()
+        for op, eager in zip(self.ops, self.eager):
+            if not eager:
+                op(s)
+
+    def launch_eager_ops(self):
+        s = rt.current_stream_ptr()
+        for op, eager in zip(self.ops, self.eager):
+            if eager:
+                op(s)
+
     def capture(self):
-        """Record the launches into one CUDA graph (replayed by run())."""
+        """Record every launch that only touches plan-owned memory into one CUDA graph (replayed by run()); the ops
+        that read the caller's clips (stem packing) stay outside and run ahead of the replay."""
         torch.cuda.synchronize(self.device)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
@@ -522,7 +545,7 @@ class Plan:
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.launch_all()
+            self.launch_graph_ops()
         self.graph = g
 
     def profile_ops(self, repeats=3):
@@ -540,11 +563,20 @@ class Plan:
                 times[i] = min(times[i], evs[i].elapsed_time(evs[i + 1]))
         return times
 
-    def run(self):
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            self.launch_all()
+    def run(self, inputs=None):
+        """`inputs`: optional caller tensors to read INSTEAD of the plan-owned input buffers (same shape, FP32,
+        contiguous, same device) -- saves the device-to-device staging copy."""
+        self.input_override = {}
+        if inputs is not None:
+            self.input_override = {own.data_ptr(): src.data_ptr() for own, src in zip(self.inputs, inputs)}
+        try:
+            if self.graph is not None:
+                self.launch_eager_ops()
+                self.graph.replay()
+            else:
+                self.launch_all()
+        finally:
+            self.input_override = {}
         return self.out
 
     def __del__(self):

@@ -282,10 +282,14 @@ class _PlannedModel(nn.Module):
             raise rt.EsfError("the forward path is CUDA-only (sm_100a); got tensors on %s -- there is no CPU fallback"
                               % dev)
         plan = self._get_plan([tuple(t.shape) for t in x], dev)
-        for src, dst in zip(x, plan.inputs):
-            if src.data_ptr() != dst.data_ptr():
-                dst.copy_(src, non_blocking=True)
-        out = plan.run()
+        # FP32 contiguous clips are read in place by the stem kernels (launched outside the CUDA graph); anything else
+        # (other dtype / strides) is first converted into the plan-owned input buffers
+        direct = all(t.dtype == torch.float32 and t.is_contiguous() and t.data_ptr() % 16 == 0 for t in x)
+        if not direct:
+            for src, dst in zip(x, plan.inputs):
+                if src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+        out = plan.run(list(x) if direct else None)
         return out.clone()
 
     def _emit_fuse(self, plan, fuse, cur):

@@ -202,3 +202,17 @@ def test_perform_test_multi_view_ensemble(esf_lib):
     top1 = (want.argmax(1) == torch.tensor([5, 17, 3])).float().mean().item() * 100
     assert stats["top1_acc"] == "{:.2f}".format(top1) and stats["complete"]
     assert meter.clip_count.sum() == 0      # reset after finalize, like the reference
+
+
+def test_forward_reads_caller_tensors_in_place_or_converts(esf_lib):
+    """FP32 contiguous clips are read in place by the stem kernels (no staging copy); other dtypes / strides go through
+    the plan-owned input buffers.  Same answer either way, also when alternating between the two."""
+    cfg, model, gold, y0 = _run("slowfast_r50", "s64")
+    xs = [t.cuda() for t in helpers.case_inputs("slowfast_r50", "s64")]
+    with torch.no_grad():
+        y_f64 = model([t.double() for t in xs]).cpu()                                  # converted
+        y_nc = model([t.transpose(3, 4).contiguous().transpose(3, 4) for t in xs]).cpu()   # non-contiguous
+        y_again = model(xs).cpu()                                                      # in place
+        y_other = model([t * 0.5 for t in xs]).cpu()
+    assert torch.equal(y_f64, y0) and torch.equal(y_nc, y0) and torch.equal(y_again, y0)
+    assert not torch.equal(y_other, y0)
