@@ -20,10 +20,16 @@ from .engine import Plan, fold_conv_bn
 
 # video_model_builder.py:16-90 / custom_video_model_builder.py:151-168
 _MODEL_STAGE_DEPTH = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
-_TEMPORAL_KERNEL_BASIS = {
+_TEMPORAL_KERNEL_BASIS = {     # video_model_builder.py:20-75
+    "c2d": [[[1]], [[1]], [[1]], [[1]], [[1]]],
+    "c2d_nopool": [[[1]], [[1]], [[1]], [[1]], [[1]]],
+    "i3d": [[[5]], [[3]], [[3, 1]], [[3, 1]], [[1, 3]]],
+    "i3d_nopool": [[[5]], [[3]], [[3, 1]], [[3, 1]], [[1, 3]]],
+    "slow": [[[1]], [[1]], [[1]], [[3]], [[3]]],
     "slowfast": [[[1], [5]], [[1], [3]], [[1], [3]], [[3], [3]], [[3], [3]]],
 }
-_POOL1 = {"slowfast": [[1, 1, 1], [1, 1, 1]]}
+_POOL1 = {"c2d": [[2, 1, 1]], "c2d_nopool": [[1, 1, 1]], "i3d": [[2, 1, 1]], "i3d_nopool": [[1, 1, 1]],
+          "slow": [[1, 1, 1]], "slowfast": [[1, 1, 1], [1, 1, 1]]}
 
 
 class _Holder(nn.Module):
@@ -525,3 +531,99 @@ class SlowFast(_TwoStreamResNet):
     def __init__(self, cfg):
         super().__init__()
         self._build(cfg, dual_attention=False)
+
+
+@MODEL_REGISTRY.register()
+class ResNet(_TwoStreamResNet):
+    """video_model_builder.py:419-611: single-pathway ResNet (C2D, I3D, Slow) without lateral connections.  Same
+    stem / bottleneck / head kernels as the two-stream models; the max-pool after res2 is real here (kernel = stride =
+    _POOL1[arch], e.g. (2,1,1) for c2d / i3d).  Nonlocal blocks are not built (NONLOCAL.LOCATION must be empty)."""
+
+    num_pathways = 1
+
+    def __init__(self, cfg):
+        super().__init__()
+        assert cfg.MODEL.ARCH in _POOL1.keys()
+        pool_size = _POOL1[cfg.MODEL.ARCH]
+        assert len({len(pool_size), self.num_pathways}) == 1
+        assert cfg.RESNET.DEPTH in _MODEL_STAGE_DEPTH.keys()
+        if cfg.DETECTION.ENABLE:
+            raise NotImplementedError("DETECTION.ENABLE (ResNetRoIHead) is out of scope")
+        self.norm_module = get_norm(cfg)
+        self.enable_detection = False
+        depths = _MODEL_STAGE_DEPTH[cfg.RESNET.DEPTH]
+        num_groups, wpg = cfg.RESNET.NUM_GROUPS, cfg.RESNET.WIDTH_PER_GROUP
+        dim_inner = num_groups * wpg
+        tk = _TEMPORAL_KERNEL_BASIS[cfg.MODEL.ARCH]
+        self.s1 = VideoModelStem(dim_in=cfg.DATA.INPUT_CHANNEL_NUM, dim_out=[wpg], kernel=[tk[0][0] + [7, 7]],
+                                 stride=[[1, 2, 2]], padding=[[tk[0][0][0] // 2, 3, 3]], norm_module=self.norm_module)
+        c_prev = wpg
+        for i, name in enumerate(("s2", "s3", "s4", "s5")):
+            c_out = wpg * 4 * (2 ** i)
+            setattr(self, name, ResStage(
+                dim_in=[c_prev], dim_out=[c_out], dim_inner=[dim_inner * (2 ** i)], temp_kernel_sizes=tk[i + 1],
+                stride=cfg.RESNET.SPATIAL_STRIDES[i], num_blocks=[depths[i]], num_groups=[num_groups],
+                num_block_temp_kernel=cfg.RESNET.NUM_BLOCK_TEMP_KERNEL[i], nonlocal_inds=cfg.NONLOCAL.LOCATION[i],
+                dilation=cfg.RESNET.SPATIAL_DILATIONS[i], trans_func_name=cfg.RESNET.TRANS_FUNC,
+                stride_1x1=cfg.RESNET.STRIDE_1X1, norm_module=self.norm_module))
+            if name == "s2":
+                self.add_module("pathway0_pool",
+                                nn.MaxPool3d(kernel_size=pool_size[0], stride=pool_size[0], padding=[0, 0, 0]))
+            c_prev = c_out
+        if cfg.MULTIGRID.SHORT_CYCLE:
+            head_pool = [None, None]    # as in the reference (video_model_builder.py:584-586): the head then rejects it
+        else:
+            c = cfg.DATA.CROP_SIZE // 32
+            head_pool = [[cfg.DATA.NUM_FRAMES // pool_size[0][0], c // pool_size[0][1], c // pool_size[0][2]]]
+        self.head = ResNetBasicHead(dim_in=[wpg * 32], num_classes=cfg.MODEL.NUM_CLASSES, pool_size=head_pool,
+                                    dropout_rate=cfg.MODEL.DROPOUT_RATE, act_func=cfg.MODEL.HEAD_ACT)
+        init_weights(self, cfg.MODEL.FC_INIT_STD, cfg.RESNET.ZERO_INIT_FINAL_BN)
+        self._init_runtime(cfg)
+
+    def _compile(self, plan):
+        cfg = self._cfg
+        x = plan.inputs[0]
+        B, _, T, H, W = x.shape
+        wpg = cfg.RESNET.WIDTH_PER_GROUP
+
+        def conv_out(n, k, s, p, d=1):
+            return (n + 2 * p - d * (k - 1) - 1) // s + 1
+
+        stem = self.s1.pathway0_stem
+        k, s, p = stem.kernel, stem.stride, stem.padding
+        To, Ho, Wo = conv_out(T, k[0], s[0], p[0]), conv_out(H, k[1], s[1], p[1]), conv_out(W, k[2], s[2], p[2])
+        y = plan.act(B, To, Ho, Wo, wpg)
+        w, b = fold_conv_bn(stem.conv.weight, None, stem.bn)
+        plan.stem(x, y, w, b, tuple(s), tuple(p), act=rt.ACT_RELU)
+        cur = plan.act(B, To, conv_out(Ho, 3, 2, 1), conv_out(Wo, 3, 2, 1), wpg, name="s1_cat0")
+        plan.pool(y, cur, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+        for i, name in enumerate(("s2", "s3", "s4", "s5")):
+            stage = getattr(self, name)
+            co = wpg * 4 * (2 ** i)
+            stride, dil = cfg.RESNET.SPATIAL_STRIDES[i][0], cfg.RESNET.SPATIAL_DILATIONS[i][0]
+            _, T, H, W, _ = cur.shape
+            Ho, Wo = conv_out(H, 1, stride, 0), conv_out(W, 1, stride, 0)
+            dst = plan.act(B, T, Ho, Wo, co, name="%s_cat0" % name)
+            nblocks = stage.num_blocks[0]
+            ping = [plan.act(B, T, Ho, Wo, co) for _ in range(min(2, nblocks - 1))]
+            xin = cur
+            for bi in range(nblocks):
+                yb = dst if bi == nblocks - 1 else ping[bi % 2]
+                self._emit_block(plan, getattr(stage, "pathway0_res{}".format(bi)), xin, yb, stride if bi == 0 else 1, dil)
+                xin = yb
+            cur = dst
+            if name == "s2":
+                ks = [int(v) for v in self.pathway0_pool.kernel_size]
+                if ks != [1, 1, 1]:
+                    _, T, H, W, _ = cur.shape
+                    pooled = plan.act(B, (T - ks[0]) // ks[0] + 1, (H - ks[1]) // ks[1] + 1, (W - ks[2]) // ks[2] + 1, co,
+                                      name="s2_pool0")
+                    plan.pool(cur, pooled, tuple(ks), tuple(ks), (0, 0, 0))
+                    cur = pooled
+        ps = self.head.pool_size[0]
+        if ps is not None and [int(v) for v in ps] != list(cur.shape[1:4]):
+            raise NotImplementedError("head AvgPool3d kernel %s smaller than the feature map %s is not built yet; use "
+                                      "MULTIGRID.SHORT_CYCLE or matching DATA.CROP_SIZE/NUM_FRAMES"
+                                      % (ps, list(cur.shape[1:4])))
+        act = {"softmax": rt.HEAD_SOFTMAX, "sigmoid": rt.HEAD_SIGMOID}[self.head.act_func]
+        plan.head([cur], self.head.projection.weight, self.head.projection.bias, act)

@@ -1,10 +1,11 @@
 """TEST INFRASTRUCTURE ONLY -- CPU oracle for the batched clip forward path.
 
 A functional, state_dict-driven restatement (torch CPU ops, FP32 or FP64) of the
-reference's eval-mode forward for the two ResNet-50 based two-stream models:
+reference's eval-mode forward for the ResNet based models:
 
   * SlowFastDualAttention  (SlowFast/slowfast/models/custom_video_model_builder.py:171-445)
   * SlowFast               (SlowFast/slowfast/models/video_model_builder.py:153-416)
+  * ResNet                 (SlowFast/slowfast/models/video_model_builder.py:419-611; C2D / I3D / Slow, no Nonlocal)
 
 Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference`
 legs of `bench.py` may import this file.  The product package never does: the
@@ -28,9 +29,15 @@ BN_EPS = 1e-5  # every BatchNorm3d on the path is built with eps=1e-5 (resnet_he
 # custom_video_model_builder.py:151-168 / video_model_builder.py:16-90
 STAGE_DEPTH = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
 TEMPORAL_KERNEL_BASIS = {
+    "c2d": [[[1]], [[1]], [[1]], [[1]], [[1]]],
+    "c2d_nopool": [[[1]], [[1]], [[1]], [[1]], [[1]]],
+    "i3d": [[[5]], [[3]], [[3, 1]], [[3, 1]], [[1, 3]]],
+    "i3d_nopool": [[[5]], [[3]], [[3, 1]], [[3, 1]], [[1, 3]]],
+    "slow": [[[1]], [[1]], [[1]], [[3]], [[3]]],
     "slowfast": [[[1], [5]], [[1], [3]], [[1], [3]], [[3], [3]], [[3], [3]]],
 }
-POOL1 = {"slowfast": [[1, 1, 1], [1, 1, 1]]}
+POOL1 = {"c2d": [[2, 1, 1]], "c2d_nopool": [[1, 1, 1]], "i3d": [[2, 1, 1]], "i3d_nopool": [[1, 1, 1]],
+         "slow": [[1, 1, 1]], "slowfast": [[1, 1, 1], [1, 1, 1]]}
 
 
 def _bn(x, sd, p):
@@ -209,9 +216,41 @@ def slowfast_forward(cfg, sd, inputs, dtype=torch.float32, taps=None):
     return _resnet_two_stream(cfg, sd, inputs, lambda xs, s, p: fuse_fast_to_slow(xs, s, p, a), dtype, taps)
 
 
+def resnet_forward(cfg, sd, inputs, dtype=torch.float32, taps=None):
+    """ResNet.forward (video_model_builder.py:599-611): single pathway C2D / I3D / Slow, eval mode, no Nonlocal.
+    The temporal kernels of the blocks are read from the weights; the only arch-dependent step is the max-pool after
+    res2 (kernel = stride = _POOL1[arch], video_model_builder.py:503-509)."""
+    assert len(inputs) == 1, "Input tensor does not contain 1 pathway"
+    depth = STAGE_DEPTH[cfg.RESNET.DEPTH]
+    sd = {k: v.detach().to("cpu") for k, v in sd.items()}
+    xs = [inputs[0].detach().to("cpu", dtype)]
+
+    def tap(name, val):
+        if taps is not None:
+            taps[name] = [t.clone() for t in val]
+
+    xs = [resnet_stem(xs[0], sd, "s1.pathway0_stem")]
+    tap("s1", xs)
+    pool = POOL1[cfg.MODEL.ARCH][0]
+    for i, stage in enumerate(("s2", "s3", "s4", "s5")):
+        xs = res_stage(xs, sd, stage, [depth[i]], cfg.RESNET.SPATIAL_STRIDES[i], cfg.RESNET.SPATIAL_DILATIONS[i],
+                       [cfg.RESNET.NUM_GROUPS], cfg.RESNET.STRIDE_1X1)
+        tap(stage, xs)
+        if stage == "s2":
+            xs = [F.max_pool3d(xs[0], kernel_size=pool, stride=pool, padding=0)]
+    assert not cfg.MULTIGRID.SHORT_CYCLE, "pathway dimensions are not consistent."   # as the reference head asserts
+    c = cfg.DATA.CROP_SIZE // 32
+    pools = [[cfg.DATA.NUM_FRAMES // pool[0], c // pool[1], c // pool[2]]]
+    y, logits = resnet_basic_head(xs, sd, "head", pools, cfg.MODEL.HEAD_ACT, return_logits=True)
+    if taps is not None:
+        taps["logits"], taps["head"] = logits.clone(), y.clone()
+    return y
+
+
 FORWARDS = {
     "SlowFastDualAttention": slowfast_dual_attention_forward,
     "SlowFast": slowfast_forward,
+    "ResNet": resnet_forward,
 }
 
 

@@ -39,7 +39,7 @@ def make_case(name):
     spec = recipe.CASES[name]
     cfg = ref_shim.get_cfg(spec["yaml"], spec["opts"])
     assert cfg.MODEL.MODEL_NAME == spec["model"]
-    alpha = cfg.SLOWFAST.ALPHA
+    alpha = 0 if spec.get("single") else cfg.SLOWFAST.ALPHA
     torch.manual_seed(0)
     model = ref_shim.build_reference_model(cfg)
     sd = recipe.seeded_state_dict(model.state_dict(), seed=0, stress=spec.get("stress", False))

@@ -76,6 +76,8 @@ def seeded_clip(batch, frames, size, seed=1, channels=3):
 
 def pack_pathway_output(frames, alpha):
     """datasets/utils.py:73-112 (arch 'slowfast'): slow = frames[:, :, linspace(0, T-1, T//alpha).long()]."""
+    if not alpha:                     # single-pathway archs (c2d / i3d / slow): datasets/utils.py:86-88
+        return [frames]
     T = frames.shape[2]
     idx = torch.linspace(0, T - 1, T // alpha).long().to(frames.device)
     return [frames.index_select(2, idx).contiguous(), frames]
@@ -109,6 +111,14 @@ CASES = {
     "ghostnet_w1": dict(        # BASELINE configs[3]: SlowFastGhostNet width 1.0 (224^2 x 32 frames has N = 100 352)
         model="SlowFastGhostNet", yaml="configs/Kinetics/SLOWFAST_GHOSTNET_8x8_R50_stepwise_multigrid.yaml",
         opts=["SLOWFAST.WIDTH_MULTI", 1.0], calib=(2, 16, 112), inputs=[("s112", 2, 16, 112), ("s64", 2, 16, 64)]),
+    # section 8(f3): single-pathway ResNet.  The reference cannot build it with MULTIGRID.SHORT_CYCLE (its head gets two
+    # pool sizes for one pathway, video_model_builder.py:584-586), so the crop is fixed per case.
+    "i3d_r50": dict(            # I3D temporal kernels, (2,1,1) max-pool after res2
+        model="ResNet", yaml="configs/Kinetics/I3D_8x8_R50.yaml", single=True,
+        opts=[], calib=(2, 8, 224), inputs=[("s224", 1, 8, 224)]),
+    "slow_r50": dict(
+        model="ResNet", yaml="configs/Kinetics/SLOW_8x8_R50.yaml", single=True,
+        opts=["DATA.CROP_SIZE", 64], calib=(2, 8, 64), inputs=[("s64", 2, 8, 64)]),
     "dual_r50_stress": dict(
         model="SlowFastDualAttention", yaml="configs/Kinetics/SLOWFAST_DUAL_8x8_R50_stepwise_multigrid.yaml",
         stress=True, opts=[], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),

@@ -31,6 +31,11 @@ def case_cfg(name):
         cfg = esf.slowfast_ghostnet_cfg(1.0)
     elif name == "shufflenet_w2g3":
         cfg = esf.slowfast_shufflenet_cfg(2.0, 3)
+    elif name == "i3d_r50":
+        cfg = esf.resnet_cfg("i3d")
+    elif name == "slow_r50":
+        cfg = esf.resnet_cfg("slow")
+        cfg.DATA.CROP_SIZE = 64
     else:
         raise KeyError(name)
     cfg.NUM_GPUS = 0
@@ -58,7 +63,8 @@ def case_inputs(name, tag):
     for t, b, frames, crop in recipe.CASES[name]["inputs"]:
         if t == tag:
             cfg = case_cfg(name)
-            return recipe.pack_pathway_output(recipe.seeded_clip(b, frames, crop, seed=1), cfg.SLOWFAST.ALPHA)
+            alpha = 0 if recipe.CASES[name].get("single") else cfg.SLOWFAST.ALPHA
+            return recipe.pack_pathway_output(recipe.seeded_clip(b, frames, crop, seed=1), alpha)
     raise KeyError(tag)
 
 

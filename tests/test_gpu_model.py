@@ -30,7 +30,8 @@ def _run(name, tag, precision="fp16"):
                                       ("slowfast_r50", "s224"), ("shufflenetv2_w05", "s112"),
                                       ("shufflenetv2_w05", "s224"), ("shufflenet_w2g3", "s112"),
                                       ("shufflenet_w2g3", "s64"), ("mobilenetv2_w1", "s112"),
-                                      ("mobilenetv2_w1", "s224"), ("ghostnet_w1", "s112"), ("ghostnet_w1", "s64")])
+                                      ("mobilenetv2_w1", "s224"), ("ghostnet_w1", "s112"), ("ghostnet_w1", "s64"),
+                                      ("i3d_r50", "s224"), ("slow_r50", "s64")])
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 def test_model_matches_reference_golden(esf_lib, name, tag, precision):
     cfg, model, gold, y = _run(name, tag, precision)

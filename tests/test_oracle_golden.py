@@ -13,7 +13,8 @@ from oracle import slowfast_oracle as O
                                       ("dual_r50_stress", "s64"), ("shufflenetv2_w05", "s112"),
                                       ("shufflenetv2_w05", "s224"), ("shufflenet_w2g3", "s112"),
                                       ("shufflenet_w2g3", "s64"), ("mobilenetv2_w1", "s112"),
-                                      ("mobilenetv2_w1", "s224"), ("ghostnet_w1", "s112"), ("ghostnet_w1", "s64")])
+                                      ("mobilenetv2_w1", "s224"), ("ghostnet_w1", "s112"), ("ghostnet_w1", "s64"),
+                                      ("i3d_r50", "s224"), ("slow_r50", "s64")])
 def test_oracle_matches_reference_golden(name, tag):
     cfg, model, gold = helpers.case_model_and_weights(name)
     xs = helpers.case_inputs(name, tag)
@@ -30,7 +31,7 @@ def test_oracle_matches_reference_golden(name, tag):
                   "s7_fuse", "s8"):
         if sname not in taps:
             continue            # the ShuffleNet models end at s4_fuse
-        for pw in range(2):
+        for pw in range(len(taps[sname])):
             t = taps[sname][pw]
             assert list(t.shape) == list(gold["%s/%s/%d/shape" % (tag, sname, pw)])
             flat = t.reshape(-1)

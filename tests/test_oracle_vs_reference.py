@@ -11,7 +11,7 @@ pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="/root/referenc
 
 
 @pytest.mark.parametrize("name", ["dual_r50", "slowfast_r50", "shufflenetv2_w05", "shufflenet_w2g3", "mobilenetv2_w1",
-                                  "ghostnet_w1"])
+                                  "ghostnet_w1", "i3d_r50", "slow_r50"])
 def test_every_stage_bit_exact(name):
     spec = recipe.CASES[name]
     cfg = ref_shim.get_cfg(spec["yaml"], spec["opts"])
@@ -22,7 +22,10 @@ def test_every_stage_bit_exact(name):
     ref.load_state_dict(recipe.seeded_state_dict(ref.state_dict(), seed=0, bn_stats=bn,
                                                   stress=spec.get("stress", False)), strict=True)
     ref.eval()
-    xs = recipe.pack_pathway_output(recipe.seeded_clip(2, 32, 48, seed=5), cfg.SLOWFAST.ALPHA)
+    if spec.get("single"):      # fixed head pool: the clip must have the cfg's frames / crop
+        xs = [recipe.seeded_clip(1, cfg.DATA.NUM_FRAMES, cfg.DATA.CROP_SIZE, seed=5)]
+    else:
+        xs = recipe.pack_pathway_output(recipe.seeded_clip(2, 32, 48, seed=5), cfg.SLOWFAST.ALPHA)
     got = {}
     hooks = [getattr(ref, n).register_forward_hook(lambda m, i, o, n=n: got.__setitem__(n, [t.clone() for t in o]))
              for n in ("s0", "s1", "s1_fuse", "s2", "s2_fuse", "s3", "s3_fuse", "s4", "s4_fuse", "s5", "s5_fuse", "s6",
@@ -34,13 +37,13 @@ def test_every_stage_bit_exact(name):
     taps = {}
     y = O.forward(cfg, ref.state_dict(), xs, taps=taps)
     for n, ts in got.items():
-        for pw in range(2):
+        for pw in range(len(ts)):
             assert torch.equal(ts[pw], taps[n][pw]), (n, pw)
     assert torch.equal(y, y_ref)
 
 
 @pytest.mark.parametrize("name", ["dual_r50", "slowfast_r50", "shufflenetv2_w05", "shufflenet_w2g3", "mobilenetv2_w1",
-                                  "ghostnet_w1"])
+                                  "ghostnet_w1", "i3d_r50", "slow_r50"])
 def test_state_dict_schema_and_seeded_init_match_reference(name):
     import efficient_slowfast_b200 as esf
 
