@@ -17,6 +17,7 @@
 // Reference ops replaced: SpatialAttention.forward (wdf_attention_helper.py:33-54) + bn_s2f + ReLU + nearest x alpha
 // upsample + concat (custom_video_model_builder.py:142-146).
 #include <math_constants.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -368,13 +369,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
 // What DID help after instrumenting the loop with clock64 (-DESF_ATTN_TIMING): the softmax warps found S_{j+1} missing
 // on 87 % of the tiles (~200 of ~1500 cycles) because one warp issued both MMAs and could only issue S_{j+1} after it
 // had waited for both halves of P_{j-1}; a Q.K^T issuer warp of its own removed that wait (-4 .. -8 %).
+// The FMA-pipe exponential was repeated with packed sm_100 arithmetic (FFMA2 / FADD2.RM, 5.5 issue slots per element
+// instead of ~8; template parameter POLY, knob ESF_ATTN_POLY = pairs of every 8): correct (kernel tests green at 2/8
+// and 4/8) but no faster -- d = 8: 3.26 / 3.16 / 3.07 / 3.31 / 3.05 Texp/s at 0 .. 4/8, d = 32: 2.97 / 2.96 / 2.93 /
+// 2.82 / 2.61 (8 clips, N = 25 088).  The scale FFMA of every pair is an FFMA2 since then.  Default stays MUFU only.
 // TMEM columns: S[q][buf] 4 x 64 | O[q][h] 4 x DVp (<= 48) | P[q][h] 4 x 16  = 512.
 // 16 softmax warps + TMA producer + Q.K^T issuer + 2 P.V issuers.  20 warps: ptxas sizes the register file for the
 // block rounded up to 128 threads, so 21 warps would cap the softmax threads at 80 registers (spills).
 constexpr int kV2Threads = 640;
 constexpr int kV2PCol = 448;     // first TMEM column of P
+constexpr int kV2DefaultPoly = 0;
 
-template <bool F16>
+// exp2 of a pair on the FMA pipe (packed FFMA2 / FADD2, sm_100): Cody-Waite split x = floor(x) + f with the
+// round-down magic-number add, degree-3 minimax polynomial for 2^f on [0, 1) (max relative error 8.8e-5, below the
+// half-ulp of the 16-bit P it is rounded to), exponent inserted with an integer add.  x is clamped at -126: smaller
+// arguments would wrap the exponent field (2^-126 rounds to 0 in P).
+__device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 t = __fadd2_rd(x, make_float2(12582912.f, 12582912.f));       // 1.5 * 2^23 + floor(x)
+  const float2 fl = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 fr = __ffma2_rn(fl, make_float2(-1.f, -1.f), x);              // exact
+  float2 pl = __ffma2_rn(fr, make_float2(0.077119089663028717f, 0.077119089663028717f),
+                         make_float2(0.227564394474029541f, 0.227564394474029541f));
+  pl = __ffma2_rn(pl, fr, make_float2(0.695146143436431885f, 0.695146143436431885f));
+  pl = __ffma2_rn(pl, fr, make_float2(1.f, 1.f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
+// POLY: how many of every 8 element pairs take the FMA-pipe exponential instead of MUFU.EX2 (0 = none)
+template <bool F16, int POLY>
 __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -565,12 +592,24 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
       float ms = (m == -CUDART_INF_F) ? 0.f : m * kTcLog2e;
       float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
       ESF_TICK(0)   // tail mask + ping-pong wait
+      const float2 ms2 = make_float2(-ms, -ms), c2 = make_float2(kTcLog2e, kTcLog2e);
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         mx0 = fmaxf(fmaxf(mx0, v[i]), v[i + 1]);
         mx1 = fmaxf(fmaxf(mx1, v[i + 2]), v[i + 3]);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[i + e] = fast_exp2(fmaf(v[i + e], kTcLog2e, -ms));
+        for (int e = 0; e < 4; e += 2) {
+          const int k = (i + e) >> 1;   // pair index 0..15
+          float2 x = __ffma2_rn(make_float2(v[i + e], v[i + e + 1]), c2, ms2);
+          if (POLY > 0 && ((k * POLY) & 7) < POLY) {
+            x = poly_exp2_pair(x);
+          } else {
+            x.x = fast_exp2(x.x);
+            x.y = fast_exp2(x.y);
+          }
+          v[i + e] = x.x;
+          v[i + e + 1] = x.y;
+        }
       }
       const float mx = fmaxf(mx0, mx1);
       asm volatile("" ::"f"(v[31]), "f"(mx));
@@ -848,10 +887,20 @@ struct AttnTcOp : esf_op {
   dim3 grid;
   int smem_bytes = 0;
   int v2 = 0;
+  int poly = 0;   // pairs of every 8 whose exponential runs on the FMA pipe (v2 only)
   int launch(cudaStream_t stream) override {
     if (v2) {
-      if (params.f16) attn_tc_v2_kernel<true><<<grid, kV2Threads, smem_bytes, stream>>>(params);
-      else attn_tc_v2_kernel<false><<<grid, kV2Threads, smem_bytes, stream>>>(params);
+#define ESF_V2_LAUNCH(PL)                                                                             \
+  if (params.f16) attn_tc_v2_kernel<true, PL><<<grid, kV2Threads, smem_bytes, stream>>>(params);       \
+  else attn_tc_v2_kernel<false, PL><<<grid, kV2Threads, smem_bytes, stream>>>(params);
+      switch (poly) {
+        case 1: ESF_V2_LAUNCH(1) break;
+        case 2: ESF_V2_LAUNCH(2) break;
+        case 3: ESF_V2_LAUNCH(3) break;
+        case 4: ESF_V2_LAUNCH(4) break;
+        default: ESF_V2_LAUNCH(0) break;
+      }
+#undef ESF_V2_LAUNCH
       return check_launch("attn_tc_v2_kernel");
     }
     attn_tc_kernel<<<grid, kTcThreads, smem_bytes, stream>>>(params);
@@ -978,6 +1027,11 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
   p.k_tile_bytes = kTcBN * g.KQ * 2;
   p.v_tile_bytes = g.DVp * 128;
   op->v2 = g.v2;
+  {
+    const char* e = getenv("ESF_ATTN_POLY");   // experiment knob; default chosen from measurements (see header)
+    op->poly = e ? atoi(e) : kV2DefaultPoly;
+    if (op->poly < 0 || op->poly > 4) op->poly = 0;
+  }
   // v1 streams P through 2 x 16 KB of shared memory; v2 keeps P in TMEM and needs 2 KB for the split-K maxima
   const int fixed = 1024 + 2 * (int)p.q_tile_bytes + 512 + (g.v2 ? 2048 : 2 * 16384);
   int stages = (kTcSmemLimit - fixed) / (int)(p.k_tile_bytes + p.v_tile_bytes);
@@ -997,10 +1051,13 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(attn_tc_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(attn_tc_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+#define ESF_V2_ATTR(PL)                                                                                                  \
+  if (e == cudaSuccess)                                                                                                  \
+    e = cudaFuncSetAttribute(attn_tc_v2_kernel<true, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);    \
+  if (e == cudaSuccess)                                                                                                  \
+    e = cudaFuncSetAttribute(attn_tc_v2_kernel<false, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+      ESF_V2_ATTR(0) ESF_V2_ATTR(1) ESF_V2_ATTR(2) ESF_V2_ATTR(3) ESF_V2_ATTR(4)
+#undef ESF_V2_ATTR
       if (e != cudaSuccess) rc = set_error(ESF_ERR_CUDA, "cudaFuncSetAttribute(attn_tc) failed: %s", cudaGetErrorString(e));
       else attr_set = true;
     }
