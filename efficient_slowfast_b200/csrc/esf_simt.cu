@@ -128,6 +128,99 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------- uint8 frames
+// The decoder's frames arrive as uint8 (B, Tsrc, H, W, C) -- already channels-last.  The reference normalises them on
+// the host (tensor_normalize: x/255 - mean, /std, datasets/utils.py:298-315), permutes to C,T,H,W and gathers the slow
+// pathway's frames by index (pack_pathway_output, datasets/utils.py:73-112), then ships FP32.  Here the byte frames
+// are shipped and these kernels do all of it: lut[c][u] holds the normalised value of byte u in (output) channel c,
+// built on the host with the reference's own FP32 operations, so the values are bit-identical; chan_src maps an output
+// channel to its source channel (DATA.REVERSE_INPUT_CHANNEL); t_index (device, T entries, or null) is the frame gather.
+struct FramesParams {
+  const uint8_t* frames;
+  const int32_t* t_index;
+  int B, Tsrc, T, H, W, C;
+  int chan_src[4];
+};
+
+// -> packed 16-bit stem rows [B][T][H][pitch] (see stem_pack_kernel): one thread = 8 consecutive row elements
+__global__ void __launch_bounds__(256) stem_pack_u8_kernel(const FramesParams p, const uint16_t* __restrict__ lut, int pitch,
+                                                           int lpad, uint16_t* __restrict__ xp) {
+  __shared__ uint16_t lut_s[4 * 256];
+  for (int i = threadIdx.x; i < p.C * 256; i += blockDim.x) lut_s[i] = lut[i];
+  __syncthreads();
+  const int chunks = pitch / 8;
+  const int WC = p.W * p.C;
+  const bool direct = p.chan_src[0] == 0 && p.chan_src[1] == 1 && p.chan_src[2] == 2 && p.chan_src[3] == 3;
+  const long long total = (long long)p.B * p.T * p.H * chunks;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ck = idx % chunks;
+    long long r = idx / chunks;
+    const int h = r % p.H;
+    r /= p.H;
+    const int t = r % p.T;
+    const int b = r / p.T;
+    const int ts = p.t_index ? __ldg(p.t_index + t) : t;
+    const uint8_t* row = p.frames + (((long long)b * p.Tsrc + ts) * p.H + h) * WC;
+    const int j0 = ck * 8 - lpad;
+    int c = ((j0 % p.C) + p.C) % p.C;
+    uint16_t v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = j0 + e;
+      uint16_t o = 0;
+      if (j >= 0 && j < WC) {
+        const int js = direct ? j : j - c + p.chan_src[c];
+        o = lut_s[c * 256 + __ldg(row + js)];
+      }
+      v[e] = o;
+      c = (c + 1 == p.C) ? 0 : c + 1;
+    }
+    uint4 o4;
+    o4.x = v[0] | (uint32_t)v[1] << 16;
+    o4.y = v[2] | (uint32_t)v[3] << 16;
+    o4.z = v[4] | (uint32_t)v[5] << 16;
+    o4.w = v[6] | (uint32_t)v[7] << 16;
+    *reinterpret_cast<uint4*>(xp + (((long long)b * p.T + t) * p.H + h) * pitch + ck * 8) = o4;
+  }
+}
+
+// -> FP32 NCDHW clip (B, C, T, H, W): the generic route for stems that do not take packed rows.  One thread = 4
+// consecutive w of one (b, c, t, h) row (16-byte store).
+__global__ void __launch_bounds__(256) frames_to_clip_kernel(const FramesParams p, const float* __restrict__ lut,
+                                                             float* __restrict__ clip) {
+  __shared__ float lut_s[4 * 256];
+  for (int i = threadIdx.x; i < p.C * 256; i += blockDim.x) lut_s[i] = lut[i];
+  __syncthreads();
+  const int W4 = (p.W + 3) / 4;
+  const bool vec = (p.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(clip) & 15) == 0);
+  const long long total = (long long)p.B * p.C * p.T * p.H * W4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int w0 = (idx % W4) * 4;
+    long long r = idx / W4;
+    const int h = r % p.H;
+    r /= p.H;
+    const int t = r % p.T;
+    r /= p.T;
+    const int c = r % p.C;
+    const int b = r / p.C;
+    const int ts = p.t_index ? __ldg(p.t_index + t) : t;
+    const uint8_t* src = p.frames + ((((long long)b * p.Tsrc + ts) * p.H + h) * p.W + w0) * p.C + p.chan_src[c];
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = (w0 + e < p.W) ? lut_s[c * 256 + __ldg(src + e * p.C)] : 0.f;
+    float* dst = clip + ((((long long)b * p.C + c) * p.T + t) * p.H + h) * p.W + w0;
+    if (vec) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (w0 + e < p.W) dst[e] = v[e];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------- direct conv
 struct DirectParams {
   View x, y, res;
@@ -1058,6 +1151,45 @@ extern "C" int esf_stem_pack(const float* x, int32_t B, int32_t Cin, int32_t T, 
   stem_pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp));
   return check_launch("stem_pack_kernel");
+}
+
+static int frames_params(FramesParams* p, const uint8_t* frames, int32_t B, int32_t Tsrc, int32_t H, int32_t W, int32_t C,
+                         const int32_t* t_index, int32_t T, const int32_t* chan_src, const char* who) {
+  ESF_CHECK_ARG(frames && B > 0 && Tsrc > 0 && T > 0 && H > 0 && W > 0 && C >= 1 && C <= 4, "%s: null/bad argument", who);
+  ESF_CHECK_ARG(t_index || T == Tsrc, "%s: T (%d) != Tsrc (%d) needs a frame index", who, T, Tsrc);
+  p->frames = frames, p->t_index = t_index;
+  p->B = B, p->Tsrc = Tsrc, p->T = T, p->H = H, p->W = W, p->C = C;
+  for (int c = 0; c < 4; ++c) {
+    p->chan_src[c] = (chan_src && c < C) ? chan_src[c] : c;
+    ESF_CHECK_ARG(c >= C || (p->chan_src[c] >= 0 && p->chan_src[c] < C), "%s: chan_src[%d] out of range", who, c);
+  }
+  return ESF_OK;
+}
+
+extern "C" int esf_stem_pack_u8(const uint8_t* frames, int32_t B, int32_t Tsrc, int32_t H, int32_t W, int32_t C,
+                                const int32_t* t_index, int32_t T, const int32_t* chan_src, const void* lut16,
+                                int32_t pitch, int32_t lpad, void* xp, void* stream) {
+  FramesParams p;
+  const int rc = frames_params(&p, frames, B, Tsrc, H, W, C, t_index, T, chan_src, "esf_stem_pack_u8");
+  if (rc != ESF_OK) return rc;
+  ESF_CHECK_ARG(lut16 && xp, "esf_stem_pack_u8: null argument");
+  ESF_CHECK_ARG(pitch % 8 == 0 && lpad >= 0 && pitch >= lpad + W * C, "esf_stem_pack_u8: bad pitch %d", pitch);
+  const long long total = (long long)B * T * H * (pitch / 8);
+  stem_pack_u8_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, static_cast<const uint16_t*>(lut16), pitch, lpad, static_cast<uint16_t*>(xp));
+  return check_launch("stem_pack_u8_kernel");
+}
+
+extern "C" int esf_frames_to_clip(const uint8_t* frames, int32_t B, int32_t Tsrc, int32_t H, int32_t W, int32_t C,
+                                  const int32_t* t_index, int32_t T, const int32_t* chan_src, const float* lut32,
+                                  float* clip, void* stream) {
+  FramesParams p;
+  const int rc = frames_params(&p, frames, B, Tsrc, H, W, C, t_index, T, chan_src, "esf_frames_to_clip");
+  if (rc != ESF_OK) return rc;
+  ESF_CHECK_ARG(lut32 && clip, "esf_frames_to_clip: null argument");
+  const long long total = (long long)B * C * T * H * ((W + 3) / 4);
+  frames_to_clip_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, lut32, clip);
+  return check_launch("frames_to_clip_kernel");
 }
 
 extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {

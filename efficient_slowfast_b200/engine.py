@@ -140,6 +140,7 @@ class Plan:
         self.ops = []         # callables taking a stream pointer
         self.eager = []       # per op: launched outside the CUDA graph (reads a caller-provided input tensor)
         self.input_override = {}   # plan-owned input data_ptr -> data_ptr of the caller's tensor for this run
+        self.stem_routes = {}      # plan-owned input data_ptr -> (packed stem rows, pitch, lpad) of a banded stem
         self.handles = []     # esf_op* to destroy
         self.graph = None
         self.out = None
@@ -327,9 +328,11 @@ class Plan:
                                          ctypes.byref(yv), ctypes.byref(h)), "esf_stem_igemm_create")
         self.handles.append(h)
         m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
+        self.stem_routes[x_nc.data_ptr()] = (xp, pitch, lpad)   # the uint8 frame route writes xp itself (frames.py)
         self._add(lambda s: rt.check(L.esf_stem_pack(self._in_ptr(x_nc), B, Cin, T, H, W, pitch, lpad, self.a16,
                                                      xp.data_ptr(), s),
                                      "esf_stem_pack"), "stem_pack", "", nbytes=self._nbytes(x_nc, xp), eager=True)
+        self.meta[-1]["is_pack"] = True
         self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "stem_igemm",
                   "%dx%dx%d %d->%d banded" % (kt, kh, kw, Cin, cout), flops=2.0 * m * cout * Cin * kt * kh * kw,
                   nbytes=self._nbytes(xp, y) + wb.numel() * 2)
@@ -562,6 +565,21 @@ class Plan:
             for i in range(len(self.ops)):
                 times[i] = min(times[i], evs[i].elapsed_time(evs[i + 1]))
         return times
+
+    def run_frames(self, fill):
+        """Frame route: `fill()` launches the kernels that write the stem inputs from uint8 frames (frames.py); the
+        FP32 stem-pack launches are skipped, every other launch is the same as in run()."""
+        self.input_override = {}
+        fill()
+        s = rt.current_stream_ptr()
+        for op, eager, meta in zip(self.ops, self.eager, self.meta):
+            if meta.get("is_pack"):
+                continue
+            if eager or self.graph is None:
+                op(s)
+        if self.graph is not None:
+            self.graph.replay()
+        return self.out
 
     def run(self, inputs=None):
         """`inputs`: optional caller tensors to read INSTEAD of the plan-owned input buffers (same shape, FP32,

@@ -298,6 +298,37 @@ class _PlannedModel(nn.Module):
         out = plan.run(list(x) if direct else None)
         return out.clone()
 
+    def frame_shapes(self, frames_shape):
+        """[slow, fast] (or [single]) clip shapes that pack_pathway_output (datasets/utils.py:73-112) makes of uint8
+        frames (B, T, H, W, C)."""
+        B, T, H, W, C = frames_shape
+        if self.num_pathways == 1:
+            return [(B, C, T, H, W)]
+        return [(B, C, T // self._cfg.SLOWFAST.ALPHA, H, W), (B, C, T, H, W)]
+
+    def forward_frames(self, frames, bboxes=None):
+        """Same result as `forward(pack_pathway_output(cfg, tensor_normalize(frames, MEAN, STD).permute(...)))` of the
+        reference's loader chain, from the decoder's uint8 frames (B, T, H, W, C) on the device: normalisation,
+        layout change and the slow-pathway frame gather run inside the stem-pack kernel (frames.py)."""
+        from . import frames as esf_frames
+        if self.training:
+            raise NotImplementedError("eval-mode forward path only")
+        if bboxes is not None:
+            raise NotImplementedError("detection (bboxes) is out of scope")
+        if frames.device.type != "cuda":
+            raise rt.EsfError("the forward path is CUDA-only (sm_100a); got frames on %s -- there is no CPU fallback"
+                              % frames.device)
+        if frames.dtype != torch.uint8 or frames.dim() != 5 or not frames.is_contiguous():
+            raise rt.EsfError("forward_frames expects contiguous uint8 frames (B, T, H, W, C)")
+        dev = frames.device
+        plan = self._get_plan(self.frame_shapes(tuple(frames.shape)), dev)
+        fin = getattr(plan, "frame_input", None)
+        if fin is None:
+            fin = plan.frame_input = esf_frames.FrameInput(self._cfg, dev, plan.adt, channels=frames.shape[4])
+        alpha = self._cfg.SLOWFAST.ALPHA if self.num_pathways > 1 else 1
+        out = plan.run_frames(lambda: esf_frames.launch_frames(plan, fin, frames, alpha))
+        return out.clone()
+
     def _emit_fuse(self, plan, fuse, cur):
         (sbuf, soff, cs), (fbuf, foff, cf) = cur
         x_s = sbuf[..., soff:soff + cs]

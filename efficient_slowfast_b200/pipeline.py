@@ -19,16 +19,21 @@ from . import runtime as rt
 
 
 class ClipStream:
-    def __init__(self, model, shapes, device=None, depth=2, gather=False):
+    def __init__(self, model, shapes, device=None, depth=2, gather=False, frames=False):
         """`depth` staging slots (>= 2 overlaps copy and compute); `gather=True` all-gathers the predictions over the
-        process group before the D2H copy, like the reference's test loop."""
+        process group before the D2H copy, like the reference's test loop.  `frames=True`: every batch is ONE pinned
+        uint8 tensor of decoded frames (B, T, H, W, C) (`shapes` = [that shape]) and goes through
+        `model.forward_frames` -- normalisation and pathway packing on the device, 1/5 of the H2D bytes."""
         device = torch.device(device) if device is not None else next(model.parameters()).device
         if device.type != "cuda":
             raise rt.EsfError("ClipStream needs a CUDA device; there is no CPU fallback")
         assert depth >= 1
         self.model, self.device, self.depth, self.gather = model, device, depth, gather
         self.copy_stream = torch.cuda.Stream(device=device)
-        self.stage = [[torch.empty(tuple(s), dtype=torch.float32, device=device) for s in shapes] for _ in range(depth)]
+        self.frames = bool(frames)
+        assert not self.frames or len(shapes) == 1
+        dt = torch.uint8 if self.frames else torch.float32
+        self.stage = [[torch.empty(tuple(s), dtype=dt, device=device) for s in shapes] for _ in range(depth)]
         self.ready = [torch.cuda.Event() for _ in range(depth)]     # H2D of the slot finished
         self.consumed = [torch.cuda.Event() for _ in range(depth)]  # forward no longer reads the slot
         self.done = [torch.cuda.Event() for _ in range(depth)]      # predictions of the slot are on the host
@@ -51,7 +56,7 @@ class ClipStream:
                 d.copy_(h, non_blocking=True)
             self.ready[slot].record(self.copy_stream)
         cur.wait_event(self.ready[slot])
-        out = self.model(self.stage[slot])
+        out = self.model.forward_frames(self.stage[slot][0]) if self.frames else self.model(self.stage[slot])
         self.consumed[slot].record(cur)
         if self.gather:
             out = esf_dist.all_gather([out])[0]

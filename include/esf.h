@@ -109,6 +109,22 @@ int esf_stem_geometry(int32_t W, int32_t Cin, int32_t kW, int32_t sW, int32_t pW
                       int32_t* window);
 int esf_stem_pack(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
                   int32_t lpad, int32_t dtype, void* xp, void* stream);
+/* ---- uint8 frame input ---------------------------------------------------------------------
+ * Replaces the loader-side chain the reference runs on the host before the H2D copy: tensor_normalize
+ * (SlowFast/slowfast/datasets/utils.py:298-315: u8 -> float / 255, - mean, / std), permute(3,0,1,2)
+ * (datasets/kinetics.py:231-235) and pack_pathway_output (datasets/utils.py:73-112: channel reversal, slow-pathway
+ * frame gather by index).  frames: device uint8 (B, Tsrc, H, W, C) contiguous, C <= 4.  t_index: device int32[T]
+ * source frame of every output frame, or null for the identity (then T == Tsrc).  chan_src: host int32[C], source
+ * channel of every output channel, or null for the identity.  The look-up tables are built by the caller with the
+ * reference's own FP32 operations: lut[c * 256 + u] = normalised value of byte u in output channel c.
+ * esf_stem_pack_u8 writes the packed stem rows of esf_stem_pack directly (lut16: 16-bit values in the plan's
+ * storage format); esf_frames_to_clip writes the FP32 (B, C, T, H, W) clip for stems that read NCDHW (lut32). */
+int esf_stem_pack_u8(const uint8_t* frames, int32_t B, int32_t Tsrc, int32_t H, int32_t W, int32_t C,
+                     const int32_t* t_index, int32_t T, const int32_t* chan_src, const void* lut16, int32_t pitch,
+                     int32_t lpad, void* xp, void* stream);
+int esf_frames_to_clip(const uint8_t* frames, int32_t B, int32_t Tsrc, int32_t H, int32_t W, int32_t C,
+                       const int32_t* t_index, int32_t T, const int32_t* chan_src, const float* lut32, float* clip,
+                       void* stream);
 int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
                           const void* w_band, const float* bias_tiled, int32_t Cout, int32_t kT, int32_t kH,
                           int32_t kW, int32_t sH, int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t act,

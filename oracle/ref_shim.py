@@ -141,3 +141,17 @@ def build_reference_model(cfg):
     with contextlib.redirect_stdout(io.StringIO()):
         model = B.build_model(cfg)
     return model
+
+
+def reference_dataset_utils():
+    """slowfast/datasets/utils.py of the reference (tensor_normalize, pack_pathway_output) without executing the
+    package __init__, which imports the video decoders (`av`) that this image does not have."""
+    install()
+    import slowfast  # noqa: F401
+    name = "slowfast.datasets"
+    if name not in sys.modules or not hasattr(sys.modules[name], "__path__"):
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [os.path.join(REF_ROOT, "SlowFast", "slowfast", "datasets")]
+        sys.modules[name] = pkg
+    import importlib
+    return importlib.import_module("slowfast.datasets.utils")
