@@ -94,10 +94,15 @@ MODEL_CASES = {
 }
 
 
+def case_of(args_or_cfg):
+    return getattr(args_or_cfg, "case", None) or MODEL_CASES[args_or_cfg.model]
+
+
 def bench_cfg(args):
     import helpers
 
-    cfg = helpers.case_cfg(MODEL_CASES[args.model])
+    cfg = helpers.case_cfg(case_of(args))
+    cfg.ESF.BENCH_CASE = case_of(args)
     cfg.NUM_GPUS = 1
     cfg.DATA.CROP_SIZE = args.crop
     cfg.DATA.NUM_FRAMES = args.frames
@@ -112,7 +117,7 @@ def build_weights(cfg):
     import recipe
     import efficient_slowfast_b200 as esf
 
-    name = MODEL_CASES[cfg.MODEL.MODEL_NAME]
+    name = cfg.ESF.get("BENCH_CASE") or MODEL_CASES[cfg.MODEL.MODEL_NAME]
     c = cfg.clone()
     c.NUM_GPUS = 0
     torch.manual_seed(0)
@@ -124,10 +129,15 @@ def build_weights(cfg):
 
 
 def metric_name(args):
+    if args.case:
+        return "clips/sec %s fwd" % args.case
     return METRIC if args.model == "SlowFastDualAttention" else "clips/sec %s fwd" % args.model
 
 
 def workload_name(args):
+    if args.alpha == 0:
+        return "%s (single pathway) %dx%dx%dx%d fwd, batch %d per GPU, synthetic N(0,1) clips" % (
+            args.case, args.batch, args.frames, args.crop, args.crop, args.batch)
     return "%s %dx(%d|%d)x%dx%d fwd, batch %d per GPU, synthetic N(0,1) clips" % (
         args.model + (" R50" if args.model in ("SlowFast", "SlowFastDualAttention") else ""), args.batch, args.frames // args.alpha, args.frames, args.crop, args.crop, args.batch)
 
@@ -196,12 +206,13 @@ def run_gpu(args):
         cfg.ESF.CUDA_GRAPH = False
     model = build_weights(cfg).to(dev)
     B, T, S, alpha = args.batch, args.frames, args.crop, args.alpha
-    shapes = [(B, 3, T // alpha, S, S), (B, 3, T, S, S)]
+    shapes = [(B, 3, T // alpha, S, S), (B, 3, T, S, S)] if alpha else [(B, 3, T, S, S)]
     ins = model.input_buffers(shapes, dev)          # plan-owned static inputs (the CUDA graph reads these)
     plan = model._get_plan(shapes, dev)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
-    ins[1].normal_(generator=g)
-    ins[0].copy_(recipe.pack_pathway_output(ins[1], alpha)[0])
+    ins[-1].normal_(generator=g)
+    if alpha:
+        ins[0].copy_(recipe.pack_pathway_output(ins[1], alpha)[0])
     K = cfg.MODEL.NUM_CLASSES
 
     from efficient_slowfast_b200 import distributed as esf_dist
@@ -250,8 +261,9 @@ def run_gpu(args):
 
     # ---- end-to-end through the public API with pinned host inputs (H2D + forward + D2H per step)
     host = [torch.empty(s, dtype=torch.float32).pin_memory() for s in shapes]
-    host[1].normal_()
-    host[0].copy_(recipe.pack_pathway_output(host[1], alpha)[0])
+    host[-1].normal_()
+    if alpha:
+        host[0].copy_(recipe.pack_pathway_output(host[1], alpha)[0])
     host_out = torch.empty(B, K, dtype=torch.float32).pin_memory()
 
     # ClipStream = the package's public host-side loop: per batch H2D from pinned memory -> model.forward ->
@@ -386,6 +398,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="SlowFastDualAttention", choices=sorted(MODEL_CASES))
+    ap.add_argument("--case", default="", help="golden case (tests/golden/recipe.py CASES) instead of --model, e.g. "
+                    "slow_nln_r50 / i3d_nln_r50 / i3d_r50 / slow_r50 (single-pathway ResNet, section 8-f3)")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--frames", type=int, default=32)
     ap.add_argument("--crop", type=int, default=224)
@@ -399,6 +413,15 @@ def main():
                     help="for ncu: eager launches (no CUDA graph), 1 warm-up + --steps steps, nothing else")
     args = ap.parse_args()
     args.alpha = 8 if args.model == "SlowFast" else 4
+    if args.case:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import recipe
+        spec = recipe.CASES[args.case]
+        args.model = spec["model"]
+        if spec.get("single"):
+            args.alpha = 0
+        elif args.model == "SlowFast":
+            args.alpha = 8
     if args.impl == "reference":
         run_reference(args)
     else:

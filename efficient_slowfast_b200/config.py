@@ -112,14 +112,16 @@ def slowfast_dual_8x8_r50_cfg():
     return c
 
 
-def resnet_cfg(arch="i3d", num_frames=8):
+def resnet_cfg(arch="i3d", num_frames=8, nln=False):
     """configs/Kinetics/{C2D,I3D,SLOW}_8x8_R50.yaml: single-pathway ResNet-50, MODEL_NAME ResNet, ARCH c2d / i3d / slow."""
     c = get_cfg()
     c.RESNET._merge(dict(ZERO_INIT_FINAL_BN=True, WIDTH_PER_GROUP=64, NUM_GROUPS=1, DEPTH=50,
                          TRANS_FUNC="bottleneck_transform", STRIDE_1X1=False,
                          NUM_BLOCK_TEMP_KERNEL=[[3], [4], [6], [3]], SPATIAL_STRIDES=[[1], [2], [2], [2]],
                          SPATIAL_DILATIONS=[[1], [1], [1], [1]]))
-    c.NONLOCAL._merge(dict(LOCATION=[[[]], [[]], [[]], [[]]], GROUP=[[1], [1], [1], [1]],
+    # nln: configs/Kinetics/{C2D,I3D,SLOW}_NLN_8x8_R50.yaml
+    c.NONLOCAL._merge(dict(LOCATION=[[[]], [[1, 3]], [[1, 3, 5]], [[]]] if nln else [[[]], [[]], [[]], [[]]],
+                           GROUP=[[1], [1], [1], [1]],
                            INSTANTIATION="softmax" if arch != "slow" else "dot_product"))
     c.DATA._merge(dict(NUM_FRAMES=num_frames, INPUT_CHANNEL_NUM=[3]))
     c.MODEL._merge(dict(NUM_CLASSES=400, ARCH=arch, MODEL_NAME="ResNet", DROPOUT_RATE=0.5))

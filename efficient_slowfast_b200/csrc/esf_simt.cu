@@ -221,6 +221,60 @@ __global__ void __launch_bounds__(256) frames_to_clip_kernel(const FramesParams 
   }
 }
 
+// ------------------------------------------------------------------------------------------- Nonlocal helpers
+// Non-local block (SlowFast/slowfast/models/nonlocal_helper.py:105-148).  The two matrix products of a clip run as
+// implicit GEMMs whose "weights" are the clip's own phi rows / transposed g rows (engine.Plan.nonlocal_block); these
+// two kernels are the glue: the row normalisation of the affinity matrix and the g transpose.
+// mode 0: P = softmax_j(scale * S)  (instantiation "softmax", scale = dim_inner^-0.5, nonlocal_helper.py:127-130)
+// mode 1: P = scale * S             (instantiation "dot_product", scale = 1 / N_keys, nonlocal_helper.py:131-133)
+// One warp per row: the row (n <= a few thousand FP32) is read three times, the second and third from L1.
+__global__ void __launch_bounds__(256) row_softmax_kernel(const float* __restrict__ S, long long rows, int n, long long s_pitch,
+                                                          float scale, int mode, int f16, __nv_bfloat16* __restrict__ P,
+                                                          long long p_pitch) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    const float* s = S + r * s_pitch;
+    __nv_bfloat16* p = P + r * p_pitch;
+    float m = 0.f, inv = 1.f;
+    if (mode == 0) {
+      m = -CUDART_INF_F;
+      for (int j = lane; j < n; j += 32) m = fmaxf(m, s[j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float l = 0.f;
+      for (int j = lane; j < n; j += 32) l += expf((s[j] - m) * scale);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+      inv = 1.f / l;
+    }
+    for (int j = lane; j < n; j += 32) {
+      const float v = mode == 0 ? expf((s[j] - m) * scale) * inv : s[j] * scale;
+      p[j] = f2h16(v, f16);
+    }
+  }
+}
+
+// out[b][c][r] = in[b][r][c] for 16-bit elements; 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __restrict__ in, int rows, int cols,
+                                                          long long in_bstride, long long in_pitch,
+                                                          uint16_t* __restrict__ out, long long out_bstride,
+                                                          long long out_pitch) {
+  __shared__ uint16_t tile[32][33];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? in[b * in_bstride + r * in_pitch + c] : 0;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < cols && r < rows) out[b * out_bstride + c * out_pitch + r] = tile[tx][i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------- direct conv
 struct DirectParams {
   View x, y, res;
@@ -1190,6 +1244,28 @@ extern "C" int esf_frames_to_clip(const uint8_t* frames, int32_t B, int32_t Tsrc
   const long long total = (long long)B * C * T * H * ((W + 3) / 4);
   frames_to_clip_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, lut32, clip);
   return check_launch("frames_to_clip_kernel");
+}
+
+extern "C" int esf_row_softmax(const float* S, int64_t rows, int32_t n, int64_t s_pitch, float scale, int32_t mode,
+                               int32_t dtype, void* P, int64_t p_pitch, void* stream) {
+  ESF_CHECK_ARG(S && P && rows > 0 && n > 0 && s_pitch >= n && p_pitch >= n, "esf_row_softmax: null/bad argument");
+  ESF_CHECK_ARG(is16(dtype) && (mode == 0 || mode == 1), "esf_row_softmax: bad dtype / mode");
+  const long long blocks = (rows + 7) / 8;
+  row_softmax_kernel<<<(unsigned)std::min(blocks, 148LL * 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      S, rows, n, s_pitch, scale, mode, dtype == ESF_F16, static_cast<__nv_bfloat16*>(P), p_pitch);
+  return check_launch("row_softmax_kernel");
+}
+
+extern "C" int esf_transpose16(const void* in, int32_t B, int32_t rows, int32_t cols, int64_t in_bstride, int64_t in_pitch,
+                               void* out, int64_t out_bstride, int64_t out_pitch, void* stream) {
+  ESF_CHECK_ARG(in && out && B > 0 && rows > 0 && cols > 0 && in_pitch >= cols && out_pitch >= rows && B <= 65535,
+                "esf_transpose16: null/bad argument");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, B);
+  ESF_CHECK_ARG(grid.y <= 65535, "esf_transpose16: too many rows");
+  transpose16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(in), rows, cols, in_bstride, in_pitch, static_cast<uint16_t*>(out), out_bstride,
+      out_pitch);
+  return check_launch("transpose16_kernel");
 }
 
 extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {

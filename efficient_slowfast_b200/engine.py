@@ -202,6 +202,122 @@ class Plan:
                   "%dx%dx%d s%s %d->%d @%s" % (kt, kh, kw, "".join(map(str, stride)), cin, cout, tuple(y.shape[1:4])),
                   flops=2.0 * m * cout * cin * kt * kh * kw, nbytes=self._nbytes(x, y, res) + wp.numel() * 2)
 
+    def gemm_rows(self, x, y, w_rows, bias, kind, label):
+        """y[pos, n] = sum_c x[pos, c] * w_rows[n, c] + bias[n] on the implicit-GEMM kernel with a DEVICE-RESIDENT
+        weight matrix in the kernel's own layout ([n_pad][kchunks * kc] 16-bit rows, FP32 bias [n_pad]) -- used where
+        the "weights" are activations of the same clip (Non-local block)."""
+        cin, cout = x.shape[4], y.shape[4]
+        kc, kchunks, _, n_pad = rt.igemm_geometry(cin, cout)
+        assert tuple(w_rows.shape) == (n_pad, kc * kchunks) and w_rows.is_contiguous() and w_rows.dtype == self.adt
+        assert bias.numel() == n_pad and bias.dtype == torch.float32
+        d = rt.EsfConvDesc(rt.view(x), rt.view(y), rt.null_view(), w_rows.data_ptr(), bias.data_ptr(), 1, 1, 1,
+                           1, 1, 1, 0, 0, 0, 1, 1, 1, 1, rt.ACT_NONE, rt.dtype_code(y))
+        h = ctypes.c_void_p()
+        L = rt.lib()
+        rt.check(L.esf_conv_igemm_create(ctypes.byref(d), ctypes.byref(h)), "esf_conv_igemm_create")
+        self.handles.append(h)
+        m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
+        self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), kind, label,
+                  flops=2.0 * m * cout * cin, nbytes=self._nbytes(x, y) + cout * cin * 2)
+
+    def scratch(self, shape, dtype, zero=False):
+        """Plan-lifetime scratch tensor shared by every op that asks for the same (shape, dtype): the launches of a
+        plan are serialised on one stream, so the Non-local blocks of a model reuse one affinity matrix."""
+        key = (tuple(shape), dtype, bool(zero))
+        if not hasattr(self, "_scratch"):
+            self._scratch = {}
+        if key not in self._scratch:
+            t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
+            self.keep.append(t)
+            self._scratch[key] = t
+        return self._scratch[key]
+
+    def nonlocal_block(self, x, y, nln, group=1):
+        """Nonlocal.forward (nonlocal_helper.py:105-148) + the temporal group folding of ResStage.forward
+        (resnet_helper.py:541-560): y = x + bn(conv_out(normalise(theta^T phi) g^T)).
+
+        theta / phi / g / out are ordinary implicit GEMMs (bias in the epilogue; BN folded into conv_out, the residual
+        add in its epilogue).  The two matrix products are implicit GEMMs as well, one launch per clip, whose weight
+        operand is the clip's own phi rows ([N_keys][d], exactly the kernel's [n][k] layout) and g^T rows
+        ([d][N_keys], written by esf_transpose16); the affinity matrix is materialised once in FP32, normalised by
+        esf_row_softmax (softmax with d^-0.5, or the 1/N_keys of "dot_product") into the 16-bit A operand of the
+        second product."""
+        L = rt.lib()
+        if group > 1:   # (b, t) -> (b * group, t / group): a pure view in channels-last memory
+            def fold(t):
+                B, T, H, W, C = t.shape
+                assert T % group == 0 and t.stride(0) == T * t.stride(1)
+                return t.as_strided((B * group, T // group, H, W, C),
+                                    (t.stride(1) * (T // group), t.stride(1), t.stride(2), t.stride(3), 1),
+                                    t.storage_offset())
+            x, y = fold(x), fold(y)
+        B, T, H, W, C = x.shape
+        d = nln.dim_inner
+        f64 = torch.float64
+
+        def wb(conv):
+            return conv.weight.detach().to(f64), conv.bias.detach().to(f64)
+
+        theta = self.act(B, T, H, W, d)
+        self.conv(x, theta, *wb(nln.conv_theta))
+        if nln.use_pool:
+            ps = [int(v) for v in nln.pool_size]
+            Tp, Hp, Wp = (T - ps[0]) // ps[0] + 1, (H - ps[1]) // ps[1] + 1, (W - ps[2]) // ps[2] + 1
+            xp = self.act(B, Tp, Hp, Wp, C)
+            self.pool(x, xp, tuple(ps), tuple(ps), (0, 0, 0))
+        else:
+            Tp, Hp, Wp, xp = T, H, W, x
+        Nq, Nk = T * H * W, Tp * Hp * Wp
+        # phi rows of a clip = the [n][k] weight matrix of the first product: rows padded to the GEMM's n_pad
+        kc1, kch1, _, npad1 = rt.igemm_geometry(d, Nk)
+        assert kc1 * kch1 == d, "dim_inner must fill whole K chunks"
+        phi_rows = torch.zeros((B, npad1, d), dtype=self.adt, device=self.device)
+        phi = phi_rows.as_strided((B, Tp, Hp, Wp, d), (npad1 * d, Hp * Wp * d, Wp * d, d, 1))
+        g = self.act(B, Tp, Hp, Wp, d)
+        self.keep += [phi_rows]
+        self.conv(xp, phi, *wb(nln.conv_phi))
+        self.conv(xp, g, *wb(nln.conv_g))
+        # g^T rows = the [n][k] weight matrix of the second product (k = keys, zero padded to whole chunks)
+        kc2, kch2, _, npad2 = rt.igemm_geometry(Nk, d)
+        kpad2 = kc2 * kch2
+        gT = torch.zeros((B, npad2, kpad2), dtype=self.adt, device=self.device)
+        self.keep += [gT]
+        self._add(lambda s: rt.check(L.esf_transpose16(g.data_ptr(), B, Nk, d, g.stride(0), g.stride(3), gT.data_ptr(),
+                                                       npad2 * kpad2, kpad2, s), "esf_transpose16"),
+                  "nl_transpose", "", nbytes=2 * self._nbytes(g))
+        Sbuf = self.scratch((B, T, H, W, (Nk + 3) // 4 * 4), torch.float32)
+        S = Sbuf[..., :Nk]
+        Pbuf = self.scratch((B, T, H, W, (Nk + 7) // 8 * 8), self.adt)
+        P = Pbuf[..., :Nk]
+        zero1 = self.scratch((npad1,), torch.float32, zero=True)
+        # Precision: with near-uniform attention the block output is a large per-channel constant plus a small
+        # variation, and the BN behind conv_out removes the constant -- 16-bit rounding of `att` would then be
+        # amplified by |mean| / std.  conv_out is linear, so a per-channel offset mu can be subtracted in the FP32
+        # epilogue of the second product (its bias) and added back through conv_out's bias: W (att - mu) + (W mu + b).
+        # mu = least-squares solution of W mu = running_mean - b, the att-space mean the BN statistics imply.
+        w_out = nln.conv_out.weight.detach().to(f64).reshape(C, d)
+        rhs = (nln.bn.running_mean.detach().to(f64) - nln.conv_out.bias.detach().to(f64)).reshape(C, 1)
+        mu = torch.linalg.lstsq(w_out.cpu(), rhs.cpu()).solution.reshape(d).to(w_out.device)
+        bias2 = torch.zeros(npad2, dtype=torch.float32, device=self.device)
+        bias2[:d] = (-mu).to(torch.float32)
+        mu = -bias2[:d].to(f64).to(w_out.device)     # the value actually subtracted (FP32-rounded)
+        self.keep.append(bias2)
+        for b in range(B):
+            self.gemm_rows(theta[b:b + 1], S[b:b + 1], phi_rows[b], zero1, "nl_gemm", "theta.phi N=%dx%d d=%d" % (Nq, Nk, d))
+        softmax = nln.instantiation == "softmax"
+        if not softmax and nln.instantiation != "dot_product":
+            raise NotImplementedError("Unknown norm type {}".format(nln.instantiation))
+        scale = float(d) ** -0.5 if softmax else 1.0 / Nk
+        self._add(lambda s: rt.check(L.esf_row_softmax(Sbuf.data_ptr(), B * Nq, Nk, Sbuf.shape[4], scale, 0 if softmax else 1, self.a16,
+                                                       Pbuf.data_ptr(), Pbuf.shape[4], s), "esf_row_softmax"),
+                  "nl_softmax", nln.instantiation, nbytes=self._nbytes(S, P), exps=float(B * Nq * Nk) if softmax else 0)
+        att = self.act(B, T, H, W, d)
+        for b in range(B):
+            self.gemm_rows(P[b:b + 1], att[b:b + 1], gT[b], bias2, "nl_gemm", "p.g N=%dx%d d=%d" % (Nq, Nk, d))
+        w, bias = fold_conv_bn(nln.conv_out.weight, nln.conv_out.bias, nln.bn)
+        bias = bias + w.reshape(C, d) @ mu.to(w.device)
+        self.conv(att, y, w, bias, res=x)
+
     def conv_wfold(self, x, y, w_folded, bias, WB, stride=(1, 1, 1), padding=(0, 0, 0), act=rt.ACT_NONE, res=None):
         """Thin-layer (C_in <= 32) conv as a W-folded banded GEMM: see esf_conv_wfold_create."""
         wp, bp = pack_wfold_band(w_folded, bias, WB, stride[2], self.device, self.adt)

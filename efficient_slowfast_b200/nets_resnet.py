@@ -109,18 +109,38 @@ class ResBlock(_Holder):
         self.relu = nn.ReLU(True)
 
 
+class Nonlocal(_Holder):
+    """nonlocal_helper.py:10-103 (parameter holder; forward = engine.Plan.nonlocal_block)."""
+
+    def __init__(self, dim, dim_inner, pool_size=None, instantiation="softmax", zero_init_final_conv=False,
+                 zero_init_final_norm=True, norm_eps=1e-5, norm_momentum=0.1, norm_module=nn.BatchNorm3d):
+        super().__init__()
+        self.dim, self.dim_inner, self.pool_size, self.instantiation = dim, dim_inner, pool_size, instantiation
+        self.use_pool = False if pool_size is None else any((size > 1 for size in pool_size))
+        self.conv_theta = nn.Conv3d(dim, dim_inner, kernel_size=1, stride=1, padding=0)
+        self.conv_phi = nn.Conv3d(dim, dim_inner, kernel_size=1, stride=1, padding=0)
+        self.conv_g = nn.Conv3d(dim, dim_inner, kernel_size=1, stride=1, padding=0)
+        self.conv_out = nn.Conv3d(dim_inner, dim, kernel_size=1, stride=1, padding=0)
+        self.conv_out.zero_init = zero_init_final_conv
+        self.bn = norm_module(num_features=dim, eps=norm_eps, momentum=norm_momentum)
+        self.bn.transform_final_bn = zero_init_final_norm
+        if self.use_pool:
+            self.pool = nn.MaxPool3d(kernel_size=pool_size, stride=pool_size, padding=[0, 0, 0])
+
+
 class ResStage(_Holder):
-    """resnet_helper.py:361-561 (without Nonlocal blocks: every BASELINE config has NONLOCAL.LOCATION empty)."""
+    """resnet_helper.py:361-561, Nonlocal blocks after the listed residual blocks included."""
 
     def __init__(self, dim_in, dim_out, stride, temp_kernel_sizes, num_blocks, dim_inner, num_groups,
-                 num_block_temp_kernel, nonlocal_inds, dilation, trans_func_name, stride_1x1, norm_module):
+                 num_block_temp_kernel, nonlocal_inds, dilation, trans_func_name, stride_1x1, norm_module,
+                 nonlocal_group=None, nonlocal_pool=None, instantiation="softmax"):
         super().__init__()
         assert all(num_block_temp_kernel[i] <= num_blocks[i] for i in range(len(temp_kernel_sizes)))
         if trans_func_name != "bottleneck_transform":
             raise NotImplementedError("RESNET.TRANS_FUNC '%s' (only bottleneck_transform is on the BASELINE path)"
                                       % trans_func_name)
-        if any(len(x) for x in nonlocal_inds):
-            raise NotImplementedError("Nonlocal blocks are not built (NONLOCAL.LOCATION must be empty)")
+        self.nonlocal_group = nonlocal_group if nonlocal_group is not None else [1] * len(num_blocks)
+        nonlocal_pool = nonlocal_pool if nonlocal_pool is not None else [[1, 2, 2]] * len(num_blocks)
         self.num_blocks = num_blocks
         self.temp_kernel_sizes = [
             (temp_kernel_sizes[i] * num_blocks[i])[: num_block_temp_kernel[i]]
@@ -134,6 +154,10 @@ class ResStage(_Holder):
                                stride[p] if i == 0 else 1, dim_inner[p], num_groups[p], stride_1x1, dilation[p],
                                norm_module)
                 self.add_module("pathway{}_res{}".format(p, i), blk)
+                if i in nonlocal_inds[p]:
+                    nln = Nonlocal(dim_out[p], dim_out[p] // 2, nonlocal_pool[p], instantiation=instantiation,
+                                   norm_module=norm_module)
+                    self.add_module("pathway{}_nonlocal{}".format(p, i), nln)
 
 
 class FuseFastToSlow(_Holder):
@@ -402,7 +426,8 @@ class _TwoStreamResNet(_PlannedModel):
                 dim_in=[c_prev + c_prev // out_dim_ratio, fast_in], dim_out=[c_out, c_out // beta],
                 dim_inner=[dim_inner * (2 ** i), dim_inner * (2 ** i) // beta], temp_kernel_sizes=tk[i + 1],
                 stride=cfg.RESNET.SPATIAL_STRIDES[i], num_blocks=[depths[i]] * 2, num_groups=[num_groups] * 2,
-                num_block_temp_kernel=cfg.RESNET.NUM_BLOCK_TEMP_KERNEL[i], nonlocal_inds=cfg.NONLOCAL.LOCATION[i],
+                num_block_temp_kernel=cfg.RESNET.NUM_BLOCK_TEMP_KERNEL[i], nonlocal_inds=cfg.NONLOCAL.LOCATION[i], nonlocal_group=cfg.NONLOCAL.GROUP[i],
+                nonlocal_pool=cfg.NONLOCAL.POOL[i], instantiation=cfg.NONLOCAL.INSTANTIATION,
                 dilation=cfg.RESNET.SPATIAL_DILATIONS[i], trans_func_name=cfg.RESNET.TRANS_FUNC,
                 stride_1x1=cfg.RESNET.STRIDE_1X1, norm_module=self.norm_module)
             setattr(self, name, stage)
@@ -493,13 +518,7 @@ class _TwoStreamResNet(_PlannedModel):
                     tot = tots[pw]
                     off = 0 if (pw == 0 or not dual) else c_out // beta
                 dst = plan.act(B, T, Ho, Wo, tot, name="%s_cat%d" % (name, pw))
-                nblocks = stage.num_blocks[pw]
-                ping = [plan.act(B, T, Ho, Wo, co) for _ in range(min(2, nblocks - 1))]
-                for bi in range(nblocks):
-                    blk = getattr(stage, "pathway{}_res{}".format(pw, bi))
-                    y = dst[..., off:off + co] if bi == nblocks - 1 else ping[bi % 2]
-                    self._emit_block(plan, blk, x, y, stride if bi == 0 else 1, dil)
-                    x = y
+                self._emit_stage_pathway(plan, stage, pw, x, dst[..., off:off + co], stride, dil)
                 nxt.append((dst, off, co))
             cur = nxt
             if not last:
@@ -518,6 +537,25 @@ class _TwoStreamResNet(_PlannedModel):
                         % (ps, [T, H, W]))
         act = {"softmax": rt.HEAD_SOFTMAX, "sigmoid": rt.HEAD_SIGMOID}[self.head.act_func]
         plan.head(xs, self.head.projection.weight, self.head.projection.bias, act)
+
+    def _emit_stage_pathway(self, plan, stage, pw, x, dst, stride, dil):
+        """One pathway of ResStage.forward (resnet_helper.py:530-561): residual blocks, each optionally followed by
+        its Nonlocal block; the units ping-pong between two scratch activations and the last one writes `dst`."""
+        units = []
+        for bi in range(stage.num_blocks[pw]):
+            units.append(("res", getattr(stage, "pathway{}_res{}".format(pw, bi)), stride if bi == 0 else 1))
+            nln = getattr(stage, "pathway{}_nonlocal{}".format(pw, bi), None)
+            if nln is not None:
+                units.append(("nonlocal", nln, None))
+        B, T, Ho, Wo, co = dst.shape
+        ping = [plan.act(B, T, Ho, Wo, co) for _ in range(min(2, len(units) - 1))]
+        for ui, (kind, mod, st) in enumerate(units):
+            y = dst if ui == len(units) - 1 else ping[ui % 2]
+            if kind == "res":
+                self._emit_block(plan, mod, x, y, st, dil)
+            else:
+                plan.nonlocal_block(x, y, mod, group=stage.nonlocal_group[pw])
+            x = y
 
     def _emit_block(self, plan, blk, x, y, stride, dil):
         """ResBlock (resnet_helper.py:352-358): y = relu(shortcut(x) + bn(c(relu(bn(b(relu(bn(a(x))))))))).
@@ -568,7 +606,7 @@ class SlowFast(_TwoStreamResNet):
 class ResNet(_TwoStreamResNet):
     """video_model_builder.py:419-611: single-pathway ResNet (C2D, I3D, Slow) without lateral connections.  Same
     stem / bottleneck / head kernels as the two-stream models; the max-pool after res2 is real here (kernel = stride =
-    _POOL1[arch], e.g. (2,1,1) for c2d / i3d).  Nonlocal blocks are not built (NONLOCAL.LOCATION must be empty)."""
+    _POOL1[arch], e.g. (2,1,1) for c2d / i3d).  Nonlocal blocks (C2D_NLN / I3D_NLN / SLOW_NLN): engine.nonlocal_block."""
 
     num_pathways = 1
 
@@ -594,7 +632,8 @@ class ResNet(_TwoStreamResNet):
             setattr(self, name, ResStage(
                 dim_in=[c_prev], dim_out=[c_out], dim_inner=[dim_inner * (2 ** i)], temp_kernel_sizes=tk[i + 1],
                 stride=cfg.RESNET.SPATIAL_STRIDES[i], num_blocks=[depths[i]], num_groups=[num_groups],
-                num_block_temp_kernel=cfg.RESNET.NUM_BLOCK_TEMP_KERNEL[i], nonlocal_inds=cfg.NONLOCAL.LOCATION[i],
+                num_block_temp_kernel=cfg.RESNET.NUM_BLOCK_TEMP_KERNEL[i], nonlocal_inds=cfg.NONLOCAL.LOCATION[i], nonlocal_group=cfg.NONLOCAL.GROUP[i],
+                nonlocal_pool=cfg.NONLOCAL.POOL[i], instantiation=cfg.NONLOCAL.INSTANTIATION,
                 dilation=cfg.RESNET.SPATIAL_DILATIONS[i], trans_func_name=cfg.RESNET.TRANS_FUNC,
                 stride_1x1=cfg.RESNET.STRIDE_1X1, norm_module=self.norm_module))
             if name == "s2":
@@ -635,13 +674,7 @@ class ResNet(_TwoStreamResNet):
             _, T, H, W, _ = cur.shape
             Ho, Wo = conv_out(H, 1, stride, 0), conv_out(W, 1, stride, 0)
             dst = plan.act(B, T, Ho, Wo, co, name="%s_cat0" % name)
-            nblocks = stage.num_blocks[0]
-            ping = [plan.act(B, T, Ho, Wo, co) for _ in range(min(2, nblocks - 1))]
-            xin = cur
-            for bi in range(nblocks):
-                yb = dst if bi == nblocks - 1 else ping[bi % 2]
-                self._emit_block(plan, getattr(stage, "pathway0_res{}".format(bi)), xin, yb, stride if bi == 0 else 1, dil)
-                xin = yb
+            self._emit_stage_pathway(plan, stage, 0, cur, dst, stride, dil)
             cur = dst
             if name == "s2":
                 ks = [int(v) for v in self.pathway0_pool.kernel_size]

@@ -182,6 +182,18 @@ int esf_attn_generic(const float* proj, int32_t B, int32_t T, int32_t H, int32_t
                      const float* bn_scale, const float* bn_shift, int32_t alpha, const esf_view* y_fast_slice,
                      void* stream);
 
+/* ---- Non-local block glue (SlowFast/slowfast/models/nonlocal_helper.py:105-148) ------------------
+ * The block's two matrix products (theta^T phi and (.) g^T, einsum lines 122 / 139) are launched per clip as
+ * esf_conv_igemm_create GEMMs whose weight matrix is the clip's own phi rows / transposed g rows; the 1x1x1 convs
+ * theta / phi / g / out, the max-pool and the residual + BN are the ordinary conv / pool entry points.
+ * esf_row_softmax normalises the FP32 affinity rows S[rows][n] (pitch s_pitch) into 16-bit P (pitch p_pitch):
+ *   mode 0: softmax_j(scale * S) ("softmax", scale = dim_inner^-0.5);  mode 1: scale * S ("dot_product", 1 / n).
+ * esf_transpose16: out[b][c][r] = in[b][r][c] on 16-bit elements (g rows -> g^T, the GEMM's [n][k] weight layout). */
+int esf_row_softmax(const float* S, int64_t rows, int32_t n, int64_t s_pitch, float scale, int32_t mode, int32_t dtype,
+                    void* P, int64_t p_pitch, void* stream);
+int esf_transpose16(const void* in, int32_t B, int32_t rows, int32_t cols, int64_t in_bstride, int64_t in_pitch, void* out,
+                    int64_t out_bstride, int64_t out_pitch, void* stream);
+
 /* ---- head: global average pool of each pathway -> concat -> Linear -> softmax/ReLU/none -----------------
  * replaces ResNetBasicHead.forward eval branch (head_helper.py:198-223) and the efficient heads'
  * pool+classifier tails.  feat: FP32 scratch (B, C0 + C1).  act: 0 none (logits), 1 softmax, 2 relu, 3 sigmoid,

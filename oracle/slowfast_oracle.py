@@ -5,7 +5,7 @@ reference's eval-mode forward for the ResNet based models:
 
   * SlowFastDualAttention  (SlowFast/slowfast/models/custom_video_model_builder.py:171-445)
   * SlowFast               (SlowFast/slowfast/models/video_model_builder.py:153-416)
-  * ResNet                 (SlowFast/slowfast/models/video_model_builder.py:419-611; C2D / I3D / Slow, no Nonlocal)
+  * ResNet                 (SlowFast/slowfast/models/video_model_builder.py:419-611; C2D / I3D / Slow, with Nonlocal blocks)
 
 Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference`
 legs of `bench.py` may import this file.  The product package never does: the
@@ -79,13 +79,50 @@ def bottleneck_block(x, sd, p, stride, dilation=1, num_groups=1, stride_1x1=Fals
     return F.relu(x + y)
 
 
-def res_stage(xs, sd, p, num_blocks, strides, dilations, num_groups=(1, 1), stride_1x1=False):
-    """ResStage.forward (resnet_helper.py:530-561), no Nonlocal (every BASELINE cfg has NONLOCAL.LOCATION empty)."""
+def nonlocal_block(x, sd, p, pool_size, instantiation):
+    """Nonlocal.forward (nonlocal_helper.py:105-148): theta / phi / g 1x1x1 convs (phi, g on the max-pooled input),
+    affinity einsum("nct,ncp->ntp"), softmax with dim_inner^-0.5 or division by the number of keys, second einsum,
+    conv_out -> BN -> + identity."""
+    identity = x
+    N, C, T, H, W = x.shape
+    theta = _conv(x, sd, p + ".conv_theta")
+    if pool_size is not None and any(v > 1 for v in pool_size):
+        x = F.max_pool3d(x, kernel_size=list(pool_size), stride=list(pool_size), padding=0)
+    phi = _conv(x, sd, p + ".conv_phi")
+    g = _conv(x, sd, p + ".conv_g")
+    d = theta.shape[1]
+    theta, phi, g = theta.view(N, d, -1), phi.view(N, d, -1), g.view(N, d, -1)
+    theta_phi = torch.einsum("nct,ncp->ntp", (theta, phi))
+    if instantiation == "softmax":
+        theta_phi = theta_phi * (d ** -0.5)
+        theta_phi = F.softmax(theta_phi, dim=2)
+    elif instantiation == "dot_product":
+        theta_phi = theta_phi / theta_phi.shape[2]
+    else:
+        raise NotImplementedError("Unknown norm type {}".format(instantiation))
+    y = torch.einsum("ntg,ncg->nct", (theta_phi, g)).view(N, d, T, H, W)
+    return identity + _bn(_conv(y, sd, p + ".conv_out"), sd, p + ".bn")
+
+
+def res_stage(xs, sd, p, num_blocks, strides, dilations, num_groups=(1, 1), stride_1x1=False, nonlocal_group=None,
+              nonlocal_pool=None, instantiation="softmax"):
+    """ResStage.forward (resnet_helper.py:530-561).  A Nonlocal block follows residual block i whenever the weights
+    hold `pathway{pw}_nonlocal{i}` (the reference tests hasattr the same way); NONLOCAL.GROUP > 1 folds the temporal
+    axis into the batch around it (resnet_helper.py:541-560)."""
     out = []
     for pw, x in enumerate(xs):
         for i in range(num_blocks[pw]):
             x = bottleneck_block(x, sd, "%s.pathway%d_res%d" % (p, pw, i), strides[pw] if i == 0 else 1,
                                  dilations[pw], num_groups[pw], stride_1x1)
+            q = "%s.pathway%d_nonlocal%d" % (p, pw, i)
+            if (q + ".conv_theta.weight") in sd:
+                grp = nonlocal_group[pw] if nonlocal_group is not None else 1
+                b, c, t, h, w = x.shape
+                if grp > 1:
+                    x = x.permute(0, 2, 1, 3, 4).reshape(b * grp, t // grp, c, h, w).permute(0, 2, 1, 3, 4)
+                x = nonlocal_block(x, sd, q, nonlocal_pool[pw] if nonlocal_pool is not None else [1, 2, 2], instantiation)
+                if grp > 1:
+                    x = x.permute(0, 2, 1, 3, 4).reshape(b, t, c, h, w).permute(0, 2, 1, 3, 4)
         out.append(x)
     return out
 
@@ -217,7 +254,7 @@ def slowfast_forward(cfg, sd, inputs, dtype=torch.float32, taps=None):
 
 
 def resnet_forward(cfg, sd, inputs, dtype=torch.float32, taps=None):
-    """ResNet.forward (video_model_builder.py:599-611): single pathway C2D / I3D / Slow, eval mode, no Nonlocal.
+    """ResNet.forward (video_model_builder.py:599-611): single pathway C2D / I3D / Slow (+ _NLN), eval mode.
     The temporal kernels of the blocks are read from the weights; the only arch-dependent step is the max-pool after
     res2 (kernel = stride = _POOL1[arch], video_model_builder.py:503-509)."""
     assert len(inputs) == 1, "Input tensor does not contain 1 pathway"
@@ -234,7 +271,8 @@ def resnet_forward(cfg, sd, inputs, dtype=torch.float32, taps=None):
     pool = POOL1[cfg.MODEL.ARCH][0]
     for i, stage in enumerate(("s2", "s3", "s4", "s5")):
         xs = res_stage(xs, sd, stage, [depth[i]], cfg.RESNET.SPATIAL_STRIDES[i], cfg.RESNET.SPATIAL_DILATIONS[i],
-                       [cfg.RESNET.NUM_GROUPS], cfg.RESNET.STRIDE_1X1)
+                       [cfg.RESNET.NUM_GROUPS], cfg.RESNET.STRIDE_1X1, cfg.NONLOCAL.GROUP[i], cfg.NONLOCAL.POOL[i],
+                       cfg.NONLOCAL.INSTANTIATION)
         tap(stage, xs)
         if stage == "s2":
             xs = [F.max_pool3d(xs[0], kernel_size=pool, stride=pool, padding=0)]

@@ -16,6 +16,10 @@ out every bottleneck and every attention branch), so parity runs use perturbed w
     un-normalised logits q.k reach |s| ~ 200 on calibrated activations, the softmax is one-hot and the attention
     output flips between keys under perturbations of 1e-3 (a property of that random draw, not of an
     implementation); at |s| ~ 10 every key still matters and the branch is well conditioned;
+  * Nonlocal blocks: theta / phi keep the c2_msra_fill scale (the d^-0.5 softmax logits then have std ~ 4: a few
+    dozen keys matter; scaled down, the attention becomes uniform, the block output nearly constant and its BN divides
+    by a variance of 0.02 -- measured with the reference); their final BN gets the U(0.15,0.45) weight of a residual
+    branch;
   * BN running statistics are calibrated by the generator with train-mode forwards of the reference model and are
     STORED in the fixture (they cannot be regenerated without the reference).
 """
@@ -45,7 +49,8 @@ def seeded_state_dict(template, seed=0, bn_stats=None, stress=False):
                 t = torch.zeros(shape) if leaf == "running_mean" else torch.ones(shape)
         elif is_bn and leaf == "weight":
             t = torch.rand(shape, generator=g) + 0.5
-            if (key.endswith("c_bn.weight") or key.endswith(".bn3.weight")) and not stress:
+            if (key.endswith("c_bn.weight") or key.endswith(".bn3.weight")
+                    or ("_nonlocal" in key and key.endswith(".bn.weight"))) and not stress:
                 t = (t - 0.5) * 0.3 + 0.15   # last BN of a residual branch (R50 bottleneck, ShuffleNet unit)
         elif is_bn and leaf == "bias":
             t = torch.rand(shape, generator=g) * 0.4 - 0.2
@@ -119,6 +124,13 @@ CASES = {
     "slow_r50": dict(
         model="ResNet", yaml="configs/Kinetics/SLOW_8x8_R50.yaml", single=True,
         opts=["DATA.CROP_SIZE", 64], calib=(2, 8, 64), inputs=[("s64", 2, 8, 64)]),
+    # Nonlocal blocks after res3 blocks 1,3 and res4 blocks 1,3,5 (pool (1,2,2) on phi / g)
+    "slow_nln_r50": dict(       # "dot_product" instantiation
+        model="ResNet", yaml="configs/Kinetics/SLOW_NLN_8x8_R50.yaml", single=True,
+        opts=["DATA.CROP_SIZE", 64], calib=(2, 8, 64), inputs=[("s64", 2, 8, 64)]),
+    "i3d_nln_r50": dict(        # "softmax" instantiation, (2,1,1) max-pool after res2
+        model="ResNet", yaml="configs/Kinetics/I3D_NLN_8x8_R50.yaml", single=True,
+        opts=["DATA.CROP_SIZE", 96], calib=(2, 8, 96), inputs=[("s96", 2, 8, 96)]),
     "dual_r50_stress": dict(
         model="SlowFastDualAttention", yaml="configs/Kinetics/SLOWFAST_DUAL_8x8_R50_stepwise_multigrid.yaml",
         stress=True, opts=[], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),

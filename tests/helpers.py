@@ -36,6 +36,12 @@ def case_cfg(name):
     elif name == "slow_r50":
         cfg = esf.resnet_cfg("slow")
         cfg.DATA.CROP_SIZE = 64
+    elif name == "slow_nln_r50":
+        cfg = esf.resnet_cfg("slow", nln=True)
+        cfg.DATA.CROP_SIZE = 64
+    elif name == "i3d_nln_r50":
+        cfg = esf.resnet_cfg("i3d", nln=True)
+        cfg.DATA.CROP_SIZE = 96
     else:
         raise KeyError(name)
     cfg.NUM_GPUS = 0

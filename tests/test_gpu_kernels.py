@@ -574,3 +574,74 @@ def test_errors_are_reported_not_swallowed(esf_lib):
     with pytest.raises(rt.EsfError):
         plan.conv_igemm(x, y, torch.zeros(16, 12, 1, 1, 1).double(), torch.zeros(16).double())
     assert "multiple of 16" in L.esf_last_error().decode()
+
+
+# ------------------------------------------------------------------------------------------------ Nonlocal block
+@pytest.mark.parametrize("mode,n", [(0, 1568), (1, 392), (0, 37)])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_row_softmax(esf_lib, mode, n, dt):
+    g = torch.Generator().manual_seed(21)
+    rows, pitch = 300, (n + 3) // 4 * 4
+    S = (torch.randn(rows, pitch, generator=g) * 3).to(DEV)
+    ppitch = (n + 7) // 8 * 8
+    P = torch.zeros(rows, ppitch, dtype=dt, device=DEV)
+    scale = 0.0625 if mode == 0 else 1.0 / n
+    rt.check(esf_lib.esf_row_softmax(S.data_ptr(), rows, n, pitch, scale, mode, rt.dtype_code(dt), P.data_ptr(), ppitch,
+                                     rt.current_stream_ptr()))
+    torch.cuda.synchronize()
+    ref = torch.softmax(S[:, :n].double() * scale, dim=1) if mode == 0 else S[:, :n].double() * scale
+    tol = 2 ** -10 if dt == torch.float16 else 2 ** -7
+    assert ((P[:, :n].double() - ref).abs() <= tol * ref.abs() + 1e-7).all()
+    assert (P[:, n:] == 0).all()
+
+
+def test_transpose16(esf_lib):
+    g = torch.Generator().manual_seed(22)
+    B, rows, cols = 3, 100, 72
+    x = torch.randn(B, rows, cols, generator=g).to(torch.float16).to(DEV)
+    out = torch.zeros(B, 80, 128, dtype=torch.float16, device=DEV)
+    rt.check(esf_lib.esf_transpose16(x.data_ptr(), B, rows, cols, rows * cols, cols, out.data_ptr(), 80 * 128, 128,
+                                     rt.current_stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, :cols, :rows], x.transpose(1, 2))
+    assert (out[:, cols:] == 0).all() and (out[:, :, rows:] == 0).all()
+
+
+@pytest.mark.parametrize("inst,pool,group", [("softmax", [1, 2, 2], 1), ("dot_product", [1, 2, 2], 1),
+                                             ("softmax", [1, 1, 1], 2)])
+def test_nonlocal_block(esf_lib, inst, pool, group):
+    """Plan.nonlocal_block vs the oracle's restatement of Nonlocal.forward on FP16-rounded operands."""
+    from efficient_slowfast_b200.nets_resnet import Nonlocal
+    from oracle import slowfast_oracle as O
+
+    torch.manual_seed(5)
+    B, T, H, W, C = 2, 4, 8, 8, 128
+    nln = Nonlocal(C, C // 2, pool, instantiation=inst).eval()
+    with torch.no_grad():
+        for m in (nln.conv_theta, nln.conv_phi, nln.conv_g, nln.conv_out):
+            m.weight.normal_(0, (2.0 / m.out_channels) ** 0.5)
+            m.bias.uniform_(-0.1, 0.1)
+        nln.bn.weight.uniform_(0.5, 1.5)
+        nln.bn.bias.uniform_(-0.2, 0.2)
+        nln.bn.running_mean.uniform_(-0.1, 0.1)
+        nln.bn.running_var.uniform_(0.5, 1.5)
+    x = torch.randn(B, T, H, W, C).to(torch.float16)
+    plan = Plan(torch.device(DEV), precision="fp16")
+    xd = x.to(DEV)
+    y = torch.zeros_like(xd)
+    with torch.no_grad():
+        plan.nonlocal_block(xd, y, nln, group=group)
+    plan.launch_all()
+    torch.cuda.synchronize()
+    sd = {"n." + k: v for k, v in nln.state_dict().items()}
+    xr = _to_ncdhw(x).double()
+    b, c, t, h, w = xr.shape
+    if group > 1:
+        xr = xr.permute(0, 2, 1, 3, 4).reshape(b * group, t // group, c, h, w).permute(0, 2, 1, 3, 4)
+    ref = O.nonlocal_block(xr, {k: v.double() for k, v in sd.items()}, "n", pool, inst)
+    if group > 1:
+        ref = ref.permute(0, 2, 1, 3, 4).reshape(b, t, c, h, w).permute(0, 2, 1, 3, 4)
+    got = _to_ncdhw(y.cpu()).double()
+    err = ((got - ref).abs().max() / ref.abs().max()).item()
+    print("nonlocal %s pool %s group %d: rel err %.3e" % (inst, pool, group, err))
+    assert err < 1e-2
