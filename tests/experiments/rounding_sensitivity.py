@@ -1,5 +1,16 @@
+"""CPU experiment (test infrastructure, not collected by pytest): how much does 16-bit STORAGE rounding alone move the
+output of a golden case?  Runs the oracle twice -- exact FP32, and with activations rounded to fp16 / bf16 after every
+ReLU ("act"), inside the Non-local blocks ("nl") or both -- and prints max|d| / max|ref| of the probabilities.
+
+    python tests/experiments/rounding_sensitivity.py i3d_nln_r50 s96 act [float16|bfloat16]
+
+Measured (FP16): i3d_nln_r50 act 1.5e-2, nl 2.2e-3, both 1.6e-2; i3d_r50 act 3.2e-4; slow_nln_r50 both 2.6e-3.
+"""
 import sys, torch
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests'); sys.path.insert(0,'/root/repo/tests/golden')
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+for q in (ROOT, os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'tests', 'golden')):
+    sys.path.insert(0, q)
 import helpers, recipe
 from oracle import slowfast_oracle as O
 import torch.nn.functional as F
