@@ -792,17 +792,32 @@ __device__ __forceinline__ __nv_bfloat16 h_lo(float v, int f16) { return f2h16(v
 // proj rows are [x_d | q | k | v] (d each, FP32).  One block stages R consecutive rows of one clip in shared memory
 // (coalesced loads) and writes Q~/K~ rows, x_d rows and the TRANSPOSED value tile V^T[j][n0..n0+R) from there, so every
 // global access is coalesced.
-__global__ void __launch_bounds__(256) attn_tc_pack_kernel(const float* __restrict__ proj, int N, int Npad, int d,
-                                                           int KQ, int DVp, int mode, int R, int f16, int ones_row,
-                                                           __nv_bfloat16* __restrict__ Q, __nv_bfloat16* __restrict__ K,
-                                                           __nv_bfloat16* __restrict__ VT, float* __restrict__ X) {
+// Template parameters: the geometry of the head dims of the R50 / efficient models at compile time (D = 0: everything
+// from the run-time arguments) -- the index arithmetic of every phase is divisions and remainders by these numbers, and
+// with run-time divisors the kernel was bound by integer instructions (2.1 TB/s).
+template <int D, int KQc, int DVc, int MODEc, int Rc>
+__global__ void __launch_bounds__(256) attn_tc_pack_kernel(const float* __restrict__ proj, int N, int Npad, int d_rt,
+                                                           int KQ_rt, int DVp_rt, int mode_rt, int R_rt, int f16,
+                                                           int ones_row, __nv_bfloat16* __restrict__ Q,
+                                                           __nv_bfloat16* __restrict__ K, __nv_bfloat16* __restrict__ VT,
+                                                           float* __restrict__ X) {
   extern __shared__ float tile[];  // [R][4d + 1]
+  const int d = D ? D : d_rt, KQ = D ? KQc : KQ_rt, DVp = D ? DVc : DVp_rt, mode = D ? MODEc : mode_rt;
+  const int R = D ? Rc : R_rt;
   const int b = blockIdx.y;
   const int n0 = blockIdx.x * R;
   const int rows = min(R, N - n0);
   const int W4 = 4 * d, pitch = W4 + 1;
   const float* src = proj + ((long long)b * N + n0) * W4;
-  for (int i = threadIdx.x; i < rows * W4; i += blockDim.x) tile[(i / W4) * pitch + (i % W4)] = src[i];
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {   // 16-byte loads (rows are 16 d bytes)
+    for (int i = threadIdx.x; i < rows * d; i += blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+      float* t = tile + (i / d) * pitch + (i % d) * 4;
+      t[0] = v.x, t[1] = v.y, t[2] = v.z, t[3] = v.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < rows * W4; i += blockDim.x) tile[(i / W4) * pitch + (i % W4)] = src[i];
+  }
   __syncthreads();
   // Q~ / K~: one thread = 8 consecutive elements of a row (one 16-byte store each)
   __nv_bfloat16* qd = Q + ((long long)b * N + n0) * KQ;
@@ -941,15 +956,26 @@ extern "C" int esf_attn_tc_pack(const float* proj, int32_t B, int32_t N, int32_t
   const TcLayout L = tc_layout(B, N, d, g);
   char* base = static_cast<char*>(packed);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  int R = 64;
+  int R = 256;
   while (R > 8 && (size_t)R * (4 * d + 1) * sizeof(float) > 40 * 1024) R >>= 1;
   const size_t smem = (size_t)R * (4 * d + 1) * sizeof(float);
   dim3 grid(cdiv(L.Npad, R), B);
-  attn_tc_pack_kernel<<<grid, 256, smem, s>>>(proj, N, L.Npad, d, g.KQ, g.DVp, g.mode, R, dtype == ESF_F16, g.v2,
-                                              reinterpret_cast<__nv_bfloat16*>(base + L.q_off),
-                                              reinterpret_cast<__nv_bfloat16*>(base + L.k_off),
-                                              reinterpret_cast<__nv_bfloat16*>(base + L.v_off),
-                                              reinterpret_cast<float*>(base + L.x_off));
+#define ESF_PACK_ARGS                                                                                          \
+  proj, N, L.Npad, d, g.KQ, g.DVp, g.mode, R, dtype == ESF_F16, g.v2, reinterpret_cast<__nv_bfloat16*>(base + L.q_off),  \
+      reinterpret_cast<__nv_bfloat16*>(base + L.k_off), reinterpret_cast<__nv_bfloat16*>(base + L.v_off),       \
+      reinterpret_cast<float*>(base + L.x_off)
+  // compile-time geometry for the head dims of the shipped models (must agree with tc_geom and R above)
+  if (d == 8 && g.KQ == 32 && g.DVp == 16 && g.mode == 0 && R == 256)
+    attn_tc_pack_kernel<8, 32, 16, 0, 256><<<grid, 256, smem, s>>>(ESF_PACK_ARGS);
+  else if (d == 32 && g.KQ == 64 && g.DVp == 48 && g.mode == 1 && R == 64)
+    attn_tc_pack_kernel<32, 64, 48, 1, 64><<<grid, 256, smem, s>>>(ESF_PACK_ARGS);
+  else if (d == 64 && g.KQ == 128 && g.DVp == 64 && g.mode == 1 && R == 32)
+    attn_tc_pack_kernel<64, 128, 64, 1, 32><<<grid, 256, smem, s>>>(ESF_PACK_ARGS);
+  else if (d == 128 && g.KQ == 128 && g.DVp == 128 && g.mode == 2 && R == 16)
+    attn_tc_pack_kernel<128, 128, 128, 2, 16><<<grid, 256, smem, s>>>(ESF_PACK_ARGS);
+  else
+    attn_tc_pack_kernel<0, 0, 0, 0, 0><<<grid, 256, smem, s>>>(ESF_PACK_ARGS);
+#undef ESF_PACK_ARGS
   return check_launch("attn_tc_pack_kernel");
 }
 

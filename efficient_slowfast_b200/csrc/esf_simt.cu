@@ -100,31 +100,37 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
 // FP32 (B,Cin,T,H,W) clip -> BF16 channels-last rows [B][T][H][pitch] with xp[.., lpad + w*Cin + c] = x[b,c,t,h,w] and
 // zeros in the left/right padding (the zero padding of the stem conv along W, made explicit so that every banded
 // GEMM block starts 16-byte aligned).  One thread per 8 consecutive output elements (one 16 B store).
-__global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x, int B, int Cin, int T, int H, int W,
+template <int CIN>   // channel count at compile time (0: run-time Cin_rt) -- the per-element division is the hot loop
+__global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x, int B, int Cin_rt, int T, int H, int W,
                                                         int pitch, int lpad, int f16, __nv_bfloat16* __restrict__ xp) {
+  // block = 128 chunk lanes x 2 rows; one (b, t, h) row per threadIdx.y, decomposed once with 32-bit arithmetic
+  const int Cin = CIN ? CIN : Cin_rt;
   const int chunks = pitch / 8;
-  const long long total = (long long)B * T * H * chunks;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int ck = idx % chunks;
-    long long r = idx / chunks;
-    const int h = r % H;
-    r /= H;
-    const int t = r % T;
-    const int b = r / T;
-    float v[8];
+  const long long nrows = (long long)B * T * H;
+  const long long plane = (long long)T * H * W;
+  for (long long row = blockIdx.x * 2LL + threadIdx.y; row < nrows; row += 2LL * gridDim.x) {
+    const int h = (int)(row % H);
+    const int bt = (int)(row / H);
+    const int t = bt % T, b = bt / T;
+    const float* xrow = x + (long long)b * Cin * plane + ((long long)t * H + h) * W;   // channel 0 of this row
+    __nv_bfloat16* orow = xp + row * pitch;
+    for (int ck = threadIdx.x; ck < chunks; ck += blockDim.x) {
+      float v[8];
+      const int j0 = ck * 8 - lpad;
+      int w = j0 >= 0 ? j0 / Cin : -1 - ((-1 - j0) / Cin);   // floor division
+      int c = j0 - w * Cin;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int j = ck * 8 + e - lpad;
-      const int w = j / Cin, c = j - w * Cin;
-      v[e] = (j >= 0 && w < W) ? __ldg(x + ((((long long)b * Cin + c) * T + t) * H + h) * W + w) : 0.f;
+      for (int e = 0; e < 8; ++e) {
+        v[e] = (w >= 0 && w < W) ? __ldg(xrow + c * plane + w) : 0.f;
+        if (++c == Cin) c = 0, ++w;
+      }
+      uint4 o;
+      o.x = pack16x2(v[0], v[1], f16);
+      o.y = pack16x2(v[2], v[3], f16);
+      o.z = pack16x2(v[4], v[5], f16);
+      o.w = pack16x2(v[6], v[7], f16);
+      *reinterpret_cast<uint4*>(orow + ck * 8) = o;
     }
-    uint4 o;
-    o.x = pack16x2(v[0], v[1], f16);
-    o.y = pack16x2(v[2], v[3], f16);
-    o.z = pack16x2(v[4], v[5], f16);
-    o.w = pack16x2(v[6], v[7], f16);
-    *reinterpret_cast<uint4*>(xp + (((long long)b * T + t) * H + h) * pitch + ck * 8) = o;
   }
 }
 
@@ -272,6 +278,18 @@ __global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __rest
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, r = r0 + tx;
     if (c < cols && r < rows) out[b * out_bstride + c * out_pitch + r] = tile[tx][i];
+  }
+}
+
+// out[b][k] = mean_p in[b][p][k]: the `x.mean([1, 2, 3])` of fully-convolutional inference (head_helper.py:218-220)
+__global__ void __launch_bounds__(256) group_mean_kernel(const float* __restrict__ in, int B, int P, int K,
+                                                         float* __restrict__ out) {
+  const int total = B * K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / K, k = i - b * K;
+    float acc = 0.f;
+    for (int q = 0; q < P; ++q) acc += in[((long long)b * P + q) * K + k];
+    out[i] = acc / (float)P;
   }
 }
 
@@ -623,15 +641,16 @@ struct PoolParams {
   int kT, kH, kW, sT, sH, sW, pT, pH, pW, is_avg, act;
 };
 // VEC = 8: one thread handles 8 channels (16 B); VEC = 1: scalar tail path for C % 8 != 0.
-template <int VEC>
+// I: index type -- unsigned 32-bit whenever the element count allows (64-bit divisions cost ~5x more instructions
+// and this kernel has four of them per 16 bytes of output).
+template <int VEC, typename I>
 __global__ void __launch_bounds__(256) pool3d_kernel(const PoolParams p) {
   const int cv = p.y.C / VEC;
-  const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W * cv;
+  const I total = (I)p.y.B * p.y.T * p.y.H * p.y.W * cv;
   const float inv = 1.f / (p.kT * p.kH * p.kW);  // AvgPool3d default count_include_pad=True
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (idx % cv) * VEC;
-    long long pos = idx / cv;
+  for (I idx = blockIdx.x * (I)blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * VEC;
+    I pos = idx / cv;
     const int wo = pos % p.y.W;
     pos /= p.y.W;
     const int ho = pos % p.y.H;
@@ -1201,9 +1220,14 @@ extern "C" int esf_stem_pack(const float* x, int32_t B, int32_t Cin, int32_t T, 
   ESF_CHECK_ARG(is16(dtype), "esf_stem_pack: dtype must be BF16 or F16");
   ESF_CHECK_ARG(x && xp && B > 0 && Cin > 0 && T > 0 && H > 0 && W > 0, "esf_stem_pack: null/bad argument");
   ESF_CHECK_ARG(pitch % 8 == 0 && pitch >= lpad + W * Cin, "esf_stem_pack: bad pitch %d", pitch);
-  const long long total = (long long)B * T * H * (pitch / 8);
-  stem_pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp));
+  const long long nrows = (long long)B * T * H;
+  const unsigned grid = (unsigned)std::max(1LL, std::min((nrows + 1) / 2, 148LL * 64));
+  if (Cin == 3)
+    stem_pack_kernel<3><<<grid, dim3(128, 2), 0, static_cast<cudaStream_t>(stream)>>>(
+        x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp));
+  else
+    stem_pack_kernel<0><<<grid, dim3(128, 2), 0, static_cast<cudaStream_t>(stream)>>>(
+        x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp));
   return check_launch("stem_pack_kernel");
 }
 
@@ -1268,6 +1292,12 @@ extern "C" int esf_transpose16(const void* in, int32_t B, int32_t rows, int32_t 
   return check_launch("transpose16_kernel");
 }
 
+extern "C" int esf_group_mean(const float* in, int32_t B, int32_t P, int32_t K, float* out, void* stream) {
+  ESF_CHECK_ARG(in && out && B > 0 && P > 0 && K > 0 && (long long)B * K < (1LL << 31), "esf_group_mean: null/bad argument");
+  group_mean_kernel<<<grid_for((long long)B * K, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, B, P, K, out);
+  return check_launch("group_mean_kernel");
+}
+
 extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {
   ESF_CHECK_ARG(d && view_ok(&d->x) && view_ok(&d->y) && d->w && d->bias, "esf_conv_direct: null/bad argument");
   ESF_CHECK_ARG(d->groups >= 1 && d->x.C % d->groups == 0 && d->y.C % d->groups == 0,
@@ -1329,8 +1359,14 @@ extern "C" int esf_pool3d(const esf_view* x, const esf_view* y, int32_t kT, int3
   };
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long long pos = (long long)y->B * To * Ho * Wo;
-  if (x->C % 8 == 0 && al8(x) && al8(y)) pool3d_kernel<8><<<grid_for(pos * (x->C / 8), 256), 256, 0, s>>>(p);
-  else pool3d_kernel<1><<<grid_for(pos * x->C, 256), 256, 0, s>>>(p);
+  const bool small = pos * x->C < (1LL << 31) - (148LL * 32 * 256);   // idx + grid stride stays inside 32 bits
+  if (x->C % 8 == 0 && al8(x) && al8(y)) {
+    if (small) pool3d_kernel<8, unsigned><<<grid_for(pos * (x->C / 8), 256), 256, 0, s>>>(p);
+    else pool3d_kernel<8, long long><<<grid_for(pos * (x->C / 8), 256), 256, 0, s>>>(p);
+  } else {
+    if (small) pool3d_kernel<1, unsigned><<<grid_for(pos * x->C, 256), 256, 0, s>>>(p);
+    else pool3d_kernel<1, long long><<<grid_for(pos * x->C, 256), 256, 0, s>>>(p);
+  }
   return check_launch("pool3d_kernel");
 }
 

@@ -604,6 +604,36 @@ class Plan:
         self.out = out
         return out
 
+    def head_positions(self, xs, pool_sizes, weight, bias, act):
+        """ResNetBasicHead.forward, eval branch, general case (head_helper.py:198-223): per-pathway AvgPool3d(kernel,
+        stride 1) leaves P = T' * H' * W' positions; Linear + activation at every position, mean over the positions."""
+        B = xs[0].shape[0]
+        pooled = []
+        for x, ps in zip(xs, pool_sizes):
+            _, T, H, W, C = x.shape
+            kt, kh, kw = [int(v) for v in ps]
+            y = self.act(B, T - kt + 1, H - kh + 1, W - kw + 1, C)
+            self.pool(x, y, (kt, kh, kw), (1, 1, 1), (0, 0, 0), is_avg=True)
+            pooled.append(y)
+        pos = tuple(pooled[0].shape[1:4])
+        assert all(tuple(y.shape[1:4]) == pos for y in pooled), "pathway dimensions are not consistent."
+        P = pos[0] * pos[1] * pos[2]
+        rows = []
+        for y in pooled:    # (B, T', H', W', C) -> one 1x1x1 "clip" per (clip, position)
+            C = y.shape[4]
+            assert y.stride(3) * pos[2] == y.stride(2) and y.stride(2) * pos[1] == y.stride(1) and y.stride(1) * pos[0] == y.stride(0)
+            rows.append(y.as_strided((B * P, 1, 1, 1, C), (y.stride(3), y.stride(3), y.stride(3), y.stride(3), 1),
+                                     y.storage_offset()))
+        per_pos = self.head(rows, weight, bias, act)
+        K = weight.shape[0]
+        out = torch.empty((B, K), dtype=torch.float32, device=self.device)
+        self.keep += [out]
+        L = rt.lib()
+        self._add(lambda s: rt.check(L.esf_group_mean(per_pos.data_ptr(), B, P, K, out.data_ptr(), s), "esf_group_mean"),
+                  "head_mean", "P=%d" % P, nbytes=self._nbytes(per_pos, out))
+        self.out = out
+        return out
+
     def pooled_fc(self, x, weight, bias, act, out, out_stride):
         """global mean over (T,H,W) of one activation -> FC (+bias, act) -> `out` (FP32 rows of stride out_stride):
         the `avg_pool3d -> conv_head_{slow,fast} -> ReLU` tail of GhostNetBasicHead (head_helper.py:676-688)."""

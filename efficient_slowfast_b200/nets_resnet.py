@@ -527,16 +527,21 @@ class _TwoStreamResNet(_PlannedModel):
 
         # ---- head
         xs = [c[0] for c in cur]
-        for pw, ps in enumerate(self.head.pool_size):
-            if ps is not None:
-                _, T, H, W, _ = xs[pw].shape
-                if [T, H, W] != [int(v) for v in ps]:
-                    raise NotImplementedError(
-                        "head AvgPool3d kernel %s smaller than the feature map %s (fully-convolutional multi-position "
-                        "head) is not built yet; use MULTIGRID.SHORT_CYCLE or matching DATA.CROP_SIZE/NUM_FRAMES"
-                        % (ps, [T, H, W]))
         act = {"softmax": rt.HEAD_SOFTMAX, "sigmoid": rt.HEAD_SIGMOID}[self.head.act_func]
-        plan.head(xs, self.head.projection.weight, self.head.projection.bias, act)
+        self._emit_head(plan, xs, act)
+
+    def _emit_head(self, plan, xs, act):
+        """ResNetBasicHead (head_helper.py:198-223): global pooling when the AvgPool3d kernel covers the feature map
+        (or is adaptive), else fully-convolutional inference over the remaining positions."""
+        sizes = self.head.pool_size
+        full = all(ps is None or [int(v) for v in ps] == list(x.shape[1:4]) for x, ps in zip(xs, sizes))
+        if full:
+            return plan.head(xs, self.head.projection.weight, self.head.projection.bias, act)
+        for x, ps in zip(xs, sizes):
+            if ps is None or any(int(k) > n for k, n in zip(ps, x.shape[1:4])):
+                raise NotImplementedError("head AvgPool3d kernel %s does not fit the feature map %s"
+                                          % (ps, list(x.shape[1:4])))
+        return plan.head_positions(xs, sizes, self.head.projection.weight, self.head.projection.bias, act)
 
     def _emit_stage_pathway(self, plan, stage, pw, x, dst, stride, dil):
         """One pathway of ResStage.forward (resnet_helper.py:530-561): residual blocks, each optionally followed by
@@ -684,10 +689,5 @@ class ResNet(_TwoStreamResNet):
                                       name="s2_pool0")
                     plan.pool(cur, pooled, tuple(ks), tuple(ks), (0, 0, 0))
                     cur = pooled
-        ps = self.head.pool_size[0]
-        if ps is not None and [int(v) for v in ps] != list(cur.shape[1:4]):
-            raise NotImplementedError("head AvgPool3d kernel %s smaller than the feature map %s is not built yet; use "
-                                      "MULTIGRID.SHORT_CYCLE or matching DATA.CROP_SIZE/NUM_FRAMES"
-                                      % (ps, list(cur.shape[1:4])))
         act = {"softmax": rt.HEAD_SOFTMAX, "sigmoid": rt.HEAD_SIGMOID}[self.head.act_func]
-        plan.head([cur], self.head.projection.weight, self.head.projection.bias, act)
+        self._emit_head(plan, [cur], act)

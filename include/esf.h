@@ -201,6 +201,11 @@ int esf_transpose16(const void* in, int32_t B, int32_t rows, int32_t cols, int64
 int esf_head_pool(const esf_view* x0, const esf_view* x1, float* feat, void* stream);
 int esf_head_fc(const float* feat, int32_t B, int32_t Cin, int32_t feat_stride, const float* w, const float* bias,
                 int32_t num_classes, int32_t act, float* out, int32_t out_stride, void* stream);
+/* Fully-convolutional inference (head_helper.py:218-220: `x = self.act(x); x = x.mean([1, 2, 3])`) when the head's
+ * AvgPool3d kernel is smaller than the feature map (e.g. TEST_CROP_SIZE 256 on a 224 model): esf_pool3d (avg, stride
+ * 1) -> esf_head_pool / esf_head_fc with one row per (clip, position) -> esf_group_mean over the P positions:
+ * out[b][k] = mean_p in[b][p][k]. */
+int esf_group_mean(const float* in, int32_t B, int32_t P, int32_t K, float* out, void* stream);
 
 #ifdef __cplusplus
 }

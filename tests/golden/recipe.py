@@ -123,7 +123,13 @@ CASES = {
         opts=[], calib=(2, 8, 224), inputs=[("s224", 1, 8, 224)]),
     "slow_r50": dict(
         model="ResNet", yaml="configs/Kinetics/SLOW_8x8_R50.yaml", single=True,
-        opts=["DATA.CROP_SIZE", 64], calib=(2, 8, 64), inputs=[("s64", 2, 8, 64)]),
+        opts=["DATA.CROP_SIZE", 64], calib=(2, 8, 64), inputs=[("s64", 2, 8, 64), ("s96", 1, 8, 96)]),
+    # fully-convolutional inference: the head's AvgPool3d kernel ([4,2,2] / [32,2,2] at CROP_SIZE 64) is smaller than
+    # the 3x3 feature map of a 96^2 clip -> Linear + softmax at 2x2 positions, then their mean (head_helper.py:218-220);
+    # ("s96" of slow_r50 above is the single-pathway instance of the same path)
+    "slowfast_r50_fcn": dict(
+        model="SlowFast", yaml="configs/Kinetics/SLOWFAST_4x16_R50.yaml",
+        opts=["DATA.CROP_SIZE", 64], calib=(2, 32, 96), inputs=[("s96", 1, 32, 96), ("s64", 2, 32, 64)]),
     # Nonlocal blocks after res3 blocks 1,3 and res4 blocks 1,3,5 (pool (1,2,2) on phi / g)
     "slow_nln_r50": dict(       # "dot_product" instantiation
         model="ResNet", yaml="configs/Kinetics/SLOW_NLN_8x8_R50.yaml", single=True,

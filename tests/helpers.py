@@ -36,6 +36,9 @@ def case_cfg(name):
     elif name == "slow_r50":
         cfg = esf.resnet_cfg("slow")
         cfg.DATA.CROP_SIZE = 64
+    elif name == "slowfast_r50_fcn":
+        cfg = esf.slowfast_4x16_r50_cfg()
+        cfg.DATA.CROP_SIZE = 64
     elif name == "slow_nln_r50":
         cfg = esf.resnet_cfg("slow", nln=True)
         cfg.DATA.CROP_SIZE = 64

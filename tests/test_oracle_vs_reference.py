@@ -11,7 +11,7 @@ pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="/root/referenc
 
 
 @pytest.mark.parametrize("name", ["dual_r50", "slowfast_r50", "shufflenetv2_w05", "shufflenet_w2g3", "mobilenetv2_w1",
-                                  "ghostnet_w1", "i3d_r50", "slow_r50", "slow_nln_r50", "i3d_nln_r50"])
+                                  "ghostnet_w1", "i3d_r50", "slow_r50", "slow_nln_r50", "i3d_nln_r50", "slowfast_r50_fcn"])
 def test_every_stage_bit_exact(name):
     spec = recipe.CASES[name]
     cfg = ref_shim.get_cfg(spec["yaml"], spec["opts"])
@@ -43,7 +43,7 @@ def test_every_stage_bit_exact(name):
 
 
 @pytest.mark.parametrize("name", ["dual_r50", "slowfast_r50", "shufflenetv2_w05", "shufflenet_w2g3", "mobilenetv2_w1",
-                                  "ghostnet_w1", "i3d_r50", "slow_r50", "slow_nln_r50", "i3d_nln_r50"])
+                                  "ghostnet_w1", "i3d_r50", "slow_r50", "slow_nln_r50", "i3d_nln_r50", "slowfast_r50_fcn"])
 def test_state_dict_schema_and_seeded_init_match_reference(name):
     import efficient_slowfast_b200 as esf
 
