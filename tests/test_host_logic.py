@@ -152,3 +152,53 @@ def test_head_fc_launch_accounting():
     assert engine.head_fc_launches(64, 2304, 400, rt.HEAD_RELU) == 1
     assert engine.head_fc_launches(2, 2304, 400, rt.HEAD_SOFTMAX) == 1
     assert engine.head_fc_launches(2, 20000, 400, rt.HEAD_SOFTMAX) == 2
+
+
+# ------------------------------------------------------------------------------------------------ Caffe2 checkpoints
+def test_caffe2_name_mapping_matches_reference_fixture():
+    """tests/golden/caffe2_names.json: 646 Caffe2 blob names (stems, bottlenecks of both pathways, lateral convs,
+    Nonlocal blocks, classifier) converted by the reference's utils/c2_model_loading.get_name_convert_func."""
+    import json
+    import os
+
+    import helpers
+    from efficient_slowfast_b200.checkpoint import caffe2_to_pytorch_name
+
+    want = json.load(open(os.path.join(helpers.GOLDEN_DIR, "caffe2_names.json")))
+    assert len(want) > 600
+    for c2, key in want.items():
+        assert caffe2_to_pytorch_name(c2) == key, c2
+
+
+def test_caffe2_checkpoint_loads(tmp_path):
+    """A Caffe2-format pickle ({"blobs": {name: ndarray}}, checkpoint.py:206-259) fills the drop-in model."""
+    import json
+    import os
+    import pickle
+
+    import numpy as np
+    import torch
+
+    import efficient_slowfast_b200 as esf
+    import helpers
+
+    cfg = esf.resnet_cfg("slow", nln=True)
+    cfg.NUM_GPUS = 0
+    model = esf.build_model(cfg)
+    sd = model.state_dict()
+    names = json.load(open(os.path.join(helpers.GOLDEN_DIR, "caffe2_names.json")))
+    rng = np.random.RandomState(0)
+    blobs = {c2: rng.randn(*sd[key].shape).astype(np.float32) for c2, key in names.items() if key in sd}
+    assert len(blobs) > 100
+    blobs["lr"] = np.zeros(1, np.float32)
+    blobs["res2_0_branch2a_w_momentum"] = np.zeros(3, np.float32)
+    blobs["res9_0_branch2a_w"] = np.zeros(3, np.float32)            # no such layer: reported, not loaded
+    path = str(tmp_path / "c2.pkl")
+    with open(path, "wb") as f:
+        pickle.dump({"blobs": blobs}, f)
+    assert esf.load_checkpoint(path, model, convert_from_caffe2=True) == -1
+    after = model.state_dict()
+    for c2, key in names.items():
+        if key in sd:
+            assert torch.equal(after[key], torch.tensor(blobs[c2])), key
+    assert esf.load_checkpoint.last_report["skipped"] == ["res9_0_branch2a_w"]

@@ -60,3 +60,20 @@ def test_state_dict_schema_and_seeded_init_match_reference(name):
     assert [n for n, _ in mine.named_children()] == [n for n, _ in ref.named_children()]
     # a reference checkpoint loads into the drop-in (utils/checkpoint.py:279 uses strict=False)
     mine.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_caffe2_name_fixture_is_the_reference_mapping():
+    """tests/golden/caffe2_names.json was produced by the reference's own converter (utils/c2_model_loading.py)."""
+    import importlib.util
+    import json
+    import os
+
+    ref_shim.install()
+    spec = importlib.util.spec_from_file_location(
+        "c2_model_loading", os.path.join(ref_shim.REF_ROOT, "SlowFast", "slowfast", "utils", "c2_model_loading.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    convert = mod.get_name_convert_func()
+    want = json.load(open(os.path.join(helpers.GOLDEN_DIR, "caffe2_names.json")))
+    for c2, key in want.items():
+        assert convert(c2) == key
