@@ -188,7 +188,12 @@ def test_caffe2_checkpoint_loads(tmp_path):
     sd = model.state_dict()
     names = json.load(open(os.path.join(helpers.GOLDEN_DIR, "caffe2_names.json")))
     rng = np.random.RandomState(0)
-    blobs = {c2: rng.randn(*sd[key].shape).astype(np.float32) for c2, key in names.items() if key in sd}
+    blobs, used = {}, set()
+    for c2, key in sorted(names.items()):
+        if key in sd and key not in used:       # 'conv1_w' and 'res_conv1_w' name the same tensor
+            used.add(key)
+            blobs[c2] = rng.randn(*sd[key].shape).astype(np.float32)
+    names = {c2: names[c2] for c2 in blobs}
     assert len(blobs) > 100
     blobs["lr"] = np.zeros(1, np.float32)
     blobs["res2_0_branch2a_w_momentum"] = np.zeros(3, np.float32)
