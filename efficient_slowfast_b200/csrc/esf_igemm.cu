@@ -71,6 +71,9 @@ struct __align__(64) IgemmParams {
   // W-folded GEMMs (thin-channel layers): innermost start coordinate of the activation loads, and -- when the output
   // (residual) is a channel slice -- the (w, c) decomposition of an output column n = w_in_block * cout + c
   int a_c_base, fold_wb, out_fold_cout, res_fold_cout;
+  // per-clip weights (Non-local block: the "weight" matrix of a clip is its own phi / g^T rows): the packed weight
+  // matrices of all clips are stacked along n, b_clip_rows rows each, and an M tile never spans two clips (bb = 1)
+  int b_clip_rows;
 };
 
 struct TileCoord {
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
               tma_load_5d(smem_a + stage * kAStageBytes, &p.a_maps[tp.x], &full_bar[stage],
                             p.a_c_base + tc.cb * p.a_cb_stride + ch * p.kc, tc.w0 + tp.y, tc.h0 + tp.z, tc.t0 + tp.w, tc.b0);
               tma_load_2d(smem_b + stage * p.b_stride, &p.b_map, &full_bar[stage], (tap * p.kchunks + ch) * p.kc,
-                          tc.n_idx * p.n_tile);
+                          tc.n_idx * p.n_tile + tc.b0 * p.b_clip_rows);
             }
             __syncwarp();
             if (++stage == p.stages) {
@@ -522,7 +525,18 @@ static void choose_box(int W, int H, int T, int B, int* obw, int* obh, int* obt,
 
 static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
+static int igemm_create_impl(const esf_conv_desc* d, int clip_weights, esf_op** out);
+
+extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) { return igemm_create_impl(d, 0, out); }
+
+extern "C" int esf_gemm_clip_weights_create(const esf_conv_desc* d, esf_op** out) {
+  ESF_CHECK_ARG(d && d->kT == 1 && d->kH == 1 && d->kW == 1 && d->sT == 1 && d->sH == 1 && d->sW == 1 && d->pT == 0 &&
+                    d->pH == 0 && d->pW == 0 && !d->res.ptr,
+                "esf_gemm_clip_weights_create: 1x1x1, stride 1, no residual");
+  return igemm_create_impl(d, 1, out);
+}
+
+static int igemm_create_impl(const esf_conv_desc* d, int clip_weights, esf_op** out) {
   ESF_CHECK_ARG(d && out, "esf_conv_igemm_create: null argument");
   ESF_CHECK_ARG(view_ok(&d->x) && view_ok(&d->y), "esf_conv_igemm_create: bad x/y view");
   ESF_CHECK_ARG(d->groups == 1, "esf_conv_igemm_create: groups must be 1 (use esf_conv_direct)");
@@ -561,7 +575,8 @@ extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
   p.n_tile = n_tile;
   p.n_tiles = n_pad / n_tile;
   p.num_taps = num_taps;
-  choose_box(Wo, Ho, To, y.B, &p.bw, &p.bh, &p.bt, &p.bb);
+  choose_box(Wo, Ho, To, clip_weights ? 1 : y.B, &p.bw, &p.bh, &p.bt, &p.bb);
+  p.b_clip_rows = clip_weights ? n_pad : 0;
   p.tw = cdiv(Wo, p.bw);
   p.th = cdiv(Ho, p.bh);
   p.tt = cdiv(To, p.bt);
@@ -643,7 +658,7 @@ extern "C" int esf_conv_igemm_create(const esf_conv_desc* d, esf_op** out) {
     if (!enc) rc = set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     else {
       const cuuint64_t K = (cuuint64_t)num_taps * kchunks * kc;
-      cuuint64_t dims[2] = {K, (cuuint64_t)n_pad};
+      cuuint64_t dims[2] = {K, (cuuint64_t)n_pad * (clip_weights ? y.B : 1)};
       cuuint64_t strides[1] = {K * 2};
       cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)n_tile};
       cuuint32_t estr[2] = {1, 1};

@@ -203,22 +203,22 @@ class Plan:
                   flops=2.0 * m * cout * cin * kt * kh * kw, nbytes=self._nbytes(x, y, res) + wp.numel() * 2)
 
     def gemm_rows(self, x, y, w_rows, bias, kind, label):
-        """y[pos, n] = sum_c x[pos, c] * w_rows[n, c] + bias[n] on the implicit-GEMM kernel with a DEVICE-RESIDENT
-        weight matrix in the kernel's own layout ([n_pad][kchunks * kc] 16-bit rows, FP32 bias [n_pad]) -- used where
-        the "weights" are activations of the same clip (Non-local block)."""
+        """y[b, pos, n] = sum_c x[b, pos, c] * w_rows[b, n, c] + bias[n] on the implicit-GEMM kernel with one
+        DEVICE-RESIDENT weight matrix per clip, in the kernel's own layout ([B][n_pad][kchunks * kc] 16-bit rows, FP32
+        bias [n_pad]) -- used where the "weights" are activations of the same clip (Non-local block)."""
         cin, cout = x.shape[4], y.shape[4]
         kc, kchunks, _, n_pad = rt.igemm_geometry(cin, cout)
-        assert tuple(w_rows.shape) == (n_pad, kc * kchunks) and w_rows.is_contiguous() and w_rows.dtype == self.adt
-        assert bias.numel() == n_pad and bias.dtype == torch.float32
+        assert tuple(w_rows.shape) == (x.shape[0], n_pad, kc * kchunks) and w_rows.is_contiguous()
+        assert w_rows.dtype == self.adt and bias.numel() == n_pad and bias.dtype == torch.float32
         d = rt.EsfConvDesc(rt.view(x), rt.view(y), rt.null_view(), w_rows.data_ptr(), bias.data_ptr(), 1, 1, 1,
                            1, 1, 1, 0, 0, 0, 1, 1, 1, 1, rt.ACT_NONE, rt.dtype_code(y))
         h = ctypes.c_void_p()
         L = rt.lib()
-        rt.check(L.esf_conv_igemm_create(ctypes.byref(d), ctypes.byref(h)), "esf_conv_igemm_create")
+        rt.check(L.esf_gemm_clip_weights_create(ctypes.byref(d), ctypes.byref(h)), "esf_gemm_clip_weights_create")
         self.handles.append(h)
         m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
         self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), kind, label,
-                  flops=2.0 * m * cout * cin, nbytes=self._nbytes(x, y) + cout * cin * 2)
+                  flops=2.0 * m * cout * cin, nbytes=self._nbytes(x, y) + x.shape[0] * cout * cin * 2)
 
     def scratch(self, shape, dtype, zero=False):
         """Plan-lifetime scratch tensor shared by every op that asks for the same (shape, dtype): the launches of a
@@ -237,8 +237,9 @@ class Plan:
         (resnet_helper.py:541-560): y = x + bn(conv_out(normalise(theta^T phi) g^T)).
 
         theta / phi / g / out are ordinary implicit GEMMs (bias in the epilogue; BN folded into conv_out, the residual
-        add in its epilogue).  The two matrix products are implicit GEMMs as well, one launch per clip, whose weight
-        operand is the clip's own phi rows ([N_keys][d], exactly the kernel's [n][k] layout) and g^T rows
+        add in its epilogue).  The two matrix products are implicit GEMMs as well (esf_gemm_clip_weights_create: one
+        launch for the whole batch, the weight tile of an M tile is selected by its clip), whose weight operand is
+        the clip's own phi rows ([N_keys][d], exactly the kernel's [n][k] layout) and g^T rows
         ([d][N_keys], written by esf_transpose16); the affinity matrix is materialised once in FP32, normalised by
         esf_row_softmax (softmax with d^-0.5, or the 1/N_keys of "dot_product") into the 16-bit A operand of the
         second product."""
@@ -258,8 +259,6 @@ class Plan:
         def wb(conv):
             return conv.weight.detach().to(f64), conv.bias.detach().to(f64)
 
-        theta = self.act(B, T, H, W, d)
-        self.conv(x, theta, *wb(nln.conv_theta))
         if nln.use_pool:
             ps = [int(v) for v in nln.pool_size]
             Tp, Hp, Wp = (T - ps[0]) // ps[0] + 1, (H - ps[1]) // ps[1] + 1, (W - ps[2]) // ps[2] + 1
@@ -268,52 +267,81 @@ class Plan:
         else:
             Tp, Hp, Wp, xp = T, H, W, x
         Nq, Nk = T * H * W, Tp * Hp * Wp
-        # phi rows of a clip = the [n][k] weight matrix of the first product: rows padded to the GEMM's n_pad
-        kc1, kch1, _, npad1 = rt.igemm_geometry(d, Nk)
-        assert kc1 * kch1 == d, "dim_inner must fill whole K chunks"
-        phi_rows = torch.zeros((B, npad1, d), dtype=self.adt, device=self.device)
-        phi = phi_rows.as_strided((B, Tp, Hp, Wp, d), (npad1 * d, Hp * Wp * d, Wp * d, d, 1))
-        g = self.act(B, Tp, Hp, Wp, d)
-        self.keep += [phi_rows]
-        self.conv(xp, phi, *wb(nln.conv_phi))
-        self.conv(xp, g, *wb(nln.conv_g))
-        # g^T rows = the [n][k] weight matrix of the second product (k = keys, zero padded to whole chunks)
-        kc2, kch2, _, npad2 = rt.igemm_geometry(Nk, d)
-        kpad2 = kc2 * kch2
-        gT = torch.zeros((B, npad2, kpad2), dtype=self.adt, device=self.device)
-        self.keep += [gT]
-        self._add(lambda s: rt.check(L.esf_transpose16(g.data_ptr(), B, Nk, d, g.stride(0), g.stride(3), gT.data_ptr(),
-                                                       npad2 * kpad2, kpad2, s), "esf_transpose16"),
-                  "nl_transpose", "", nbytes=2 * self._nbytes(g))
-        Sbuf = self.scratch((B, T, H, W, (Nk + 3) // 4 * 4), torch.float32)
-        S = Sbuf[..., :Nk]
-        Pbuf = self.scratch((B, T, H, W, (Nk + 7) // 8 * 8), self.adt)
-        P = Pbuf[..., :Nk]
-        zero1 = self.scratch((npad1,), torch.float32, zero=True)
+        softmax = nln.instantiation == "softmax"
+        if not softmax and nln.instantiation != "dot_product":
+            raise NotImplementedError("Unknown norm type {}".format(nln.instantiation))
         # Precision: with near-uniform attention the block output is a large per-channel constant plus a small
         # variation, and the BN behind conv_out removes the constant -- 16-bit rounding of `att` would then be
         # amplified by |mean| / std.  conv_out is linear, so a per-channel offset mu can be subtracted in the FP32
-        # epilogue of the second product (its bias) and added back through conv_out's bias: W (att - mu) + (W mu + b).
+        # epilogue of the last product (its bias) and added back through conv_out's bias: W (att - mu) + (W mu + b).
         # mu = least-squares solution of W mu = running_mean - b, the att-space mean the BN statistics imply.
         w_out = nln.conv_out.weight.detach().to(f64).reshape(C, d)
         rhs = (nln.bn.running_mean.detach().to(f64) - nln.conv_out.bias.detach().to(f64)).reshape(C, 1)
         mu = torch.linalg.lstsq(w_out.cpu(), rhs.cpu()).solution.reshape(d).to(w_out.device)
-        bias2 = torch.zeros(npad2, dtype=torch.float32, device=self.device)
+        _, _, _, npad_d = rt.igemm_geometry(Nk if softmax else d, d)
+        bias2 = torch.zeros(npad_d, dtype=torch.float32, device=self.device)
         bias2[:d] = (-mu).to(torch.float32)
         mu = -bias2[:d].to(f64).to(w_out.device)     # the value actually subtracted (FP32-rounded)
         self.keep.append(bias2)
-        for b in range(B):
-            self.gemm_rows(theta[b:b + 1], S[b:b + 1], phi_rows[b], zero1, "nl_gemm", "theta.phi N=%dx%d d=%d" % (Nq, Nk, d))
-        softmax = nln.instantiation == "softmax"
-        if not softmax and nln.instantiation != "dot_product":
-            raise NotImplementedError("Unknown norm type {}".format(nln.instantiation))
-        scale = float(d) ** -0.5 if softmax else 1.0 / Nk
-        self._add(lambda s: rt.check(L.esf_row_softmax(Sbuf.data_ptr(), B * Nq, Nk, Sbuf.shape[4], scale, 0 if softmax else 1, self.a16,
-                                                       Pbuf.data_ptr(), Pbuf.shape[4], s), "esf_row_softmax"),
-                  "nl_softmax", nln.instantiation, nbytes=self._nbytes(S, P), exps=float(B * Nq * Nk) if softmax else 0)
         att = self.act(B, T, H, W, d)
-        for b in range(B):
-            self.gemm_rows(P[b:b + 1], att[b:b + 1], gT[b], bias2, "nl_gemm", "p.g N=%dx%d d=%d" % (Nq, Nk, d))
+
+        def transposed(t, name):
+            """(B, Tp, Hp, Wp, d) rows -> [B][n_pad][k_pad] = t^T per clip, zero padded: the [n][k] weight layout of a
+            GEMM that contracts over the keys."""
+            kc, kch, _, npad = rt.igemm_geometry(Nk, d)
+            kpad = kc * kch
+            tT = torch.zeros((B, npad, kpad), dtype=self.adt, device=self.device)
+            self.keep.append(tT)
+            self._add(lambda s: rt.check(L.esf_transpose16(t.data_ptr(), B, Nk, d, t.stride(0), t.stride(3), tT.data_ptr(),
+                                                           npad * kpad, kpad, s), "esf_transpose16"),
+                      "nl_transpose", name, nbytes=2 * self._nbytes(t))
+            return tT
+
+        if softmax:
+            # phi rows of a clip = the [n][k] weight matrix of theta^T phi: rows padded to the GEMM's n_pad
+            kc1, kch1, _, npad1 = rt.igemm_geometry(d, Nk)
+            assert kc1 * kch1 == d, "dim_inner must fill whole K chunks"
+            theta = self.act(B, T, H, W, d)
+            self.conv(x, theta, *wb(nln.conv_theta))
+            phi_rows = torch.zeros((B, npad1, d), dtype=self.adt, device=self.device)
+            phi = phi_rows.as_strided((B, Tp, Hp, Wp, d), (npad1 * d, Hp * Wp * d, Wp * d, d, 1))
+            g = self.act(B, Tp, Hp, Wp, d)
+            self.keep += [phi_rows]
+            self.conv(xp, phi, *wb(nln.conv_phi))
+            self.conv(xp, g, *wb(nln.conv_g))
+            gT = transposed(g, "g")
+            Sbuf = self.scratch((B, T, H, W, (Nk + 3) // 4 * 4), torch.float32)
+            S = Sbuf[..., :Nk]
+            Pbuf = self.scratch((B, T, H, W, (Nk + 7) // 8 * 8), self.adt)
+            P = Pbuf[..., :Nk]
+            zero1 = self.scratch((npad1,), torch.float32, zero=True)
+            self.gemm_rows(theta, S, phi_rows, zero1, "nl_gemm", "theta.phi N=%dx%d d=%d" % (Nq, Nk, d))
+            self._add(lambda s: rt.check(L.esf_row_softmax(Sbuf.data_ptr(), B * Nq, Nk, Sbuf.shape[4], float(d) ** -0.5, 0,
+                                                           self.a16, Pbuf.data_ptr(), Pbuf.shape[4], s), "esf_row_softmax"),
+                      "nl_softmax", nln.instantiation, nbytes=self._nbytes(S, P), exps=float(B * Nq * Nk))
+            self.gemm_rows(P, att, gT, bias2, "nl_gemm", "p.g N=%dx%d d=%d" % (Nq, Nk, d))
+        else:
+            # "dot_product" has no non-linearity between the two products:  (theta^T phi / Nk) g^T = theta^T (phi g^T / Nk),
+            # a d x d matrix per clip instead of the Nq x Nk affinity -- 2 Nk d^2 + 2 Nq d^2 FLOP instead of 4 Nq Nk d,
+            # and nothing of size Nq x Nk is ever written.  M^T[c][c'] = sum_p (g[p][c] / Nk) phi[p][c'] is itself a
+            # per-clip-weights GEMM over the transposed rows, and its 16-bit output IS the [n][k] weight matrix of
+            # att = theta M.  (The 1 / Nk goes into the g conv so that M stays O(1) in 16 bits.)
+            assert rt.igemm_geometry(d, d)[3] == d, "dim_inner must be a whole N tile"
+            theta = self.act(B, T, H, W, d)
+            self.conv(x, theta, *wb(nln.conv_theta))
+            phi = self.act(B, Tp, Hp, Wp, d)
+            g = self.act(B, Tp, Hp, Wp, d)
+            self.conv(xp, phi, *wb(nln.conv_phi))
+            wg, bg = wb(nln.conv_g)
+            self.conv(xp, g, wg / Nk, bg / Nk)
+            phiT, gT = transposed(phi, "phi"), transposed(g, "g")
+            MT = torch.zeros((B, 1, 1, d, d), dtype=self.adt, device=self.device)
+            self.keep.append(MT)
+            zero_d = self.scratch((d,), torch.float32, zero=True)
+            kpad = gT.shape[2]
+            gT_act = gT.as_strided((B, 1, 1, d, Nk), (gT.stride(0), d * kpad, d * kpad, kpad, 1))
+            self.gemm_rows(gT_act, MT, phiT, zero_d, "nl_gemm", "g^T.phi d=%d Nk=%d" % (d, Nk))
+            self.gemm_rows(theta, att, MT.reshape(B, d, d), bias2, "nl_gemm", "theta.M N=%d d=%d" % (Nq, d))
         w, bias = fold_conv_bn(nln.conv_out.weight, nln.conv_out.bias, nln.bn)
         bias = bias + w.reshape(C, d) @ mu.to(w.device)
         self.conv(att, y, w, bias, res=x)

@@ -56,6 +56,7 @@ def lib():
     L.esf_launch_count.restype = i64
     L.esf_igemm_geometry.argtypes = [i32, i32, P(i32), P(i32), P(i32), P(i32)]
     L.esf_conv_igemm_create.argtypes = [P(EsfConvDesc), P(vp)]
+    L.esf_gemm_clip_weights_create.argtypes = [P(EsfConvDesc), P(vp)]
     L.esf_conv_wfold_create.argtypes = [P(EsfConvDesc), ctypes.c_int32, P(vp)]
     L.esf_op_launch.argtypes = [vp, vp]
     L.esf_op_destroy.argtypes = [vp]
@@ -91,7 +92,7 @@ def lib():
     L.esf_attn_generic.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, i32, P(EsfView), vp]
     L.esf_head_pool.argtypes = [P(EsfView), P(EsfView), vp, vp]
     L.esf_head_fc.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp, i32, vp]
-    for name in ("esf_group_mean", "esf_row_softmax", "esf_transpose16", "esf_stem_pack_u8", "esf_frames_to_clip", "esf_attn_generic", "esf_shuffle_concat", "esf_eltwise_add", "esf_channel_scale", "esf_attn_tc_pack", "esf_attn_tc_create", "esf_stem_geometry", "esf_stem_pack", "esf_stem_igemm_create", "esf_igemm_geometry",
+    for name in ("esf_gemm_clip_weights_create", "esf_group_mean", "esf_row_softmax", "esf_transpose16", "esf_stem_pack_u8", "esf_frames_to_clip", "esf_attn_generic", "esf_shuffle_concat", "esf_eltwise_add", "esf_channel_scale", "esf_attn_tc_pack", "esf_attn_tc_create", "esf_stem_geometry", "esf_stem_pack", "esf_stem_igemm_create", "esf_igemm_geometry",
                  "esf_conv_igemm_create", "esf_conv_wfold_create", "esf_op_launch", "esf_conv_direct", "esf_stem_conv",
                  "esf_pool3d", "esf_eca_fuse", "esf_attn_pack", "esf_attn_fused", "esf_head_pool", "esf_head_fc"):
         getattr(L, name).restype = ctypes.c_int

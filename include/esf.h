@@ -189,6 +189,10 @@ int esf_attn_generic(const float* proj, int32_t B, int32_t T, int32_t H, int32_t
  * esf_row_softmax normalises the FP32 affinity rows S[rows][n] (pitch s_pitch) into 16-bit P (pitch p_pitch):
  *   mode 0: softmax_j(scale * S) ("softmax", scale = dim_inner^-0.5);  mode 1: scale * S ("dot_product", 1 / n).
  * esf_transpose16: out[b][c][r] = in[b][r][c] on 16-bit elements (g rows -> g^T, the GEMM's [n][k] weight layout). */
+/* esf_gemm_clip_weights_create: the 1x1x1 implicit GEMM of esf_conv_igemm_create with one weight matrix PER CLIP --
+ * d->w points at B stacked matrices ([B][n_pad][kchunks * kc] 16-bit), d->bias at one shared FP32 [n_pad] vector; an
+ * M tile never spans two clips.  One launch computes theta^T phi (or P g^T) of every clip of the batch. */
+int esf_gemm_clip_weights_create(const esf_conv_desc* d, esf_op** out);
 int esf_row_softmax(const float* S, int64_t rows, int32_t n, int64_t s_pitch, float scale, int32_t mode, int32_t dtype,
                     void* P, int64_t p_pitch, void* stream);
 int esf_transpose16(const void* in, int32_t B, int32_t rows, int32_t cols, int64_t in_bstride, int64_t in_pitch, void* out,
