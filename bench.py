@@ -339,7 +339,7 @@ def run_gpu(args):
     # `ncu --set full` capture of this command at the default workload (profiles/r1_ncu_bench_attention_d32_b64.md)
     traffic = None
     if top["kind"] == "attention" and top["label"] == "N=25088 d=32" and B == 64:
-        traffic = 772628736 + 389633536
+        traffic = 772445184 + 390810112
     roof.update({"traffic": traffic, "algorithmic_bytes": top["bytes"],
                  "kernel": "%s %s" % (top["kind"], top["label"]), "ms": top_ms,
                  "share_of_step": top_ms / total_ms, "peak_source": pk["_source"]})
