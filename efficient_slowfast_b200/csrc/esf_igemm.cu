@@ -74,6 +74,13 @@ struct __align__(64) IgemmParams {
   // per-clip weights (Non-local block: the "weight" matrix of a clip is its own phi / g^T rows): the packed weight
   // matrices of all clips are stacked along n, b_clip_rows rows each, and an M tile never spans two clips (bb = 1)
   int b_clip_rows;
+  // T-halo mode (halo_g > 0): the taps of a group differ only by their T offset, stride 1.  The activation tile is
+  // loaded ONCE per (group, chunk) with halo_g - 1 extra T planes, and tap j of the group is the same smem tile read
+  // from row j * (bw * bh) on -- a descriptor offset of whole swizzle atoms because bw * bh is a multiple of 8 and
+  // bb = 1.  The A tiles then live in their own ring (a_stages, a_full / a_empty); rows >= `rows` of the M tile
+  // accumulate garbage that is never stored.  taps[g * halo_g] carries the group's map / W / H / first T offset.
+  int halo_g, halo_step16, a_stages;
+  int tap_k[kMaxTaps];   // K block (in the packed weights) of every tap in kernel order
 };
 
 struct TileCoord {
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + p.stages * kAStageBytes;
+  uint8_t* smem_b = smem_a + p.a_stages * kAStageBytes;
   uint8_t* smem_out = smem_b + p.stages * p.b_stride;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_out + p.obufs * kOutStageBytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -172,7 +179,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_full = tmem_empty + 2;
   uint64_t* buf_free = res_full + kMaxOutBufs;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_free + kMaxOutBufs);
+  uint64_t* a_full = buf_free + kMaxOutBufs;
+  uint64_t* a_empty = a_full + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + kMaxStages);
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -190,6 +199,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       mbar_init(&res_full[a], 1);
       mbar_init(&buf_free[a], 1);
     }
+    if (p.halo_g)
+      for (int a = 0; a < p.a_stages; ++a) {
+        mbar_init(&a_full[a], 1);
+        mbar_init(&a_empty[a], 1);
+      }
     fence_barrier_init();
   }
   if (warp == kProducerWarp && lane == 0) {
@@ -209,7 +223,43 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   const int num_kb = p.num_taps * p.kchunks;
 
   if (warp == kProducerWarp) {
-    {
+    if (p.halo_g) {
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      const int groups = p.num_taps / p.halo_g;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(p, tile);
+        for (int g = 0; g < groups; ++g) {
+          const int4 tp = p.taps[g * p.halo_g];
+          for (int ch = 0; ch < p.kchunks; ++ch) {
+            mbar_wait(&a_empty[as], aphase ^ 1, 7);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&a_full[as], p.a_bytes);
+              tma_load_5d(smem_a + as * kAStageBytes, &p.a_maps[tp.x], &a_full[as],
+                          p.a_c_base + tc.cb * p.a_cb_stride + ch * p.kc, tc.w0 + tp.y, tc.h0 + tp.z, tc.t0 + tp.w, tc.b0);
+            }
+            __syncwarp();
+            if (++as == p.a_stages) {
+              as = 0;
+              aphase ^= 1;
+            }
+            for (int j = 0; j < p.halo_g; ++j) {
+              mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&full_bar[stage], p.b_bytes);
+                tma_load_2d(smem_b + stage * p.b_stride, &p.b_map, &full_bar[stage],
+                            (p.tap_k[g * p.halo_g + j] * p.kchunks + ch) * p.kc, tc.n_idx * p.n_tile);
+              }
+              __syncwarp();
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    } else {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -222,8 +272,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
               mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
               tma_load_5d(smem_a + stage * kAStageBytes, &p.a_maps[tp.x], &full_bar[stage],
                             p.a_c_base + tc.cb * p.a_cb_stride + ch * p.kc, tc.w0 + tp.y, tc.h0 + tp.z, tc.t0 + tp.w, tc.b0);
-              tma_load_2d(smem_b + stage * p.b_stride, &p.b_map, &full_bar[stage], (tap * p.kchunks + ch) * p.kc,
-                          tc.n_idx * p.n_tile + tc.b0 * p.b_clip_rows);
+              tma_load_2d(smem_b + stage * p.b_stride, &p.b_map, &full_bar[stage],
+                          (p.tap_k[tap] * p.kchunks + ch) * p.kc, tc.n_idx * p.n_tile + tc.b0 * p.b_clip_rows);
             }
             __syncwarp();
             if (++stage == p.stages) {
@@ -246,6 +296,51 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       uint32_t phase = 0;
       uint32_t a_lo = a_lo0, b_lo = b_lo0;
       int iter = 0;
+      if (p.halo_g) {
+        int as = 0;
+        uint32_t aphase = 0;
+        const int groups = p.num_taps / p.halo_g;
+        const int nsteps = groups * p.kchunks;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+          const int acc = iter & 1;
+          const uint32_t acc_phase = (iter >> 1) & 1;
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * p.n_tile;
+          uint32_t accum = 0;
+          for (int st = 0; st < nsteps; ++st) {
+            mbar_wait(&a_full[as], aphase, 8);
+            tc_fence_after();
+            const uint32_t a_tile = a_lo0 + as * a_step;
+            for (int j = 0; j < p.halo_g; ++j) {
+              mbar_wait(&full_bar[stage], phase, 3);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t aj = a_tile + j * p.halo_step16;
+                for (int k = 0; k < ksteps; ++k)
+                  umma_bf16_lohi(d_tmem, aj + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, k ? 1u : accum);
+                umma_commit(&empty_bar[stage]);
+                if (j == p.halo_g - 1) {
+                  umma_commit(&a_empty[as]);
+                  if (st == nsteps - 1) umma_commit(&tmem_full[acc]);
+                }
+              }
+              __syncwarp();
+              accum = 1;
+              b_lo += b_step;
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+                b_lo = b_lo0;
+              }
+            }
+            if (++as == p.a_stages) {
+              as = 0;
+              aphase ^= 1;
+            }
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
@@ -407,8 +502,19 @@ EncodeTiledFn get_encode_fn() {
 // (1x1x1 expansions) are bound by the epilogue and the residual stream, so they get the deeper ring; layers with a
 // long K loop need the stages.
 static void plan_smem(IgemmParams& p, int* smem_bytes) {
-  const int stage_bytes = kAStageBytes + (int)p.b_stride;
   const int avail = kSmemLimit - 1024 - 512;
+  if (p.halo_g) {
+    // own A ring (one haloed tile per (group, chunk)), B ring as deep as two tap groups
+    p.a_stages = 3;
+    int R = p.has_res ? 4 : 3;
+    p.obufs = R;
+    const int left = avail - R * kOutStageBytes - p.a_stages * kAStageBytes;
+    p.stages = std::max(2, std::min({left / (int)p.b_stride, kMaxStages, 2 * p.halo_g + 2}));
+    *smem_bytes = 1024 + 512 + R * kOutStageBytes + p.a_stages * kAStageBytes + p.stages * (int)p.b_stride;
+    return;
+  }
+  for (int i = 0; i < kMaxTaps; ++i) p.tap_k[i] = i;
+  const int stage_bytes = kAStageBytes + (int)p.b_stride;
   const int ksteps = p.num_taps * p.kchunks;
   const int want_stages = std::min(p.n_tile >= 256 ? 3 : 4, ksteps + 1);
   int R = p.has_res ? 6 : 3;
@@ -416,6 +522,7 @@ static void plan_smem(IgemmParams& p, int* smem_bytes) {
   p.obufs = R;
   const int stages = (avail - R * kOutStageBytes) / stage_bytes;
   p.stages = std::max(2, std::min(stages, kMaxStages));
+  p.a_stages = p.stages;
   *smem_bytes = 1024 + 512 + R * kOutStageBytes + p.stages * stage_bytes;
 }
 
@@ -523,6 +630,31 @@ static void choose_box(int W, int H, int T, int B, int* obw, int* obh, int* obt,
   *obw = rb[0], *obh = rb[1], *obt = rb[2], *obb = rb[3];
 }
 
+// T-halo tile for a kT x 1 x 1, stride-1 conv: (bw, bh) with bw * bh a multiple of 8 and bt output planes such that
+// bw * bh * (bt + kT - 1) <= 128.  Picks the tile that loads the fewest rows; returns the loaded rows relative to the
+// ordinary one-box-per-tap scheme (< 1: fewer L2 -> smem bytes), or 0 when no such tile exists.
+static double choose_halo_box(int W, int H, int T, int kT, int* obw, int* obh, int* obt) {
+  long long best = -1;
+  int ordinary[4];
+  choose_box(W, H, T, 1, &ordinary[0], &ordinary[1], &ordinary[2], &ordinary[3]);
+  for (int bw = 1; bw <= std::min(W, 128); ++bw)
+    for (int bh = 1; bh <= std::min(H, 128 / bw); ++bh) {
+      const int r = bw * bh;
+      if (r % 8 != 0) continue;
+      const int bt = std::min(T, 128 / r - (kT - 1));
+      if (bt < 1) continue;
+      // rows actually fetched: planes outside [0, T) are TMA out-of-bounds fill, not traffic
+      const long long tiles_sp = (long long)cdiv(W, bw) * cdiv(H, bh);
+      long long planes = 0;
+      for (int t0 = 0; t0 < T; t0 += bt) planes += std::min(T, t0 + bt + kT / 2) - std::max(0, t0 - kT / 2);
+      const long long loaded = tiles_sp * r * planes;
+      if (best < 0 || loaded < best) best = loaded, *obw = bw, *obh = bh, *obt = bt;
+    }
+  if (best < 0) return 0.0;
+  return (double)best / ((double)W * H * T * kT);
+}
+
+
 static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 static int igemm_create_impl(const esf_conv_desc* d, int clip_weights, esf_op** out);
@@ -577,6 +709,25 @@ static int igemm_create_impl(const esf_conv_desc* d, int clip_weights, esf_op** 
   p.num_taps = num_taps;
   choose_box(Wo, Ho, To, clip_weights ? 1 : y.B, &p.bw, &p.bh, &p.bt, &p.bb);
   p.b_clip_rows = clip_weights ? n_pad : 0;
+  // T-halo mode for k x 1 x 1 layers: OFF by default (ESF_IGEMM_THALO=1: layers with n_tile <= 64 whose haloed tile
+  // loads < 0.7x the rows; =2: every k x 1 x 1 layer).  Measured on the fast pathway's thirteen 3x1x1 layers of the
+  // headline workload: correct, and the L2 -> smem bytes drop from 3x to 1.2x, but 1.25 ms -> 1.88 ms in total
+  // (64->16 @56^2: 0.42 -> 0.58 ms): with bw * bh = 8 only 112 of the 128 MMA rows are outputs and T = 32 splits into
+  // 14 + 14 + 4 planes, i.e. 1.5x the tiles -- these layers are bound by the per-tile hand-over (accumulator, epilogue,
+  // store), not by the activation loads.
+  {
+    const char* env = getenv("ESF_IGEMM_THALO");
+    const int mode = env ? atoi(env) : 0;
+    if (mode > 0 && !clip_weights && d->kT > 1 && d->kT <= 8 && d->kH == 1 && d->kW == 1 && d->sT == 1 && d->sH == 1 &&
+        d->sW == 1 && d->dT == 1 && d->pH == 0 && d->pW == 0 && (mode == 2 || n_tile <= 64)) {
+      int hw = 0, hh = 0, ht = 0;
+      const double rel = choose_halo_box(Wo, Ho, To, d->kT, &hw, &hh, &ht);
+      if (rel > 0.0 && (mode == 2 || rel < 0.7)) {
+        p.halo_g = d->kT;
+        p.bw = hw, p.bh = hh, p.bt = ht, p.bb = 1;
+      }
+    }
+  }
   p.tw = cdiv(Wo, p.bw);
   p.th = cdiv(Ho, p.bh);
   p.tt = cdiv(To, p.bt);
@@ -592,6 +743,10 @@ static int igemm_create_impl(const esf_conv_desc* d, int clip_weights, esf_op** 
   p.a_cb_stride = p.out_cb_w = 0;
   const int row_bytes = kc * 2;
   p.a_bytes = p.rows * row_bytes;
+  if (p.halo_g) {
+    p.a_bytes = p.bw * p.bh * (p.bt + p.halo_g - 1) * row_bytes;
+    p.halo_step16 = (p.bw * p.bh * row_bytes) >> 4;
+  }
   p.b_bytes = n_tile * row_bytes;
   p.b_stride = (p.b_bytes + 1023) & ~1023u;
   p.sbo = 8 * row_bytes;
@@ -643,10 +798,11 @@ static int igemm_create_impl(const esf_conv_desc* d, int clip_weights, esf_op** 
           }
           char* base = static_cast<char*>(x.ptr) + 2 * (ph.pt * x.sT + ph.ph * x.sH + ph.pw * x.sW);
           rc = encode_act_map(&p.a_maps[idx], dt16, 2, base, x.C, Wp, Hp, Tp, x.B,
-                              x.sW * d->sW, x.sH * d->sH, x.sT * d->sT, x.sB, kc, p.bw, p.bh, p.bt, p.bb,
-                              swizzle_for_row_bytes(row_bytes), "activation");
+                              x.sW * d->sW, x.sH * d->sH, x.sT * d->sT, x.sB, kc, p.bw, p.bh,
+                              p.halo_g ? p.bt + p.halo_g - 1 : p.bt, p.bb, swizzle_for_row_bytes(row_bytes), "activation");
         }
         p.taps[tap_i] = make_int4(idx, qw, qh, qt);
+        if (p.halo_g) p.tap_k[tap_i] = tap_i;   // kT x 1 x 1: one group, taps already ordered by kt
       }
   // unused map slots alias map 0 so that the kernel parameter block is fully initialised
   if (rc == ESF_OK)

@@ -66,13 +66,21 @@ CONV_CASES = [
     ("tiny_8to32", (2, 8, 14, 14), 8, 32, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1), 0, True, False),
     ("b_1x3x3_s2_7x7", (3, 8, 14, 14), 512, 512, (1, 3, 3), (1, 2, 2), (0, 1, 1), (1, 1, 1), 1, False, False),
     ("many_tiles", (8, 8, 28, 28), 128, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1), (1, 1, 1), 1, False, False),
+    # k x 1 x 1 layers in T-halo mode (one haloed activation tile per chunk, taps = descriptor offsets; opt-in)
+    ("halo_3x1x1_64to16", (2, 32, 28, 28), 64, 16, (3, 1, 1), (1, 1, 1), (1, 0, 0), (1, 1, 1), 1, False, False),
+    ("halo_3x1x1_res_2chunks", (1, 16, 14, 14), 128, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), (1, 1, 1), 1, True, False),
+    ("halo_5x1x1_partial_t", (1, 13, 8, 16), 64, 64, (5, 1, 1), (1, 1, 1), (2, 0, 0), (1, 1, 1), 0, False, False),
+    ("halo_3x1x1_kc32_odd", (2, 9, 7, 9), 32, 16, (3, 1, 1), (1, 1, 1), (1, 0, 0), (1, 1, 1), 1, False, False),
+    ("halo_3x1x1_f32_out", (1, 8, 8, 8), 64, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), (1, 1, 1), 0, False, True),
 ]
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp16"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_conv_igemm(esf_lib, case, precision):
+def test_conv_igemm(esf_lib, case, precision, monkeypatch):
     name, (B, T, H, W), cin, cout, k, s, p, d, act, use_res, out_f32 = case
+    if name.startswith("halo_"):        # the T-halo mode is an opt-in experiment (csrc/esf_igemm.cu): keep it tested
+        monkeypatch.setenv("ESF_IGEMM_THALO", "2")
     adt = rt.TORCH_DTYPE[precision]
     g = torch.Generator().manual_seed(sum(map(ord, name)) % 1000)
     # input and output live inside wider concat buffers (channel slices) to exercise strided views
