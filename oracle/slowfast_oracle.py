@@ -40,6 +40,10 @@ POOL1 = {"c2d": [[2, 1, 1]], "c2d_nopool": [[1, 1, 1]], "i3d": [[2, 1, 1]], "i3d
          "slow": [[1, 1, 1]], "slowfast": [[1, 1, 1], [1, 1, 1]]}
 
 
+# Where the restatement runs.  "cpu" always -- it is the oracle -- except in tests/experiments/eager_torch_gpu.py, which
+# times the same torch ops (cuDNN / cuBLAS eager kernels, what the reference itself would launch) on the GPU.
+DEVICE = "cpu"
+
 def _bn(x, sd, p):
     """Eval-mode BatchNorm3d (batchnorm_helper.py:15-24 -> nn.BatchNorm3d)."""
     w, b = sd[p + ".weight"], sd[p + ".bias"]
@@ -139,7 +143,7 @@ def position_attention(x, sd, p, row_chunk=2048):
     q = _conv(x, sd, p + ".query_conv").reshape(B, -1, N)   # (B, dq, N)
     k = _conv(x, sd, p + ".key_conv").reshape(B, -1, N)     # (B, dq, N)
     v = _conv(x, sd, p + ".value_conv").reshape(B, -1, N)   # (B, C,  N)
-    out = torch.empty(B, C, N, dtype=x.dtype)
+    out = torch.empty(B, C, N, dtype=x.dtype, device=x.device)
     for n0 in range(0, N, row_chunk):
         n1 = min(N, n0 + row_chunk)
         att = torch.softmax(torch.bmm(q[:, :, n0:n1].transpose(1, 2), k), dim=-1)  # (B, n, N)
@@ -215,8 +219,8 @@ def _resnet_two_stream(cfg, sd, inputs, fuse, dtype, taps):
     assert len(inputs) == 2, "Input tensor does not contain 2 pathway"
     depth = STAGE_DEPTH[cfg.RESNET.DEPTH]
     ng = [cfg.RESNET.NUM_GROUPS] * 2
-    sd = {k: v.detach().to("cpu") for k, v in sd.items()}
-    xs = [t.detach().to("cpu", dtype) for t in inputs]
+    sd = {k: v.detach().to(DEVICE) for k, v in sd.items()}
+    xs = [t.detach().to(DEVICE, dtype) for t in inputs]
 
     def tap(name, val):
         if taps is not None:
@@ -259,8 +263,8 @@ def resnet_forward(cfg, sd, inputs, dtype=torch.float32, taps=None):
     res2 (kernel = stride = _POOL1[arch], video_model_builder.py:503-509)."""
     assert len(inputs) == 1, "Input tensor does not contain 1 pathway"
     depth = STAGE_DEPTH[cfg.RESNET.DEPTH]
-    sd = {k: v.detach().to("cpu") for k, v in sd.items()}
-    xs = [inputs[0].detach().to("cpu", dtype)]
+    sd = {k: v.detach().to(DEVICE) for k, v in sd.items()}
+    xs = [inputs[0].detach().to(DEVICE, dtype)]
 
     def tap(name, val):
         if taps is not None:
