@@ -66,15 +66,21 @@ class FrameInput:
         return self._index[key]
 
 
-def launch_frames(plan, fin, frames, alpha):
-    """Fill the stem inputs of `plan` from uint8 frames (B, T, H, W, C) on the current stream."""
+def launch_frames(plan, fin, frames, alpha, frame_index=None):
+    """Fill the stem inputs of `plan` from uint8 frames (B, T, H, W, C) on the current stream.  `frame_index`: optional
+    list (one entry per pathway) of device int32 tensors, source frame of every pathway frame -- replaces the loader's
+    rule (slow = linspace gather of the fast frames) for callers that keep frames in a ring (demo.SlidingWindow)."""
     L = rt.lib()
     s = rt.current_stream_ptr()
     B, Tsrc, H, W, C = frames.shape
-    for own in plan.inputs:
+    for pw, own in enumerate(plan.inputs):
         b, c, T, h, w = own.shape
         assert (b, c, h, w) == (B, C, H, W)
-        idx = fin.index(Tsrc, T, alpha)
+        if frame_index is not None:
+            idx = frame_index[pw]
+            assert idx.dtype == torch.int32 and idx.numel() == T and idx.device == frames.device
+        else:
+            idx = fin.index(Tsrc, T, alpha)
         iptr = idx.data_ptr() if idx is not None else None
         route = plan.stem_routes.get(own.data_ptr())
         if route is not None:

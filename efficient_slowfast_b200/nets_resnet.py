@@ -330,7 +330,7 @@ class _PlannedModel(nn.Module):
             return [(B, C, T, H, W)]
         return [(B, C, T // self._cfg.SLOWFAST.ALPHA, H, W), (B, C, T, H, W)]
 
-    def forward_frames(self, frames, bboxes=None):
+    def forward_frames(self, frames, bboxes=None, frame_index=None):
         """Same result as `forward(pack_pathway_output(cfg, tensor_normalize(frames, MEAN, STD).permute(...)))` of the
         reference's loader chain, from the decoder's uint8 frames (B, T, H, W, C) on the device: normalisation,
         layout change and the slow-pathway frame gather run inside the stem-pack kernel (frames.py)."""
@@ -345,12 +345,17 @@ class _PlannedModel(nn.Module):
         if frames.dtype != torch.uint8 or frames.dim() != 5 or not frames.is_contiguous():
             raise rt.EsfError("forward_frames expects contiguous uint8 frames (B, T, H, W, C)")
         dev = frames.device
-        plan = self._get_plan(self.frame_shapes(tuple(frames.shape)), dev)
+        shapes = self.frame_shapes(tuple(frames.shape))
+        if frame_index is not None:     # explicit source frame of every pathway frame (frames may be a ring buffer)
+            assert len(frame_index) == self.num_pathways
+            B, _, H, W, C = frames.shape
+            shapes = [(B, C, int(ix.numel()), H, W) for ix in frame_index]
+        plan = self._get_plan(shapes, dev)
         fin = getattr(plan, "frame_input", None)
         if fin is None:
             fin = plan.frame_input = esf_frames.FrameInput(self._cfg, dev, plan.adt, channels=frames.shape[4])
         alpha = self._cfg.SLOWFAST.ALPHA if self.num_pathways > 1 else 1
-        out = plan.run_frames(lambda: esf_frames.launch_frames(plan, fin, frames, alpha))
+        out = plan.run_frames(lambda: esf_frames.launch_frames(plan, fin, frames, alpha, frame_index))
         return out.clone()
 
     def _emit_fuse(self, plan, fuse, cur):

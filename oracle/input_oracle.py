@@ -43,3 +43,15 @@ def frames_to_inputs(frames_u8, mean, std, alpha, single_pathway=False, reverse_
         f = f.permute(3, 0, 1, 2)
         per_clip.append(pack_pathway_output(f, alpha, single_pathway, reverse_input_channel))
     return [torch.stack([c[i] for c in per_clip]).contiguous() for i in range(len(per_clip[0]))]
+
+
+def demo_window_inputs(window_u8, mean, std, num_frames, alpha=None):
+    """SlowFast/tools/demo_net.py:198-224: the model inputs the demo builds from its frame buffer.  window_u8: uint8
+    (L, H, W, C), oldest frame first.  tensor_normalize -> permute(3,0,1,2) -> unsqueeze(0) -> fast (or single) pathway =
+    index_select(linspace(0, L-1, num_frames).long()); slow = index_select(fast, linspace(0, NF-1, NF // alpha).long())."""
+    x = tensor_normalize(window_u8, list(mean), list(std)).permute(3, 0, 1, 2).unsqueeze(0)
+    fast = torch.index_select(x, 2, torch.linspace(0, x.shape[2] - 1, num_frames).long())
+    if alpha is None:
+        return [fast]
+    slow = torch.index_select(fast, 2, torch.linspace(0, fast.shape[2] - 1, fast.shape[2] // alpha).long())
+    return [slow, fast]
