@@ -81,23 +81,34 @@ struct __align__(64) IgemmParams {
   // accumulate garbage that is never stored.  taps[g * halo_g] carries the group's map / W / H / first T offset.
   int halo_g, halo_step16, a_stages;
   int tap_k[kMaxTaps];   // K block (in the packed weights) of every tap in kernel order
+  uint32_t dv_mul[5], dv_shr[5];   // magic numbers of the divisions by n_tiles, ncb, tw, th, tt (finish_op)
 };
 
 struct TileCoord {
   int n_idx, cb, w0, h0, t0, b0;
 };
+// x / d for 0 <= x < 2^31 by a multiply-high and a shift (m = ceil(2^(31 + ceil(log2 d)) / d), the usual magic-number
+// division): the five run-time divisions of a tile index were a ~1000-cycle dependent chain on the critical path of
+// every tile (the TMA-store leader, the producer and the residual warp all decompose the index).
+__device__ __forceinline__ int fast_div(int x, uint32_t mul, uint32_t shr) {
+  return mul ? (int)(__umulhi((uint32_t)x, mul) >> shr) : x;
+}
 __device__ __forceinline__ TileCoord tile_coord(const IgemmParams& p, int tile) {
   TileCoord c;
-  c.n_idx = tile % p.n_tiles;
-  int m = tile / p.n_tiles;
-  c.cb = m % p.ncb;
-  m /= p.ncb;
-  c.w0 = (m % p.tw) * p.bw;
-  m /= p.tw;
-  c.h0 = (m % p.th) * p.bh;
-  m /= p.th;
-  c.t0 = (m % p.tt) * p.bt;
-  c.b0 = (m / p.tt) * p.bb;
+  int m = fast_div(tile, p.dv_mul[0], p.dv_shr[0]);
+  c.n_idx = tile - m * p.n_tiles;
+  int q = fast_div(m, p.dv_mul[1], p.dv_shr[1]);
+  c.cb = m - q * p.ncb;
+  m = q;
+  q = fast_div(m, p.dv_mul[2], p.dv_shr[2]);
+  c.w0 = (m - q * p.tw) * p.bw;
+  m = q;
+  q = fast_div(m, p.dv_mul[3], p.dv_shr[3]);
+  c.h0 = (m - q * p.th) * p.bh;
+  m = q;
+  q = fast_div(m, p.dv_mul[4], p.dv_shr[4]);
+  c.t0 = (m - q * p.tt) * p.bt;
+  c.b0 = q * p.bb;
   return c;
 }
 
@@ -425,8 +436,15 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     int buf = 0, use = 0, prev_buf = 0;
     bool first = true;
     int iter = 0;
+    // Per-tile integer work of the 512 epilogue threads is what bounds the small-N layers (ncu, 1x1x1 64->32 @56^2: 309
+    // instructions per warp and tile, half of them the six divisions of tile_coord; 89 % of all instructions of the
+    // kernel): only the leader needs the tile's coordinates (for the TMA store), everybody else just its N tile, which
+    // is carried incrementally.
+    const int n_step = gridDim.x % p.n_tiles;
+    int n_idx = blockIdx.x % p.n_tiles;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
-      const TileCoord tc = tile_coord(p, tile);
+      TileCoord tc;
+      if (leader) tc = tile_coord(p, tile);
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase, 4);
@@ -437,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         if (active) {
           const int col = s * p.slab_cols + part * cpt;
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_tile + col;
-          const float* bias = p.bias + tc.n_idx * p.n_tile + col;
+          const float* bias = p.bias + n_idx * p.n_tile + col;
           uint8_t* row = stage_buf + rowoff;
           if (p.out_f32) epi_process32(taddr, bias, row, inner, x, p.act, row_valid);
           else if (cpt == 16) {
@@ -475,6 +493,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           ++use;
         }
       }
+      n_idx += n_step;
+      if (n_idx >= p.n_tiles) n_idx -= p.n_tiles;
     }
     if (leader) tma_store_wait_all<0>();
   }
@@ -583,7 +603,24 @@ struct IgemmOp : esf_op {
 
 using namespace esf;
 
+static void magic_div(int d, uint32_t* mul, uint32_t* shr) {
+  if (d <= 1) {
+    *mul = 0, *shr = 0;     // fast_div: identity
+    return;
+  }
+  int lg = 0;
+  while ((1LL << lg) < d) ++lg;           // ceil(log2 d)
+  const int pw = 31 + lg;
+  *mul = (uint32_t)(((1ULL << pw) + (uint64_t)d - 1) / (uint64_t)d);
+  *shr = (uint32_t)(pw - 32);
+}
+
 static int finish_op(IgemmOp* op) {
+  {
+    IgemmParams& p = op->params;
+    const int dv[5] = {p.n_tiles, p.ncb, p.tw, p.th, p.tt};
+    for (int i = 0; i < 5; ++i) magic_div(dv[i], &p.dv_mul[i], &p.dv_shr[i]);
+  }
   const int sms = num_sms();
   if (sms <= 0) return set_error(ESF_ERR_CUDA, "no CUDA device");
   op->grid = std::min(op->params.num_tiles, sms);
