@@ -178,6 +178,93 @@ __device__ __forceinline__ void epi_process32(uint32_t taddr, const float* __res
   }
 }
 
+struct EpiCtx {
+  uint8_t* smem_out;
+  uint64_t *tmem_full, *tmem_empty, *res_full, *buf_free;
+  uint32_t tmem_base;
+  int warp, lane;
+};
+
+// The tile loop of the 16 epilogue warps (see the kernel header): TMEM -> + bias (+ residual) -> activation -> staging
+// smem -> TMA store.
+template <int CPT, bool F16, bool F32OUT>
+__device__ __forceinline__ void epilogue_loop(const IgemmParams& p, const EpiCtx& ec) {
+  const int warp = ec.warp, lane = ec.lane;
+  const int act = p.act;
+  const int q = warp & 3;       // TMEM lane quarter this warp may access
+  const int part = warp >> 2;   // which share of the slab's columns
+  const int r = q * 32 + lane;
+  const bool row_valid = r < p.rows;
+  const bool leader = threadIdx.x == 0;
+  const int slabs = p.n_tile / p.slab_cols;
+  constexpr int cpt = CPT;  // columns per thread per slab
+  const bool active = part * cpt < p.slab_cols;
+  constexpr int oes = F32OUT ? 4 : 2;
+  const uint32_t rowoff = r * p.slab_cols * oes;
+  const uint32_t inner = part * cpt * oes;
+  const uint32_t x = ((rowoff >> 7) & p.out_swz) << 4;
+  const int R = p.obufs;
+  const bool has_res = p.has_res != 0;
+  int buf = 0, use = 0, prev_buf = 0;
+  bool first = true;
+  int iter = 0;
+  // Per-tile integer work of the 512 epilogue threads is what bounds the small-N layers (ncu, 1x1x1 64->32 @56^2: 309
+  // instructions per warp and tile, half of them the six divisions of tile_coord; 89 % of all instructions of the
+  // kernel): only the leader needs the tile's coordinates (for the TMA store), everybody else just its N tile, which
+  // is carried incrementally.
+  const int n_step = gridDim.x % p.n_tiles;
+  int n_idx = blockIdx.x % p.n_tiles;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+    TileCoord tc;
+    if (leader) tc = tile_coord(p, tile);
+    const int acc = iter & 1;
+    const uint32_t acc_phase = (iter >> 1) & 1;
+    mbar_wait(&ec.tmem_full[acc], acc_phase, 4);
+    tc_fence_after();
+    for (int s = 0; s < slabs; ++s) {
+      uint8_t* stage_buf = ec.smem_out + buf * kOutStageBytes;
+      if (has_res) mbar_wait(&ec.res_full[buf], use & 1, 5);
+      if (active) {
+        const int col = s * p.slab_cols + part * cpt;
+        const uint32_t taddr = ec.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_tile + col;
+        const float* bias = p.bias + n_idx * p.n_tile + col;
+        uint8_t* row = stage_buf + rowoff;
+        if constexpr (F32OUT) epi_process32(taddr, bias, row, inner, x, act, row_valid);
+        else epi_process16<CPT, F16>(taddr, bias, row, inner, x, has_res, act, row_valid);
+      }
+      if (s == slabs - 1) {  // accumulator fully drained: hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ec.tmem_empty[acc]);
+      }
+      fence_proxy_async_smem();
+      // One barrier per slab is enough with a ring of >= 3 buffers: a thread that runs ahead writes buffer
+      // (g + 1) % R, whose previous store (g + 1 - R <= g - 2) the leader saw finish reading before it arrived here.
+      epi_bar_sync(1);
+      if (leader) {
+        int c = tc.n_idx * p.n_tile + s * p.slab_cols, w = tc.w0 + tc.cb * p.out_cb_w;
+        if (p.out_fold_cout) {
+          w = tc.cb * p.fold_wb + c / p.out_fold_cout;
+          c = c % p.out_fold_cout;
+        }
+        tma_store_5d(&p.out_map, stage_buf, c, w, tc.h0, tc.t0, tc.b0);
+        tma_store_commit();
+        tma_store_wait_read<1>();  // every store before this one has finished reading its staging buffer
+        if (has_res && !first) mbar_arrive(&ec.buf_free[prev_buf]);
+      }
+      first = false;
+      prev_buf = buf;
+      if (++buf == R) {
+        buf = 0;
+        ++use;
+      }
+    }
+    n_idx += n_step;
+    if (n_idx >= p.n_tiles) n_idx -= p.n_tiles;
+  }
+  if (leader) tma_store_wait_all<0>();
+}
+
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -419,84 +506,21 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps 0..15
-    const int q = warp & 3;       // TMEM lane quarter this warp may access
-    const int part = warp >> 2;   // which share of the slab's columns
-    const int r = q * 32 + lane;
-    const bool row_valid = r < p.rows;
-    const bool leader = threadIdx.x == 0;
-    const int slabs = p.n_tile / p.slab_cols;
+    // dispatched ONCE on the layer's output format / columns per thread, so that the per-slab body is straight-line code
+    // with compile-time shapes (the run-time `if (out_f32) .. else if (cpt == 16) .. if (f16)` ladder inside the loop
+    // cost ~100 of the 173 instructions per warp and tile that bound the small-N layers)
+    EpiCtx c;
+    c.smem_out = smem_out, c.tmem_full = tmem_full, c.tmem_empty = tmem_empty, c.res_full = res_full;
+    c.buf_free = buf_free, c.tmem_base = tmem_base, c.warp = warp, c.lane = lane;
     const int cpt = max(8, p.slab_cols >> 2);  // columns per thread per slab
-    const bool active = part * cpt < p.slab_cols;
-    const int oes = p.out_f32 ? 4 : 2;
-    const uint32_t rowoff = r * p.slab_cols * oes;
-    const uint32_t inner = part * cpt * oes;
-    const uint32_t x = ((rowoff >> 7) & p.out_swz) << 4;
-    const int R = p.obufs;
-    const bool has_res = p.has_res != 0;
-    int buf = 0, use = 0, prev_buf = 0;
-    bool first = true;
-    int iter = 0;
-    // Per-tile integer work of the 512 epilogue threads is what bounds the small-N layers (ncu, 1x1x1 64->32 @56^2: 309
-    // instructions per warp and tile, half of them the six divisions of tile_coord; 89 % of all instructions of the
-    // kernel): only the leader needs the tile's coordinates (for the TMA store), everybody else just its N tile, which
-    // is carried incrementally.
-    const int n_step = gridDim.x % p.n_tiles;
-    int n_idx = blockIdx.x % p.n_tiles;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
-      TileCoord tc;
-      if (leader) tc = tile_coord(p, tile);
-      const int acc = iter & 1;
-      const uint32_t acc_phase = (iter >> 1) & 1;
-      mbar_wait(&tmem_full[acc], acc_phase, 4);
-      tc_fence_after();
-      for (int s = 0; s < slabs; ++s) {
-        uint8_t* stage_buf = smem_out + buf * kOutStageBytes;
-        if (has_res) mbar_wait(&res_full[buf], use & 1, 5);
-        if (active) {
-          const int col = s * p.slab_cols + part * cpt;
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_tile + col;
-          const float* bias = p.bias + n_idx * p.n_tile + col;
-          uint8_t* row = stage_buf + rowoff;
-          if (p.out_f32) epi_process32(taddr, bias, row, inner, x, p.act, row_valid);
-          else if (cpt == 16) {
-            if (p.f16) epi_process16<16, true>(taddr, bias, row, inner, x, has_res, p.act, row_valid);
-            else epi_process16<16, false>(taddr, bias, row, inner, x, has_res, p.act, row_valid);
-          } else {
-            if (p.f16) epi_process16<8, true>(taddr, bias, row, inner, x, has_res, p.act, row_valid);
-            else epi_process16<8, false>(taddr, bias, row, inner, x, has_res, p.act, row_valid);
-          }
-        }
-        if (s == slabs - 1) {  // accumulator fully drained: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-        fence_proxy_async_smem();
-        // One barrier per slab is enough with a ring of >= 3 buffers: a thread that runs ahead writes buffer
-        // (g + 1) % R, whose previous store (g + 1 - R <= g - 2) the leader saw finish reading before it arrived here.
-        epi_bar_sync(1);
-        if (leader) {
-          int c = tc.n_idx * p.n_tile + s * p.slab_cols, w = tc.w0 + tc.cb * p.out_cb_w;
-          if (p.out_fold_cout) {
-            w = tc.cb * p.fold_wb + c / p.out_fold_cout;
-            c = c % p.out_fold_cout;
-          }
-          tma_store_5d(&p.out_map, stage_buf, c, w, tc.h0, tc.t0, tc.b0);
-          tma_store_commit();
-          tma_store_wait_read<1>();  // every store before this one has finished reading its staging buffer
-          if (has_res && !first) mbar_arrive(&buf_free[prev_buf]);
-        }
-        first = false;
-        prev_buf = buf;
-        if (++buf == R) {
-          buf = 0;
-          ++use;
-        }
-      }
-      n_idx += n_step;
-      if (n_idx >= p.n_tiles) n_idx -= p.n_tiles;
+    if (p.out_f32) epilogue_loop<8, false, true>(p, c);
+    else if (cpt == 16) {
+      if (p.f16) epilogue_loop<16, true, false>(p, c);
+      else epilogue_loop<16, false, false>(p, c);
+    } else {
+      if (p.f16) epilogue_loop<8, true, false>(p, c);
+      else epilogue_loop<8, false, false>(p, c);
     }
-    if (leader) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
