@@ -112,12 +112,23 @@ __device__ __forceinline__ TileCoord tile_coord(const IgemmParams& p, int tile) 
   return c;
 }
 
+// staging rows are addressed in the shared state space (32-bit addresses, LDS / STS) -- generic 64-bit pointers cost
+// two extra integer instructions per access and a generic-to-shared resolution on the epilogue's critical path
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kEpiThreads) : "memory"); }
 
 // One epilogue thread: NC accumulator columns of its row for one output slab.  `row` points at the thread's staging row,
 // `inner` is the byte offset of its first column inside the row and `x` the row's swizzle XOR term.
 template <int NC, bool F16>
-__device__ __forceinline__ void epi_process16(uint32_t taddr, const float* __restrict__ bias, uint8_t* row, uint32_t inner,
+__device__ __forceinline__ void epi_process16(uint32_t taddr, const float* __restrict__ bias, uint32_t row, uint32_t inner,
                                               uint32_t x, bool has_res, int act, bool row_valid) {
   float v[NC], b[NC];
   uint4 rr[NC / 8];
@@ -128,7 +139,7 @@ __device__ __forceinline__ void epi_process16(uint32_t taddr, const float* __res
   }
   if (has_res) {
 #pragma unroll
-    for (int c = 0; c < NC / 8; ++c) rr[c] = *reinterpret_cast<const uint4*>(row + ((inner + c * 16) ^ x));
+    for (int c = 0; c < NC / 8; ++c) rr[c] = lds128(row + ((inner + c * 16) ^ x));
   }
   tmem_ld<NC>(taddr, v);
 #pragma unroll
@@ -160,21 +171,22 @@ __device__ __forceinline__ void epi_process16(uint32_t taddr, const float* __res
       o.y = pack16x2(v[8 * c + 2], v[8 * c + 3], F16);
       o.z = pack16x2(v[8 * c + 4], v[8 * c + 5], F16);
       o.w = pack16x2(v[8 * c + 6], v[8 * c + 7], F16);
-      *reinterpret_cast<uint4*>(row + ((inner + c * 16) ^ x)) = o;
+      sts128(row + ((inner + c * 16) ^ x), o);
     }
   }
 }
 
 // FP32 destination (attention projections): 8 columns per thread, no residual.
-__device__ __forceinline__ void epi_process32(uint32_t taddr, const float* __restrict__ bias, uint8_t* row, uint32_t inner,
+__device__ __forceinline__ void epi_process32(uint32_t taddr, const float* __restrict__ bias, uint32_t row, uint32_t inner,
                                               uint32_t x, int act, bool row_valid) {
   float v[8];
   tmem_ld<8>(taddr, v);
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j] + __ldg(bias + j), act);
   if (row_valid) {
-    *reinterpret_cast<float4*>(row + (inner ^ x)) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(row + ((inner + 16) ^ x)) = make_float4(v[4], v[5], v[6], v[7]);
+    sts128(row + (inner ^ x), make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+    sts128(row + ((inner + 16) ^ x),
+           make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
   }
 }
 
@@ -205,6 +217,7 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, const EpiCtx
   const uint32_t x = ((rowoff >> 7) & p.out_swz) << 4;
   const int R = p.obufs;
   const bool has_res = p.has_res != 0;
+  const uint32_t stage_base = smem_u32(ec.smem_out);
   int buf = 0, use = 0, prev_buf = 0;
   bool first = true;
   int iter = 0;
@@ -228,7 +241,7 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, const EpiCtx
         const int col = s * p.slab_cols + part * cpt;
         const uint32_t taddr = ec.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_tile + col;
         const float* bias = p.bias + n_idx * p.n_tile + col;
-        uint8_t* row = stage_buf + rowoff;
+        const uint32_t row = stage_base + buf * kOutStageBytes + rowoff;
         if constexpr (F32OUT) epi_process32(taddr, bias, row, inner, x, act, row_valid);
         else epi_process16<CPT, F16>(taddr, bias, row, inner, x, has_res, act, row_valid);
       }
