@@ -80,6 +80,7 @@ struct __align__(64) IgemmParams {
   // bb = 1.  The A tiles then live in their own ring (a_stages, a_full / a_empty); rows >= `rows` of the M tile
   // accumulate garbage that is never stored.  taps[g * halo_g] carries the group's map / W / H / first T offset.
   int halo_g, halo_step16, a_stages;
+  uint32_t a_stride;   // bytes between A stages (kAStageBytes; more when a haloed tile has more than 128 rows)
   int tap_k[kMaxTaps];   // K block (in the packed weights) of every tap in kernel order
   uint32_t dv_mul[5], dv_shr[5];   // magic numbers of the divisions by n_tiles, ncb, tw, th, tt (finish_op)
 };
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + p.a_stages * kAStageBytes;
+  uint8_t* smem_b = smem_a + p.a_stages * p.a_stride;
   uint8_t* smem_out = smem_b + p.stages * p.b_stride;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_out + p.obufs * kOutStageBytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             mbar_wait(&a_empty[as], aphase ^ 1, 7);
             if (elect_one()) {
               mbar_arrive_expect_tx(&a_full[as], p.a_bytes);
-              tma_load_5d(smem_a + as * kAStageBytes, &p.a_maps[tp.x], &a_full[as],
+              tma_load_5d(smem_a + as * p.a_stride, &p.a_maps[tp.x], &a_full[as],
                           p.a_c_base + tc.cb * p.a_cb_stride + ch * p.kc, tc.w0 + tp.y, tc.h0 + tp.z, tc.t0 + tp.w, tc.b0);
             }
             __syncwarp();
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             mbar_wait(&empty_bar[stage], phase ^ 1, 1);
             if (elect_one()) {
               mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-              tma_load_5d(smem_a + stage * kAStageBytes, &p.a_maps[tp.x], &full_bar[stage],
+              tma_load_5d(smem_a + stage * p.a_stride, &p.a_maps[tp.x], &full_bar[stage],
                             p.a_c_base + tc.cb * p.a_cb_stride + ch * p.kc, tc.w0 + tp.y, tc.h0 + tp.z, tc.t0 + tp.w, tc.b0);
               tma_load_2d(smem_b + stage * p.b_stride, &p.b_map, &full_bar[stage],
                           (p.tap_k[tap] * p.kchunks + ch) * p.kc, tc.n_idx * p.n_tile + tc.b0 * p.b_clip_rows);
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const uint32_t idesc = make_idesc_16(128, p.n_tile, p.f16);
       const uint32_t desc_hi = kmajor_desc_hi(p.sbo, p.layout_type);
       const uint32_t a_lo0 = kmajor_desc_lo(smem_u32(smem_a)), b_lo0 = kmajor_desc_lo(smem_u32(smem_b));
-      const uint32_t a_step = kAStageBytes >> 4, b_step = p.b_stride >> 4;
+      const uint32_t a_step = p.a_stride >> 4, b_step = p.b_stride >> 4;
       const int ksteps = p.kc >> 4;
       int stage = 0;
       uint32_t phase = 0;
@@ -563,13 +564,15 @@ static void plan_smem(IgemmParams& p, int* smem_bytes) {
   if (p.halo_g) {
     // own A ring (one haloed tile per (group, chunk)), B ring as deep as two tap groups
     p.a_stages = 3;
+    if (p.a_stride == 0) p.a_stride = kAStageBytes;
     int R = p.has_res ? 4 : 3;
     p.obufs = R;
-    const int left = avail - R * kOutStageBytes - p.a_stages * kAStageBytes;
+    const int left = avail - R * kOutStageBytes - p.a_stages * (int)p.a_stride;
     p.stages = std::max(2, std::min({left / (int)p.b_stride, kMaxStages, 2 * p.halo_g + 2}));
-    *smem_bytes = 1024 + 512 + R * kOutStageBytes + p.a_stages * kAStageBytes + p.stages * (int)p.b_stride;
+    *smem_bytes = 1024 + 512 + R * kOutStageBytes + p.a_stages * (int)p.a_stride + p.stages * (int)p.b_stride;
     return;
   }
+  p.a_stride = kAStageBytes;
   for (int i = 0; i < kMaxTaps; ++i) p.tap_k[i] = i;
   const int stage_bytes = kAStageBytes + (int)p.b_stride;
   const int ksteps = p.num_taps * p.kchunks;
@@ -980,6 +983,21 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
   esf_igemm_geometry(64, N, &kc, &kchunks, &n_tile, &n_pad);
   p.kc = 64, p.kchunks = 1, p.n_tile = n_tile, p.n_tiles = n_pad / n_tile, p.num_taps = num_taps;
   choose_box(1, Ho, To, B, &p.bw, &p.bh, &p.bt, &p.bb);
+  // T-halo mode (see IgemmParams::halo_g), opt-in with ESF_STEM_THALO=1: the kT taps of one kh share ONE activation
+  // tile of (bt + kT - 1) planes x 8 rows -- 7 tile loads per M tile instead of 35 for the 5x7x7 stem -- and the tile
+  // keeps all 128 MMA rows (16 output planes x 8 rows; the 160-row haloed tile gets a 20 KB stage).  Measured: bit-correct
+  // (kernel + model tests), 4x fewer L2 -> smem bytes, but 1.20 -> 1.36 ms: the stem is not bound by its 11.6 TB/s of
+  // smem fill either.  140 MMAs of 128 x 64 x 16 per tile take ~100 cycles each instead of 32 -- the serial
+  // wait / issue / commit loop of the MMA warp per 4-MMA k-block is the limit, and the halo adds a barrier to it.
+  {
+    const char* env = getenv("ESF_STEM_THALO");
+    if (env && atoi(env) != 0 && kT > 1 && kT <= 8 && Ho >= 8) {
+      p.halo_g = kT;
+      p.bw = 1, p.bh = 8, p.bt = std::min(To, 16), p.bb = 1;
+      p.a_stride = (uint32_t)((8 * (p.bt + kT - 1) * 128 + 1023) & ~1023);
+      p.halo_step16 = (8 * 128) >> 4;
+    }
+  }
   p.tw = 1, p.th = cdiv(Ho, p.bh), p.tt = cdiv(To, p.bt), p.tb = cdiv(B, p.bb);
   p.rows = p.bw * p.bh * p.bt * p.bb;
   p.ncb = cdiv(Wo, kStemWB);
@@ -992,6 +1010,7 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
   }
   p.num_tiles = (int)ntiles;
   p.a_bytes = p.rows * 128, p.b_bytes = n_tile * 128, p.b_stride = (p.b_bytes + 1023) & ~1023u;
+  if (p.halo_g) p.a_bytes = 8 * (p.bt + kT - 1) * 128;
   p.sbo = 1024, p.layout_type = 2;
   p.bias = bias_tiled, p.act = act, p.has_res = 0, p.out_f32 = 0;
   p.f16 = y->dtype == ESF_F16;
@@ -1005,9 +1024,12 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
   // one activation map per row phase of the H stride
   int phase_map[8];
   for (int i = 0; i < 8; ++i) phase_map[i] = -1;
-  int nmaps = 0, tap_i = 0;
+  int nmaps = 0;
   for (int it = 0; it < kT && rc == ESF_OK; ++it)
-    for (int ih = 0; ih < kH && rc == ESF_OK; ++ih, ++tap_i) {
+    for (int ih = 0; ih < kH && rc == ESF_OK; ++ih) {
+      // kernel order of the taps: (kt, kh) as packed in the weights, or kh-major groups of kT taps in T-halo mode
+      const int tap_i = p.halo_g ? ih * kT + it : it * kH + ih;
+      p.tap_k[tap_i] = it * kH + ih;
       const int oh = ih - pH;
       const int qh = floordiv(oh, sH);
       const int ph = oh - qh * sH;
@@ -1024,7 +1046,7 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
         char* base = static_cast<char*>(const_cast<void*>(xp)) + 2LL * ph * pitch;
         rc = encode_act_map(&p.a_maps[nmaps], dt16, 2, base, pitch, 1, Hp, T, B,
                             (int64_t)sH * pitch, (int64_t)sH * pitch, (int64_t)H * pitch, (int64_t)T * H * pitch, 64,
-                            1, p.bh, p.bt, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, "stem activation");
+                            1, p.bh, p.halo_g ? p.bt + kT - 1 : p.bt, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, "stem activation");
         phase_map[ph] = nmaps++;
       }
       p.taps[tap_i] = make_int4(phase_map[ph], 0, qh, it - pT);

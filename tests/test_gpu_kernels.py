@@ -330,10 +330,15 @@ def test_stem_conv(esf_lib, kt, cout):
     assert err <= 6e-3 * ref.abs().max().item()   # FP32 math, BF16 output rounding (2^-8 relative worst case)
 
 
+@pytest.mark.parametrize("thalo", [0, 1])
 @pytest.mark.parametrize("precision", ["bf16", "fp16"])
 @pytest.mark.parametrize("kt,cout,k,size", [(1, 64, 7, 64), (5, 8, 7, 64), (3, 24, 3, 48), (1, 64, 7, 224)])
-def test_stem_banded_gemm(esf_lib, kt, cout, k, size, precision):
-    """Tensor-core stem (banded implicit GEMM) vs F.conv3d on the 16-bit-rounded clip and weights."""
+def test_stem_banded_gemm(esf_lib, kt, cout, k, size, precision, thalo, monkeypatch):
+    """Tensor-core stem (banded implicit GEMM) vs F.conv3d on the 16-bit-rounded clip and weights; also in the opt-in
+    T-halo mode (one haloed activation tile per kh, the kt taps as descriptor offsets)."""
+    if thalo and kt == 1:
+        pytest.skip("no temporal taps")
+    monkeypatch.setenv("ESF_STEM_THALO", str(thalo))
     adt = rt.TORCH_DTYPE[precision]
     g = torch.Generator().manual_seed(kt + cout)
     B, T = (2, 8) if size < 200 else (1, 2)
