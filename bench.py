@@ -197,8 +197,9 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner on stdout, next to the JSON line
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION / WARN / INFO) to stdout, next to the ONE JSON line of the
+        # contract: send its log to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
 
