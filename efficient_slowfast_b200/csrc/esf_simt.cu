@@ -910,6 +910,59 @@ static bool vec8_ok(const View& v) {
   return (reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && v.sB % 8 == 0 && v.sT % 8 == 0 && v.sH % 8 == 0 && v.sW % 8 == 0;
 }
 
+// ------------------------------------------------------------------------------------------- global mean
+// feat[b][c] = mean over (T, H, W) of x[b, :, :, :, c] for LARGE activations (the squeeze of SqueezeExcite,
+// ghostnet_helper.py:46-52, runs on up to 32 x 56 x 56 positions; head_pool_kernel's one block per clip and 64
+// channels ran at 47 GB/s there).  Two deterministic passes: kGmBlocks partial sums per clip, then their sum.
+constexpr int kGmBlocks = 64;
+template <int VEC>
+__global__ void __launch_bounds__(256) global_sum_partial_kernel(const View x, int npos, float* __restrict__ partial) {
+  __shared__ float red[256][VEC + 1];
+  const int C = x.C, cgs = C / VEC;
+  const int lanes = 256 / cgs;                 // host guarantees cgs <= 256
+  const int b = blockIdx.y;
+  const int chunk = (npos + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * chunk, p1 = min(npos, p0 + chunk);
+  const int cg = threadIdx.x % cgs, lane = threadIdx.x / cgs;
+  float s[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) s[j] = 0.f;
+  if (lane < lanes) {
+    const int HW = x.H * x.W;
+    for (int pos = p0 + lane; pos < p1; pos += lanes) {
+      const int t = pos / HW, r = pos - t * HW, h = r / x.W, w = r - h * x.W;
+      const __nv_bfloat16* px = reinterpret_cast<const __nv_bfloat16*>(x.ptr) + voff(x, b, t, h, w) + cg * VEC;
+      if constexpr (VEC == 8) {
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(px)), x.f16, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += v[j];
+      } else {
+        s[0] += h162f(px[0], x.f16);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) red[threadIdx.x][j] = s[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / VEC, j = c - g * VEC;
+    float t = 0.f;
+    for (int i = 0; i < lanes; ++i) t += red[i * cgs + g][j];
+    partial[((long long)b * gridDim.x + blockIdx.x) * C + c] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) global_mean_finish_kernel(const float* __restrict__ partial, int nblk, int C, int npos,
+                                                                 float* __restrict__ feat, int feat_stride, int feat_off) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+  for (int i = 0; i < nblk; ++i) t += partial[((long long)b * nblk + i) * C + c];
+  feat[(long long)b * feat_stride + feat_off + c] = t / (float)npos;
+}
+
 // ------------------------------------------------------------------------------------------- head
 // 16-byte variant of head_pool_kernel: block = (clip, up to 256 channels), thread = 8 channels x a strided set of positions
 __global__ void __launch_bounds__(256) head_pool_vec_kernel(const View x, float* feat, int feat_stride, int feat_off) {
@@ -1296,6 +1349,29 @@ extern "C" int esf_group_mean(const float* in, int32_t B, int32_t P, int32_t K, 
   ESF_CHECK_ARG(in && out && B > 0 && P > 0 && K > 0 && (long long)B * K < (1LL << 31), "esf_group_mean: null/bad argument");
   group_mean_kernel<<<grid_for((long long)B * K, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, B, P, K, out);
   return check_launch("group_mean_kernel");
+}
+
+extern "C" int64_t esf_global_mean_scratch_floats(int32_t B, int32_t C) { return (int64_t)B * kGmBlocks * C; }
+
+extern "C" int esf_global_mean(const esf_view* x, float* scratch, float* feat, int32_t feat_stride, int32_t feat_off,
+                               void* stream) {
+  ESF_CHECK_ARG(view_ok(x) && scratch && feat && feat_stride >= feat_off + x->C, "esf_global_mean: null/bad argument");
+  const long long npos = (long long)x->T * x->H * x->W;
+  ESF_CHECK_ARG(npos < (1LL << 31), "esf_global_mean: too many positions");
+  const View v = to_view(x);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nblk = (int)std::max(1LL, std::min<long long>(kGmBlocks, npos / 64));
+  dim3 grid(nblk, x->B);
+  if (x->C % 8 == 0 && x->C / 8 <= 256 && vec8_ok(v)) global_sum_partial_kernel<8><<<grid, 256, 0, s>>>(v, (int)npos, scratch);
+  else {
+    ESF_CHECK_ARG(x->C <= 256, "esf_global_mean: %d channels need 16-byte addressable rows", x->C);
+    global_sum_partial_kernel<1><<<grid, 256, 0, s>>>(v, (int)npos, scratch);
+  }
+  int rc = check_launch("global_sum_partial_kernel");
+  if (rc != ESF_OK) return rc;
+  global_mean_finish_kernel<<<dim3(cdiv(x->C, 256), x->B), 256, 0, s>>>(scratch, nblk, x->C, (int)npos, feat, feat_stride,
+                                                                       feat_off);
+  return check_launch("global_mean_finish_kernel");
 }
 
 extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {

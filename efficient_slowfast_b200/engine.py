@@ -517,14 +517,32 @@ class Plan:
         xv, yv, nv = rt.view(x), rt.view(y), rt.null_view()
         self.keep += [feat, hid, gate, xv, yv, nv]
         L = rt.lib()
-        self._add(lambda s: rt.check(L.esf_head_pool(ctypes.byref(xv), ctypes.byref(nv), feat.data_ptr(), s),
-                                     "esf_head_pool"), "se_pool", "", nbytes=self._nbytes(x))
+        self.global_mean(x, feat, C, 0, "se_pool")
         self._add(lambda s: rt.check(L.esf_head_fc(feat.data_ptr(), B, C, C, w1.data_ptr(), b1.data_ptr(), R, rt.HEAD_RELU,
                                                    hid.data_ptr(), R, s), "esf_head_fc"), "se_fc", "")
         self._add(lambda s: rt.check(L.esf_head_fc(hid.data_ptr(), B, R, R, w2.data_ptr(), b2.data_ptr(), C,
                                                    rt.HEAD_HARD_SIGMOID, gate.data_ptr(), C, s), "esf_head_fc"), "se_fc", "")
         self._add(lambda s: rt.check(L.esf_channel_scale(ctypes.byref(xv), gate.data_ptr(), ctypes.byref(yv), s),
                                      "esf_channel_scale"), "se_scale", "", nbytes=2 * self._nbytes(x))
+
+    def global_mean(self, x, feat, feat_stride, feat_off, kind="head_pool"):
+        """feat[:, feat_off : feat_off + C] = mean over (T, H, W) of x: the two-pass esf_global_mean for large maps, the
+        single-block head kernel for the small ones."""
+        L = rt.lib()
+        xv = rt.view(x)
+        self.keep.append(xv)
+        B, T, H, W, C = x.shape
+        if T * H * W >= 1024 and (C % 8 == 0 or C <= 256):
+            scratch = self.scratch((int(L.esf_global_mean_scratch_floats(B, C)),), torch.float32)
+            self._add(lambda s: rt.check(L.esf_global_mean(ctypes.byref(xv), scratch.data_ptr(), feat.data_ptr(),
+                                                           feat_stride, feat_off, s), "esf_global_mean"),
+                      kind, "two-pass", nbytes=self._nbytes(x), launches=2)
+        else:
+            assert feat_off == 0
+            nv = rt.null_view()
+            self.keep.append(nv)
+            self._add(lambda s: rt.check(L.esf_head_pool(ctypes.byref(xv), ctypes.byref(nv), feat.data_ptr(), s),
+                                         "esf_head_pool"), kind, "", nbytes=self._nbytes(x))
 
     def eca_fuse(self, x_fast, y_slice, alpha, eca_weight, bn):
         """MaxPool(alpha,1,1) -> ECA -> BN -> ReLU -> concat slice (custom_video_model_builder.py:131-135)."""

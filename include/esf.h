@@ -205,6 +205,11 @@ int esf_transpose16(const void* in, int32_t B, int32_t rows, int32_t cols, int64
 int esf_head_pool(const esf_view* x0, const esf_view* x1, float* feat, void* stream);
 int esf_head_fc(const float* feat, int32_t B, int32_t Cin, int32_t feat_stride, const float* w, const float* bias,
                 int32_t num_classes, int32_t act, float* out, int32_t out_stride, void* stream);
+/* esf_global_mean: the same global average as esf_head_pool for LARGE activations (the squeeze of SqueezeExcite,
+ * ghostnet_helper.py:46-52, sees up to 32 x 56 x 56 positions): 64 deterministic partial sums per clip in `scratch`
+ * (esf_global_mean_scratch_floats(B, C) floats), then their sum.  feat[b][feat_off + c] = mean_{t,h,w} x[b,t,h,w,c]. */
+int64_t esf_global_mean_scratch_floats(int32_t B, int32_t C);
+int esf_global_mean(const esf_view* x, float* scratch, float* feat, int32_t feat_stride, int32_t feat_off, void* stream);
 /* Fully-convolutional inference (head_helper.py:218-220: `x = self.act(x); x = x.mean([1, 2, 3])`) when the head's
  * AvgPool3d kernel is smaller than the feature map (e.g. TEST_CROP_SIZE 256 on a 224 model): esf_pool3d (avg, stride
  * 1) -> esf_head_pool / esf_head_fc with one row per (clip, position) -> esf_group_mean over the P positions:

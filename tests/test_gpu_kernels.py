@@ -658,3 +658,28 @@ def test_nonlocal_block(esf_lib, inst, pool, group):
     err = ((got - ref).abs().max() / ref.abs().max()).item()
     print("nonlocal %s pool %s group %d: rel err %.3e" % (inst, pool, group, err))
     assert err < 1e-2
+
+
+@pytest.mark.parametrize("C,shape", [(72, (2, 8, 28, 28)), (960, (3, 4, 7, 7)), (12, (2, 16, 14, 14)), (240, (1, 32, 56, 56))])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_global_mean(esf_lib, C, shape, dt):
+    """esf_global_mean (two-pass, deterministic) vs torch.mean on the 16-bit-rounded activation, inside a wider row."""
+    B, T, H, W = shape
+    g = torch.Generator().manual_seed(C)
+    Cp = (C + 7) // 8 * 8 if C >= 8 else C
+    xbuf = _rand_act(g, B, T, H, W, Cp, dtype=dt).to(DEV)
+    x = xbuf[..., :C]
+    feat = torch.full((B, C + 5), 7.0, device=DEV)
+    scratch = torch.empty(int(esf_lib.esf_global_mean_scratch_floats(B, C)), device=DEV)
+    xv = rt.view(x)
+    for _ in range(2):
+        rt.check(esf_lib.esf_global_mean(ctypes.byref(xv), scratch.data_ptr(), feat.data_ptr(), C + 5, 3,
+                                         rt.current_stream_ptr()))
+    torch.cuda.synchronize()
+    ref = x.float().mean(dim=(1, 2, 3))
+    assert torch.allclose(feat[:, 3:3 + C], ref, rtol=1e-4, atol=1e-5)
+    assert (feat[:, :3] == 7.0).all() and (feat[:, 3 + C:] == 7.0).all()
+    first = feat.clone()
+    rt.check(esf_lib.esf_global_mean(ctypes.byref(xv), scratch.data_ptr(), feat.data_ptr(), C + 5, 3, rt.current_stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(first, feat)            # deterministic
