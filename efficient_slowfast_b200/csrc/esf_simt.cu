@@ -299,6 +299,7 @@ struct DirectParams {
   const float* w;  // [Cout][kT][kH][kW][Cin/groups]
   const float* bias;
   int kT, kH, kW, sT, sH, sW, pT, pH, pW, dT, dH, dW, groups, act, has_res, out_f32;
+  int c_real;   // depthwise over padded rows (esf_dwconv_padded): channels >= c_real have zero weights / bias
 };
 
 __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectParams p) {
@@ -492,11 +493,12 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const DirectParams p, in
   const int taps = p.kT * p.kH * KW;
   float* bias_s = dw_sm;
   __nv_bfloat16* w_s = reinterpret_cast<__nv_bfloat16*>(dw_sm + kDwCgPerBlock * VEC);
+  const int c_real = p.c_real ? p.c_real : C;
   for (int i = threadIdx.x; i < taps * chb; i += blockDim.x) {
     const int tap = i / chb, c = i - tap * chb;
-    w_s[i] = f2h16(__ldg(p.w + (long long)(cg0 * VEC + c) * taps + tap), F16);
+    w_s[i] = f2h16(cg0 * VEC + c < c_real ? __ldg(p.w + (long long)(cg0 * VEC + c) * taps + tap) : 0.f, F16);
   }
-  for (int i = threadIdx.x; i < chb; i += blockDim.x) bias_s[i] = __ldg(p.bias + cg0 * VEC + i);
+  for (int i = threadIdx.x; i < chb; i += blockDim.x) bias_s[i] = cg0 * VEC + i < c_real ? __ldg(p.bias + cg0 * VEC + i) : 0.f;
   __syncthreads();
   const int lanes = blockDim.x / cb;
   const int cgl = threadIdx.x % cb, lane = threadIdx.x / cb;
@@ -1374,6 +1376,37 @@ extern "C" int esf_global_mean(const esf_view* x, float* scratch, float* feat, i
   return check_launch("global_mean_finish_kernel");
 }
 
+// Depthwise conv over rows whose channel count was padded to a multiple of 8 by the allocator (engine.Plan.act): the
+// kernel runs on c_pad channels with 16-byte vectors (C = 18 -> 24, 162 -> 168 ...), the padding channels get zero
+// weights; what lands in the padding of y is never read as data.  The caller vouches that channels [C, c_pad) of x, y
+// and res are padding owned by the same allocation.
+extern "C" int esf_dwconv_padded(const esf_conv_desc* d, int32_t c_pad, void* stream) {
+  ESF_CHECK_ARG(d && view_ok(&d->x) && view_ok(&d->y) && d->w && d->bias, "esf_dwconv_padded: null/bad argument");
+  const int C = d->x.C;
+  ESF_CHECK_ARG(d->groups == C && d->y.C == C && c_pad % 8 == 0 && c_pad >= C && c_pad < C + 8 && d->x.sW >= c_pad &&
+                    d->y.sW >= c_pad && (!d->res.ptr || (d->res.C == C && d->res.sW >= c_pad)),
+                "esf_dwconv_padded: not a depthwise conv over rows padded to %d channels", c_pad);
+  ESF_CHECK_ARG((d->kW == 3 || d->kW == 5) && d->dT == 1 && d->dH == 1 && d->dW == 1 && (d->sW == 1 || d->sW == 2) &&
+                    is16(d->x.dtype) && d->y.dtype == d->x.dtype && d->out_dtype == d->x.dtype &&
+                    (!d->res.ptr || d->res.dtype == d->x.dtype),
+                "esf_dwconv_padded: unsupported geometry / dtype");
+  DirectParams p;
+  p.x = to_view(&d->x), p.y = to_view(&d->y);
+  p.has_res = d->res.ptr != nullptr;
+  p.res = p.has_res ? to_view(&d->res) : p.y;
+  p.x.C = p.y.C = p.res.C = c_pad;
+  p.c_real = C;
+  p.w = static_cast<const float*>(d->w), p.bias = d->bias;
+  p.kT = d->kT, p.kH = d->kH, p.kW = d->kW, p.sT = d->sT, p.sH = d->sH, p.sW = d->sW;
+  p.pT = d->pT, p.pH = d->pH, p.pW = d->pW, p.dT = d->dT, p.dH = d->dH, p.dW = d->dW;
+  p.groups = c_pad, p.act = d->act, p.out_f32 = 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ESF_CHECK_ARG(vec_ok(p.x, 8) && vec_ok(p.y, 8), "esf_dwconv_padded: rows are not 16-byte addressable");
+  const bool done = d->kW == 3 ? launch_dwconv<8, 3>(p, s) : launch_dwconv<8, 5>(p, s);
+  if (!done) return set_error(ESF_ERR_UNSUPPORTED, "esf_dwconv_padded: filter too large for shared memory");
+  return check_launch("dwconv_kernel");
+}
+
 extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {
   ESF_CHECK_ARG(d && view_ok(&d->x) && view_ok(&d->y) && d->w && d->bias, "esf_conv_direct: null/bad argument");
   ESF_CHECK_ARG(d->groups >= 1 && d->x.C % d->groups == 0 && d->y.C % d->groups == 0,
@@ -1391,6 +1424,7 @@ extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {
   p.kT = d->kT, p.kH = d->kH, p.kW = d->kW, p.sT = d->sT, p.sH = d->sH, p.sW = d->sW;
   p.pT = d->pT, p.pH = d->pH, p.pW = d->pW, p.dT = d->dT, p.dH = d->dH, p.dW = d->dW;
   p.groups = d->groups, p.act = d->act, p.out_f32 = d->out_dtype == ESF_F32;
+  p.c_real = 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (p.groups == p.x.C && p.y.C == p.x.C && (d->kW == 3 || d->kW == 5) && d->dT == 1 && d->dH == 1 && d->dW == 1 &&
       (d->sW == 1 || d->sW == 2) && !p.out_f32 && is16(d->x.dtype) && d->y.dtype == d->x.dtype &&

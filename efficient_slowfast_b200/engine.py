@@ -141,6 +141,7 @@ class Plan:
         self.eager = []       # per op: launched outside the CUDA graph (reads a caller-provided input tensor)
         self.input_override = {}   # plan-owned input data_ptr -> data_ptr of the caller's tensor for this run
         self.stem_routes = {}      # plan-owned input data_ptr -> (packed stem rows, pitch, lpad) of a banded stem
+        self.padded = {}           # data_ptr of a channel-padded activation -> (logical C, padded C)
         self.handles = []     # esf_op* to destroy
         self.graph = None
         self.out = None
@@ -160,6 +161,7 @@ class Plan:
         t = torch.empty((B, T, H, W, Cp), dtype=dtype, device=self.device)
         self.keep.append(t)
         if Cp != C:
+            self.padded[t.data_ptr()] = (C, Cp)     # channels [C, Cp) of every row are padding owned by this tensor
             t = t[..., :C]
         if name:
             self.buffers[name] = t
@@ -424,6 +426,16 @@ class Plan:
         L = rt.lib()
         m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
         depthwise = groups == x.shape[4] == y.shape[4] and kw in (3, 5)
+        C = x.shape[4]
+        pad_of = lambda t: self.padded.get(t.data_ptr()) if t is not None else (C, (C + 7) // 8 * 8)
+        if (depthwise and C % 8 != 0 and C >= 8 and tuple(dilation) == (1, 1, 1) and stride[2] in (1, 2)
+                and all(pad_of(t) == (C, (C + 7) // 8 * 8) for t in (x, y, res)) and y.dtype == x.dtype == self.adt):
+            # rows padded to a multiple of 8 channels by act(): 16-byte vectors over the padded width (zero weights)
+            cp = (C + 7) // 8 * 8
+            self._add(lambda s, d=d: rt.check(L.esf_dwconv_padded(ctypes.byref(d), cp, s), "esf_dwconv_padded"),
+                      "dwconv", "%dx%dx%d g%d %d->%d pad%d" % (kt, kh, kw, groups, C, C, cp),
+                      flops=2.0 * m * C * kt * kh * kw, nbytes=self._nbytes(x, y, res) + wd.numel() * 4)
+            return
         self._add(lambda s, d=d: rt.check(L.esf_conv_direct(ctypes.byref(d), s), "esf_conv_direct"),
                   "dwconv" if depthwise else "conv_direct",
                   "%dx%dx%d g%d %d->%d" % (kt, kh, kw, groups, x.shape[4], y.shape[4]),

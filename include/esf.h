@@ -91,6 +91,11 @@ void esf_op_destroy(esf_op* op);
  * shufflenet_helper.py:50-62, mobilenetv2_helper.py:40-55, ghostnet_helper.py:88-143.
  * Weights: FP32 [Cout][kT][kH][kW][Cin/groups]. */
 int esf_conv_direct(const esf_conv_desc* d, void* stream);
+/* esf_dwconv_padded: the depthwise case of esf_conv_direct for activations whose rows were padded to c_pad (a multiple
+ * of 8) channels by the allocator: runs with 16-byte vectors over c_pad channels (zero weights on the padding), e.g.
+ * the C = 18 / 162 / 12 / 36 depthwise layers of the fast pathway of SlowFastMoibleNetV2 (mobilenetv2_helper.py:40-55).
+ * The caller vouches that channels [C, c_pad) of x, y and res are padding of the same allocation. */
+int esf_dwconv_padded(const esf_conv_desc* d, int32_t c_pad, void* stream);
 
 /* ---- stem: Conv3d on the FP32 NCDHW clip + folded BN + ReLU -> BF16 channels-last ----------------------
  * replaces ResNetBasicStem.conv/bn/relu (stem_helper.py:173-177) and the efficient stems
