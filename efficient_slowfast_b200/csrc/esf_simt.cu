@@ -389,7 +389,10 @@ __device__ __forceinline__ void store_vec(__nv_bfloat16* ptr, int f16, const flo
 // first fast-pathway layers of the efficient backbones, which the tensor-core GEMM cannot address).  One thread = one
 // position x one group of up to 8 output channels; the weights sit in shared memory as [c_in][c_out]; inputs are read
 // with the widest aligned vector, outputs written as one 16-byte store when the group is full and aligned.
-template <int VIN>
+// FLAT: x, y and res are dense over their positions (offset = position * sW), so an item needs no (b, t, h, w)
+// decomposition at all; I: 32-bit item index when the item count allows.  With run-time 64-bit divisions the index
+// arithmetic of an item (four div/mod pairs) outweighed its cin x 8 FMAs several times over.
+template <int VIN, bool FLAT, typename I>
 __global__ void __launch_bounds__(256) pw_small_kernel(const DirectParams p, int vec_out) {
   extern __shared__ float pw_sm[];  // w[cin][coutp], bias[coutp]
   const int cin = p.x.C, cout = p.y.C, cogs = (cout + 7) / 8, coutp = cogs * 8;
@@ -400,21 +403,28 @@ __global__ void __launch_bounds__(256) pw_small_kernel(const DirectParams p, int
   float* bias_s = pw_sm + cin * coutp;
   for (int i = threadIdx.x; i < coutp; i += blockDim.x) bias_s[i] = i < cout ? __ldg(p.bias + i) : 0.f;
   __syncthreads();
-  const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W * cogs;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int cog = idx % cogs;
-    long long pos = idx / cogs;
-    const int w = pos % p.y.W;
-    pos /= p.y.W;
-    const int h = pos % p.y.H;
-    pos /= p.y.H;
-    const int t = pos % p.y.T;
-    const int b = pos / p.y.T;
+  const I total = (I)p.y.B * p.y.T * p.y.H * p.y.W * cogs;
+  for (I idx = blockIdx.x * (I)blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
+    I pos = cogs == 1 ? idx : idx / cogs;
+    const int cog = cogs == 1 ? 0 : (int)(idx - pos * cogs);
+    long long xo, yo0, ro0 = 0;
+    if constexpr (FLAT) {
+      xo = (long long)pos * p.x.sW, yo0 = (long long)pos * p.y.sW;
+      if (p.has_res) ro0 = (long long)pos * p.res.sW;
+    } else {
+      const int w = (int)(pos % p.y.W);
+      pos /= p.y.W;
+      const int h = (int)(pos % p.y.H);
+      pos /= p.y.H;
+      const int t = (int)(pos % p.y.T);
+      const int b = (int)(pos / p.y.T);
+      xo = voff(p.x, b, t, h, w), yo0 = voff(p.y, b, t, h, w);
+      if (p.has_res) ro0 = voff(p.res, b, t, h, w);
+    }
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = bias_s[cog * 8 + j];
-    const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + voff(p.x, b, t, h, w);
+    const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + xo;
     for (int c0 = 0; c0 < cin; c0 += VIN) {
       float xv[VIN];
       load_vec<VIN>(xr + c0, p.x.f16, xv);
@@ -425,10 +435,10 @@ __global__ void __launch_bounds__(256) pw_small_kernel(const DirectParams p, int
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[e], wr[j], acc[j]);
       }
     }
-    const long long yo = voff(p.y, b, t, h, w) + cog * 8;
+    const long long yo = yo0 + cog * 8;
     const int valid = min(8, cout - cog * 8);
     if (p.has_res) {
-      const long long ro = voff(p.res, b, t, h, w) + cog * 8;
+      const long long ro = ro0 + cog * 8;
       for (int j = 0; j < valid; ++j) acc[j] += ldbf(p.res, ro + j);
     }
 #pragma unroll
@@ -908,6 +918,9 @@ __global__ void __launch_bounds__(kEcaThreads) eca_apply_vec_kernel(const EcaPar
   }
 }
 
+static bool dense_pos(const View& v) {
+  return v.sH == (long long)v.W * v.sW && v.sT == (long long)v.H * v.sH && v.sB == (long long)v.T * v.sT;
+}
 static bool vec8_ok(const View& v) {
   return (reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && v.sB % 8 == 0 && v.sT % 8 == 0 && v.sH % 8 == 0 && v.sW % 8 == 0;
 }
@@ -1164,31 +1177,44 @@ __global__ void __launch_bounds__(256) shuffle_concat_kernel(const View a, const
 // a warp covers it completely) and one VEC*2-byte store.
 template <int VEC>
 __global__ void __launch_bounds__(256) shuffle_concat_vec_kernel(const View a, const View b, int cb, int groups,
-                                                                 const View y) {
+                                                                 const View y, int flat32) {
   const int C = y.C, cv = C / VEC;
   const int cpg = C / groups;
   const long long total = (long long)y.B * y.T * y.H * y.W * cv;
   const unsigned short* ap = reinterpret_cast<const unsigned short*>(a.ptr);
   const unsigned short* bp = reinterpret_cast<const unsigned short*>(b.ptr);
+  // dense views (offset = position * sW) and a 32-bit item count: no (b, t, h, w) decomposition, no 64-bit divisions
+  const bool flat = flat32;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int o0 = (idx % cv) * VEC;
-    long long pos = idx / cv;
-    const int w = pos % y.W;
-    pos /= y.W;
-    const int h = pos % y.H;
-    pos /= y.H;
-    const int t = pos % y.T;
-    const int bb = pos / y.T;
-    const long long ao = voff(a, bb, t, h, w), bo = cb ? voff(b, bb, t, h, w) : 0;
+    int o0;
+    long long ao, bo = 0, yo;
+    if (flat) {
+      const unsigned i32 = (unsigned)idx, pos = i32 / (unsigned)cv;
+      o0 = (int)(i32 - pos * cv) * VEC;
+      ao = (long long)pos * a.sW, yo = (long long)pos * y.sW;
+      if (cb) bo = (long long)pos * b.sW;
+    } else {
+      o0 = (idx % cv) * VEC;
+      long long pos = idx / cv;
+      const int w = pos % y.W;
+      pos /= y.W;
+      const int h = pos % y.H;
+      pos /= y.H;
+      const int t = pos % y.T;
+      const int bb = pos / y.T;
+      ao = voff(a, bb, t, h, w), yo = voff(y, bb, t, h, w);
+      if (cb) bo = voff(b, bb, t, h, w);
+    }
     unsigned short v[VEC];
+    int q = o0 / groups, r = o0 - q * groups;     // o = q * groups + r  ->  source channel r * cpg + q of cat(a, b)
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      const int o = o0 + e;
-      const int c = (o % groups) * cpg + o / groups;  // source channel in cat(a, b)
+      const int c = r * cpg + q;
       v[e] = c < a.C ? __ldg(ap + ao + c) : __ldg(bp + bo + (c - a.C));
+      if (++r == groups) r = 0, ++q;
     }
-    unsigned short* yp = reinterpret_cast<unsigned short*>(y.ptr) + voff(y, bb, t, h, w) + o0;
+    unsigned short* yp = reinterpret_cast<unsigned short*>(y.ptr) + yo + o0;
     if constexpr (VEC == 8) {
       *reinterpret_cast<uint4*>(yp) = make_uint4(v[0] | ((uint32_t)v[1] << 16), v[2] | ((uint32_t)v[3] << 16),
                                                   v[4] | ((uint32_t)v[5] << 16), v[6] | ((uint32_t)v[7] << 16));
@@ -1218,6 +1244,32 @@ __global__ void __launch_bounds__(256) eltwise_add_kernel(const View a, const Vi
   }
 }
 // y = x * scale[b][c]  (squeeze-excite gate, ghostnet_helper.py:46-52)
+// Fast path of eltwise_add / channel_scale: 8 channels per thread (16-byte accesses), views dense over their positions
+// (offset = position * sW), 32-bit index arithmetic.  OP 0: y = act(a + b); OP 1: y = a * scale[batch][c].  The scalar
+// kernels around it did five 64-bit div/mod pairs per ELEMENT (~600 GB/s).
+template <int OP>
+__global__ void __launch_bounds__(256) eltwise_vec8_kernel(const View a, const View b, const float* __restrict__ scale,
+                                                           const View y, int act, unsigned npos_clip) {
+  const unsigned cv = y.C >> 3;
+  const unsigned total = (unsigned)y.B * npos_clip * cv;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned pos = idx / cv, c0 = (idx - pos * cv) << 3;
+    float va[8], vb[8];
+    load_vec<8>(reinterpret_cast<const __nv_bfloat16*>(a.ptr) + (long long)pos * a.sW + c0, a.f16, va);
+    if constexpr (OP == 0) {
+      load_vec<8>(reinterpret_cast<const __nv_bfloat16*>(b.ptr) + (long long)pos * b.sW + c0, b.f16, vb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) va[j] = apply_act(va[j] + vb[j], act);
+    } else {
+      const float* sc = scale + (long long)(pos / npos_clip) * y.C + c0;
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc)), s1 = __ldg(reinterpret_cast<const float4*>(sc) + 1);
+      va[0] *= s0.x, va[1] *= s0.y, va[2] *= s0.z, va[3] *= s0.w;
+      va[4] *= s1.x, va[5] *= s1.y, va[6] *= s1.z, va[7] *= s1.w;
+    }
+    store_vec<8>(reinterpret_cast<__nv_bfloat16*>(y.ptr) + (long long)pos * y.sW + c0, y.f16, va);
+  }
+}
+
 __global__ void __launch_bounds__(256) channel_scale_kernel(const View x, const float* __restrict__ scale, const View y) {
   const int C = y.C;
   const long long total = (long long)y.B * y.T * y.H * y.W * C;
@@ -1434,17 +1486,28 @@ extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {
   }
   if (p.groups == 1 && d->kT == 1 && d->kH == 1 && d->kW == 1 && d->sT == 1 && d->sH == 1 && d->sW == 1 && d->pT == 0 &&
       d->pH == 0 && d->pW == 0 && !p.out_f32 && is16(d->x.dtype) && d->y.dtype == d->x.dtype &&
-      (!p.has_res || d->res.dtype == d->x.dtype) && (p.x.C < 8 || p.y.C < 8 || p.x.C * p.y.C <= 1024)) {
+      (!p.has_res || d->res.dtype == d->x.dtype) && (p.x.C < 8 || p.y.C < 8 || p.x.C * p.y.C <= 4096)) {
     const int cin = p.x.C, coutp = (p.y.C + 7) / 8 * 8;
     const size_t smem = (size_t)(cin + 1) * coutp * sizeof(float);
     if (smem <= 48 * 1024) {
       const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W * (coutp / 8);
       const int vec_out = vec_ok(p.y, 8);
       const unsigned grid = grid_for(total, 256);
-      if (cin % 8 == 0 && vec_ok(p.x, 8)) pw_small_kernel<8><<<grid, 256, smem, s>>>(p, vec_out);
-      else if (cin % 4 == 0 && vec_ok(p.x, 4)) pw_small_kernel<4><<<grid, 256, smem, s>>>(p, vec_out);
-      else if (cin % 2 == 0 && vec_ok(p.x, 2)) pw_small_kernel<2><<<grid, 256, smem, s>>>(p, vec_out);
-      else pw_small_kernel<1><<<grid, 256, smem, s>>>(p, vec_out);
+      auto dense = [](const View& v) {
+        return v.sH == (long long)v.W * v.sW && v.sT == (long long)v.H * v.sH && v.sB == (long long)v.T * v.sT;
+      };
+      const bool flat = dense(p.x) && dense(p.y) && (!p.has_res || dense(p.res)) &&
+                        (long long)p.y.B * p.y.T * p.y.H * p.y.W < (1LL << 31);
+      const bool i32 = total < (1LL << 32) - (148LL * 32 * 256);
+#define ESF_PW(V)                                                                                         \
+  if (flat && i32) pw_small_kernel<V, true, unsigned><<<grid, 256, smem, s>>>(p, vec_out);                \
+  else if (i32) pw_small_kernel<V, false, unsigned><<<grid, 256, smem, s>>>(p, vec_out);                  \
+  else pw_small_kernel<V, false, long long><<<grid, 256, smem, s>>>(p, vec_out);
+      if (cin % 8 == 0 && vec_ok(p.x, 8)) { ESF_PW(8) }
+      else if (cin % 4 == 0 && vec_ok(p.x, 4)) { ESF_PW(4) }
+      else if (cin % 2 == 0 && vec_ok(p.x, 2)) { ESF_PW(2) }
+      else { ESF_PW(1) }
+#undef ESF_PW
       return check_launch("pw_small_kernel");
     }
   }
@@ -1568,12 +1631,13 @@ extern "C" int esf_shuffle_concat(const esf_view* a, const esf_view* b, int32_t 
   const long long total = (long long)y->B * y->T * y->H * y->W * y->C;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const View va = to_view(a), vb = cb ? to_view(b) : to_view(a), vy = to_view(y);
+  const int flat32 = dense_pos(va) && dense_pos(vb) && dense_pos(vy) && total / 2 < (1LL << 31);
   if (y->C % 8 == 0 && vec_ok(vy, 8))
-    shuffle_concat_vec_kernel<8><<<grid_for(total / 8, 256), 256, 0, s>>>(va, vb, cb, groups, vy);
+    shuffle_concat_vec_kernel<8><<<grid_for(total / 8, 256), 256, 0, s>>>(va, vb, cb, groups, vy, flat32);
   else if (y->C % 4 == 0 && vec_ok(vy, 4))
-    shuffle_concat_vec_kernel<4><<<grid_for(total / 4, 256), 256, 0, s>>>(va, vb, cb, groups, vy);
+    shuffle_concat_vec_kernel<4><<<grid_for(total / 4, 256), 256, 0, s>>>(va, vb, cb, groups, vy, flat32);
   else if (y->C % 2 == 0 && vec_ok(vy, 2))
-    shuffle_concat_vec_kernel<2><<<grid_for(total / 2, 256), 256, 0, s>>>(va, vb, cb, groups, vy);
+    shuffle_concat_vec_kernel<2><<<grid_for(total / 2, 256), 256, 0, s>>>(va, vb, cb, groups, vy, flat32);
   else
     shuffle_concat_kernel<<<grid_for(total, 256), 256, 0, s>>>(va, vb, cb, groups, vy);
   return check_launch("shuffle_concat_kernel");
@@ -1583,14 +1647,27 @@ extern "C" int esf_eltwise_add(const esf_view* a, const esf_view* b, const esf_v
   ESF_CHECK_ARG(view_ok(a) && view_ok(b) && view_ok(y) && same_pos(a, y) && same_pos(b, y) && a->C == y->C && b->C == y->C,
                 "esf_eltwise_add: null/bad argument");
   const long long total = (long long)y->B * y->T * y->H * y->W * y->C;
-  eltwise_add_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(to_view(a), to_view(b),
-                                                                                          to_view(y), act);
+  const View va = to_view(a), vb = to_view(b), vy = to_view(y);
+  if (y->C % 8 == 0 && vec8_ok(va) && vec8_ok(vb) && vec8_ok(vy) && dense_pos(va) && dense_pos(vb) && dense_pos(vy) &&
+      total / 8 < (1LL << 32) - (148LL * 32 * 256)) {
+    eltwise_vec8_kernel<0><<<grid_for(total / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        va, vb, nullptr, vy, act, (unsigned)(y->T * y->H * y->W));
+    return check_launch("eltwise_vec8_kernel");
+  }
+  eltwise_add_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(va, vb, vy, act);
   return check_launch("eltwise_add_kernel");
 }
 
 extern "C" int esf_channel_scale(const esf_view* x, const float* scale, const esf_view* y, void* stream) {
   ESF_CHECK_ARG(view_ok(x) && view_ok(y) && scale && same_pos(x, y) && x->C == y->C, "esf_channel_scale: null/bad argument");
   const long long total = (long long)y->B * y->T * y->H * y->W * y->C;
-  channel_scale_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(to_view(x), scale, to_view(y));
+  const View vx = to_view(x), vy = to_view(y);
+  if (y->C % 8 == 0 && vec8_ok(vx) && vec8_ok(vy) && dense_pos(vx) && dense_pos(vy) &&
+      (reinterpret_cast<uintptr_t>(scale) & 15) == 0 && total / 8 < (1LL << 32) - (148LL * 32 * 256)) {
+    eltwise_vec8_kernel<1><<<grid_for(total / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        vx, vx, scale, vy, 0, (unsigned)(y->T * y->H * y->W));
+    return check_launch("eltwise_vec8_kernel");
+  }
+  channel_scale_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(vx, scale, vy);
   return check_launch("channel_scale_kernel");
 }
