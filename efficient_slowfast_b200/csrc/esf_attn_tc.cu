@@ -379,6 +379,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
 constexpr int kV2Threads = 640;
 constexpr int kV2PCol = 448;     // first TMEM column of P
 constexpr int kV2DefaultPoly = 0;
+// Experiment (-DESF_ATTN_LATE_HANDOFF=1): issue the tcgen05.st of P, fetch the next scores, and complete the hand-over
+// (wait::st, fence, arrive p_full) half way through the next tile's exponentials, so that the ~200 cycles of store
+// latency are covered by MUFU work.  Measured with the dedicated Q.K^T issuer in place: correct, but 12 % SLOWER
+// (d = 8: 3.56 -> 3.12 Texp/s, d = 32: 3.25 -> 2.88) -- the P.V MMA then finishes after the next P is ready, and the
+// sync in the middle of the MUFU stream lets the pipe drain.
+#ifndef ESF_ATTN_LATE_HANDOFF
+#define ESF_ATTN_LATE_HANDOFF 0
+#endif
 
 // exp2 of a pair on the FMA pipe (packed FFMA2 / FADD2, sm_100): Cody-Waite split x = floor(x) + f with the
 // round-down magic-number add, degree-3 minimax polynomial for 2^f on [0, 1) (max relative error 8.8e-5, below the
@@ -595,6 +603,14 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
       const float2 ms2 = make_float2(-ms, -ms), c2 = make_float2(kTcLog2e, kTcLog2e);
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
+        if (ESF_ATTN_LATE_HANDOFF && i == 16 && j > 0) {
+          // P of the PREVIOUS tile: its tcgen05.st was issued before this tile's scores were fetched; the ~200 cycles
+          // until the store is visible are covered by the first half of this tile's exponentials
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[q * 2 + h]);
+        }
         mx0 = fmaxf(fmaxf(mx0, v[i]), v[i + 1]);
         mx1 = fmaxf(fmaxf(mx1, v[i + 2]), v[i + 3]);
 #pragma unroll
@@ -664,10 +680,12 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
         }
       }
       tmem_st16_b32(p_addr, pk);
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[q * 2 + h]);
+      if (!ESF_ATTN_LATE_HANDOFF || j + 1 == nt) {   // otherwise handed over from inside the next tile's exponentials
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[q * 2 + h]);
+      }
       ESF_TICK(5)   // O rescale + P store + p_full arrive
       if (j + 1 < nt) {
         mbar_wait(&s_full[q * 2 + (buf ^ 1)], ((j + 1) >> 1) & 1, 37);
