@@ -387,6 +387,10 @@ constexpr int kV2DefaultPoly = 0;
 #ifndef ESF_ATTN_LATE_HANDOFF
 #define ESF_ATTN_LATE_HANDOFF 0
 #endif
+// Also tried and dropped: P aliased onto the S tile it was computed from (FlashAttention-4 style; consecutive P tiles then
+// live in different TMEM buffers, the S buffer is released by the P.V commits and p_free is only consulted before an O
+// rescale).  No measurable gain (d = 8: 0.812 vs 0.814 ms, d = 32: 0.863 vs 0.860 ms at 4 clips) and the interaction
+// with the replay / rescale path was not yet right (one kernel test failed at 4x logits), so it is not in the tree.
 
 // exp2 of a pair on the FMA pipe (packed FFMA2 / FADD2, sm_100): Cody-Waite split x = floor(x) + f with the
 // round-down magic-number add, degree-3 minimax polynomial for 2^f on [0, 1) (max relative error 8.8e-5, below the
