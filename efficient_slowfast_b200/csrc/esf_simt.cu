@@ -4,6 +4,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "esf_common.cuh"
 #include "esf_host.h"
@@ -612,9 +613,614 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const DirectParams p, in
   }
 }
 
+// Depthwise kT x 3 x 3 (pad 1 in H and W, stride 1 or 2) as a MARCH down the rows: one thread = VEC channels x OW output
+// columns of one (b, t_out) and walks `hs` consecutive output rows.  Every input row is loaded ONCE per kt (NCOL 16-byte
+// loads) and feeds all three kh taps out of registers -- the rolling accumulators of the 3 (stride 1) / 2 (stride 2)
+// output rows that are in flight live in registers with compile-time slot numbers (the row loop is unrolled by the
+// rotation period).  The tile kernel above re-read every input row for each (kt, kh) from L1: per output element it
+// moved 27 B through the L1 next to 27 FMAs, i.e. the 128 B/clk L1 port and the FMA pipe saturated together (ncu: FMA
+// 37 %, issue 69 %).  Here the L1 traffic is 3x lower and the FMAs are what is left.  Consecutive threads are
+// consecutive channel groups, then `wbg` column blocks, then t_out -- a block covers a few output planes of the same
+// columns, so the kt re-reads of a row by the neighbouring planes hit L1.  All weights of the layer sit in shared memory
+// in the activations' 16-bit format ([tap][C]); blocks are persistent (grid-stride), so they are staged once.
+template <int VEC, int OW, int SW, bool F16>
+struct DwMarch {
+  static constexpr int NW = (VEC + 1) / 2;
+  static constexpr int NCOL = (OW - 1) * SW + 3;
+  static constexpr int NS = SW == 1 ? 3 : 2;
+  float acc[NS][OW][2 * NW];
+  const DirectParams& p;
+  const __nv_bfloat16* xb;   // x + b * sB + channel offset
+  const __nv_bfloat16* ws;   // smem weights + channel offset, [tap][C]
+  const float* bias_s;       // smem bias + channel offset
+  int C, to, wi0, colmask;
+  __device__ __forceinline__ DwMarch(const DirectParams& p_) : p(p_) {}
+
+  template <int S>
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int o = 0; o < OW; ++o)
+#pragma unroll
+      for (int e = 0; e < 2 * NW; ++e) acc[S][o][e] = e < VEC ? bias_s[e] : 0.f;
+  }
+  template <int S>
+  __device__ __forceinline__ void fma_kh(const uint32_t (&xv)[NCOL][NW], const __nv_bfloat16* wt) {
+    if constexpr (S >= 0) {
+      uint32_t wv[3][NW];
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        if constexpr (VEC == 8) {
+          const uint4 u = *reinterpret_cast<const uint4*>(wt + kw * C);
+          wv[kw][0] = u.x, wv[kw][1] = u.y, wv[kw][2] = u.z, wv[kw][3] = u.w;
+        } else if constexpr (VEC == 4) {
+          const uint2 u = *reinterpret_cast<const uint2*>(wt + kw * C);
+          wv[kw][0] = u.x, wv[kw][1] = u.y;
+        } else if constexpr (VEC == 2) {
+          wv[kw][0] = *reinterpret_cast<const uint32_t*>(wt + kw * C);
+        } else {
+          wv[kw][0] = *reinterpret_cast<const unsigned short*>(wt + kw * C);
+        }
+      }
+#pragma unroll
+      for (int col = 0; col < NCOL; ++col) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          if ((col - kw) % SW == 0 && col - kw >= 0 && (col - kw) / SW < OW) {
+            const int o = (col - kw) / SW;
+#pragma unroll
+            for (int q = 0; q < NW; ++q) {
+              if constexpr (VEC == 1) mac1<F16>(acc[S][o][0], xv[col][0], wv[kw][0]);
+              else mac2<F16>(acc[S][o][2 * q], acc[S][o][2 * q + 1], xv[col][q], wv[kw][q]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // input row hi: tap kh accumulates into slot S<kh> when m<kh> (the output row of that tap is one of ours)
+  template <int S0, int S1, int S2>
+  __device__ __forceinline__ void step(int hi, bool m0, bool m1, bool m2) {
+    if (hi < 0 || hi >= p.x.H) return;
+    const __nv_bfloat16* xrow = xb + (long long)hi * p.x.sH;
+    for (int kt = 0; kt < p.kT; ++kt) {
+      const int ti = to * p.sT + kt - p.pT;
+      if (ti < 0 || ti >= p.x.T) continue;
+      const __nv_bfloat16* rp = xrow + (long long)ti * p.x.sT;
+      uint32_t xv[NCOL][NW];
+#pragma unroll
+      for (int col = 0; col < NCOL; ++col) {
+        if ((colmask >> col) & 1) load_raw<VEC>(rp + (long long)(wi0 + col) * p.x.sW, xv[col]);
+        else {
+#pragma unroll
+          for (int q = 0; q < NW; ++q) xv[col][q] = 0u;
+        }
+      }
+      const __nv_bfloat16* wt = ws + kt * 9 * C;
+      if (S0 >= 0 && m0) fma_kh<S0>(xv, wt);
+      if (S1 >= 0 && m1) fma_kh<S1>(xv, wt + 3 * C);
+      if (S2 >= 0 && m2) fma_kh<S2>(xv, wt + 6 * C);
+    }
+  }
+  template <int S>
+  __device__ __forceinline__ void store(long long yrow, int wb, int res_vec, const __nv_bfloat16* rb,
+                                        __nv_bfloat16* yb) {
+#pragma unroll
+    for (int o = 0; o < OW; ++o) {
+      const int wo = wb * OW + o;
+      if (wo < p.y.W) {
+        if (p.has_res) {
+          // res has the geometry of y but its own strides
+          float rv[VEC];
+          const long long ro = yrow_res + wo * p.res.sW;
+          if (res_vec) load_vec<VEC>(rb + ro, F16, rv);
+          else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) rv[e] = h162f(rb[ro + e], F16);
+          }
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[S][o][e] += rv[e];
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[S][o][e] = apply_act(acc[S][o][e], p.act);
+        store_vec<VEC>(yb + yrow + wo * p.y.sW, F16, acc[S][o]);
+      }
+    }
+    reset<S>();
+  }
+  long long yrow_res;
+};
+
+template <int VEC, int OW, int SW, bool F16>
+__global__ void __launch_bounds__(128) dwconv_march_kernel(const DirectParams p, int res_vec, int hs, int wbg) {
+  extern __shared__ float dwm_sm[];  // bias[C] (FP32), then w[kT * 9][C] in the activations' 16-bit format
+  using M = DwMarch<VEC, OW, SW, F16>;
+  const int C = p.x.C, cgs = C / VEC;
+  const int taps = p.kT * 9;
+  float* bias_all = dwm_sm;
+  __nv_bfloat16* w_all = reinterpret_cast<__nv_bfloat16*>(dwm_sm + C);
+  const int c_real = p.c_real ? p.c_real : C;
+  for (int i = threadIdx.x; i < taps * C; i += blockDim.x) {
+    const int tap = i / C, c = i - tap * C;
+    w_all[i] = f2h16(c < c_real ? __ldg(p.w + (long long)c * taps + tap) : 0.f, F16);
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) bias_all[i] = i < c_real ? __ldg(p.bias + i) : 0.f;
+  __syncthreads();
+  const int wblocks = (p.y.W + OW - 1) / OW, nwg = (wblocks + wbg - 1) / wbg, nseg = (p.y.H + hs - 1) / hs;
+  const long long items = (long long)p.y.B * nseg * nwg * p.y.T * wbg * cgs;
+  M m(p);
+  m.C = C;
+  for (long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x; item < items;
+       item += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(item % cgs);
+    long long r = item / cgs;
+    const int wl = (int)(r % wbg);
+    r /= wbg;
+    const int to = (int)(r % p.y.T);
+    r /= p.y.T;
+    const int wg = (int)(r % nwg);
+    r /= nwg;
+    const int seg = (int)(r % nseg);
+    const int b = (int)(r / nseg);
+    const int wb = wg * wbg + wl;
+    if (wb >= wblocks) continue;
+    const int ho0 = seg * hs, ho1 = min(ho0 + hs, p.y.H);
+    m.to = to;
+    m.wi0 = wb * OW * SW - 1;
+    int mask = 0;
+#pragma unroll
+    for (int col = 0; col < M::NCOL; ++col) mask |= (m.wi0 + col >= 0 && m.wi0 + col < p.x.W) ? (1 << col) : 0;
+    m.colmask = mask;
+    m.xb = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + b * p.x.sB + cg * VEC;
+    m.ws = w_all + cg * VEC;
+    m.bias_s = bias_all + cg * VEC;
+    __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + b * p.y.sB + to * p.y.sT + cg * VEC;
+    const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(p.res.ptr) + b * p.res.sB + to * p.res.sT + cg * VEC;
+    m.template reset<0>();
+    m.template reset<1>();
+    if constexpr (SW == 1) m.template reset<2>();
+#define DW_STORE(S, ho)                                                     \
+  do {                                                                      \
+    m.yrow_res = (long long)(ho) * p.res.sH;                                \
+    m.template store<S>((long long)(ho) * p.y.sH, wb, res_vec, rb, yb);     \
+  } while (0)
+    if constexpr (SW == 1) {
+      // stride 1: input row hi feeds output rows hi+1 (kh 0), hi (kh 1), hi-1 (kh 2); row hi-1 is complete after it
+      int hi = ho0 - 1;
+      while (true) {
+        m.template step<2, 1, 0>(hi, hi + 1 < ho1, hi >= ho0 && hi < ho1, hi - 1 >= ho0);
+        if (hi - 1 >= ho0) DW_STORE(0, hi - 1);
+        if (hi >= ho1) break;
+        ++hi;
+        m.template step<0, 2, 1>(hi, hi + 1 < ho1, hi >= ho0 && hi < ho1, hi - 1 >= ho0);
+        if (hi - 1 >= ho0) DW_STORE(1, hi - 1);
+        if (hi >= ho1) break;
+        ++hi;
+        m.template step<1, 0, 2>(hi, hi + 1 < ho1, hi >= ho0 && hi < ho1, hi - 1 >= ho0);
+        if (hi - 1 >= ho0) DW_STORE(2, hi - 1);
+        if (hi >= ho1) break;
+        ++hi;
+      }
+    } else {
+      // stride 2: output row ho reads input rows 2ho-1 (kh 0), 2ho (kh 1), 2ho+1 (kh 2); row 2ho+1 is also kh 0 of ho+1
+      m.template step<0, -1, -1>(2 * ho0 - 1, true, false, false);
+      int ho = ho0;
+      while (true) {
+        m.template step<-1, 0, -1>(2 * ho, false, true, false);
+        m.template step<1, -1, 0>(2 * ho + 1, ho + 1 < ho1, false, true);
+        DW_STORE(0, ho);
+        if (++ho >= ho1) break;
+        m.template step<-1, 1, -1>(2 * ho, false, true, false);
+        m.template step<0, -1, 1>(2 * ho + 1, ho + 1 < ho1, false, true);
+        DW_STORE(1, ho);
+        if (++ho >= ho1) break;
+      }
+    }
+#undef DW_STORE
+  }
+}
+
+static int dw_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+// Depthwise kT x 3 x 3 with SHARED-MEMORY HALO STAGING: the march above, fed by TMA instead of per-thread global loads.
+// A block of 128 threads owns a tile of cb channel groups (cb x 8 channels = one <= 128-byte row) x wbt column blocks of
+// 4 outputs x tt output planes and marches down `hs` output rows.  Per input row ONE 5-D TMA box
+// {cb*8 channels, ncols, 1 row, planes, 1 clip} lands in a ring of `stages` buffers (mbarrier complete_tx); the filter
+// halo in W and T is part of the box, zero padding is TMA out-of-bounds fill, so the compute loop has no bounds tests
+// and no global-load latency at all: 6 (stride 1) / 9 (stride 2) LDS.128 of activations and 9 LDS.128 of weights per
+// 288 / 144 FMAs, the three kh taps of a row served from registers.  Measured against the tile kernel and the
+// global-load march: DESIGN.md 3.5.
+struct DwTmaParams {
+  DirectParams p;
+  int cb, wbt, tt, hs, stages, ncols, planes, nct, nwt, ntt, nseg, cgs, wblocks;
+  uint32_t stage_bytes, stage_stride;   // TMA box bytes; ring pitch (128-byte aligned destinations)
+  long long tiles;
+};
+constexpr int kDwTmaMaxStages = 4;
+constexpr int kDwTmaHeader = 128;    // mbarriers
+
+template <int SW, int KT, bool F16>
+struct DwTma {
+  // thread = 2 channels (one 32-bit word per position) x OW output columns: the KT x 9 filter taps of its channel pair
+  // stay in registers for the whole kernel, a warp reads 32 consecutive words of a staged row per LDS (one wavefront)
+  static constexpr int OW = 8, NCOL = (OW - 1) * SW + 3, NS = SW == 1 ? 3 : 2;
+  float acc[NS][OW][2];
+  uint32_t w[KT * 9];
+  float bias[2];
+  const DirectParams& p;
+  uint32_t xoff, pitch, plane_bytes;
+  __device__ __forceinline__ DwTma(const DirectParams& p_) : p(p_) {}
+  template <int S>
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int o = 0; o < OW; ++o) acc[S][o][0] = bias[0], acc[S][o][1] = bias[1];
+  }
+  template <int S, int KT_, int KH>
+  __device__ __forceinline__ void fma_kh(const uint32_t (&xv)[NCOL]) {
+    if constexpr (S >= 0) {
+#pragma unroll
+      for (int col = 0; col < NCOL; ++col) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          if ((col - kw) % SW == 0 && col - kw >= 0 && (col - kw) / SW < OW) {
+            const int o = (col - kw) / SW;
+            mac2<F16>(acc[S][o][0], acc[S][o][1], xv[col], w[(KT_ * 3 + KH) * 3 + kw]);
+          }
+        }
+      }
+    }
+  }
+  template <int S0, int S1, int S2, int KT_>
+  __device__ __forceinline__ void plane(const char* xp, bool m0, bool m1, bool m2) {
+    uint32_t xv[NCOL];
+#pragma unroll
+    for (int col = 0; col < NCOL; ++col) xv[col] = *reinterpret_cast<const uint32_t*>(xp + col * pitch);
+    if (S0 >= 0 && m0) fma_kh<S0, KT_, 0>(xv);
+    if (S1 >= 0 && m1) fma_kh<S1, KT_, 1>(xv);
+    if (S2 >= 0 && m2) fma_kh<S2, KT_, 2>(xv);
+  }
+  template <int S0, int S1, int S2>
+  __device__ __forceinline__ void compute(const char* stage, bool m0, bool m1, bool m2) {
+    const char* xp = stage + xoff;
+    plane<S0, S1, S2, 0>(xp, m0, m1, m2);
+    if constexpr (KT == 3) {
+      plane<S0, S1, S2, 1>(xp + plane_bytes, m0, m1, m2);
+      plane<S0, S1, S2, 2>(xp + 2 * plane_bytes, m0, m1, m2);
+    }
+  }
+  // Row store.  ncu on the first version: the per-column 64-bit address arithmetic, bounds test, residual / activation
+  // branches of this path cost ~90 instructions per output column -- with 2 channels per thread as many issue slots as
+  // the 432 FMAs of the row.  Now: 32-bit column offsets from a per-row pointer, activation as a clamp, the residual
+  // decided once per row.
+  float act_lo, act_hi;
+  int y_sw, r_sw;
+  template <int S, bool RES>
+  __device__ __forceinline__ void store_row(__nv_bfloat16* yrow, const __nv_bfloat16* rrow, int nvalid) {
+#pragma unroll
+    for (int o = 0; o < OW; ++o) {
+      if (o < nvalid) {
+        float v0 = acc[S][o][0], v1 = acc[S][o][1];
+        if constexpr (RES) {
+          const float2 rv = unpack16x2(__ldg(reinterpret_cast<const uint32_t*>(rrow + o * r_sw)), F16);
+          v0 += rv.x, v1 += rv.y;
+        }
+        v0 = fminf(fmaxf(v0, act_lo), act_hi), v1 = fminf(fmaxf(v1, act_lo), act_hi);
+        *reinterpret_cast<uint32_t*>(yrow + o * y_sw) = pack16x2(v0, v1, F16);
+      }
+    }
+    reset<S>();
+  }
+  template <int S>
+  __device__ __forceinline__ void store(__nv_bfloat16* yrow, const __nv_bfloat16* rrow, int nvalid) {
+    if (p.has_res) store_row<S, true>(yrow, rrow, nvalid);
+    else store_row<S, false>(yrow, rrow, nvalid);
+  }
+};
+
+template <int SW, int KT, bool F16>
+__global__ void __launch_bounds__(256, 2) dwconv_tma_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                            const __grid_constant__ DwTmaParams q) {
+  extern __shared__ __align__(128) char dwt_sm[];
+  using M = DwTma<SW, KT, F16>;
+  const DirectParams& p = q.p;
+  uint64_t* full = reinterpret_cast<uint64_t*>(dwt_sm);
+  char* stages = dwt_sm + kDwTmaHeader;
+  const int tid = threadIdx.x;
+  const int cb = q.cb, chb = cb * 2;   // channel pairs / channels of a block tile
+  constexpr int taps = KT * 9;
+  const int c_real = p.c_real ? p.c_real : p.x.C;
+  if (tid == 0) {
+    for (int i = 0; i < q.stages; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
+    prefetch_tmap(&xmap);
+  }
+  __syncthreads();
+  const int cg = tid % cb, lane = tid / cb;
+  const int wb = lane % q.wbt, tl = lane / q.wbt;
+  // ---- producer cursor (thread 0): one TMA box per valid input row of every tile of this block, q.stages ahead
+  // (the cursor lives in shared memory: only thread 0 touches it, and the compute threads need every register)
+  struct Cursor {
+    long long tile;
+    int hi, hi_end, c0, w0, t0, b;
+  };
+  Cursor& pc = *reinterpret_cast<Cursor*>(dwt_sm + 64);
+#define p_tile pc.tile
+#define p_hi pc.hi
+#define p_hi_end pc.hi_end
+#define p_c0 pc.c0
+#define p_w0 pc.w0
+#define p_t0 pc.t0
+#define p_b pc.b
+  auto decode = [&](long long tile, int& wt, int& tt, int& seg, int& b, int& ct) {
+    // channel tile fastest: the tiles of one spatial region run at the same time, so the 256-byte L2 promotion of a
+    // < 128-byte tile row is shared (ncu with the channel tile slowest: 2.5x the algorithmic DRAM reads at C = 144)
+    ct = (int)(tile % q.nct);
+    long long r = tile / q.nct;
+    wt = (int)(r % q.nwt);
+    r /= q.nwt;
+    tt = (int)(r % q.ntt);
+    r /= q.ntt;
+    seg = (int)(r % q.nseg);
+    b = (int)(r / q.nseg);
+  };
+  auto open_tile = [&]() {
+    if (p_tile >= q.tiles) return;
+    int wt, tt, seg, b, ct;
+    decode(p_tile, wt, tt, seg, b, ct);
+    const int ho0 = seg * q.hs, ho1 = min(ho0 + q.hs, p.y.H);   // input rows the segment consumes, clipped
+    p_hi = max(ho0 * SW - 1, 0);
+    p_hi_end = min((ho1 - 1) * SW + 1, p.x.H - 1);
+    p_c0 = ct * chb, p_w0 = wt * q.wbt * M::OW * SW - 1, p_t0 = tt * q.tt * p.sT - p.pT, p_b = b;
+  };
+  auto issue_next = [&](uint32_t s) {   // s: the ring slot to fill (the one the block has just finished reading)
+    if (p_tile >= q.tiles) return;
+    mbar_arrive_expect_tx(&full[s], q.stage_bytes);
+    tma_load_5d(stages + (size_t)s * q.stage_stride, &xmap, &full[s], p_c0, p_w0, p_hi, p_t0, p_b);
+    if (++p_hi > p_hi_end) {
+      p_tile += gridDim.x;
+      open_tile();
+    }
+  };
+  if (tid == 0) {
+    p_tile = blockIdx.x;
+    open_tile();
+    for (int i = 0; i < q.stages; ++i) issue_next(i);
+  }
+#undef p_tile
+#undef p_hi
+#undef p_hi_end
+#undef p_c0
+#undef p_w0
+#undef p_t0
+#undef p_b
+  M m(p);
+  m.pitch = chb * 2;
+  m.plane_bytes = q.ncols * m.pitch;
+  m.xoff = (uint32_t)((tl * p.sT * q.ncols + wb * M::OW * SW) * (int)m.pitch + cg * 4);
+  m.act_lo = p.act == 0 ? -CUDART_INF_F : 0.f;
+  m.act_hi = p.act == 2 ? 6.f : CUDART_INF_F;
+  m.y_sw = (int)p.y.sW, m.r_sw = (int)p.res.sW;
+  uint32_t rs = 0, rph = 0;   // ring slot and phase parity of the next row to consume
+  int cur_ct = -1;
+  for (long long tile = blockIdx.x; tile < q.tiles; tile += gridDim.x) {
+    int wt, tt, seg, b, ct;
+    decode(tile, wt, tt, seg, b, ct);
+    const int ch = ct * chb + cg * 2;
+    if (ct != cur_ct) {   // filter taps + bias of this thread's channel pair
+#pragma unroll
+      for (int tap = 0; tap < taps; ++tap) {
+        const float w0 = ch < c_real ? __ldg(p.w + (long long)ch * taps + tap) : 0.f;
+        const float w1 = ch + 1 < c_real ? __ldg(p.w + (long long)(ch + 1) * taps + tap) : 0.f;
+        m.w[tap] = pack16x2(w0, w1, F16);
+      }
+      m.bias[0] = ch < c_real ? __ldg(p.bias + ch) : 0.f;
+      m.bias[1] = ch + 1 < c_real ? __ldg(p.bias + ch + 1) : 0.f;
+      cur_ct = ct;
+    }
+    const int ho0 = seg * q.hs, ho1 = min(ho0 + q.hs, p.y.H);
+    const int to = tt * q.tt + tl, wbg = wt * q.wbt + wb;
+    const bool active = tl < q.tt && to < p.y.T && wbg < q.wblocks && ch < p.x.C;
+    const int nvalid = p.y.W - wbg * M::OW;   // output columns of this thread inside the tensor (>= OW: all)
+    __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + b * p.y.sB + to * p.y.sT +
+                        (long long)wbg * M::OW * p.y.sW + ch;
+    const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(p.res.ptr) + b * p.res.sB + to * p.res.sT +
+                              (long long)wbg * M::OW * p.res.sW + ch;
+    m.template reset<0>();
+    m.template reset<1>();
+    if constexpr (SW == 1) m.template reset<2>();
+#define DW_ROW(S0, S1, S2, hi, m0, m1, m2)                                                        \
+  do {                                                                                            \
+    if ((hi) >= 0 && (hi) < p.x.H) {                                                              \
+      mbar_wait(&full[rs], rph, 7);                                                               \
+      if (active) m.template compute<S0, S1, S2>(stages + rs * q.stage_stride, m0, m1, m2);       \
+      __syncthreads();                                                                            \
+      if (tid == 0) issue_next(rs);                                                               \
+      if (++rs == (uint32_t)q.stages) rs = 0, rph ^= 1;                                           \
+    }                                                                                             \
+  } while (0)
+#define DW_STORE(S, ho)                                                                                 \
+  do {                                                                                                  \
+    if (active) m.template store<S>(yb + (long long)(ho) * p.y.sH, rb + (long long)(ho) * p.res.sH, nvalid); \
+  } while (0)
+    if constexpr (SW == 1) {
+      // stride 1: input row hi feeds output rows hi+1 (kh 0), hi (kh 1), hi-1 (kh 2); row hi-1 is complete after it
+      int hi = ho0 - 1;
+      while (true) {
+        DW_ROW(2, 1, 0, hi, hi + 1 < ho1, hi >= ho0 && hi < ho1, hi - 1 >= ho0);
+        if (hi - 1 >= ho0) DW_STORE(0, hi - 1);
+        if (hi >= ho1) break;
+        ++hi;
+        DW_ROW(0, 2, 1, hi, hi + 1 < ho1, hi >= ho0 && hi < ho1, hi - 1 >= ho0);
+        if (hi - 1 >= ho0) DW_STORE(1, hi - 1);
+        if (hi >= ho1) break;
+        ++hi;
+        DW_ROW(1, 0, 2, hi, hi + 1 < ho1, hi >= ho0 && hi < ho1, hi - 1 >= ho0);
+        if (hi - 1 >= ho0) DW_STORE(2, hi - 1);
+        if (hi >= ho1) break;
+        ++hi;
+      }
+    } else {
+      // stride 2: output row ho reads input rows 2ho-1 (kh 0), 2ho (kh 1), 2ho+1 (kh 2); row 2ho+1 is also kh 0 of ho+1
+      DW_ROW(0, -1, -1, 2 * ho0 - 1, true, false, false);
+      int ho = ho0;
+      while (true) {
+        DW_ROW(-1, 0, -1, 2 * ho, false, true, false);
+        DW_ROW(1, -1, 0, 2 * ho + 1, ho + 1 < ho1, false, true);
+        DW_STORE(0, ho);
+        if (++ho >= ho1) break;
+        DW_ROW(-1, 1, -1, 2 * ho, false, true, false);
+        DW_ROW(0, -1, 1, 2 * ho + 1, ho + 1 < ho1, false, true);
+        DW_STORE(1, ho);
+        if (++ho >= ho1) break;
+      }
+    }
+#undef DW_ROW
+#undef DW_STORE
+  }
+}
+
 static bool vec_ok(const View& v, int vec);
+// false = geometry not covered (caller falls back to the global-load kernels)
+static bool launch_dwconv_tma(const DirectParams& p, cudaStream_t s) {
+  if (!vec_ok(p.x, 8) || !vec_ok(p.y, 2) || p.x.C % 8 != 0 || (p.kT != 1 && p.kT != 3)) return false;
+  if (p.has_res && !vec_ok(p.res, 2)) return false;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  static const int hs_env = dw_env_int("ESF_DW_HS", 0), tt_env = dw_env_int("ESF_DW_TT", 0),
+                   wbt_env = dw_env_int("ESF_DW_WBT", 0), st_env = dw_env_int("ESF_DW_STAGES", 0),
+                   ch8_env = dw_env_int("ESF_DW_CH8", 0);
+  constexpr int OW = 8, kThreads = 256;
+  DwTmaParams q;
+  q.p = p;
+  const int SW = p.sW;
+  // Tile search: channels per block (a multiple of 8 = 16-byte TMA rows; 2 per thread), column blocks and output
+  // planes per block, maximising the fraction of the 256 threads that own real outputs (C = 144: 48 channels x 1 x 8
+  // planes or 72 x 7 x 1 instead of 64-channel tiles with a quarter of the lanes idle -- ncu: barrier stalls 2.2 per
+  // issue), then the smallest halo; the stage has to leave room for >= 3 stages x 2 blocks per SM.
+  const int c8 = p.x.C / 8;
+  q.cgs = p.x.C / 2;
+  q.wblocks = cdiv(p.y.W, OW);
+  int cb = 0, wbt = 1, tt = 1;
+  double best = -1;
+  for (int ch8 = std::min(c8, 16); ch8 >= 1; --ch8) {
+    const int cbc = ch8 * 4;
+    if (cbc > kThreads || (ch8_env > 0 && ch8 != std::min(ch8_env, c8))) continue;
+    if (ch8 == 1 && c8 > 1 && ch8_env == 0) continue;   // 16-byte rows: too many TMA rows / DRAM sectors per byte
+    const int lanes = kThreads / cbc, nct = cdiv(c8, ch8);
+    for (int w = 1; w <= std::min(lanes, q.wblocks); ++w) {
+      if (wbt_env > 0 && w != std::min(wbt_env, q.wblocks)) continue;
+      int t = std::min(p.y.T, lanes / w);
+      if (tt_env > 0) t = std::min(t, tt_env);
+      t = cdiv(p.y.T, cdiv(p.y.T, t));
+      const int ncols = (w * OW - 1) * SW + 3, planes = (t - 1) * p.sT + p.kT;
+      const size_t bytes = (size_t)cbc * 4 * ncols * planes;
+      if (bytes > 24 * 1024 || ncols > 256 || planes > 256) continue;
+      const double eff = (double)(p.x.C / 2) * q.wblocks * p.y.T /
+                         ((double)nct * cdiv(q.wblocks, w) * cdiv(p.y.T, t) * kThreads);
+      const double halo = ((double)ncols / (w * OW * SW)) * ((double)planes / (t * p.sT));
+      // full-warp channel rows read conflict-free; rows under 64 bytes cost TMA rows and partial DRAM bursts
+      const double score = eff - 0.02 * halo - (cbc % 32 ? 0.01 : 0.0) - (ch8 < 4 ? 0.03 * (4 - ch8) : 0.0);
+      if (score > best) best = score, cb = cbc, wbt = w, tt = t;
+    }
+  }
+  if (cb == 0) return false;
+  q.cb = cb;
+  q.nct = cdiv(q.cgs, cb);
+  q.wbt = wbt, q.tt = tt;
+  q.ncols = (wbt * OW - 1) * SW + 3;
+  q.planes = (tt - 1) * p.sT + p.kT;
+  q.stage_bytes = (uint32_t)(cb * 4 * q.ncols * q.planes);
+  q.stage_stride = (q.stage_bytes + 127u) & ~127u;
+  if (q.ncols > 256 || q.planes > 256 || q.stage_bytes > 32 * 1024) return false;
+  q.stages = std::max(2, std::min(kDwTmaMaxStages, (int)((100 * 1024 - kDwTmaHeader) / q.stage_stride)));
+  if (st_env > 0) q.stages = std::max(2, std::min(kDwTmaMaxStages, st_env));
+  q.nseg = cdiv(p.y.H, hs_env > 0 ? hs_env : 16);
+  q.hs = cdiv(p.y.H, q.nseg);
+  q.nseg = cdiv(p.y.H, q.hs);
+  q.nwt = cdiv(q.wblocks, wbt), q.ntt = cdiv(p.y.T, tt);
+  q.tiles = (long long)q.nct * p.y.B * q.nseg * q.ntt * q.nwt;
+  CUtensorMap xmap;
+  {
+    const int c_map = p.c_real ? p.c_real : p.x.C;   // padding channels of the rows read as zeros
+    cuuint64_t dims[5] = {(cuuint64_t)c_map, (cuuint64_t)p.x.W, (cuuint64_t)p.x.H, (cuuint64_t)p.x.T, (cuuint64_t)p.x.B};
+    cuuint64_t strides[4] = {(cuuint64_t)p.x.sW * 2, (cuuint64_t)p.x.sH * 2, (cuuint64_t)p.x.sT * 2, (cuuint64_t)p.x.sB * 2};
+    cuuint32_t box[5] = {(cuuint32_t)(cb * 2), (cuuint32_t)q.ncols, 1, (cuuint32_t)q.planes, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (enc(&xmap, p.x.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.x.ptr, dims, strides,
+            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  const size_t smem = kDwTmaHeader + (size_t)q.stages * q.stage_stride;
+  const unsigned grid = (unsigned)std::min<long long>(q.tiles, (long long)std::max(num_sms(), 1) * 2);
+  auto launch = [&](auto kern) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024);
+    kern<<<grid, kThreads, smem, s>>>(xmap, q);
+  };
+  const int key = (p.x.f16 ? 4 : 0) | (SW == 2 ? 2 : 0) | (p.kT == 3 ? 1 : 0);
+  switch (key) {
+    case 0: launch(dwconv_tma_kernel<1, 1, false>); break;
+    case 1: launch(dwconv_tma_kernel<1, 3, false>); break;
+    case 2: launch(dwconv_tma_kernel<2, 1, false>); break;
+    case 3: launch(dwconv_tma_kernel<2, 3, false>); break;
+    case 4: launch(dwconv_tma_kernel<1, 1, true>); break;
+    case 5: launch(dwconv_tma_kernel<1, 3, true>); break;
+    case 6: launch(dwconv_tma_kernel<2, 1, true>); break;
+    default: launch(dwconv_tma_kernel<2, 3, true>); break;
+  }
+  return true;
+}
+
+static int dw_march_enabled() {
+  static const int on = [] {
+    const char* e = getenv("ESF_DW_MARCH");
+    return e ? atoi(e) : 2;
+  }();
+  return on;
+}
+
+template <int VEC>
+static bool launch_dwconv_march(const DirectParams& p, cudaStream_t s) {
+  const int C = p.x.C, cgs = C / VEC;
+  const int taps = p.kT * 9;
+  const size_t smem = (size_t)C * (sizeof(float) + taps * 2);
+  if (smem > 96 * 1024) return false;
+  constexpr int OW = 4;
+  const int res_vec = p.has_res && vec_ok(p.res, VEC);
+  static const int hs_env = dw_env_int("ESF_DW_HS", 0), wbg_env = dw_env_int("ESF_DW_WBG", 0);
+  const int nseg = cdiv(p.y.H, hs_env > 0 ? hs_env : 16);
+  const int hs = cdiv(p.y.H, nseg);
+  const int wblocks = cdiv(p.y.W, OW);
+  const int wbg = std::max(1, std::min(wblocks, wbg_env > 0 ? wbg_env : 32 / std::max(cgs, 1)));
+  const long long items = (long long)p.y.B * cdiv(p.y.H, hs) * cdiv(wblocks, wbg) * p.y.T * wbg * cgs;
+  const unsigned grid = (unsigned)std::min<long long>((items + 127) / 128, 148 * 16);
+  auto launch = [&](auto kern) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    kern<<<grid, 128, smem, s>>>(p, res_vec, hs, wbg);
+  };
+  if (p.x.f16) {
+    if (p.sW == 1) launch(dwconv_march_kernel<VEC, OW, 1, true>);
+    else launch(dwconv_march_kernel<VEC, OW, 2, true>);
+  } else {
+    if (p.sW == 1) launch(dwconv_march_kernel<VEC, OW, 1, false>);
+    else launch(dwconv_march_kernel<VEC, OW, 2, false>);
+  }
+  return true;
+}
+
 template <int VEC, int KW>
 static bool launch_dwconv(const DirectParams& p, cudaStream_t s) {
+  if constexpr (KW == 3) {
+    if (p.kH == 3 && p.pH == 1 && p.pW == 1 && p.sH == p.sW && dw_march_enabled()) {
+      // 2 (default): TMA-staged march; 1: global-load march (kept for A/B); 0: tile kernel
+      if constexpr (VEC == 8) {
+        if (dw_march_enabled() >= 2 && launch_dwconv_tma(p, s)) return true;
+      }
+      // rows that TMA cannot address (C < 8: 4- or 8-byte pitch): the global-load march (C = 4 @112^2: 0.286 -> 0.198 ms)
+      if ((dw_march_enabled() == 1 || (dw_march_enabled() >= 2 && VEC < 8)) && launch_dwconv_march<VEC>(p, s)) return true;
+    }
+  }
   const int cgs = p.x.C / VEC;
   const int taps = p.kT * p.kH * KW;
   const size_t smem = (size_t)kDwCgPerBlock * VEC * (sizeof(float) + taps * 2);

@@ -433,12 +433,14 @@ class Plan:
             # rows padded to a multiple of 8 channels by act(): 16-byte vectors over the padded width (zero weights)
             cp = (C + 7) // 8 * 8
             self._add(lambda s, d=d: rt.check(L.esf_dwconv_padded(ctypes.byref(d), cp, s), "esf_dwconv_padded"),
-                      "dwconv", "%dx%dx%d g%d %d->%d pad%d" % (kt, kh, kw, groups, C, C, cp),
+                      "dwconv", "%dx%dx%d s%d%d%d g%d %d->%d pad%d @%s" % (kt, kh, kw, *stride, groups, C, C, cp,
+                                                                              tuple(x.shape[1:4])),
                       flops=2.0 * m * C * kt * kh * kw, nbytes=self._nbytes(x, y, res) + wd.numel() * 4)
             return
         self._add(lambda s, d=d: rt.check(L.esf_conv_direct(ctypes.byref(d), s), "esf_conv_direct"),
                   "dwconv" if depthwise else "conv_direct",
-                  "%dx%dx%d g%d %d->%d" % (kt, kh, kw, groups, x.shape[4], y.shape[4]),
+                  "%dx%dx%d s%d%d%d g%d %d->%d @%s" % (kt, kh, kw, *stride, groups, x.shape[4], y.shape[4],
+                                                       tuple(x.shape[1:4])),
                   flops=2.0 * m * y.shape[4] * (x.shape[4] // groups) * kt * kh * kw,
                   nbytes=self._nbytes(x, y, res) + wd.numel() * 4)
 

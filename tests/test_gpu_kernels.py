@@ -202,7 +202,12 @@ def test_conv_direct_depthwise_and_grouped(esf_lib):
     (4, (3, 3, 3), (1, 1, 1), (1, 4, 12, 12)), (320, (3, 3, 3), (1, 2, 2), (1, 2, 7, 7)),
     (40, (3, 3, 3), (2, 2, 2), (1, 4, 9, 9)), (72, (1, 5, 5), (1, 1, 1), (2, 3, 9, 9)),
     (28, (1, 5, 5), (1, 2, 2), (1, 3, 14, 14)), (7, (1, 5, 5), (1, 2, 2), (1, 2, 9, 11)),
-    (12, (3, 3, 3), (1, 1, 1), (2, 10, 17, 19))])
+    (12, (3, 3, 3), (1, 1, 1), (2, 10, 17, 19)),
+    # marching kernel: several row segments per plane (H > 16), ragged W, stride 2 in T, weights beyond 48 KB of smem
+    (144, (3, 3, 3), (1, 1, 1), (1, 3, 37, 21)), (24, (3, 3, 3), (1, 2, 2), (1, 3, 40, 23)),
+    (16, (3, 3, 3), (2, 2, 2), (1, 5, 35, 35)), (8, (1, 3, 3), (1, 1, 1), (2, 2, 33, 18)),
+    (960, (3, 3, 3), (1, 1, 1), (1, 2, 7, 7)), (1080, (3, 3, 3), (1, 2, 2), (1, 2, 7, 7)),
+    (4, (3, 3, 3), (1, 2, 2), (1, 4, 34, 30)), (28, (3, 3, 3), (1, 1, 1), (1, 2, 18, 5))])
 def test_depthwise_vector_kernel(esf_lib, C, k, s, shape, precision):
     """Depthwise convs through Plan.conv: vector kernel (VEC 8/4/2/1 by channel count), padded channel pitch, slices."""
     adt = rt.TORCH_DTYPE[precision]

@@ -1,0 +1,10 @@
+#!/bin/bash
+set -u
+cd "$(dirname "$0")/../.."
+O=gpurun_out/s77
+mkdir -p $O
+python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:dwconv -s 1 -c 1 -o $O/dw_tma_c32 -f python tools/prof_dwconv.py 1 2 > $O/ncu_c32.log 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:dwconv -s 1 -c 1 -o $O/dw_tma_c144 -f python tools/prof_dwconv.py 1 0 > $O/ncu_c144.log 2>&1
+tail -3 $O/ncu_c32.log $O/ncu_c144.log
+ls -la $O
