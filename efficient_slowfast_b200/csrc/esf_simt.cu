@@ -301,6 +301,7 @@ struct DirectParams {
   const float* bias;
   int kT, kH, kW, sT, sH, sW, pT, pH, pW, dT, dH, dW, groups, act, has_res, out_f32;
   int c_real;   // depthwise over padded rows (esf_dwconv_padded): channels >= c_real have zero weights / bias
+  int y_pad;    // pointwise over padded output rows (esf_pointwise_padded): channels [C, y_pad) of y may be written (zeros)
 };
 
 __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectParams p) {
@@ -404,10 +405,11 @@ __global__ void __launch_bounds__(256) pw_small_kernel(const DirectParams p, int
   float* bias_s = pw_sm + cin * coutp;
   for (int i = threadIdx.x; i < coutp; i += blockDim.x) bias_s[i] = i < cout ? __ldg(p.bias + i) : 0.f;
   __syncthreads();
-  const I total = (I)p.y.B * p.y.T * p.y.H * p.y.W * cogs;
+  // thread = one position, looping over its groups of 8 output channels (the first version gave every (position, group)
+  // its own thread: a run-time division per thread -- as many instructions as the cin x 8 FMAs of a 2 -> 12 layer)
+  const I total = (I)p.y.B * p.y.T * p.y.H * p.y.W;
   for (I idx = blockIdx.x * (I)blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
-    I pos = cogs == 1 ? idx : idx / cogs;
-    const int cog = cogs == 1 ? 0 : (int)(idx - pos * cogs);
+    I pos = idx;
     long long xo, yo0, ro0 = 0;
     if constexpr (FLAT) {
       xo = (long long)pos * p.x.sW, yo0 = (long long)pos * p.y.sW;
@@ -422,32 +424,57 @@ __global__ void __launch_bounds__(256) pw_small_kernel(const DirectParams p, int
       xo = voff(p.x, b, t, h, w), yo0 = voff(p.y, b, t, h, w);
       if (p.has_res) ro0 = voff(p.res, b, t, h, w);
     }
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias_s[cog * 8 + j];
     const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + xo;
-    for (int c0 = 0; c0 < cin; c0 += VIN) {
-      float xv[VIN];
-      load_vec<VIN>(xr + c0, p.x.f16, xv);
+    for (int cog = 0; cog < cogs; ++cog) {
+      float acc[8];
 #pragma unroll
-      for (int e = 0; e < VIN; ++e) {
-        const float* wr = pw_sm + (c0 + e) * coutp + cog * 8;
+      for (int j = 0; j < 8; ++j) acc[j] = bias_s[cog * 8 + j];
+      for (int c0 = 0; c0 < cin; c0 += VIN) {
+        float xv[VIN];
+        load_vec<VIN>(xr + c0, p.x.f16, xv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[e], wr[j], acc[j]);
+        for (int e = 0; e < VIN; ++e) {
+          const float* wr = pw_sm + (c0 + e) * coutp + cog * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[e], wr[j], acc[j]);
+        }
       }
-    }
-    const long long yo = yo0 + cog * 8;
-    const int valid = min(8, cout - cog * 8);
-    if (p.has_res) {
-      const long long ro = ro0 + cog * 8;
-      for (int j = 0; j < valid; ++j) acc[j] += ldbf(p.res, ro + j);
-    }
+      const long long yo = yo0 + cog * 8;
+      // y_pad: the row padding may be written too (zero weights + bias there => zeros), which turns the 24-byte row of a
+      // 12-channel output into one full 32-byte sector instead of a partial-sector write (read-modify-write in L2)
+      const int valid = min(8, (p.y_pad ? p.y_pad : cout) - cog * 8);
+      if (p.has_res) {
+        const long long ro = ro0 + cog * 8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], p.act);
-    if (valid == 8 && vec_out) {
-      store_vec<8>(reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + yo, p.y.f16, acc);
-    } else {
-      for (int j = 0; j < valid; ++j) sth(p.y, yo + j, acc[j]);
+        for (int j = 0; j < 8; ++j)
+          if (cog * 8 + j < cout) acc[j] += ldbf(p.res, ro + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], p.act);
+      __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + yo;
+      if (valid == 8 && vec_out) {
+        store_vec<8>(yp, p.y.f16, acc);
+      } else if (vec_out) {
+        // ragged last group (12 = 8 + 4, 18 = 16 + 2 output channels): the widest aligned pieces, not a scalar loop
+        if (valid >= 4) {
+          store_vec<4>(yp, p.y.f16, acc);
+          if (valid >= 6) {
+            store_vec<2>(yp + 4, p.y.f16, acc + 4);
+            if (valid == 7) sth(p.y, yo + 6, acc[6]);
+          } else if (valid == 5) {
+            sth(p.y, yo + 4, acc[4]);
+          }
+        } else if (valid >= 2) {
+          store_vec<2>(yp, p.y.f16, acc);
+          if (valid == 3) sth(p.y, yo + 2, acc[2]);
+        } else {
+          sth(p.y, yo, acc[0]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < valid) sth(p.y, yo + j, acc[j]);
+      }
     }
   }
 }
@@ -905,7 +932,8 @@ struct DwTma {
           const float2 rv = unpack16x2(__ldg(reinterpret_cast<const uint32_t*>(rrow + o * r_sw)), F16);
           v0 += rv.x, v1 += rv.y;
         }
-        v0 = fminf(fmaxf(v0, act_lo), act_hi), v1 = fminf(fmaxf(v1, act_lo), act_hi);
+        v0 = fmaxf(v0, act_lo), v1 = fmaxf(v1, act_lo);
+        if (p.act == 2) v0 = fminf(v0, act_hi), v1 = fminf(v1, act_hi);
         *reinterpret_cast<uint32_t*>(yrow + o * y_sw) = pack16x2(v0, v1, F16);
       }
     }
@@ -2053,7 +2081,7 @@ extern "C" int esf_dwconv_padded(const esf_conv_desc* d, int32_t c_pad, void* st
   p.has_res = d->res.ptr != nullptr;
   p.res = p.has_res ? to_view(&d->res) : p.y;
   p.x.C = p.y.C = p.res.C = c_pad;
-  p.c_real = C;
+  p.c_real = C, p.y_pad = 0;
   p.w = static_cast<const float*>(d->w), p.bias = d->bias;
   p.kT = d->kT, p.kH = d->kH, p.kW = d->kW, p.sT = d->sT, p.sH = d->sH, p.sW = d->sW;
   p.pT = d->pT, p.pH = d->pH, p.pW = d->pW, p.dT = d->dT, p.dH = d->dH, p.dW = d->dW;
@@ -2065,7 +2093,21 @@ extern "C" int esf_dwconv_padded(const esf_conv_desc* d, int32_t c_pad, void* st
   return check_launch("dwconv_kernel");
 }
 
-extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {
+static int conv_direct_impl(const esf_conv_desc* d, int y_pad, void* stream);
+extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) { return conv_direct_impl(d, 0, stream); }
+
+// Pointwise conv whose OUTPUT rows were padded to y_c_pad (a multiple of 8) channels by the allocator (engine.Plan.act):
+// the tiny-channel kernel writes whole 16-byte groups including the padding (zeros).  The caller vouches that channels
+// [C, y_c_pad) of y are padding owned by the same allocation; geometries the tiny-channel kernel does not take run as
+// esf_conv_direct (the vouch is then simply unused).
+extern "C" int esf_pointwise_padded(const esf_conv_desc* d, int32_t y_c_pad, void* stream) {
+  ESF_CHECK_ARG(d && view_ok(&d->y), "esf_pointwise_padded: null/bad argument");
+  ESF_CHECK_ARG(y_c_pad % 8 == 0 && y_c_pad >= d->y.C && y_c_pad < d->y.C + 8 && d->y.sW >= y_c_pad,
+                "esf_pointwise_padded: y rows are not padded to %d channels", y_c_pad);
+  return conv_direct_impl(d, y_c_pad, stream);
+}
+
+static int conv_direct_impl(const esf_conv_desc* d, int y_pad, void* stream) {
   ESF_CHECK_ARG(d && view_ok(&d->x) && view_ok(&d->y) && d->w && d->bias, "esf_conv_direct: null/bad argument");
   ESF_CHECK_ARG(d->groups >= 1 && d->x.C % d->groups == 0 && d->y.C % d->groups == 0,
                 "esf_conv_direct: channels not divisible by groups");
@@ -2082,7 +2124,7 @@ extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {
   p.kT = d->kT, p.kH = d->kH, p.kW = d->kW, p.sT = d->sT, p.sH = d->sH, p.sW = d->sW;
   p.pT = d->pT, p.pH = d->pH, p.pW = d->pW, p.dT = d->dT, p.dH = d->dH, p.dW = d->dW;
   p.groups = d->groups, p.act = d->act, p.out_f32 = d->out_dtype == ESF_F32;
-  p.c_real = 0;
+  p.c_real = 0, p.y_pad = y_pad;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (p.groups == p.x.C && p.y.C == p.x.C && (d->kW == 3 || d->kW == 5) && d->dT == 1 && d->dH == 1 && d->dW == 1 &&
       (d->sW == 1 || d->sW == 2) && !p.out_f32 && is16(d->x.dtype) && d->y.dtype == d->x.dtype &&
@@ -2096,7 +2138,7 @@ extern "C" int esf_conv_direct(const esf_conv_desc* d, void* stream) {
     const int cin = p.x.C, coutp = (p.y.C + 7) / 8 * 8;
     const size_t smem = (size_t)(cin + 1) * coutp * sizeof(float);
     if (smem <= 48 * 1024) {
-      const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W * (coutp / 8);
+      const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W;   // one thread per position
       const int vec_out = vec_ok(p.y, 8);
       const unsigned grid = grid_for(total, 256);
       auto dense = [](const View& v) {

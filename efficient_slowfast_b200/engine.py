@@ -437,7 +437,14 @@ class Plan:
                                                                               tuple(x.shape[1:4])),
                       flops=2.0 * m * C * kt * kh * kw, nbytes=self._nbytes(x, y, res) + wd.numel() * 4)
             return
-        self._add(lambda s, d=d: rt.check(L.esf_conv_direct(ctypes.byref(d), s), "esf_conv_direct"),
+        cout = y.shape[4]
+        call = lambda s, d=d: rt.check(L.esf_conv_direct(ctypes.byref(d), s), "esf_conv_direct")
+        if (groups == 1 and (kt, kh, kw) == (1, 1, 1) and cout >= 8 and cout % 8 != 0 and y.dtype == self.adt
+                and self.padded.get(y.data_ptr()) == (cout, (cout + 7) // 8 * 8)):
+            # y is a whole padded allocation (not a concat slice): the kernel may write the row padding too
+            cp = (cout + 7) // 8 * 8
+            call = lambda s, d=d, cp=cp: rt.check(L.esf_pointwise_padded(ctypes.byref(d), cp, s), "esf_pointwise_padded")
+        self._add(call,
                   "dwconv" if depthwise else "conv_direct",
                   "%dx%dx%d s%d%d%d g%d %d->%d @%s" % (kt, kh, kw, *stride, groups, x.shape[4], y.shape[4],
                                                        tuple(x.shape[1:4])),

@@ -96,6 +96,11 @@ int esf_conv_direct(const esf_conv_desc* d, void* stream);
  * the C = 18 / 162 / 12 / 36 depthwise layers of the fast pathway of SlowFastMoibleNetV2 (mobilenetv2_helper.py:40-55).
  * The caller vouches that channels [C, c_pad) of x, y and res are padding of the same allocation. */
 int esf_dwconv_padded(const esf_conv_desc* d, int32_t c_pad, void* stream);
+/* esf_pointwise_padded: esf_conv_direct for a 1x1x1 conv whose OUTPUT rows were padded to y_c_pad (a multiple of 8)
+ * channels by the allocator: the tiny-channel kernel (C_in < 8 or C_out < 8 -- the first fast-pathway layers, e.g. the
+ * 2 -> 12 / 6 -> 36 / 3 -> 18 expansions of mobilenetv2_helper.py:40-55) stores whole 16-byte groups, zeros in the padding,
+ * i.e. full 32-byte sectors.  The caller vouches that channels [C, y_c_pad) of y are padding of the same allocation. */
+int esf_pointwise_padded(const esf_conv_desc* d, int32_t y_c_pad, void* stream);
 
 /* ---- stem: Conv3d on the FP32 NCDHW clip + folded BN + ReLU -> BF16 channels-last ----------------------
  * replaces ResNetBasicStem.conv/bn/relu (stem_helper.py:173-177) and the efficient stems
