@@ -1074,6 +1074,23 @@ __global__ void __launch_bounds__(256, 2) dwconv_tma_kernel(const __grid_constan
     if constexpr (SW == 1) {
       // stride 1: input row hi feeds output rows hi+1 (kh 0), hi (kh 1), hi-1 (kh 2); row hi-1 is complete after it
       int hi = ho0 - 1;
+#ifdef ESF_DW_ROTATE_MOV
+      // one copy of the row body, the three accumulator sets rotated with register moves (32 MOVs per row, a third of
+      // the code size)
+      while (true) {
+        DW_ROW(2, 1, 0, hi, hi + 1 < ho1, hi >= ho0 && hi < ho1, hi - 1 >= ho0);
+        if (hi - 1 >= ho0) DW_STORE(0, hi - 1);
+        if (hi >= ho1) break;
+        ++hi;
+#pragma unroll
+        for (int o = 0; o < M::OW; ++o)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float fresh = m.acc[0][o][e];
+            m.acc[0][o][e] = m.acc[1][o][e], m.acc[1][o][e] = m.acc[2][o][e], m.acc[2][o][e] = fresh;
+          }
+      }
+#else
       while (true) {
         DW_ROW(2, 1, 0, hi, hi + 1 < ho1, hi >= ho0 && hi < ho1, hi - 1 >= ho0);
         if (hi - 1 >= ho0) DW_STORE(0, hi - 1);
@@ -1088,6 +1105,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_tma_kernel(const __grid_constan
         if (hi >= ho1) break;
         ++hi;
       }
+#endif
     } else {
       // stride 2: output row ho reads input rows 2ho-1 (kh 0), 2ho (kh 1), 2ho+1 (kh 2); row 2ho+1 is also kh 0 of ho+1
       DW_ROW(0, -1, -1, 2 * ho0 - 1, true, false, false);

@@ -1,0 +1,9 @@
+#!/bin/bash
+set -u
+cd "$(dirname "$0")/../.."
+O=gpurun_out/s86
+mkdir -p $O
+python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "depthwise or direct" 2>&1 | tail -5
+timeout 300 python tools/prof_dwconv.py 5 2>&1 | tee $O/prof.log
+ESF_DW_STAGES=3 timeout 300 python tools/prof_dwconv.py 5 2>&1 | tee $O/prof_st3.log
