@@ -508,7 +508,7 @@ class Plan:
         L = rt.lib()
         self._add(lambda s: rt.check(
             L.esf_pool3d(ctypes.byref(xv), ctypes.byref(yv), *kernel, *stride, *padding, int(is_avg), act, s),
-            "esf_pool3d"), "pool", "%s" % (tuple(kernel),), nbytes=self._nbytes(x, y))
+            "esf_pool3d"), "pool", "%s C=%d" % (tuple(kernel), x.shape[4]), nbytes=self._nbytes(x, y))
 
     def shuffle_concat(self, a, b, groups, y):
         av, yv = rt.view(a), rt.view(y)

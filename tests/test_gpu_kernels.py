@@ -391,6 +391,35 @@ def test_pool3d(esf_lib, C):
             assert torch.equal(got, ref)   # max of BF16 values is exact
 
 
+@pytest.mark.parametrize("C,off", [(30, 0), (19, 0), (60, 16), (243, 8), (9, 24)])
+def test_pool3d_odd_channels_padded_rows(esf_lib, C, off):
+    """C % 8 != 0 over rows with a 16-byte aligned pitch (the allocator's padding, or a slice of a concat buffer at a
+    multiple of 8 channels): full groups of 8 channels vectorised, the ragged tail element-wise -- the neighbours of the
+    slice and the row padding stay untouched."""
+    g = torch.Generator().manual_seed(C + off)
+    plan = Plan(DEV, "fp16")
+    x = plan.act(2, 3, 13, 11, C)
+    x.copy_(_rand_act(g, 2, 3, 13, 11, C, dtype=torch.float16))
+    for kernel, stride, pad, avg in [((3, 3, 3), (1, 2, 2), (1, 1, 1), True), ((1, 3, 3), (1, 2, 2), (0, 1, 1), False),
+                                     ((3, 3, 3), (2, 2, 2), (1, 1, 1), False)]:
+        xr = _to_ncdhw(x.cpu())
+        ref = F.avg_pool3d(xr, kernel, stride, pad) if avg else F.max_pool3d(xr, kernel, stride, pad)
+        Bo, To, Ho, Wo, _ = _to_ndhwc(ref).shape
+        ybuf = plan.act(Bo, To, Ho, Wo, off + C + 5)
+        full = next(t for t in reversed(plan.keep) if isinstance(t, torch.Tensor))   # the padded allocation behind ybuf
+        full.fill_(7.0)
+        y = ybuf[..., off:off + C]
+        plan.pool(x, y, kernel, stride, pad, is_avg=avg)
+        plan.launch_all()
+        torch.cuda.synchronize()
+        got = _to_ncdhw(y.cpu())
+        if avg:
+            assert (got - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+        else:
+            assert torch.equal(got, ref)
+        assert (full[..., :off].float() == 7.0).all() and (full[..., off + C:].float() == 7.0).all()
+
+
 @pytest.mark.parametrize("C,alpha", [(8, 4), (32, 4), (128, 4), (6, 4), (64, 8)])
 def test_eca_fuse(esf_lib, C, alpha):
     g = torch.Generator().manual_seed(C)
