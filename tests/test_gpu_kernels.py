@@ -194,6 +194,32 @@ def test_conv_direct_depthwise_and_grouped(esf_lib):
         assert err <= 1e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("cin,cout,groups,off", [(15, 60, 3, 60), (24, 36, 1, 12), (48, 20, 1, 6)])
+def test_conv_into_unaligned_concat_slice(esf_lib, cin, cout, groups, off):
+    """A dense / grouped pointwise conv whose output is a concat slice at a channel offset that is not a multiple of 8
+    still runs on the implicit GEMM (aligned buffer + row copy); the neighbouring channels stay untouched."""
+    g = torch.Generator().manual_seed(cin + cout)
+    B, T, H, W = 2, 4, 7, 7
+    plan = Plan(DEV, "fp16")
+    x = plan.act(B, T, H, W, cin)
+    x.copy_(_rand_act(g, B, T, H, W, cin, dtype=torch.float16))
+    w = torch.randn(cout, cin // groups, 1, 1, 1, generator=g) * (2.0 * groups / cin) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv3d(_to_ncdhw(x.cpu()).float(), w.half().float(), bias, groups=groups).relu()
+    ybuf = plan.act(B, T, H, W, off + cout + 4)
+    full = next(t for t in reversed(plan.keep) if isinstance(t, torch.Tensor))
+    full.fill_(7.0)
+    y = ybuf[..., off:off + cout]
+    plan.conv(x, y, w.double(), bias.double(), groups=groups, act=rt.ACT_RELU)
+    kinds = [m["kind"] for m in plan.meta]
+    assert "conv_direct" not in kinds and kinds[-1] == "shuffle", kinds
+    plan.launch_all()
+    torch.cuda.synchronize()
+    err = (_to_ncdhw(y.cpu()).float() - ref).abs().max().item()
+    assert err <= 3e-3 * ref.abs().max().item(), err
+    assert (full[..., :off].float() == 7.0).all() and (full[..., off + cout:].float() == 7.0).all()
+
+
 @pytest.mark.parametrize("precision", ["bf16", "fp16"])
 @pytest.mark.parametrize("C,k,s,shape", [
     (144, (3, 3, 3), (1, 1, 1), (2, 4, 14, 14)), (24, (3, 3, 3), (1, 2, 2), (2, 4, 14, 14)),
