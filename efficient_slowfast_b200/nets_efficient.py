@@ -11,6 +11,7 @@ arithmetic is a launch plan of libesf_b200 kernels.  These backbones have channe
 automatically (engine.Plan.conv).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -401,13 +402,34 @@ class SlowFastShuffleNet(_EfficientBase):
         init_weights(self, cfg.MODEL.FC_INIT_STD, cfg.RESNET.ZERO_INIT_FINAL_BN)
         self._init_runtime(cfg)
 
+    # fold the channel shuffle behind conv1 into its weight rows (A/B knob: ESF_FOLD_SHUFFLE=0 keeps the shuffle kernel)
+    _fold_shuffle = os.environ.get("ESF_FOLD_SHUFFLE", "1") != "0"
+
     def _emit_unit(self, plan, blk, x, y):
         """Bottleneck.forward (shufflenet_helper.py:75-84)."""
-        t = self._emit_conv(plan, x, blk.conv1, blk.bn1, rt.ACT_RELU)
-        if blk.groups > 1:
-            ts = plan.act(*t.shape)
-            plan.shuffle_concat(t, None, blk.groups, ts)
-            t = ts
+        conv1 = blk.conv1
+        if (blk.groups > 1 and self._fold_shuffle and tuple(conv1.kernel_size) == (1, 1, 1) and x.shape[4] >= 8
+                and conv1.out_channels % blk.groups == 0):
+            # channel_shuffle(relu(bn(conv1(x)))) is a permutation of conv1's output channels: fold it into the ORDER of
+            # the weight rows.  A permuted grouped conv is no longer grouped, so the layer runs as one dense implicit
+            # GEMM over a block-diagonal weight (the layers are HBM bound; `groups`-fold MACs on structural zeros) --
+            # one launch instead of a GEMM per group plus the shuffle kernel (1.6 ms of the 12.3 ms ShuffleNet step).
+            w, b = fold_conv_bn(conv1.weight, conv1.bias, blk.bn1)
+            cout, cin_g, g = w.shape[0], w.shape[1], conv1.groups
+            wd = torch.zeros((cout, cin_g * g, 1, 1, 1), dtype=w.dtype, device=w.device)
+            for i in range(g):
+                rows = slice(i * (cout // g), (i + 1) * (cout // g))
+                wd[rows, i * cin_g:(i + 1) * cin_g] = w[rows]
+            G, cpg = blk.groups, cout // blk.groups
+            src = torch.tensor([(o % G) * cpg + o // G for o in range(cout)], device=w.device)   # shuffled[o] = y[src[o]]
+            t = plan.act(*x.shape[:4], cout)
+            plan.conv(x, t, wd[src], b[src], act=rt.ACT_RELU)
+        else:
+            t = self._emit_conv(plan, x, conv1, blk.bn1, rt.ACT_RELU)
+            if blk.groups > 1:
+                ts = plan.act(*t.shape)
+                plan.shuffle_concat(t, None, blk.groups, ts)
+                t = ts
         t = self._emit_conv(plan, t, blk.conv2, blk.bn2, rt.ACT_NONE)
         if blk.stride == 2:
             c3 = blk.conv3.out_channels
