@@ -1515,15 +1515,15 @@ __device__ __forceinline__ void eca_tmax8(const EcaParams& p, int b, int pos, in
 
 __global__ void __launch_bounds__(kEcaThreads) eca_partial_vec_kernel(const EcaParams p) {
   __shared__ float red[kEcaThreads][9];
-  const int C = p.x.C, cgs = C >> 3;
+  const int C = p.x.C, cgs = (C + 7) >> 3;          // a ragged last group reads the row padding (never summed below)
   const int b = blockIdx.y;
   const int npos = (p.x.T / p.alpha) * p.x.H * p.x.W;
   const int chunk = (npos + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * chunk, p1 = min(npos, p0 + chunk);
-  const int cg = threadIdx.x & (cgs - 1);          // kEcaThreads % cgs == 0: a thread keeps its channel group
-  const int lanes = kEcaThreads / cgs;
+  const int cg = threadIdx.x % cgs;                 // a thread keeps its channel group
+  const int lanes = kEcaThreads / cgs;              // threads beyond lanes * cgs idle (cgs need not divide 256)
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int pos = p0 + threadIdx.x / cgs; pos < p1; pos += lanes) {
+  for (int pos = threadIdx.x / cgs < lanes ? p0 + threadIdx.x / cgs : p1; pos < p1; pos += lanes) {
     float m[8];
     eca_tmax8(p, b, pos, cg, m);
 #pragma unroll
@@ -1541,18 +1541,20 @@ __global__ void __launch_bounds__(kEcaThreads) eca_partial_vec_kernel(const EcaP
 }
 
 __global__ void __launch_bounds__(kEcaThreads) eca_apply_vec_kernel(const EcaParams p, int nblk) {
-  extern __shared__ float sm[];  // mean[C], mul[C], shift[C]
-  const int C = p.x.C, cgs = C >> 3;
+  extern __shared__ float sm[];  // mean[Cp], mul[Cp], shift[Cp], Cp = C rounded up to 8 (zeros behind C)
+  const int C = p.x.C, cgs = (C + 7) >> 3, Cp = cgs * 8;
   float* mean = sm;
-  float* mul = sm + C;
-  float* shift = sm + 2 * C;
+  float* mul = sm + Cp;
+  float* shift = sm + 2 * Cp;
   const int b = blockIdx.y;
   const int npos = (p.x.T / p.alpha) * p.x.H * p.x.W;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
     float t = 0.f;
-    for (int i = 0; i < nblk; ++i) t += p.partial[((long long)b * nblk + i) * C + c];
+    if (c < C)
+      for (int i = 0; i < nblk; ++i) t += p.partial[((long long)b * nblk + i) * C + c];
     mean[c] = t / (float)npos;
-    shift[c] = __ldg(p.bn_shift + c);
+    shift[c] = c < C ? __ldg(p.bn_shift + c) : 0.f;
+    mul[c] = 0.f;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -1568,12 +1570,13 @@ __global__ void __launch_bounds__(kEcaThreads) eca_apply_vec_kernel(const EcaPar
   __syncthreads();
   const int chunk = (npos + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * chunk, p1 = min(npos, p0 + chunk);
-  const int cg = threadIdx.x & (cgs - 1);
+  const int cg = threadIdx.x % cgs;
   const int lanes = kEcaThreads / cgs;
+  const int nv = min(8, C - cg * 8);   // channels of this thread's group (< 8: ragged last group)
   float ml[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) ml[j] = mul[cg * 8 + j], sh[j] = shift[cg * 8 + j];
-  for (int pos = p0 + threadIdx.x / cgs; pos < p1; pos += lanes) {
+  for (int pos = threadIdx.x / cgs < lanes ? p0 + threadIdx.x / cgs : p1; pos < p1; pos += lanes) {
     float m[8];
     eca_tmax8(p, b, pos, cg, m);
 #pragma unroll
@@ -1582,10 +1585,17 @@ __global__ void __launch_bounds__(kEcaThreads) eca_apply_vec_kernel(const EcaPar
     const int r = pos / p.x.W;
     const int h = r % p.x.H;
     const int tp = r / p.x.H;
-    uint4 o;
-    o.x = pack16x2(m[0], m[1], p.y.f16), o.y = pack16x2(m[2], m[3], p.y.f16);
-    o.z = pack16x2(m[4], m[5], p.y.f16), o.w = pack16x2(m[6], m[7], p.y.f16);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + voff(p.y, b, tp, h, w) + cg * 8) = o;
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + voff(p.y, b, tp, h, w) + cg * 8;
+    if (nv == 8) {
+      uint4 o;
+      o.x = pack16x2(m[0], m[1], p.y.f16), o.y = pack16x2(m[2], m[3], p.y.f16);
+      o.z = pack16x2(m[4], m[5], p.y.f16), o.w = pack16x2(m[6], m[7], p.y.f16);
+      *reinterpret_cast<uint4*>(yp) = o;
+    } else {   // the neighbours of the concat slice stay untouched
+#pragma unroll
+      for (int j = 0; j < 7; ++j)
+        if (j < nv) yp[j] = f2h16(m[j], p.y.f16);
+    }
   }
 }
 
@@ -2264,13 +2274,14 @@ extern "C" int esf_eca_fuse(const esf_view* x_fast, int32_t alpha, const float* 
   dim3 grid(nblk, x_fast->B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int cw = std::min(x_fast->C, kEcaThreads);
-  const int cgs = x_fast->C / 8;
-  if (x_fast->C % 8 == 0 && cgs <= 32 && (cgs & (cgs - 1)) == 0 && vec8_ok(p.x) && vec8_ok(p.y) &&
-      npos < (1LL << 31)) {
+  // 16-byte path: any C <= 256 whose rows are 16-byte addressable and at least ceil8(C) wide (C = 60 / 120 / 240 of
+  // ShuffleNet as well as the powers of two of the R50 models); the ragged last group is stored element-wise
+  const int cgs = (x_fast->C + 7) / 8;
+  if (cgs <= 32 && vec8_ok(p.x) && vec8_ok(p.y) && p.x.sW >= cgs * 8 && npos < (1LL << 31)) {
     eca_partial_vec_kernel<<<grid, kEcaThreads, 0, s>>>(p);
     int rc = check_launch("eca_partial_vec_kernel");
     if (rc != ESF_OK) return rc;
-    eca_apply_vec_kernel<<<grid, kEcaThreads, 3 * x_fast->C * sizeof(float), s>>>(p, nblk);
+    eca_apply_vec_kernel<<<grid, kEcaThreads, 3 * cgs * 8 * sizeof(float), s>>>(p, nblk);
     return check_launch("eca_apply_vec_kernel");
   }
   eca_partial_kernel<<<grid, kEcaThreads, (kEcaThreads / cw) * cw * sizeof(float), s>>>(p);

@@ -474,6 +474,39 @@ def test_eca_fuse(esf_lib, C, alpha):
     assert (ybuf[..., :2 * C] == 0).all()
 
 
+@pytest.mark.parametrize("C,off", [(60, 240), (120, 480), (240, 16), (20, 8), (9, 0)])
+def test_eca_fuse_any_channel_count(esf_lib, C, off):
+    """ECA fuse on the 16-byte path for channel counts that are not powers of two / not multiples of 8 (ShuffleNet's
+    60 / 120 / 240): padded fast rows, output slice of a padded concat buffer; its neighbours stay untouched."""
+    g = torch.Generator().manual_seed(C)
+    B, T, H, W, alpha = 2, 8, 9, 7, 4
+    plan = Plan(DEV, "fp16")
+    x = plan.act(B, T, H, W, C)
+    x.copy_(_rand_act(g, B, T, H, W, C, dtype=torch.float16))
+    bn = torch.nn.BatchNorm3d(C)
+    bn.weight.data = torch.rand(C, generator=g) + 0.5
+    bn.bias.data = torch.rand(C, generator=g) - 0.5
+    bn.running_mean = torch.randn(C, generator=g) * 0.3
+    bn.running_var = torch.rand(C, generator=g) + 0.5
+    bn.eval()
+    wk = torch.rand(1, 1, 3, generator=g) - 0.5
+    xr = _to_ncdhw(x.cpu()).float()
+    f = F.max_pool3d(xr, (alpha, 1, 1), (alpha, 1, 1))
+    s = torch.sigmoid(F.conv1d(f.mean((2, 3, 4)).unsqueeze(1), wk, padding=1).squeeze(1))
+    with torch.no_grad():
+        ref = bn(f * s[:, :, None, None, None]).relu()
+    ybuf = plan.act(B, T // alpha, H, W, off + C + 3)
+    full = next(t for t in reversed(plan.keep) if isinstance(t, torch.Tensor))
+    full.fill_(7.0)
+    y = ybuf[..., off:off + C]
+    plan.eca_fuse(x, y, alpha, wk, bn)
+    plan.launch_all()
+    torch.cuda.synchronize()
+    got = _to_ncdhw(y.cpu()).float()
+    assert (got - ref).abs().max().item() <= 3e-3 * ref.abs().max().item()
+    assert (full[..., :off].float() == 7.0).all() and (full[..., off + C:].float() == 7.0).all()
+
+
 def _attention_reference(proj, B, T, H, W, d, gamma, scale, shift, alpha):
     N = T * H * W
     p = proj.double().reshape(B, N, 4, d)
