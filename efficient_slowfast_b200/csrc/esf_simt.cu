@@ -1181,11 +1181,22 @@ static bool launch_dwconv_tma(const DirectParams& p, cudaStream_t s) {
   if (q.ncols > 256 || q.planes > 256 || q.stage_bytes > 32 * 1024) return false;
   q.stages = std::max(2, std::min(kDwTmaMaxStages, (int)((100 * 1024 - kDwTmaHeader) / q.stage_stride)));
   if (st_env > 0) q.stages = std::max(2, std::min(kDwTmaMaxStages, st_env));
-  q.nseg = cdiv(p.y.H, hs_env > 0 ? hs_env : 16);
-  q.hs = cdiv(p.y.H, q.nseg);
-  q.nseg = cdiv(p.y.H, q.hs);
   q.nwt = cdiv(q.wblocks, wbt), q.ntt = cdiv(p.y.T, tt);
-  q.tiles = (long long)q.nct * p.y.B * q.nseg * q.ntt * q.nwt;
+  // rows per segment: long segments amortise the two halo rows (16 rows: 18 row steps, 32 rows: 34), short ones fill
+  // the last wave of the persistent grid; pick by (useful rows / row steps) x (tiles / tiles rounded up to whole waves)
+  const long long per_seg = (long long)q.nct * p.y.B * q.ntt * q.nwt;
+  const long long wave = (long long)std::max(num_sms(), 1) * 2;
+  double best_hs = -1;
+  for (int target : {16, 32, 56}) {
+    if (hs_env > 0) target = hs_env;
+    const int nseg = cdiv(p.y.H, target), hs = cdiv(p.y.H, nseg);
+    const long long tiles = per_seg * cdiv(p.y.H, hs);
+    const double rows = (double)hs * SW / (hs * SW + (SW == 1 ? 2 : 1));
+    const double waves = (double)tiles / (double)(cdiv((int)std::min<long long>(tiles, 1 << 30), (int)wave) * wave);
+    if (rows * waves > best_hs) best_hs = rows * waves, q.hs = hs;
+  }
+  q.nseg = cdiv(p.y.H, q.hs);
+  q.tiles = per_seg * q.nseg;
   CUtensorMap xmap;
   {
     const int c_map = p.c_real ? p.c_real : p.x.C;   // padding channels of the rows read as zeros
