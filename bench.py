@@ -22,8 +22,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch  # noqa: E402
 
@@ -99,7 +97,7 @@ def case_of(args_or_cfg):
 
 
 def bench_cfg(args):
-    import helpers
+    from efficient_slowfast_b200 import workloads as helpers
 
     cfg = helpers.case_cfg(case_of(args))
     cfg.ESF.BENCH_CASE = case_of(args)
@@ -113,9 +111,9 @@ def bench_cfg(args):
 def build_weights(cfg):
     """Random-init weights of the named architecture, made non-degenerate with the parity recipe (gamma != 0, final
     BN != 0; BN statistics calibrated offline by the reference and shipped as a test fixture)."""
-    import helpers
-    import recipe
     import efficient_slowfast_b200 as esf
+    from efficient_slowfast_b200 import workloads as helpers
+    from efficient_slowfast_b200 import workloads as recipe
 
     name = cfg.ESF.get("BENCH_CASE") or MODEL_CASES[cfg.MODEL.MODEL_NAME]
     c = cfg.clone()
@@ -145,7 +143,7 @@ def workload_name(args):
 # ------------------------------------------------------------------------------------------------ CPU arms
 def cpu_forward_timed(cfg, model, clips, frames, crop, alpha, steps, warmup):
     """Times the CPU oracle (restatement of the reference forward) on `clips` clips per step, all host threads."""
-    import recipe
+    from efficient_slowfast_b200 import workloads as recipe
     from oracle import slowfast_oracle as O
 
     torch.set_num_threads(os.cpu_count() or 1)
@@ -185,65 +183,208 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_gpu(args):
-    import torch.distributed as dist
+# BASELINE.json's other configs, run for a few steps each after the headline when N = 1 (`configs` in the JSON line):
+# (key, model, batch, frames, crop).  configs[0] is the reference's CPU-runnable case; it is run here on the GPU at a
+# batch that fills it.  GhostNet at batch 128 falls back to a smaller batch only if the arena does not fit (reason kept).
+EXTRA_CONFIGS = [
+    ("cfg1_shufflenetv2_w0.5", "SlowFastShuffleNetV2", 64, 32, 224),
+    ("cfg2_slowfast_4x16_r50", "SlowFast", 32, 32, 224),
+    ("cfg4a_ghostnet_w1.0", "SlowFastGhostNet", 128, 32, 224),
+    ("cfg4b_mobilenetv2_w1.0", "SlowFastMoibleNetV2", 128, 32, 224),
+    ("cfg5_shufflenet_w2.0_g3", "SlowFastShuffleNet", 256, 16, 112),
+]
 
-    import recipe
-    from efficient_slowfast_b200 import runtime as rt
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # NCCL writes its version banner (NCCL_DEBUG=VERSION / WARN / INFO) to stdout, next to the ONE JSON line of the
-        # contract: send its log to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+def golden_for(case, frames, crop):
+    """(tag, batch) of the reference-generated golden of `case` whose clip has this shape, or None."""
+    from efficient_slowfast_b200 import workloads as W
 
-    rt.lib()  # fails loudly when the CUDA extension is missing
-    cfg = bench_cfg(args)
-    if args.profile_mode:
-        cfg.ESF.CUDA_GRAPH = False
-    model = build_weights(cfg).to(dev)
-    B, T, S, alpha = args.batch, args.frames, args.crop, args.alpha
-    shapes = [(B, 3, T // alpha, S, S), (B, 3, T, S, S)] if alpha else [(B, 3, T, S, S)]
-    ins = model.input_buffers(shapes, dev)          # plan-owned static inputs (the CUDA graph reads these)
-    plan = model._get_plan(shapes, dev)
+    for tag, b, f, c in W.CASES[case]["inputs"]:
+        if f == frames and c == crop:
+            return tag, b
+    return None
+
+
+def fill_inputs(ins, alpha, rank, dev):
+    """Synthetic N(0,1) clips into the plan's static inputs: the fast clip is drawn, the slow one is its frame subset."""
+    from efficient_slowfast_b200 import workloads as W
+
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     ins[-1].normal_(generator=g)
     if alpha:
-        ins[0].copy_(recipe.pack_pathway_output(ins[1], alpha)[0])
-    K = cfg.MODEL.NUM_CLASSES
+        ins[0].copy_(W.pack_pathway_output(ins[1], alpha)[0])
 
-    from efficient_slowfast_b200 import distributed as esf_dist
 
-    def step():
-        out = model(ins)                            # graph replay; no staging copy (inputs are the static buffers)
-        if world > 1:
-            return esf_dist.all_gather([out])[0]    # the only collective on the path (tools/test_net.py:95-98)
-        return out
+def parity_check(model, ins, case, frames, crop, alpha):
+    """OUTSIDE the timed region: the golden clip of this shape (made by the reference, tests/golden) goes into the
+    first and the last batch slots of the benched static input; both output rows must match the golden (<= 2e-2, the
+    north star's 16-bit tolerance) and each other bit-exactly -- the benched batch size, plan and index paths are the
+    ones being checked.  The slots are refilled with the synthetic clips afterwards."""
+    from efficient_slowfast_b200 import workloads as W
 
-    def barrier():
+    g = golden_for(case, frames, crop)
+    if g is None:
+        return {"skipped": "no reference golden of shape %dx%d^2 for %s" % (frames, crop, case)}
+    tag, gb = g
+    B = ins[0].shape[0]
+    if B < gb:
+        return {"skipped": "batch %d smaller than the golden's %d" % (B, gb)}
+    gold = W.load_golden(case)
+    xs = W.pack_pathway_output(W.seeded_clip(gb, frames, crop, seed=1), alpha)
+    saved = [(t[:gb].clone(), t[B - gb:].clone()) for t in ins]
+    for t, x in zip(ins, xs):
+        t[:gb].copy_(x)
+        t[B - gb:].copy_(x)
+    with torch.no_grad():
+        y = model(ins).float().cpu()
+    torch.cuda.synchronize()
+    for t, (a, b) in zip(ins, saved):
+        t[:gb].copy_(a)
+        t[B - gb:].copy_(b)
+    ref = torch.as_tensor(gold[tag + "/probs"])
+    first, last = y[:gb], y[B - gb:]
+    err = max(W.rel_err(first, ref), W.rel_err(last, ref))
+    same = bool(torch.equal(first, last))
+    argmax_ok = bool(torch.equal(first.argmax(1), ref.argmax(1)) and torch.equal(last.argmax(1), ref.argmax(1)))
+    ok = err <= 2e-2 and same
+    return {"golden": "%s/%s" % (case, tag), "rows": [0, B - gb] if gb == 1 else [[0, gb - 1], [B - gb, B - 1]],
+            "batch": B, "rel_err": err, "tol": 2e-2, "first_equals_last_bitwise": same, "argmax_equal": argmax_ok,
+            "ok": ok}
+
+
+def ncu_traffic(label, batch):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel, from the committed
+    summaries of `ncu --set full` captures (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    for e in json.load(open(p)):
+        if e.get("label") == label and e.get("batch") == batch:
+            return e["dram_bytes_read"] + e["dram_bytes_write"], e.get("source")
+    return None, None
+
+
+class Harness:
+    def __init__(self, args):
+        import torch.distributed as dist
+
+        from efficient_slowfast_b200 import distributed as esf_dist
+
+        self.dist, self.esf_dist = dist, esf_dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.affinity0 = os.sched_getaffinity(0)
+        # pinned clip buffers must live on the GPU's own NUMA node (efficient_slowfast_b200/distributed.py)
+        self.numa = esf_dist.bind_to_gpu_numa_node(self.local_rank) if not args.no_numa_bind else {"skipped": "flag"}
+        if self.world > 1:
+            # NCCL writes its version banner to stdout, next to the ONE JSON line of the contract: send it to stderr
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+            dist.init_process_group("nccl", device_id=self.dev)
+        assert self.world == args.gpus or self.world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+
+    def barrier(self):
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        if self.world > 1:
+            self.dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
+    def timed(self, fn, steps):
+        """ms for `steps` calls of fn: barrier + synchronize on both sides, CUDA events, max over ranks."""
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
         return float(ms.item())
+
+
+def setup_workload(h, args):
+    from efficient_slowfast_b200 import runtime as rt
+
+    rt.lib()  # fails loudly when the CUDA extension is missing
+    cfg = bench_cfg(args)
+    if args.profile_mode:
+        cfg.ESF.CUDA_GRAPH = False
+    model = build_weights(cfg).to(h.dev)
+    B, T, S, alpha = args.batch, args.frames, args.crop, args.alpha
+    shapes = [(B, 3, T // alpha, S, S), (B, 3, T, S, S)] if alpha else [(B, 3, T, S, S)]
+    ins = model.input_buffers(shapes, h.dev)          # plan-owned static inputs (the CUDA graph reads these)
+    plan = model._get_plan(shapes, h.dev)
+    fill_inputs(ins, alpha, h.rank, h.dev)
+    return cfg, model, shapes, ins, plan
+
+
+def run_extra_config(h, base_args, key, model_name, batch, frames, crop):
+    """One of BASELINE.json's other configs: parity check at the benched batch, >= 1 s of timed steps with clocks."""
+    a = argparse.Namespace(**vars(base_args))
+    a.model, a.case, a.batch, a.frames, a.crop = model_name, "", batch, frames, crop
+    a.alpha = 8 if model_name == "SlowFast" else 4
+    a.profile_mode = False
+    note = None
+    while True:
+        try:
+            cfg, model, shapes, ins, plan = setup_workload(h, a)
+            break
+        except torch.cuda.OutOfMemoryError:
+            note = "batch %d does not fit 180 GB (activation arena of one plan); halved" % a.batch
+            model = plan = ins = None
+            torch.cuda.empty_cache()
+            if a.batch <= 8:
+                return {"error": note}
+            a.batch //= 2
+    step = lambda: model(ins)
+    par = parity_check(model, ins, case_of(a), frames, crop, a.alpha)
+    for _ in range(3):
+        step()
+    est = h.timed(step, 2) / 2
+    steps = max(5, int(1000.0 / max(est, 1e-3)) + 1)
+    sampler = ClockSampler(h.local_rank)
+    sampler.start()
+    ms = h.timed(step, steps)
+    clocks = sampler.stop()
+    out = {"workload": workload_name(a), "value": a.batch * steps / (ms * 1e-3), "unit": UNIT, "steps": steps, "warmup": 5,
+           "ms_per_step": ms / steps, "batch": a.batch, "launches_per_step": plan.launches_per_run,
+           "arena_gb": round(plan.arena_bytes() / 1e9, 2), "clocks": clocks, "parity_check": par}
+    if note:
+        out["note"] = note
+    del model, plan, ins
+    torch.cuda.empty_cache()
+    return out
+
+
+def h2d_ceiling(h, nbytes, iters=6):
+    """What the box's host-to-device path gives THIS job layout: every rank copies `nbytes` from pinned host memory to
+    its GPU `iters` times, all ranks at once; aggregate GB/s over the slowest rank."""
+    host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=h.dev)
+    dst.copy_(host, non_blocking=True)
+    ms = h.timed(lambda: dst.copy_(host, non_blocking=True), iters)
+    return h.world * nbytes * iters / (ms * 1e-3) / 1e9
+
+
+def run_gpu(args):
+    from efficient_slowfast_b200 import ClipStream
+    from efficient_slowfast_b200 import workloads as recipe
+
+    h = Harness(args)
+    world, rank, dev, dist = h.world, h.rank, h.dev, h.dist
+    cfg, model, shapes, ins, plan = setup_workload(h, args)
+    B, T, S, alpha = args.batch, args.frames, args.crop, args.alpha
+    K = cfg.MODEL.NUM_CLASSES
+
+    def step():
+        out = model(ins)                            # graph replay; no staging copy (inputs are the static buffers)
+        if world > 1:
+            return h.esf_dist.all_gather([out])[0]  # the only collective on the path (tools/test_net.py:95-98)
+        return out
 
     if args.profile_mode:
         step()
@@ -253,45 +394,54 @@ def run_gpu(args):
         torch.cuda.synchronize()
         print(json.dumps({"profile_mode": True, "launches_per_step": plan.launches_per_run}))
         return
+    parity = parity_check(model, ins, case_of(args), T, S, alpha) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(h.local_rank)
     if rank == 0:
         sampler.start()
-    ms_total = timed(step, args.steps)
+    ms_total = h.timed(step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # ---- end-to-end through the public API with pinned host inputs (H2D + forward + D2H per step)
+    # ClipStream = the package's public host-side loop: per batch H2D from pinned memory -> model.forward ->
+    # (all_gather) -> D2H, with the copy of batch i+1 overlapping the forward of batch i.  The caller hands over the
+    # reference loader's [slow, fast] pair; slow_from_fast=True (verified on the first batch) uploads the fast clip only
+    # and the slow pathway reads its frames out of it -- `e2e_both_pathways_uploaded` is the same loop without that.
     host = [torch.empty(s, dtype=torch.float32).pin_memory() for s in shapes]
     host[-1].normal_()
     if alpha:
         host[0].copy_(recipe.pack_pathway_output(host[1], alpha)[0])
-    host_out = torch.empty(B, K, dtype=torch.float32).pin_memory()
-
-    # ClipStream = the package's public host-side loop: per batch H2D from pinned memory -> model.forward ->
-    # (all_gather) -> D2H, with the copy of batch i+1 overlapping the forward of batch i (double-buffered staging).
-    from efficient_slowfast_b200 import ClipStream
-    stream = ClipStream(model, shapes, dev, depth=2, gather=world > 1)
     e2e_steps = max(2, args.e2e_steps if args.e2e_steps > 0 else args.steps)
 
-    def e2e_run():
-        got = 0
-        for _ in range(e2e_steps):
-            got += stream.submit(host) is not None
-        got += len(stream.flush())
-        assert got == e2e_steps
+    def e2e_measure(**kw):
+        stream = ClipStream(model, shapes, dev, depth=args.e2e_depth, gather=world > 1, **kw)
 
-    stream.submit(host)
-    stream.flush()
-    ms_e2e = timed(e2e_run, 1)
-    e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
-    h2d = stream.h2d_bytes
-    d2h = host_out.numel() * 4 * world
+        def run():
+            got = 0
+            for _ in range(e2e_steps):
+                got += stream.submit(host) is not None
+            got += len(stream.flush())
+            assert got == e2e_steps
+
+        stream.submit(host)
+        stream.flush()
+        ms = h.timed(run, 1)
+        return {"value": world * B * e2e_steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": stream.h2d_bytes,
+                "d2h_bytes_per_step": B * K * 4 * world, "steps": e2e_steps, "ms_per_step": ms / e2e_steps}
+
+    e2e = e2e_measure(slow_from_fast=bool(alpha) and hasattr(model, "forward_fast"))
+    e2e["input"] = "pinned FP32 [slow, fast] host clips; the fast clip is copied, slow = its frame subset (verified)" \
+        if alpha else "pinned FP32 host clip"
+    e2e_both = e2e_measure() if alpha else None
+    ceiling = h2d_ceiling(h, e2e["h2d_bytes_per_step"])
+    e2e["h2d_ceiling_gbs"] = ceiling
+    e2e["h2d_achieved_gbs"] = world * e2e["h2d_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9
+    e2e["numa_bind"] = h.numa
 
     # ---- the same loop fed with the decoder's uint8 frames: model.forward_frames does the reference
     # loader's normalisation + pathway packing on the device; extra information, `e2e` above stays the FP32 contract
-    del stream
     e2e_u8 = None
     if hasattr(model, "forward_frames"):
         fshape = (B, T, S, S, 3)
@@ -307,11 +457,12 @@ def run_gpu(args):
 
         fstream.submit([hostf])
         fstream.flush()
-        ms_u8 = timed(e2e_frames_run, 1)
+        ms_u8 = h.timed(e2e_frames_run, 1)
         e2e_u8 = {"value": world * B * e2e_steps / (ms_u8 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": fstream.h2d_bytes,
-                  "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_u8 / e2e_steps,
+                  "d2h_bytes_per_step": B * K * 4 * world, "steps": e2e_steps, "ms_per_step": ms_u8 / e2e_steps,
                   "input": "uint8 frames (B,T,H,W,C) through model.forward_frames"}
-        del fstream
+        del fstream, hostf
+    del host
 
     # ---- per-kernel device times (CUDA events, eager launches of the same plan) and the roofline of the top kernel
     pk = peaks()
@@ -338,12 +489,8 @@ def run_gpu(args):
     else:
         ach = top["bytes"] / (top_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"]}
-    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
-    # `ncu --set full` capture of this command at the default workload (profiles/r1_ncu_bench_attention_d32_b64.md)
-    traffic = None
-    if top["kind"] == "attention" and top["label"] == "N=25088 d=32" and B == 64:
-        traffic = 772445184 + 390810112
-    roof.update({"traffic": traffic, "algorithmic_bytes": top["bytes"],
+    traffic, traffic_src = ncu_traffic("%s %s" % (top["kind"], top["label"]), B)
+    roof.update({"traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": top["bytes"],
                  "kernel": "%s %s" % (top["kind"], top["label"]), "ms": top_ms,
                  "share_of_step": top_ms / total_ms, "peak_source": pk["_source"]})
     if top["exps"]:
@@ -367,6 +514,7 @@ def run_gpu(args):
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample (rank 0, N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, h.affinity0)      # all host cores again (the NUMA binding was for the pinned buffers)
         cv, csec = cpu_forward_timed(cfg, model, args.cpu_clips, T, S, alpha, steps=1, warmup=1)
         cpu = {"value": cv, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": "%d clip(s) of the same workload, 1 warm-up + 1 timed oracle forward (%.1f s)" % (
@@ -377,18 +525,30 @@ def run_gpu(args):
         "scaling": "weak", "vs_baseline": None, "dtype": str(cfg.ESF.PRECISION), "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": world * B, "parallelism": "dp%d" % world,
                    "l2": "inputs (1.54 GB per step) and activations (>20 GB) exceed the 126 MB L2",
-                   "cuda_graph": True, "weights": "random init + parity recipe (tests/golden/recipe.py)"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+                   "cuda_graph": True, "arena_gb": round(plan.arena_bytes() / 1e9, 2),
+                   "weights": "random init + parity recipe (efficient_slowfast_b200/workloads.py); no trained "
+                              "checkpoint is available offline"},
+        "e2e": e2e,
         "gpu_launches": plan.launches_per_run * args.steps,
         "launches_per_step": plan.launches_per_run,
-        "clocks": clocks, "roofline": roof, "kernel_breakdown": breakdown,
+        "clocks": clocks, "parity_check": parity, "roofline": roof, "kernel_breakdown": breakdown,
         "eager_sum_ms": round(total_ms, 3),
     }
+    if e2e_both:
+        line["e2e_both_pathways_uploaded"] = e2e_both
     if e2e_u8:
         line["e2e_uint8_frames"] = e2e_u8
     if cpu:
         line["cpu_baseline"] = cpu
+    if world == 1 and not args.no_extra_configs and not args.case and args.model == "SlowFastDualAttention":
+        del model, plan, ins
+        torch.cuda.empty_cache()
+        line["configs"] = {}
+        for key, name, b, f, c in EXTRA_CONFIGS:
+            try:
+                line["configs"][key] = run_extra_config(h, args, key, name, b, f, c)
+            except Exception as e:  # noqa: BLE001 -- the headline line must still be printed
+                line["configs"][key] = {"error": "%s: %s" % (type(e).__name__, e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -412,13 +572,16 @@ def main():
     ap.add_argument("--dump-ops", default="", help="write per-op device times (JSON lines) to this file")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
                     help="16-bit storage / tensor-core operand format (FP32 accumulation in both)")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="staging slots of the end-to-end ClipStream")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="skip the short runs of BASELINE.json's other configs (`configs` in the JSON line)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for ncu: eager launches (no CUDA graph), 1 warm-up + --steps steps, nothing else")
     args = ap.parse_args()
     args.alpha = 8 if args.model == "SlowFast" else 4
     if args.case:
-        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-        import recipe
+        from efficient_slowfast_b200 import workloads as recipe
         spec = recipe.CASES[args.case]
         args.model = spec["model"]
         if spec.get("single"):

@@ -5,6 +5,7 @@ state uses the same keys as this package's modules (tests/test_oracle_vs_referen
 (checkpoint.py:290-324).  Caffe2 `.pkl` checkpoints (the model zoo's format: `{"blobs": {caffe2 name: ndarray}}`,
 checkpoint.py:206-259) are converted by name (`caffe2_to_pytorch_name`, same mapping as utils/c2_model_loading.py).
 2D->3D inflation is a training-time feature and not built."""
+import os
 import pickle
 import re
 
@@ -102,10 +103,21 @@ def _normalise_keys(state):
     return out
 
 
-def load_checkpoint(path_to_checkpoint, model, data_parallel=False, strict=False, convert_from_caffe2=False):
-    """Loads `model_state` into `model` (or `model.module` when `data_parallel`); returns the stored epoch or -1
-    (always -1 for a Caffe2 file, as in the reference).  Changing the weights invalidates the model's compiled launch
-    plans (they fold BN into the packed weights)."""
+def load_checkpoint(path_to_checkpoint, model, data_parallel=True, optimizer=None, inflation=False,
+                    convert_from_caffe2=False, *, strict=False):
+    """utils/checkpoint.py:178-285 of the reference, same positional order, names and defaults (its call sites pass
+    `load_checkpoint(path, model, cfg.NUM_GPUS > 1, None, inflation=False, convert_from_caffe2=...)`).  Loads
+    `model_state` into `model.module` when `data_parallel` (the DDP wrapper, as in the reference: a bare model with
+    data_parallel=True raises AttributeError there too) else into `model`; restores `optimizer` from
+    `optimizer_state` when given; returns the stored epoch or -1 (always -1 for a Caffe2 file).  `inflation`
+    (2D -> 3D weight inflation, a fine-tuning feature) is out of scope and raises.  `strict` is keyword-only and not
+    part of the reference signature (the reference always loads with strict=False).  Changing the weights invalidates
+    the model's compiled launch plans (they fold BN into the packed weights)."""
+    if not os.path.exists(path_to_checkpoint):
+        raise AssertionError("Checkpoint '{}' not found".format(path_to_checkpoint))
+    if inflation:
+        raise NotImplementedError("inflation of 2D checkpoints (utils/checkpoint.py:271-276) is a training-time feature "
+                                  "outside the forward path")
     target = model.module if data_parallel else model
     if convert_from_caffe2:
         with open(path_to_checkpoint, "rb") as f:
@@ -121,6 +133,8 @@ def load_checkpoint(path_to_checkpoint, model, data_parallel=False, strict=False
     missing, unexpected = target.load_state_dict(_normalise_keys(state), strict=strict)
     if hasattr(target, "invalidate_plans"):
         target.invalidate_plans()
+    if optimizer:
+        optimizer.load_state_dict(ckpt["optimizer_state"])
     load_checkpoint.last_report = {"missing": list(missing), "unexpected": list(unexpected)}
     return int(ckpt.get("epoch", -1)) if isinstance(ckpt, dict) else -1
 

@@ -103,17 +103,20 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
 // GEMM block starts 16-byte aligned).  One thread per 8 consecutive output elements (one 16 B store).
 template <int CIN>   // channel count at compile time (0: run-time Cin_rt) -- the per-element division is the hot loop
 __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x, int B, int Cin_rt, int T, int H, int W,
-                                                        int pitch, int lpad, int f16, __nv_bfloat16* __restrict__ xp) {
+                                                        int pitch, int lpad, int f16, __nv_bfloat16* __restrict__ xp,
+                                                        int Tsrc, const int32_t* __restrict__ t_index) {
   // block = 128 chunk lanes x 2 rows; one (b, t, h) row per threadIdx.y, decomposed once with 32-bit arithmetic
   const int Cin = CIN ? CIN : Cin_rt;
   const int chunks = pitch / 8;
   const long long nrows = (long long)B * T * H;
-  const long long plane = (long long)T * H * W;
+  // frame gather (esf_stem_pack_gather): output frame t reads source frame t_index[t] of a clip with Tsrc frames
+  const long long plane = (long long)Tsrc * H * W;
   for (long long row = blockIdx.x * 2LL + threadIdx.y; row < nrows; row += 2LL * gridDim.x) {
     const int h = (int)(row % H);
     const int bt = (int)(row / H);
     const int t = bt % T, b = bt / T;
-    const float* xrow = x + (long long)b * Cin * plane + ((long long)t * H + h) * W;   // channel 0 of this row
+    const int ts = t_index ? __ldg(t_index + t) : t;
+    const float* xrow = x + (long long)b * Cin * plane + ((long long)ts * H + h) * W;   // channel 0 of this row
     __nv_bfloat16* orow = xp + row * pitch;
     for (int ck = threadIdx.x; ck < chunks; ck += blockDim.x) {
       float v[8];
@@ -2014,20 +2017,33 @@ extern "C" int esf_stem_conv(const float* x, int32_t B, int32_t Cin, int32_t T, 
   return check_launch("stem_conv_kernel");
 }
 
-extern "C" int esf_stem_pack(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
-                             int32_t lpad, int32_t dtype, void* xp, void* stream) {
-  ESF_CHECK_ARG(is16(dtype), "esf_stem_pack: dtype must be BF16 or F16");
-  ESF_CHECK_ARG(x && xp && B > 0 && Cin > 0 && T > 0 && H > 0 && W > 0, "esf_stem_pack: null/bad argument");
-  ESF_CHECK_ARG(pitch % 8 == 0 && pitch >= lpad + W * Cin, "esf_stem_pack: bad pitch %d", pitch);
+static int stem_pack_launch(const char* who, const float* x, int32_t B, int32_t Cin, int32_t Tsrc, int32_t H, int32_t W,
+                            const int32_t* t_index, int32_t T, int32_t pitch, int32_t lpad, int32_t dtype, void* xp,
+                            void* stream) {
+  ESF_CHECK_ARG(is16(dtype), "%s: dtype must be BF16 or F16", who);
+  ESF_CHECK_ARG(x && xp && B > 0 && Cin > 0 && T > 0 && Tsrc > 0 && H > 0 && W > 0, "%s: null/bad argument", who);
+  ESF_CHECK_ARG(pitch % 8 == 0 && pitch >= lpad + W * Cin, "%s: bad pitch %d", who, pitch);
   const long long nrows = (long long)B * T * H;
   const unsigned grid = (unsigned)std::max(1LL, std::min((nrows + 1) / 2, 148LL * 64));
   if (Cin == 3)
     stem_pack_kernel<3><<<grid, dim3(128, 2), 0, static_cast<cudaStream_t>(stream)>>>(
-        x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp));
+        x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp), Tsrc, t_index);
   else
     stem_pack_kernel<0><<<grid, dim3(128, 2), 0, static_cast<cudaStream_t>(stream)>>>(
-        x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp));
+        x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp), Tsrc, t_index);
   return check_launch("stem_pack_kernel");
+}
+
+extern "C" int esf_stem_pack(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
+                             int32_t lpad, int32_t dtype, void* xp, void* stream) {
+  return stem_pack_launch("esf_stem_pack", x, B, Cin, T, H, W, nullptr, T, pitch, lpad, dtype, xp, stream);
+}
+
+extern "C" int esf_stem_pack_gather(const float* x, int32_t B, int32_t Cin, int32_t Tsrc, int32_t H, int32_t W,
+                                    const int32_t* t_index, int32_t T, int32_t pitch, int32_t lpad, int32_t dtype,
+                                    void* xp, void* stream) {
+  ESF_CHECK_ARG(t_index != nullptr, "esf_stem_pack_gather: t_index is null");
+  return stem_pack_launch("esf_stem_pack_gather", x, B, Cin, Tsrc, H, W, t_index, T, pitch, lpad, dtype, xp, stream);
 }
 
 static int frames_params(FramesParams* p, const uint8_t* frames, int32_t B, int32_t Tsrc, int32_t H, int32_t W, int32_t C,

@@ -17,20 +17,34 @@ from . import runtime as rt
 BN_EPS_DEFAULT = 1e-5
 
 
+def host64(t):
+    """Parameter / buffer -> FP64 tensor on the HOST.  All weight preparation (BN folding, composition of 1x1x1 convs,
+    packing into the kernels' layouts) is plan-build-time work on a few MB and runs on the CPU: one D2H copy per
+    parameter and one H2D copy per packed tensor, no element-wise GPU launches -- the first kernels a process launches
+    are the forward path's own (the round-1 build issued > 1 000 tiny FP64 ATen kernels per plan)."""
+    return t.detach().cpu().to(torch.float64)
+
+
+def to_device(t, device, dtype):
+    """Host tensor -> contiguous device tensor of `dtype`; the conversion happens on the host."""
+    return t.detach().to(dtype).contiguous().to(device)
+
+
 def bn_affine(bn):
-    """Eval-mode BatchNorm as y = x * scale + shift (FP64 math, FP32 result)."""
-    w = bn.weight.detach().double() if bn.weight is not None else torch.ones_like(bn.running_var).double()
-    b = bn.bias.detach().double() if bn.bias is not None else torch.zeros_like(bn.running_var).double()
-    scale = w / torch.sqrt(bn.running_var.detach().double() + bn.eps)
-    shift = b - bn.running_mean.detach().double() * scale
+    """Eval-mode BatchNorm as y = x * scale + shift (FP64 math on the host)."""
+    var = host64(bn.running_var)
+    w = host64(bn.weight) if bn.weight is not None else torch.ones_like(var)
+    b = host64(bn.bias) if bn.bias is not None else torch.zeros_like(var)
+    scale = w / torch.sqrt(var + bn.eps)
+    shift = b - host64(bn.running_mean) * scale
     return scale, shift
 
 
 def fold_conv_bn(weight, conv_bias, bn):
     """(Cout,Cin/g,kT,kH,kW) conv weight (+ optional bias) followed by eval BN -> folded FP64 weight and bias."""
-    w = weight.detach().double()
+    w = host64(weight)
     cout = w.shape[0]
-    b = conv_bias.detach().double() if conv_bias is not None else torch.zeros(cout, dtype=torch.float64, device=w.device)
+    b = host64(conv_bias) if conv_bias is not None else torch.zeros(cout, dtype=torch.float64)
     if bn is not None:
         scale, shift = bn_affine(bn)
         w = w * scale.view(-1, 1, 1, 1, 1)
@@ -48,8 +62,7 @@ def pack_igemm_weight(w, bias, device, dtype=torch.bfloat16):
     wp[:cout, :, :cin] = w.permute(0, 2, 3, 4, 1).reshape(cout, kt * kh * kw, cin)
     bp = torch.zeros(n_pad, dtype=torch.float64, device=w.device)
     bp[:cout] = bias
-    return (wp.reshape(n_pad, -1).to(device=device, dtype=dtype).contiguous(),
-            bp.to(device=device, dtype=torch.float32).contiguous())
+    return to_device(wp.reshape(n_pad, -1), device, dtype), to_device(bp, device, torch.float32)
 
 
 STEM_WB = 8  # output columns per banded-GEMM block (csrc/esf_igemm.cu kStemWB)
@@ -71,8 +84,7 @@ def pack_stem_band(w, bias, stride_w, device, dtype=torch.bfloat16):
         band[i * cout:(i + 1) * cout, :, j0:j0 + kw * cin] = wt.reshape(cout, kt * kh, kw * cin)
     bt = torch.zeros(n_pad, dtype=torch.float64, device=w.device)
     bt[:N] = bias.repeat(STEM_WB)
-    return (band.reshape(n_pad, -1).to(device=device, dtype=dtype).contiguous(),
-            bt.to(device=device, dtype=torch.float32).contiguous())
+    return to_device(band.reshape(n_pad, -1), device, dtype), to_device(bt, device, torch.float32)
 
 
 def pack_wfold_band(w, bias, WB, stride_w, device, dtype=torch.bfloat16):
@@ -92,8 +104,7 @@ def pack_wfold_band(w, bias, WB, stride_w, device, dtype=torch.bfloat16):
         band[i * cout:(i + 1) * cout, :, j0:j0 + kw * cin] = wt
     bt = torch.zeros(n_pad, dtype=torch.float64, device=w.device)
     bt[:N] = bias.repeat(WB)
-    return (band.reshape(n_pad, -1).to(device=device, dtype=dtype).contiguous(),
-            bt.to(device=device, dtype=torch.float32).contiguous())
+    return to_device(band.reshape(n_pad, -1), device, dtype), to_device(bt, device, torch.float32)
 
 
 def wfold_block(x, y, res, w_shape, stride, padding, dilation):
@@ -141,6 +152,8 @@ class Plan:
         self.eager = []       # per op: launched outside the CUDA graph (reads a caller-provided input tensor)
         self.input_override = {}   # plan-owned input data_ptr -> data_ptr of the caller's tensor for this run
         self.stem_routes = {}      # plan-owned input data_ptr -> (packed stem rows, pitch, lpad) of a banded stem
+        self.gather = {}           # plan-owned input data_ptr -> (source clip ptr, its frame count, device int32 frame
+                                   # index ptr): this run packs the pathway out of ANOTHER clip's frames (slow from fast)
         self.padded = {}           # data_ptr of a channel-padded activation -> (logical C, padded C)
         self.handles = []     # esf_op* to destroy
         self.graph = None
@@ -167,8 +180,23 @@ class Plan:
             self.buffers[name] = t
         return t
 
+    def arena_bytes(self):
+        """Device bytes this plan keeps alive (activations, packed weights, scratch, static inputs)."""
+        seen, total = set(), 0
+        for t in list(self.keep) + list(getattr(self, "inputs", [])):
+            if isinstance(t, torch.Tensor) and t.device.type == "cuda":
+                st = t.untyped_storage()
+                if st.data_ptr() not in seen:
+                    seen.add(st.data_ptr())
+                    total += st.nbytes()
+        return total
+
     def tensor(self, t, dtype=torch.float32):
-        t = t.detach().to(device=self.device, dtype=dtype).contiguous()
+        """Plan-lifetime device copy of a (small) parameter-derived tensor; host tensors are converted on the host."""
+        if t.device.type == "cpu":
+            t = to_device(t, self.device, dtype)
+        else:
+            t = t.detach().to(device=self.device, dtype=dtype).contiguous()
         self.keep.append(t)
         return t
 
@@ -259,7 +287,7 @@ class Plan:
         f64 = torch.float64
 
         def wb(conv):
-            return conv.weight.detach().to(f64), conv.bias.detach().to(f64)
+            return host64(conv.weight), host64(conv.bias)
 
         if nln.use_pool:
             ps = [int(v) for v in nln.pool_size]
@@ -277,14 +305,14 @@ class Plan:
         # amplified by |mean| / std.  conv_out is linear, so a per-channel offset mu can be subtracted in the FP32
         # epilogue of the last product (its bias) and added back through conv_out's bias: W (att - mu) + (W mu + b).
         # mu = least-squares solution of W mu = running_mean - b, the att-space mean the BN statistics imply.
-        w_out = nln.conv_out.weight.detach().to(f64).reshape(C, d)
-        rhs = (nln.bn.running_mean.detach().to(f64) - nln.conv_out.bias.detach().to(f64)).reshape(C, 1)
-        mu = torch.linalg.lstsq(w_out.cpu(), rhs.cpu()).solution.reshape(d).to(w_out.device)
+        w_out = host64(nln.conv_out.weight).reshape(C, d)
+        rhs = (host64(nln.bn.running_mean) - host64(nln.conv_out.bias)).reshape(C, 1)
+        mu = torch.linalg.lstsq(w_out, rhs).solution.reshape(d)
         _, _, _, npad_d = rt.igemm_geometry(Nk if softmax else d, d)
-        bias2 = torch.zeros(npad_d, dtype=torch.float32, device=self.device)
-        bias2[:d] = (-mu).to(torch.float32)
-        mu = -bias2[:d].to(f64).to(w_out.device)     # the value actually subtracted (FP32-rounded)
-        self.keep.append(bias2)
+        bias2_h = torch.zeros(npad_d, dtype=torch.float32)
+        bias2_h[:d] = (-mu).to(torch.float32)
+        mu = -bias2_h[:d].to(f64)                    # the value actually subtracted (FP32-rounded)
+        bias2 = self.tensor(bias2_h)
         att = self.act(B, T, H, W, d)
 
         def transposed(t, name):
@@ -345,7 +373,7 @@ class Plan:
             self.gemm_rows(gT_act, MT, phiT, zero_d, "nl_gemm", "g^T.phi d=%d Nk=%d" % (d, Nk))
             self.gemm_rows(theta, att, MT.reshape(B, d, d), bias2, "nl_gemm", "theta.M N=%d d=%d" % (Nq, d))
         w, bias = fold_conv_bn(nln.conv_out.weight, nln.conv_out.bias, nln.bn)
-        bias = bias + w.reshape(C, d) @ mu.to(w.device)
+        bias = bias + w.reshape(C, d) @ mu
         self.conv(att, y, w, bias, res=x)
 
     def conv_wfold(self, x, y, w_folded, bias, WB, stride=(1, 1, 1), padding=(0, 0, 0), act=rt.ACT_NONE, res=None):
@@ -505,9 +533,17 @@ class Plan:
         self.handles.append(h)
         m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
         self.stem_routes[x_nc.data_ptr()] = (xp, pitch, lpad)   # the uint8 frame route writes xp itself (frames.py)
-        self._add(lambda s: rt.check(L.esf_stem_pack(self._in_ptr(x_nc), B, Cin, T, H, W, pitch, lpad, self.a16,
-                                                     xp.data_ptr(), s),
-                                     "esf_stem_pack"), "stem_pack", "", nbytes=self._nbytes(x_nc, xp), eager=True)
+        def pack(s):
+            g = self.gather.get(x_nc.data_ptr())
+            if g is not None:       # frames of this pathway are read out of another pathway's clip (slow from fast)
+                src, tsrc, idx = g
+                rt.check(L.esf_stem_pack_gather(src, B, Cin, tsrc, H, W, idx, T, pitch, lpad, self.a16, xp.data_ptr(), s),
+                         "esf_stem_pack_gather")
+            else:
+                rt.check(L.esf_stem_pack(self._in_ptr(x_nc), B, Cin, T, H, W, pitch, lpad, self.a16, xp.data_ptr(), s),
+                         "esf_stem_pack")
+
+        self._add(pack, "stem_pack", "", nbytes=self._nbytes(x_nc, xp), eager=True)
         self.meta[-1]["is_pack"] = True
         self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "stem_igemm",
                   "%dx%dx%d %d->%d banded" % (kt, kh, kw, Cin, cout), flops=2.0 * m * cout * Cin * kt * kh * kw,
@@ -598,14 +634,14 @@ class Plan:
         flash-style attention + gamma*O + x + BN + ReLU + x alpha upsample + concat
         (custom_video_model_builder.py:141-146, wdf_attention_helper.py:33-54)."""
         B, T, H, W, C = x_slow.shape
-        wd = w_down.detach().double().reshape(w_down.shape[0], C)            # (d, C)
+        wd = host64(w_down).reshape(w_down.shape[0], C)                      # (d, C)
         d = wd.shape[0]
-        mats, biases = [wd], [torch.zeros(d, dtype=torch.float64, device=wd.device)]
+        mats, biases = [wd], [torch.zeros(d, dtype=torch.float64)]
         for conv in (att.query_conv, att.key_conv, att.value_conv):
-            wc = conv.weight.detach().double().reshape(conv.weight.shape[0], d)
+            wc = host64(conv.weight).reshape(conv.weight.shape[0], d)
             assert wc.shape[0] == d, "SpatialAttention reduction != 1 is not used by any registered model"
             mats.append(wc @ wd)
-            biases.append(conv.bias.detach().double())
+            biases.append(host64(conv.bias))
         w_all = torch.cat(mats, 0).reshape(4 * d, C, 1, 1, 1)
         b_all = torch.cat(biases, 0)
         proj = self.act(B, T, H, W, 4 * d, dtype=torch.float32)
@@ -805,12 +841,19 @@ class Plan:
             self.graph.replay()
         return self.out
 
-    def run(self, inputs=None):
+    def run(self, inputs=None, gather=None):
         """`inputs`: optional caller tensors to read INSTEAD of the plan-owned input buffers (same shape, FP32,
-        contiguous, same device) -- saves the device-to-device staging copy."""
+        contiguous, same device; None entries keep the plan's buffer) -- saves the device-to-device staging copy.
+        `gather`: {pathway: (source clip tensor, device int32 frame index)} -- that pathway's banded stem packs its rows
+        out of the source clip's frames (Plan.stem / esf_stem_pack_gather)."""
         self.input_override = {}
         if inputs is not None:
-            self.input_override = {own.data_ptr(): src.data_ptr() for own, src in zip(self.inputs, inputs)}
+            self.input_override = {own.data_ptr(): src.data_ptr() for own, src in zip(self.inputs, inputs)
+                                   if src is not None}
+        self.gather = {}
+        for pw, (src, idx) in (gather or {}).items():
+            assert self.inputs[pw].data_ptr() in self.stem_routes
+            self.gather[self.inputs[pw].data_ptr()] = (src.data_ptr(), src.shape[2], idx.data_ptr())
         try:
             if self.graph is not None:
                 self.launch_eager_ops()
@@ -819,6 +862,7 @@ class Plan:
                 self.launch_all()
         finally:
             self.input_override = {}
+            self.gather = {}
         return self.out
 
     def __del__(self):

@@ -9,6 +9,8 @@ arithmetic is not in these modules: `forward([slow, fast])` compiles (once per i
 hand-written sm_100a kernels (engine.py, csrc/) and replays it.  Eval mode only -- the training path (batch-stat BN,
 autograd) is outside the hot path this package accelerates and raises.
 """
+import collections
+import itertools
 import math
 
 import torch
@@ -264,34 +266,56 @@ class _PlannedModel(nn.Module):
 
     def _init_runtime(self, cfg):
         self._cfg = cfg
-        self._plans = {}
-        self._use_graph = bool(cfg.get("ESF", {}).get("CUDA_GRAPH", True)) if hasattr(cfg, "get") else True
+        self._plans = collections.OrderedDict()     # (shapes, device) -> (weights stamp, Plan), least recently used first
+        esf = cfg.get("ESF", {}) if hasattr(cfg, "get") else {}
+        self._use_graph = bool(esf.get("CUDA_GRAPH", True))
+        # live plans kept per model: the activation arena of a plan is large (25 GB at batch 64), but a test loader
+        # alternates between the full batch and a short last one, and the demo between window and batch shapes
+        self._max_plans = max(1, int(esf.get("MAX_PLANS", 2)))
 
     def _weights_stamp(self):
-        s = 0
-        for t in list(self.parameters()) + list(self.buffers()):
-            s += t._version + (t.data_ptr() & 0xFFFF)
-        return s
+        """Identity of the weights a plan was compiled from: (storage address, version counter) of every parameter
+        and buffer.  In-place edits through autograd-visible ops and load_state_dict bump the version; edits through
+        `.data` / `.detach()` views do NOT (PyTorch gives them no counter) -- call invalidate_plans() after those
+        (load_state_dict / .to() / .cuda() do it themselves)."""
+        return hash(tuple((t.data_ptr(), t._version) for t in itertools.chain(self.parameters(), self.buffers())))
 
     def invalidate_plans(self):
-        self._plans = {}
+        self._plans.clear()
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_plans()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "_plans"):
+            self.invalidate_plans()
+        return out
 
     def _get_plan(self, shapes, device):
         key = (tuple(tuple(s) for s in shapes), str(device))
         stamp = self._weights_stamp()
         ent = self._plans.get(key)
         if ent is not None and ent[0] == stamp:
+            self._plans.move_to_end(key)
             return ent[1]
+        if ent is not None or any(st != stamp for st, _ in self._plans.values()):
+            self._plans.clear()                      # the weights changed: every compiled plan is stale
         prec = "fp16"
         if hasattr(self._cfg, "get") and self._cfg.get("ESF") is not None:
             prec = str(self._cfg.ESF.get("PRECISION", "fp16"))
-        plan = Plan(device, precision=prec)
-        plan.inputs = [torch.empty(s, dtype=torch.float32, device=device) for s in shapes]
-        with torch.no_grad():
-            self._compile(plan)
-        if self._use_graph:
-            plan.capture()
-        self._plans = {key: (stamp, plan)}  # one live plan: activation arenas are large
+        while len(self._plans) >= self._max_plans:
+            self._plans.popitem(last=False)          # frees the arena of the least recently used shape
+        with torch.cuda.device(device):
+            plan = Plan(device, precision=prec)
+            plan.inputs = [torch.empty(s, dtype=torch.float32, device=device) for s in shapes]
+            with torch.no_grad():
+                self._compile(plan)
+            if self._use_graph:
+                plan.capture()
+        self._plans[key] = (stamp, plan)
         return plan
 
     def input_buffers(self, shapes, device=None):
@@ -315,12 +339,46 @@ class _PlannedModel(nn.Module):
         # FP32 contiguous clips are read in place by the stem kernels (launched outside the CUDA graph); anything else
         # (other dtype / strides) is first converted into the plan-owned input buffers
         direct = all(t.dtype == torch.float32 and t.is_contiguous() and t.data_ptr() % 16 == 0 for t in x)
-        if not direct:
-            for src, dst in zip(x, plan.inputs):
-                if src.data_ptr() != dst.data_ptr():
-                    dst.copy_(src, non_blocking=True)
-        out = plan.run(list(x) if direct else None)
-        return out.clone()
+        with torch.cuda.device(dev):     # launches go to the tensors' device and ITS current stream
+            if not direct:
+                for src, dst in zip(x, plan.inputs):
+                    if src.data_ptr() != dst.data_ptr():
+                        dst.copy_(src, non_blocking=True)
+            out = plan.run(list(x) if direct else None)
+            return out.clone()
+
+    def forward_fast(self, fast, bboxes=None):
+        """Same result as `forward(pack_pathway_output(cfg, fast))`: the loader's pack_pathway_output
+        (SlowFast/slowfast/datasets/utils.py:93-102) makes the slow clip out of the
+        `linspace(0, T-1, T // ALPHA).long()` frames of the fast clip, i.e. the same pixels a second time (20 % of the
+        host-to-device bytes of a batch).  Here only the fast clip (B, C, T, H, W) FP32 is given; the slow pathway's
+        stem packs its rows straight out of those frames (esf_stem_pack_gather), so the slow clip is neither uploaded
+        nor materialised.  Stems without the packed-row route gather on the device into the plan's slow input."""
+        if self.num_pathways != 2:
+            raise rt.EsfError("forward_fast is for the two-pathway models")
+        if self.training:
+            raise NotImplementedError("eval-mode forward path only")
+        if bboxes is not None:
+            raise NotImplementedError("detection (bboxes) is out of scope")
+        dev = fast.device
+        if dev.type != "cuda":
+            raise rt.EsfError("the forward path is CUDA-only (sm_100a); got tensors on %s -- there is no CPU fallback"
+                              % dev)
+        if fast.dtype != torch.float32 or fast.dim() != 5 or not fast.is_contiguous() or fast.data_ptr() % 16:
+            raise rt.EsfError("forward_fast expects a contiguous FP32 clip (B, C, T, H, W)")
+        B, C, T, H, W = fast.shape
+        alpha = self._cfg.SLOWFAST.ALPHA
+        plan = self._get_plan([(B, C, T // alpha, H, W), (B, C, T, H, W)], dev)
+        idx = getattr(plan, "slow_index", None)
+        if idx is None:
+            idx = plan.slow_index = torch.linspace(0, T - 1, T // alpha).long().to(torch.int32).to(dev)
+        with torch.cuda.device(dev):
+            if plan.inputs[0].data_ptr() in plan.stem_routes:
+                out = plan.run([None, fast], gather={0: (fast, idx)})
+            else:
+                torch.index_select(fast, 2, idx.long(), out=plan.inputs[0])
+                out = plan.run([None, fast])
+            return out.clone()
 
     def frame_shapes(self, frames_shape):
         """[slow, fast] (or [single]) clip shapes that pack_pathway_output (datasets/utils.py:73-112) makes of uint8
@@ -355,8 +413,9 @@ class _PlannedModel(nn.Module):
         if fin is None:
             fin = plan.frame_input = esf_frames.FrameInput(self._cfg, dev, plan.adt, channels=frames.shape[4])
         alpha = self._cfg.SLOWFAST.ALPHA if self.num_pathways > 1 else 1
-        out = plan.run_frames(lambda: esf_frames.launch_frames(plan, fin, frames, alpha, frame_index))
-        return out.clone()
+        with torch.cuda.device(dev):
+            out = plan.run_frames(lambda: esf_frames.launch_frames(plan, fin, frames, alpha, frame_index))
+            return out.clone()
 
     def _emit_fuse(self, plan, fuse, cur):
         (sbuf, soff, cs), (fbuf, foff, cf) = cur
@@ -376,7 +435,7 @@ class _PlannedModel(nn.Module):
 
     def debug_buffers(self):
         """name -> channels-last BF16 activation tensors of the live plan (tests only)."""
-        for _, plan in self._plans.values():
+        for _, plan in reversed(self._plans.values()):    # most recently used
             return plan.buffers
         return {}
 

@@ -47,6 +47,15 @@ def lib():
     if not os.path.exists(_LIB_PATH):
         raise EsfError("libesf_b200.so not found at %s -- build it with `python -m efficient_slowfast_b200._build` "
                        "(there is no CPU or PyTorch fallback for the forward path)" % _LIB_PATH)
+    # a library older than its sources must not be used silently: the stamp written by _build holds the digest of the
+    # sources + flags it was compiled from
+    from . import _build
+    stamp = _LIB_PATH + ".stamp"
+    if not os.path.exists(stamp) or open(stamp).read().strip() != _build._digest():
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise EsfError("libesf_b200.so is older than csrc/ (digest mismatch) and the rebuild failed: %s" % e)
     L = ctypes.CDLL(_LIB_PATH)
     vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
     P = ctypes.POINTER
@@ -66,6 +75,7 @@ def lib():
                                 i32, P(EsfView), vp]
     L.esf_stem_geometry.argtypes = [i32, i32, i32, i32, i32, P(i32), P(i32), P(i32)]
     L.esf_stem_pack.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+    L.esf_stem_pack_gather.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp]
     i64 = ctypes.c_int64
     L.esf_row_softmax.argtypes = [vp, i64, i32, i64, f32, i32, i32, vp, i64, vp]
     L.esf_transpose16.argtypes = [vp, i32, i32, i32, i64, i64, vp, i64, i64, vp]
@@ -97,7 +107,7 @@ def lib():
     L.esf_attn_generic.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, i32, P(EsfView), vp]
     L.esf_head_pool.argtypes = [P(EsfView), P(EsfView), vp, vp]
     L.esf_head_fc.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp, i32, vp]
-    for name in ("esf_dwconv_padded", "esf_pointwise_padded", "esf_global_mean", "esf_gemm_clip_weights_create", "esf_group_mean", "esf_row_softmax", "esf_transpose16", "esf_stem_pack_u8", "esf_frames_to_clip", "esf_attn_generic", "esf_shuffle_concat", "esf_eltwise_add", "esf_channel_scale", "esf_attn_tc_pack", "esf_attn_tc_create", "esf_stem_geometry", "esf_stem_pack", "esf_stem_igemm_create", "esf_igemm_geometry",
+    for name in ("esf_stem_pack_gather", "esf_dwconv_padded", "esf_pointwise_padded", "esf_global_mean", "esf_gemm_clip_weights_create", "esf_group_mean", "esf_row_softmax", "esf_transpose16", "esf_stem_pack_u8", "esf_frames_to_clip", "esf_attn_generic", "esf_shuffle_concat", "esf_eltwise_add", "esf_channel_scale", "esf_attn_tc_pack", "esf_attn_tc_create", "esf_stem_geometry", "esf_stem_pack", "esf_stem_igemm_create", "esf_igemm_geometry",
                  "esf_conv_igemm_create", "esf_conv_wfold_create", "esf_op_launch", "esf_conv_direct", "esf_stem_conv",
                  "esf_pool3d", "esf_eca_fuse", "esf_attn_pack", "esf_attn_fused", "esf_head_pool", "esf_head_fc"):
         getattr(L, name).restype = ctypes.c_int

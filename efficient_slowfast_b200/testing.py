@@ -84,10 +84,20 @@ class TestMeter:
         return stats
 
 
+def _slow_is_subset_of_fast(inputs):
+    """True when [slow, fast] is what pack_pathway_output (datasets/utils.py:93-102) makes of the fast clip."""
+    if len(inputs) != 2 or inputs[0].dim() != 5 or inputs[0].shape[2] > inputs[1].shape[2]:
+        return False
+    idx = torch.linspace(0, inputs[1].shape[2] - 1, inputs[0].shape[2]).long()
+    return bool(torch.equal(inputs[0], inputs[1].index_select(2, idx)))
+
+
 @torch.no_grad()
-def perform_test(test_loader, model, test_meter, cfg, depth=2):
+def perform_test(test_loader, model, test_meter, cfg, depth=2, slow_from_fast=None):
     """Classification branch of tools/test_net.py:21-123 over `(inputs, labels, video_idx, meta)` batches.  `inputs` is
-    the reference's list [slow, fast] of FP32 host tensors (pinned memory makes the copies asynchronous)."""
+    the reference's list [slow, fast] of FP32 host tensors (pinned memory makes the copies asynchronous); the last
+    batch may be shorter (the reference's test loader has drop_last=False).  `slow_from_fast`: upload only the fast
+    clip and let the slow pathway read its frames out of it (ClipStream); None = decide from the first batch."""
     if cfg.DETECTION.ENABLE:
         raise NotImplementedError("detection testing is out of scope")
     model.eval()
@@ -109,7 +119,10 @@ def perform_test(test_loader, model, test_meter, cfg, depth=2):
         if not isinstance(inputs, (list, tuple)):
             inputs = [inputs]
         if stream is None:
-            stream = ClipStream(model, [tuple(t.shape) for t in inputs], device=device, depth=depth, gather=multi)
+            if slow_from_fast is None:
+                slow_from_fast = hasattr(model, "forward_fast") and _slow_is_subset_of_fast(inputs)
+            stream = ClipStream(model, [tuple(t.shape) for t in inputs], device=device, depth=depth, gather=multi,
+                                slow_from_fast=slow_from_fast)
         if multi:
             labels, video_idx = [t.cpu() for t in esf_dist.all_gather([labels.to(device), video_idx.to(device)])]
         queued.append((labels, video_idx))

@@ -119,6 +119,13 @@ int esf_stem_geometry(int32_t W, int32_t Cin, int32_t kW, int32_t sW, int32_t pW
                       int32_t* window);
 int esf_stem_pack(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
                   int32_t lpad, int32_t dtype, void* xp, void* stream);
+/* esf_stem_pack_gather: esf_stem_pack of the SLOW pathway straight out of the FAST pathway's clip.  The loader's
+ * pack_pathway_output (SlowFast/slowfast/datasets/utils.py:93-102) makes slow = fast[:, :, linspace(0, T-1, T/alpha)]:
+ * the same pixels twice.  x: FP32 (B, Cin, Tsrc, H, W) fast clip; t_index: device int32[T], source frame of every slow
+ * frame -- the slow clip is never uploaded nor materialised (ClipStream(slow_from_fast=True)). */
+int esf_stem_pack_gather(const float* x, int32_t B, int32_t Cin, int32_t Tsrc, int32_t H, int32_t W,
+                         const int32_t* t_index, int32_t T, int32_t pitch, int32_t lpad, int32_t dtype, void* xp,
+                         void* stream);
 /* ---- uint8 frame input ---------------------------------------------------------------------
  * Replaces the loader-side chain the reference runs on the host before the H2D copy: tensor_normalize
  * (SlowFast/slowfast/datasets/utils.py:298-315: u8 -> float / 255, - mean, / std), permute(3,0,1,2)

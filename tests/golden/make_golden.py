@@ -35,8 +35,37 @@ def calibrate_bn(model, clips, alpha):
     model.eval()
 
 
+def patch_large_n_attention(threshold=40000, rows=2048):
+    """SURVEY 8(c) "Large-N oracle": at N = T*H*W = 100 352 keys (SlowFastGhostNet, 224^2 x 32 frames) the reference's
+    N x N affinity is 40 GB per clip and cannot be materialised.  SpatialAttention.forward
+    (wdf_attention_helper.py:33-54) is replaced, for such inputs only, by the same arithmetic evaluated for `rows`
+    query rows at a time: every row still sees its complete softmax over all N keys (bmm -> softmax(dim=-1) -> bmm),
+    only the batching of the rows changes."""
+    from slowfast.models import wdf_attention_helper as W
+
+    orig = W.SpatialAttention.forward
+
+    def forward(self, x):
+        B, C, T, H, Wd = x.size()
+        N = T * H * Wd
+        if N <= threshold:
+            return orig(self, x)
+        q = self.query_conv(x).view(B, -1, N).permute(0, 2, 1)
+        k = self.key_conv(x).view(B, -1, N)
+        v = self.value_conv(x).view(B, -1, N)
+        out = torch.empty(B, C, N, dtype=x.dtype)
+        for r0 in range(0, N, rows):
+            att = self.softmax(torch.bmm(q[:, r0:r0 + rows], k))
+            out[:, :, r0:r0 + rows] = torch.bmm(v, att.permute(0, 2, 1))
+        return self.gamma * out.view(B, C, T, H, Wd) + x
+
+    W.SpatialAttention.forward = forward
+
+
 def make_case(name):
     spec = recipe.CASES[name]
+    ref_shim.install()
+    patch_large_n_attention()
     cfg = ref_shim.get_cfg(spec["yaml"], spec["opts"])
     assert cfg.MODEL.MODEL_NAME == spec["model"]
     alpha = 0 if spec.get("single") else cfg.SLOWFAST.ALPHA

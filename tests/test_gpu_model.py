@@ -30,7 +30,7 @@ def _run(name, tag, precision="fp16"):
                                       ("slowfast_r50", "s224"), ("shufflenetv2_w05", "s112"),
                                       ("shufflenetv2_w05", "s224"), ("shufflenet_w2g3", "s112"),
                                       ("shufflenet_w2g3", "s64"), ("mobilenetv2_w1", "s112"),
-                                      ("mobilenetv2_w1", "s224"), ("ghostnet_w1", "s112"), ("ghostnet_w1", "s64"),
+                                      ("mobilenetv2_w1", "s224"), ("ghostnet_w1", "s112"), ("ghostnet_w1", "s64"), ("ghostnet_w1", "s224"),
                                       ("i3d_r50", "s224"), ("slow_r50", "s64"),
                                       ("slow_nln_r50", "s64"), ("i3d_nln_r50", "s96"),
                                       ("slowfast_r50_fcn", "s96"), ("slowfast_r50_fcn", "s64"), ("slow_r50", "s96")])
@@ -227,3 +227,137 @@ def test_forward_reads_caller_tensors_in_place_or_converts(esf_lib):
         y_other = model([t * 0.5 for t in xs]).cpu()
     assert torch.equal(y_f64, y0) and torch.equal(y_nc, y0) and torch.equal(y_again, y0)
     assert not torch.equal(y_other, y0)
+
+
+def _golden_in_first_and_last_slots(name, tag, batch, precision="fp16"):
+    """The reference-made golden clip in the first and the last slots of a batch of `batch` synthetic clips: the
+    plan, index paths and CUDA graph of the BENCHED batch size are the ones checked (bench.py does the same outside
+    its timed region and prints it as `parity_check`)."""
+    cfg, model, gold = helpers.case_model_and_weights(name, precision)
+    model = model.cuda().eval()
+    xs = helpers.case_inputs(name, tag)
+    gb = xs[0].shape[0]
+    g = torch.Generator(device="cuda").manual_seed(11)
+    big = [torch.randn((batch,) + tuple(x.shape[1:]), device="cuda", generator=g) for x in xs]
+    if len(big) == 2:
+        big[0].copy_(recipe.pack_pathway_output(big[1], cfg.SLOWFAST.ALPHA)[0])
+    for t, x in zip(big, xs):
+        t[:gb].copy_(x)
+        t[batch - gb:].copy_(x)
+    with torch.no_grad():
+        y = model(big).cpu()
+    torch.cuda.synchronize()
+    ref = torch.as_tensor(gold[tag + "/probs"])
+    first, last = y[:gb], y[batch - gb:]
+    print("%s/%s at batch %d: rel err %.3e / %.3e" % (name, tag, batch, helpers.rel_err(first, ref),
+                                                      helpers.rel_err(last, ref)))
+    assert helpers.rel_err(first, ref) <= BF16_TOL and helpers.rel_err(last, ref) <= BF16_TOL
+    assert torch.equal(first, last), "the same clip gives different results in different batch slots"
+    assert torch.equal(first.argmax(1), ref.argmax(1))
+    assert torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize("name,tag,batch", [
+    ("dual_r50", "s224", 64),            # BASELINE configs[2]: the headline bench workload
+    ("slowfast_r50", "s224", 32),        # configs[1]
+    ("mobilenetv2_w1", "s112", 128),     # configs[3] batch, at the crop that fits the test budget
+    ("ghostnet_w1", "s112", 128),
+    ("shufflenet_w2g3", "s112", 256),    # configs[4]: the Jester shape itself
+    ("shufflenetv2_w05", "s112", 64)])
+def test_benched_batch_matches_reference_golden(esf_lib, name, tag, batch):
+    _golden_in_first_and_last_slots(name, tag, batch)
+
+
+def test_forward_fast_equals_forward_of_packed_pathways(esf_lib):
+    """model.forward_fast(fast) == model.forward(pack_pathway_output(fast)): the slow pathway's stem reads its frames
+    out of the fast clip (esf_stem_pack_gather), bit-identical to uploading the slow clip."""
+    for name, tag in (("dual_r50", "s64"), ("slowfast_r50", "s64"), ("shufflenetv2_w05", "s112")):
+        cfg, model, gold, y = _run(name, tag)
+        xs = [t.cuda() for t in helpers.case_inputs(name, tag)]
+        with torch.no_grad():
+            y2 = model.forward_fast(xs[1]).cpu()
+            y3 = model(xs).cpu()
+        assert torch.equal(y2, y), name
+        assert torch.equal(y3, y), name
+
+
+def test_clip_stream_short_last_batch_and_slow_from_fast(esf_lib):
+    """A loader with drop_last=False ends on a short batch: ClipStream copies it into the leading rows of
+    its staging slot and returns exactly the rows of that batch; slow_from_fast=True gives identical predictions while
+    copying only the fast clip, and refuses a slow clip that is not the frame subset of the fast one."""
+    import efficient_slowfast_b200 as esf
+    from efficient_slowfast_b200 import runtime as rt
+
+    cfg, model, gold, _ = _run("slowfast_r50", "s64")
+    base = helpers.case_inputs("slowfast_r50", "s64")
+    batches = []
+    for i, n in enumerate((2, 2, 1)):
+        fast = (torch.roll(base[1], shifts=i, dims=2) * (1.0 + 0.1 * i))[:n]
+        batches.append([t.contiguous().pin_memory() for t in recipe.pack_pathway_output(fast, cfg.SLOWFAST.ALPHA)])
+    with torch.no_grad():
+        want = [model([t.cuda() for t in xs]).cpu() for xs in batches]
+        for sff in (False, True):
+            stream = esf.ClipStream(model, [tuple(t.shape) for t in batches[0]], depth=2, slow_from_fast=sff)
+            got = []
+            for xs in batches:
+                r = stream.submit(xs)
+                if r is not None:
+                    got.append(r)
+            got += stream.flush()
+            assert [tuple(y.shape) for _, y in got] == [(2, 400), (2, 400), (1, 400)]
+            for (_, y), w in zip(got, want):
+                assert torch.equal(y, w)
+            assert stream.h2d_bytes == sum(t.numel() * 4 for t in (batches[0][1:] if sff else batches[0]))
+        bad = [batches[0][0] + 1.0, batches[0][1]]
+        with pytest.raises(rt.EsfError):
+            esf.ClipStream(model, [tuple(t.shape) for t in bad], depth=2, slow_from_fast=True).submit(bad)
+        with pytest.raises(rt.EsfError):      # a batch LARGER than the staging slot is an error, not a reallocation
+            big = [torch.cat([t, t]) for t in batches[0]]
+            esf.ClipStream(model, [tuple(t.shape) for t in batches[0]], depth=2).submit(big)
+
+
+def test_perform_test_short_last_batch(esf_lib):
+    """perform_test over 5 clips in batches of 2 (last batch: 1 clip), as the reference's drop_last=False loader yields."""
+    import efficient_slowfast_b200 as esf
+
+    cfg, model, gold, _ = _run("slowfast_r50", "s64")
+    base = helpers.case_inputs("slowfast_r50", "s64")[1][:1]
+    clips = [recipe.pack_pathway_output(torch.roll(base, shifts=2 * i, dims=4) * (1.0 + 0.03 * i), cfg.SLOWFAST.ALPHA)
+             for i in range(5)]
+    labels = torch.tensor([1, 2, 3, 4, 5])
+    loader = []
+    for i in range(0, 5, 2):
+        n = min(2, 5 - i)
+        inputs = [torch.cat([clips[i + j][p] for j in range(n)]).contiguous().pin_memory() for p in range(2)]
+        loader.append((inputs, labels[i:i + n], torch.arange(i, i + n), {}))
+    with torch.no_grad():
+        direct = torch.cat([model([t.cuda() for t in c]).cpu() for c in clips])
+    meter = esf.TestMeter(5, 1, cfg.MODEL.NUM_CLASSES, len(loader))
+    snaps = []
+    orig = meter.finalize_metrics
+    meter.finalize_metrics = lambda ks=(1, 5): (snaps.append(meter.video_preds.clone()), orig(ks))[1]
+    cfg.NUM_GPUS = 1
+    stats = esf.perform_test(loader, model, meter, cfg)
+    assert stats["complete"]
+    assert torch.allclose(snaps[0], direct, atol=1e-6)
+
+
+def test_plan_cache_keeps_two_shapes_and_drops_stale_weights(esf_lib):
+    cfg, model, gold, y = _run("slowfast_r50", "s64")
+    xs = [t.cuda() for t in helpers.case_inputs("slowfast_r50", "s64")]
+    with torch.no_grad():
+        y1 = model([t[:1].contiguous() for t in xs]).cpu()
+        plans = list(model._plans.values())
+        assert len(plans) == 2
+        y_again = model(xs).cpu()
+        assert [p for _, p in model._plans.values()][-1] is plans[0][1]      # the batch-2 plan was reused, now MRU
+        assert torch.equal(y_again, y) and torch.allclose(y1[0], y[0], atol=1e-6, rtol=0)
+        # a weight edit through an autograd-visible in-place op changes the stamp: every plan is rebuilt
+        model.head.projection.bias.add_(torch.arange(400, device="cuda") / 400.0)
+        y_new = model(xs).cpu()
+        assert len(model._plans) == 1 and not torch.equal(y_new, y)
+        # `.data` edits carry no version counter: invalidate_plans() is the documented way
+        model.head.projection.bias.data.zero_()
+        model.invalidate_plans()
+        y_zero = model(xs).cpu()
+        assert not torch.equal(y_zero, y_new)

@@ -201,7 +201,7 @@ def test_caffe2_checkpoint_loads(tmp_path):
     path = str(tmp_path / "c2.pkl")
     with open(path, "wb") as f:
         pickle.dump({"blobs": blobs}, f)
-    assert esf.load_checkpoint(path, model, convert_from_caffe2=True) == -1
+    assert esf.load_checkpoint(path, model, False, convert_from_caffe2=True) == -1
     after = model.state_dict()
     for c2, key in names.items():
         if key in sd:

@@ -13,7 +13,7 @@ from oracle import slowfast_oracle as O
                                       ("dual_r50_stress", "s64"), ("shufflenetv2_w05", "s112"),
                                       ("shufflenetv2_w05", "s224"), ("shufflenet_w2g3", "s112"),
                                       ("shufflenet_w2g3", "s64"), ("mobilenetv2_w1", "s112"),
-                                      ("mobilenetv2_w1", "s224"), ("ghostnet_w1", "s112"), ("ghostnet_w1", "s64"),
+                                      ("mobilenetv2_w1", "s224"), ("ghostnet_w1", "s112"), ("ghostnet_w1", "s64"), ("ghostnet_w1", "s224"),
                                       ("i3d_r50", "s224"), ("slow_r50", "s64"),
                                       ("slow_nln_r50", "s64"), ("i3d_nln_r50", "s96"),
                                       ("slowfast_r50_fcn", "s96"), ("slowfast_r50_fcn", "s64"), ("slow_r50", "s96")])

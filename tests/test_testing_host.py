@@ -102,7 +102,8 @@ def test_checkpoint_roundtrip_and_key_normalisation(tmp_path):
     dst = esf.build_model(cfg)
     path = str(tmp_path / "checkpoint_epoch_00007.pyth")
     esf.save_checkpoint(path, src, epoch=7)
-    assert esf.load_checkpoint(path, dst) == 7
+    # the reference's own call shape (tools/test_net.py -> cu.load_test_checkpoint): positional data_parallel, optimizer
+    assert esf.load_checkpoint(path, dst, False, None, inflation=False, convert_from_caffe2=False) == 7
     for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
         assert torch.equal(a, b), k
     # DDP prefix + Sub-BN naming as written by a multi-GPU training run of the reference
@@ -120,7 +121,16 @@ def test_checkpoint_roundtrip_and_key_normalisation(tmp_path):
     torch.save({"epoch": 3, "model_state": sd, "optimizer_state": {}, "cfg": ""}, path)
     torch.manual_seed(4)
     dst2 = esf.build_model(cfg)
-    assert esf.load_checkpoint(path, dst2) == 3
+    assert esf.load_checkpoint(path, dst2, data_parallel=False) == 3
+    # reference defaults: data_parallel=True expects the DDP wrapper (model.module), inflation is out of scope
+    import pytest
+    with pytest.raises(AttributeError):
+        esf.load_checkpoint(path, dst2)
+    with pytest.raises(NotImplementedError):
+        esf.load_checkpoint(path, dst2, False, None, inflation=True)
+    wrapped = torch.nn.Module()
+    wrapped.module = dst2
+    assert esf.load_checkpoint(path, wrapped) == 3
     assert esf.load_checkpoint.last_report == {"missing": [], "unexpected": []}
     for (k, a), (_, b) in zip(src.state_dict().items(), dst2.state_dict().items()):
         assert torch.equal(a, b), k
