@@ -1,0 +1,332 @@
+// FP32-accurate path (cfg.ESF.PRECISION = "fp32"): the glue kernels around the tcgen05 implicit GEMM.
+//
+// The reference computes everything in FP32 (resnet_helper.py:182-240, wdf_attention_helper.py:42-53).  The tensor cores
+// take 16-bit operands, so in this mode every operand is carried as a PAIR of FP16 numbers x = hi + lo (hi = fp16(x),
+// lo = fp16(x - hi): 22 mantissa bits) and a product is evaluated as three FP16 MMAs with FP32 accumulation,
+//     x . w  ~=  x_hi . w_hi + x_lo . w_hi + x_hi . w_lo          (the dropped lo . lo term is 2^-24 relative).
+// No new GEMM kernel is needed for that: an activation is stored channels-last as THREE planes [hi | lo | hi] and the
+// folded weight as [w_hi | w_hi | w_lo] along its input-channel axis, which makes the split product an ordinary
+// convolution with 3x the input channels on the existing igemm kernel (FP32 output).  What remains -- and lives in
+// this file -- is FP32 element-wise work: the GEMM's post-pass (per-channel scale + bias, residual, activation, split
+// into planes), max/avg pooling, the ECA fuse, the head's global average, all on FP32 channels-last views.
+// Weight rows are pre-scaled by a power of two (so that w_lo stays a normal FP16 number) and `scale` undoes it.
+//
+// These are HBM-bound helper kernels of an accuracy mode, written for clarity: one thread per 8 (or 1) channels,
+// coalesced over the channel axis.
+#include <math_constants.h>
+
+#include <algorithm>
+
+#include "esf_common.cuh"
+#include "esf_host.h"
+
+namespace esf {
+
+struct V32 {
+  char* ptr;
+  int B, T, H, W, C;
+  long long sB, sT, sH, sW;
+};
+static V32 to_v32(const esf_view* v) {
+  V32 r;
+  r.ptr = static_cast<char*>(v->ptr);
+  r.B = v->B, r.T = v->T, r.H = v->H, r.W = v->W, r.C = v->C;
+  r.sB = v->sB, r.sT = v->sT, r.sH = v->sH, r.sW = v->sW;
+  return r;
+}
+static V32 null_v32() {
+  V32 r;
+  memset(&r, 0, sizeof(r));
+  return r;
+}
+__device__ __forceinline__ long long off32(const V32& v, int b, int t, int h, int w) {
+  return b * v.sB + t * v.sT + h * v.sH + w * v.sW;
+}
+__device__ __forceinline__ void split_hi_lo(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+  lo = __float2half_rn(x - __half2float(hi));
+}
+
+static int p32_grid(long long total, int threads) {
+  long long g = (total + threads - 1) / threads;
+  return (int)std::max(1LL, std::min(g, 148LL * 32));
+}
+
+// ------------------------------------------------------------------------------------------- GEMM post-pass / split
+// v = act(acc * scale[c] + bias[c] + res);  y32 = v;  y3 planes = [hi(v) | lo(v) | hi(v)]
+struct PostParams {
+  V32 acc, res, y32, y3;   // y3: FP16 view of the hi plane's slice; the other planes follow at +plane, +2*plane elements
+  const float* scale;
+  const float* bias;
+  int act, plane;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) p32_post_kernel(const PostParams p) {
+  const int groups = (p.acc.C + VEC - 1) / VEC;
+  const long long total = (long long)p.acc.B * p.acc.T * p.acc.H * p.acc.W * groups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    long long pos = idx / groups;
+    const int w = (int)(pos % p.acc.W);
+    pos /= p.acc.W;
+    const int h = (int)(pos % p.acc.H);
+    pos /= p.acc.H;
+    const int t = (int)(pos % p.acc.T);
+    const int b = (int)(pos / p.acc.T);
+    const int c0 = g * VEC;
+    float v[VEC];
+    const float* a = reinterpret_cast<const float*>(p.acc.ptr) + off32(p.acc, b, t, h, w) + c0;
+    if constexpr (VEC == 8) {
+      const float4 a0 = *reinterpret_cast<const float4*>(a), a1 = *reinterpret_cast<const float4*>(a + 4);
+      v[0] = a0.x, v[1] = a0.y, v[2] = a0.z, v[3] = a0.w, v[4] = a1.x, v[5] = a1.y, v[6] = a1.z, v[7] = a1.w;
+    } else {
+      v[0] = a[0];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      if (p.scale) v[j] *= __ldg(p.scale + c0 + j);
+      if (p.bias) v[j] += __ldg(p.bias + c0 + j);
+    }
+    if (p.res.ptr) {
+      const float* r = reinterpret_cast<const float*>(p.res.ptr) + off32(p.res, b, t, h, w) + c0;
+      if constexpr (VEC == 8) {
+        const float4 r0 = *reinterpret_cast<const float4*>(r), r1 = *reinterpret_cast<const float4*>(r + 4);
+        v[0] += r0.x, v[1] += r0.y, v[2] += r0.z, v[3] += r0.w, v[4] += r1.x, v[5] += r1.y, v[6] += r1.z, v[7] += r1.w;
+      } else {
+        v[0] += r[0];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = apply_act(v[j], p.act);
+    if (p.y32.ptr) {
+      float* y = reinterpret_cast<float*>(p.y32.ptr) + off32(p.y32, b, t, h, w) + c0;
+      if constexpr (VEC == 8) {
+        *reinterpret_cast<float4*>(y) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(y + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+        y[0] = v[0];
+      }
+    }
+    if (p.y3.ptr) {
+      __half* y = reinterpret_cast<__half*>(p.y3.ptr) + off32(p.y3, b, t, h, w) + c0;
+      __half hi[VEC], lo[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) split_hi_lo(v[j], hi[j], lo[j]);
+      if constexpr (VEC == 8) {
+        const uint4 H = *reinterpret_cast<const uint4*>(hi), L = *reinterpret_cast<const uint4*>(lo);
+        *reinterpret_cast<uint4*>(y) = H;
+        *reinterpret_cast<uint4*>(y + p.plane) = L;
+        *reinterpret_cast<uint4*>(y + 2 * p.plane) = H;
+      } else {
+        y[0] = hi[0];
+        y[p.plane] = lo[0];
+        y[2 * p.plane] = hi[0];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- pooling (FP32)
+struct Pool32Params {
+  V32 x, y;
+  int kT, kH, kW, sT, sH, sW, pT, pH, pW, is_avg;
+};
+__global__ void __launch_bounds__(256) p32_pool_kernel(const Pool32Params p) {
+  const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W * p.y.C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % p.y.C);
+    long long pos = idx / p.y.C;
+    const int w = (int)(pos % p.y.W);
+    pos /= p.y.W;
+    const int h = (int)(pos % p.y.H);
+    pos /= p.y.H;
+    const int t = (int)(pos % p.y.T);
+    const int b = (int)(pos / p.y.T);
+    float m = p.is_avg ? 0.f : -CUDART_INF_F;
+    for (int kt = 0; kt < p.kT; ++kt) {
+      const int ti = t * p.sT + kt - p.pT;
+      if (ti < 0 || ti >= p.x.T) continue;
+      for (int kh = 0; kh < p.kH; ++kh) {
+        const int hi = h * p.sH + kh - p.pH;
+        if (hi < 0 || hi >= p.x.H) continue;
+        for (int kw = 0; kw < p.kW; ++kw) {
+          const int wi = w * p.sW + kw - p.pW;
+          if (wi < 0 || wi >= p.x.W) continue;
+          const float v = reinterpret_cast<const float*>(p.x.ptr)[off32(p.x, b, ti, hi, wi) + c];
+          m = p.is_avg ? m + v : fmaxf(m, v);
+        }
+      }
+    }
+    if (p.is_avg) m /= (float)(p.kT * p.kH * p.kW);   // count_include_pad = True, as nn.AvgPool3d
+    reinterpret_cast<float*>(p.y.ptr)[off32(p.y, b, t, h, w) + c] = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- ECA fuse (FP32)
+// pass 1: partial[b][chunk][c] = sum over the chunk's (t', h, w) of max_r x[b, alpha t' + r, h, w, c]   (deterministic)
+// pass 2: y = relu(bn(maxpool_t(x) * sigmoid(conv1d_k(mean)[c])))
+constexpr int kEcaChunks = 64;
+struct Eca32Params {
+  V32 x, y;
+  int alpha, k;
+  const float* w;
+  const float* bn_scale;
+  const float* bn_shift;
+  float* partial;   // [B][kEcaChunks][C]
+};
+__global__ void __launch_bounds__(256) p32_eca_partial_kernel(const Eca32Params p) {
+  __shared__ float red[256];
+  const int C = p.x.C, b = blockIdx.y, chunk = blockIdx.x;
+  const int To = p.x.T / p.alpha;
+  const long long npos = (long long)To * p.x.H * p.x.W;
+  const long long per = (npos + kEcaChunks - 1) / kEcaChunks;
+  const long long p0 = chunk * per, p1 = min(npos, p0 + per);
+  const int lanes = 256 / C;                 // C divides 256 (checked on the host)
+  const int c = threadIdx.x % C, pl = threadIdx.x / C;
+  float s = 0.f;
+  for (long long q = p0 + pl; q < p1; q += lanes) {
+    const int w = (int)(q % p.x.W);
+    const long long r = q / p.x.W;
+    const int h = (int)(r % p.x.H), t = (int)(r / p.x.H);
+    float m = -CUDART_INF_F;
+    for (int a = 0; a < p.alpha; ++a)
+      m = fmaxf(m, reinterpret_cast<const float*>(p.x.ptr)[off32(p.x, b, t * p.alpha + a, h, w) + c]);
+    s += m;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (pl == 0) {
+    float tot = 0.f;
+    for (int l = 0; l < lanes; ++l) tot += red[l * C + c];   // fixed order
+    p.partial[((long long)b * kEcaChunks + chunk) * C + c] = tot;
+  }
+}
+__global__ void __launch_bounds__(256) p32_eca_apply_kernel(const Eca32Params p) {
+  const int C = p.x.C;
+  const int To = p.x.T / p.alpha;
+  const float inv = 1.f / ((float)To * p.x.H * p.x.W);
+  const long long total = (long long)p.x.B * To * p.x.H * p.x.W * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    long long pos = idx / C;
+    const int w = (int)(pos % p.x.W);
+    pos /= p.x.W;
+    const int h = (int)(pos % p.x.H);
+    pos /= p.x.H;
+    const int t = (int)(pos % To);
+    const int b = (int)(pos / To);
+    float z = 0.f;
+    for (int j = 0; j < p.k; ++j) {
+      const int cc = c + j - (p.k - 1) / 2;
+      if (cc < 0 || cc >= C) continue;
+      float mean = 0.f;
+      for (int ch = 0; ch < kEcaChunks; ++ch) mean += p.partial[((long long)b * kEcaChunks + ch) * C + cc];
+      z = fmaf(__ldg(p.w + j), mean * inv, z);
+    }
+    const float gate = 1.f / (1.f + expf(-z));
+    float m = -CUDART_INF_F;
+    for (int a = 0; a < p.alpha; ++a)
+      m = fmaxf(m, reinterpret_cast<const float*>(p.x.ptr)[off32(p.x, b, t * p.alpha + a, h, w) + c]);
+    const float v = fmaf(m * gate, __ldg(p.bn_scale + c), __ldg(p.bn_shift + c));
+    reinterpret_cast<float*>(p.y.ptr)[off32(p.y, b, t, h, w) + c] = fmaxf(v, 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- head pool (FP32)
+// feat[b][off + c] = mean over (t, h, w) of x[b, t, h, w, c]; one block per (clip, 256-channel group), fixed order
+__global__ void __launch_bounds__(256) p32_head_pool_kernel(const V32 x, float* __restrict__ feat, int feat_stride, int off) {
+  const int b = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= x.C) return;
+  float s = 0.f;
+  for (int t = 0; t < x.T; ++t)
+    for (int h = 0; h < x.H; ++h)
+      for (int w = 0; w < x.W; ++w) s += reinterpret_cast<const float*>(x.ptr)[off32(x, b, t, h, w) + c];
+  feat[(long long)b * feat_stride + off + c] = s / ((float)x.T * x.H * x.W);
+}
+
+static bool f32_view_ok(const esf_view* v) { return view_ok(v) && v->dtype == ESF_F32; }
+static bool same_pos(const esf_view* a, const esf_view* b) {
+  return a->B == b->B && a->T == b->T && a->H == b->H && a->W == b->W;
+}
+static bool vec8_ok(const esf_view* v, int elem) {
+  const int q = 16 / elem;
+  return v->C % 8 == 0 && reinterpret_cast<uintptr_t>(v->ptr) % 16 == 0 && v->sW % q == 0 && v->sH % q == 0 &&
+         v->sT % q == 0 && v->sB % q == 0;
+}
+
+}  // namespace esf
+
+using namespace esf;
+
+extern "C" int esf_p32_post(const esf_view* acc, const float* scale, const float* bias, const esf_view* res, int32_t act,
+                            const esf_view* y32, const esf_view* y3, int32_t plane, void* stream) {
+  ESF_CHECK_ARG(f32_view_ok(acc), "esf_p32_post: acc must be an FP32 view");
+  ESF_CHECK_ARG(!res || !res->ptr || (f32_view_ok(res) && same_pos(res, acc) && res->C == acc->C),
+                "esf_p32_post: residual must be an FP32 view of the accumulator's shape");
+  ESF_CHECK_ARG(!y32 || !y32->ptr || (f32_view_ok(y32) && same_pos(y32, acc) && y32->C == acc->C),
+                "esf_p32_post: y32 must be an FP32 view of the accumulator's shape");
+  ESF_CHECK_ARG(!y3 || !y3->ptr || (view_ok(y3) && y3->dtype == ESF_F16 && same_pos(y3, acc) && y3->C == acc->C &&
+                                    plane >= acc->C && y3->sW >= 3LL * plane),
+                "esf_p32_post: y3 must be the FP16 hi-plane slice of a [hi|lo|hi] buffer (plane %d)", plane);
+  PostParams p;
+  p.acc = to_v32(acc);
+  p.res = (res && res->ptr) ? to_v32(res) : null_v32();
+  p.y32 = (y32 && y32->ptr) ? to_v32(y32) : null_v32();
+  p.y3 = (y3 && y3->ptr) ? to_v32(y3) : null_v32();
+  p.scale = scale, p.bias = bias, p.act = act, p.plane = plane;
+  const long long pos = (long long)acc->B * acc->T * acc->H * acc->W;
+  const bool v8 = vec8_ok(acc, 4) && (!p.res.ptr || vec8_ok(res, 4)) && (!p.y32.ptr || vec8_ok(y32, 4)) &&
+                  (!p.y3.ptr || (vec8_ok(y3, 2) && plane % 8 == 0));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (v8) p32_post_kernel<8><<<p32_grid(pos * (acc->C / 8), 256), 256, 0, s>>>(p);
+  else p32_post_kernel<1><<<p32_grid(pos * acc->C, 256), 256, 0, s>>>(p);
+  return check_launch("p32_post_kernel");
+}
+
+extern "C" int esf_p32_pool3d(const esf_view* x, const esf_view* y, int32_t kT, int32_t kH, int32_t kW, int32_t sT,
+                              int32_t sH, int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t is_avg, void* stream) {
+  ESF_CHECK_ARG(f32_view_ok(x) && f32_view_ok(y) && x->C == y->C && x->B == y->B, "esf_p32_pool3d: FP32 views expected");
+  ESF_CHECK_ARG(y->T == (x->T + 2 * pT - kT) / sT + 1 && y->H == (x->H + 2 * pH - kH) / sH + 1 &&
+                    y->W == (x->W + 2 * pW - kW) / sW + 1,
+                "esf_p32_pool3d: output shape does not match the window");
+  Pool32Params p;
+  p.x = to_v32(x), p.y = to_v32(y);
+  p.kT = kT, p.kH = kH, p.kW = kW, p.sT = sT, p.sH = sH, p.sW = sW, p.pT = pT, p.pH = pH, p.pW = pW, p.is_avg = is_avg;
+  const long long total = (long long)y->B * y->T * y->H * y->W * y->C;
+  p32_pool_kernel<<<p32_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("p32_pool_kernel");
+}
+
+extern "C" int64_t esf_p32_eca_scratch_floats(int32_t B, int32_t C) { return (int64_t)B * kEcaChunks * C; }
+
+extern "C" int esf_p32_eca_fuse(const esf_view* x_fast, int32_t alpha, const float* eca_w, int32_t eca_k,
+                                const float* bn_scale, const float* bn_shift, float* partial, const esf_view* y,
+                                void* stream) {
+  ESF_CHECK_ARG(f32_view_ok(x_fast) && f32_view_ok(y) && eca_w && bn_scale && bn_shift && partial,
+                "esf_p32_eca_fuse: null / non-FP32 argument");
+  ESF_CHECK_ARG(alpha >= 1 && x_fast->T % alpha == 0 && y->T == x_fast->T / alpha && y->H == x_fast->H &&
+                    y->W == x_fast->W && y->C == x_fast->C && y->B == x_fast->B,
+                "esf_p32_eca_fuse: shapes do not match");
+  ESF_CHECK_ARG(x_fast->C <= 256 && 256 % x_fast->C == 0, "esf_p32_eca_fuse: C = %d must divide 256", x_fast->C);
+  Eca32Params p;
+  p.x = to_v32(x_fast), p.y = to_v32(y);
+  p.alpha = alpha, p.k = eca_k, p.w = eca_w, p.bn_scale = bn_scale, p.bn_shift = bn_shift, p.partial = partial;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  p32_eca_partial_kernel<<<dim3(kEcaChunks, x_fast->B), 256, 0, s>>>(p);
+  int rc = check_launch("p32_eca_partial_kernel");
+  if (rc) return rc;
+  const long long total = (long long)y->B * y->T * y->H * y->W * y->C;
+  p32_eca_apply_kernel<<<p32_grid(total, 256), 256, 0, s>>>(p);
+  return check_launch("p32_eca_apply_kernel");
+}
+
+extern "C" int esf_p32_head_pool(const esf_view* x, float* feat, int32_t feat_stride, int32_t feat_off, void* stream) {
+  ESF_CHECK_ARG(f32_view_ok(x) && feat && feat_stride >= feat_off + x->C, "esf_p32_head_pool: bad argument");
+  p32_head_pool_kernel<<<dim3((x->C + 255) / 256, x->B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      to_v32(x), feat, feat_stride, feat_off);
+  return check_launch("p32_head_pool_kernel");
+}
