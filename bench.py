@@ -570,7 +570,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps (0: same as --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-ops", default="", help="write per-op device times (JSON lines) to this file")
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"],
                     help="16-bit storage / tensor-core operand format (FP32 accumulation in both)")
     ap.add_argument("--e2e-depth", type=int, default=3, help="staging slots of the end-to-end ClipStream")
     ap.add_argument("--no-extra-configs", action="store_true",

@@ -53,6 +53,7 @@ struct __align__(64) AttnTcParams {
   int stages;
   uint32_t q_tile_bytes, k_tile_bytes, v_tile_bytes;
   int f16;  // 16-bit operands (Q~, K~, V^T, P) and the output are IEEE half instead of BF16
+  int out_f32;  // the output view is FP32 (FP32-accurate path, esf_precise.cu); strides stay in elements
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -314,6 +315,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
           const float a = fmaf(p.gamma, o[jj] * inv, xr[ch]);
           o[jj] = fmaxf(fmaf(a, __ldg(p.bn_scale + ch), __ldg(p.bn_shift + ch)), 0.f);
         }
+      }
+      if (p.out_f32) {
+        for (int rep = 0; rep < p.alpha; ++rep) {
+          float* yf = reinterpret_cast<float*>(p.y) + b * p.ysB + hh * p.ysH + ww * p.ysW +
+                      (long long)(t * p.alpha + rep) * p.ysT + c0;
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj)
+            if (c0 + jj < p.d) yf[jj] = o[jj];
+        }
+        continue;
       }
       for (int rep = 0; rep < p.alpha; ++rep) {
         __nv_bfloat16* yp = yb + (long long)(t * p.alpha + rep) * p.ysT + c0;
@@ -748,6 +759,16 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
           o[jj] = fmaxf(fmaf(a, __ldg(p.bn_scale + ch), __ldg(p.bn_shift + ch)), 0.f);
         }
       }
+      if (p.out_f32) {
+        for (int rep = 0; rep < p.alpha; ++rep) {
+          float* yf = reinterpret_cast<float*>(p.y) + b * p.ysB + hh * p.ysH + ww * p.ysW +
+                      (long long)(t * p.alpha + rep) * p.ysT + c0;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            if (c0 + jj < p.d) yf[jj] = o[jj];
+        }
+        continue;
+      }
       for (int rep = 0; rep < p.alpha; ++rep) {
         __nv_bfloat16* yp = yb + (long long)(t * p.alpha + rep) * p.ysT + c0;
         if (vec_ok) {
@@ -1005,7 +1026,9 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
                                   float gamma, const float* bn_scale, const float* bn_shift, int32_t alpha,
                                   const esf_view* y_fast_slice, esf_op** out) {
   ESF_CHECK_ARG(packed && bn_scale && bn_shift && view_ok(y_fast_slice) && out, "esf_attn_tc_create: null/bad argument");
-  ESF_CHECK_ARG(is16(y_fast_slice->dtype), "esf_attn_tc_create: output must be BF16 or F16");
+  // an FP32 output view selects the FP32-accurate path: the packed operands are then FP16 (esf_attn_tc_pack dtype F16)
+  ESF_CHECK_ARG(is16(y_fast_slice->dtype) || y_fast_slice->dtype == ESF_F32,
+                "esf_attn_tc_create: output must be BF16, F16 or F32");
   TcGeom g;
   if (!tc_geom(d, &g)) return set_error(ESF_ERR_UNSUPPORTED, "esf_attn_tc_create: unsupported head dim %d", d);
   const esf_view* y = y_fast_slice;
@@ -1025,7 +1048,8 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
   p.y = static_cast<__nv_bfloat16*>(y->ptr);
   p.ysB = y->sB, p.ysT = y->sT, p.ysH = y->sH, p.ysW = y->sW;
   p.DVp = g.DVp, p.nchunks = g.nchunks, p.chunk_el = g.chunk_el;
-  p.f16 = y->dtype == ESF_F16;
+  p.f16 = y->dtype == ESF_F16 || y->dtype == ESF_F32;
+  p.out_f32 = y->dtype == ESF_F32;
   const int RB = g.chunk_el * 2;
   p.sbo = 8 * RB;
   p.layout_type = RB == 128 ? 2 : 4;

@@ -248,6 +248,116 @@ __global__ void __launch_bounds__(256) p32_head_pool_kernel(const V32 x, float* 
   feat[(long long)b * feat_stride + off + c] = s / ((float)x.T * x.H * x.W);
 }
 
+// ------------------------------------------------------------------------------------------- position attention (FP32)
+// out[i] = relu(bn(gamma * sum_j softmax_j(q_i . k_j) v_j + x_i)) in FP32 on the CUDA cores, flash style: the tcgen05
+// kernel of the 16-bit plan rounds P and V to FP16 (2^-11), which is the whole error budget of this mode.  proj rows are
+// [x_d | q | k | v] (D FP32 each).  A block owns 128 / G query rows, G = D / DT threads per row (DT = min(D, 32) channels
+// of q and O per thread); key tiles of 32 rows of K and V go through shared memory, every thread computes the 32 logits
+// of its row (partial dot over its channels, summed across the G lanes), one online-softmax update per tile, then
+// O += P V on its channels.  The N x N matrix is never formed.
+template <int D>
+__global__ void __launch_bounds__(128) p32_attn_kernel(const float* __restrict__ proj, int N, int T, int H, int W,
+                                                       float gamma, const float* __restrict__ bn_scale,
+                                                       const float* __restrict__ bn_shift, int alpha,
+                                                       float* __restrict__ y, long long ysB, long long ysT, long long ysH,
+                                                       long long ysW) {
+  constexpr int DT = D < 32 ? D : 32;
+  constexpr int G = D / DT;
+  constexpr int R = 128 / G;          // query rows per block
+  constexpr int KT = 32;              // keys per tile
+  constexpr int PITCH = D + 4 * G;    // sub-row g starts at g * (DT + 4): 16-byte aligned, G lanes hit different banks
+  __shared__ __align__(16) float Ks[KT * PITCH];
+  __shared__ __align__(16) float Vs[KT * PITCH];
+  const int b = blockIdx.y;
+  const int g = threadIdx.x % G;
+  const int row = blockIdx.x * R + threadIdx.x / G;
+  const bool valid = row < N;
+  const float* base = proj + (long long)b * N * 4 * D;
+  float q[DT], o[DT];
+  {
+    const float* qr = base + (long long)(valid ? row : 0) * 4 * D + D + g * DT;
+#pragma unroll
+    for (int c = 0; c < DT; ++c) q[c] = valid ? qr[c] : 0.f, o[c] = 0.f;
+  }
+  float m = -CUDART_INF_F, l = 0.f;
+  const float kLog2e = 1.4426950408889634f;
+  for (int j0 = 0; j0 < N; j0 += KT) {
+    __syncthreads();
+    // cooperative tile load: KT rows x D floats of K and of V (float4, coalesced within a row)
+    for (int i = threadIdx.x; i < KT * (D / 4); i += 128) {
+      const int j = i / (D / 4), c4 = i % (D / 4);
+      const int c = c4 * 4, sub = c / DT, cc = c % DT;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (j0 + j < N) {
+        const float* r = base + (long long)(j0 + j) * 4 * D;
+        kv = *reinterpret_cast<const float4*>(r + 2 * D + c);
+        vv = *reinterpret_cast<const float4*>(r + 3 * D + c);
+      }
+      *reinterpret_cast<float4*>(&Ks[j * PITCH + sub * (DT + 4) + cc]) = kv;
+      *reinterpret_cast<float4*>(&Vs[j * PITCH + sub * (DT + 4) + cc]) = vv;
+    }
+    __syncthreads();
+    float sc[KT];
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      const float* kr = &Ks[j * PITCH + g * (DT + 4)];
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < DT; c += 4) {
+        const float4 k4 = *reinterpret_cast<const float4*>(kr + c);
+        a0 = fmaf(q[c], k4.x, a0);
+        a1 = fmaf(q[c + 1], k4.y, a1);
+        a0 = fmaf(q[c + 2], k4.z, a0);
+        a1 = fmaf(q[c + 3], k4.w, a1);
+      }
+      float a = a0 + a1;
+#pragma unroll
+      for (int sh = 1; sh < G; sh <<= 1) a += __shfl_xor_sync(0xffffffffu, a, sh);   // the G lanes of a row are adjacent
+      sc[j] = (j0 + j < N) ? a : -CUDART_INF_F;
+    }
+    float mx = sc[0];
+#pragma unroll
+    for (int j = 1; j < KT; ++j) mx = fmaxf(mx, sc[j]);
+    const float m_new = fmaxf(m, mx);
+    const float f = exp2f((m - m_new) * kLog2e);     // first tile: exp2(-inf) = 0
+    m = m_new;
+    l *= f;
+#pragma unroll
+    for (int c = 0; c < DT; ++c) o[c] *= f;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      const float pj = exp2f((sc[j] - m) * kLog2e);
+      l += pj;
+      const float* vr = &Vs[j * PITCH + g * (DT + 4)];
+#pragma unroll
+      for (int c = 0; c < DT; c += 4) {
+        const float4 v4 = *reinterpret_cast<const float4*>(vr + c);
+        o[c] = fmaf(pj, v4.x, o[c]);
+        o[c + 1] = fmaf(pj, v4.y, o[c + 1]);
+        o[c + 2] = fmaf(pj, v4.z, o[c + 2]);
+        o[c + 3] = fmaf(pj, v4.w, o[c + 3]);
+      }
+    }
+  }
+  if (!valid) return;
+  const float inv = 1.f / l;
+  const int HW = H * W;
+  const int t = row / HW, hw = row % HW, hh = hw / W, ww = hw % W;
+  const float* xr = base + (long long)row * 4 * D + g * DT;
+  float* yb = y + b * ysB + hh * ysH + ww * ysW + g * DT;
+#pragma unroll
+  for (int c = 0; c < DT; ++c) {
+    const int ch = g * DT + c;
+    const float a = fmaf(gamma, o[c] * inv, xr[c]);
+    o[c] = fmaxf(fmaf(a, __ldg(bn_scale + ch), __ldg(bn_shift + ch)), 0.f);
+  }
+  for (int r = 0; r < alpha; ++r) {
+    float* yp = yb + (long long)(t * alpha + r) * ysT;
+#pragma unroll
+    for (int c = 0; c < DT; ++c) yp[c] = o[c];
+  }
+}
+
 static bool f32_view_ok(const esf_view* v) { return view_ok(v) && v->dtype == ESF_F32; }
 static bool same_pos(const esf_view* a, const esf_view* b) {
   return a->B == b->B && a->T == b->T && a->H == b->H && a->W == b->W;
@@ -329,4 +439,29 @@ extern "C" int esf_p32_head_pool(const esf_view* x, float* feat, int32_t feat_st
   p32_head_pool_kernel<<<dim3((x->C + 255) / 256, x->B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       to_v32(x), feat, feat_stride, feat_off);
   return check_launch("p32_head_pool_kernel");
+}
+
+extern "C" int esf_p32_attention(const float* proj, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d, float gamma,
+                                 const float* bn_scale, const float* bn_shift, int32_t alpha, const esf_view* y,
+                                 void* stream) {
+  ESF_CHECK_ARG(proj && bn_scale && bn_shift && f32_view_ok(y), "esf_p32_attention: null / non-FP32 argument");
+  ESF_CHECK_ARG(y->B == B && y->T == T * alpha && y->H == H && y->W == W && y->C == d,
+                "esf_p32_attention: output slice shape mismatch");
+  ESF_CHECK_ARG(reinterpret_cast<uintptr_t>(proj) % 16 == 0, "esf_p32_attention: proj must be 16-byte aligned");
+  const int N = T * H * W;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* yp = static_cast<float*>(y->ptr);
+#define ESF_P32_ATTN(DD)                                                                                              \
+  p32_attn_kernel<DD><<<dim3(cdiv(N, 128 / (DD / (DD < 32 ? DD : 32))), B), 128, 0, s>>>(                             \
+      proj, N, T, H, W, gamma, bn_scale, bn_shift, alpha, yp, y->sB, y->sT, y->sH, y->sW)
+  switch (d) {
+    case 8: ESF_P32_ATTN(8); break;
+    case 16: ESF_P32_ATTN(16); break;
+    case 32: ESF_P32_ATTN(32); break;
+    case 64: ESF_P32_ATTN(64); break;
+    case 128: ESF_P32_ATTN(128); break;
+    default: return set_error(ESF_ERR_UNSUPPORTED, "esf_p32_attention: head dim %d (8, 16, 32, 64 or 128)", d);
+  }
+#undef ESF_P32_ATTN
+  return check_launch("p32_attn_kernel");
 }

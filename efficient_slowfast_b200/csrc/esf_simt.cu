@@ -45,6 +45,7 @@ struct StemParams {
   int Cout, kT, kH, kW, sT, sH, sW, pT, pH, pW, act;
   int To, Ho, Wo;
   View y;
+  int y_f32;   // FP32 destination (the FP32-accurate path, esf_precise.cu) instead of the 16-bit storage format
 };
 
 template <int CO_T>
@@ -81,6 +82,12 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
           }
         }
       }
+    }
+    if (p.y_f32) {
+      float* yf = reinterpret_cast<float*>(p.y.ptr) + voff(p.y, b, to, ho, wo) + cg * CO_T;
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j) yf[j] = apply_act(acc[j], p.act);
+      continue;
     }
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + voff(p.y, b, to, ho, wo) + cg * CO_T;
     if constexpr (CO_T == 8) {
@@ -2005,6 +2012,7 @@ extern "C" int esf_stem_conv(const float* x, int32_t B, int32_t Cin, int32_t T, 
   p.Ho = (H + 2 * pH - kH) / sH + 1;
   p.Wo = (W + 2 * pW - kW) / sW + 1;
   p.y = to_view(y);
+  p.y_f32 = y->dtype == ESF_F32;
   ESF_CHECK_ARG(y->B == B && y->T == p.To && y->H == p.Ho && y->W == p.Wo && y->C == Cout,
                 "esf_stem_conv: output view (%d,%d,%d,%d,%d) != expected (%d,%d,%d,%d,%d)", y->B, y->T, y->H, y->W,
                 y->C, B, p.To, p.Ho, p.Wo, Cout);

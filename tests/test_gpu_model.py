@@ -33,7 +33,8 @@ def _run(name, tag, precision="fp16"):
                                       ("mobilenetv2_w1", "s224"), ("ghostnet_w1", "s112"), ("ghostnet_w1", "s64"), ("ghostnet_w1", "s224"),
                                       ("i3d_r50", "s224"), ("slow_r50", "s64"),
                                       ("slow_nln_r50", "s64"), ("i3d_nln_r50", "s96"),
-                                      ("slowfast_r50_fcn", "s96"), ("slowfast_r50_fcn", "s64"), ("slow_r50", "s96")])
+                                      ("slowfast_r50_fcn", "s96"), ("slowfast_r50_fcn", "s64"), ("slow_r50", "s96"),
+                                      ("slowfast_r50_g2", "s64")])
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 def test_model_matches_reference_golden(esf_lib, name, tag, precision):
     cfg, model, gold, y = _run(name, tag, precision)

@@ -207,3 +207,35 @@ def test_caffe2_checkpoint_loads(tmp_path):
         if key in sd:
             assert torch.equal(after[key], torch.tensor(blobs[c2])), key
     assert esf.load_checkpoint.last_report["skipped"] == ["res9_0_branch2a_w"]
+
+
+def test_fp32_path_operand_split_reproduces_fp32_conv():
+    """The algebra of the FP32-accurate plan (engine_fp32.py), on the host: activation planes [hi | lo | hi], weight
+    [w_hi | w_hi | w_lo] with power-of-two row scaling -> an ordinary convolution over 3 C channels whose result,
+    un-scaled, equals the FP32 convolution to ~2^-22 -- also when the input is a channel slice of a wider concat
+    buffer (zero weights on the other channels)."""
+    import torch.nn.functional as F
+    from efficient_slowfast_b200.engine_fp32 import split_weight_rows
+
+    g = torch.Generator().manual_seed(0)
+    ctot, c0, cin, cout = 24, 8, 16, 12
+    x = torch.randn(2, ctot, 3, 5, 5, generator=g) * 3.0
+    w = torch.randn(cout, cin, 3, 1, 1, generator=g).double() * 0.02 * torch.logspace(-3, 1, cout).double().view(-1, 1, 1, 1, 1)
+    hi, lo, inv = split_weight_rows(w)
+    assert torch.equal(hi, hi.half().double()) and torch.equal(lo, lo.half().double())
+    assert (lo.abs().amax(dim=(1, 2, 3, 4)) > 6.2e-5).all()          # w_lo stays a normal FP16 number in every row
+    plane = ctot
+    w3 = torch.zeros(cout, 3 * plane, 3, 1, 1, dtype=torch.float64)
+    w3[:, c0:c0 + cin] = hi
+    w3[:, plane + c0:plane + c0 + cin] = hi
+    w3[:, 2 * plane + c0:2 * plane + c0 + cin] = lo
+    x_hi = x.half()
+    x_lo = (x - x_hi.float()).half()
+    x3 = torch.cat([x_hi, x_lo, x_hi], dim=1).double()
+    got = F.conv3d(x3, w3, padding=(1, 0, 0)) * inv.view(1, -1, 1, 1, 1)
+    want = F.conv3d(x[:, c0:c0 + cin].double(), w, padding=(1, 0, 0))
+    err = ((got - want).abs().amax(dim=(0, 2, 3, 4)) / want.abs().amax(dim=(0, 2, 3, 4))).max().item()
+    assert err < 2e-6, err
+    # the same product with single FP16 operands is three orders of magnitude worse
+    plain = F.conv3d(x[:, c0:c0 + cin].half().double(), w.half().double(), padding=(1, 0, 0))
+    assert ((plain - want).abs().amax() / want.abs().amax()).item() > 1e-4

@@ -16,7 +16,8 @@ from oracle import slowfast_oracle as O
                                       ("mobilenetv2_w1", "s224"), ("ghostnet_w1", "s112"), ("ghostnet_w1", "s64"), ("ghostnet_w1", "s224"),
                                       ("i3d_r50", "s224"), ("slow_r50", "s64"),
                                       ("slow_nln_r50", "s64"), ("i3d_nln_r50", "s96"),
-                                      ("slowfast_r50_fcn", "s96"), ("slowfast_r50_fcn", "s64"), ("slow_r50", "s96")])
+                                      ("slowfast_r50_fcn", "s96"), ("slowfast_r50_fcn", "s64"), ("slow_r50", "s96"),
+                                      ("slowfast_r50_g2", "s64")])
 def test_oracle_matches_reference_golden(name, tag):
     cfg, model, gold = helpers.case_model_and_weights(name)
     xs = helpers.case_inputs(name, tag)
