@@ -54,6 +54,8 @@ struct __align__(64) AttnTcParams {
   uint32_t q_tile_bytes, k_tile_bytes, v_tile_bytes;
   int f16;  // 16-bit operands (Q~, K~, V^T, P) and the output are IEEE half instead of BF16
   int out_f32;  // the output view is FP32 (FP32-accurate path, esf_precise.cu); strides stay in elements
+  int pdbl;     // v2 kernel: two P buffers per (query tile, half) -- TMEM has the columns when DVp <= 32 (d < 32)
+  int qk_async; // v2 kernel: the Q.K^T issuer serves the two query tiles independently (no lock step)
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -438,9 +440,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
   uint64_t* kv_empty = kv_full + kTcMaxStages;
   uint64_t* s_full = kv_empty + kTcMaxStages;  // [q][buf]
   uint64_t* s_free = s_full + 4;
-  uint64_t* p_full = s_free + 4;               // [q][h]
-  uint64_t* p_free = p_full + 4;
-  uint64_t* o_full = p_free + 4;               // [q]
+  uint64_t* p_full = s_free + 4;               // [q][h][buffer]
+  uint64_t* p_free = p_full + 8;
+  uint64_t* o_full = p_free + 8;               // [q]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = uniform_warp_idx();
@@ -449,6 +451,12 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
   const int row0 = blockIdx.x * 256;
   const int N = p.N;
   const int nt = (N + kTcBN - 1) / kTcBN;
+  // P buffers: one per (q, h) at columns 448.., or two (tile j uses buffer j & 1) at columns 384.. when O leaves room.
+  // With one buffer the P store of tile j waits for the P.V MMA of tile j - 1, which queues behind the Q.K^T MMAs of
+  // tile j + 1 on the in-order tensor pipe (ncu: 4.7 % of the softmax warps' samples sit in that wait).
+  const int pdbl = p.pdbl;
+  const uint32_t p_col0 = pdbl ? 384u : (uint32_t)kV2PCol;
+  const uint32_t p_qh_cols = pdbl ? 32u : 16u;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -459,6 +467,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 8);   // 8 softmax warps read every S tile
+    }
+    for (int i = 0; i < 8; ++i) {
       mbar_init(&p_full[i], 4);
       mbar_init(&p_free[i], 1);
     }
@@ -514,30 +524,66 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
     const uint32_t k_stage_step = p.k_tile_bytes >> 4;
     mbar_wait(q_full, 0, 33);
     tc_fence_after();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int c = 0; c < nt; ++c) {
-      const int buf = c & 1;
-      mbar_wait(&kv_full[stage], phase, 34);
+    auto issue_s = [&](int q, int c, int stage) {
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + (q * 2 + (c & 1)) * kTcBN;
+        const uint32_t kb = k_lo + stage * k_stage_step;
+        const uint32_t q_lo = q_lo0 + q * q_step;
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        mbar_wait(&s_free[q * 2 + buf], ((c >> 1) & 1) ^ 1, 32);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t d_tmem = tmem_base + (q * 2 + buf) * kTcBN;
-          const uint32_t kb = k_lo + stage * k_stage_step;
-          const uint32_t q_lo = q_lo0 + q * q_step;
-#pragma unroll
-          for (int i = 0; i < 6; ++i)
-            if (i < p.nsteps2)
-              umma_bf16_lohi(d_tmem, q_lo + (p.steps2[i] & 0xffff), qk_hi, kb + (p.steps2[i] >> 16), qk_hi, idesc_s, i != 0);
-          umma_commit(&s_full[q * 2 + buf]);
-        }
-        __syncwarp();
+        for (int i = 0; i < 6; ++i)
+          if (i < p.nsteps2)
+            umma_bf16_lohi(d_tmem, q_lo + (p.steps2[i] & 0xffff), qk_hi, kb + (p.steps2[i] >> 16), qk_hi, idesc_s, i != 0);
+        umma_commit(&s_full[q * 2 + (c & 1)]);
       }
-      if (++stage == p.stages) {
-        stage = 0;
-        phase ^= 1;
+      __syncwarp();
+    };
+    if (p.qk_async) {
+      // The two query tiles advance independently: whichever has its S buffer free (and its K tile landed) gets its
+      // next Q.K^T issued.  In lock step (the loop below) a late warp of one tile also delays the other tile's scores,
+      // and all sixteen softmax warps reach their MUFU phase together (ncu: 6 % of their samples wait for S).
+      int cq[2] = {0, 0}, stq[2] = {0, 0};
+      uint32_t phq[2] = {0, 0};
+      uint32_t spins = 0;
+      uint64_t t0 = 0;
+      while (cq[0] < nt || cq[1] < nt) {
+        bool progress = false;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = cq[q];
+          if (c >= nt) continue;
+          if (!mbar_try_wait(&kv_full[stq[q]], phq[q])) continue;
+          if (!mbar_try_wait(&s_free[q * 2 + (c & 1)], ((c >> 1) & 1) ^ 1)) continue;
+          tc_fence_after();
+          issue_s(q, c, stq[q]);
+          cq[q] = c + 1;
+          if (++stq[q] == p.stages) stq[q] = 0, phq[q] ^= 1;
+          progress = true;
+        }
+        if (!progress && ((++spins) & 0xfff) == 0) {   // bounded like mbar_wait: a pipeline bug traps instead of hanging
+          const uint64_t now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > ESF_WAIT_TIMEOUT_NS) {
+            if (lane == 0) printf("[esf] attention Q.K issuer timeout: block %d tiles %d/%d of %d\n", (int)blockIdx.x, cq[0], cq[1], nt);
+            __trap();
+          }
+        }
+        if (progress) spins = 0, t0 = 0;
+      }
+    } else {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < nt; ++c) {
+        mbar_wait(&kv_full[stage], phase, 34);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          mbar_wait(&s_free[q * 2 + (c & 1)], ((c >> 1) & 1) ^ 1, 32);
+          tc_fence_after();
+          issue_s(q, c, stage);
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else if (warp == 18 || warp == 19) {
@@ -552,16 +598,18 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
     for (int j = 0; j < nt; ++j) {
       mbar_wait(&kv_full[stage], phase, 35);   // already complete (S_j was computed from this stage): visibility only
       const uint32_t vl = v_lo + stage * v_stage_step;
+      const int pb = pdbl ? (j & 1) : 0;                       // P buffer of this tile
+      const uint32_t p_par = pdbl ? ((j >> 1) & 1) : (j & 1);   // parity of this use of the buffer
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        mbar_wait(&p_full[q * 2 + h], j & 1, 36);
+        mbar_wait(&p_full[(q * 2 + h) * 2 + pb], p_par, 36);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t o_tmem = tmem_base + 4 * kTcBN + (q * 2 + h) * p.DVp;
-          const uint32_t p_tmem = tmem_base + kV2PCol + (q * 2 + h) * 16;
+          const uint32_t p_tmem = tmem_base + p_col0 + (q * 2 + h) * p_qh_cols + pb * 16;
           umma_f16_ts(o_tmem, p_tmem, vl + 4 * h, pv_hi, idesc_o, j != 0);      // keys 32h .. 32h+15
           umma_f16_ts(o_tmem, p_tmem + 8, vl + 4 * h + 2, pv_hi, idesc_o, 1);  // keys 32h+16 .. 32h+31
-          umma_commit(&p_free[q * 2 + h]);
+          umma_commit(&p_free[(q * 2 + h) * 2 + pb]);
           if (h == 1) {
             umma_commit(&kv_empty[stage]);
             if (j == nt - 1) umma_commit(&o_full[q]);
@@ -583,7 +631,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
     const int n = row0 + q * 128 + r;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t o_addr = lane_addr + 4 * kTcBN + (q * 2 + h) * p.DVp;
-    const uint32_t p_addr = lane_addr + kV2PCol + (q * 2 + h) * 16;
+    const uint32_t p_addr0 = lane_addr + p_col0 + (q * 2 + h) * p_qh_cols;
     const bool tail = (N % kTcBN) != 0;
     float m = -CUDART_INF_F;
     // 12 * ln 2: p = exp(s - m) stays <= 4096, inside FP16 and harmless in the FP32 sums; a larger window means
@@ -624,7 +672,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[q * 2 + h]);
+          if (lane == 0) mbar_arrive(&p_full[(q * 2 + h) * 2 + (pdbl ? ((j - 1) & 1) : 0)]);
         }
         mx0 = fmaxf(fmaxf(mx0, v[i]), v[i + 1]);
         mx1 = fmaxf(fmaxf(mx1, v[i + 2]), v[i + 3]);
@@ -682,10 +730,19 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
       for (int i = 0; i < 16; ++i) pk[i] = pack16x2(v[2 * i], v[2 * i + 1], F16);
       asm volatile("" ::"r"(pk[15]));
       ESF_TICK(3)   // pack
-      mbar_wait(&p_free[q * 2 + h], (j & 1) ^ 1, 38);
+      const int pb = pdbl ? (j & 1) : 0;
+      const uint32_t p_par = pdbl ? ((j >> 1) & 1) : (j & 1);
+      const uint32_t p_addr = p_addr0 + pb * 16;
+      mbar_wait(&p_free[(q * 2 + h) * 2 + pb], p_par ^ 1, 38);   // the previous use of this P buffer has been consumed
       tc_fence_after();
       ESF_TICK(4)   // wait p_free
       if (j > 0 && any_raise) {
+        // O may only be touched while no P.V MMA of this (q, h) is in flight: with two P buffers that also means the
+        // MMA of tile j - 1 (the other buffer)
+        if (pdbl) {
+          mbar_wait(&p_free[(q * 2 + h) * 2 + (pb ^ 1)], ((j - 1) >> 1) & 1, 40);
+          tc_fence_after();
+        }
         for (int c0 = 0; c0 < p.DVp; c0 += 16) {
           float o[16];
           tmem_ld16(o_addr + c0, o);
@@ -699,7 +756,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[q * 2 + h]);
+        if (lane == 0) mbar_arrive(&p_full[(q * 2 + h) * 2 + pb]);
       }
       ESF_TICK(5)   // O rescale + P store + p_full arrive
       if (j + 1 < nt) {
@@ -1099,6 +1156,19 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
   p.k_tile_bytes = kTcBN * g.KQ * 2;
   p.v_tile_bytes = g.DVp * 128;
   op->v2 = g.v2;
+  {
+    // Measured (round 2, gpurun_out/r2_s4, profiles/r2_attention_experiments.md): a second P buffer (d < 32) and an
+    // independent Q.K^T issue of the two query tiles are both correct (kernel tests) and change nothing: d = 8
+    // 2.993 / 3.002 / 2.980 / 2.989 ms, d = 32 3.214 / 3.212 / 3.219 / 3.217 ms (16 clips, N = 25 088; off-off, P, QK,
+    // both).  The waits they remove (ncu: 4.7 % + 6 % of the softmax warps' samples) are not what bounds the loop.
+    // Both stay OFF by default; ESF_ATTN_PDBL=1 / ESF_ATTN_QKASYNC=1 enable them for A/B runs.
+    const char* e = getenv("ESF_ATTN_PDBL");
+    p.pdbl = (g.v2 && g.DVp <= 32 && e && atoi(e) == 1) ? 1 : 0;
+  }
+  {
+    const char* e = getenv("ESF_ATTN_QKASYNC");   // A/B knob: 1 = independent issue of the two query tiles
+    p.qk_async = (e && atoi(e) == 1) ? 1 : 0;
+  }
   {
     const char* e = getenv("ESF_ATTN_POLY");   // experiment knob; default chosen from measurements (see header)
     op->poly = e ? atoi(e) : kV2DefaultPoly;

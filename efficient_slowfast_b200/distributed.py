@@ -58,11 +58,22 @@ def bind_to_gpu_numa_node(device_index, sysfs="/sys"):
     try:
         bus = torch.cuda.get_device_properties(device_index)
         pci = "%04x:%02x:%02x.0" % (bus.pci_domain_id, bus.pci_bus_id, bus.pci_device_id)
-        with open(os.path.join(sysfs, "bus/pci/devices", pci, "numa_node")) as fh:
-            node = int(fh.read().strip())
+        node_dir = os.path.join(sysfs, "devices/system/node")
+        nodes = sorted(int(n[4:]) for n in os.listdir(node_dir) if n.startswith("node") and n[4:].isdigit())
+        how = "sysfs"
+        try:
+            with open(os.path.join(sysfs, "bus/pci/devices", pci, "numa_node")) as fh:
+                node = int(fh.read().strip())
+        except OSError:
+            node = -1
         if node < 0:
-            return {"skipped": "device %s reports no NUMA node" % pci}
-        with open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)) as fh:
+            # virtualised PCI topology (the device reports no node): on HGX boards GPUs are split evenly and in order
+            # over the sockets, so the device ordinal picks the node
+            if len(nodes) < 2:
+                return {"skipped": "device %s reports no NUMA node and the host shows %d node(s)" % (pci, len(nodes))}
+            node = nodes[min(len(nodes) - 1, device_index * len(nodes) // max(1, torch.cuda.device_count()))]
+            how = "ordinal"
+        with open(os.path.join(node_dir, "node%d/cpulist" % node)) as fh:
             cpus = _parse_cpulist(fh.read())
         allowed = os.sched_getaffinity(0)
         use = cpus & allowed
@@ -70,6 +81,6 @@ def bind_to_gpu_numa_node(device_index, sysfs="/sys"):
             return {"skipped": "no allowed CPU on node %d" % node}
         os.sched_setaffinity(0, use)
         torch.set_num_threads(max(1, min(torch.get_num_threads(), len(use))))
-        return {"node": node, "cpus": len(use)}
+        return {"node": node, "cpus": len(use), "nodes": len(nodes), "how": how}
     except Exception as e:  # noqa: BLE001 -- best effort by design
         return {"skipped": "%s: %s" % (type(e).__name__, e)}

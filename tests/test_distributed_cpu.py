@@ -61,3 +61,16 @@ def test_shard_batch_requires_divisible_batch():
     a, = D.shard_batch([torch.arange(8).reshape(4, 2)], 1, 2)
     assert a.tolist() == [[4, 5], [6, 7]]
     assert D.all_gather([torch.ones(2)])[0].tolist() == [1.0, 1.0]   # no process group: identity
+
+
+def test_numa_bind_is_best_effort_and_never_raises(tmp_path):
+    """bind_to_gpu_numa_node on a box without a GPU / with a hidden topology reports why it did nothing."""
+    import os
+
+    from efficient_slowfast_b200 import distributed as esf_dist
+
+    before = os.sched_getaffinity(0)
+    out = esf_dist.bind_to_gpu_numa_node(0, sysfs=str(tmp_path))
+    assert "skipped" in out or "node" in out
+    assert os.sched_getaffinity(0) == before or "node" in out
+    assert esf_dist._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}

@@ -47,5 +47,35 @@ def main(path):
         print()
 
 
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def traffic(path, label, batch, out="profiles/ncu_traffic.json"):
+    """--traffic: append {label, batch, dram bytes read / written, ncu duration, source} of the FIRST kernel of an
+    `ncu --set full` capture to profiles/ncu_traffic.json -- what bench.py reports as roofline.traffic."""
+    import json
+    import os
+
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    H, U, r = rows[0], rows[1], rows[2]
+    d = {h: (u, v) for h, u, v in zip(H, U, r)}
+
+    def nbytes(k):
+        return float(d[k][1].replace(",", "")) * UNIT[d[k][0]]
+
+    ent = {"label": label, "batch": int(batch), "kernel": d["Kernel Name"][1], "grid": d["Grid Size"][1],
+           "dram_bytes_read": nbytes("dram__bytes_read.sum"), "dram_bytes_write": nbytes("dram__bytes_write.sum"),
+           "ncu_duration": "%s %s" % (d["gpu__time_duration.sum"][1], d["gpu__time_duration.sum"][0]),
+           "source": "ncu --set full --clock-control none, %s" % os.path.basename(path)}
+    cur = json.load(open(out)) if os.path.exists(out) else []
+    cur = [e for e in cur if not (e["label"] == label and e["batch"] == int(batch))] + [ent]
+    json.dump(cur, open(out, "w"), indent=1)
+    print(json.dumps(ent))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if sys.argv[1] == "--traffic":     # python tools/ncu_summary.py --traffic x.ncu-rep "attention N=25088 d=32" 64
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        main(sys.argv[1])

@@ -22,14 +22,14 @@ g = torch.Generator().manual_seed(0)
 proj = torch.randn(B * N, 4 * d, generator=g).to(DEV)
 proj[:, d:3 * d] *= 1.0 / d ** 0.25
 alpha = 4
-ybuf = torch.zeros(B, T * alpha, HW, HW, 2 * d, dtype=torch.bfloat16, device=DEV)
+ybuf = torch.zeros(B, T * alpha, HW, HW, 2 * d, dtype=torch.float16, device=DEV)   # FP16: the default storage format
 yv = rt.view(ybuf[..., :d])
 sc = torch.ones(d, device=DEV)
 sh = torch.zeros(d, device=DEV)
 s = rt.current_stream_ptr()
 if impl == "tc":
     packed = torch.empty(L.esf_attn_tc_pack_bytes(B, N, d), dtype=torch.uint8, device=DEV)
-    rt.check(L.esf_attn_tc_pack(proj.data_ptr(), B, N, d, rt.BF16, packed.data_ptr(), s))
+    rt.check(L.esf_attn_tc_pack(proj.data_ptr(), B, N, d, rt.F16, packed.data_ptr(), s))
     h = ctypes.c_void_p()
     rt.check(L.esf_attn_tc_create(packed.data_ptr(), B, T, HW, HW, d, 0.5, sc.data_ptr(), sh.data_ptr(), alpha,
                                   ctypes.byref(yv), ctypes.byref(h)))
