@@ -390,10 +390,11 @@ static PackLayout pack_layout(long long rows, const PackGeom& g) {
 template <int DV, int DK, int MB>
 static int launch_attn(const AttnParams& p, cudaStream_t s) {
   using Cfg = AttnCfg<DV, DK, MB>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned char attr_done[kMaxDevices] = {0};   // kernel attributes are per device
+  unsigned char* slot = device_slot(attr_done);
+  if (!slot || !*slot) {
     ESF_CUDA(cudaFuncSetAttribute(attn_kernel<DV, DK, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes));
-    attr_set = true;
+    if (slot) *slot = 1;
   }
   dim3 grid(cdiv(p.N, Cfg::BM), p.B);
   attn_kernel<DV, DK, MB><<<grid, kAttnThreads, Cfg::smem_bytes, s>>>(p);
@@ -473,10 +474,11 @@ extern "C" int esf_attn_generic(const float* proj, int32_t B, int32_t T, int32_t
   const int N = T * H * W;
   const size_t smem = (size_t)4 * N * sizeof(float);
   ESF_CHECK_ARG(smem <= 160 * 1024, "esf_attn_generic: N = %d too large for the fallback kernel", N);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned char attr_done[kMaxDevices] = {0};
+  unsigned char* slot = device_slot(attr_done);
+  if (!slot || !*slot) {
     ESF_CUDA(cudaFuncSetAttribute(attn_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+    if (slot) *slot = 1;
   }
   attn_generic_kernel<<<dim3(cdiv(N, 4), B), 128, smem, static_cast<cudaStream_t>(stream)>>>(
       proj, N, T, H, W, d, gamma, bn_scale, bn_shift, alpha, y->dtype == ESF_F16, static_cast<__nv_bfloat16*>(y->ptr),

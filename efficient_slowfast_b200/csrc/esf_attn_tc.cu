@@ -1190,8 +1190,9 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
     rc = encode3(&p.v_map, p.f16, base + L.v_off, N, g.DVp, B, (uint64_t)L.Npad * 2, (uint64_t)g.DVp * L.Npad * 2, kTcBN, g.DVp,
                  CU_TENSOR_MAP_SWIZZLE_128B, "attention V^T");
   if (rc == ESF_OK) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned char attr_done[kMaxDevices] = {0};   // kernel attributes are per device
+    unsigned char* slot = device_slot(attr_done);
+    if (!slot || !*slot) {
       cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
 #define ESF_V2_ATTR(PL)                                                                                                  \
   if (e == cudaSuccess)                                                                                                  \
@@ -1201,7 +1202,7 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
       ESF_V2_ATTR(0) ESF_V2_ATTR(1) ESF_V2_ATTR(2) ESF_V2_ATTR(3) ESF_V2_ATTR(4)
 #undef ESF_V2_ATTR
       if (e != cudaSuccess) rc = set_error(ESF_ERR_CUDA, "cudaFuncSetAttribute(attn_tc) failed: %s", cudaGetErrorString(e));
-      else attr_set = true;
+      else if (slot) *slot = 1;
     }
   }
   if (rc != ESF_OK) {

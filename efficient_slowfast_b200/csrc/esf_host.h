@@ -42,7 +42,16 @@ inline bool is16(int dtype) { return dtype == ESF_BF16 || dtype == ESF_F16; }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-int num_sms();  // SM count of the current device (cached); 0 when there is no device
+int num_sms();  // SM count of the CURRENT device (cached per device ordinal); 0 when there is no device
+
+// Kernel attributes (max dynamic shared memory) are per DEVICE: a process-wide "already set" flag would skip the second
+// GPU of a process.  Returns the slot of the current device in a per-call-site table (or nullptr: always set).
+constexpr int kMaxDevices = 64;
+inline unsigned char* device_slot(unsigned char (&table)[kMaxDevices]) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  return &table[dev];
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

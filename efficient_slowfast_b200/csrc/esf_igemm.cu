@@ -619,13 +619,13 @@ static int encode_act_map(CUtensorMap* m, CUtensorMapDataType dt, int esize, voi
   return ESF_OK;
 }
 
-static int g_num_sms = 0;
+static int g_num_sms[kMaxDevices] = {0};
 int num_sms() {
-  if (g_num_sms > 0) return g_num_sms;
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < kMaxDevices && g_num_sms[dev] > 0) return g_num_sms[dev];
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-  g_num_sms = n;
+  if (dev >= 0 && dev < kMaxDevices) g_num_sms[dev] = n;
   return n;
 }
 
@@ -664,11 +664,12 @@ static int finish_op(IgemmOp* op) {
   const int sms = num_sms();
   if (sms <= 0) return set_error(ESF_ERR_CUDA, "no CUDA device");
   op->grid = std::min(op->params.num_tiles, sms);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned char attr_done[kMaxDevices] = {0};
+  unsigned char* slot = device_slot(attr_done);
+  if (!slot || !*slot) {
     cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return set_error(ESF_ERR_CUDA, "cudaFuncSetAttribute(igemm) failed: %s", cudaGetErrorString(e));
-    attr_set = true;
+    if (slot) *slot = 1;
   }
   return ESF_OK;
 }
