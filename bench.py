@@ -413,7 +413,9 @@ def run_gpu(args):
     host[-1].normal_()
     if alpha:
         host[0].copy_(recipe.pack_pathway_output(host[1], alpha)[0])
-    e2e_steps = max(2, args.e2e_steps if args.e2e_steps > 0 else args.steps)
+    # the loop is a pipeline: its fill (first copy) and drain (last forward) cost one extra step in total, so it is
+    # timed over at least 30 batches -- a test run streams thousands
+    e2e_steps = max(2, args.e2e_steps if args.e2e_steps > 0 else max(args.steps, 30))
 
     def e2e_measure(**kw):
         stream = ClipStream(model, shapes, dev, depth=args.e2e_depth, gather=world > 1, **kw)
@@ -438,6 +440,9 @@ def run_gpu(args):
     ceiling = h2d_ceiling(h, e2e["h2d_bytes_per_step"])
     e2e["h2d_ceiling_gbs"] = ceiling
     e2e["h2d_achieved_gbs"] = world * e2e["h2d_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9
+    e2e["h2d_frac_of_ceiling"] = e2e["h2d_achieved_gbs"] / ceiling
+    e2e["bound"] = "host-to-device copies (all ranks share the host's PCIe / memory path)" \
+        if e2e["h2d_frac_of_ceiling"] > 0.85 else "forward"
     e2e["numa_bind"] = h.numa
 
     # ---- the same loop fed with the decoder's uint8 frames: model.forward_frames does the reference

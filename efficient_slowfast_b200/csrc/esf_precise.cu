@@ -59,6 +59,7 @@ struct PostParams {
   const float* scale;
   const float* bias;
   int act, plane;
+  int worder;   // 0: activation planes [hi | lo | hi];  1: weight-operand planes [hi | hi | lo] (per-clip "weights")
 };
 
 template <int VEC>
@@ -117,12 +118,12 @@ __global__ void __launch_bounds__(256) p32_post_kernel(const PostParams p) {
       if constexpr (VEC == 8) {
         const uint4 H = *reinterpret_cast<const uint4*>(hi), L = *reinterpret_cast<const uint4*>(lo);
         *reinterpret_cast<uint4*>(y) = H;
-        *reinterpret_cast<uint4*>(y + p.plane) = L;
-        *reinterpret_cast<uint4*>(y + 2 * p.plane) = H;
+        *reinterpret_cast<uint4*>(y + p.plane) = p.worder ? H : L;
+        *reinterpret_cast<uint4*>(y + 2 * p.plane) = p.worder ? L : H;
       } else {
         y[0] = hi[0];
-        y[p.plane] = lo[0];
-        y[2 * p.plane] = hi[0];
+        y[p.plane] = p.worder ? hi[0] : lo[0];
+        y[2 * p.plane] = p.worder ? lo[0] : hi[0];
       }
     }
   }
@@ -358,6 +359,36 @@ __global__ void __launch_bounds__(128) p32_attn_kernel(const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------- Non-local row softmax (FP32)
+// P[r][:] = softmax(scale * S[r][:]) (mode 0) or scale * S[r][:] (mode 1), written as the three planes [hi | lo | hi]
+// (plane pitch `plane` elements, row pitch p_pitch) that the second product reads as its A operand.  One warp per row.
+__global__ void __launch_bounds__(256) p32_row_softmax_kernel(const float* __restrict__ S, long long rows, int n,
+                                                              long long s_pitch, float scale, int mode,
+                                                              __half* __restrict__ P, long long p_pitch, int plane) {
+  const int lane = threadIdx.x & 31;
+  const long long r = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* s = S + r * s_pitch;
+  float m = -CUDART_INF_F, l = 1.f;
+  if (mode == 0) {
+    for (int j = lane; j < n; j += 32) m = fmaxf(m, s[j] * scale);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    l = 0.f;
+    for (int j = lane; j < n; j += 32) l += expf(s[j] * scale - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  }
+  const float inv = 1.f / l;
+  __half* p = P + r * p_pitch;
+  for (int j = lane; j < n; j += 32) {
+    const float v = mode == 0 ? expf(s[j] * scale - m) * inv : s[j] * scale;
+    __half hi, lo;
+    split_hi_lo(v, hi, lo);
+    p[j] = hi, p[plane + j] = lo, p[2 * plane + j] = hi;
+  }
+}
+
 static bool f32_view_ok(const esf_view* v) { return view_ok(v) && v->dtype == ESF_F32; }
 static bool same_pos(const esf_view* a, const esf_view* b) {
   return a->B == b->B && a->T == b->T && a->H == b->H && a->W == b->W;
@@ -373,7 +404,7 @@ static bool vec8_ok(const esf_view* v, int elem) {
 using namespace esf;
 
 extern "C" int esf_p32_post(const esf_view* acc, const float* scale, const float* bias, const esf_view* res, int32_t act,
-                            const esf_view* y32, const esf_view* y3, int32_t plane, void* stream) {
+                            const esf_view* y32, const esf_view* y3, int32_t plane, int32_t weight_order, void* stream) {
   ESF_CHECK_ARG(f32_view_ok(acc), "esf_p32_post: acc must be an FP32 view");
   ESF_CHECK_ARG(!res || !res->ptr || (f32_view_ok(res) && same_pos(res, acc) && res->C == acc->C),
                 "esf_p32_post: residual must be an FP32 view of the accumulator's shape");
@@ -387,7 +418,7 @@ extern "C" int esf_p32_post(const esf_view* acc, const float* scale, const float
   p.res = (res && res->ptr) ? to_v32(res) : null_v32();
   p.y32 = (y32 && y32->ptr) ? to_v32(y32) : null_v32();
   p.y3 = (y3 && y3->ptr) ? to_v32(y3) : null_v32();
-  p.scale = scale, p.bias = bias, p.act = act, p.plane = plane;
+  p.scale = scale, p.bias = bias, p.act = act, p.plane = plane, p.worder = weight_order != 0;
   const long long pos = (long long)acc->B * acc->T * acc->H * acc->W;
   const bool v8 = vec8_ok(acc, 4) && (!p.res.ptr || vec8_ok(res, 4)) && (!p.y32.ptr || vec8_ok(y32, 4)) &&
                   (!p.y3.ptr || (vec8_ok(y3, 2) && plane % 8 == 0));
@@ -464,4 +495,14 @@ extern "C" int esf_p32_attention(const float* proj, int32_t B, int32_t T, int32_
   }
 #undef ESF_P32_ATTN
   return check_launch("p32_attn_kernel");
+}
+
+extern "C" int esf_p32_row_softmax(const float* S, int64_t rows, int32_t n, int64_t s_pitch, float scale, int32_t mode,
+                                   void* P3, int64_t p_pitch, int32_t plane, void* stream) {
+  ESF_CHECK_ARG(S && P3 && rows > 0 && n > 0 && s_pitch >= n && plane >= n && p_pitch >= 3LL * plane,
+                "esf_p32_row_softmax: bad argument");
+  ESF_CHECK_ARG(rows <= 8LL * 0x7fffffff, "esf_p32_row_softmax: too many rows");
+  p32_row_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      S, rows, n, s_pitch, scale, mode, static_cast<__half*>(P3), p_pitch, plane);
+  return check_launch("p32_row_softmax_kernel");
 }

@@ -15,7 +15,7 @@ Concat stays free: a producer writes its channel slice of the FP32 buffer and of
 runs in FP32 on the CUDA cores (esf_p32_attention, flash style): the tcgen05 attention kernel rounds P and V to FP16,
 which alone costs 5e-4 on the probabilities (measured).
 
-Scope: the two ResNet-50 two-stream models (and single-pathway ResNet without Non-local blocks).  About 3x the
+Scope: the two ResNet-50 two-stream models and the single-pathway ResNet (C2D / I3D / Slow), Non-local blocks included.  About 3x the
 tensor-core work and ~5x the activation bytes of the FP16 plan: an accuracy mode, benchmarked beside it.
 """
 import ctypes
@@ -23,7 +23,7 @@ import ctypes
 import torch
 
 from . import runtime as rt
-from .engine import Plan, bn_affine, host64, pack_igemm_weight, to_device
+from .engine import Plan, bn_affine, fold_conv_bn, host64
 
 
 class Act32:
@@ -31,8 +31,9 @@ class Act32:
     (B,T,H,W,3*plane) it is mirrored into at channel offset `c0` of every plane.  Supports the `[..., a:b]` channel
     slicing the model code uses for concat buffers."""
 
-    def __init__(self, f32, x3, plane, c0, c_total):
+    def __init__(self, f32, x3, plane, c0, c_total, weight_order=False):
         self.f32, self.x3, self.plane, self.c0, self.c_total = f32, x3, plane, c0, c_total
+        self.weight_order = weight_order    # planes [hi | hi | lo]: the tensor is the WEIGHT operand of a per-clip GEMM
 
     @property
     def shape(self):
@@ -50,7 +51,7 @@ class Act32:
         assert isinstance(idx, tuple) and len(idx) == 2 and idx[0] is Ellipsis and isinstance(idx[1], slice)
         start, stop, step = idx[1].indices(self.f32.shape[4])
         assert step == 1
-        return Act32(self.f32[..., start:stop], self.x3, self.plane, self.c0 + start, self.c_total)
+        return Act32(self.f32[..., start:stop], self.x3, self.plane, self.c0 + start, self.c_total, self.weight_order)
 
 
 def split_weight_rows(w):
@@ -95,14 +96,15 @@ class PrecisePlan(Plan):
             y32 = rt.null_view() if y.f32.data_ptr() == acc.data_ptr() and scale is None and bias is None and \
                 res is None and act == rt.ACT_NONE else rt.view(y.f32)
             y3, plane = rt.view(y.hi), y.plane
+            worder = int(y.weight_order)
         else:
-            y32, y3, plane = rt.view(y), rt.null_view(), 0
+            y32, y3, plane, worder = rt.view(y), rt.null_view(), 0, 0
         sc = scale.data_ptr() if scale is not None else None
         bs = bias.data_ptr() if bias is not None else None
         self.keep += [av, rv, y32, y3, scale, bias]
         n = acc.numel()
         self._add(lambda s: rt.check(L.esf_p32_post(ctypes.byref(av), sc, bs, ctypes.byref(rv), act, ctypes.byref(y32),
-                                                    ctypes.byref(y3), plane, s), "esf_p32_post"),
+                                                    ctypes.byref(y3), plane, worder, s), "esf_p32_post"),
                   "p32_post", label, nbytes=n * (4 + (4 if res is not None else 0) + (4 if y32.ptr else 0) +
                                                   (6 if y3.ptr else 0)))
 
@@ -113,7 +115,7 @@ class PrecisePlan(Plan):
         [w_hi|w_hi|w_lo] weight (raw FP32 accumulators), then the FP32 post-pass."""
         if groups != 1:
             raise NotImplementedError("grouped convolutions are not part of the FP32-accurate plan (R50 models only)")
-        assert isinstance(x, Act32)
+        assert isinstance(x, Act32) and not x.weight_order
         w = w_folded.to(torch.float64)
         cout, cin = w.shape[:2]
         assert cin == x.shape[4]
@@ -224,4 +226,74 @@ class PrecisePlan(Plan):
         raise NotImplementedError("fully-convolutional testing is not part of the FP32-accurate plan")
 
     def nonlocal_block(self, x, y, nln, group=1):
-        raise NotImplementedError("Non-local blocks are not part of the FP32-accurate plan")
+        """Nonlocal.forward (nonlocal_helper.py:105-148) at FP32 accuracy: theta / phi / g / out are split-operand convs;
+        the two matrix products are per-clip-weight GEMMs on split operands as well -- theta and the normalised affinity
+        are A operands ([hi | lo | hi] planes), the clip's phi rows and transposed g rows are the weight operands
+        ([hi | hi | lo]); the affinity is materialised in FP32 and normalised by esf_p32_row_softmax.  (Not fused: an
+        accuracy mode.)"""
+        if group > 1:
+            raise NotImplementedError("NONLOCAL.GROUP > 1 is not part of the FP32-accurate plan")
+        L = rt.lib()
+        B, T, H, W, C = x.shape
+        d = nln.dim_inner
+        dp = (d + 7) // 8 * 8
+
+        def wb(conv):
+            return host64(conv.weight), host64(conv.bias)
+
+        if nln.use_pool:
+            ps = [int(v) for v in nln.pool_size]
+            Tp, Hp, Wp = (T - ps[0]) // ps[0] + 1, (H - ps[1]) // ps[1] + 1, (W - ps[2]) // ps[2] + 1
+            xp = self.act(B, Tp, Hp, Wp, C)
+            self.pool(x, xp, tuple(ps), tuple(ps), (0, 0, 0))
+        else:
+            Tp, Hp, Wp, xp = T, H, W, x
+        Nq, Nk = T * H * W, Tp * Hp * Wp
+        softmax = nln.instantiation == "softmax"
+        if not softmax and nln.instantiation != "dot_product":
+            raise NotImplementedError("Unknown norm type {}".format(nln.instantiation))
+        theta = self.act(B, T, H, W, d)
+        self.conv(x, theta, *wb(nln.conv_theta))
+        # phi rows of a clip ARE the [n][k] weight matrix of theta^T phi (k = the 3 d plane channels): allocate them
+        # inside a zero-padded (B, n_pad, 3 dp) matrix and view its first Nk rows as the activation
+        kc1, kch1, _, npad1 = rt.igemm_geometry(3 * dp, Nk)
+        assert kc1 * kch1 == 3 * dp, "3 x dim_inner must fill whole K chunks"
+        phi_rows = torch.zeros((B, npad1, 3 * dp), dtype=torch.float16, device=self.device)
+        phi32 = torch.empty((B, Tp, Hp, Wp, d), dtype=torch.float32, device=self.device)
+        phi_x3 = phi_rows.as_strided((B, Tp, Hp, Wp, 3 * dp), (npad1 * 3 * dp, Hp * Wp * 3 * dp, Wp * 3 * dp, 3 * dp, 1))
+        phi = Act32(phi32, phi_x3, dp, 0, d, weight_order=True)
+        g32 = torch.empty((B, Tp, Hp, Wp, d), dtype=torch.float32, device=self.device)
+        g_x3 = torch.zeros((B, Tp, Hp, Wp, 3 * dp), dtype=torch.float16, device=self.device)
+        g = Act32(g32, g_x3, dp, 0, d, weight_order=True)
+        self.keep += [phi_rows, phi32, g32, g_x3]
+        self.conv(xp, phi, *wb(nln.conv_phi))
+        self.conv(xp, g, *wb(nln.conv_g))
+        # affinity S = theta^T phi (FP32), one launch for the whole batch
+        S = self.scratch((B, T, H, W, (Nk + 3) // 4 * 4), torch.float32)
+        zero1 = self.scratch((npad1,), torch.float32, zero=True)
+        self.gemm_rows(theta.x3, S[..., :Nk], phi_rows, zero1, "nl_gemm", "theta.phi x3 N=%dx%d d=%d" % (Nq, Nk, d))
+        # normalise into the [hi | lo | hi] planes of the second product's A operand
+        nkp = (Nk + 7) // 8 * 8
+        P3 = self.scratch((B, T, H, W, 3 * nkp), torch.float16, zero=True)
+        scale, mode = (float(d) ** -0.5, 0) if softmax else (1.0 / Nk, 1)
+        self._add(lambda s: rt.check(L.esf_p32_row_softmax(S.data_ptr(), B * Nq, Nk, S.shape[4], scale, mode, P3.data_ptr(),
+                                                           3 * nkp, nkp, s), "esf_p32_row_softmax"),
+                  "p32_nl_softmax", nln.instantiation, nbytes=B * Nq * Nk * 10.0, exps=float(B * Nq * Nk))
+        # g^T in weight order: gT3[b][c][plane * nkp + k] = plane(g)[b, k, c], planes (hi, hi, lo)
+        kc2, kch2, _, npad2 = rt.igemm_geometry(3 * nkp, d)
+        kpad = kc2 * kch2
+        gT3 = torch.zeros((B, npad2, kpad), dtype=torch.float16, device=self.device)
+        self.keep.append(gT3)
+        for pl in range(3):
+            src = g_x3.data_ptr() + 2 * pl * dp
+            dst = gT3.data_ptr() + 2 * pl * nkp
+            self._add(lambda s, src=src, dst=dst: rt.check(
+                L.esf_transpose16(src, B, Nk, d, Nk * 3 * dp, 3 * dp, dst, npad2 * kpad, kpad, s), "esf_transpose16"),
+                "nl_transpose", "g plane %d" % pl, nbytes=4.0 * B * Nk * d)
+        att = self.act(B, T, H, W, d)
+        acc = self.scratch((B, T, H, W, d), torch.float32)
+        zero2 = self.scratch((npad2,), torch.float32, zero=True)
+        self.gemm_rows(P3, acc, gT3, zero2, "nl_gemm", "p.g x3 N=%dx%d d=%d" % (Nq, Nk, d))
+        self._post(acc, att, label="split")
+        w, bias = fold_conv_bn(nln.conv_out.weight, nln.conv_out.bias, nln.bn)
+        self.conv(att, y, w, bias, res=x)

@@ -243,7 +243,8 @@ int esf_group_mean(const float* in, int32_t B, int32_t P, int32_t K, float* out,
  * axis, i.e. an ordinary convolution with 3x the input channels.  The entry points below are the FP32 element-wise glue:
  *   esf_p32_post:      v = act(acc * scale[c] + bias[c] + res); y32 = v (optional); y3 = planes of v (optional).
  *                      acc / res / y32: FP32 views; y3: FP16 view of the hi plane's channel slice (lo at + plane,
- *                      second hi at + 2 * plane elements).  scale undoes the power-of-two row scaling of the weights.
+ *                      second hi at + 2 * plane elements; weight_order = 1: [hi | hi | lo] instead).  scale undoes the
+ *                      power-of-two row scaling of the weights.
  *   esf_p32_pool3d:    MaxPool3d / AvgPool3d on FP32 views (stem_helper.py:169-171).
  *   esf_p32_eca_fuse:  the FP32 form of esf_eca_fuse (custom_video_model_builder.py:131-135); partial:
  *                      esf_p32_eca_scratch_floats(B, C) floats; C must divide 256.
@@ -253,7 +254,12 @@ int esf_group_mean(const float* in, int32_t B, int32_t P, int32_t K, float* out,
  *                      d in {8, 16, 32, 64, 128}.  (The tcgen05 attention rounds P and V to FP16.)
  * esf_stem_conv accepts an FP32 output view (FP32 CUDA-core stem) and esf_attn_tc_create an FP32 output slice. */
 int esf_p32_post(const esf_view* acc, const float* scale, const float* bias, const esf_view* res, int32_t act,
-                 const esf_view* y32, const esf_view* y3, int32_t plane, void* stream);
+                 const esf_view* y32, const esf_view* y3, int32_t plane, int32_t weight_order, void* stream);
+/* Non-local block in this mode (nonlocal_helper.py:105-148): the clip's own phi / g rows are the "weights" of the two
+ * products, so they are stored in weight order [hi | hi | lo] (esf_p32_post weight_order = 1); esf_p32_row_softmax
+ * turns the FP32 affinity rows into the [hi | lo | hi] planes of softmax(scale * S) (mode 0) or scale * S (mode 1). */
+int esf_p32_row_softmax(const float* S, int64_t rows, int32_t n, int64_t s_pitch, float scale, int32_t mode, void* P3,
+                        int64_t p_pitch, int32_t plane, void* stream);
 int esf_p32_pool3d(const esf_view* x, const esf_view* y, int32_t kT, int32_t kH, int32_t kW, int32_t sT, int32_t sH,
                    int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t is_avg, void* stream);
 int64_t esf_p32_eca_scratch_floats(int32_t B, int32_t C);

@@ -189,7 +189,12 @@ def test_attention_fp32(esf_lib, d, T, H, W, alpha):
     # (FP32 vs FP64 evaluation, SURVEY finding 8), and at N = 25 088 keys the summation order of its materialised
     # softmax matters at that level -- 2e-4 is the bound written for the 224^2 clip
     ("dual_r50", "s64", 1e-4), ("dual_r50", "s224", 2e-4),
-    ("i3d_r50", "s224", 1e-4)])
+    ("i3d_r50", "s224", 1e-4),
+    # Non-local blocks (softmax / dot_product instantiation): the 16-bit plan is held to 4e-2 / 2e-2 on these draws
+    # (tests/test_gpu_model.py: the softmax blocks of this random draw amplify ANY perturbation ~50x more than the plain
+    # I3D trunk) -- the same weights and clips in the FP32-accurate plan: measured 2.8e-4 / 1.8e-4, i.e. 70x / 14x
+    # closer than FP16 storage, and the same ~4x above the plain trunk's 7.8e-5 that the amplification predicts
+    ("i3d_nln_r50", "s96", 5e-4), ("slow_nln_r50", "s64", 3e-4)])
 def test_fp32_path_matches_reference_golden(esf_lib, name, tag, tol):
     cfg, model, gold = helpers.case_model_and_weights(name, "fp32")
     model = model.cuda().eval()
