@@ -21,7 +21,7 @@ from .build import MODEL_REGISTRY
 from .engine import Plan, fold_conv_bn
 
 # video_model_builder.py:16-90 / custom_video_model_builder.py:151-168
-_MODEL_STAGE_DEPTH = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
+_MODEL_STAGE_DEPTH = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 18: (2, 2, 2, 2), 34: (3, 4, 6, 3)}   # 18 / 34: the fork's additions
 _TEMPORAL_KERNEL_BASIS = {     # video_model_builder.py:20-75
     "c2d": [[[1]], [[1]], [[1]], [[1]], [[1]]],
     "c2d_nopool": [[[1]], [[1]], [[1]], [[1]], [[1]]],
@@ -29,9 +29,10 @@ _TEMPORAL_KERNEL_BASIS = {     # video_model_builder.py:20-75
     "i3d_nopool": [[[5]], [[3]], [[3, 1]], [[3, 1]], [[1, 3]]],
     "slow": [[[1]], [[1]], [[1]], [[3]], [[3]]],
     "slowfast": [[[1], [5]], [[1], [3]], [[1], [3]], [[3], [3]], [[3], [3]]],
+    "fast": [[[5]], [[3]], [[3]], [[3]], [[3]]],      # the fork's single-pathway "fast" arch (video_model_builder.py:79-85)
 }
 _POOL1 = {"c2d": [[2, 1, 1]], "c2d_nopool": [[1, 1, 1]], "i3d": [[2, 1, 1]], "i3d_nopool": [[1, 1, 1]],
-          "slow": [[1, 1, 1]], "slowfast": [[1, 1, 1], [1, 1, 1]]}
+          "slow": [[1, 1, 1]], "slowfast": [[1, 1, 1], [1, 1, 1]], "fast": [[1, 1, 1]]}
 
 
 class _Holder(nn.Module):

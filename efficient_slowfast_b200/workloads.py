@@ -145,6 +145,17 @@ CASES = {
     "i3d_nln_r50": dict(        # "softmax" instantiation, (2,1,1) max-pool after res2
         model="ResNet", yaml="configs/Kinetics/I3D_NLN_8x8_R50.yaml", single=True,
         opts=["DATA.CROP_SIZE", 96], calib=(2, 8, 96), inputs=[("s96", 2, 8, 96)]),
+    # the fork's own product configs (configs/TIRED): grey-scale clips (one input channel), RESNET.DEPTH 18 with bottleneck
+    # blocks (2, 2, 2, 2), ALPHA 8 with 16 frames (slow pathway: 2 frames), spatial strides (1, 1, 2, 2) so that a 112^2
+    # crop reaches the 7 x 7 head pool of the default CROP_SIZE 224; s128 = its TEST_CROP_SIZE -> fully-convolutional head
+    "dual_r18_gray": dict(
+        model="SlowFastDualAttention", yaml="configs/TIRED/DUAL_TIRED_SLOWFAST_8x8_R18_HALF_112_GRAY.yaml", opts=[],
+        channels=1, calib=(2, 16, 112), inputs=[("s112", 2, 16, 112), ("s128", 1, 16, 128)]),
+    # MODEL.ARCH "fast" (video_model_builder.py:79-85, the fork's single-pathway arch with the fast pathway's temporal
+    # kernels), DEPTH 18, WIDTH_PER_GROUP 16, grey-scale
+    "fast_r18_gray": dict(
+        model="ResNet", yaml="configs/TIRED/TIRED_FAST_NLN_8x8_R50_112.yaml", single=True, opts=[],
+        channels=1, calib=(2, 16, 112), inputs=[("s112", 2, 16, 112)]),
     "dual_r50_stress": dict(
         model="SlowFastDualAttention", yaml="configs/Kinetics/SLOWFAST_DUAL_8x8_R50_stepwise_multigrid.yaml",
         stress=True, opts=[], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),
@@ -174,6 +185,27 @@ def case_cfg(name):
         cfg = esf.slowfast_4x16_r50_cfg()
         cfg.MULTIGRID.SHORT_CYCLE = True
         cfg.RESNET.NUM_GROUPS = 2
+    elif name == "dual_r18_gray":       # configs/TIRED/DUAL_TIRED_SLOWFAST_8x8_R18_HALF_112_GRAY.yaml, model keys
+        cfg = esf.slowfast_dual_8x8_r50_cfg()
+        cfg.DATA._merge(dict(NUM_FRAMES=16, SAMPLING_RATE=2, TRAIN_CROP_SIZE=112, TEST_CROP_SIZE=128, CROP_SIZE=224,
+                             INPUT_CHANNEL_NUM=[1, 1], MEAN=[0.45], STD=[0.225]))
+        cfg.SLOWFAST._merge(dict(ALPHA=8, BETA_INV=8, FUSION_CONV_CHANNEL_RATIO=2, FUSION_KERNEL_SZ=7))
+        cfg.RESNET._merge(dict(ZERO_INIT_FINAL_BN=True, WIDTH_PER_GROUP=64, NUM_GROUPS=1, DEPTH=18,
+                               TRANS_FUNC="bottleneck_transform", STRIDE_1X1=False,
+                               NUM_BLOCK_TEMP_KERNEL=[[2, 2]] * 4, SPATIAL_STRIDES=[[1, 1], [1, 1], [2, 2], [2, 2]],
+                               SPATIAL_DILATIONS=[[1, 1]] * 4))
+        cfg.NONLOCAL._merge(dict(LOCATION=[[[], []]] * 4, GROUP=[[1, 1]] * 4, INSTANTIATION="dot_product"))
+        cfg.MODEL._merge(dict(NUM_CLASSES=3, ARCH="slowfast", MODEL_NAME="SlowFastDualAttention", DROPOUT_RATE=0.5))
+        cfg.MULTIGRID.SHORT_CYCLE = False
+    elif name == "fast_r18_gray":       # configs/TIRED/TIRED_FAST_NLN_8x8_R50_112.yaml, model keys
+        cfg = esf.resnet_cfg("slow")
+        cfg.DATA._merge(dict(NUM_FRAMES=16, SAMPLING_RATE=2, TRAIN_CROP_SIZE=112, TEST_CROP_SIZE=128, CROP_SIZE=224,
+                             INPUT_CHANNEL_NUM=[1], MEAN=[0.45], STD=[0.225]))
+        cfg.RESNET._merge(dict(ZERO_INIT_FINAL_BN=True, WIDTH_PER_GROUP=16, NUM_GROUPS=1, DEPTH=18,
+                               TRANS_FUNC="bottleneck_transform", STRIDE_1X1=False, NUM_BLOCK_TEMP_KERNEL=[[2]] * 4,
+                               SPATIAL_STRIDES=[[1], [1], [2], [2]], SPATIAL_DILATIONS=[[1]] * 4))
+        cfg.NONLOCAL._merge(dict(LOCATION=[[[]]] * 4, GROUP=[[1]] * 4, INSTANTIATION="dot_product"))
+        cfg.MODEL._merge(dict(NUM_CLASSES=3, ARCH="fast", MODEL_NAME="ResNet", DROPOUT_RATE=0.5))
     elif name == "shufflenetv2_w05":
         cfg = esf.slowfast_shufflenetv2_cfg(0.5)
     elif name == "mobilenetv2_w1":
@@ -224,7 +256,8 @@ def case_inputs(name, tag):
         if t == tag:
             cfg = case_cfg(name)
             alpha = 0 if CASES[name].get("single") else cfg.SLOWFAST.ALPHA
-            return pack_pathway_output(seeded_clip(b, frames, crop, seed=1), alpha)
+            return pack_pathway_output(seeded_clip(b, frames, crop, seed=1, channels=CASES[name].get("channels", 3)),
+                                       alpha)
     raise KeyError(tag)
 
 

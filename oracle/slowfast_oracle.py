@@ -27,17 +27,18 @@ import torch.nn.functional as F
 BN_EPS = 1e-5  # every BatchNorm3d on the path is built with eps=1e-5 (resnet_helper.py:124, stem_helper.py:18)
 
 # custom_video_model_builder.py:151-168 / video_model_builder.py:16-90
-STAGE_DEPTH = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
+STAGE_DEPTH = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 18: (2, 2, 2, 2), 34: (3, 4, 6, 3)}   # video_model_builder.py:15-16
 TEMPORAL_KERNEL_BASIS = {
     "c2d": [[[1]], [[1]], [[1]], [[1]], [[1]]],
     "c2d_nopool": [[[1]], [[1]], [[1]], [[1]], [[1]]],
     "i3d": [[[5]], [[3]], [[3, 1]], [[3, 1]], [[1, 3]]],
     "i3d_nopool": [[[5]], [[3]], [[3, 1]], [[3, 1]], [[1, 3]]],
     "slow": [[[1]], [[1]], [[1]], [[3]], [[3]]],
+    "fast": [[[5]], [[3]], [[3]], [[3]], [[3]]],          # video_model_builder.py:79-85
     "slowfast": [[[1], [5]], [[1], [3]], [[1], [3]], [[3], [3]], [[3], [3]]],
 }
 POOL1 = {"c2d": [[2, 1, 1]], "c2d_nopool": [[1, 1, 1]], "i3d": [[2, 1, 1]], "i3d_nopool": [[1, 1, 1]],
-         "slow": [[1, 1, 1]], "slowfast": [[1, 1, 1], [1, 1, 1]]}
+         "slow": [[1, 1, 1]], "slowfast": [[1, 1, 1], [1, 1, 1]], "fast": [[1, 1, 1]]}
 
 
 # Where the restatement runs.  "cpu" always -- it is the oracle -- except in tests/experiments/eager_torch_gpu.py, which

@@ -74,7 +74,8 @@ def make_case(name):
     sd = recipe.seeded_state_dict(model.state_dict(), seed=0, stress=spec.get("stress", False))
     model.load_state_dict(sd, strict=True)
     cb, cf, cs = spec["calib"]
-    calibrate_bn(model, [recipe.seeded_clip(cb, cf, cs, seed=100 + i) for i in range(2)], alpha)
+    ch = spec.get("channels", 3)
+    calibrate_bn(model, [recipe.seeded_clip(cb, cf, cs, seed=100 + i, channels=ch) for i in range(2)], alpha)
     out = {}
     for k, v in model.state_dict().items():
         if k.endswith("running_mean") or k.endswith("running_var"):
@@ -88,7 +89,7 @@ def make_case(name):
                 lambda m, i, o, sname=sname: taps.__setitem__(sname, [t.detach().clone() for t in o])))
         fc = [m for m in model.head.modules() if isinstance(m, torch.nn.Linear)][-1]
         hooks.append(fc.register_forward_hook(lambda m, i, o: taps.__setitem__("logits", o.detach().clone())))
-        x = recipe.seeded_clip(b, frames, crop, seed=1)
+        x = recipe.seeded_clip(b, frames, crop, seed=1, channels=ch)
         with torch.no_grad():
             y = model([t.clone() for t in recipe.pack_pathway_output(x, alpha)])
         for h in hooks:

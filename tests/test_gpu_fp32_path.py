@@ -190,6 +190,9 @@ def test_attention_fp32(esf_lib, d, T, H, W, alpha):
     # softmax matters at that level -- 2e-4 is the bound written for the 224^2 clip
     ("dual_r50", "s64", 1e-4), ("dual_r50", "s224", 2e-4),
     ("i3d_r50", "s224", 1e-4),
+    # the fork's grey-scale R18 product configs (one input channel, ALPHA 8, strides (1,1,2,2); s128: fully-convolutional
+    # head is not part of this plan)
+    ("dual_r18_gray", "s112", 1e-4), ("fast_r18_gray", "s112", 1e-4),
     # Non-local blocks (softmax / dot_product instantiation): the 16-bit plan is held to 4e-2 / 2e-2 on these draws
     # (tests/test_gpu_model.py: the softmax blocks of this random draw amplify ANY perturbation ~50x more than the plain
     # I3D trunk) -- the same weights and clips in the FP32-accurate plan: measured 2.8e-4 / 1.8e-4, i.e. 70x / 14x

@@ -34,7 +34,8 @@ def _run(name, tag, precision="fp16"):
                                       ("i3d_r50", "s224"), ("slow_r50", "s64"),
                                       ("slow_nln_r50", "s64"), ("i3d_nln_r50", "s96"),
                                       ("slowfast_r50_fcn", "s96"), ("slowfast_r50_fcn", "s64"), ("slow_r50", "s96"),
-                                      ("slowfast_r50_g2", "s64")])
+                                      ("slowfast_r50_g2", "s64"), ("dual_r18_gray", "s112"), ("dual_r18_gray", "s128"),
+                                      ("fast_r18_gray", "s112")])
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 def test_model_matches_reference_golden(esf_lib, name, tag, precision):
     cfg, model, gold, y = _run(name, tag, precision)

@@ -17,7 +17,8 @@ from oracle import slowfast_oracle as O
                                       ("i3d_r50", "s224"), ("slow_r50", "s64"),
                                       ("slow_nln_r50", "s64"), ("i3d_nln_r50", "s96"),
                                       ("slowfast_r50_fcn", "s96"), ("slowfast_r50_fcn", "s64"), ("slow_r50", "s96"),
-                                      ("slowfast_r50_g2", "s64")])
+                                      ("slowfast_r50_g2", "s64"), ("dual_r18_gray", "s112"), ("dual_r18_gray", "s128"),
+                                      ("fast_r18_gray", "s112")])
 def test_oracle_matches_reference_golden(name, tag):
     cfg, model, gold = helpers.case_model_and_weights(name)
     xs = helpers.case_inputs(name, tag)

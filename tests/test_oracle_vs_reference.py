@@ -77,3 +77,50 @@ def test_caffe2_name_fixture_is_the_reference_mapping():
     want = json.load(open(os.path.join(helpers.GOLDEN_DIR, "caffe2_names.json")))
     for c2, key in want.items():
         assert convert(c2) == key
+
+
+def _config_signature(path):
+    import yaml
+    with open(path) as fh:
+        y = yaml.safe_load(fh)
+    m, r, d = y.get("MODEL", {}), y.get("RESNET", {}), y.get("DATA", {})
+    return (m.get("MODEL_NAME"), m.get("ARCH"), r.get("DEPTH"), r.get("WIDTH_PER_GROUP"), str(d.get("INPUT_CHANNEL_NUM")),
+            str(y.get("NONLOCAL", {}).get("LOCATION")), y.get("SLOWFAST", {}).get("WIDTH_MULTI"))
+
+
+def test_reference_yaml_configs_build_with_the_same_schema():
+    """Every classification YAML the reference itself can build (57 of its 72: detection configs are out of scope, 8
+    name unregistered models or fail its own asserts) must build here with the same state_dict keys and shapes and, for
+    the same seed, the same initial weights.  One YAML per distinct (model, arch, depth, width, input channels,
+    non-local layout) signature by default; ESF_FULL_CONFIG_SWEEP=1 runs all of them (6 min;
+    profiles/r2_reference_config_sweep.txt is that run)."""
+    import glob
+    import os
+
+    import efficient_slowfast_b200 as esf
+
+    root = os.path.join(ref_shim.REF_ROOT, "SlowFast")
+    seen, checked = set(), 0
+    for y in sorted(glob.glob(os.path.join(root, "configs", "**", "*.yaml"), recursive=True)):
+        sig = _config_signature(y)
+        if sig in seen and not os.environ.get("ESF_FULL_CONFIG_SWEEP"):
+            continue
+        seen.add(sig)
+        try:
+            cfg = ref_shim.get_cfg(os.path.relpath(y, root), [])
+            if cfg.DETECTION.ENABLE:
+                continue
+            torch.manual_seed(0)
+            ref = ref_shim.build_reference_model(cfg)
+        except Exception:
+            continue                     # the reference cannot build this YAML itself
+        ours_cfg = esf.get_cfg()
+        ours_cfg.merge_from_file(y)
+        ours_cfg.NUM_GPUS = 0
+        torch.manual_seed(0)
+        ours = esf.build_model(ours_cfg)
+        a, b = ref.state_dict(), ours.state_dict()
+        assert {k: tuple(v.shape) for k, v in a.items()} == {k: tuple(v.shape) for k, v in b.items()}, y
+        assert all(torch.equal(a[k], b[k]) for k in a), y
+        checked += 1
+    assert checked >= 12
