@@ -37,6 +37,7 @@ constexpr float kTcLog2e = 1.4426950408889634f;
 
 struct __align__(64) AttnTcParams {
   CUtensorMap q_map, k_map, v_map;
+  CUtensorMap vlo_map;  // split mode: V_lo^T (same shape as V^T)
   const float* x;  // [B][N][d]
   int B, N, T, H, W, d, alpha;
   float gamma;
@@ -56,6 +57,10 @@ struct __align__(64) AttnTcParams {
   int out_f32;  // the output view is FP32 (FP32-accurate path, esf_precise.cu); strides stay in elements
   int pdbl;     // v2 kernel: two P buffers per (query tile, half) -- TMEM has the columns when DVp <= 32 (d < 32)
   int qk_async; // v2 kernel: the Q.K^T issuer serves the two query tiles independently (no lock step)
+  // split mode (v1 kernel, FP32-accurate plan): P and V are FP16 PAIRS, O += P_hi V_hi + P_lo V_hi + P_hi V_lo.  P_lo
+  // lives 16 KB behind P_hi in shared memory, V_lo^T `v_half` bytes behind V^T inside a stage.
+  int split;
+  uint32_t v_half;
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -78,8 +83,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
   uint8_t* Qs = smem;                                   // 2 tiles x q_tile_bytes
   uint8_t* Ks = Qs + 2 * p.q_tile_bytes;                // stages x k_tile_bytes
   uint8_t* Vs = Ks + p.stages * p.k_tile_bytes;         // stages x v_tile_bytes
-  uint8_t* Ps = Vs + p.stages * p.v_tile_bytes;         // 2 x 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + 2 * 16384);
+  uint8_t* Ps = Vs + p.stages * p.v_tile_bytes;         // 2 x 16 KB (split mode: 2 x (16 KB P_hi + 16 KB P_lo))
+  const uint32_t p_q_bytes = p.split ? 32768u : 16384u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + 2 * p_q_bytes);
   uint64_t* q_full = bars;                   // 1
   uint64_t* kv_full = q_full + 1;            // stages
   uint64_t* kv_empty = kv_full + kTcMaxStages;
@@ -118,6 +124,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
     prefetch_tmap(&p.q_map);
     prefetch_tmap(&p.k_map);
     prefetch_tmap(&p.v_map);
+    if (p.split) prefetch_tmap(&p.vlo_map);
   }
   if (warp == 9) {
     tmem_alloc(tmem_slot, 512);
@@ -149,6 +156,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
           tma_load_3d(Ks + stage * p.k_tile_bytes + ch * chunk_bytes_k, &p.k_map, &kv_full[stage], ch * p.chunk_el,
                       j * kTcBN, b);
         tma_load_3d(Vs + stage * p.v_tile_bytes, &p.v_map, &kv_full[stage], j * kTcBN, 0, b);
+        if (p.split) tma_load_3d(Vs + stage * p.v_tile_bytes + p.v_half, &p.vlo_map, &kv_full[stage], j * kTcBN, 0, b);
       }
       __syncwarp();
       if (++stage == p.stages) {
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
     const uint32_t q_lo = kmajor_desc_lo(smem_u32(Qs) + q * p.q_tile_bytes);
     const uint32_t k_lo = kmajor_desc_lo(smem_u32(Ks));
     const uint32_t v_lo = kmajor_desc_lo(smem_u32(Vs));
-    const uint32_t p_lo = kmajor_desc_lo(smem_u32(Ps) + q * 16384);
+    const uint32_t p_lo = kmajor_desc_lo(smem_u32(Ps) + q * p_q_bytes);
     const uint32_t k_stage_step = p.k_tile_bytes >> 4, v_stage_step = p.v_tile_bytes >> 4;
     const uint32_t o_tmem = tmem_base + 4 * kTcBN + q * p.DVp;
     auto issue_s = [&](int c, int stage) {
@@ -213,6 +221,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
         umma_bf16_lohi(o_tmem, p_lo + 2, pv_hi, vl + 2, pv_hi, idesc_o, 1);
         umma_bf16_lohi(o_tmem, p_lo + 4, pv_hi, vl + 4, pv_hi, idesc_o, 1);
         umma_bf16_lohi(o_tmem, p_lo + 6, pv_hi, vl + 6, pv_hi, idesc_o, 1);
+        if (p.split) {
+          // the two correction products (2^-11 of the main one) go to an accumulator of their own, O2 = O + 2 DVp
+          // columns: added to O they would only triple the number of roundings of the big accumulator
+          const uint32_t pl2 = p_lo + (16384u >> 4), vl2 = vl + (p.v_half >> 4), o2 = o_tmem + 2 * p.DVp;
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) umma_bf16_lohi(o2, pl2 + k, pv_hi, vl + k, pv_hi, idesc_o, (j != 0) || (k != 0));  // P_lo V_hi
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) umma_bf16_lohi(o2, p_lo + k, pv_hi, vl2 + k, pv_hi, idesc_o, 1);                  // P_hi V_lo
+        }
         umma_commit(&p_free[q]);
         umma_commit(&kv_empty[pv_stage]);
         if (j == nt - 1) umma_commit(&o_full[q]);
@@ -229,7 +246,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
     const bool tail = (N % kTcBN) != 0;
     float m = -CUDART_INF_F;   // running row maximum (raised lazily), natural-log units
     float l = 0.f;             // running sum of p
-    uint8_t* prow = Ps + q * 16384;
+    uint8_t* prow = Ps + q * p_q_bytes;
     const uint32_t o_addr = lane_addr + 4 * kTcBN + q * p.DVp;
     constexpr float kTau = 5.545177f;  // 8 * ln 2: p = exp(s - m) never exceeds 256
     for (int j = 0; j < nt; ++j) {
@@ -272,13 +289,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
       if (j > 0 && __any_sync(0xffffffffu, raise)) {
         // rare: some row of this warp raised its maximum -> rescale this warp's 32 TMEM lanes of O
         tc_fence_after();
-        for (int c0 = 0; c0 < p.DVp; c0 += 16) {
-          float o[16];
-          tmem_ld16(o_addr + c0, o);
+        for (int part = 0; part < (p.split ? 2 : 1); ++part)
+          for (int c0 = 0; c0 < p.DVp; c0 += 16) {
+            float o[16];
+            tmem_ld16(o_addr + part * 2 * p.DVp + c0, o);
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) o[jj] *= f;
-          tmem_st16(o_addr + c0, o);
-        }
+            for (int jj = 0; jj < 16; ++jj) o[jj] *= f;
+            tmem_st16(o_addr + part * 2 * p.DVp + c0, o);
+          }
         tmem_wait_st();
       }
 #pragma unroll
@@ -289,6 +307,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
         o.z = pack16x2(v[8 * ck + 4], v[8 * ck + 5], p.f16);
         o.w = pack16x2(v[8 * ck + 6], v[8 * ck + 7], p.f16);
         *reinterpret_cast<uint4*>(prow + swz(r * 128 + ck * 16, 7)) = o;
+        if (p.split) {   // P_lo = fp16(p - P_hi): the pair carries p to 2^-22
+          const uint32_t hh[4] = {o.x, o.y, o.z, o.w};
+          uint32_t ll[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 h2 = unpack16x2(hh[e], p.f16);
+            ll[e] = pack16x2(v[8 * ck + 2 * e] - h2.x, v[8 * ck + 2 * e + 1] - h2.y, p.f16);
+          }
+          *reinterpret_cast<uint4*>(prow + 16384 + swz(r * 128 + ck * 16, 7)) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -309,6 +337,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
     for (int c0 = 0; c0 < p.DVp; c0 += 16) {
       float o[16];
       tmem_ld16(lane_addr + 4 * kTcBN + q * p.DVp + c0, o);
+      if (p.split) {
+        float o2[16];
+        tmem_ld16(lane_addr + 4 * kTcBN + 2 * p.DVp + q * p.DVp + c0, o2);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) o[jj] += o2[jj];
+      }
       if (!valid) continue;
 #pragma unroll
       for (int jj = 0; jj < 16; ++jj) {
@@ -1079,9 +1113,62 @@ extern "C" int esf_attn_tc_pack(const float* proj, int32_t B, int32_t N, int32_t
   return check_launch("attn_tc_pack_kernel");
 }
 
+static int attn_tc_create_impl(const void* packed, const void* v_lo, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d,
+                               float gamma, const float* bn_scale, const float* bn_shift, int32_t alpha,
+                               const esf_view* y_fast_slice, esf_op** out);
+
 extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d,
                                   float gamma, const float* bn_scale, const float* bn_shift, int32_t alpha,
                                   const esf_view* y_fast_slice, esf_op** out) {
+  return attn_tc_create_impl(packed, nullptr, B, T, H, W, d, gamma, bn_scale, bn_shift, alpha, y_fast_slice, out);
+}
+
+// ---- split mode (FP32-accurate plan): P and V as FP16 pairs ------------------------------------------------------------
+// V_lo^T has the layout of V^T inside `packed` ([B][DVp][Npad] FP16): v_lo = fp16(v - fp16(v)), zeros in the ones row.
+__global__ void __launch_bounds__(256) attn_tc_vlo_kernel(const float* __restrict__ proj, int N, int Npad, int d, int DVp,
+                                                          __half* __restrict__ vlo) {
+  const int b = blockIdx.y;
+  const long long total = (long long)DVp * Npad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i / Npad), n = (int)(i % Npad);
+    float lo = 0.f;
+    if (j < d && n < N) {
+      const float v = proj[((long long)b * N + n) * 4 * d + 3 * d + j];
+      lo = v - __half2float(__float2half_rn(v));
+    }
+    vlo[(long long)b * total + i] = __float2half_rn(lo);
+  }
+}
+
+extern "C" int64_t esf_attn_tc_vlo_bytes(int32_t B, int32_t N, int32_t d) {
+  TcGeom g;
+  if (B <= 0 || N <= 0 || !tc_geom(d, &g)) return set_error(ESF_ERR_ARG, "esf_attn_tc_vlo_bytes: bad argument");
+  return (int64_t)B * g.DVp * ((N + 7) & ~7) * 2;
+}
+
+extern "C" int esf_attn_tc_pack_vlo(const float* proj, int32_t B, int32_t N, int32_t d, void* v_lo, void* stream) {
+  ESF_CHECK_ARG(proj && v_lo && B > 0 && N > 0, "esf_attn_tc_pack_vlo: null/bad argument");
+  TcGeom g;
+  if (!tc_geom(d, &g)) return set_error(ESF_ERR_UNSUPPORTED, "esf_attn_tc_pack_vlo: unsupported head dim %d", d);
+  const int Npad = (N + 7) & ~7;
+  const long long total = (long long)g.DVp * Npad;
+  dim3 grid((unsigned)std::min<long long>((total + 255) / 256, 148 * 8), B);
+  attn_tc_vlo_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(proj, N, Npad, d, g.DVp, static_cast<__half*>(v_lo));
+  return check_launch("attn_tc_vlo_kernel");
+}
+
+extern "C" int esf_attn_tc_create_split(const void* packed, const void* v_lo, int32_t B, int32_t T, int32_t H, int32_t W,
+                                        int32_t d, float gamma, const float* bn_scale, const float* bn_shift,
+                                        int32_t alpha, const esf_view* y_fast_slice, esf_op** out) {
+  ESF_CHECK_ARG(v_lo != nullptr, "esf_attn_tc_create_split: v_lo is null");
+  ESF_CHECK_ARG(y_fast_slice && y_fast_slice->dtype == ESF_F32, "esf_attn_tc_create_split: the output view must be FP32");
+  ESF_CHECK_ARG(d <= 64, "esf_attn_tc_create_split: head dim %d > 64 has no hi/lo logit split (use esf_p32_attention)", d);
+  return attn_tc_create_impl(packed, v_lo, B, T, H, W, d, gamma, bn_scale, bn_shift, alpha, y_fast_slice, out);
+}
+
+static int attn_tc_create_impl(const void* packed, const void* v_lo, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d,
+                               float gamma, const float* bn_scale, const float* bn_shift, int32_t alpha,
+                               const esf_view* y_fast_slice, esf_op** out) {
   ESF_CHECK_ARG(packed && bn_scale && bn_shift && view_ok(y_fast_slice) && out, "esf_attn_tc_create: null/bad argument");
   // an FP32 output view selects the FP32-accurate path: the packed operands are then FP16 (esf_attn_tc_pack dtype F16)
   ESF_CHECK_ARG(is16(y_fast_slice->dtype) || y_fast_slice->dtype == ESF_F32,
@@ -1156,6 +1243,12 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
   p.k_tile_bytes = kTcBN * g.KQ * 2;
   p.v_tile_bytes = g.DVp * 128;
   op->v2 = g.v2;
+  if (v_lo) {   // split mode runs on the one-row-per-thread kernel (row sums in FP32 registers, P through shared memory)
+    p.split = 1;
+    p.v_half = p.v_tile_bytes;
+    p.v_tile_bytes *= 2;
+    op->v2 = 0;
+  }
   {
     // Measured (round 2, gpurun_out/r2_s4, profiles/r2_attention_experiments.md): a second P buffer (d < 32) and an
     // independent Q.K^T issue of the two query tiles are both correct (kernel tests) and change nothing: d = 8
@@ -1163,7 +1256,7 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
     // both).  The waits they remove (ncu: 4.7 % + 6 % of the softmax warps' samples) are not what bounds the loop.
     // Both stay OFF by default; ESF_ATTN_PDBL=1 / ESF_ATTN_QKASYNC=1 enable them for A/B runs.
     const char* e = getenv("ESF_ATTN_PDBL");
-    p.pdbl = (g.v2 && g.DVp <= 32 && e && atoi(e) == 1) ? 1 : 0;
+    p.pdbl = (op->v2 && g.DVp <= 32 && e && atoi(e) == 1) ? 1 : 0;
   }
   {
     const char* e = getenv("ESF_ATTN_QKASYNC");   // A/B knob: 1 = independent issue of the two query tiles
@@ -1175,7 +1268,7 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
     if (op->poly < 0 || op->poly > 4) op->poly = 0;
   }
   // v1 streams P through 2 x 16 KB of shared memory; v2 keeps P in TMEM and needs 2 KB for the split-K maxima
-  const int fixed = 1024 + 2 * (int)p.q_tile_bytes + 512 + (g.v2 ? 2048 : 2 * 16384);
+  const int fixed = 1024 + 2 * (int)p.q_tile_bytes + 512 + (op->v2 ? 2048 : 2 * (p.split ? 32768 : 16384));
   int stages = (kTcSmemLimit - fixed) / (int)(p.k_tile_bytes + p.v_tile_bytes);
   p.stages = std::max(2, std::min(stages, kTcMaxStages));
   op->smem_bytes = fixed + p.stages * (int)(p.k_tile_bytes + p.v_tile_bytes);
@@ -1189,6 +1282,10 @@ extern "C" int esf_attn_tc_create(const void* packed, int32_t B, int32_t T, int3
   if (rc == ESF_OK)
     rc = encode3(&p.v_map, p.f16, base + L.v_off, N, g.DVp, B, (uint64_t)L.Npad * 2, (uint64_t)g.DVp * L.Npad * 2, kTcBN, g.DVp,
                  CU_TENSOR_MAP_SWIZZLE_128B, "attention V^T");
+  if (rc == ESF_OK && v_lo)
+    rc = encode3(&p.vlo_map, p.f16, const_cast<void*>(v_lo), N, g.DVp, B, (uint64_t)L.Npad * 2, (uint64_t)g.DVp * L.Npad * 2,
+                 kTcBN, g.DVp, CU_TENSOR_MAP_SWIZZLE_128B, "attention V_lo^T");
+  if (rc == ESF_OK && !v_lo) p.vlo_map = p.v_map;   // fully initialised parameter block
   if (rc == ESF_OK) {
     static unsigned char attr_done[kMaxDevices] = {0};   // kernel attributes are per device
     unsigned char* slot = device_slot(attr_done);

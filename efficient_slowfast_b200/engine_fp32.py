@@ -189,12 +189,37 @@ class PrecisePlan(Plan):
         gamma = float(att.gamma.detach().float().item())
         yv = rt.view(y_slice.f32)
         self.keep.append(yv)
-        # FP32 flash attention on the CUDA cores: the tcgen05 kernel's FP16 P and V (2^-11 each) would be the whole
-        # error budget of this mode (measured: 3e-4 on the s1 fuse output, 5e-4 on the probabilities)
-        self._add(lambda s: rt.check(
-            L.esf_p32_attention(proj.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(), sh.data_ptr(), alpha,
-                                ctypes.byref(yv), s), "esf_p32_attention"), "p32_attention", "N=%d d=%d" % (N, d),
-            flops=4.0 * B * N * N * d, exps=float(B) * N * N, nbytes=self._nbytes(proj) + self._nbytes(y_slice.f32))
+        if d <= 64 and self.attn_impl == "tcgen05":
+            # tensor cores at FP32 accuracy: the logits are hi/lo split already; P and V become FP16 pairs too
+            # (esf_attn_tc_create_split: O += P_hi V_hi + P_lo V_hi + P_hi V_lo, row sums in FP32 registers)
+            nbytes = int(L.esf_attn_tc_pack_bytes(B, N, d))
+            nlo = int(L.esf_attn_tc_vlo_bytes(B, N, d))
+            if nbytes < 0 or nlo < 0:
+                rt.check(min(nbytes, nlo), "esf_attn_tc_pack_bytes")
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            vlo = torch.empty(nlo, dtype=torch.uint8, device=self.device)
+            self.keep += [packed, vlo]
+            h = ctypes.c_void_p()
+            rt.check(L.esf_attn_tc_create_split(packed.data_ptr(), vlo.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(),
+                                                sh.data_ptr(), alpha, ctypes.byref(yv), ctypes.byref(h)),
+                     "esf_attn_tc_create_split")
+            self.handles.append(h)
+
+            def pack(s):
+                rt.check(L.esf_attn_tc_pack(proj.data_ptr(), B, N, d, rt.F16, packed.data_ptr(), s), "esf_attn_tc_pack")
+                rt.check(L.esf_attn_tc_pack_vlo(proj.data_ptr(), B, N, d, vlo.data_ptr(), s), "esf_attn_tc_pack_vlo")
+
+            self._add(pack, "attn_pack", "N=%d d=%d split" % (N, d), nbytes=self._nbytes(proj) + nbytes + nlo, launches=2)
+            self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "attention",
+                      "N=%d d=%d split" % (N, d), flops=8.0 * B * N * N * d, exps=float(B) * N * N,
+                      nbytes=nbytes + nlo + self._nbytes(y_slice.f32))
+        else:
+            # d = 128 has no hi/lo logit split on the tensor cores (the split Q tile does not fit in shared memory):
+            # FP32 flash attention on the CUDA cores (N = 1 568 there)
+            self._add(lambda s: rt.check(
+                L.esf_p32_attention(proj.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(), sh.data_ptr(), alpha,
+                                    ctypes.byref(yv), s), "esf_p32_attention"), "p32_attention", "N=%d d=%d" % (N, d),
+                flops=4.0 * B * N * N * d, exps=float(B) * N * N, nbytes=self._nbytes(proj) + self._nbytes(y_slice.f32))
         self._post(y_slice.f32, y_slice, label="split")
 
     def head(self, xs, weight, bias, act):

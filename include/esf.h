@@ -266,6 +266,15 @@ int64_t esf_p32_eca_scratch_floats(int32_t B, int32_t C);
 int esf_p32_eca_fuse(const esf_view* x_fast, int32_t alpha, const float* eca_w, int32_t eca_k, const float* bn_scale,
                      const float* bn_shift, float* partial, const esf_view* y, void* stream);
 int esf_p32_head_pool(const esf_view* x, float* feat, int32_t feat_stride, int32_t feat_off, void* stream);
+/* The same attention on the tensor cores at FP32 accuracy for d <= 64 ("split mode" of the one-row-per-thread tcgen05
+ * kernel): logits are hi/lo split already; here P and V are FP16 PAIRS as well, O += P_hi V_hi + P_lo V_hi + P_hi V_lo,
+ * row sums in FP32 registers.  esf_attn_tc_pack (dtype F16) fills `packed`; esf_attn_tc_pack_vlo writes V_lo^T
+ * (esf_attn_tc_vlo_bytes bytes, the layout of V^T); esf_attn_tc_create_split plans the launch (FP32 output view). */
+int64_t esf_attn_tc_vlo_bytes(int32_t B, int32_t N, int32_t d);
+int esf_attn_tc_pack_vlo(const float* proj, int32_t B, int32_t N, int32_t d, void* v_lo, void* stream);
+int esf_attn_tc_create_split(const void* packed, const void* v_lo, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d,
+                             float gamma, const float* bn_scale, const float* bn_shift, int32_t alpha,
+                             const esf_view* y_fast_slice, esf_op** out);
 int esf_p32_attention(const float* proj, int32_t B, int32_t T, int32_t H, int32_t W, int32_t d, float gamma,
                       const float* bn_scale, const float* bn_shift, int32_t alpha, const esf_view* y, void* stream);
 

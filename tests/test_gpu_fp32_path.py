@@ -180,6 +180,46 @@ def test_attention_fp32(esf_lib, d, T, H, W, alpha):
     assert (ybuf[..., :8] == 7.0).all()
 
 
+@pytest.mark.parametrize("d,T,H,W,alpha,qk", [(8, 2, 9, 7, 4, 1.0), (8, 4, 28, 28, 4, 2.0), (32, 4, 12, 10, 4, 1.0),
+                                              (32, 8, 20, 20, 2, 2.0), (64, 2, 7, 7, 2, 1.0), (16, 3, 40, 33, 1, 1.0)])
+def test_attention_split_tensor_core(esf_lib, d, T, H, W, alpha, qk):
+    """esf_attn_tc_create_split (tcgen05, P and V as FP16 pairs) vs the FP64 evaluation of the same attention."""
+    import ctypes
+
+    g = torch.Generator().manual_seed(d + T + H)
+    B, N = 2, T * H * W
+    proj = torch.randn(B, N, 4 * d, generator=g)
+    proj[:, :, d:3 * d] *= qk * (6.0 / d) ** 0.5
+    scale, shift = torch.rand(d, generator=g) + 0.5, torch.randn(d, generator=g) * 0.2
+    gamma = 0.7
+    p = proj.double().reshape(B, N, 4, d)
+    att = torch.softmax(p[:, :, 1] @ p[:, :, 2].transpose(1, 2), dim=-1)
+    ref = ((gamma * (att @ p[:, :, 3]) + p[:, :, 0]) * scale.double() + shift.double()).relu()
+    ref = ref.reshape(B, T, H, W, d).repeat_interleave(alpha, dim=1)
+    L = esf_lib
+    ybuf = torch.full((B, T * alpha, H, W, d + 8), 7.0, dtype=torch.float32, device=DEV)
+    y = ybuf[..., 8:]
+    pj, sc, sh = proj.to(DEV), scale.to(DEV), shift.to(DEV)
+    packed = torch.empty(L.esf_attn_tc_pack_bytes(B, N, d), dtype=torch.uint8, device=DEV)
+    vlo = torch.empty(L.esf_attn_tc_vlo_bytes(B, N, d), dtype=torch.uint8, device=DEV)
+    yv = rt.view(y)
+    h = ctypes.c_void_p()
+    rt.check(L.esf_attn_tc_pack(pj.data_ptr(), B, N, d, rt.F16, packed.data_ptr(), None))
+    rt.check(L.esf_attn_tc_pack_vlo(pj.data_ptr(), B, N, d, vlo.data_ptr(), None))
+    rt.check(L.esf_attn_tc_create_split(packed.data_ptr(), vlo.data_ptr(), B, T, H, W, d, gamma, sc.data_ptr(),
+                                        sh.data_ptr(), alpha, ctypes.byref(yv), ctypes.byref(h)))
+    rt.check(L.esf_op_launch(h, None))
+    torch.cuda.synchronize()
+    L.esf_op_destroy(h)
+    err = ((y.double().cpu() - ref).abs().max() / ref.abs().max()).item()
+    print("split tcgen05 attention d=%d N=%d: rel err %.3e" % (d, N, err))
+    assert err <= 2e-5
+    assert (ybuf[..., :8] == 7.0).all()
+    hh = ctypes.c_void_p()
+    assert L.esf_attn_tc_create_split(packed.data_ptr(), vlo.data_ptr(), B, T, H, W, 128, gamma, sc.data_ptr(),
+                                      sh.data_ptr(), alpha, ctypes.byref(yv), ctypes.byref(hh)) < 0
+
+
 @pytest.mark.parametrize("name,tag,tol", [
     # s224: measured 1.4e-4 -- the reference's own FP32 result depends on the evaluation order at that level (two CPU
     # FP32 evaluations of this model differ by ~1e-4, tests/test_oracle_golden.py) and the tensor core's accumulator
