@@ -960,7 +960,9 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
                                      int32_t kT, int32_t kH, int32_t kW, int32_t sH, int32_t sW, int32_t pT, int32_t pH,
                                      int32_t pW, int32_t act, const esf_view* y, esf_op** out) {
   ESF_CHECK_ARG(xp && w_band && bias_tiled && view_ok(y) && out, "esf_stem_igemm_create: null/bad argument");
-  ESF_CHECK_ARG(is16(y->dtype), "esf_stem_igemm_create: output must be BF16 or F16");
+  // an FP32 output view: raw accumulators of one of the three split products of the FP32-accurate plan; the operands
+  // (packed rows, band weights) are then FP16
+  ESF_CHECK_ARG(is16(y->dtype) || y->dtype == ESF_F32, "esf_stem_igemm_create: output must be BF16, F16 or F32");
   int pt_expected = 0, lpad = 0, win = 0;
   int rc = esf_stem_geometry(W, Cin, kW, sW, pW, &pt_expected, &lpad, &win);
   if (rc != ESF_OK) return rc;
@@ -1013,11 +1015,12 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
   p.a_bytes = p.rows * 128, p.b_bytes = n_tile * 128, p.b_stride = (p.b_bytes + 1023) & ~1023u;
   if (p.halo_g) p.a_bytes = 8 * (p.bt + kT - 1) * 128;
   p.sbo = 1024, p.layout_type = 2;
-  p.bias = bias_tiled, p.act = act, p.has_res = 0, p.out_f32 = 0;
-  p.f16 = y->dtype == ESF_F16;
+  p.bias = bias_tiled, p.act = act, p.has_res = 0, p.out_f32 = y->dtype == ESF_F32;
+  p.f16 = y->dtype == ESF_F16 || y->dtype == ESF_F32;
   const CUtensorMapDataType dt16 = p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  p.slab_cols = std::min(n_tile, 64);
-  const int out_row_bytes = p.slab_cols * 2;
+  const int oes = p.out_f32 ? 4 : 2;
+  p.slab_cols = std::min(n_tile, 128 / oes);
+  const int out_row_bytes = p.slab_cols * oes;
   p.out_swz = out_row_bytes == 128 ? 7 : (out_row_bytes == 64 ? 3 : 1);
   p.res_bytes = 0;
   plan_smem(p, &op->smem_bytes);
@@ -1071,9 +1074,9 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
   }
   if (rc == ESF_OK)
     // dims (8*Cout, Wo/8, Ho, To, B): the column block is the W coordinate, so a tile wider than 8*Cout is clipped
-    rc = encode_act_map(&p.out_map, dt16, 2, y->ptr, (int64_t)kStemWB * Cout, Wo / kStemWB,
-                        Ho, To, B, (int64_t)kStemWB * Cout, y->sH, y->sT, y->sB, p.slab_cols, 1, p.bh, p.bt, p.bb,
-                        swizzle_for_row_bytes(out_row_bytes), "stem output");
+    rc = encode_act_map(&p.out_map, p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt16, oes, y->ptr,
+                        (int64_t)kStemWB * Cout, Wo / kStemWB, Ho, To, B, (int64_t)kStemWB * Cout, y->sH, y->sT, y->sB,
+                        p.slab_cols, 1, p.bh, p.bt, p.bb, swizzle_for_row_bytes(out_row_bytes), "stem output");
   if (rc == ESF_OK) {
     p.res_map = p.out_map;
     rc = finish_op(op);

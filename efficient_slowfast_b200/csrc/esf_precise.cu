@@ -55,7 +55,8 @@ static int p32_grid(long long total, int threads) {
 // ------------------------------------------------------------------------------------------- GEMM post-pass / split
 // v = act(acc * scale[c] + bias[c] + res);  y32 = v;  y3 planes = [hi(v) | lo(v) | hi(v)]
 struct PostParams {
-  V32 acc, res, y32, y3;   // y3: FP16 view of the hi plane's slice; the other planes follow at +plane, +2*plane elements
+  V32 acc, acc2, acc3;     // acc2 / acc3 (optional): further partial accumulators added BEFORE the scale (split stem)
+  V32 res, y32, y3;   // y3: FP16 view of the hi plane's slice; the other planes follow at +plane, +2*plane elements
   const float* scale;
   const float* bias;
   int act, plane;
@@ -84,6 +85,17 @@ __global__ void __launch_bounds__(256) p32_post_kernel(const PostParams p) {
       v[0] = a0.x, v[1] = a0.y, v[2] = a0.z, v[3] = a0.w, v[4] = a1.x, v[5] = a1.y, v[6] = a1.z, v[7] = a1.w;
     } else {
       v[0] = a[0];
+    }
+    for (int extra = 0; extra < 2; ++extra) {
+      const V32& e = extra ? p.acc3 : p.acc2;
+      if (!e.ptr) continue;
+      const float* a2 = reinterpret_cast<const float*>(e.ptr) + off32(e, b, t, h, w) + c0;
+      if constexpr (VEC == 8) {
+        const float4 r0 = *reinterpret_cast<const float4*>(a2), r1 = *reinterpret_cast<const float4*>(a2 + 4);
+        v[0] += r0.x, v[1] += r0.y, v[2] += r0.z, v[3] += r0.w, v[4] += r1.x, v[5] += r1.y, v[6] += r1.z, v[7] += r1.w;
+      } else {
+        v[0] += a2[0];
+      }
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -415,12 +427,40 @@ extern "C" int esf_p32_post(const esf_view* acc, const float* scale, const float
                 "esf_p32_post: y3 must be the FP16 hi-plane slice of a [hi|lo|hi] buffer (plane %d)", plane);
   PostParams p;
   p.acc = to_v32(acc);
+  p.acc2 = p.acc3 = null_v32();
   p.res = (res && res->ptr) ? to_v32(res) : null_v32();
   p.y32 = (y32 && y32->ptr) ? to_v32(y32) : null_v32();
   p.y3 = (y3 && y3->ptr) ? to_v32(y3) : null_v32();
   p.scale = scale, p.bias = bias, p.act = act, p.plane = plane, p.worder = weight_order != 0;
   const long long pos = (long long)acc->B * acc->T * acc->H * acc->W;
   const bool v8 = vec8_ok(acc, 4) && (!p.res.ptr || vec8_ok(res, 4)) && (!p.y32.ptr || vec8_ok(y32, 4)) &&
+                  (!p.y3.ptr || (vec8_ok(y3, 2) && plane % 8 == 0));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (v8) p32_post_kernel<8><<<p32_grid(pos * (acc->C / 8), 256), 256, 0, s>>>(p);
+  else p32_post_kernel<1><<<p32_grid(pos * acc->C, 256), 256, 0, s>>>(p);
+  return check_launch("p32_post_kernel");
+}
+
+// esf_p32_post with three partial accumulators: v = act((acc + acc2 + acc3) * scale + bias) -- the banded stem GEMM cannot
+// chain its three split products along K (5 x 7 x 3 taps exceed its tap table), so they are three launches
+extern "C" int esf_p32_post3(const esf_view* acc, const esf_view* acc2, const esf_view* acc3, const float* scale,
+                             const float* bias, int32_t act, const esf_view* y32, const esf_view* y3, int32_t plane,
+                             void* stream) {
+  ESF_CHECK_ARG(f32_view_ok(acc) && f32_view_ok(acc2) && f32_view_ok(acc3) && same_pos(acc, acc2) && same_pos(acc, acc3) &&
+                    acc2->C == acc->C && acc3->C == acc->C,
+                "esf_p32_post3: three FP32 accumulators of one shape expected");
+  ESF_CHECK_ARG(!y32 || !y32->ptr || (f32_view_ok(y32) && same_pos(y32, acc) && y32->C == acc->C), "esf_p32_post3: bad y32");
+  ESF_CHECK_ARG(!y3 || !y3->ptr || (view_ok(y3) && y3->dtype == ESF_F16 && same_pos(y3, acc) && y3->C == acc->C &&
+                                    plane >= acc->C && y3->sW >= 3LL * plane),
+                "esf_p32_post3: bad y3");
+  PostParams p;
+  p.acc = to_v32(acc), p.acc2 = to_v32(acc2), p.acc3 = to_v32(acc3);
+  p.res = null_v32();
+  p.y32 = (y32 && y32->ptr) ? to_v32(y32) : null_v32();
+  p.y3 = (y3 && y3->ptr) ? to_v32(y3) : null_v32();
+  p.scale = scale, p.bias = bias, p.act = act, p.plane = plane, p.worder = 0;
+  const long long pos = (long long)acc->B * acc->T * acc->H * acc->W;
+  const bool v8 = vec8_ok(acc, 4) && vec8_ok(acc2, 4) && vec8_ok(acc3, 4) && (!p.y32.ptr || vec8_ok(y32, 4)) &&
                   (!p.y3.ptr || (vec8_ok(y3, 2) && plane % 8 == 0));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (v8) p32_post_kernel<8><<<p32_grid(pos * (acc->C / 8), 256), 256, 0, s>>>(p);

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
 template <int CIN>   // channel count at compile time (0: run-time Cin_rt) -- the per-element division is the hot loop
 __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x, int B, int Cin_rt, int T, int H, int W,
                                                         int pitch, int lpad, int f16, __nv_bfloat16* __restrict__ xp,
-                                                        int Tsrc, const int32_t* __restrict__ t_index) {
+                                                        int Tsrc, const int32_t* __restrict__ t_index, int lo_part) {
   // block = 128 chunk lanes x 2 rows; one (b, t, h) row per threadIdx.y, decomposed once with 32-bit arithmetic
   const int Cin = CIN ? CIN : Cin_rt;
   const int chunks = pitch / 8;
@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict_
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         v[e] = (w >= 0 && w < W) ? __ldg(xrow + c * plane + w) : 0.f;
+        if (lo_part) v[e] -= h162f(f2h16(v[e], f16), f16);   // the low half of the (hi, lo) pair (FP32-accurate plan)
         if (++c == Cin) c = 0, ++w;
       }
       uint4 o;
@@ -2027,7 +2028,7 @@ extern "C" int esf_stem_conv(const float* x, int32_t B, int32_t Cin, int32_t T, 
 
 static int stem_pack_launch(const char* who, const float* x, int32_t B, int32_t Cin, int32_t Tsrc, int32_t H, int32_t W,
                             const int32_t* t_index, int32_t T, int32_t pitch, int32_t lpad, int32_t dtype, void* xp,
-                            void* stream) {
+                            void* stream, int lo_part = 0) {
   ESF_CHECK_ARG(is16(dtype), "%s: dtype must be BF16 or F16", who);
   ESF_CHECK_ARG(x && xp && B > 0 && Cin > 0 && T > 0 && Tsrc > 0 && H > 0 && W > 0, "%s: null/bad argument", who);
   ESF_CHECK_ARG(pitch % 8 == 0 && pitch >= lpad + W * Cin, "%s: bad pitch %d", who, pitch);
@@ -2035,16 +2036,21 @@ static int stem_pack_launch(const char* who, const float* x, int32_t B, int32_t 
   const unsigned grid = (unsigned)std::max(1LL, std::min((nrows + 1) / 2, 148LL * 64));
   if (Cin == 3)
     stem_pack_kernel<3><<<grid, dim3(128, 2), 0, static_cast<cudaStream_t>(stream)>>>(
-        x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp), Tsrc, t_index);
+        x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp), Tsrc, t_index, lo_part);
   else
     stem_pack_kernel<0><<<grid, dim3(128, 2), 0, static_cast<cudaStream_t>(stream)>>>(
-        x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp), Tsrc, t_index);
+        x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp), Tsrc, t_index, lo_part);
   return check_launch("stem_pack_kernel");
 }
 
 extern "C" int esf_stem_pack(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
                              int32_t lpad, int32_t dtype, void* xp, void* stream) {
   return stem_pack_launch("esf_stem_pack", x, B, Cin, T, H, W, nullptr, T, pitch, lpad, dtype, xp, stream);
+}
+
+extern "C" int esf_stem_pack_lo(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
+                                int32_t lpad, int32_t dtype, void* xp, void* stream) {
+  return stem_pack_launch("esf_stem_pack_lo", x, B, Cin, T, H, W, nullptr, T, pitch, lpad, dtype, xp, stream, 1);
 }
 
 extern "C" int esf_stem_pack_gather(const float* x, int32_t B, int32_t Cin, int32_t Tsrc, int32_t H, int32_t W,

@@ -134,9 +134,54 @@ class PrecisePlan(Plan):
         self._post(acc, y, self.tensor(inv_scale), self.tensor(bias), res, act)
 
     def stem(self, x_nc, y, w_folded, bias, stride, padding, act=rt.ACT_RELU):
-        """FP32 CUDA-core stem (esf_stem_conv with an FP32 destination) + split into planes."""
-        self.stem_conv(x_nc, y.f32, w_folded, bias, stride, padding, act)
-        self._post(y.f32, y, label="split")
+        """Stem conv + folded BN + ReLU at FP32 accuracy.  Banded tensor-core GEMM (Plan.stem) when the geometry
+        allows: the clip is packed twice (hi and lo halves), the band weight is split like any other weight, and the
+        three products hi.hi, lo.hi, hi.lo are three launches of the same GEMM with FP32 outputs (its tap table cannot
+        hold 3 x kT x kH taps), summed, un-scaled, biased and activated by esf_p32_post3.  Else the FP32 CUDA-core stem."""
+        from .engine import pack_stem_band
+        B, Cin, T, H, W = x_nc.shape
+        cout = w_folded.shape[0]
+        kt, kh, kw = w_folded.shape[2:]
+        geo = rt.stem_geometry(W, Cin, kw, stride[2], padding[2]) if stride[0] == 1 else None
+        if geo is None or not y.f32.is_contiguous():
+            self.stem_conv(x_nc, y.f32, w_folded, bias, stride, padding, act)
+            return self._post(y.f32, y, label="split")
+        pitch, lpad, _ = geo
+        L = rt.lib()
+        hi, lo, inv_scale = split_weight_rows(w_folded.to(torch.float64))
+        zero = torch.zeros(cout, dtype=torch.float64)
+        xps, accs = [], []
+        for part in range(2):
+            xp = torch.empty((B, T, H, pitch), dtype=torch.float16, device=self.device)
+            self.keep.append(xp)
+            fn = L.esf_stem_pack_lo if part else L.esf_stem_pack
+            self._add(lambda s, xp=xp, fn=fn: rt.check(fn(self._in_ptr(x_nc), B, Cin, T, H, W, pitch, lpad, rt.F16,
+                                                          xp.data_ptr(), s), "esf_stem_pack"),
+                      "stem_pack", "lo" if part else "hi", nbytes=self._nbytes(x_nc, xp), eager=True)
+            xps.append(xp)
+        m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
+        for name, xp, wpart in (("hi.hi", xps[0], hi), ("lo.hi", xps[1], hi), ("hi.lo", xps[0], lo)):
+            wb, bt = pack_stem_band(wpart, zero, stride[2], self.device, torch.float16)
+            acc = torch.empty(tuple(y.shape), dtype=torch.float32, device=self.device)
+            self.keep += [wb, bt, acc]
+            yv = rt.view(acc)
+            h = ctypes.c_void_p()
+            rt.check(L.esf_stem_igemm_create(xp.data_ptr(), B, Cin, T, H, W, pitch, wb.data_ptr(), bt.data_ptr(), cout,
+                                             kt, kh, kw, stride[1], stride[2], padding[0], padding[1], padding[2],
+                                             rt.ACT_NONE, ctypes.byref(yv), ctypes.byref(h)), "esf_stem_igemm_create")
+            self.handles.append(h)
+            self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "stem_igemm",
+                      "%dx%dx%d %d->%d banded %s" % (kt, kh, kw, Cin, cout, name),
+                      flops=2.0 * m * cout * Cin * kt * kh * kw, nbytes=self._nbytes(xp, acc) + wb.numel() * 2)
+            accs.append(acc)
+        sc, bs = self.tensor(inv_scale), self.tensor(bias)
+        avs = [rt.view(a) for a in accs]
+        y32, y3 = rt.view(y.f32), rt.view(y.hi)
+        self.keep += avs + [y32, y3]
+        self._add(lambda s: rt.check(L.esf_p32_post3(ctypes.byref(avs[0]), ctypes.byref(avs[1]), ctypes.byref(avs[2]),
+                                                     sc.data_ptr(), bs.data_ptr(), act, ctypes.byref(y32),
+                                                     ctypes.byref(y3), y.plane, s), "esf_p32_post3"),
+                  "p32_post", "stem sum", nbytes=accs[0].numel() * (12 + 4 + 6))
 
     def pool(self, x, y, kernel, stride, padding, is_avg=False, act=rt.ACT_NONE):
         assert act == rt.ACT_NONE

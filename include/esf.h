@@ -255,6 +255,13 @@ int esf_group_mean(const float* in, int32_t B, int32_t P, int32_t K, float* out,
  * esf_stem_conv accepts an FP32 output view (FP32 CUDA-core stem) and esf_attn_tc_create an FP32 output slice. */
 int esf_p32_post(const esf_view* acc, const float* scale, const float* bias, const esf_view* res, int32_t act,
                  const esf_view* y32, const esf_view* y3, int32_t plane, int32_t weight_order, void* stream);
+/* esf_p32_post3: v = act((acc + acc2 + acc3) * scale + bias) -> y32 / planes: the banded stem GEMM runs its three split
+ * products as three launches (esf_stem_igemm_create with an FP32 output view; esf_stem_pack_lo packs the low halves of
+ * the clip: xp_lo = fp16(x - fp16(x))). */
+int esf_p32_post3(const esf_view* acc, const esf_view* acc2, const esf_view* acc3, const float* scale, const float* bias,
+                  int32_t act, const esf_view* y32, const esf_view* y3, int32_t plane, void* stream);
+int esf_stem_pack_lo(const float* x, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch, int32_t lpad,
+                     int32_t dtype, void* xp, void* stream);
 /* Non-local block in this mode (nonlocal_helper.py:105-148): the clip's own phi / g rows are the "weights" of the two
  * products, so they are stored in weight order [hi | hi | lo] (esf_p32_post weight_order = 1); esf_p32_row_softmax
  * turns the FP32 affinity rows into the [hi | lo | hi] planes of softmax(scale * S) (mode 0) or scale * S (mode 1). */

@@ -115,6 +115,32 @@ def test_conv_fp32_path(esf_lib, case):
     assert ((val - y.f32.double()).abs() <= 2.0 ** -21 * y.f32.double().abs() + 1e-7).all()
 
 
+@pytest.mark.parametrize("cin,cout,kt,T,S", [(3, 64, 1, 2, 64), (3, 8, 5, 8, 64), (1, 8, 5, 4, 32), (3, 24, 3, 4, 48)])
+def test_stem_fp32_path(esf_lib, cin, cout, kt, T, S):
+    """Stem conv kt x 7 x 7 stride (1,2,2) + bias + ReLU in the FP32-accurate plan (three launches of the banded tensor
+    core GEMM on FP16 pairs, or the FP32 CUDA-core stem when the band does not fit) vs FP64 conv3d."""
+    g = torch.Generator().manual_seed(cin + cout + kt)
+    B = 2
+    plan = PrecisePlan(DEV)
+    x = (torch.randn(B, cin, T, S, S, generator=g) * 2).to(DEV)
+    plan.inputs = [x]
+    w = torch.randn(cout, cin, kt, 7, 7, generator=g).double() * (2.0 / (cout * kt * 49)) ** 0.5
+    w = w * torch.logspace(-1.5, 0.5, cout).double().view(-1, 1, 1, 1, 1)
+    b = torch.randn(cout, generator=g).double() * 0.1
+    y = plan.act(B, T, S // 2, S // 2, cout)
+    plan.stem(x, y, w, b, (1, 2, 2), (kt // 2, 3, 3), act=rt.ACT_RELU)
+    plan.launch_all()
+    torch.cuda.synchronize()
+    ref = F.conv3d(x.double().cpu(), w, b, stride=(1, 2, 2), padding=(kt // 2, 3, 3)).relu()
+    got = _ncdhw(y.f32).double().cpu()
+    err = ((got - ref).abs().max() / ref.abs().max()).item()
+    kinds = sorted({m["kind"] for m in plan.meta})
+    print("stem %dx7x7 %d->%d: rel err %.3e via %s" % (kt, cin, cout, err, kinds))
+    assert err <= 2e-6
+    val, _, _ = _planes_value(y)
+    assert ((val - y.f32.double()).abs() <= 2.0 ** -21 * y.f32.double().abs() + 1e-7).all()
+
+
 def test_pool_eca_head_fp32(esf_lib):
     g = torch.Generator().manual_seed(3)
     B, T, H, W, C, alpha = 2, 8, 9, 7, 32, 4

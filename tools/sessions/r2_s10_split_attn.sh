@@ -2,7 +2,7 @@
 # round 2: tensor-core attention of the FP32-accurate plan (P and V as FP16 pairs) -- kernel + model parity, throughput
 set -u
 cd "$(dirname "$0")/../.."
-O=gpurun_out/r2_s10
+O=gpurun_out/r2_s11
 mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1 || { tail -5 $O/build.log; exit 1; }
 timeout 900 python -m pytest tests/test_gpu_fp32_path.py -q -s -m gpu > $O/pytest_fp32.log 2>&1; echo "pytest fp32 rc $?"
