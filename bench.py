@@ -215,7 +215,7 @@ def fill_inputs(ins, alpha, rank, dev):
         ins[0].copy_(W.pack_pathway_output(ins[1], alpha)[0])
 
 
-def parity_check(model, ins, case, frames, crop, alpha):
+def parity_check(model, ins, case, frames, crop, alpha, tol=2e-2):
     """OUTSIDE the timed region: the golden clip of this shape (made by the reference, tests/golden) goes into the
     first and the last batch slots of the benched static input; both output rows must match the golden (<= 2e-2, the
     north star's 16-bit tolerance) and each other bit-exactly -- the benched batch size, plan and index paths are the
@@ -246,9 +246,9 @@ def parity_check(model, ins, case, frames, crop, alpha):
     err = max(W.rel_err(first, ref), W.rel_err(last, ref))
     same = bool(torch.equal(first, last))
     argmax_ok = bool(torch.equal(first.argmax(1), ref.argmax(1)) and torch.equal(last.argmax(1), ref.argmax(1)))
-    ok = err <= 2e-2 and same
+    ok = err <= tol and same
     return {"golden": "%s/%s" % (case, tag), "rows": [0, B - gb] if gb == 1 else [[0, gb - 1], [B - gb, B - 1]],
-            "batch": B, "rel_err": err, "tol": 2e-2, "first_equals_last_bitwise": same, "argmax_equal": argmax_ok,
+            "batch": B, "rel_err": err, "tol": tol, "first_equals_last_bitwise": same, "argmax_equal": argmax_ok,
             "ok": ok}
 
 
@@ -394,7 +394,9 @@ def run_gpu(args):
         torch.cuda.synchronize()
         print(json.dumps({"profile_mode": True, "launches_per_step": plan.launches_per_run}))
         return
-    parity = parity_check(model, ins, case_of(args), T, S, alpha) if rank == 0 else None
+    # north star: <= 2e-2 on the 16-bit path, <= 1e-4 on the FP32 path (2e-4 written for 224^2 clips)
+    parity = parity_check(model, ins, case_of(args), T, S, alpha,
+                          tol=2e-4 if args.precision == "fp32" else 2e-2) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     sampler = ClockSampler(h.local_rank)

@@ -146,6 +146,122 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict_
   }
 }
 
+// The same packing with the clip rows staged in shared memory: the kernel above issues eight scalar loads per 16-byte
+// store (ncu, round 2, profiles/r2_ncu_small_kernels.md: 28 sectors per load request instead of 4, 76 % of the issue
+// slots busy, 2.7 TB/s = 0.41 of the HBM peak).
+// Here a block of 256 threads owns kPackRows rows: phase 1 copies their Cin x W floats with coalesced 16-byte loads,
+// phase 2 builds the interleaved (w, c) 16-byte chunks out of shared memory.
+constexpr int kPackRows = 4;
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+// ncu of the first two versions of this kernel (profiles/r2_ncu_small_kernels.md): 76 % of the issue slots busy and
+// ~590 thread instructions per 16-byte chunk -- not the conversions but the INDEX ARITHMETIC: 64-bit row % H, row / H and
+// run-time i % n, i / n per element.  Here the (b, t, h) decomposition happens once per row in shared memory
+// (32-bit), loops run row-outer / lane-inner without divisions, the rows of the next group are in flight (cp.async)
+// while this group is packed, and Cin = 3 uses a static pattern: element 6 u of a row is channel 0 of pixel
+// 2 u - lpad / 3, so a thread turns two whole pixels into three packed words written to a staging row (stride 3 words:
+// conflict-free) that leaves with coalesced 16-byte stores.
+template <int CIN>
+__global__ void __launch_bounds__(256) stem_pack_smem_kernel(const float* __restrict__ x, int B, int Cin_rt, int T, int H,
+                                                             int W, int pitch, int lpad, int f16,
+                                                             __nv_bfloat16* __restrict__ xp, int Tsrc,
+                                                             const int32_t* __restrict__ t_index, int lo_part) {
+  extern __shared__ __align__(16) float tile_all[];   // 2 x [kPackRows][Cin][W] FP32, then [kPackRows][pitch] 16-bit
+  __shared__ long long src_off[2][kPackRows];          // element offset of channel 0 of every row of a group
+  const int Cin = CIN ? CIN : Cin_rt;
+  const int chunks = pitch / 8;
+  const int w4 = W / 4;
+  const int tile_floats = kPackRows * Cin * W;
+  const int nrows = B * T * H;                          // < 2^31 (checked on the host)
+  const long long plane = (long long)Tsrc * H * W;
+  const int stride = gridDim.x * kPackRows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto issue = [&](int buf, int row0) {
+    const int nr = min(kPackRows, nrows - row0);
+    if (threadIdx.x < nr) {
+      const int row = row0 + threadIdx.x;
+      const int h = row % H, bt = row / H, t = bt % T, b = bt / T;
+      const int ts = t_index ? __ldg(t_index + t) : t;
+      src_off[buf][threadIdx.x] = (long long)b * Cin * plane + ((long long)ts * H + h) * W;
+    }
+    __syncthreads();
+    float* tile = tile_all + buf * tile_floats;
+    for (int rc = warp; rc < nr * Cin; rc += 8) {        // one (row, channel) line per warp, 16 bytes per lane
+      const int r = CIN ? rc / CIN : rc / Cin, c = rc - r * Cin;
+      const float* src = x + src_off[buf][r] + c * plane;
+      float* dst = tile + rc * W;
+      for (int q = lane; q < w4; q += 32) cp_async16(dst + q * 4, src + q * 4);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  int row0 = blockIdx.x * kPackRows;
+  if (row0 < nrows) issue(0, row0);
+  for (; row0 < nrows; row0 += stride, buf ^= 1) {
+    const int nr = min(kPackRows, nrows - row0);
+    const float* tile = tile_all + buf * tile_floats;
+    if (row0 + stride < nrows) {
+      issue(buf ^ 1, row0 + stride);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (CIN == 3 && lpad % 3 == 0) {
+      uint32_t* outw = reinterpret_cast<uint32_t*>(tile_all + 2 * tile_floats);   // [kPackRows][pitch / 2] words
+      const int words = pitch / 2, U = (words + 2) / 3;
+      const int w_first = -(lpad / 3);
+      for (int r = 0; r < nr; ++r) {
+        const float* trow = tile + r * 3 * W;
+        uint32_t* orow = outw + r * words;
+        for (int u = threadIdx.x; u < U; u += 256) {
+          const int wa = 2 * u + w_first, wb = wa + 1;
+          const bool ia = wa >= 0 && wa < W, ib = wb >= 0 && wb < W;
+          float a0 = ia ? trow[wa] : 0.f, a1 = ia ? trow[W + wa] : 0.f, a2 = ia ? trow[2 * W + wa] : 0.f;
+          float b0 = ib ? trow[wb] : 0.f, b1 = ib ? trow[W + wb] : 0.f, b2 = ib ? trow[2 * W + wb] : 0.f;
+          if (lo_part) {
+            a0 -= h162f(f2h16(a0, f16), f16), a1 -= h162f(f2h16(a1, f16), f16), a2 -= h162f(f2h16(a2, f16), f16);
+            b0 -= h162f(f2h16(b0, f16), f16), b1 -= h162f(f2h16(b1, f16), f16), b2 -= h162f(f2h16(b2, f16), f16);
+          }
+          orow[3 * u] = pack16x2(a0, a1, f16);
+          if (3 * u + 1 < words) orow[3 * u + 1] = pack16x2(a2, b0, f16);
+          if (3 * u + 2 < words) orow[3 * u + 2] = pack16x2(b1, b2, f16);
+        }
+      }
+      __syncthreads();
+      for (int r = 0; r < nr; ++r) {
+        const uint4* srow = reinterpret_cast<const uint4*>(outw + r * words);
+        uint4* drow = reinterpret_cast<uint4*>(xp + (long long)(row0 + r) * pitch);
+        for (int ck = threadIdx.x; ck < chunks; ck += 256) drow[ck] = srow[ck];
+      }
+    } else {
+      for (int r = 0; r < nr; ++r) {
+        const float* trow = tile + r * Cin * W;
+        for (int ck = threadIdx.x; ck < chunks; ck += 256) {
+          float v[8];
+          const int j0 = ck * 8 - lpad;
+          int w = j0 >= 0 ? j0 / Cin : -1 - ((-1 - j0) / Cin);   // floor division
+          int c = j0 - w * Cin;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            v[e] = (w >= 0 && w < W) ? trow[c * W + w] : 0.f;
+            if (lo_part) v[e] -= h162f(f2h16(v[e], f16), f16);
+            if (++c == Cin) c = 0, ++w;
+          }
+          uint4 o;
+          o.x = pack16x2(v[0], v[1], f16);
+          o.y = pack16x2(v[2], v[3], f16);
+          o.z = pack16x2(v[4], v[5], f16);
+          o.w = pack16x2(v[6], v[7], f16);
+          *reinterpret_cast<uint4*>(xp + (long long)(row0 + r) * pitch + ck * 8) = o;
+        }
+      }
+    }
+    // the barrier at the top of the next iteration (inside issue) orders this group's reads before the refill
+  }
+}
+
 // ------------------------------------------------------------------------------------------- uint8 frames
 // The decoder's frames arrive as uint8 (B, Tsrc, H, W, C) -- already channels-last.  The reference normalises them on
 // the host (tensor_normalize: x/255 - mean, /std, datasets/utils.py:298-315), permutes to C,T,H,W and gathers the slow
@@ -1334,6 +1450,52 @@ struct PoolParams {
 // ran at 0.64 / 0.38 / 0.20 ms against 0.03 / 0.04 / 0.02 ms of HBM time.
 // I: index type -- unsigned 32-bit whenever the element count allows (64-bit divisions cost ~5x more instructions).
 // RAGGED = false (C % 8 == 0): every group is full, the tail logic compiles away.
+// elementwise maximum of two packed 16-bit pairs (FP16 or BF16 bit patterns)
+__device__ __forceinline__ uint32_t hmax2_bits(uint32_t a, uint32_t b, int f16) {
+  if (f16) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+// Max-pool of full 16-byte channel groups, one block per OUTPUT ROW (b, to, ho): the row is decomposed once per block,
+// the threads walk (wo, channel group) without divisions (cv_shift: C / 8 is a power of two), and the maximum stays in
+// the 16-bit format (packed HMNMX2, exact).  The general kernel below spends ~300 instructions per 16-byte output on
+// seven 32-bit divisions and nine 64-bit address computations (ncu, round 2: 64 - 74 % of the issue slots at half the HBM
+// peak); this is the path of the two R50 stem pools.
+__global__ void __launch_bounds__(256) pool3d_rows_kernel(const PoolParams p, int cv_shift) {
+  const int row = blockIdx.x;
+  const int ho = row % p.y.H, bt = row / p.y.H, to = bt % p.y.T, b = bt / p.y.T;
+  const int f16 = p.x.f16;
+  const int cv = 1 << cv_shift, items = p.y.W << cv_shift;
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + (long long)b * p.x.sB;
+  __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + voff(p.y, b, to, ho, 0);
+  const uint32_t ninf = f16 ? 0xFC00FC00u : 0xFF80FF80u;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int cg = i & (cv - 1), wo = i >> cv_shift;
+    uint4 m = make_uint4(ninf, ninf, ninf, ninf);
+    for (int kt = 0; kt < p.kT; ++kt) {
+      const int ti = to * p.sT + kt - p.pT;
+      if (ti < 0 || ti >= p.x.T) continue;
+      for (int kh = 0; kh < p.kH; ++kh) {
+        const int hi = ho * p.sH + kh - p.pH;
+        if (hi < 0 || hi >= p.x.H) continue;
+        const __nv_bfloat16* xr = xb + ti * p.x.sT + hi * p.x.sH + cg * 8;
+        for (int kw = 0; kw < p.kW; ++kw) {
+          const int wi = wo * p.sW + kw - p.pW;
+          if (wi < 0 || wi >= p.x.W) continue;
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + wi * p.x.sW));
+          m.x = hmax2_bits(m.x, u.x, f16), m.y = hmax2_bits(m.y, u.y, f16);
+          m.z = hmax2_bits(m.z, u.z, f16), m.w = hmax2_bits(m.w, u.w, f16);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(yrow + wo * p.y.sW + cg * 8) = m;
+  }
+}
+
 template <int XV, int YV, typename I, bool RAGGED>
 __global__ void __launch_bounds__(256) pool3d_kernel(const PoolParams p) {
   const int C = p.y.C, cv = (C + 7) / 8;
@@ -1350,6 +1512,31 @@ __global__ void __launch_bounds__(256) pool3d_kernel(const PoolParams p) {
     const int to = pos % p.y.T;
     const int b = pos / p.y.T;
     const int nv = RAGGED ? min(8, C - c) : 8;   // channels of this group
+    if (XV == 8 && YV == 8 && !RAGGED && !p.is_avg && p.act == 0) {
+      // max-pool of full 16-byte groups without leaving the 16-bit format: the maximum of FP16 / BF16 numbers is exact in
+      // that format, so four packed HMNMX2 per tap replace eight conversions and eight FP32 maxima (ncu, round 2: the
+      // kernel was issue-bound, 64 - 74 % of the issue slots at 0.46 - 0.52 of the HBM peak)
+      uint4 m = f16 ? make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u)
+                    : make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);   // -inf pairs
+      for (int kt = 0; kt < p.kT; ++kt) {
+        const int ti = to * p.sT + kt - p.pT;
+        if (ti < 0 || ti >= p.x.T) continue;
+        for (int kh = 0; kh < p.kH; ++kh) {
+          const int hi = ho * p.sH + kh - p.pH;
+          if (hi < 0 || hi >= p.x.H) continue;
+          for (int kw = 0; kw < p.kW; ++kw) {
+            const int wi = wo * p.sW + kw - p.pW;
+            if (wi < 0 || wi >= p.x.W) continue;
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) +
+                                                                 voff(p.x, b, ti, hi, wi) + c));
+            m.x = hmax2_bits(m.x, u.x, f16), m.y = hmax2_bits(m.y, u.y, f16);
+            m.z = hmax2_bits(m.z, u.z, f16), m.w = hmax2_bits(m.w, u.w, f16);
+          }
+        }
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + voff(p.y, b, to, ho, wo) + c) = m;
+      continue;
+    }
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = p.is_avg ? 0.f : -CUDART_INF_F;
@@ -1683,11 +1870,14 @@ __global__ void __launch_bounds__(256) global_mean_finish_kernel(const float* __
 
 // ------------------------------------------------------------------------------------------- head
 // 16-byte variant of head_pool_kernel: block = (clip, up to 256 channels), thread = 8 channels x a strided set of positions
-__global__ void __launch_bounds__(256) head_pool_vec_kernel(const View x, float* feat, int feat_stride, int feat_off) {
+// gpb: channel groups per block (a power of two <= 32) -- few-channel tensors get narrow blocks so that the grid fills
+// the GPU (the fast pathway's 256 channels ran as 64 blocks: 12 % occupancy, 0.65 TB/s, 80 us)
+__global__ void __launch_bounds__(256) head_pool_vec_kernel(const View x, float* feat, int feat_stride, int feat_off,
+                                                            int gpb) {
   __shared__ float red[256][9];
   const int b = blockIdx.y;
   const int cgs_total = x.C >> 3;
-  const int cgs = min(cgs_total - blockIdx.x * 32, 32);   // channel groups of this block (power of two by construction)
+  const int cgs = min(cgs_total - blockIdx.x * gpb, gpb);   // channel groups of this block (power of two by construction)
   const int cg = threadIdx.x % cgs, l = threadIdx.x / cgs, lanes = 256 / cgs;
   const int npos = x.T * x.H * x.W;
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1698,7 +1888,7 @@ __global__ void __launch_bounds__(256) head_pool_vec_kernel(const View x, float*
     const int t = r / x.H;
     float v[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x.ptr) + voff(x, b, t, h, w) +
-                                                 (blockIdx.x * 32 + cg) * 8)),
+                                                 (blockIdx.x * gpb + cg) * 8)),
             x.f16, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] += v[j];
@@ -1710,7 +1900,7 @@ __global__ void __launch_bounds__(256) head_pool_vec_kernel(const View x, float*
     const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
     float t = 0.f;
     for (int i = 0; i < lanes; ++i) t += red[i * cgs + g][j];
-    feat[(long long)b * feat_stride + feat_off + blockIdx.x * 256 + threadIdx.x] = t / (float)npos;
+    feat[(long long)b * feat_stride + feat_off + blockIdx.x * gpb * 8 + threadIdx.x] = t / (float)npos;
   }
 }
 
@@ -2033,6 +2223,20 @@ static int stem_pack_launch(const char* who, const float* x, int32_t B, int32_t 
   ESF_CHECK_ARG(x && xp && B > 0 && Cin > 0 && T > 0 && Tsrc > 0 && H > 0 && W > 0, "%s: null/bad argument", who);
   ESF_CHECK_ARG(pitch % 8 == 0 && pitch >= lpad + W * Cin, "%s: bad pitch %d", who, pitch);
   const long long nrows = (long long)B * T * H;
+  // two buffers of clip rows [kPackRows][Cin][W] FP32 + (Cin = 3 static path) packed output rows [kPackRows][pitch] 16-bit
+  const size_t tile_bytes = 2 * (size_t)kPackRows * Cin * W * sizeof(float) + (size_t)kPackRows * pitch * 2;
+  static const bool use_smem = []() { const char* e = getenv("ESF_STEM_PACK_SMEM"); return !(e && atoi(e) == 0); }();
+  if (use_smem && W % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && tile_bytes <= 48 * 1024 &&
+      nrows < (1LL << 31) - 148LL * 16 * kPackRows) {
+    const unsigned g2 = (unsigned)std::max(1LL, std::min((nrows + kPackRows - 1) / kPackRows, 148LL * 16));
+    if (Cin == 3)
+      stem_pack_smem_kernel<3><<<g2, 256, tile_bytes, static_cast<cudaStream_t>(stream)>>>(
+          x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp), Tsrc, t_index, lo_part);
+    else
+      stem_pack_smem_kernel<0><<<g2, 256, tile_bytes, static_cast<cudaStream_t>(stream)>>>(
+          x, B, Cin, T, H, W, pitch, lpad, dtype == ESF_F16, static_cast<__nv_bfloat16*>(xp), Tsrc, t_index, lo_part);
+    return check_launch("stem_pack_smem_kernel");
+  }
   const unsigned grid = (unsigned)std::max(1LL, std::min((nrows + 1) / 2, 148LL * 64));
   if (Cin == 3)
     stem_pack_kernel<3><<<grid, dim3(128, 2), 0, static_cast<cudaStream_t>(stream)>>>(
@@ -2274,6 +2478,20 @@ extern "C" int esf_pool3d(const esf_view* x, const esf_view* y, int32_t kT, int3
   const bool small = pos * x->C < (1LL << 31) - (148LL * 32 * 256);   // idx + grid stride stays inside 32 bits
   const unsigned grid = grid_for(items, 256);
   const int xv = width(x), yv = width(y);
+  {
+    const int cv = x->C / 8;
+    const long long rows = (long long)y->B * To * Ho;
+    static const bool use_rows = []() { const char* e = getenv("ESF_POOL_ROWS"); return !(e && atoi(e) == 0); }();
+    if (use_rows && xv == 8 && yv == 8 && x->C % 8 == 0 && (cv & (cv - 1)) == 0 && !is_avg && act == 0 &&
+        rows < (1LL << 31) && x->sT < (1LL << 31) / std::max(1, x->T) && x->sB < (1LL << 40)) {
+      int sh = 0;
+      while ((1 << sh) < cv) ++sh;
+      const int items = Wo * cv;
+      const int threads = std::min(256, (items + 31) / 32 * 32);
+      pool3d_rows_kernel<<<(unsigned)rows, threads, 0, s>>>(p, sh);
+      return check_launch("pool3d_rows_kernel");
+    }
+  }
 #define ESF_POOL(XV, YV)                                                          \
   do {                                                                            \
     if (x->C % 8 == 0) {                                                          \
@@ -2339,9 +2557,12 @@ extern "C" int esf_head_pool(const esf_view* x0, const esf_view* x1, float* feat
   const int stride = x0->C + c1;
   auto pool_one = [&](const esf_view* x, int off) {
     const View v = to_view(x);
-    const int cgs = x->C / 8, last = cgs % 32;   // channel groups in the last block must divide 256 threads evenly
+    const int cgs = x->C / 8;
+    int gpb = 32;                                 // narrower blocks until the grid has ~4 blocks per SM
+    while (gpb > 4 && (long long)cdiv(cgs, gpb) * x->B < 148 * 4) gpb >>= 1;
+    const int last = cgs % gpb;                   // channel groups in the last block must divide 256 threads evenly
     if (x->C % 8 == 0 && (last & (last - 1)) == 0 && vec8_ok(v) && (long long)x->T * x->H * x->W < (1LL << 31))
-      head_pool_vec_kernel<<<dim3(cdiv(cgs, 32), x->B), 256, 0, s>>>(v, feat, stride, off);
+      head_pool_vec_kernel<<<dim3(cdiv(cgs, gpb), x->B), 256, 0, s>>>(v, feat, stride, off, gpb);
     else
       head_pool_kernel<<<dim3(cdiv(x->C, 64), x->B), 256, 0, s>>>(v, feat, stride, off);
     return check_launch("head_pool_kernel");

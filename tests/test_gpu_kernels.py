@@ -780,3 +780,56 @@ def test_global_mean(esf_lib, C, shape, dt):
     rt.check(esf_lib.esf_global_mean(ctypes.byref(xv), scratch.data_ptr(), feat.data_ptr(), C + 5, 3, rt.current_stream_ptr()))
     torch.cuda.synchronize()
     assert torch.equal(first, feat)            # deterministic
+
+
+@pytest.mark.parametrize("cin,W,kw,pw", [(3, 224, 7, 3), (3, 64, 7, 3), (1, 112, 7, 3), (3, 48, 3, 1), (2, 40, 5, 2),
+                                         (3, 50, 7, 3)])
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_stem_pack_variants(esf_lib, cin, W, kw, pw, precision, monkeypatch):
+    """esf_stem_pack / _lo / _gather against a torch restatement of the packed row layout, for the shared-memory staged
+    kernel (W % 4 == 0; the static 24-element path when Cin = 3) and the scalar-load kernel (W = 50, or forced)."""
+    adt = rt.TORCH_DTYPE[precision]
+    geo = rt.stem_geometry(W, cin, kw, 2, pw)
+    if geo is None:
+        pytest.skip("no banded geometry")
+    pitch, lpad, _ = geo
+    g = torch.Generator().manual_seed(cin * W)
+    B, T, H = 2, 6, 5
+    x = (torch.randn(B, cin, T, H, W, generator=g) * 3).to(DEV)
+    idx = torch.tensor([0, 2, 5], dtype=torch.int32, device=DEV)
+
+    def expect(src, lo):
+        rows = src.permute(0, 2, 3, 4, 1).reshape(B, src.shape[2], H, W * cin)        # (w, c) interleaved
+        v = rows - rows.to(adt).float() if lo else rows
+        out = torch.zeros(B, src.shape[2], H, pitch, device=DEV)
+        out[..., lpad:lpad + W * cin] = v
+        return out.to(adt)
+
+    for smem in ("1", "0"):
+        monkeypatch.setenv("ESF_STEM_PACK_SMEM", smem)   # read once per process: the second value only documents intent
+        a = torch.full((B, T, H, pitch), 7.0, dtype=adt, device=DEV)
+        rt.check(esf_lib.esf_stem_pack(x.data_ptr(), B, cin, T, H, W, pitch, lpad, rt.dtype_code(adt), a.data_ptr(), None))
+        lo = torch.full((B, T, H, pitch), 7.0, dtype=adt, device=DEV)
+        rt.check(esf_lib.esf_stem_pack_lo(x.data_ptr(), B, cin, T, H, W, pitch, lpad, rt.dtype_code(adt), lo.data_ptr(), None))
+        ga = torch.full((B, 3, H, pitch), 7.0, dtype=adt, device=DEV)
+        rt.check(esf_lib.esf_stem_pack_gather(x.data_ptr(), B, cin, T, H, W, idx.data_ptr(), 3, pitch, lpad,
+                                              rt.dtype_code(adt), ga.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert torch.equal(a, expect(x, False))
+        assert torch.equal(lo, expect(x, True))
+        assert torch.equal(ga, expect(x.index_select(2, idx.long()), False))
+
+
+def test_pool3d_fp16_packed_max(esf_lib):
+    """The packed 16-bit max path (full 16-byte groups, max-pool, no activation) in FP16 with -inf padding semantics."""
+    g = torch.Generator().manual_seed(5)
+    x = _rand_act(g, 2, 3, 15, 14, 24, dtype=torch.float16).to(DEV)
+    x[0, 0, 0, 0, :] = -60000.0          # a window whose only valid taps are very negative must not see the padding
+    for kernel, stride, pad in [((1, 3, 3), (1, 2, 2), (0, 1, 1)), ((3, 3, 3), (1, 2, 2), (1, 1, 1)), ((2, 1, 1), (2, 1, 1), (0, 0, 0))]:
+        ref = F.max_pool3d(_to_ncdhw(x.cpu()), kernel, stride, pad)
+        y = torch.empty(_to_ndhwc(ref).shape, dtype=torch.float16, device=DEV)
+        plan = Plan(DEV, "fp16")
+        plan.pool(x, y, kernel, stride, pad)
+        plan.launch_all()
+        torch.cuda.synchronize()
+        assert torch.equal(_to_ncdhw(y.cpu()), ref)
