@@ -1616,6 +1616,7 @@ struct EcaParams {
   const float* bn_scale;
   const float* bn_shift;
   float* partial;  // [B][kEcaBlocksPerClip][C]
+  int dense;       // x and y are dense over their positions (sH = W sW, sT = H sH): division-free position walk
 };
 
 __device__ __forceinline__ float eca_tmax(const EcaParams& p, int b, long long pos, int c) {
@@ -1722,6 +1723,20 @@ __device__ __forceinline__ void eca_tmax8(const EcaParams& p, int b, int pos, in
   }
 }
 
+// eca_tmax8 for views that are dense over their positions (offset = b sB + t sT + hw sW): (tp, hw) are carried
+// incrementally by the caller, no divisions in the position loop
+__device__ __forceinline__ void eca_tmax8_dense(const EcaParams& p, const __nv_bfloat16* xb, int tp, int hw, int cg, float* m) {
+  const __nv_bfloat16* base = xb + (long long)tp * p.alpha * p.x.sT + (long long)hw * p.x.sW + cg * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -CUDART_INF_F;
+  for (int a = 0; a < p.alpha; ++a) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + a * p.x.sT)), p.x.f16, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+  }
+}
+
 __global__ void __launch_bounds__(kEcaThreads) eca_partial_vec_kernel(const EcaParams p) {
   __shared__ float red[kEcaThreads][9];
   const int C = p.x.C, cgs = (C + 7) >> 3;          // a ragged last group reads the row padding (never summed below)
@@ -1732,11 +1747,26 @@ __global__ void __launch_bounds__(kEcaThreads) eca_partial_vec_kernel(const EcaP
   const int cg = threadIdx.x % cgs;                 // a thread keeps its channel group
   const int lanes = kEcaThreads / cgs;              // threads beyond lanes * cgs idle (cgs need not divide 256)
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int pos = threadIdx.x / cgs < lanes ? p0 + threadIdx.x / cgs : p1; pos < p1; pos += lanes) {
-    float m[8];
-    eca_tmax8(p, b, pos, cg, m);
+  if (p.dense) {
+    const int HW = p.x.H * p.x.W;
+    const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + (long long)b * p.x.sB;
+    int pos = threadIdx.x / cgs < lanes ? p0 + threadIdx.x / cgs : p1;
+    int tp = pos / HW, hw = pos - tp * HW;
+    for (; pos < p1; pos += lanes) {
+      float m[8];
+      eca_tmax8_dense(p, xb, tp, hw, cg, m);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] += m[j];
+      for (int j = 0; j < 8; ++j) s[j] += m[j];
+      hw += lanes;
+      while (hw >= HW) hw -= HW, ++tp;
+    }
+  } else {
+    for (int pos = threadIdx.x / cgs < lanes ? p0 + threadIdx.x / cgs : p1; pos < p1; pos += lanes) {
+      float m[8];
+      eca_tmax8(p, b, pos, cg, m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += m[j];
+    }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = s[j];
@@ -1785,16 +1815,29 @@ __global__ void __launch_bounds__(kEcaThreads) eca_apply_vec_kernel(const EcaPar
   float ml[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) ml[j] = mul[cg * 8 + j], sh[j] = shift[cg * 8 + j];
-  for (int pos = threadIdx.x / cgs < lanes ? p0 + threadIdx.x / cgs : p1; pos < p1; pos += lanes) {
+  const int HW = p.x.H * p.x.W;
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + (long long)b * p.x.sB;
+  int pos = threadIdx.x / cgs < lanes ? p0 + threadIdx.x / cgs : p1;
+  int tpd = pos / HW, hwd = pos - tpd * HW;       // carried incrementally on the dense path
+  for (; pos < p1; pos += lanes) {
     float m[8];
-    eca_tmax8(p, b, pos, cg, m);
+    __nv_bfloat16* yp;
+    if (p.dense) {
+      eca_tmax8_dense(p, xb, tpd, hwd, cg, m);
+      yp = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + (long long)b * p.y.sB + (long long)tpd * p.y.sT +
+           (long long)hwd * p.y.sW + cg * 8;
+      hwd += lanes;
+      while (hwd >= HW) hwd -= HW, ++tpd;
+    } else {
+      eca_tmax8(p, b, pos, cg, m);
+      const int w = pos % p.x.W;
+      const int r = pos / p.x.W;
+      const int h = r % p.x.H;
+      const int tp = r / p.x.H;
+      yp = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + voff(p.y, b, tp, h, w) + cg * 8;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = fmaxf(fmaf(m[j], ml[j], sh[j]), 0.f);
-    const int w = pos % p.x.W;
-    const int r = pos / p.x.W;
-    const int h = r % p.x.H;
-    const int tp = r / p.x.H;
-    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + voff(p.y, b, tp, h, w) + cg * 8;
     if (nv == 8) {
       uint4 o;
       o.x = pack16x2(m[0], m[1], p.y.f16), o.y = pack16x2(m[2], m[3], p.y.f16);
@@ -2528,6 +2571,7 @@ extern "C" int esf_eca_fuse(const esf_view* x_fast, int32_t alpha, const float* 
   EcaParams p;
   p.x = to_view(x_fast), p.y = to_view(y_slow_slice);
   p.alpha = alpha, p.eca_w = eca_w, p.eca_k = eca_k, p.bn_scale = bn_scale, p.bn_shift = bn_shift, p.partial = partial;
+  p.dense = p.x.sH == (long long)p.x.W * p.x.sW && p.y.sH == (long long)p.y.W * p.y.sW;
   const long long npos = (long long)(x_fast->T / alpha) * x_fast->H * x_fast->W;
   const int nblk = (int)std::max(1LL, std::min<long long>(kEcaBlocksPerClip, npos / 32));
   dim3 grid(nblk, x_fast->B);

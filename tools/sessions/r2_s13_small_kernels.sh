@@ -2,7 +2,7 @@
 # round 2: reworked HBM-bound helpers (stem pack through shared memory, packed 16-bit max-pool, head pool grid): tests + step
 set -u
 cd "$(dirname "$0")/../.."
-O=gpurun_out/r2_s13
+O=gpurun_out/r2_s16
 mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1 || { tail -5 $O/build.log; exit 1; }
 timeout 1500 python -m pytest tests/ -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc $?"; tail -6 $O/pytest_gpu.log
