@@ -77,6 +77,8 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, ui
       : "memory");
 }
 
+// SPLIT (compile time: the 16-bit plan's code must not carry the FP32 plan's branches): P and V as FP16 pairs
+template <bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
   uint8_t* Ks = Qs + 2 * p.q_tile_bytes;                // stages x k_tile_bytes
   uint8_t* Vs = Ks + p.stages * p.k_tile_bytes;         // stages x v_tile_bytes
   uint8_t* Ps = Vs + p.stages * p.v_tile_bytes;         // 2 x 16 KB (split mode: 2 x (16 KB P_hi + 16 KB P_lo))
-  const uint32_t p_q_bytes = p.split ? 32768u : 16384u;
+  const uint32_t p_q_bytes = SPLIT ? 32768u : 16384u;
   uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + 2 * p_q_bytes);
   uint64_t* q_full = bars;                   // 1
   uint64_t* kv_full = q_full + 1;            // stages
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
     prefetch_tmap(&p.q_map);
     prefetch_tmap(&p.k_map);
     prefetch_tmap(&p.v_map);
-    if (p.split) prefetch_tmap(&p.vlo_map);
+    if (SPLIT) prefetch_tmap(&p.vlo_map);
   }
   if (warp == 9) {
     tmem_alloc(tmem_slot, 512);
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
           tma_load_3d(Ks + stage * p.k_tile_bytes + ch * chunk_bytes_k, &p.k_map, &kv_full[stage], ch * p.chunk_el,
                       j * kTcBN, b);
         tma_load_3d(Vs + stage * p.v_tile_bytes, &p.v_map, &kv_full[stage], j * kTcBN, 0, b);
-        if (p.split) tma_load_3d(Vs + stage * p.v_tile_bytes + p.v_half, &p.vlo_map, &kv_full[stage], j * kTcBN, 0, b);
+        if (SPLIT) tma_load_3d(Vs + stage * p.v_tile_bytes + p.v_half, &p.vlo_map, &kv_full[stage], j * kTcBN, 0, b);
       }
       __syncwarp();
       if (++stage == p.stages) {
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
         umma_bf16_lohi(o_tmem, p_lo + 2, pv_hi, vl + 2, pv_hi, idesc_o, 1);
         umma_bf16_lohi(o_tmem, p_lo + 4, pv_hi, vl + 4, pv_hi, idesc_o, 1);
         umma_bf16_lohi(o_tmem, p_lo + 6, pv_hi, vl + 6, pv_hi, idesc_o, 1);
-        if (p.split) {
+        if (SPLIT) {
           // the two correction products (2^-11 of the main one) go to an accumulator of their own, O2 = O + 2 DVp
           // columns: added to O they would only triple the number of roundings of the big accumulator
           const uint32_t pl2 = p_lo + (16384u >> 4), vl2 = vl + (p.v_half >> 4), o2 = o_tmem + 2 * p.DVp;
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
       if (j > 0 && __any_sync(0xffffffffu, raise)) {
         // rare: some row of this warp raised its maximum -> rescale this warp's 32 TMEM lanes of O
         tc_fence_after();
-        for (int part = 0; part < (p.split ? 2 : 1); ++part)
+        for (int part = 0; part < (SPLIT ? 2 : 1); ++part)
           for (int c0 = 0; c0 < p.DVp; c0 += 16) {
             float o[16];
             tmem_ld16(o_addr + part * 2 * p.DVp + c0, o);
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
         o.z = pack16x2(v[8 * ck + 4], v[8 * ck + 5], p.f16);
         o.w = pack16x2(v[8 * ck + 6], v[8 * ck + 7], p.f16);
         *reinterpret_cast<uint4*>(prow + swz(r * 128 + ck * 16, 7)) = o;
-        if (p.split) {   // P_lo = fp16(p - P_hi): the pair carries p to 2^-22
+        if (SPLIT) {   // P_lo = fp16(p - P_hi): the pair carries p to 2^-22
           const uint32_t hh[4] = {o.x, o.y, o.z, o.w};
           uint32_t ll[4];
 #pragma unroll
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
     for (int c0 = 0; c0 < p.DVp; c0 += 16) {
       float o[16];
       tmem_ld16(lane_addr + 4 * kTcBN + q * p.DVp + c0, o);
-      if (p.split) {
+      if (SPLIT) {
         float o2[16];
         tmem_ld16(lane_addr + 4 * kTcBN + 2 * p.DVp + q * p.DVp + c0, o2);
 #pragma unroll
@@ -460,7 +462,10 @@ __device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
 }
 
 // POLY: how many of every 8 element pairs take the FMA-pipe exponential instead of MUFU.EX2 (0 = none)
-template <bool F16, int POLY>
+// KNOBS (compile time): the round-2 experiment paths (second P buffer, independent Q.K^T issue).  With the knobs as
+// run-time flags the DEFAULT path lost 4 - 6 % (88 instead of 96 registers, d = 8: 11.04 -> 11.68 ms, d = 32: 12.23 ->
+// 12.68 ms at batch 64 on one box, tools/sessions/r2_s18_attn_regress.sh), so they are a separate instantiation.
+template <bool F16, int POLY, bool KNOBS>
 __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -488,7 +493,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
   // P buffers: one per (q, h) at columns 448.., or two (tile j uses buffer j & 1) at columns 384.. when O leaves room.
   // With one buffer the P store of tile j waits for the P.V MMA of tile j - 1, which queues behind the Q.K^T MMAs of
   // tile j + 1 on the in-order tensor pipe (ncu: 4.7 % of the softmax warps' samples sit in that wait).
-  const int pdbl = p.pdbl;
+  const int pdbl = KNOBS ? p.pdbl : 0;
   const uint32_t p_col0 = pdbl ? 384u : (uint32_t)kV2PCol;
   const uint32_t p_qh_cols = pdbl ? 32u : 16u;
 
@@ -571,7 +576,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
       }
       __syncwarp();
     };
-    if (p.qk_async) {
+    if (KNOBS && p.qk_async) {
       // The two query tiles advance independently: whichever has its S buffer free (and its K tile landed) gets its
       // next Q.K^T issued.  In lock step (the loop below) a late warp of one tile also delays the other tile's scores,
       // and all sixteen softmax warps reach their MUFU phase together (ncu: 6 % of their samples wait for S).
@@ -1039,9 +1044,14 @@ struct AttnTcOp : esf_op {
   int poly = 0;   // pairs of every 8 whose exponential runs on the FMA pipe (v2 only)
   int launch(cudaStream_t stream) override {
     if (v2) {
-#define ESF_V2_LAUNCH(PL)                                                                             \
-  if (params.f16) attn_tc_v2_kernel<true, PL><<<grid, kV2Threads, smem_bytes, stream>>>(params);       \
-  else attn_tc_v2_kernel<false, PL><<<grid, kV2Threads, smem_bytes, stream>>>(params);
+#define ESF_V2_LAUNCH(PL)                                                                                   \
+  if (params.f16) attn_tc_v2_kernel<true, PL, false><<<grid, kV2Threads, smem_bytes, stream>>>(params);      \
+  else attn_tc_v2_kernel<false, PL, false><<<grid, kV2Threads, smem_bytes, stream>>>(params);
+      if (params.pdbl || params.qk_async) {   // experiment build of the default (MUFU-only) loop
+        if (params.f16) attn_tc_v2_kernel<true, 0, true><<<grid, kV2Threads, smem_bytes, stream>>>(params);
+        else attn_tc_v2_kernel<false, 0, true><<<grid, kV2Threads, smem_bytes, stream>>>(params);
+        return check_launch("attn_tc_v2_kernel");
+      }
       switch (poly) {
         case 1: ESF_V2_LAUNCH(1) break;
         case 2: ESF_V2_LAUNCH(2) break;
@@ -1052,7 +1062,8 @@ struct AttnTcOp : esf_op {
 #undef ESF_V2_LAUNCH
       return check_launch("attn_tc_v2_kernel");
     }
-    attn_tc_kernel<<<grid, kTcThreads, smem_bytes, stream>>>(params);
+    if (params.split) attn_tc_kernel<true><<<grid, kTcThreads, smem_bytes, stream>>>(params);
+    else attn_tc_kernel<false><<<grid, kTcThreads, smem_bytes, stream>>>(params);
     return check_launch("attn_tc_kernel");
   }
 };
@@ -1290,12 +1301,18 @@ static int attn_tc_create_impl(const void* packed, const void* v_lo, int32_t B, 
     static unsigned char attr_done[kMaxDevices] = {0};   // kernel attributes are per device
     unsigned char* slot = device_slot(attr_done);
     if (!slot || !*slot) {
-      cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+      cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_tc_v2_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_tc_v2_kernel<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
 #define ESF_V2_ATTR(PL)                                                                                                  \
   if (e == cudaSuccess)                                                                                                  \
-    e = cudaFuncSetAttribute(attn_tc_v2_kernel<true, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);    \
+    e = cudaFuncSetAttribute(attn_tc_v2_kernel<true, PL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);    \
   if (e == cudaSuccess)                                                                                                  \
-    e = cudaFuncSetAttribute(attn_tc_v2_kernel<false, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+    e = cudaFuncSetAttribute(attn_tc_v2_kernel<false, PL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
       ESF_V2_ATTR(0) ESF_V2_ATTR(1) ESF_V2_ATTR(2) ESF_V2_ATTR(3) ESF_V2_ATTR(4)
 #undef ESF_V2_ATTR
       if (e != cudaSuccess) rc = set_error(ESF_ERR_CUDA, "cudaFuncSetAttribute(attn_tc) failed: %s", cudaGetErrorString(e));

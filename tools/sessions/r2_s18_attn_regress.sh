@@ -17,3 +17,9 @@ extern "C" int esf_attn_tc_create_split(const void*, const void*, int32_t, int32
 CU
 python -c "from efficient_slowfast_b200 import _build; _build.build(force=True)" > $O/build_old.log 2>&1 || { tail -5 $O/build_old.log; }
 for rep in 1 2; do for d in 8 32; do echo -n "round-1 kernel: "; timeout 120 python tools/prof_attn.py $d 8 56 64 tc 5 2>&1 | tail -1; done; done | tee $O/old.txt
+# back to the round-2 source; attention tests with the knobs off and on (the knob paths are a separate instantiation)
+cp $O/esf_attn_tc_r2.cu.bak efficient_slowfast_b200/csrc/esf_attn_tc.cu
+python -c "from efficient_slowfast_b200 import _build; _build.build(force=True)" > /dev/null 2>&1
+for k in "0 0" "1 1"; do set -- $k
+  ESF_ATTN_PDBL=$1 ESF_ATTN_QKASYNC=$2 timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fp32_path.py -x -q -m gpu -k "attention" 2>&1 | tail -1
+done
