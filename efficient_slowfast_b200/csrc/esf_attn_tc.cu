@@ -563,65 +563,95 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
     const uint32_t k_stage_step = p.k_tile_bytes >> 4;
     mbar_wait(q_full, 0, 33);
     tc_fence_after();
-    auto issue_s = [&](int q, int c, int stage) {
-      if (elect_one()) {
-        const uint32_t d_tmem = tmem_base + (q * 2 + (c & 1)) * kTcBN;
-        const uint32_t kb = k_lo + stage * k_stage_step;
-        const uint32_t q_lo = q_lo0 + q * q_step;
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-          if (i < p.nsteps2)
-            umma_bf16_lohi(d_tmem, q_lo + (p.steps2[i] & 0xffff), qk_hi, kb + (p.steps2[i] >> 16), qk_hi, idesc_s, i != 0);
-        umma_commit(&s_full[q * 2 + (c & 1)]);
-      }
-      __syncwarp();
-    };
-    if (KNOBS && p.qk_async) {
-      // The two query tiles advance independently: whichever has its S buffer free (and its K tile landed) gets its
-      // next Q.K^T issued.  In lock step (the loop below) a late warp of one tile also delays the other tile's scores,
-      // and all sixteen softmax warps reach their MUFU phase together (ncu: 6 % of their samples wait for S).
-      int cq[2] = {0, 0}, stq[2] = {0, 0};
-      uint32_t phq[2] = {0, 0};
-      uint32_t spins = 0;
-      uint64_t t0 = 0;
-      while (cq[0] < nt || cq[1] < nt) {
-        bool progress = false;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int c = cq[q];
-          if (c >= nt) continue;
-          if (!mbar_try_wait(&kv_full[stq[q]], phq[q])) continue;
-          if (!mbar_try_wait(&s_free[q * 2 + (c & 1)], ((c >> 1) & 1) ^ 1)) continue;
-          tc_fence_after();
-          issue_s(q, c, stq[q]);
-          cq[q] = c + 1;
-          if (++stq[q] == p.stages) stq[q] = 0, phq[q] ^= 1;
-          progress = true;
-        }
-        if (!progress && ((++spins) & 0xfff) == 0) {   // bounded like mbar_wait: a pipeline bug traps instead of hanging
-          const uint64_t now = globaltimer_ns();
-          if (t0 == 0) t0 = now;
-          else if (now - t0 > ESF_WAIT_TIMEOUT_NS) {
-            if (lane == 0) printf("[esf] attention Q.K issuer timeout: block %d tiles %d/%d of %d\n", (int)blockIdx.x, cq[0], cq[1], nt);
-            __trap();
-          }
-        }
-        if (progress) spins = 0, t0 = 0;
-      }
-    } else {
+    if constexpr (!KNOBS) {
+      // round 1's loop, verbatim (the two query tiles in lock step)
       int stage = 0;
       uint32_t phase = 0;
       for (int c = 0; c < nt; ++c) {
+        const int buf = c & 1;
         mbar_wait(&kv_full[stage], phase, 34);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          mbar_wait(&s_free[q * 2 + (c & 1)], ((c >> 1) & 1) ^ 1, 32);
+          mbar_wait(&s_free[q * 2 + buf], ((c >> 1) & 1) ^ 1, 32);
           tc_fence_after();
-          issue_s(q, c, stage);
+          if (elect_one()) {
+            const uint32_t d_tmem = tmem_base + (q * 2 + buf) * kTcBN;
+            const uint32_t kb = k_lo + stage * k_stage_step;
+            const uint32_t q_lo = q_lo0 + q * q_step;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+              if (i < p.nsteps2)
+                umma_bf16_lohi(d_tmem, q_lo + (p.steps2[i] & 0xffff), qk_hi, kb + (p.steps2[i] >> 16), qk_hi, idesc_s, i != 0);
+            umma_commit(&s_full[q * 2 + buf]);
+          }
+          __syncwarp();
         }
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
+        }
+      }
+    } else {
+      auto issue_s = [&](int q, int c, int stage) {
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + (q * 2 + (c & 1)) * kTcBN;
+          const uint32_t kb = k_lo + stage * k_stage_step;
+          const uint32_t q_lo = q_lo0 + q * q_step;
+  #pragma unroll
+          for (int i = 0; i < 6; ++i)
+            if (i < p.nsteps2)
+              umma_bf16_lohi(d_tmem, q_lo + (p.steps2[i] & 0xffff), qk_hi, kb + (p.steps2[i] >> 16), qk_hi, idesc_s, i != 0);
+          umma_commit(&s_full[q * 2 + (c & 1)]);
+        }
+        __syncwarp();
+      };
+      if (KNOBS && p.qk_async) {
+        // The two query tiles advance independently: whichever has its S buffer free (and its K tile landed) gets its
+        // next Q.K^T issued.  In lock step (the loop below) a late warp of one tile also delays the other tile's scores,
+        // and all sixteen softmax warps reach their MUFU phase together (ncu: 6 % of their samples wait for S).
+        int cq[2] = {0, 0}, stq[2] = {0, 0};
+        uint32_t phq[2] = {0, 0};
+        uint32_t spins = 0;
+        uint64_t t0 = 0;
+        while (cq[0] < nt || cq[1] < nt) {
+          bool progress = false;
+  #pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c = cq[q];
+            if (c >= nt) continue;
+            if (!mbar_try_wait(&kv_full[stq[q]], phq[q])) continue;
+            if (!mbar_try_wait(&s_free[q * 2 + (c & 1)], ((c >> 1) & 1) ^ 1)) continue;
+            tc_fence_after();
+            issue_s(q, c, stq[q]);
+            cq[q] = c + 1;
+            if (++stq[q] == p.stages) stq[q] = 0, phq[q] ^= 1;
+            progress = true;
+          }
+          if (!progress && ((++spins) & 0xfff) == 0) {   // bounded like mbar_wait: a pipeline bug traps instead of hanging
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > ESF_WAIT_TIMEOUT_NS) {
+              if (lane == 0) printf("[esf] attention Q.K issuer timeout: block %d tiles %d/%d of %d\n", (int)blockIdx.x, cq[0], cq[1], nt);
+              __trap();
+            }
+          }
+          if (progress) spins = 0, t0 = 0;
+        }
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int c = 0; c < nt; ++c) {
+          mbar_wait(&kv_full[stage], phase, 34);
+  #pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            mbar_wait(&s_free[q * 2 + (c & 1)], ((c >> 1) & 1) ^ 1, 32);
+            tc_fence_after();
+            issue_s(q, c, stage);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -641,14 +671,14 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
       const uint32_t p_par = pdbl ? ((j >> 1) & 1) : (j & 1);   // parity of this use of the buffer
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        mbar_wait(&p_full[(q * 2 + h) * 2 + pb], p_par, 36);
+        mbar_wait(KNOBS ? &p_full[(q * 2 + h) * 2 + pb] : &p_full[q * 2 + h], p_par, 36);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t o_tmem = tmem_base + 4 * kTcBN + (q * 2 + h) * p.DVp;
           const uint32_t p_tmem = tmem_base + p_col0 + (q * 2 + h) * p_qh_cols + pb * 16;
           umma_f16_ts(o_tmem, p_tmem, vl + 4 * h, pv_hi, idesc_o, j != 0);      // keys 32h .. 32h+15
           umma_f16_ts(o_tmem, p_tmem + 8, vl + 4 * h + 2, pv_hi, idesc_o, 1);  // keys 32h+16 .. 32h+31
-          umma_commit(&p_free[(q * 2 + h) * 2 + pb]);
+          umma_commit(KNOBS ? &p_free[(q * 2 + h) * 2 + pb] : &p_free[q * 2 + h]);
           if (h == 1) {
             umma_commit(&kv_empty[stage]);
             if (j == nt - 1) umma_commit(&o_full[q]);
@@ -711,7 +741,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[(q * 2 + h) * 2 + (pdbl ? ((j - 1) & 1) : 0)]);
+          if (lane == 0) mbar_arrive(KNOBS ? &p_full[(q * 2 + h) * 2 + (pdbl ? ((j - 1) & 1) : 0)] : &p_full[q * 2 + h]);
         }
         mx0 = fmaxf(fmaxf(mx0, v[i]), v[i + 1]);
         mx1 = fmaxf(fmaxf(mx1, v[i + 2]), v[i + 3]);
@@ -772,7 +802,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
       const int pb = pdbl ? (j & 1) : 0;
       const uint32_t p_par = pdbl ? ((j >> 1) & 1) : (j & 1);
       const uint32_t p_addr = p_addr0 + pb * 16;
-      mbar_wait(&p_free[(q * 2 + h) * 2 + pb], p_par ^ 1, 38);   // the previous use of this P buffer has been consumed
+      mbar_wait(KNOBS ? &p_free[(q * 2 + h) * 2 + pb] : &p_free[q * 2 + h], p_par ^ 1, 38);   // previous use consumed
       tc_fence_after();
       ESF_TICK(4)   // wait p_free
       if (j > 0 && any_raise) {
@@ -795,7 +825,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[(q * 2 + h) * 2 + pb]);
+        if (lane == 0) mbar_arrive(KNOBS ? &p_full[(q * 2 + h) * 2 + pb] : &p_full[q * 2 + h]);
       }
       ESF_TICK(5)   // O rescale + P store + p_full arrive
       if (j + 1 < nt) {
