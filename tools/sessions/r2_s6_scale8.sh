@@ -2,12 +2,12 @@
 # round 2: 8-GPU weak scaling of the headline bench, e2e from FP32 host clips (slow-from-fast upload, H2D ceiling in the line)
 set -u
 cd "$(dirname "$0")/../.."
-O=gpurun_out/r2_s6
+O=gpurun_out/r2_s20
 mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1 || { tail -5 $O/build.log; exit 1; }
 ls /sys/devices/system/node/ | tr '\n' ' '; echo; nvidia-smi topo -m 2>/dev/null | head -14
 N=${1:-8}
-for extra in "" "--no-numa-bind"; do
+for extra in ""; do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus $N --steps 8 --warmup 3 $extra > $O/bench_n${N}${extra}.json 2> $O/bench_n${N}${extra}.err
   python - <<PY
