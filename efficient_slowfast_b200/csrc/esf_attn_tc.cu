@@ -1016,7 +1016,47 @@ __global__ void __launch_bounds__(256) attn_tc_pack_kernel(const float* __restri
   auto bits = [](__nv_bfloat16 a, __nv_bfloat16 b2) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
   };
-  if (KQ % 8 == 0) {
+  // pair (e, e + 1) of a Q~ / K~ row as one packed word each: one F2FP per hi pair, unpack + two FADD + one F2FP per lo
+  // pair (the element-wise form below converts and shifts every half on its own; ncu, round 2: 61 - 74 % of the issue
+  // slots busy at 2.9 - 4.5 TB/s)
+  auto qk_pair = [&](const float* pr, int e, uint32_t& qw, uint32_t& kw) {
+    qw = kw = 0u;
+    int part_q = 0, part_k = 0, jj = -1;       // part: 0 hi, 1 lo;  jj: first channel of the pair (-1: zero padding)
+    if (mode == 0) {
+      const int seg = e >> 3;
+      if (seg < 3 && (e & 7) < d) jj = e & 7, part_q = seg == 1, part_k = seg == 2;
+    } else if (mode == 1) {
+      const int half = KQ >> 1;
+      const int part = e / half;
+      if (e % half < d) jj = e % half, part_q = part_k = part;
+    } else if (e < d) {
+      jj = e;
+    }
+    if (jj < 0) return;
+    const float q0 = pr[d + jj], q1 = pr[d + jj + 1], k0 = pr[2 * d + jj], k1 = pr[2 * d + jj + 1];
+    qw = pack16x2(q0, q1, f16);
+    kw = pack16x2(k0, k1, f16);
+    if (part_q) {
+      const float2 h = unpack16x2(qw, f16);
+      qw = pack16x2(q0 - h.x, q1 - h.y, f16);
+    }
+    if (part_k) {
+      const float2 h = unpack16x2(kw, f16);
+      kw = pack16x2(k0 - h.x, k1 - h.y, f16);
+    }
+  };
+  if (KQ % 8 == 0 && d % 2 == 0) {
+    const int g8 = KQ >> 3;
+    for (int i = threadIdx.x; i < rows * g8; i += blockDim.x) {
+      const int r = i / g8, e0 = (i % g8) * 8;
+      const float* pr = tile + r * pitch;
+      uint32_t qw[4], kw[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) qk_pair(pr, e0 + 2 * e, qw[e], kw[e]);
+      *reinterpret_cast<uint4*>(qd + (long long)r * KQ + e0) = make_uint4(qw[0], qw[1], qw[2], qw[3]);
+      *reinterpret_cast<uint4*>(kd + (long long)r * KQ + e0) = make_uint4(kw[0], kw[1], kw[2], kw[3]);
+    }
+  } else if (KQ % 8 == 0) {
     const int g8 = KQ >> 3;
     for (int i = threadIdx.x; i < rows * g8; i += blockDim.x) {
       const int r = i / g8, e0 = (i % g8) * 8;
