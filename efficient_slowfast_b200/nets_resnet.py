@@ -347,6 +347,8 @@ class _PlannedModel(nn.Module):
         if dev.type != "cuda":
             raise rt.EsfError("the forward path is CUDA-only (sm_100a); got tensors on %s -- there is no CPU fallback"
                               % dev)
+        if x[0].shape[0] == 0:        # an empty batch is an empty result (nn.Conv3d / nn.Linear of the reference agree)
+            return torch.empty((0, int(self._cfg.MODEL.NUM_CLASSES)), dtype=torch.float32, device=dev)
         plan = self._get_plan([tuple(t.shape) for t in x], dev)
         # FP32 contiguous clips are read in place by the stem kernels (launched outside the CUDA graph); anything else
         # (other dtype / strides) is first converted into the plan-owned input buffers
@@ -379,6 +381,8 @@ class _PlannedModel(nn.Module):
         if fast.dtype != torch.float32 or fast.dim() != 5 or not fast.is_contiguous() or fast.data_ptr() % 16:
             raise rt.EsfError("forward_fast expects a contiguous FP32 clip (B, C, T, H, W)")
         B, C, T, H, W = fast.shape
+        if B == 0:
+            return torch.empty((0, int(self._cfg.MODEL.NUM_CLASSES)), dtype=torch.float32, device=dev)
         alpha = self._cfg.SLOWFAST.ALPHA
         plan = self._get_plan([(B, C, T // alpha, H, W), (B, C, T, H, W)], dev)
         idx = getattr(plan, "slow_index", None)
@@ -415,6 +419,8 @@ class _PlannedModel(nn.Module):
         if frames.dtype != torch.uint8 or frames.dim() != 5 or not frames.is_contiguous():
             raise rt.EsfError("forward_frames expects contiguous uint8 frames (B, T, H, W, C)")
         dev = frames.device
+        if frames.shape[0] == 0:
+            return torch.empty((0, int(self._cfg.MODEL.NUM_CLASSES)), dtype=torch.float32, device=dev)
         shapes = self.frame_shapes(tuple(frames.shape))
         if frame_index is not None:     # explicit source frame of every pathway frame (frames may be a ring buffer)
             assert len(frame_index) == self.num_pathways

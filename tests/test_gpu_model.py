@@ -363,3 +363,13 @@ def test_plan_cache_keeps_two_shapes_and_drops_stale_weights(esf_lib):
         model.invalidate_plans()
         y_zero = model(xs).cpu()
         assert not torch.equal(y_zero, y_new)
+
+
+def test_empty_batch_returns_empty_predictions(esf_lib):
+    """Edge case: a zero-clip batch gives a (0, num_classes) result on every entry point instead of a kernel launch."""
+    cfg, model, gold, _ = _run("slowfast_r50", "s64")
+    xs = [t.cuda()[:0] for t in helpers.case_inputs("slowfast_r50", "s64")]
+    with torch.no_grad():
+        assert tuple(model(xs).shape) == (0, 400)
+        assert tuple(model.forward_fast(xs[1]).shape) == (0, 400)
+        assert tuple(model.forward_frames(torch.zeros(0, 32, 64, 64, 3, dtype=torch.uint8, device="cuda")).shape) == (0, 400)
