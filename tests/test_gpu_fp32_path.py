@@ -259,6 +259,11 @@ def test_attention_split_tensor_core(esf_lib, d, T, H, W, alpha, qk):
     # the fork's grey-scale R18 product configs (one input channel, ALPHA 8, strides (1,1,2,2); s128: fully-convolutional
     # head is not part of this plan)
     ("dual_r18_gray", "s112", 1e-4), ("fast_r18_gray", "s112", 1e-4),
+    # the STRESS recipe of SURVEY 8(c) (final-BN gamma ~ U(0.5, 1.5), un-scaled q / k: logits reach |s| ~ 200 and the
+    # random network amplifies any perturbation ~3x per stage, so the 16-bit plans are only held to argmax + 3e-1 on
+    # it, tests/test_gpu_model.py): with FP32-accurate arithmetic the same weights and clips are inside the north star's
+    # 16-bit tolerance by a wide margin -- the looseness there is storage precision, not the implementation
+    ("slowfast_r50_stress", "s64", 2e-3), ("dual_r50_stress", "s64", 5e-3),   # measured 2.9e-4 / 1.8e-3 (FP16: 4.0e-2 / 7.0e-2)
     # Non-local blocks (softmax / dot_product instantiation): the 16-bit plan is held to 4e-2 / 2e-2 on these draws
     # (tests/test_gpu_model.py: the softmax blocks of this random draw amplify ANY perturbation ~50x more than the plain
     # I3D trunk) -- the same weights and clips in the FP32-accurate plan: measured 2.8e-4 / 1.8e-4, i.e. 70x / 14x
