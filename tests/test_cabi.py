@@ -59,3 +59,33 @@ def test_forward_without_gpu_fails_loudly():
     m.train()
     with pytest.raises(NotImplementedError):
         m([torch.zeros(1, 3, 8, 32, 32), torch.zeros(1, 3, 32, 32, 32)])
+
+
+def test_hot_kernels_keep_their_resource_budget(esf_lib):
+    """Guard for a regression measured in round 2: adding run-time flags to the position-attention kernel changed the
+    register allocation of its default instantiation (96 -> 88) and cost 4-6 % of the step although the flags were off
+    (profiles/r2_attention_experiments.md section 5).  The default instantiations of the two hot kernels must keep the
+    resources they were tuned with and must not use local memory."""
+    import shutil
+    import subprocess
+
+    from efficient_slowfast_b200 import runtime
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-res-usage", runtime.lib_path()], stdout=subprocess.PIPE, text=True).stdout
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        line = line.strip()
+        if line.startswith("Function "):
+            name = line[len("Function "):].rstrip(":")
+        elif line.startswith("REG:") and name:
+            usage[name] = dict(kv.split(":") for kv in line.split() if ":" in kv and not kv.startswith("CONSTANT"))
+    v2 = [u for n, u in usage.items() if "attn_tc_v2_kernelILb1ELi0ELb0E" in n or "attn_tc_v2_kernelILb0ELi0ELb0E" in n]
+    assert len(v2) == 2, sorted(usage)[:5]
+    for u in v2:          # 640 threads per CTA cap the kernel at 102 registers; the tuned loop uses 96
+        assert int(u["REG"]) == 96 and int(u["LOCAL"]) == 0, u
+    ig = [u for n, u in usage.items() if "igemm_kernel" in n]
+    assert ig and all(int(u["REG"]) <= 104 and int(u["LOCAL"]) == 0 for u in ig), ig
