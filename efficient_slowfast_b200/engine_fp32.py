@@ -220,9 +220,17 @@ class PrecisePlan(Plan):
         mats, biases = [wd], [torch.zeros(d, dtype=torch.float64)]
         for conv in (att.query_conv, att.key_conv, att.value_conv):
             wc = host64(conv.weight).reshape(conv.weight.shape[0], d)
-            assert wc.shape[0] == d, "SpatialAttention reduction != 1 is not used by any registered model"
+            bc = host64(conv.bias)
+            if wc.shape[0] < d:
+                # SpatialAttention(reduction > 1) (wdf_attention_helper.py:17-26): query / key have d / reduction
+                # channels.  Zero rows up to d leave every logit q.k unchanged and keep the kernels' one head dim.
+                # (No cfg key reaches this: every call site of the reference hard-codes reduction = 1.)
+                assert conv is not att.value_conv, "value_conv keeps all channels"
+                pad = d - wc.shape[0]
+                wc = torch.cat([wc, torch.zeros(pad, d, dtype=wc.dtype)], 0)
+                bc = torch.cat([bc, torch.zeros(pad, dtype=bc.dtype)], 0)
             mats.append(wc @ wd)
-            biases.append(host64(conv.bias))
+            biases.append(bc)
         w_all = torch.cat(mats, 0).reshape(4 * d, C, 1, 1, 1)
         b_all = torch.cat(biases, 0)
         proj = super().act(B, T, H, W, 4 * d, dtype=torch.float32)

@@ -107,6 +107,13 @@ CASES = {
     "slowfast_r50_g2": dict(     # ResNeXt-style grouped 1x3x3 (RESNET.NUM_GROUPS = 2; resnet_helper.py:196-205)
         model="SlowFast", yaml="configs/Kinetics/SLOWFAST_4x16_R50.yaml",
         opts=["MULTIGRID.SHORT_CYCLE", True, "RESNET.NUM_GROUPS", 2], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),
+    "slowfast_r101": dict(       # RESNET.DEPTH 101: 23 blocks in res4 (video_model_builder.py:15)
+        model="SlowFast", yaml="configs/Kinetics/SLOWFAST_4x16_R50.yaml",
+        opts=["MULTIGRID.SHORT_CYCLE", True, "RESNET.DEPTH", 101], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),
+    "slowfast_r50_sigmoid": dict(    # MODEL.HEAD_ACT sigmoid (the multi-label configs, head_helper.py:189-196)
+        model="SlowFast", yaml="configs/Kinetics/SLOWFAST_4x16_R50.yaml",
+        opts=["MULTIGRID.SHORT_CYCLE", True, "MODEL.HEAD_ACT", "sigmoid", "MODEL.NUM_CLASSES", 157],
+        calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),
     "slowfast_r50_stress": dict(
         model="SlowFast", yaml="configs/Kinetics/SLOWFAST_4x16_R50.yaml", stress=True,
         opts=["MULTIGRID.SHORT_CYCLE", True], calib=(2, 32, 96), inputs=[("s64", 2, 32, 64)]),
@@ -181,6 +188,15 @@ def case_cfg(name):
     elif name in ("slowfast_r50", "slowfast_r50_stress"):
         cfg = esf.slowfast_4x16_r50_cfg()
         cfg.MULTIGRID.SHORT_CYCLE = True
+    elif name == "slowfast_r101":
+        cfg = esf.slowfast_4x16_r50_cfg()
+        cfg.MULTIGRID.SHORT_CYCLE = True
+        cfg.RESNET.DEPTH = 101
+    elif name == "slowfast_r50_sigmoid":
+        cfg = esf.slowfast_4x16_r50_cfg()
+        cfg.MULTIGRID.SHORT_CYCLE = True
+        cfg.MODEL.HEAD_ACT = "sigmoid"
+        cfg.MODEL.NUM_CLASSES = 157
     elif name == "slowfast_r50_g2":
         cfg = esf.slowfast_4x16_r50_cfg()
         cfg.MULTIGRID.SHORT_CYCLE = True

@@ -833,3 +833,43 @@ def test_pool3d_fp16_packed_max(esf_lib):
         plan.launch_all()
         torch.cuda.synchronize()
         assert torch.equal(_to_ncdhw(y.cpu()), ref)
+
+
+def test_position_attention_with_channel_reduction(esf_lib):
+    """SpatialAttention(reduction = 2) (wdf_attention_helper.py:17-26; no cfg key of the reference reaches it): query / key
+    with d / 2 channels run on the same kernels through zero-padded projection rows."""
+    from efficient_slowfast_b200.nets_resnet import FuseFastAndSlow
+
+    g = torch.Generator().manual_seed(9)
+    B, T, H, W, C, beta, alpha = 2, 2, 6, 5, 64, 8, 4
+    fuse = FuseFastAndSlow([C, C // beta], alpha, beta, torch.nn.BatchNorm3d, reduction=2)
+    d = C // beta
+    with torch.no_grad():
+        for prm in fuse.parameters():
+            prm.copy_(torch.randn(prm.shape, generator=g) * 0.3)
+        fuse.attention_spatial_s2f.gamma.fill_(0.6)
+        bn = fuse.bn_s2f
+        bn.running_mean.copy_(torch.randn(d, generator=g) * 0.2)
+        bn.running_var.copy_(torch.rand(d, generator=g) + 0.5)
+    fuse.eval()
+    att = fuse.attention_spatial_s2f
+    assert att.query_conv.out_channels == d // 2
+    x = torch.randn(B, C, T, H, W, generator=g)
+    with torch.no_grad():    # wdf_attention_helper.py:33-54 + custom_video_model_builder.py:141-146, FP64
+        xd = F.conv3d(x.double(), fuse.downsample_c_of_slow.weight.double())
+        N = T * H * W
+        q = F.conv3d(xd, att.query_conv.weight.double(), att.query_conv.bias.double()).view(B, -1, N).permute(0, 2, 1)
+        k = F.conv3d(xd, att.key_conv.weight.double(), att.key_conv.bias.double()).view(B, -1, N)
+        v = F.conv3d(xd, att.value_conv.weight.double(), att.value_conv.bias.double()).view(B, -1, N)
+        o = torch.bmm(v, torch.softmax(torch.bmm(q, k), dim=-1).permute(0, 2, 1)).view(B, d, T, H, W)
+        ref = bn.double()(att.gamma.double() * o + xd).relu().repeat_interleave(alpha, dim=2)
+    bn.float()
+    plan = Plan(DEV, "fp16")
+    xs = plan.act(B, T, H, W, C)
+    xs.copy_(_to_ndhwc(x).to(torch.float16))
+    ybuf = plan.act(B, T * alpha, H, W, 2 * d)
+    plan.position_attention(xs, ybuf[..., :d], alpha, fuse.downsample_c_of_slow.weight, att, bn)
+    plan.launch_all()
+    torch.cuda.synchronize()
+    got = _to_ncdhw(ybuf[..., :d].cpu()).double()
+    assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()

@@ -18,7 +18,7 @@ from oracle import slowfast_oracle as O
                                       ("slow_nln_r50", "s64"), ("i3d_nln_r50", "s96"),
                                       ("slowfast_r50_fcn", "s96"), ("slowfast_r50_fcn", "s64"), ("slow_r50", "s96"),
                                       ("slowfast_r50_g2", "s64"), ("dual_r18_gray", "s112"), ("dual_r18_gray", "s128"),
-                                      ("fast_r18_gray", "s112")])
+                                      ("fast_r18_gray", "s112"), ("slowfast_r101", "s64"), ("slowfast_r50_sigmoid", "s64")])
 def test_oracle_matches_reference_golden(name, tag):
     cfg, model, gold = helpers.case_model_and_weights(name)
     xs = helpers.case_inputs(name, tag)
@@ -43,7 +43,7 @@ def test_oracle_matches_reference_golden(name, tag):
             ref = gold["%s/%s/%d/samples" % (tag, sname, pw)]
             scale = gold["%s/%s/%d/stats" % (tag, sname, pw)][2]
             assert np.abs(smp.numpy() - ref).max() <= tol * scale, (sname, pw)
-    if name != "ghostnet_w1":       # the GhostNet head returns ReLU(logits), not probabilities
+    if name != "ghostnet_w1" and cfg.MODEL.HEAD_ACT == "softmax":   # GhostNet: ReLU(logits); sigmoid heads: multi-label
         assert abs(y.sum(1) - 1).max() < 1e-5
 
 
