@@ -1089,6 +1089,357 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
   return ESF_OK;
 }
 
+// ---- temporal-band stem: the kT x kH x kW stem with the TIME taps folded into N ------------------------------------
+// Why: the banded stem above is bound by the shared-memory port, not by the tensor pipe.  Its N is one
+// block of output columns (64), so every 16 KB activation tile is filled once and read once by MMAs that also re-read
+// 8 KB of weights each: 1 680 KB per 128 x 8 outputs through a 128 B/clk port.  Here
+//   * an M tile (128 rows = bh output rows x bb clips, one block of WB output columns) STAYS on its SM while the input
+//     frames g = 0 .. T-1 stream through: the tile of input frame g and row tap kh is loaded once and multiplied by
+//     the weights of ALL kT time taps at once -- N = (kT output frames) x (WB x Cout) -- so the A read of an MMA is
+//     amortised over kT times more columns and the tile is fetched kT times less often;
+//   * output frame t accumulates in its own TMEM slot (t mod nslots, NB = WB x Cout columns each; 512 columns = 16
+//     slots of 32) from the kT input frames that touch it; a slot is published to the epilogue warps as soon as its last
+//     input frame is done and is re-used nslots frames later -- the accumulators are a ring over time;
+//   * the whole band matrix (kH tiles of [kT x NB rows][64]) is loaded ONCE per CTA and stays in shared memory.
+// MMA of input frame g, tap kh, k-step ks:  D[slot(t_lo) ..][128 x cnt*NB] += A_g,kh[128 x 16] . Wb_kh[u_lo*NB ..]^T
+// with t = g + pT - kT + 1 + u, weights of time tap kt = kT - 1 - u; split where the slot ring wraps and where a slot
+// is written for the first time (accumulate flag off).
+constexpr int kTbThreads = 6 * 32;   // TMA producer, MMA issuer, 4 epilogue warps (one per TMEM lane quarter)
+constexpr int kTbMaxKH = 8;
+constexpr int kTbMaxStages = 8;
+
+struct __align__(64) StemTbParams {
+  CUtensorMap a_maps[kMaxAMaps];   // one per row phase of the H stride
+  CUtensorMap b_map;
+  int a_map_of_kh[kTbMaxKH], qh_of_kh[kTbMaxKH];
+  int kT, kH, pT;
+  int T, To, Ho, B;
+  int bh, bb, th, tb, ncb, rows;
+  int a_cb_stride;   // elements between the windows of consecutive column blocks
+  int ksteps;        // 16-element K steps per tap
+  int NB, nslots;    // columns per output-frame slot, slots in the ring (power of two)
+  int stages;
+  uint32_t a_bytes, b_tile_bytes;
+  const float* bias;   // [NB] tiled (i, co)
+  int act, f16;
+  __nv_bfloat16* y;
+  long long ysB, ysT, ysH;
+  int num_tiles;
+};
+
+__global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_constant__ StemTbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem;
+  uint8_t* smem_a = smem_b + p.kH * p.b_tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + p.stages * kAStageBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kTbMaxStages;
+  uint64_t* acc_full = a_empty + kTbMaxStages;   // [nslots <= 32]
+  uint64_t* acc_free = acc_full + 32;
+  uint64_t* b_full = acc_free + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  const int smask = p.nslots - 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < p.nslots; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_free[s], 4);
+    }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.b_map);
+    prefetch_tmap(&p.a_maps[0]);
+    prefetch_tmap(&p.a_maps[1]);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(b_full, p.kH * p.b_tile_bytes);
+      for (int kh = 0; kh < p.kH; ++kh) tma_load_2d(smem_b + kh * p.b_tile_bytes, &p.b_map, b_full, kh * 64, 0);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int cb = tile % p.ncb, m = tile / p.ncb;
+      const int h0 = (m % p.th) * p.bh, b0 = (m / p.th) * p.bb;
+      for (int g = 0; g < p.T; ++g)
+        for (int kh = 0; kh < p.kH; ++kh) {
+          mbar_wait(&a_empty[stage], phase ^ 1, 51);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&a_full[stage], p.a_bytes);
+            tma_load_5d(smem_a + stage * kAStageBytes, &p.a_maps[p.a_map_of_kh[kh]], &a_full[stage], cb * p.a_cb_stride,
+                        0, h0 + p.qh_of_kh[kh], g, b0);
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc0 = make_idesc_16(128, 0, p.f16);
+    const uint32_t desc_hi = kmajor_desc_hi(1024, 2);
+    const uint32_t a_lo0 = kmajor_desc_lo(smem_u32(smem_a)), b_lo0 = kmajor_desc_lo(smem_u32(smem_b));
+    const uint32_t b_kh_step = p.b_tile_bytes >> 4, b_u_step = (uint32_t)(p.NB * 128) >> 4;
+    const int back = p.kT - 1 - p.pT;   // output frame t is complete after input frame min(t + back, T - 1)
+    mbar_wait(b_full, 0, 52);
+    tc_fence_after();
+    int stage = 0;
+    uint32_t phase = 0, free_bits = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int g = 0; g < p.T; ++g) {
+        const int t_base = g + p.pT - p.kT + 1;
+        const int t_lo = max(t_base, 0), t_hi = min(g + p.pT, p.To - 1);
+        const int new_lo = g == 0 ? 0 : g + p.pT;     // frames >= new_lo are written for the first time in this step
+        for (int t = max(new_lo, t_lo); t <= t_hi; ++t) {   // their slots must have been drained by the epilogue
+          const int s = t & smask;
+          mbar_wait(&acc_free[s], ((free_bits >> s) & 1) ^ 1, 53);
+          free_bits ^= 1u << s;
+        }
+        tc_fence_after();
+        for (int kh = 0; kh < p.kH; ++kh) {
+          mbar_wait(&a_full[stage], phase, 54);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo = a_lo0 + stage * (kAStageBytes >> 4);
+            const uint32_t b_lo = b_lo0 + kh * b_kh_step;
+            // frames [a, b] with one accumulate flag, split where the slot ring wraps
+            auto emit = [&](int a, int b, int ks, uint32_t acc) {
+              if (a > b) return;
+              const int sa = a & smask;
+              const int n1 = min(b - a + 1, p.nslots - sa);
+              umma_bf16_lohi(tmem_base + sa * p.NB, a_lo + 2 * ks, desc_hi, b_lo + (a - t_base) * b_u_step + 2 * ks, desc_hi,
+                             idesc0 | ((uint32_t)((n1 * p.NB) >> 3) << 17), acc);
+              if (n1 < b - a + 1)
+                umma_bf16_lohi(tmem_base, a_lo + 2 * ks, desc_hi, b_lo + (a + n1 - t_base) * b_u_step + 2 * ks, desc_hi,
+                               idesc0 | ((uint32_t)(((b - a + 1 - n1) * p.NB) >> 3) << 17), acc);
+            };
+            for (int ks = 0; ks < p.ksteps; ++ks) {
+              if (kh == 0 && ks == 0) {
+                emit(t_lo, min(new_lo - 1, t_hi), ks, 1);
+                emit(max(new_lo, t_lo), t_hi, ks, 0);
+              } else {
+                emit(t_lo, t_hi, ks, 1);
+              }
+            }
+            umma_commit(&a_empty[stage]);
+            if (kh == p.kH - 1)
+              for (int t = t_lo; t <= t_hi; ++t)
+                if (g == min(t + back, p.T - 1)) umma_commit(&acc_full[t & smask]);
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: one warp per TMEM lane quarter
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t full_bits = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int cb = tile % p.ncb, m = tile / p.ncb;
+      const int ho = (m % p.th) * p.bh + r % p.bh, b = (m / p.th) * p.bb + r / p.bh;
+      const bool valid = r < p.rows && ho < p.Ho && b < p.B;
+      __nv_bfloat16* yrow = p.y + b * p.ysB + ho * p.ysH + (long long)cb * p.NB;
+      for (int t = 0; t < p.To; ++t) {
+        const int s = t & smask;
+        mbar_wait(&acc_full[s], (full_bits >> s) & 1, 55);
+        full_bits ^= 1u << s;
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.NB; c0 += 16) {
+          float v[16];
+          tmem_ld16(lane_addr + s * p.NB + c0, v);
+          if (valid) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              pk[i] = pack16x2(apply_act(v[2 * i] + __ldg(p.bias + c0 + 2 * i), p.act),
+                               apply_act(v[2 * i + 1] + __ldg(p.bias + c0 + 2 * i + 1), p.act), p.f16);
+            uint4* dst = reinterpret_cast<uint4*>(yrow + t * p.ysT + c0);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_free[s]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+struct StemTbOp : esf_op {
+  StemTbParams params;
+  int grid = 0;
+  int smem_bytes = 0;
+  int launch(cudaStream_t stream) override {
+    stem_tband_kernel<<<grid, kTbThreads, smem_bytes, stream>>>(params);
+    return check_launch("stem_tband_kernel");
+  }
+};
+
+// Width of the output-column block (WB) of the temporal-band stem for this geometry, 0 when it does not apply.
+static int stem_tband_wb(int Cin, int Cout, int kT, int kH, int kW, int sW, int Wo) {
+  if (kT < 2 || kT > 8 || kH > kTbMaxKH) return 0;
+  const int cand[3] = {4, 8, 2};
+  for (int i = 0; i < 3; ++i) {
+    const int WB = cand[i];
+    const int win = ((WB - 1) * sW + kW) * Cin, NB = WB * Cout;
+    if (win > 64 || (WB * sW * Cin) % 8 != 0 || Wo % WB != 0) continue;
+    if (NB != 16 && NB != 32 && NB != 64) continue;
+    if (kT * NB > 256 || kTmemCols / NB < kT + 1) continue;
+    const int b_bytes = kH * kT * NB * 128;
+    if ((kSmemLimit - 1024 - 1024 - b_bytes) / kAStageBytes < 3) continue;
+    return WB;
+  }
+  return 0;
+}
+
+extern "C" int esf_stem_tband_wb(int32_t W, int32_t Cin, int32_t Cout, int32_t kT, int32_t kH, int32_t kW, int32_t sW,
+                                 int32_t pW) {
+  if (W <= 0 || Cin <= 0 || Cout <= 0 || kW <= 0 || sW <= 0 || pW < 0) return 0;
+  return stem_tband_wb(Cin, Cout, kT, kH, kW, sW, (W + 2 * pW - kW) / sW + 1);
+}
+
+extern "C" int esf_stem_tband_create(const void* xp, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W,
+                                     int32_t pitch, const void* w_band, const float* bias_tiled, int32_t Cout,
+                                     int32_t kT, int32_t kH, int32_t kW, int32_t sH, int32_t sW, int32_t pT, int32_t pH,
+                                     int32_t pW, int32_t act, const esf_view* y, esf_op** out) {
+  ESF_CHECK_ARG(xp && w_band && bias_tiled && view_ok(y) && out, "esf_stem_tband_create: null/bad argument");
+  ESF_CHECK_ARG(is16(y->dtype), "esf_stem_tband_create: output must be BF16 or F16");
+  ESF_CHECK_ARG(pT >= 0 && pT < kT && sH >= 1 && sH <= 8, "esf_stem_tband_create: bad temporal padding / H stride");
+  int pt_expected = 0, lpad = 0, win8 = 0;
+  int rc = esf_stem_geometry(W, Cin, kW, sW, pW, &pt_expected, &lpad, &win8);
+  if (rc != ESF_OK) return rc;
+  ESF_CHECK_ARG(pitch == pt_expected, "esf_stem_tband_create: pitch %d != esf_stem_geometry pitch %d", pitch, pt_expected);
+  const int To = T + 2 * pT - kT + 1;
+  const int Ho = (H + 2 * pH - kH) / sH + 1;
+  const int Wo = (W + 2 * pW - kW) / sW + 1;
+  ESF_CHECK_ARG(To >= 1 && y->B == B && y->T == To && y->H == Ho && y->W == Wo && y->C == Cout && y->sW == Cout,
+                "esf_stem_tband_create: output must be a dense (B,%d,%d,%d,%d) channels-last tensor", To, Ho, Wo, Cout);
+  const int WB = stem_tband_wb(Cin, Cout, kT, kH, kW, sW, Wo);
+  if (WB == 0) return set_error(ESF_ERR_UNSUPPORTED, "temporal-band stem does not apply to this geometry");
+  ESF_CHECK_ARG((reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && (y->sH * 2) % 16 == 0 && (y->sT * 2) % 16 == 0 &&
+                    (y->sB * 2) % 16 == 0, "esf_stem_tband_create: output rows must be 16-byte aligned");
+
+  StemTbOp* op = new (std::nothrow) StemTbOp();
+  if (!op) return set_error(ESF_ERR_ARG, "out of host memory");
+  StemTbParams& p = op->params;
+  memset(&p, 0, sizeof(p));
+  p.kT = kT, p.kH = kH, p.pT = pT, p.T = T, p.To = To, p.Ho = Ho, p.B = B;
+  p.NB = WB * Cout, p.nslots = kTmemCols / p.NB;
+  if (p.nslots > 32) p.nslots = 32;
+  p.ksteps = cdiv(((WB - 1) * sW + kW) * Cin, 16);
+  p.ncb = Wo / WB, p.a_cb_stride = WB * sW * Cin;
+  int bw = 1, bt = 1;
+  choose_box(1, Ho, 1, B, &bw, &p.bh, &bt, &p.bb);
+  p.th = cdiv(Ho, p.bh), p.tb = cdiv(B, p.bb), p.rows = p.bh * p.bb;
+  const long long ntiles = (long long)p.ncb * p.th * p.tb;
+  if (ntiles > 0x7fffffffLL) {
+    delete op;
+    return set_error(ESF_ERR_ARG, "too many tiles");
+  }
+  p.num_tiles = (int)ntiles;
+  p.a_bytes = p.rows * 128, p.b_tile_bytes = kT * p.NB * 128;
+  p.bias = bias_tiled, p.act = act, p.f16 = y->dtype == ESF_F16;
+  p.y = static_cast<__nv_bfloat16*>(y->ptr), p.ysB = y->sB, p.ysT = y->sT, p.ysH = y->sH;
+  p.stages = std::min(kTbMaxStages, (kSmemLimit - 1024 - 1024 - (int)(kH * p.b_tile_bytes)) / kAStageBytes);
+  op->smem_bytes = 1024 + 1024 + kH * p.b_tile_bytes + p.stages * kAStageBytes;
+  const CUtensorMapDataType dt16 = p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+
+  int phase_map[8];
+  for (int i = 0; i < 8; ++i) phase_map[i] = -1;
+  int nmaps = 0;
+  for (int ih = 0; ih < kH && rc == ESF_OK; ++ih) {
+    const int oh = ih - pH;
+    const int qh = floordiv(oh, sH);
+    const int ph = oh - qh * sH;
+    if (phase_map[ph] < 0) {
+      const int Hp = ph < H ? cdiv(H - ph, sH) : 0;
+      if (Hp <= 0) {
+        rc = set_error(ESF_ERR_UNSUPPORTED, "empty stride phase");
+        break;
+      }
+      char* base = static_cast<char*>(const_cast<void*>(xp)) + 2LL * ph * pitch;
+      rc = encode_act_map(&p.a_maps[nmaps], dt16, 2, base, pitch, 1, Hp, T, B, (int64_t)sH * pitch, (int64_t)sH * pitch,
+                          (int64_t)H * pitch, (int64_t)T * H * pitch, 64, 1, p.bh, 1, p.bb, CU_TENSOR_MAP_SWIZZLE_128B,
+                          "temporal-band stem activation");
+      phase_map[ph] = nmaps++;
+    }
+    p.a_map_of_kh[ih] = phase_map[ph], p.qh_of_kh[ih] = qh;
+  }
+  if (rc == ESF_OK)
+    for (int i = nmaps; i < kMaxAMaps; ++i) p.a_maps[i] = p.a_maps[0];
+  if (rc == ESF_OK) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) rc = set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    else {
+      const cuuint64_t K = (cuuint64_t)kH * 64;
+      cuuint64_t dims[2] = {K, (cuuint64_t)(kT * p.NB)};
+      cuuint64_t strides[1] = {K * 2};
+      cuuint32_t box[2] = {64, (cuuint32_t)(kT * p.NB)};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = enc(&p.b_map, dt16, 2, const_cast<void*>(w_band), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) rc = set_error(ESF_ERR_CUDA, "cuTensorMapEncodeTiled(temporal-band weights) failed with %d", (int)r);
+    }
+  }
+  if (rc == ESF_OK) {
+    const int sms = num_sms();
+    if (sms <= 0) rc = set_error(ESF_ERR_CUDA, "no CUDA device");
+    else {
+      op->grid = std::min(p.num_tiles, sms);
+      static unsigned char attr_done[kMaxDevices] = {0};
+      unsigned char* slot = device_slot(attr_done);
+      if (!slot || !*slot) {
+        cudaError_t e = cudaFuncSetAttribute(stem_tband_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        if (e != cudaSuccess) rc = set_error(ESF_ERR_CUDA, "cudaFuncSetAttribute(stem_tband) failed: %s", cudaGetErrorString(e));
+        else if (slot) *slot = 1;
+      }
+    }
+  }
+  if (rc != ESF_OK) {
+    delete op;
+    return rc;
+  }
+  *out = op;
+  return ESF_OK;
+}
+
 // ---- W-folded dense conv for thin layers (C_in <= 32) ------------------------------------------------------------
 // A (B,T,H,W,C) activation with C = 8..32 gives TMA rows of 16..64 bytes and MMA tiles of N = 8..32: both far below
 // what the hardware wants.  Folding a block of WB output columns into the GEMM's N and the ((WB-1)*sW + kW) input

@@ -9,6 +9,7 @@ Design (B200-first, not a module-by-module translation of the reference):
   * there is no PyTorch compute on the path -- torch only owns the memory and the stream.
 """
 import ctypes
+import os
 
 import torch
 
@@ -85,6 +86,23 @@ def pack_stem_band(w, bias, stride_w, device, dtype=torch.bfloat16):
     bt = torch.zeros(n_pad, dtype=torch.float64, device=w.device)
     bt[:N] = bias.repeat(STEM_WB)
     return to_device(band.reshape(n_pad, -1), device, dtype), to_device(bt, device, torch.float32)
+
+
+def pack_stem_tband(w, bias, WB, stride_w, device, dtype=torch.bfloat16):
+    """Folded (Cout,Cin,kT,kH,kW) stem weight -> band matrix [kT*NB][kH*64] and tiled bias FP32 [NB] of the temporal-band
+    stem (esf_stem_tband_create), NB = WB*Cout.  Row n = u*NB + i*Cout + co: u is the output frame relative to the oldest
+    frame an input frame touches, i.e. the weights of time tap kt = kT-1-u; i = output column inside the WB-wide block.
+    Column k = kh*64 + j, (w_in, c) = divmod(j, Cin) the j-th element of the input run the block reads, kw = w_in - sW*i."""
+    cout, cin, kt, kh, kw = w.shape
+    NB = WB * cout
+    assert ((WB - 1) * stride_w + kw) * cin <= 64
+    band = torch.zeros(kt, WB, cout, kh, 64, dtype=torch.float64, device=w.device)
+    wt = w.to(torch.float64).permute(2, 0, 3, 4, 1).reshape(kt, cout, kh, kw * cin)      # [kt][co][kh][(kw, c)]
+    for i in range(WB):
+        j0 = stride_w * i * cin
+        band[:, i, :, :, j0:j0 + kw * cin] = wt.flip(0)                                   # u = kT-1-kt
+    bt = bias.to(torch.float64).repeat(WB)
+    return to_device(band.reshape(kt * NB, kh * 64), device, dtype), to_device(bt, device, torch.float32)
 
 
 def pack_wfold_band(w, bias, WB, stride_w, device, dtype=torch.bfloat16):
@@ -523,13 +541,23 @@ class Plan:
         pitch, lpad, _ = geo
         L = rt.lib()
         xp = torch.empty((B, T, H, pitch), dtype=self.adt, device=self.device)
-        wb, bt = pack_stem_band(w_folded, bias, stride[2], self.device, self.adt)
-        self.keep += [xp, wb, bt]
         yv = rt.view(y)
         h = ctypes.c_void_p()
-        rt.check(L.esf_stem_igemm_create(xp.data_ptr(), B, Cin, T, H, W, pitch, wb.data_ptr(), bt.data_ptr(), cout,
-                                         kt, kh, kw, stride[1], stride[2], padding[0], padding[1], padding[2], act,
-                                         ctypes.byref(yv), ctypes.byref(h)), "esf_stem_igemm_create")
+        # kT > 1: the time taps are folded into N and the input frames stream past a resident M tile (csrc/esf_igemm.cu,
+        # "temporal-band stem"); ESF_STEM_TBAND=0 keeps the banded stem for A/B runs
+        twb = rt.stem_tband_wb(W, Cin, cout, kt, kh, kw, stride[2], padding[2]) \
+            if os.environ.get("ESF_STEM_TBAND", "0") != "0" else 0
+        if twb:
+            wb, bt = pack_stem_tband(w_folded, bias, twb, stride[2], self.device, self.adt)
+            rt.check(L.esf_stem_tband_create(xp.data_ptr(), B, Cin, T, H, W, pitch, wb.data_ptr(), bt.data_ptr(), cout,
+                                             kt, kh, kw, stride[1], stride[2], padding[0], padding[1], padding[2], act,
+                                             ctypes.byref(yv), ctypes.byref(h)), "esf_stem_tband_create")
+        else:
+            wb, bt = pack_stem_band(w_folded, bias, stride[2], self.device, self.adt)
+            rt.check(L.esf_stem_igemm_create(xp.data_ptr(), B, Cin, T, H, W, pitch, wb.data_ptr(), bt.data_ptr(), cout,
+                                             kt, kh, kw, stride[1], stride[2], padding[0], padding[1], padding[2], act,
+                                             ctypes.byref(yv), ctypes.byref(h)), "esf_stem_igemm_create")
+        self.keep += [xp, wb, bt]
         self.handles.append(h)
         m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
         self.stem_routes[x_nc.data_ptr()] = (xp, pitch, lpad)   # the uint8 frame route writes xp itself (frames.py)
@@ -546,7 +574,7 @@ class Plan:
         self._add(pack, "stem_pack", "", nbytes=self._nbytes(x_nc, xp), eager=True)
         self.meta[-1]["is_pack"] = True
         self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "stem_igemm",
-                  "%dx%dx%d %d->%d banded" % (kt, kh, kw, Cin, cout), flops=2.0 * m * cout * Cin * kt * kh * kw,
+                  "%dx%dx%d %d->%d %s" % (kt, kh, kw, Cin, cout, "t-band" if twb else "banded"), flops=2.0 * m * cout * Cin * kt * kh * kw,
                   nbytes=self._nbytes(xp, y) + wb.numel() * 2)
 
     def pool(self, x, y, kernel, stride, padding, is_avg=False, act=rt.ACT_NONE):

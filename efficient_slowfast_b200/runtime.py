@@ -89,6 +89,8 @@ def lib():
     L.esf_frames_to_clip.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, P(i32), vp, vp, vp]
     L.esf_stem_igemm_create.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32,
                                         i32, i32, i32, P(EsfView), P(vp)]
+    L.esf_stem_tband_create.argtypes = L.esf_stem_igemm_create.argtypes
+    L.esf_stem_tband_wb.argtypes = [i32] * 8
     L.esf_pool3d.argtypes = [P(EsfView), P(EsfView), i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     L.esf_shuffle_concat.argtypes = [P(EsfView), P(EsfView), i32, P(EsfView), vp]
     L.esf_eltwise_add.argtypes = [P(EsfView), P(EsfView), P(EsfView), i32, vp]
@@ -121,7 +123,7 @@ def lib():
     L.esf_p32_eca_fuse.argtypes = [P(EsfView), i32, vp, i32, vp, vp, vp, P(EsfView), vp]
     L.esf_p32_head_pool.argtypes = [P(EsfView), vp, i32, i32, vp]
     L.esf_p32_attention.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, i32, P(EsfView), vp]
-    for name in ("esf_p32_post3", "esf_stem_pack_lo", "esf_attn_tc_pack_vlo", "esf_attn_tc_create_split", "esf_p32_row_softmax", "esf_p32_attention", "esf_p32_post", "esf_p32_pool3d", "esf_p32_eca_fuse", "esf_p32_head_pool", "esf_stem_pack_gather", "esf_dwconv_padded", "esf_pointwise_padded", "esf_global_mean", "esf_gemm_clip_weights_create", "esf_group_mean", "esf_row_softmax", "esf_transpose16", "esf_stem_pack_u8", "esf_frames_to_clip", "esf_attn_generic", "esf_shuffle_concat", "esf_eltwise_add", "esf_channel_scale", "esf_attn_tc_pack", "esf_attn_tc_create", "esf_stem_geometry", "esf_stem_pack", "esf_stem_igemm_create", "esf_igemm_geometry",
+    for name in ("esf_stem_tband_create", "esf_stem_tband_wb", "esf_p32_post3", "esf_stem_pack_lo", "esf_attn_tc_pack_vlo", "esf_attn_tc_create_split", "esf_p32_row_softmax", "esf_p32_attention", "esf_p32_post", "esf_p32_pool3d", "esf_p32_eca_fuse", "esf_p32_head_pool", "esf_stem_pack_gather", "esf_dwconv_padded", "esf_pointwise_padded", "esf_global_mean", "esf_gemm_clip_weights_create", "esf_group_mean", "esf_row_softmax", "esf_transpose16", "esf_stem_pack_u8", "esf_frames_to_clip", "esf_attn_generic", "esf_shuffle_concat", "esf_eltwise_add", "esf_channel_scale", "esf_attn_tc_pack", "esf_attn_tc_create", "esf_stem_geometry", "esf_stem_pack", "esf_stem_igemm_create", "esf_igemm_geometry",
                  "esf_conv_igemm_create", "esf_conv_wfold_create", "esf_op_launch", "esf_conv_direct", "esf_stem_conv",
                  "esf_pool3d", "esf_eca_fuse", "esf_attn_pack", "esf_attn_fused", "esf_head_pool", "esf_head_fc"):
         getattr(L, name).restype = ctypes.c_int
@@ -169,6 +171,12 @@ def stem_geometry(W, cin, kW, sW, pW):
     if rc != 0 or ((W + 2 * pW - kW) // sW + 1) % 8 != 0:
         return None
     return pitch.value, lpad.value, win.value
+
+
+def stem_tband_wb(W, cin, cout, kT, kH, kW, sW, pW):
+    """Output-column block of the temporal-band stem kernel (esf_stem_tband_create) for this geometry, 0 when it does not
+    apply and the banded stem of esf_stem_igemm_create runs instead."""
+    return int(lib().esf_stem_tband_wb(W, cin, cout, kT, kH, kW, sW, pW))
 
 
 def current_stream_ptr():

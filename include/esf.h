@@ -146,6 +146,17 @@ int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int32_t T, int
                           const void* w_band, const float* bias_tiled, int32_t Cout, int32_t kT, int32_t kH,
                           int32_t kW, int32_t sH, int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t act,
                           const esf_view* y, esf_op** out);
+/* Temporal-band stem for kT > 1 (the fast pathway's 5x7x7 stem, stem_helper.py:138-178 with cfg.SLOWFAST.BETA_INV):
+ * same operands and packed clip as esf_stem_igemm_create, but the kT time taps are folded into the GEMM's N and the
+ * input frames stream past an M tile that stays on its SM (output frames accumulate in a ring of TMEM slots).
+ * esf_stem_tband_wb: width WB of the output-column block for this geometry, 0 when the kernel does not apply (kT = 1,
+ * window or N too large).  w_band: 16-bit [kT*WB*Cout][kH*64], bias_tiled: FP32 [WB*Cout] (engine.pack_stem_tband).
+ * 16-bit dense output only. */
+int esf_stem_tband_wb(int32_t W, int32_t Cin, int32_t Cout, int32_t kT, int32_t kH, int32_t kW, int32_t sW, int32_t pW);
+int esf_stem_tband_create(const void* xp, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
+                          const void* w_band, const float* bias_tiled, int32_t Cout, int32_t kT, int32_t kH,
+                          int32_t kW, int32_t sH, int32_t sW, int32_t pT, int32_t pH, int32_t pW, int32_t act,
+                          const esf_view* y, esf_op** out);
 
 /* ---- MaxPool3d / AvgPool3d on channels-last BF16 (padding: -inf for max, zeros counted for avg) ---------
  * replaces ResNetBasicStem.pool_layer (stem_helper.py:169-171), the 3x3x3 stem pools

@@ -374,6 +374,7 @@ def test_stem_banded_gemm(esf_lib, kt, cout, k, size, precision, thalo, monkeypa
     if thalo and kt == 1:
         pytest.skip("no temporal taps")
     monkeypatch.setenv("ESF_STEM_THALO", str(thalo))
+    monkeypatch.setenv("ESF_STEM_TBAND", "0")     # the temporal-band kernel has its own test below
     adt = rt.TORCH_DTYPE[precision]
     g = torch.Generator().manual_seed(kt + cout)
     B, T = (2, 8) if size < 200 else (1, 2)
@@ -395,6 +396,69 @@ def test_stem_banded_gemm(esf_lib, kt, cout, k, size, precision, thalo, monkeypa
     if not err <= 1e-2 * ref.abs().max().item():
         _diagnose("stem_banded", got, ref, 1e-2 * ref.abs().max().item())
     assert err <= 1e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("B,cin,T,size,kt,cout", [
+    (2, 3, 8, 64, 5, 8),       # the fast stem's geometry, one wave
+    (3, 3, 21, 48, 5, 8),      # more frames than TMEM slots (ring re-use), odd batch (clipped box)
+    (2, 3, 2, 64, 5, 8),       # fewer frames than time taps
+    (1, 3, 1, 64, 5, 8),       # one frame: every slot is opened and published in the same step
+    (2, 1, 6, 64, 5, 8),       # grey-scale clip (one 16-element K step)
+    (2, 3, 6, 64, 3, 16),      # kT = 3, 64-column slots (8 slots)
+    (2, 3, 5, 64, 5, 4),       # 16-column slots (32 slots)
+    (8, 3, 4, 224, 5, 8),      # 196 tiles on 148 SMs: slots and stages carried from one tile into the next
+])
+def test_stem_temporal_band(esf_lib, B, cin, T, size, kt, cout, precision, monkeypatch):
+    """stem_tband_kernel (time taps folded into N, input frames streaming past a resident M tile, output frames in a ring
+    of TMEM slots) vs F.conv3d on the 16-bit-rounded clip and weights, and bit-identical to nothing less than itself on a
+    second launch (the barriers' phases must survive re-launching the same op)."""
+    monkeypatch.setenv("ESF_STEM_TBAND", "1")
+    adt = rt.TORCH_DTYPE[precision]
+    g = torch.Generator().manual_seed(B + T + cout)
+    x = torch.randn(B, cin, T, size, size, generator=g)
+    kk = (kt, 7, 7)
+    w = torch.randn(cout, cin, *kk, generator=g) * 0.1
+    bias = torch.randn(cout, generator=g) * 0.1
+    pad = (kt // 2, 3, 3)
+    assert rt.stem_tband_wb(size, cin, cout, kt, 7, 7, 2, 3) == 4
+    ref = F.conv3d(x.to(adt).float(), w.to(adt).float(), bias, (1, 2, 2), pad).relu()
+    y = torch.full(_to_ndhwc(ref).shape, 7.0, dtype=adt, device=DEV)
+    plan = Plan(DEV, precision)
+    xd = x.to(DEV)
+    plan.stem(xd, y, w.double(), bias.double(), (1, 2, 2), pad)
+    assert plan.meta[-1]["kind"] == "stem_igemm" and plan.meta[-1]["label"].endswith("t-band")
+    plan.launch_all()
+    torch.cuda.synchronize()
+    got = _to_ncdhw(y.cpu())
+    tol = 1e-2 * ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    if not err <= tol:
+        _diagnose("stem_tband", got, ref, tol)
+    assert err <= tol
+    y.fill_(7.0)
+    plan.launch_all()
+    torch.cuda.synchronize()
+    assert torch.equal(_to_ncdhw(y.cpu()), got)
+
+
+def test_stem_temporal_band_matches_banded_stem(esf_lib, monkeypatch):
+    """Both tensor-core stems accumulate the same FP16 products in FP32: their outputs may differ only by the order of
+    the additions (one 16-bit ulp at most after rounding)."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 8, 64, 64, generator=g)
+    w = torch.randn(8, 3, 5, 7, 7, generator=g) * 0.1
+    bias = torch.randn(8, generator=g) * 0.1
+    outs = []
+    for tband in ("1", "0"):
+        monkeypatch.setenv("ESF_STEM_TBAND", tband)
+        y = torch.empty(2, 8, 32, 32, 8, dtype=torch.float16, device=DEV)
+        plan = Plan(DEV, "fp16")
+        plan.stem(x.to(DEV), y, w.double(), bias.double(), (1, 2, 2), (2, 3, 3))
+        plan.launch_all()
+        torch.cuda.synchronize()
+        outs.append(y.float().cpu())
+    assert (outs[0] - outs[1]).abs().max().item() <= 2 ** -10 * outs[1].abs().max().item()
 
 
 @pytest.mark.parametrize("C", [64, 8, 6])

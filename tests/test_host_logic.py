@@ -121,6 +121,57 @@ def test_pack_wfold_band_is_the_convolution(esf_lib, cin, cout, k, s, WB):
     assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4)
 
 
+def _tband_reference(x_cl, band, bias_t, cout, k, s, pad, WB, nslots):
+    """CPU model of stem_tband_kernel's schedule: input frames in order, one GEMM per (g, kh) against the weights of all
+    time taps, output frames accumulating in a ring of nslots slots (first touch overwrites, last touch publishes)."""
+    B, T, H, W, C = x_cl.shape
+    kt, kh, kw = k
+    sH, sW = s
+    pT, pH, pW = pad
+    To, Ho, Wo = T + 2 * pT - kt + 1, (H + 2 * pH - kh) // sH + 1, (W + 2 * pW - kw) // sW + 1
+    NB = WB * cout
+    xp = F.pad(x_cl.double(), (0, 0, pW, pW + 64, pH, pH + sH))           # zero rows / columns the TMA box would fill
+    band = band.double().reshape(kt * NB, kh, 64)
+    out = torch.full((B, To, Ho, Wo, cout), float("nan"), dtype=torch.float64)
+    for cb in range(Wo // WB):
+        w0 = cb * WB * sW
+        slots = torch.full((nslots, B, Ho, NB), float("nan"), dtype=torch.float64)
+        for g in range(T):
+            t_base = g + pT - kt + 1
+            t_lo, t_hi = max(t_base, 0), min(g + pT, To - 1)
+            new_lo = 0 if g == 0 else g + pT
+            for ih in range(kh):
+                rows = xp[:, g, ih:ih + sH * Ho:sH, w0:w0 + 64 // C + 2].reshape(B, Ho, -1)[:, :, :64]
+                for t in range(t_lo, t_hi + 1):
+                    u = t - t_base
+                    d = rows @ band[u * NB:(u + 1) * NB, ih].T
+                    if ih == 0 and t >= new_lo:
+                        slots[t % nslots] = d
+                    else:
+                        slots[t % nslots] += d
+            for t in range(t_lo, t_hi + 1):
+                if g == min(t + kt - 1 - pT, T - 1):
+                    out[:, t, :, cb * WB:(cb + 1) * WB] = (slots[t % nslots] + bias_t.double()).reshape(B, Ho, WB, cout)
+                    slots[t % nslots] = float("nan")
+    return out
+
+
+@pytest.mark.parametrize("cin,cout,k,s,WB,T", [(3, 8, (5, 7, 7), (2, 2), 4, 11), (1, 8, (5, 7, 7), (2, 2), 4, 6),
+                                               (3, 4, (3, 3, 3), (1, 1), 4, 7), (3, 8, (5, 7, 7), (2, 2), 4, 2)])
+def test_pack_stem_tband_is_the_convolution(esf_lib, cin, cout, k, s, WB, T):
+    g = torch.Generator().manual_seed(cin + cout + T)
+    pad = (k[0] // 2, k[1] // 2, k[2] // 2)
+    x = torch.randn(2, T, 10, 8 * s[1], cin, generator=g)
+    w = torch.randn(cout, cin, *k, generator=g).double()
+    b = torch.randn(cout, generator=g).double()
+    band, bt = engine.pack_stem_tband(w, b, WB, s[1], "cpu", torch.float32)
+    assert band.shape == (k[0] * WB * cout, k[1] * 64) and bt.shape == (WB * cout,)
+    ref = F.conv3d(x.permute(0, 4, 1, 2, 3).double(), w, b, (1, s[0], s[1]), pad).permute(0, 2, 3, 4, 1)
+    got = _tband_reference(x, band, bt, cout, k, s, pad, WB, nslots=4 if k[0] == 3 else 8)
+    assert got.shape == ref.shape and not torch.isnan(got).any()
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4)
+
+
 def test_wfold_block_planner():
     def views(B, T, H, W, cin, cout, slice_out=False):
         x = torch.empty(B, T, H, W, cin)
