@@ -1107,6 +1107,9 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
 constexpr int kTbThreads = 6 * 32;   // TMA producer, MMA issuer, 4 epilogue warps (one per TMEM lane quarter)
 constexpr int kTbMaxKH = 8;
 constexpr int kTbMaxStages = 8;
+// Timing experiments are compile-time instantiations (template parameter DBG; bits: 1 no MMAs, 2 no tile loads, 4 no
+// epilogue work, 16 every MMA N = NB, 32 one k-step per tap (wrong results)), built only with ESF_NVCC_EXTRA=-DESF_TB_DBG_VARIANTS and
+// selected by ESF_STEM_TBAND_DBG.  Run-time switches in these loops are not free.
 
 struct __align__(64) StemTbParams {
   CUtensorMap a_maps[kMaxAMaps];   // one per row phase of the H stride
@@ -1116,6 +1119,8 @@ struct __align__(64) StemTbParams {
   int T, To, Ho, B;
   int bh, bb, th, tb, ncb, rows;
   int a_cb_stride;   // elements between the windows of consecutive column blocks
+  int odd_shift;     // 1: the tile of an odd column block is loaded 16 B early (its rows then start on a 32 B sector) and
+                     // its MMAs read from start address + 16 B
   int ksteps;        // 16-element K steps per tap
   int NB, nslots;    // columns per output-frame slot, slots in the ring (power of two)
   int stages;
@@ -1127,6 +1132,14 @@ struct __align__(64) StemTbParams {
   int num_tiles;
 };
 
+// one k-step of a tap: the frames of segment 0 and, when the slot ring wraps inside the window, of segment 1
+#define ESF_TB_KSTEP(ks)                                                                              \
+  {                                                                                                   \
+    umma_bf16_lohi(sd0, a_lo + 2 * (ks), desc_hi, b0 + 2 * (ks), desc_hi, si0, 1);                     \
+    if (c1 > 0) umma_bf16_lohi(tmem_base, a_lo + 2 * (ks), desc_hi, b1 + 2 * (ks), desc_hi, si1, 1);   \
+  }
+
+template <int KSTEPS, bool F16, int ESF_TB_DBG = 0>
 __global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_constant__ StemTbParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1139,6 +1152,7 @@ __global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_
   uint64_t* acc_free = acc_full + 32;
   uint64_t* b_full = acc_free + 32;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  float* bias_sh = reinterpret_cast<float*>(bars) + 256;   // [NB <= 64], 1 KB into the 2 KB barrier / bias area
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -1156,6 +1170,7 @@ __global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + p.NB) bias_sh[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.b_map);
     prefetch_tmap(&p.a_maps[0]);
@@ -1177,21 +1192,26 @@ __global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_
       for (int kh = 0; kh < p.kH; ++kh) tma_load_2d(smem_b + kh * p.b_tile_bytes, &p.b_map, b_full, kh * 64, 0);
     }
     __syncwarp();
+    const int kH = p.kH, T = p.T, stages = p.stages;
+    const uint32_t a_bytes = p.a_bytes;
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int cb = tile % p.ncb, m = tile / p.ncb;
-      const int h0 = (m % p.th) * p.bh, b0 = (m / p.th) * p.bb;
-      for (int g = 0; g < p.T; ++g)
-        for (int kh = 0; kh < p.kH; ++kh) {
+      const int h0 = (m % p.th) * p.bh, b0 = (m / p.th) * p.bb, c0 = cb * p.a_cb_stride - ((cb & p.odd_shift) ? 8 : 0);
+      for (int g = 0; g < T; ++g)
+        for (int kh = 0; kh < kH; ++kh) {
           mbar_wait(&a_empty[stage], phase ^ 1, 51);
           if (elect_one()) {
-            mbar_arrive_expect_tx(&a_full[stage], p.a_bytes);
-            tma_load_5d(smem_a + stage * kAStageBytes, &p.a_maps[p.a_map_of_kh[kh]], &a_full[stage], cb * p.a_cb_stride,
-                        0, h0 + p.qh_of_kh[kh], g, b0);
+            if (ESF_TB_DBG & 2) mbar_arrive(&a_full[stage]);
+            else {
+              mbar_arrive_expect_tx(&a_full[stage], a_bytes);
+              tma_load_5d(smem_a + stage * kAStageBytes, &p.a_maps[p.a_map_of_kh[kh]], &a_full[stage], c0, 0,
+                          h0 + p.qh_of_kh[kh], g, b0);
+            }
           }
           __syncwarp();
-          if (++stage == p.stages) {
+          if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -1199,61 +1219,94 @@ __global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc0 = make_idesc_16(128, 0, p.f16);
+    // The issuing thread is a serial instruction stream and a tap is only three or four MMAs: everything that depends
+    // on the input frame alone -- D column, weight-row offset and instruction descriptor of each segment -- is computed
+    // once per frame, the first tap of a frame (whose first k-step opens the new slot) is peeled off the tap loop, and
+    // the k-step count is a template parameter.
+    const uint32_t idesc0 = make_idesc_16(128, 0, F16);
     const uint32_t desc_hi = kmajor_desc_hi(1024, 2);
     const uint32_t a_lo0 = kmajor_desc_lo(smem_u32(smem_a)), b_lo0 = kmajor_desc_lo(smem_u32(smem_b));
     const uint32_t b_kh_step = p.b_tile_bytes >> 4, b_u_step = (uint32_t)(p.NB * 128) >> 4;
-    const int back = p.kT - 1 - p.pT;   // output frame t is complete after input frame min(t + back, T - 1)
+    const int kT = p.kT, kH = p.kH, pT = p.pT, T = p.T, To = p.To, NB = p.NB, nslots = p.nslots;
+    const int stages = p.stages, num_tiles = p.num_tiles;
+    const int back = kT - 1 - pT;   // output frame t is complete after input frame min(t + back, T - 1)
     mbar_wait(b_full, 0, 52);
     tc_fence_after();
     int stage = 0;
     uint32_t phase = 0, free_bits = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      for (int g = 0; g < p.T; ++g) {
-        const int t_base = g + p.pT - p.kT + 1;
-        const int t_lo = max(t_base, 0), t_hi = min(g + p.pT, p.To - 1);
-        const int new_lo = g == 0 ? 0 : g + p.pT;     // frames >= new_lo are written for the first time in this step
+    const int ncb = p.ncb, odd_shift = p.odd_shift;
+    uint32_t a_rel = 0;    // stage * 1024: position of the current stage in the ring, in 16 B units
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const uint32_t a_base = a_lo0 + (((tile % ncb) & odd_shift) ? 1u : 0u);
+      for (int g = 0; g < T; ++g) {
+        const int t_base = g + pT - kT + 1;
+        const int t_lo = max(t_base, 0), t_hi = min(g + pT, To - 1);
+        const int new_lo = g == 0 ? 0 : g + pT;     // frames >= new_lo are written for the first time in this step
         for (int t = max(new_lo, t_lo); t <= t_hi; ++t) {   // their slots must have been drained by the epilogue
           const int s = t & smask;
           mbar_wait(&acc_free[s], ((free_bits >> s) & 1) ^ 1, 53);
           free_bits ^= 1u << s;
         }
         tc_fence_after();
-        for (int kh = 0; kh < p.kH; ++kh) {
+        // segment = frames [a, a + n) in consecutive slots: (D address, weight-row offset in 16 B units, idesc)
+        auto seg_d = [&](int a) { return tmem_base + (uint32_t)((a & smask) * NB); };
+        auto seg_b = [&](int a) { return (uint32_t)(a - t_base) * b_u_step; };
+        auto seg_i = [&](int n) { return idesc0 | ((uint32_t)((((ESF_TB_DBG & 16) ? min(n, 1) : n) * NB) >> 3) << 17); };
+        // steady k-steps: [t_lo, t_hi], split where the slot ring wraps
+        const int cnt = t_hi - t_lo + 1;
+        const int c0 = min(cnt, nslots - (t_lo & smask)), c1 = cnt - c0;
+        const uint32_t sd0 = seg_d(t_lo), sb0 = seg_b(t_lo), si0 = seg_i(c0);
+        const uint32_t sb1 = seg_b(t_lo + c0), si1 = seg_i(c1);
+        // first k-step of the frame: the frames below new_lo accumulate (same split), the new ones overwrite; the new
+        // frames never straddle the wrap (frames 0 .. pT at g = 0, a single frame otherwise)
+        const int old_cnt = max(min(new_lo - 1, t_hi) - t_lo + 1, 0);
+        const int o0 = min(old_cnt, c0), o1 = old_cnt - o0;
+        const int nw_lo = max(new_lo, t_lo), nw_cnt = t_hi - nw_lo + 1;
+        const uint32_t oi0 = seg_i(o0), oi1 = seg_i(o1);
+        const uint32_t nd = seg_d(nw_lo), nb = seg_b(nw_lo), ni = seg_i(nw_cnt);
+        // frames completed by this input frame: t = g - back (and everything still open at the last input frame)
+        const int done_lo = max(g == T - 1 ? t_lo : g - back, 0), done_hi = g == T - 1 ? t_hi : g - back;
+        uint32_t b0 = b_lo0 + sb0, b1 = b_lo0 + sb1;
+        // ---- tap kh = 0
+        uint32_t a_lo = a_base + a_rel;
+        mbar_wait(&a_full[stage], phase, 54);
+        tc_fence_after();
+        if (elect_one()) {
+          if (!(ESF_TB_DBG & 1)) {
+            if (o0 > 0) umma_bf16_lohi(sd0, a_lo, desc_hi, b0, desc_hi, oi0, 1);
+            if (o1 > 0) umma_bf16_lohi(tmem_base, a_lo, desc_hi, b1, desc_hi, oi1, 1);
+            if (nw_cnt > 0) umma_bf16_lohi(nd, a_lo, desc_hi, b_lo0 + nb, desc_hi, ni, 0);
+            if (KSTEPS > 1 && !(ESF_TB_DBG & 32)) ESF_TB_KSTEP(1)
+            if (KSTEPS > 2 && !(ESF_TB_DBG & 32)) ESF_TB_KSTEP(2)
+            if (KSTEPS > 3 && !(ESF_TB_DBG & 32)) ESF_TB_KSTEP(3)
+          }
+          umma_commit(&a_empty[stage]);
+          if (kH == 1)
+            for (int t = done_lo; t <= done_hi; ++t) umma_commit(&acc_full[t & smask]);
+        }
+        __syncwarp();
+        a_rel += kAStageBytes >> 4;
+        if (++stage == stages) stage = 0, phase ^= 1, a_rel = 0;
+        // ---- taps kh = 1 .. kH - 1
+        for (int kh = 1; kh < kH; ++kh) {
+          b0 += b_kh_step, b1 += b_kh_step;
+          a_lo = a_base + a_rel;
           mbar_wait(&a_full[stage], phase, 54);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t a_lo = a_lo0 + stage * (kAStageBytes >> 4);
-            const uint32_t b_lo = b_lo0 + kh * b_kh_step;
-            // frames [a, b] with one accumulate flag, split where the slot ring wraps
-            auto emit = [&](int a, int b, int ks, uint32_t acc) {
-              if (a > b) return;
-              const int sa = a & smask;
-              const int n1 = min(b - a + 1, p.nslots - sa);
-              umma_bf16_lohi(tmem_base + sa * p.NB, a_lo + 2 * ks, desc_hi, b_lo + (a - t_base) * b_u_step + 2 * ks, desc_hi,
-                             idesc0 | ((uint32_t)((n1 * p.NB) >> 3) << 17), acc);
-              if (n1 < b - a + 1)
-                umma_bf16_lohi(tmem_base, a_lo + 2 * ks, desc_hi, b_lo + (a + n1 - t_base) * b_u_step + 2 * ks, desc_hi,
-                               idesc0 | ((uint32_t)(((b - a + 1 - n1) * p.NB) >> 3) << 17), acc);
-            };
-            for (int ks = 0; ks < p.ksteps; ++ks) {
-              if (kh == 0 && ks == 0) {
-                emit(t_lo, min(new_lo - 1, t_hi), ks, 1);
-                emit(max(new_lo, t_lo), t_hi, ks, 0);
-              } else {
-                emit(t_lo, t_hi, ks, 1);
-              }
+            if (!(ESF_TB_DBG & 1)) {
+              ESF_TB_KSTEP(0)
+              if (KSTEPS > 1 && !(ESF_TB_DBG & 32)) ESF_TB_KSTEP(1)
+              if (KSTEPS > 2 && !(ESF_TB_DBG & 32)) ESF_TB_KSTEP(2)
+              if (KSTEPS > 3 && !(ESF_TB_DBG & 32)) ESF_TB_KSTEP(3)
             }
             umma_commit(&a_empty[stage]);
-            if (kh == p.kH - 1)
-              for (int t = t_lo; t <= t_hi; ++t)
-                if (g == min(t + back, p.T - 1)) umma_commit(&acc_full[t & smask]);
+            if (kh == kH - 1)
+              for (int t = done_lo; t <= done_hi; ++t) umma_commit(&acc_full[t & smask]);
           }
           __syncwarp();
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          a_rel += kAStageBytes >> 4;
+          if (++stage == stages) stage = 0, phase ^= 1, a_rel = 0;
         }
       }
     }
@@ -1262,31 +1315,36 @@ __global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int NB = p.NB, To = p.To, act = p.act;
+    const long long ysT = p.ysT;
     uint32_t full_bits = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int cb = tile % p.ncb, m = tile / p.ncb;
       const int ho = (m % p.th) * p.bh + r % p.bh, b = (m / p.th) * p.bb + r / p.bh;
       const bool valid = r < p.rows && ho < p.Ho && b < p.B;
-      __nv_bfloat16* yrow = p.y + b * p.ysB + ho * p.ysH + (long long)cb * p.NB;
-      for (int t = 0; t < p.To; ++t) {
+      __nv_bfloat16* yrow = p.y + b * p.ysB + ho * p.ysH + (long long)cb * NB;
+      for (int t = 0; t < To; ++t, yrow += ysT) {
         const int s = t & smask;
         mbar_wait(&acc_full[s], (full_bits >> s) & 1, 55);
         full_bits ^= 1u << s;
         tc_fence_after();
-        for (int c0 = 0; c0 < p.NB; c0 += 16) {
-          float v[16];
-          tmem_ld16(lane_addr + s * p.NB + c0, v);
-          if (valid) {
-            uint32_t pk[8];
+        if (!(ESF_TB_DBG & 4))
+          for (int c0 = 0; c0 < NB; c0 += 16) {
+            float v[16];
+            tmem_ld16(lane_addr + s * NB + c0, v);
+            if (valid) {
+              uint32_t pk[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              pk[i] = pack16x2(apply_act(v[2 * i] + __ldg(p.bias + c0 + 2 * i), p.act),
-                               apply_act(v[2 * i + 1] + __ldg(p.bias + c0 + 2 * i + 1), p.act), p.f16);
-            uint4* dst = reinterpret_cast<uint4*>(yrow + t * p.ysT + c0);
-            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              for (int i = 0; i < 4; ++i) {       // the bias vector comes from shared memory, four columns per load
+                const float4 bv = *reinterpret_cast<const float4*>(bias_sh + c0 + 4 * i);
+                pk[2 * i] = pack16x2(apply_act(v[4 * i] + bv.x, act), apply_act(v[4 * i + 1] + bv.y, act), F16);
+                pk[2 * i + 1] = pack16x2(apply_act(v[4 * i + 2] + bv.z, act), apply_act(v[4 * i + 3] + bv.w, act), F16);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
+              dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
           }
-        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_free[s]);
@@ -1302,12 +1360,42 @@ __global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_
   }
 }
 
+using StemTbKernel = void (*)(const StemTbParams);
+static StemTbKernel stem_tband_fn(int ksteps, bool f16) {
+#ifdef ESF_TB_DBG_VARIANTS
+  if (const char* env = getenv("ESF_STEM_TBAND_DBG")) {
+    switch (atoi(env)) {
+      case 1: return stem_tband_kernel<3, true, 1>;
+      case 2: return stem_tband_kernel<3, true, 2>;
+      case 3: return stem_tband_kernel<3, true, 3>;
+      case 4: return stem_tband_kernel<3, true, 4>;
+      case 5: return stem_tband_kernel<3, true, 5>;
+      case 6: return stem_tband_kernel<3, true, 6>;
+      case 7: return stem_tband_kernel<3, true, 7>;
+      case 22: return stem_tband_kernel<3, true, 22>;
+      case 38: return stem_tband_kernel<3, true, 38>;
+      default: break;
+    }
+  }
+#endif
+  switch (ksteps * 2 + (f16 ? 1 : 0)) {
+    case 2: return stem_tband_kernel<1, false>;
+    case 3: return stem_tband_kernel<1, true>;
+    case 4: return stem_tband_kernel<2, false>;
+    case 5: return stem_tband_kernel<2, true>;
+    case 6: return stem_tband_kernel<3, false>;
+    case 7: return stem_tband_kernel<3, true>;
+    case 8: return stem_tband_kernel<4, false>;
+    default: return stem_tband_kernel<4, true>;
+  }
+}
+
 struct StemTbOp : esf_op {
   StemTbParams params;
   int grid = 0;
   int smem_bytes = 0;
   int launch(cudaStream_t stream) override {
-    stem_tband_kernel<<<grid, kTbThreads, smem_bytes, stream>>>(params);
+    stem_tband_fn(params.ksteps, params.f16 != 0)<<<grid, kTbThreads, smem_bytes, stream>>>(params);
     return check_launch("stem_tband_kernel");
   }
 };
@@ -1323,7 +1411,7 @@ static int stem_tband_wb(int Cin, int Cout, int kT, int kH, int kW, int sW, int 
     if (NB != 16 && NB != 32 && NB != 64) continue;
     if (kT * NB > 256 || kTmemCols / NB < kT + 1) continue;
     const int b_bytes = kH * kT * NB * 128;
-    if ((kSmemLimit - 1024 - 1024 - b_bytes) / kAStageBytes < 3) continue;
+    if ((kSmemLimit - 1024 - 2048 - b_bytes) / kAStageBytes < 3) continue;
     return WB;
   }
   return 0;
@@ -1363,8 +1451,14 @@ extern "C" int esf_stem_tband_create(const void* xp, int32_t B, int32_t Cin, int
   p.kT = kT, p.kH = kH, p.pT = pT, p.T = T, p.To = To, p.Ho = Ho, p.B = B;
   p.NB = WB * Cout, p.nslots = kTmemCols / p.NB;
   if (p.nslots > 32) p.nslots = 32;
-  p.ksteps = cdiv(((WB - 1) * sW + kW) * Cin, 16);
+  const int win = ((WB - 1) * sW + kW) * Cin;
+  p.ksteps = cdiv(win, 16);
   p.ncb = Wo / WB, p.a_cb_stride = WB * sW * Cin;
+  // TMA fetches rows that start in the middle of a 32 B sector at about 2/3 of the rate (measured: tile loads alone 0.59
+  // -> 0.41 ms).  With Cin = 3 the blocks are 48 B apart, so every odd block is loaded 16 B early when the widened
+  // window still fits the same number of k-steps (ESF_STEM_TBAND_SHIFT=0: off, for A/B runs)
+  p.odd_shift = ((p.a_cb_stride * 2) % 32 == 16 && win + 8 <= p.ksteps * 16) ? 1 : 0;
+  if (const char* env = getenv("ESF_STEM_TBAND_SHIFT")) p.odd_shift = p.odd_shift && atoi(env) != 0;
   int bw = 1, bt = 1;
   choose_box(1, Ho, 1, B, &bw, &p.bh, &bt, &p.bb);
   p.th = cdiv(Ho, p.bh), p.tb = cdiv(B, p.bb), p.rows = p.bh * p.bb;
@@ -1377,8 +1471,12 @@ extern "C" int esf_stem_tband_create(const void* xp, int32_t B, int32_t Cin, int
   p.a_bytes = p.rows * 128, p.b_tile_bytes = kT * p.NB * 128;
   p.bias = bias_tiled, p.act = act, p.f16 = y->dtype == ESF_F16;
   p.y = static_cast<__nv_bfloat16*>(y->ptr), p.ysB = y->sB, p.ysT = y->sT, p.ysH = y->sH;
-  p.stages = std::min(kTbMaxStages, (kSmemLimit - 1024 - 1024 - (int)(kH * p.b_tile_bytes)) / kAStageBytes);
-  op->smem_bytes = 1024 + 1024 + kH * p.b_tile_bytes + p.stages * kAStageBytes;
+  p.stages = std::min(kTbMaxStages, (kSmemLimit - 1024 - 2048 - (int)(kH * p.b_tile_bytes)) / kAStageBytes);
+  op->smem_bytes = 1024 + 2048 + kH * p.b_tile_bytes + p.stages * kAStageBytes;   // alignment slack, barriers + bias
+  {
+    const char* env = getenv("ESF_STEM_TBAND_STAGES");   // experiments: fewer activation stages
+    if (env && atoi(env) >= 2) p.stages = std::min(p.stages, atoi(env));
+  }
   const CUtensorMapDataType dt16 = p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 
   int phase_map[8];
@@ -1426,9 +1524,12 @@ extern "C" int esf_stem_tband_create(const void* xp, int32_t B, int32_t Cin, int
       static unsigned char attr_done[kMaxDevices] = {0};
       unsigned char* slot = device_slot(attr_done);
       if (!slot || !*slot) {
-        cudaError_t e = cudaFuncSetAttribute(stem_tband_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        if (e != cudaSuccess) rc = set_error(ESF_ERR_CUDA, "cudaFuncSetAttribute(stem_tband) failed: %s", cudaGetErrorString(e));
-        else if (slot) *slot = 1;
+        for (int ks = 1; ks <= 4 && rc == ESF_OK; ++ks)
+          for (int f = 0; f < 2 && rc == ESF_OK; ++f) {
+            cudaError_t e = cudaFuncSetAttribute(stem_tband_fn(ks, f != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+            if (e != cudaSuccess) rc = set_error(ESF_ERR_CUDA, "cudaFuncSetAttribute(stem_tband) failed: %s", cudaGetErrorString(e));
+          }
+        if (rc == ESF_OK && slot) *slot = 1;
       }
     }
   }

@@ -546,7 +546,7 @@ class Plan:
         # kT > 1: the time taps are folded into N and the input frames stream past a resident M tile (csrc/esf_igemm.cu,
         # "temporal-band stem"); ESF_STEM_TBAND=0 keeps the banded stem for A/B runs
         twb = rt.stem_tband_wb(W, Cin, cout, kt, kh, kw, stride[2], padding[2]) \
-            if os.environ.get("ESF_STEM_TBAND", "0") != "0" else 0
+            if os.environ.get("ESF_STEM_TBAND", "1") != "0" else 0
         if twb:
             wb, bt = pack_stem_tband(w_folded, bias, twb, stride[2], self.device, self.adt)
             rt.check(L.esf_stem_tband_create(xp.data_ptr(), B, Cin, T, H, W, pitch, wb.data_ptr(), bt.data_ptr(), cout,
