@@ -7,9 +7,9 @@ mkdir -p $O
 export ESF_NVCC_EXTRA="${EXTRA:-}"
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1 || { tail -5 $O/build.log; exit 1; }
 [ "${TESTS:-1}" = 1 ] && timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "stem" > $O/pytest.log 2>&1; echo "pytest rc $?"; tail -15 $O/pytest.log
-for cfg in "0 1 8 64" "1 0 8 64" "1 1 8 64"; do
+for cfg in "1 22 8 64" "1 150 8 64"; do
 set -- $cfg; tb=$1
-BATCH=$4 ESF_STEM_TBAND=$1 ESF_STEM_TBAND_SHIFT=$2 ESF_STEM_TBAND_STAGES=$3 timeout 300 python - <<PY
+BATCH=$4 ESF_STEM_TBAND=$1 ESF_STEM_TBAND_DBG=$2 ESF_STEM_TBAND_STAGES=$3 timeout 300 python - <<PY
 import torch
 from efficient_slowfast_b200.engine import Plan
 g = torch.Generator().manual_seed(0)
@@ -34,7 +34,7 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record()
 for _ in range(20): f()
 e1.record(); torch.cuda.synchronize()
-print("tband=$tb shift=$2 stages=$3 B=$4 %s: %.3f ms" % (plan.meta[-1]["label"], e0.elapsed_time(e1) / 20), "checksum %.6f" % y.float().abs().mean().item())
+print("tband=$tb dbg=$2 stages=$3 B=$4 %s: %.3f ms" % (plan.meta[-1]["label"], e0.elapsed_time(e1) / 20), "checksum %.6f" % y.float().abs().mean().item())
 PY
 done | tee $O/stem_ab.txt
 if [ "${BENCH:-0}" = 1 ]; then ESF_STEM_TBAND=1 timeout 900 python bench.py --steps 10 --warmup 3 --no-extra-configs > $O/bench.json 2> $O/bench.err; echo "bench rc $?"; fi
