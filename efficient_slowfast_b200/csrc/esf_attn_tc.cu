@@ -1320,6 +1320,8 @@ static int attn_tc_create_impl(const void* packed, const void* v_lo, int32_t B, 
     }
   }
   p.nsteps1 = n1, p.nsteps2 = n2;
+  if (const char* env = getenv("ESF_ATTN_QK_STEPS_DBG"))   // timing experiment only (drops logit correction terms)
+    if (atoi(env) > 0) p.nsteps2 = std::min(p.nsteps2, atoi(env));
   p.q_tile_bytes = 128 * g.KQ * 2;
   p.k_tile_bytes = kTcBN * g.KQ * 2;
   p.v_tile_bytes = g.DVp * 128;
