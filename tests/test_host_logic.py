@@ -172,6 +172,20 @@ def test_pack_stem_tband_is_the_convolution(esf_lib, cin, cout, k, s, WB, T):
     assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4)
 
 
+def test_stem_tband_planner(esf_lib):
+    """esf_stem_tband_wb (pure host code): which stems take the temporal-band kernel.  The fast pathway's 5x7x7 3->8 and
+    its grey-scale form do (WB = 4: N = 5 x 32 <= 256, 16 TMEM slots); kT = 1 stems, wide stems and odd widths do not."""
+    wb = rt.stem_tband_wb
+    assert wb(224, 3, 8, 5, 7, 7, 2, 3) == 4
+    assert wb(224, 1, 8, 5, 7, 7, 2, 3) == 4
+    assert wb(64, 3, 16, 3, 7, 7, 2, 3) == 4          # 64-column slots, 8 of them
+    assert wb(224, 3, 64, 1, 7, 7, 2, 3) == 0          # no time taps: the banded stem
+    assert wb(224, 3, 64, 5, 7, 7, 2, 3) == 0          # kT x WB x Cout > 256 columns for every block width
+    assert wb(224, 3, 24, 3, 3, 3, 2, 1) == 0          # WB x Cout not a power-of-two slot width
+    assert wb(220, 3, 8, 5, 7, 7, 2, 3) in (0, 2)      # 110 output columns: not a multiple of 4
+    assert wb(0, 3, 8, 5, 7, 7, 2, 3) == 0
+
+
 def test_wfold_block_planner():
     def views(B, T, H, W, cin, cout, slice_out=False):
         x = torch.empty(B, T, H, W, cin)
