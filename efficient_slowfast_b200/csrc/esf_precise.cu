@@ -63,20 +63,23 @@ struct PostParams {
   int worder;   // 0: activation planes [hi | lo | hi];  1: weight-operand planes [hi | hi | lo] (per-clip "weights")
 };
 
-template <int VEC>
+// IDX: unsigned when the element count fits 32 bits (every shape of the zoo), long long otherwise -- the four 64-bit
+// divisions of the index decomposition were ~500 instructions per 8 elements and bound the pass, not HBM (the same
+// finding as for the 16-bit helper kernels)
+template <int VEC, typename IDX>
 __global__ void __launch_bounds__(256) p32_post_kernel(const PostParams p) {
-  const int groups = (p.acc.C + VEC - 1) / VEC;
-  const long long total = (long long)p.acc.B * p.acc.T * p.acc.H * p.acc.W * groups;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
+  const IDX groups = (IDX)((p.acc.C + VEC - 1) / VEC);
+  const IDX total = (IDX)p.acc.B * (IDX)p.acc.T * (IDX)p.acc.H * (IDX)p.acc.W * groups;
+  const IDX W_ = (IDX)p.acc.W, H_ = (IDX)p.acc.H, T_ = (IDX)p.acc.T;
+  for (IDX idx = (IDX)blockIdx.x * (IDX)blockDim.x + threadIdx.x; idx < total; idx += (IDX)gridDim.x * (IDX)blockDim.x) {
     const int g = (int)(idx % groups);
-    long long pos = idx / groups;
-    const int w = (int)(pos % p.acc.W);
-    pos /= p.acc.W;
-    const int h = (int)(pos % p.acc.H);
-    pos /= p.acc.H;
-    const int t = (int)(pos % p.acc.T);
-    const int b = (int)(pos / p.acc.T);
+    IDX pos = idx / groups;
+    const int w = (int)(pos % W_);
+    pos /= W_;
+    const int h = (int)(pos % H_);
+    pos /= H_;
+    const int t = (int)(pos % T_);
+    const int b = (int)(pos / T_);
     const int c0 = g * VEC;
     float v[VEC];
     const float* a = reinterpret_cast<const float*>(p.acc.ptr) + off32(p.acc, b, t, h, w) + c0;
@@ -146,18 +149,19 @@ struct Pool32Params {
   V32 x, y;
   int kT, kH, kW, sT, sH, sW, pT, pH, pW, is_avg;
 };
+template <typename IDX>
 __global__ void __launch_bounds__(256) p32_pool_kernel(const Pool32Params p) {
-  const long long total = (long long)p.y.B * p.y.T * p.y.H * p.y.W * p.y.C;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % p.y.C);
-    long long pos = idx / p.y.C;
-    const int w = (int)(pos % p.y.W);
-    pos /= p.y.W;
-    const int h = (int)(pos % p.y.H);
-    pos /= p.y.H;
-    const int t = (int)(pos % p.y.T);
-    const int b = (int)(pos / p.y.T);
+  const IDX C_ = (IDX)p.y.C, W_ = (IDX)p.y.W, H_ = (IDX)p.y.H, T_ = (IDX)p.y.T;
+  const IDX total = (IDX)p.y.B * T_ * H_ * W_ * C_;
+  for (IDX idx = (IDX)blockIdx.x * (IDX)blockDim.x + threadIdx.x; idx < total; idx += (IDX)gridDim.x * (IDX)blockDim.x) {
+    const int c = (int)(idx % C_);
+    IDX pos = idx / C_;
+    const int w = (int)(pos % W_);
+    pos /= W_;
+    const int h = (int)(pos % H_);
+    pos /= H_;
+    const int t = (int)(pos % T_);
+    const int b = (int)(pos / T_);
     float m = p.is_avg ? 0.f : -CUDART_INF_F;
     for (int kt = 0; kt < p.kT; ++kt) {
       const int ti = t * p.sT + kt - p.pT;
@@ -193,20 +197,20 @@ struct Eca32Params {
 __global__ void __launch_bounds__(256) p32_eca_partial_kernel(const Eca32Params p) {
   __shared__ float red[256];
   const int C = p.x.C, b = blockIdx.y, chunk = blockIdx.x;
-  const int To = p.x.T / p.alpha;
-  const long long npos = (long long)To * p.x.H * p.x.W;
-  const long long per = (npos + kEcaChunks - 1) / kEcaChunks;
-  const long long p0 = chunk * per, p1 = min(npos, p0 + per);
+  const int To = p.x.T / p.alpha, W = p.x.W, H = p.x.H;
+  const int npos = To * H * W;               // positions of one clip: 32-bit (checked on the host)
+  const int per = (npos + kEcaChunks - 1) / kEcaChunks;
+  const int p0 = chunk * per, p1 = min(npos, p0 + per);
   const int lanes = 256 / C;                 // C divides 256 (checked on the host)
   const int c = threadIdx.x % C, pl = threadIdx.x / C;
+  const float* xb = reinterpret_cast<const float*>(p.x.ptr) + b * p.x.sB + c;
   float s = 0.f;
-  for (long long q = p0 + pl; q < p1; q += lanes) {
-    const int w = (int)(q % p.x.W);
-    const long long r = q / p.x.W;
-    const int h = (int)(r % p.x.H), t = (int)(r / p.x.H);
+  for (int q = p0 + pl; q < p1; q += lanes) {
+    const int w = q % W, r = q / W;
+    const int h = r % H, t = r / H;
+    const float* xp = xb + (long long)t * p.alpha * p.x.sT + h * p.x.sH + w * p.x.sW;
     float m = -CUDART_INF_F;
-    for (int a = 0; a < p.alpha; ++a)
-      m = fmaxf(m, reinterpret_cast<const float*>(p.x.ptr)[off32(p.x, b, t * p.alpha + a, h, w) + c]);
+    for (int a = 0; a < p.alpha; ++a) m = fmaxf(m, xp[a * p.x.sT]);
     s += m;
   }
   red[threadIdx.x] = s;
@@ -217,48 +221,71 @@ __global__ void __launch_bounds__(256) p32_eca_partial_kernel(const Eca32Params 
     p.partial[((long long)b * kEcaChunks + chunk) * C + c] = tot;
   }
 }
+// grid (chunks, B): the channel gate of the block's clip is computed once per block (first version: per element, 64 x k
+// loads of the partial sums each), then the block walks its share of the clip's positions with 32-bit indices
 __global__ void __launch_bounds__(256) p32_eca_apply_kernel(const Eca32Params p) {
-  const int C = p.x.C;
-  const int To = p.x.T / p.alpha;
+  __shared__ float mean_sh[256], gate_sh[256];
+  const int C = p.x.C, b = blockIdx.y;
+  const int To = p.x.T / p.alpha, W = p.x.W, H = p.x.H;
   const float inv = 1.f / ((float)To * p.x.H * p.x.W);
-  const long long total = (long long)p.x.B * To * p.x.H * p.x.W * C;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C);
-    long long pos = idx / C;
-    const int w = (int)(pos % p.x.W);
-    pos /= p.x.W;
-    const int h = (int)(pos % p.x.H);
-    pos /= p.x.H;
-    const int t = (int)(pos % To);
-    const int b = (int)(pos / To);
+  if (threadIdx.x < C) {
+    float mean = 0.f;
+    for (int ch = 0; ch < kEcaChunks; ++ch) mean += p.partial[((long long)b * kEcaChunks + ch) * C + threadIdx.x];
+    mean_sh[threadIdx.x] = mean;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
     float z = 0.f;
     for (int j = 0; j < p.k; ++j) {
       const int cc = c + j - (p.k - 1) / 2;
       if (cc < 0 || cc >= C) continue;
-      float mean = 0.f;
-      for (int ch = 0; ch < kEcaChunks; ++ch) mean += p.partial[((long long)b * kEcaChunks + ch) * C + cc];
-      z = fmaf(__ldg(p.w + j), mean * inv, z);
+      z = fmaf(__ldg(p.w + j), mean_sh[cc] * inv, z);
     }
-    const float gate = 1.f / (1.f + expf(-z));
+    gate_sh[c] = 1.f / (1.f + expf(-z));
+  }
+  __syncthreads();
+  const int npos = To * H * W;
+  const int per = (npos + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(npos, p0 + per);
+  const int lanes = 256 / C;
+  const int c = threadIdx.x % C, pl = threadIdx.x / C;
+  const float gate = gate_sh[c], sc = __ldg(p.bn_scale + c), sh = __ldg(p.bn_shift + c);
+  const float* xb = reinterpret_cast<const float*>(p.x.ptr) + b * p.x.sB + c;
+  float* yb = reinterpret_cast<float*>(p.y.ptr) + b * p.y.sB + c;
+  for (int q = p0 + pl; q < p1; q += lanes) {
+    const int w = q % W, r = q / W;
+    const int h = r % H, t = r / H;
+    const float* xp = xb + (long long)t * p.alpha * p.x.sT + h * p.x.sH + w * p.x.sW;
     float m = -CUDART_INF_F;
-    for (int a = 0; a < p.alpha; ++a)
-      m = fmaxf(m, reinterpret_cast<const float*>(p.x.ptr)[off32(p.x, b, t * p.alpha + a, h, w) + c]);
-    const float v = fmaf(m * gate, __ldg(p.bn_scale + c), __ldg(p.bn_shift + c));
-    reinterpret_cast<float*>(p.y.ptr)[off32(p.y, b, t, h, w) + c] = fmaxf(v, 0.f);
+    for (int a = 0; a < p.alpha; ++a) m = fmaxf(m, xp[a * p.x.sT]);
+    yb[t * p.y.sT + h * p.y.sH + w * p.y.sW] = fmaxf(fmaf(m * gate, sc, sh), 0.f);
   }
 }
 
 // ------------------------------------------------------------------------------------------- head pool (FP32)
 // feat[b][off + c] = mean over (t, h, w) of x[b, t, h, w, c]; one block per (clip, 256-channel group), fixed order
+// block = 32 channels x 8 position lanes (first version: one thread per channel walking every position of the clip --
+// 16 .. 128 blocks in all); the eight partial sums of a channel are added in a fixed order
 __global__ void __launch_bounds__(256) p32_head_pool_kernel(const V32 x, float* __restrict__ feat, int feat_stride, int off) {
-  const int b = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= x.C) return;
+  __shared__ float red[256];
+  const int b = blockIdx.y, cl = threadIdx.x & 31, lane = threadIdx.x >> 5, c = blockIdx.x * 32 + cl;
+  const int HW = x.H * x.W, npos = x.T * HW;
   float s = 0.f;
-  for (int t = 0; t < x.T; ++t)
-    for (int h = 0; h < x.H; ++h)
-      for (int w = 0; w < x.W; ++w) s += reinterpret_cast<const float*>(x.ptr)[off32(x, b, t, h, w) + c];
-  feat[(long long)b * feat_stride + off + c] = s / ((float)x.T * x.H * x.W);
+  if (c < x.C) {
+    const float* xb = reinterpret_cast<const float*>(x.ptr) + b * x.sB + c;
+    for (int q = lane; q < npos; q += 8) {
+      const int t = q / HW, r = q - t * HW, h = r / x.W, w = r - h * x.W;
+      s += xb[t * x.sT + h * x.sH + w * x.sW];
+    }
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (lane == 0 && c < x.C) {
+    float tot = 0.f;
+    for (int l = 0; l < 8; ++l) tot += red[l * 32 + cl];
+    feat[(long long)b * feat_stride + off + c] = tot / ((float)x.T * x.H * x.W);
+  }
 }
 
 // ------------------------------------------------------------------------------------------- position attention (FP32)
@@ -436,8 +463,11 @@ extern "C" int esf_p32_post(const esf_view* acc, const float* scale, const float
   const bool v8 = vec8_ok(acc, 4) && (!p.res.ptr || vec8_ok(res, 4)) && (!p.y32.ptr || vec8_ok(y32, 4)) &&
                   (!p.y3.ptr || (vec8_ok(y3, 2) && plane % 8 == 0));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (v8) p32_post_kernel<8><<<p32_grid(pos * (acc->C / 8), 256), 256, 0, s>>>(p);
-  else p32_post_kernel<1><<<p32_grid(pos * acc->C, 256), 256, 0, s>>>(p);
+  const bool small = pos * acc->C < 0x7fffffffLL - 148LL * 32 * 256;     // the grid-stride index stays below 2^31
+  if (v8 && small) p32_post_kernel<8, unsigned><<<p32_grid(pos * (acc->C / 8), 256), 256, 0, s>>>(p);
+  else if (v8) p32_post_kernel<8, long long><<<p32_grid(pos * (acc->C / 8), 256), 256, 0, s>>>(p);
+  else if (small) p32_post_kernel<1, unsigned><<<p32_grid(pos * acc->C, 256), 256, 0, s>>>(p);
+  else p32_post_kernel<1, long long><<<p32_grid(pos * acc->C, 256), 256, 0, s>>>(p);
   return check_launch("p32_post_kernel");
 }
 
@@ -463,8 +493,11 @@ extern "C" int esf_p32_post3(const esf_view* acc, const esf_view* acc2, const es
   const bool v8 = vec8_ok(acc, 4) && vec8_ok(acc2, 4) && vec8_ok(acc3, 4) && (!p.y32.ptr || vec8_ok(y32, 4)) &&
                   (!p.y3.ptr || (vec8_ok(y3, 2) && plane % 8 == 0));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (v8) p32_post_kernel<8><<<p32_grid(pos * (acc->C / 8), 256), 256, 0, s>>>(p);
-  else p32_post_kernel<1><<<p32_grid(pos * acc->C, 256), 256, 0, s>>>(p);
+  const bool small = pos * acc->C < 0x7fffffffLL - 148LL * 32 * 256;     // the grid-stride index stays below 2^31
+  if (v8 && small) p32_post_kernel<8, unsigned><<<p32_grid(pos * (acc->C / 8), 256), 256, 0, s>>>(p);
+  else if (v8) p32_post_kernel<8, long long><<<p32_grid(pos * (acc->C / 8), 256), 256, 0, s>>>(p);
+  else if (small) p32_post_kernel<1, unsigned><<<p32_grid(pos * acc->C, 256), 256, 0, s>>>(p);
+  else p32_post_kernel<1, long long><<<p32_grid(pos * acc->C, 256), 256, 0, s>>>(p);
   return check_launch("p32_post_kernel");
 }
 
@@ -478,7 +511,10 @@ extern "C" int esf_p32_pool3d(const esf_view* x, const esf_view* y, int32_t kT, 
   p.x = to_v32(x), p.y = to_v32(y);
   p.kT = kT, p.kH = kH, p.kW = kW, p.sT = sT, p.sH = sH, p.sW = sW, p.pT = pT, p.pH = pH, p.pW = pW, p.is_avg = is_avg;
   const long long total = (long long)y->B * y->T * y->H * y->W * y->C;
-  p32_pool_kernel<<<p32_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  if (total < 0x7fffffffLL - 148LL * 32 * 256)
+    p32_pool_kernel<unsigned><<<p32_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    p32_pool_kernel<long long><<<p32_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("p32_pool_kernel");
 }
 
@@ -493,6 +529,7 @@ extern "C" int esf_p32_eca_fuse(const esf_view* x_fast, int32_t alpha, const flo
                     y->W == x_fast->W && y->C == x_fast->C && y->B == x_fast->B,
                 "esf_p32_eca_fuse: shapes do not match");
   ESF_CHECK_ARG(x_fast->C <= 256 && 256 % x_fast->C == 0, "esf_p32_eca_fuse: C = %d must divide 256", x_fast->C);
+  ESF_CHECK_ARG((long long)x_fast->T * x_fast->H * x_fast->W < 0x7fffffffLL, "esf_p32_eca_fuse: clip too large");
   Eca32Params p;
   p.x = to_v32(x_fast), p.y = to_v32(y);
   p.alpha = alpha, p.k = eca_k, p.w = eca_w, p.bn_scale = bn_scale, p.bn_shift = bn_shift, p.partial = partial;
@@ -500,14 +537,15 @@ extern "C" int esf_p32_eca_fuse(const esf_view* x_fast, int32_t alpha, const flo
   p32_eca_partial_kernel<<<dim3(kEcaChunks, x_fast->B), 256, 0, s>>>(p);
   int rc = check_launch("p32_eca_partial_kernel");
   if (rc) return rc;
-  const long long total = (long long)y->B * y->T * y->H * y->W * y->C;
-  p32_eca_apply_kernel<<<p32_grid(total, 256), 256, 0, s>>>(p);
+  const long long npos = (long long)y->T * y->H * y->W;
+  const int chunks = (int)std::max(1LL, std::min(npos * y->C / 4096, 592LL / std::max(1, y->B) + 1));   // ~4 blocks per SM in all
+  p32_eca_apply_kernel<<<dim3(chunks, y->B), 256, 0, s>>>(p);
   return check_launch("p32_eca_apply_kernel");
 }
 
 extern "C" int esf_p32_head_pool(const esf_view* x, float* feat, int32_t feat_stride, int32_t feat_off, void* stream) {
   ESF_CHECK_ARG(f32_view_ok(x) && feat && feat_stride >= feat_off + x->C, "esf_p32_head_pool: bad argument");
-  p32_head_pool_kernel<<<dim3((x->C + 255) / 256, x->B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  p32_head_pool_kernel<<<dim3((x->C + 31) / 32, x->B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       to_v32(x), feat, feat_stride, feat_off);
   return check_launch("p32_head_pool_kernel");
 }
