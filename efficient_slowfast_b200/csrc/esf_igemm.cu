@@ -1127,6 +1127,7 @@ struct __align__(64) StemTbParams {
   uint32_t a_bytes, b_tile_bytes;
   const float* bias;   // [NB] tiled (i, co)
   int act, f16;
+  int out_f32;        // FP32 output (one of the three split products of the FP32-accurate plan): y counts floats
   __nv_bfloat16* y;
   long long ysB, ysT, ysH;
   int num_tiles;
@@ -1322,8 +1323,11 @@ __global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_
       const int cb = tile % p.ncb, m = tile / p.ncb;
       const int ho = (m % p.th) * p.bh + r % p.bh, b = (m / p.th) * p.bb + r / p.bh;
       const bool valid = r < p.rows && ho < p.Ho && b < p.B;
-      __nv_bfloat16* yrow = p.y + b * p.ysB + ho * p.ysH + (long long)cb * NB;
-      for (int t = 0; t < To; ++t, yrow += ysT) {
+      const long long yoff = b * p.ysB + ho * p.ysH + (long long)cb * NB;
+      __nv_bfloat16* yrow = p.y + yoff;
+      float* yrow32 = reinterpret_cast<float*>(p.y) + yoff;
+      const bool out_f32 = p.out_f32 != 0;
+      for (int t = 0; t < To; ++t, yrow += ysT, yrow32 += ysT) {
         const int s = t & smask;
         mbar_wait(&acc_full[s], (full_bits >> s) & 1, 55);
         full_bits ^= 1u << s;
@@ -1332,7 +1336,15 @@ __global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_
           for (int c0 = 0; c0 < NB; c0 += 16) {
             float v[16];
             tmem_ld16(lane_addr + s * NB + c0, v);
-            if (valid) {
+            if (valid && out_f32) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 bv = *reinterpret_cast<const float4*>(bias_sh + c0 + 4 * i);
+                *reinterpret_cast<float4*>(yrow32 + c0 + 4 * i) =
+                    make_float4(apply_act(v[4 * i] + bv.x, act), apply_act(v[4 * i + 1] + bv.y, act),
+                                apply_act(v[4 * i + 2] + bv.z, act), apply_act(v[4 * i + 3] + bv.w, act));
+              }
+            } else if (valid) {
               uint32_t pk[8];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {       // the bias vector comes from shared memory, four columns per load
@@ -1428,7 +1440,7 @@ extern "C" int esf_stem_tband_create(const void* xp, int32_t B, int32_t Cin, int
                                      int32_t kT, int32_t kH, int32_t kW, int32_t sH, int32_t sW, int32_t pT, int32_t pH,
                                      int32_t pW, int32_t act, const esf_view* y, esf_op** out) {
   ESF_CHECK_ARG(xp && w_band && bias_tiled && view_ok(y) && out, "esf_stem_tband_create: null/bad argument");
-  ESF_CHECK_ARG(is16(y->dtype), "esf_stem_tband_create: output must be BF16 or F16");
+  ESF_CHECK_ARG(is16(y->dtype) || y->dtype == ESF_F32, "esf_stem_tband_create: output must be BF16, F16 or F32");
   ESF_CHECK_ARG(pT >= 0 && pT < kT && sH >= 1 && sH <= 8, "esf_stem_tband_create: bad temporal padding / H stride");
   int pt_expected = 0, lpad = 0, win8 = 0;
   int rc = esf_stem_geometry(W, Cin, kW, sW, pW, &pt_expected, &lpad, &win8);
@@ -1441,8 +1453,9 @@ extern "C" int esf_stem_tband_create(const void* xp, int32_t B, int32_t Cin, int
                 "esf_stem_tband_create: output must be a dense (B,%d,%d,%d,%d) channels-last tensor", To, Ho, Wo, Cout);
   const int WB = stem_tband_wb(Cin, Cout, kT, kH, kW, sW, Wo);
   if (WB == 0) return set_error(ESF_ERR_UNSUPPORTED, "temporal-band stem does not apply to this geometry");
-  ESF_CHECK_ARG((reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && (y->sH * 2) % 16 == 0 && (y->sT * 2) % 16 == 0 &&
-                    (y->sB * 2) % 16 == 0, "esf_stem_tband_create: output rows must be 16-byte aligned");
+  const int oes = y->dtype == ESF_F32 ? 4 : 2;
+  ESF_CHECK_ARG((reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && (y->sH * oes) % 16 == 0 && (y->sT * oes) % 16 == 0 &&
+                    (y->sB * oes) % 16 == 0, "esf_stem_tband_create: output rows must be 16-byte aligned");
 
   StemTbOp* op = new (std::nothrow) StemTbOp();
   if (!op) return set_error(ESF_ERR_ARG, "out of host memory");
@@ -1469,7 +1482,8 @@ extern "C" int esf_stem_tband_create(const void* xp, int32_t B, int32_t Cin, int
   }
   p.num_tiles = (int)ntiles;
   p.a_bytes = p.rows * 128, p.b_tile_bytes = kT * p.NB * 128;
-  p.bias = bias_tiled, p.act = act, p.f16 = y->dtype == ESF_F16;
+  // an FP32 output view: raw accumulators of one of the three split products of the FP32-accurate plan (FP16 operands)
+  p.bias = bias_tiled, p.act = act, p.f16 = y->dtype == ESF_F16 || y->dtype == ESF_F32, p.out_f32 = y->dtype == ESF_F32;
   p.y = static_cast<__nv_bfloat16*>(y->ptr), p.ysB = y->sB, p.ysT = y->sT, p.ysH = y->sH;
   p.stages = std::min(kTbMaxStages, (kSmemLimit - 1024 - 2048 - (int)(kH * p.b_tile_bytes)) / kAStageBytes);
   op->smem_bytes = 1024 + 2048 + kH * p.b_tile_bytes + p.stages * kAStageBytes;   // alignment slack, barriers + bias

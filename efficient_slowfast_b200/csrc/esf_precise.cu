@@ -149,12 +149,13 @@ struct Pool32Params {
   V32 x, y;
   int kT, kH, kW, sT, sH, sW, pT, pH, pW, is_avg;
 };
-template <typename IDX>
+// VEC = 4: one thread = four consecutive channels of one output position (16-byte loads and stores)
+template <typename IDX, int VEC>
 __global__ void __launch_bounds__(256) p32_pool_kernel(const Pool32Params p) {
-  const IDX C_ = (IDX)p.y.C, W_ = (IDX)p.y.W, H_ = (IDX)p.y.H, T_ = (IDX)p.y.T;
+  const IDX C_ = (IDX)(p.y.C / VEC), W_ = (IDX)p.y.W, H_ = (IDX)p.y.H, T_ = (IDX)p.y.T;
   const IDX total = (IDX)p.y.B * T_ * H_ * W_ * C_;
   for (IDX idx = (IDX)blockIdx.x * (IDX)blockDim.x + threadIdx.x; idx < total; idx += (IDX)gridDim.x * (IDX)blockDim.x) {
-    const int c = (int)(idx % C_);
+    const int c = (int)(idx % C_) * VEC;
     IDX pos = idx / C_;
     const int w = (int)(pos % W_);
     pos /= W_;
@@ -162,7 +163,9 @@ __global__ void __launch_bounds__(256) p32_pool_kernel(const Pool32Params p) {
     pos /= H_;
     const int t = (int)(pos % T_);
     const int b = (int)(pos / T_);
-    float m = p.is_avg ? 0.f : -CUDART_INF_F;
+    float m[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) m[j] = p.is_avg ? 0.f : -CUDART_INF_F;
     for (int kt = 0; kt < p.kT; ++kt) {
       const int ti = t * p.sT + kt - p.pT;
       if (ti < 0 || ti >= p.x.T) continue;
@@ -172,13 +175,26 @@ __global__ void __launch_bounds__(256) p32_pool_kernel(const Pool32Params p) {
         for (int kw = 0; kw < p.kW; ++kw) {
           const int wi = w * p.sW + kw - p.pW;
           if (wi < 0 || wi >= p.x.W) continue;
-          const float v = reinterpret_cast<const float*>(p.x.ptr)[off32(p.x, b, ti, hi, wi) + c];
-          m = p.is_avg ? m + v : fmaxf(m, v);
+          const float* xp = reinterpret_cast<const float*>(p.x.ptr) + off32(p.x, b, ti, hi, wi) + c;
+          float v[VEC];
+          if constexpr (VEC == 4) {
+            const float4 q = *reinterpret_cast<const float4*>(xp);
+            v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+          } else {
+            v[0] = xp[0];
+          }
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) m[j] = p.is_avg ? m[j] + v[j] : fmaxf(m[j], v[j]);
         }
       }
     }
-    if (p.is_avg) m /= (float)(p.kT * p.kH * p.kW);   // count_include_pad = True, as nn.AvgPool3d
-    reinterpret_cast<float*>(p.y.ptr)[off32(p.y, b, t, h, w) + c] = m;
+    if (p.is_avg) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) m[j] /= (float)(p.kT * p.kH * p.kW);   // count_include_pad = True, as nn.AvgPool3d
+    }
+    float* yp = reinterpret_cast<float*>(p.y.ptr) + off32(p.y, b, t, h, w) + c;
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(yp) = make_float4(m[0], m[1], m[2], m[3]);
+    else yp[0] = m[0];
   }
 }
 
@@ -511,10 +527,19 @@ extern "C" int esf_p32_pool3d(const esf_view* x, const esf_view* y, int32_t kT, 
   p.x = to_v32(x), p.y = to_v32(y);
   p.kT = kT, p.kH = kH, p.kW = kW, p.sT = sT, p.sH = sH, p.sW = sW, p.pT = pT, p.pH = pH, p.pW = pW, p.is_avg = is_avg;
   const long long total = (long long)y->B * y->T * y->H * y->W * y->C;
-  if (total < 0x7fffffffLL - 148LL * 32 * 256)
-    p32_pool_kernel<unsigned><<<p32_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  else
-    p32_pool_kernel<long long><<<p32_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  auto al16 = [](const esf_view* v) {
+    return (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0 && v->C % 4 == 0 && v->sW % 4 == 0 && v->sH % 4 == 0 &&
+           v->sT % 4 == 0 && v->sB % 4 == 0;
+  };
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool small = total < 0x7fffffffLL - 148LL * 32 * 256;
+  if (al16(x) && al16(y)) {
+    if (small) p32_pool_kernel<unsigned, 4><<<p32_grid(total / 4, 256), 256, 0, st>>>(p);
+    else p32_pool_kernel<long long, 4><<<p32_grid(total / 4, 256), 256, 0, st>>>(p);
+  } else {
+    if (small) p32_pool_kernel<unsigned, 1><<<p32_grid(total, 256), 256, 0, st>>>(p);
+    else p32_pool_kernel<long long, 1><<<p32_grid(total, 256), 256, 0, st>>>(p);
+  }
   return check_launch("p32_pool_kernel");
 }
 

@@ -19,6 +19,7 @@ Scope: the two ResNet-50 two-stream models and the single-pathway ResNet (C2D / 
 tensor-core work and ~5x the activation bytes of the FP16 plan: an accuracy mode, benchmarked beside it.
 """
 import ctypes
+import os
 
 import torch
 
@@ -138,7 +139,7 @@ class PrecisePlan(Plan):
         allows: the clip is packed twice (hi and lo halves), the band weight is split like any other weight, and the
         three products hi.hi, lo.hi, hi.lo are three launches of the same GEMM with FP32 outputs (its tap table cannot
         hold 3 x kT x kH taps), summed, un-scaled, biased and activated by esf_p32_post3.  Else the FP32 CUDA-core stem."""
-        from .engine import pack_stem_band
+        from .engine import pack_stem_band, pack_stem_tband
         B, Cin, T, H, W = x_nc.shape
         cout = w_folded.shape[0]
         kt, kh, kw = w_folded.shape[2:]
@@ -160,18 +161,25 @@ class PrecisePlan(Plan):
                       "stem_pack", "lo" if part else "hi", nbytes=self._nbytes(x_nc, xp), eager=True)
             xps.append(xp)
         m = y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3]
+        # kT > 1: the temporal-band kernel (Plan.stem), one launch per split product as well
+        twb = rt.stem_tband_wb(W, Cin, cout, kt, kh, kw, stride[2], padding[2]) \
+            if os.environ.get("ESF_STEM_TBAND", "1") != "0" else 0
         for name, xp, wpart in (("hi.hi", xps[0], hi), ("lo.hi", xps[1], hi), ("hi.lo", xps[0], lo)):
-            wb, bt = pack_stem_band(wpart, zero, stride[2], self.device, torch.float16)
+            if twb:
+                wb, bt = pack_stem_tband(wpart, zero, twb, stride[2], self.device, torch.float16)
+            else:
+                wb, bt = pack_stem_band(wpart, zero, stride[2], self.device, torch.float16)
+            create = L.esf_stem_tband_create if twb else L.esf_stem_igemm_create
             acc = torch.empty(tuple(y.shape), dtype=torch.float32, device=self.device)
             self.keep += [wb, bt, acc]
             yv = rt.view(acc)
             h = ctypes.c_void_p()
-            rt.check(L.esf_stem_igemm_create(xp.data_ptr(), B, Cin, T, H, W, pitch, wb.data_ptr(), bt.data_ptr(), cout,
-                                             kt, kh, kw, stride[1], stride[2], padding[0], padding[1], padding[2],
-                                             rt.ACT_NONE, ctypes.byref(yv), ctypes.byref(h)), "esf_stem_igemm_create")
+            rt.check(create(xp.data_ptr(), B, Cin, T, H, W, pitch, wb.data_ptr(), bt.data_ptr(), cout,
+                            kt, kh, kw, stride[1], stride[2], padding[0], padding[1], padding[2],
+                            rt.ACT_NONE, ctypes.byref(yv), ctypes.byref(h)), "stem GEMM create")
             self.handles.append(h)
             self._add(lambda s, h=h: rt.check(L.esf_op_launch(h, s), "esf_op_launch"), "stem_igemm",
-                      "%dx%dx%d %d->%d banded %s" % (kt, kh, kw, Cin, cout, name),
+                      "%dx%dx%d %d->%d %s %s" % (kt, kh, kw, Cin, cout, "t-band" if twb else "banded", name),
                       flops=2.0 * m * cout * Cin * kt * kh * kw, nbytes=self._nbytes(xp, acc) + wb.numel() * 2)
             accs.append(acc)
         sc, bs = self.tensor(inv_scale), self.tensor(bias)

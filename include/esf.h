@@ -151,7 +151,7 @@ int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int32_t T, int
  * input frames stream past an M tile that stays on its SM (output frames accumulate in a ring of TMEM slots).
  * esf_stem_tband_wb: width WB of the output-column block for this geometry, 0 when the kernel does not apply (kT = 1,
  * window or N too large).  w_band: 16-bit [kT*WB*Cout][kH*64], bias_tiled: FP32 [WB*Cout] (engine.pack_stem_tband).
- * 16-bit dense output only. */
+ * Dense output, 16-bit or FP32 (raw accumulators of a split product of the FP32-accurate plan). */
 int esf_stem_tband_wb(int32_t W, int32_t Cin, int32_t Cout, int32_t kT, int32_t kH, int32_t kW, int32_t sW, int32_t pW);
 int esf_stem_tband_create(const void* xp, int32_t B, int32_t Cin, int32_t T, int32_t H, int32_t W, int32_t pitch,
                           const void* w_band, const float* bias_tiled, int32_t Cout, int32_t kT, int32_t kH,
