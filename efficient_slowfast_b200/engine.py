@@ -183,7 +183,8 @@ class Plan:
         self.attn_impl = "tcgen05"   # "tcgen05" (TMEM, two-pass) or "mma_sync" (register-resident, online softmax)
 
     # ---------------------------------------------------------------- memory
-    def act(self, B, T, H, W, C, name=None, dtype=None):
+    def act(self, B, T, H, W, C, name=None, dtype=None, role=None):
+        """role: a hint for the FP32-accurate plan (engine_fp32.PrecisePlan.act); 16-bit activations have one form."""
         dtype = dtype or self.adt
         # 16-bit activations with C >= 8 get a channel pitch that is a multiple of 8 elements (16 bytes), so that every
         # buffer -- also with C = 27, 36, 180, 540 ... of the efficient backbones -- is addressable by TMA and by

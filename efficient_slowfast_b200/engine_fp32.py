@@ -32,9 +32,13 @@ class Act32:
     (B,T,H,W,3*plane) it is mirrored into at channel offset `c0` of every plane.  Supports the `[..., a:b]` channel
     slicing the model code uses for concat buffers."""
 
-    def __init__(self, f32, x3, plane, c0, c_total, weight_order=False):
+    def __init__(self, f32, x3, plane, c0, c_total, weight_order=False, has_f32=True, has_planes=True):
         self.f32, self.x3, self.plane, self.c0, self.c_total = f32, x3, plane, c0, c_total
         self.weight_order = weight_order    # planes [hi | hi | lo]: the tensor is the WEIGHT operand of a per-clip GEMM
+        # an intermediate that is only ever a GEMM operand keeps no FP32 copy (f32 is a shape-only meta tensor), one that
+        # is only ever a residual keeps no planes (PrecisePlan.act(role=...)): 4 resp. 6 bytes per element the post-pass
+        # does not write
+        self.has_f32, self.has_planes = has_f32, has_planes
 
     @property
     def shape(self):
@@ -52,7 +56,12 @@ class Act32:
         assert isinstance(idx, tuple) and len(idx) == 2 and idx[0] is Ellipsis and isinstance(idx[1], slice)
         start, stop, step = idx[1].indices(self.f32.shape[4])
         assert step == 1
-        return Act32(self.f32[..., start:stop], self.x3, self.plane, self.c0 + start, self.c_total, self.weight_order)
+        return Act32(self.f32[..., start:stop], self.x3, self.plane, self.c0 + start, self.c_total, self.weight_order,
+                     self.has_f32, self.has_planes)
+
+    def need_f32(self, who):
+        assert self.has_f32, "%s reads the FP32 copy of an activation that was planned without one" % who
+        return self.f32
 
 
 def split_weight_rows(w):
@@ -76,27 +85,32 @@ class PrecisePlan(Plan):
         self.precise = True
 
     # ---------------------------------------------------------------- memory
-    def act(self, B, T, H, W, C, name=None, dtype=None):
+    def act(self, B, T, H, W, C, name=None, dtype=None, role=None):
+        """role "operand": the tensor is only read as a GEMM operand (planes, no FP32 copy); "residual": only as a
+        residual (FP32, no planes); None: both."""
         if dtype is not None and dtype != self.adt:
             return super().act(B, T, H, W, C, name=name, dtype=dtype)
+        assert role in (None, "operand", "residual") and not (name and role)
         plane = (C + 7) // 8 * 8
-        f32 = torch.empty((B, T, H, W, C), dtype=torch.float32, device=self.device)
+        has_f32, has_planes = role != "operand", role != "residual"
+        f32 = torch.empty((B, T, H, W, C), dtype=torch.float32, device=self.device if has_f32 else "meta")
         # zero-filled: the row padding [C, plane) of every plane meets zero weights in the GEMM and must stay finite
-        x3 = torch.zeros((B, T, H, W, 3 * plane), dtype=torch.float16, device=self.device)
+        x3 = torch.zeros((B, T, H, W, 3 * plane), dtype=torch.float16, device=self.device) if has_planes else None
         self.keep += [f32, x3]
         if name:
             self.buffers[name] = f32
-        return Act32(f32, x3, plane, 0, C)
+        return Act32(f32, x3, plane, 0, C, has_f32=has_f32, has_planes=has_planes)
 
     def _post(self, acc, y, scale=None, bias=None, res=None, act=rt.ACT_NONE, label=""):
         """esf_p32_post: y.f32 = act(acc * scale + bias + res) and its three FP16 planes (y: Act32 or FP32 tensor)."""
         L = rt.lib()
         av = rt.view(acc)
-        rv = rt.view(res.f32 if isinstance(res, Act32) else res) if res is not None else rt.null_view()
+        rv = rt.view(res.need_f32("a residual add") if isinstance(res, Act32) else res) if res is not None else rt.null_view()
         if isinstance(y, Act32):
-            y32 = rt.null_view() if y.f32.data_ptr() == acc.data_ptr() and scale is None and bias is None and \
-                res is None and act == rt.ACT_NONE else rt.view(y.f32)
-            y3, plane = rt.view(y.hi), y.plane
+            in_place = y.has_f32 and y.f32.data_ptr() == acc.data_ptr() and scale is None and bias is None and \
+                res is None and act == rt.ACT_NONE
+            y32 = rt.null_view() if (in_place or not y.has_f32) else rt.view(y.f32)
+            y3, plane = (rt.view(y.hi) if y.has_planes else rt.null_view()), y.plane
             worder = int(y.weight_order)
         else:
             y32, y3, plane, worder = rt.view(y), rt.null_view(), 0, 0
@@ -117,6 +131,7 @@ class PrecisePlan(Plan):
         if groups != 1:
             raise NotImplementedError("grouped convolutions are not part of the FP32-accurate plan (R50 models only)")
         assert isinstance(x, Act32) and not x.weight_order
+        assert x.has_planes, "a convolution reads the planes of an activation that was planned without them"
         w = w_folded.to(torch.float64)
         cout, cin = w.shape[:2]
         assert cin == x.shape[4]

@@ -655,10 +655,10 @@ class _TwoStreamResNet(_PlannedModel):
         ci = t.a.out_channels
         s1 = t.a.stride[1]
         Ha, Wa = (H - 1) // s1 + 1, (W - 1) // s1 + 1   # Tx1x1 conv, stride (1,s1,s1), no spatial padding
-        ta = plan.act(B, T, Ha, Wa, ci)
-        tb = plan.act(B, T, Ho, Wo, ci)
+        ta = plan.act(B, T, Ha, Wa, ci, role="operand")      # read by the next convolution only
+        tb = plan.act(B, T, Ho, Wo, ci, role="operand")
         if hasattr(blk, "branch1"):
-            sc = plan.act(B, T, Ho, Wo, co)
+            sc = plan.act(B, T, Ho, Wo, co, role="residual")  # read by conv c's residual add only
             w, b = fold_conv_bn(blk.branch1.weight, None, blk.branch1_bn)
             plan.conv(x, sc, w, b, stride=tuple(blk.branch1.stride))
         else:
