@@ -1104,6 +1104,8 @@ extern "C" int esf_stem_igemm_create(const void* xp, int32_t B, int32_t Cin, int
 // MMA of input frame g, tap kh, k-step ks:  D[slot(t_lo) ..][128 x cnt*NB] += A_g,kh[128 x 16] . Wb_kh[u_lo*NB ..]^T
 // with t = g + pT - kT + 1 + u, weights of time tap kt = kT - 1 - u; split where the slot ring wraps and where a slot
 // is written for the first time (accumulate flag off).
+namespace esf {
+
 constexpr int kTbThreads = 6 * 32;   // TMA producer, MMA issuer, 4 epilogue warps (one per TMEM lane quarter)
 constexpr int kTbMaxKH = 8;
 constexpr int kTbMaxStages = 8;
@@ -1401,6 +1403,8 @@ static StemTbKernel stem_tband_fn(int ksteps, bool f16) {
     default: return stem_tband_kernel<4, true>;
   }
 }
+
+}  // namespace esf
 
 struct StemTbOp : esf_op {
   StemTbParams params;

@@ -89,3 +89,8 @@ def test_hot_kernels_keep_their_resource_budget(esf_lib):
         assert int(u["REG"]) == 96 and int(u["LOCAL"]) == 0, u
     ig = [u for n, u in usage.items() if "igemm_kernel" in n]
     assert ig and all(int(u["REG"]) <= 104 and int(u["LOCAL"]) == 0 for u in ig), ig
+    # the temporal-band stem's issuing warp is a serial instruction stream: no local memory, and only the production
+    # instantiations (no timing variants) in the shipped library
+    tb = {n: u for n, u in usage.items() if "stem_tband_kernel" in n}
+    assert len(tb) == 8 and all(n.endswith("ELi0EEEvNS_12StemTbParamsE") for n in tb), sorted(tb)
+    assert all(int(u["LOCAL"]) == 0 for u in tb.values()), tb
