@@ -2,7 +2,7 @@
 # round 2 evidence run (one B200): round-end sequence as the driver runs it + FP32 plan + ncu launch list
 set -u
 cd "$(dirname "$0")/../.."
-O=gpurun_out/r2_s27
+O=gpurun_out/r2_s32
 mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1 || { tail -5 $O/build.log; exit 1; }
 timeout 1500 python -m pytest tests/ -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc $?"; tail -3 $O/pytest_gpu.log
