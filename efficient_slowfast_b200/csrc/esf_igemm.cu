@@ -1110,7 +1110,7 @@ constexpr int kTbThreads = 6 * 32;   // TMA producer, MMA issuer, 4 epilogue war
 constexpr int kTbMaxKH = 8;
 constexpr int kTbMaxStages = 8;
 // Timing experiments are compile-time instantiations (template parameter DBG; bits: 1 no MMAs, 2 no tile loads, 4 no
-// epilogue work, 16 every MMA N = NB, 32 one k-step per tap (wrong results)), built only with ESF_NVCC_EXTRA=-DESF_TB_DBG_VARIANTS and
+// epilogue work, 16 every MMA N = NB, 32 one k-step per tap (wrong results), 64 two MMA issuers), built only with ESF_NVCC_EXTRA=-DESF_TB_DBG_VARIANTS and
 // selected by ESF_STEM_TBAND_DBG.  Run-time switches in these loops are not free.
 
 struct __align__(64) StemTbParams {
@@ -1143,7 +1143,7 @@ struct __align__(64) StemTbParams {
   }
 
 template <int KSTEPS, bool F16, int ESF_TB_DBG = 0>
-__global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_constant__ StemTbParams p) {
+__global__ void __launch_bounds__(kTbThreads + 32, 1) stem_tband_kernel(const __grid_constant__ StemTbParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem;
@@ -1154,7 +1154,8 @@ __global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_
   uint64_t* acc_full = a_empty + kTbMaxStages;   // [nslots <= 32]
   uint64_t* acc_free = acc_full + 32;
   uint64_t* b_full = acc_free + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  uint64_t* tok = b_full + 1;          // [2] (timing variant 64: two MMA issuers pass a token)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 2);
   float* bias_sh = reinterpret_cast<float*>(bars) + 256;   // [NB <= 64], 1 KB into the 2 KB barrier / bias area
 
   const int warp = uniform_warp_idx();
@@ -1171,6 +1172,8 @@ __global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_
       mbar_init(&acc_free[s], 4);
     }
     mbar_init(b_full, 1);
+    mbar_init(&tok[0], 1);
+    mbar_init(&tok[1], 1);
     fence_barrier_init();
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + p.NB) bias_sh[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
@@ -1219,6 +1222,79 @@ __global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_
             phase ^= 1;
           }
         }
+    }
+  } else if ((ESF_TB_DBG & 64) && (warp == 1 || warp == 6)) {
+    // ------------------------------------------------------------------ timing variant: TWO MMA issuers, alternate taps
+    // The token fixes the global issue order (tap n before tap n + 1), so the accumulation order stays deterministic;
+    // the question is whether the ~50-cycle start-up of an MMA is hidden when consecutive taps come from two threads.
+    const int me = warp == 1 ? 0 : 1;
+    const uint32_t idesc0 = make_idesc_16(128, 0, F16);
+    const uint32_t desc_hi = kmajor_desc_hi(1024, 2);
+    const uint32_t a_lo0 = kmajor_desc_lo(smem_u32(smem_a)), b_lo0 = kmajor_desc_lo(smem_u32(smem_b));
+    const uint32_t b_kh_step = p.b_tile_bytes >> 4, b_u_step = (uint32_t)(p.NB * 128) >> 4;
+    const int kT = p.kT, kH = p.kH, pT = p.pT, T = p.T, To = p.To, NB = p.NB, nslots = p.nslots;
+    const int stages = p.stages, num_tiles = p.num_tiles, back = kT - 1 - pT;
+    mbar_wait(b_full, 0, 52);
+    tc_fence_after();
+    int stage = 0, n = 0;
+    uint32_t phase = 0, free_bits = 0, uses = 0, a_rel = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const uint32_t a_base = a_lo0 + (((tile % p.ncb) & p.odd_shift) ? 1u : 0u);
+      for (int g = 0; g < T; ++g) {
+        const int t_base = g + pT - kT + 1;
+        const int t_lo = max(t_base, 0), t_hi = min(g + pT, To - 1);
+        const int new_lo = g == 0 ? 0 : g + pT;
+        for (int t = max(new_lo, t_lo); t <= t_hi; ++t) {
+          const int s = t & smask;
+          mbar_wait(&acc_free[s], ((free_bits >> s) & 1) ^ 1, 53);
+          free_bits ^= 1u << s;
+        }
+        tc_fence_after();
+        auto seg_d = [&](int a) { return tmem_base + (uint32_t)((a & smask) * NB); };
+        auto seg_b = [&](int a) { return (uint32_t)(a - t_base) * b_u_step; };
+        auto seg_i = [&](int c) { return idesc0 | ((uint32_t)((c * NB) >> 3) << 17); };
+        const int cnt = t_hi - t_lo + 1;
+        const int c0 = min(cnt, nslots - (t_lo & smask)), c1 = cnt - c0;
+        const uint32_t sd0 = seg_d(t_lo), sb0 = seg_b(t_lo), si0 = seg_i(c0);
+        const uint32_t sb1 = seg_b(t_lo + c0), si1 = seg_i(c1);
+        const int old_cnt = max(min(new_lo - 1, t_hi) - t_lo + 1, 0);
+        const int o0 = min(old_cnt, c0), o1 = old_cnt - o0;
+        const int nw_lo = max(new_lo, t_lo), nw_cnt = t_hi - nw_lo + 1;
+        const uint32_t oi0 = seg_i(o0), oi1 = seg_i(o1);
+        const uint32_t nd = seg_d(nw_lo), nb = seg_b(nw_lo), ni = seg_i(nw_cnt);
+        const int done_lo = max(g == T - 1 ? t_lo : g - back, 0), done_hi = g == T - 1 ? t_hi : g - back;
+        for (int kh = 0; kh < kH; ++kh, ++n) {
+          if ((n & 1) == me) {
+            const uint32_t a_lo = a_base + a_rel;
+            const uint32_t b0 = b_lo0 + sb0 + kh * b_kh_step, b1 = b_lo0 + sb1 + kh * b_kh_step;
+            mbar_wait(&a_full[stage], phase, 54);
+            mbar_wait(&tok[me], (uses & 1) ^ (me ? 0u : 1u), 56);     // my turn: the other issuer has issued tap n - 1
+            ++uses;
+            tc_fence_after();
+            if (elect_one()) {
+              if (!(ESF_TB_DBG & 1)) {
+                if (kh == 0) {
+                  if (o0 > 0) umma_bf16_lohi(sd0, a_lo, desc_hi, b0, desc_hi, oi0, 1);
+                  if (o1 > 0) umma_bf16_lohi(tmem_base, a_lo, desc_hi, b1, desc_hi, oi1, 1);
+                  if (nw_cnt > 0) umma_bf16_lohi(nd, a_lo, desc_hi, b_lo0 + nb, desc_hi, ni, 0);
+                } else {
+                  ESF_TB_KSTEP(0)
+                }
+                if (KSTEPS > 1) ESF_TB_KSTEP(1)
+                if (KSTEPS > 2) ESF_TB_KSTEP(2)
+                if (KSTEPS > 3) ESF_TB_KSTEP(3)
+              }
+              mbar_arrive(&tok[me ^ 1]);
+              umma_commit(&a_empty[stage]);
+              if (kh == kH - 1)
+                for (int t = done_lo; t <= done_hi; ++t) umma_commit(&acc_full[t & smask]);
+            }
+            __syncwarp();
+          }
+          a_rel += kAStageBytes >> 4;
+          if (++stage == stages) stage = 0, phase ^= 1, a_rel = 0;
+        }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -1313,7 +1389,7 @@ __global__ void __launch_bounds__(kTbThreads, 1) stem_tband_kernel(const __grid_
         }
       }
     }
-  } else {
+  } else if (warp >= 2 && warp <= 5) {
     // ------------------------------------------------------------------ epilogue: one warp per TMEM lane quarter
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
@@ -1388,6 +1464,8 @@ static StemTbKernel stem_tband_fn(int ksteps, bool f16) {
       case 7: return stem_tband_kernel<3, true, 7>;
       case 22: return stem_tband_kernel<3, true, 22>;
       case 38: return stem_tband_kernel<3, true, 38>;
+      case 64: return stem_tband_kernel<3, true, 64>;
+      case 70: return stem_tband_kernel<3, true, 70>;
       default: break;
     }
   }
@@ -1411,7 +1489,12 @@ struct StemTbOp : esf_op {
   int grid = 0;
   int smem_bytes = 0;
   int launch(cudaStream_t stream) override {
-    stem_tband_fn(params.ksteps, params.f16 != 0)<<<grid, kTbThreads, smem_bytes, stream>>>(params);
+    int threads = kTbThreads;
+#ifdef ESF_TB_DBG_VARIANTS
+    if (const char* env = getenv("ESF_STEM_TBAND_DBG"))
+      if (atoi(env) & 64) threads += 32;     // the second MMA issuer of the timing variant
+#endif
+    stem_tband_fn(params.ksteps, params.f16 != 0)<<<grid, threads, smem_bytes, stream>>>(params);
     return check_launch("stem_tband_kernel");
   }
 };

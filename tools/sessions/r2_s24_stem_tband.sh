@@ -7,7 +7,7 @@ mkdir -p $O
 export ESF_NVCC_EXTRA="${EXTRA:-}"
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1 || { tail -5 $O/build.log; exit 1; }
 [ "${TESTS:-1}" = 1 ] && timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "stem" > $O/pytest.log 2>&1; echo "pytest rc $?"; tail -15 $O/pytest.log
-for cfg in "1 22 8 64" "1 150 8 64"; do
+for cfg in "1 0 8 64" "1 64 8 64" "1 6 8 64" "1 70 8 64"; do
 set -- $cfg; tb=$1
 BATCH=$4 ESF_STEM_TBAND=$1 ESF_STEM_TBAND_DBG=$2 ESF_STEM_TBAND_STAGES=$3 timeout 300 python - <<PY
 import torch
