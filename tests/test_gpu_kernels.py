@@ -442,6 +442,39 @@ def test_stem_temporal_band(esf_lib, B, cin, T, size, kt, cout, precision, monke
     assert torch.equal(_to_ncdhw(y.cpu()), got)
 
 
+def test_stem_temporal_band_random_geometries(esf_lib, monkeypatch):
+    """Seeded sweep over clip sizes the fixed cases do not hit: odd frame counts around the slot ring (15 .. 18, 33),
+    batches that do not fill the 8-clip box, heights that leave a ragged last row tile, padded / unpadded time."""
+    import random
+    monkeypatch.setenv("ESF_STEM_TBAND", "1")
+    rnd = random.Random(7)
+    done = 0
+    for _ in range(40):
+        B, T = rnd.choice([1, 2, 3, 5, 9]), rnd.choice([3, 7, 15, 16, 17, 18, 33])
+        H, W = rnd.choice([40, 56, 72, 104]), rnd.choice([32, 64, 96])
+        cin, cout, kt = rnd.choice([1, 3]), rnd.choice([4, 8, 16]), rnd.choice([3, 5])
+        pt = rnd.choice([kt // 2, 0]) if T >= kt else kt // 2
+        if rt.stem_tband_wb(W, cin, cout, kt, 7, 7, 2, 3) == 0 or B * T * H * W > 3_000_000:
+            continue
+        g = torch.Generator().manual_seed(done)
+        x = torch.randn(B, cin, T, H, W, generator=g)
+        w = torch.randn(cout, cin, kt, 7, 7, generator=g) * 0.1
+        bias = torch.randn(cout, generator=g) * 0.1
+        ref = F.conv3d(x.half().float(), w.half().float(), bias, (1, 2, 2), (pt, 3, 3)).relu()
+        y = torch.full(_to_ndhwc(ref).shape, 7.0, dtype=torch.float16, device=DEV)
+        plan = Plan(DEV, "fp16")
+        plan.stem(x.to(DEV), y, w.double(), bias.double(), (1, 2, 2), (pt, 3, 3))
+        assert plan.meta[-1]["label"].endswith("t-band")
+        plan.launch_all()
+        torch.cuda.synchronize()
+        err = (_to_ncdhw(y.cpu()) - ref).abs().max().item()
+        assert err <= 1e-2 * ref.abs().max().item(), (B, cin, T, H, W, cout, kt, pt, err)
+        done += 1
+        if done == 14:
+            break
+    assert done >= 10
+
+
 def test_stem_temporal_band_matches_banded_stem(esf_lib, monkeypatch):
     """Both tensor-core stems accumulate the same FP16 products in FP32: their outputs may differ only by the order of
     the additions (one 16-bit ulp at most after rounding)."""
