@@ -465,7 +465,13 @@ __device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
 // KNOBS (compile time): the round-2 experiment paths (second P buffer, independent Q.K^T issue).  With the knobs as
 // run-time flags the DEFAULT path lost 4 - 6 % (88 instead of 96 registers, d = 8: 11.04 -> 11.68 ms, d = 32: 12.23 ->
 // 12.68 ms at batch 64 on one box, tools/sessions/r2_s18_attn_regress.sh), so they are a separate instantiation.
-template <bool F16, int POLY, bool KNOBS>
+// PIPE (compile time, experiment ESF_ATTN_PIPE=1): software-pipelined softmax loop.  The exponentials of tile j + 1 are
+// ISSUED before tile j is packed, stored and handed over, so a warp's hand-over work runs while its own MUFU
+// instructions are in flight (default loop: exps -> wait for them -> hand-over -> next tile; with the four warps of a
+// scheduler in similar phases the MUFU pipe idles ~23 % of the time).  Two tiles of values are live, so the softmax
+// warps take 112 registers from the four control warps with setmaxnreg (32 there: 512 x 112 + 128 x 32 = 640 x 96, the
+// pool the CTA was launched with -- asking for more never returns).
+template <bool F16, int POLY, bool KNOBS, bool PIPE = false>
 __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -531,6 +537,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
 
   if (warp == 16) {
     // ------------------------------------------------------------------ TMA producer
+    if constexpr (PIPE) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * p.q_tile_bytes);
       for (int q = 0; q < 2; ++q) tma_load_3d(Qs + q * p.q_tile_bytes, &p.q_map, q_full, 0, row0 + q * 128, b);
@@ -553,6 +560,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
     }
   } else if (warp == 17) {
     // ------------------------------------------------------------------ Q.K^T issuer (both query tiles)
+    if constexpr (PIPE) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     // Separate from the P.V issuers: with one warp doing both, S_{j+1} could only be issued after that warp had waited
     // for BOTH halves of P_{j-1}, and the softmax warps found it missing on 87 % of the tiles (~200 cycles each).
     const uint32_t idesc_s = make_idesc_16(128, kTcBN, F16);
@@ -657,6 +665,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
     }
   } else if (warp == 18 || warp == 19) {
     // ------------------------------------------------------------------ P.V issuers (one per query tile)
+    if constexpr (PIPE) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     const int q = warp - 18;
     const uint32_t idesc_o = make_idesc_16(128, p.DVp, F16);
     const uint32_t pv_hi = kmajor_desc_hi(1024, 2);
@@ -693,6 +702,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
     }
   } else {
     // ------------------------------------------------------------------ softmax: warp = q * 8 + h * 4 + quarter
+    if constexpr (PIPE) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int q = warp >> 3;
     const int h = (warp >> 2) & 1;
     const int quarter = warp & 3;
@@ -719,6 +729,117 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_tc_v2_kernel(const __grid_
 #else
 #define ESF_TICK(k)
 #endif
+    if constexpr (PIPE) {
+      float w[32];
+      float f = 1.f;
+      bool any_raise = false;
+      // raw scores of tile jj in x -> speculative exponentials in place, running maximum, S buffer released.  `prev`
+      // holds the exponentials of tile jj - 1, which are not stored yet: a raise rescales them too.
+      auto stage1 = [&](float (&x)[32], float (&prev)[32], int jj, bool has_prev) {
+        const int buf = jj & 1;
+        const uint32_t s_addr = lane_addr + (q * 2 + buf) * kTcBN + 32 * h;
+        const bool last_tail = tail && jj == nt - 1;
+        if (last_tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (jj * kTcBN + 32 * h + i >= N) x[i] = -CUDART_INF_F;
+        }
+        float ms = (m == -CUDART_INF_F) ? 0.f : m * kTcLog2e;
+        float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+        const float2 ms2 = make_float2(-ms, -ms), c2 = make_float2(kTcLog2e, kTcLog2e);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmaxf(fmaxf(mx0, x[i]), x[i + 1]);
+          mx1 = fmaxf(fmaxf(mx1, x[i + 2]), x[i + 3]);
+#pragma unroll
+          for (int e = 0; e < 4; e += 2) {
+            const float2 y = __ffma2_rn(make_float2(x[i + e], x[i + e + 1]), c2, ms2);
+            x[i + e] = fast_exp2(y.x);
+            x[i + e + 1] = fast_exp2(y.y);
+          }
+        }
+        const float mx = fmaxf(mx0, mx1);
+        const bool raise = mx > m + kTau;
+        any_raise = __any_sync(0xffffffffu, raise);
+        f = 1.f;
+        if (any_raise) {
+          const float m_new = raise ? mx : m;
+          f = raise ? fast_exp2((m - m_new) * kTcLog2e) : 1.f;
+          const bool big = raise && !((mx - m) * kTcLog2e < 100.f);
+          m = m_new;
+          if (__any_sync(0xffffffffu, big)) {
+            tmem_ld32_nowait(s_addr, x);
+            tmem_wait_ld();
+            tmem_ld32_acquire(x);
+            if (last_tail) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (jj * kTcBN + 32 * h + i >= N) x[i] = -CUDART_INF_F;
+            }
+            ms = (m == -CUDART_INF_F) ? 0.f : m * kTcLog2e;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = fast_exp2(fmaf(x[i], kTcLog2e, -ms));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] *= f;
+          }
+          if (has_prev) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) prev[i] *= f;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[q * 2 + buf]);
+      };
+      // exponentials of tile jj in x -> P in TMEM, handed to the P.V issuer; O is brought to the maximum P was scaled to
+      auto stage2 = [&](float (&x)[32], int jj, bool rescale) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack16x2(x[2 * i], x[2 * i + 1], F16);
+        mbar_wait(&p_free[q * 2 + h], (jj & 1) ^ 1, 38);   // P.V of tile jj - 1 has consumed the buffer (and left O alone)
+        tc_fence_after();
+        if (jj > 0 && rescale) {
+          for (int c0 = 0; c0 < p.DVp; c0 += 16) {
+            float o[16];
+            tmem_ld16(o_addr + c0, o);
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) o[k2] *= f;
+            tmem_st16(o_addr + c0, o);
+          }
+        }
+        tmem_st16_b32(p_addr0, pk);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[q * 2 + h]);
+      };
+      auto fetch = [&](float (&x)[32], int jj) {
+        mbar_wait(&s_full[q * 2 + (jj & 1)], (jj >> 1) & 1, 37);
+        tc_fence_after();
+        tmem_ld32_nowait(lane_addr + (q * 2 + (jj & 1)) * kTcBN + 32 * h, x);
+        tmem_wait_ld();
+        tmem_ld32_acquire(x);
+      };
+      stage1(v, w, 0, false);
+      for (int j = 0; j < nt; j += 2) {
+        bool rs = false;
+        if (j + 1 < nt) {
+          fetch(w, j + 1);
+          stage1(w, v, j + 1, true);
+          rs = any_raise;
+        }
+        stage2(v, j, rs);
+        if (j + 1 >= nt) break;
+        rs = false;
+        if (j + 2 < nt) {
+          fetch(v, j + 2);
+          stage1(v, w, j + 2, true);
+          rs = any_raise;
+        }
+        stage2(w, j + 1, rs);
+      }
+    } else
     for (int j = 0; j < nt; ++j) {
       const int buf = j & 1;
       const uint32_t s_addr = lane_addr + (q * 2 + buf) * kTcBN + 32 * h;
@@ -1112,11 +1233,17 @@ struct AttnTcOp : esf_op {
   int smem_bytes = 0;
   int v2 = 0;
   int poly = 0;   // pairs of every 8 whose exponential runs on the FMA pipe (v2 only)
+  int pipe = 0;   // software-pipelined softmax loop (experiment, ESF_ATTN_PIPE=1)
   int launch(cudaStream_t stream) override {
     if (v2) {
 #define ESF_V2_LAUNCH(PL)                                                                                   \
   if (params.f16) attn_tc_v2_kernel<true, PL, false><<<grid, kV2Threads, smem_bytes, stream>>>(params);      \
   else attn_tc_v2_kernel<false, PL, false><<<grid, kV2Threads, smem_bytes, stream>>>(params);
+      if (pipe) {
+        if (params.f16) attn_tc_v2_kernel<true, 0, false, true><<<grid, kV2Threads, smem_bytes, stream>>>(params);
+        else attn_tc_v2_kernel<false, 0, false, true><<<grid, kV2Threads, smem_bytes, stream>>>(params);
+        return check_launch("attn_tc_v2_kernel");
+      }
       if (params.pdbl || params.qk_async) {   // experiment build of the default (MUFU-only) loop
         if (params.f16) attn_tc_v2_kernel<true, 0, true><<<grid, kV2Threads, smem_bytes, stream>>>(params);
         else attn_tc_v2_kernel<false, 0, true><<<grid, kV2Threads, smem_bytes, stream>>>(params);
@@ -1346,6 +1473,11 @@ static int attn_tc_create_impl(const void* packed, const void* v_lo, int32_t B, 
     p.qk_async = (e && atoi(e) == 1) ? 1 : 0;
   }
   {
+    const char* e = getenv("ESF_ATTN_PIPE");
+    op->pipe = (op->v2 && e && atoi(e) == 1) ? 1 : 0;
+    if (op->pipe) p.pdbl = p.qk_async = 0;
+  }
+  {
     const char* e = getenv("ESF_ATTN_POLY");   // experiment knob; default chosen from measurements (see header)
     op->poly = e ? atoi(e) : kV2DefaultPoly;
     if (op->poly < 0 || op->poly > 4) op->poly = 0;
@@ -1376,6 +1508,10 @@ static int attn_tc_create_impl(const void* packed, const void* v_lo, int32_t B, 
       cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_tc_v2_kernel<true, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_tc_v2_kernel<false, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(attn_tc_v2_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
       if (e == cudaSuccess)

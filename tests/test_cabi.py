@@ -83,7 +83,7 @@ def test_hot_kernels_keep_their_resource_budget(esf_lib):
             name = line[len("Function "):].rstrip(":")
         elif line.startswith("REG:") and name:
             usage[name] = dict(kv.split(":") for kv in line.split() if ":" in kv and not kv.startswith("CONSTANT"))
-    v2 = [u for n, u in usage.items() if "attn_tc_v2_kernelILb1ELi0ELb0E" in n or "attn_tc_v2_kernelILb0ELi0ELb0E" in n]
+    v2 = [u for n, u in usage.items() if "attn_tc_v2_kernelILb1ELi0ELb0ELb0E" in n or "attn_tc_v2_kernelILb0ELi0ELb0ELb0E" in n]
     assert len(v2) == 2, sorted(usage)[:5]
     for u in v2:          # 640 threads per CTA cap the kernel at 102 registers; the tuned loop uses 96
         assert int(u["REG"]) == 96 and int(u["LOCAL"]) == 0, u
