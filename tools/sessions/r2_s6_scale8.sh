@@ -2,7 +2,7 @@
 # round 2: 8-GPU weak scaling of the headline bench, e2e from FP32 host clips (slow-from-fast upload, H2D ceiling in the line)
 set -u
 cd "$(dirname "$0")/../.."
-O=gpurun_out/r2_s28
+O=gpurun_out/r2_s37
 mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1 || { tail -5 $O/build.log; exit 1; }
 ls /sys/devices/system/node/ | tr '\n' ' '; echo; nvidia-smi topo -m 2>/dev/null | head -14
